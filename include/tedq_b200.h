@@ -1,0 +1,226 @@
+/*
+ * tedq_b200.h — C ABI of the B200-native execution engine behind TeD-Q's
+ * `Circuit.compilecircuit(backend="pytorch_b200")`.
+ *
+ * The reference (jd-opensource/TeD-Q) is pure Python: there is no native
+ * interface to mirror, so every entry point below cites the *Python* interface
+ * it replaces (file:line under the reference tree).  Plain C types only: no
+ * torch types, no C++ types, no exceptions cross this boundary.  The caller
+ * owns every device buffer it passes in; kernels are enqueued on the caller's
+ * stream and never synchronise it (the *_host entry points are the exception:
+ * they take HOST buffers, copy, run and synchronise — they are the "call a
+ * user makes" for end-to-end timing).
+ *
+ * Conventions (reference: tedq/backends/pytorch_backend.py:513-522, :567-577)
+ *   - state psi is a C-contiguous [2]*n tensor: qubit q <-> tensor axis q, i.e.
+ *     qubit 0 is the MOST significant bit of the flat amplitude index;
+ *   - a k-qubit gate matrix is row-major (2^k x 2^k), row = output index,
+ *     column = input index, gate qubit 0 = most significant bit of both;
+ *   - complex numbers are interleaved (re, im); TQ_C64 = 2 x float,
+ *     TQ_C128 = 2 x double.  Parameters / real outputs use the matching real
+ *     type (float for TQ_C64, double for TQ_C128).
+ *
+ * All functions returning int return 0 on success and a negative TQ_E_* code
+ * on failure; tq_last_error() gives the message (thread-local).
+ */
+#ifndef TEDQ_B200_H
+#define TEDQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_ABI_VERSION 1
+#define TQ_MAX_GATE_QUBITS 3  /* reference gate set tops out at CSWAP/Toffoli (qubit.py:838-960) */
+#define TQ_MAX_GATE_PARAMS 3  /* Rot (qubit.py:1137-1190) */
+#define TQ_MAX_MEAS_QUBITS 64
+#define TQ_MAX_OBS_QUBITS 4   /* dense observable matrix up to 16x16 */
+
+enum tq_status {
+  TQ_OK = 0,
+  TQ_E_INVALID = -1,   /* bad argument / malformed plan input            */
+  TQ_E_UNSUPPORTED = -2,
+  TQ_E_CUDA = -3,      /* a CUDA runtime call failed                     */
+  TQ_E_WORKSPACE = -4, /* workspace too small                            */
+  TQ_E_NOMEM = -5
+};
+
+enum tq_dtype { TQ_C64 = 0, TQ_C128 = 1 };
+
+/* Gate kinds.  TQ_G_FIXED carries a constant matrix (what the reference does for
+ * every gate with no trainable slot: compiled_circuit.py:432-435,
+ * pytorch_backend.py:567-577).  The parametrised kinds are evaluated on the
+ * device from theta exactly as pytorch_backend.py:866-1188 does on the host. */
+enum tq_gate_kind {
+  TQ_G_FIXED = 0,
+  TQ_G_RX = 1,         /* pytorch_backend.py:866-894   */
+  TQ_G_RY = 2,         /* :897-922                     */
+  TQ_G_RZ = 3,         /* :925-954                     */
+  TQ_G_ROT = 4,        /* :957-984                     */
+  TQ_G_PHASESHIFT = 5, /* :987-1013                    */
+  TQ_G_CPHASE = 6,     /* :1016-1054                   */
+  TQ_G_CRX = 7,        /* :1057-1100                   */
+  TQ_G_CRY = 8,        /* :1103-1146                   */
+  TQ_G_CRZ = 9         /* :1149-1188                   */
+};
+
+typedef struct tq_gate_desc {
+  int32_t kind;                           /* enum tq_gate_kind                                  */
+  int32_t nq;                             /* 1..TQ_MAX_GATE_QUBITS                              */
+  int32_t qubits[4];                      /* qubits[0] = most significant bit of the matrix idx */
+  int32_t param_idx[TQ_MAX_GATE_PARAMS];  /* index into the flat parameter vector, -1 = const   */
+  int32_t _pad;
+  double param_const[TQ_MAX_GATE_PARAMS]; /* value used when param_idx[i] < 0                   */
+  int64_t matrix_off;                     /* TQ_G_FIXED: offset (in complex entries) into pool  */
+} tq_gate_desc;
+
+enum tq_meas_kind {
+  TQ_M_EXPVAL = 0, /* pytorch_backend.py:399-459 */
+  TQ_M_PROBS = 1,  /* :461-472                   */
+  TQ_M_STATE = 2   /* :495-496                   */
+};
+
+#define TQ_MF_ZSTRING 1 /* EXPVAL of a product of PauliZ on `qubits` (any nq) */
+
+typedef struct tq_meas_desc {
+  int32_t kind;  /* enum tq_meas_kind */
+  int32_t flags; /* TQ_MF_*           */
+  int32_t nq;    /* EXPVAL: observable qubits; PROBS: kept qubits (0 = all); STATE: 0 */
+  int32_t _pad;
+  int32_t qubits[TQ_MAX_MEAS_QUBITS];
+  int64_t matrix_off; /* EXPVAL without ZSTRING: 2^nq x 2^nq matrix in pool (nq <= TQ_MAX_OBS_QUBITS) */
+} tq_meas_desc;
+
+typedef struct tq_plan_opts {
+  int32_t max_local_qubits_fwd; /* 0 = default. log2(amplitudes of one shared-memory tile), forward  */
+  int32_t max_local_qubits_bwd; /* 0 = default. same for the adjoint sweep (holds psi and lambda)    */
+  int32_t coalesce_bits;        /* -1 = default. low amplitude-index bits always kept tile-local     */
+  int32_t threads;              /* 0 = default CTA size                                              */
+  int32_t fuse;                 /* -1 = default (1). 1: fuse runs of gates in registers               */
+  int32_t reserved[3];
+} tq_plan_opts;
+
+typedef struct tq_plan tq_plan; /* opaque, immutable after creation */
+
+/* ---- library ----------------------------------------------------------- */
+int tq_abi_version(void);
+const char* tq_last_error(void);
+
+/* ---- plan (replaces CompiledCircuit.__init__ state-vector planning,
+ *      compiled_circuit.py:82-202, and the per-call _parser_circuit :418-440) */
+int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_desc* meas, int32_t n_meas,
+                   const double* pool /* complex interleaved */, int64_t pool_complex_len, int32_t n_qubits,
+                   int32_t n_params, int32_t dtype, const double* init_state /* nullable, 2^n complex */,
+                   const tq_plan_opts* opts /* nullable */, tq_plan** out);
+void tq_plan_destroy(tq_plan* plan);
+
+/* introspection (scheduling is part of the contract the tests pin) */
+int32_t tq_plan_num_qubits(const tq_plan* plan);
+int32_t tq_plan_num_params(const tq_plan* plan);
+int32_t tq_plan_num_sweeps(const tq_plan* plan, int32_t backward);
+/* local amplitude-index bit positions of sweep s; returns count, writes up to cap entries */
+int32_t tq_plan_sweep_bits(const tq_plan* plan, int32_t backward, int32_t s, int32_t* bits, int32_t cap);
+int32_t tq_plan_sweep_num_gates(const tq_plan* plan, int32_t backward, int32_t s);
+/* number of REAL scalars one parameter set produces (all measurements, stacked) */
+int64_t tq_plan_out_reals(const tq_plan* plan);
+/* algorithmic HBM bytes one forward / backward evaluation moves (sweeps x read+write of psi [and lambda]) */
+int64_t tq_plan_hbm_bytes(const tq_plan* plan, int32_t backward);
+int64_t tq_plan_launches(const tq_plan* plan, int32_t backward);
+
+/* ---- execution (replaces PyTorchBackend.execute state-vector branch,
+ *      pytorch_backend.py:358-391 + get_measurement_results :393-498;
+ *      backward replaces autograd through that loop) -------- */
+size_t tq_workspace_bytes(const tq_plan* plan, int64_t batch, int32_t with_backward);
+
+/* params: device [batch, n_params] real. out: device [batch, out_reals] real.
+ * workspace: device, >= tq_workspace_bytes(plan, batch, with_backward); after a
+ * forward with with_backward != 0 it holds what tq_backward needs. */
+int tq_forward(const tq_plan* plan, const void* params, int64_t batch, void* out, void* workspace,
+               size_t workspace_bytes, int32_t with_backward, void* cuda_stream);
+
+/* grad_out: device [batch, out_reals] real (torch convention: for a complex
+ * STATE output the cotangent is (dL/dRe, dL/dIm) interleaved).
+ * grad_params: device [batch, n_params] real, overwritten. */
+int tq_backward(const tq_plan* plan, const void* params, int64_t batch, const void* grad_out,
+                void* grad_params, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* final state of the last tq_forward (device pointer inside workspace, [batch, 2^n] complex), or NULL
+ * when the state never left shared memory */
+void* tq_workspace_state(const tq_plan* plan, void* workspace, int64_t batch);
+
+/* HOST-buffer entry point: H2D(params[, grad_out]) -> forward [-> backward] -> D2H(out[, grad_params]),
+ * synchronises.  grad_out / grad_params may both be NULL (forward only).  Device scratch is owned by the
+ * plan and reused between calls (this one call is therefore NOT re-entrant on one plan). */
+int tq_execute_host(tq_plan* plan, const void* params, int64_t batch, void* out, const void* grad_out,
+                    void* grad_params);
+
+/* ---- state-vector plan integers (bit-exact mirror of compiled_circuit.py:126-202) */
+/* gate_pos[k] and perm[n_qubits] for one gate; returns 0 */
+int tq_sv_axes_perm(int32_t n_qubits, const int32_t* qubits, int32_t nq, int32_t* gate_pos, int32_t* perm);
+
+/* ---- tensor-network side (replaces gen_tensor_networks index maps,
+ *      tensor_network.py:850-1099, and the third-party tree.contract call sites
+ *      pytorch_backend.py:276,:339 / oe_wrapper.py:59-65) -------------------- */
+
+/* Index maps.  gate_nq[g], gate_qubits[g*4+i]; meas as in tq_plan_create.
+ * For measurement `which` writes, per tensor t, its rank into tensor_rank[t] and
+ * its integer index ids into tensor_idx[t*8 + i] (id -> symbol via tq_tn_symbol).
+ * Returns the number of tensors, or <0. out_idx gets the open indices (count in *n_out). */
+int32_t tq_tn_index_map(int32_t n_qubits, const int32_t* gate_nq, const int32_t* gate_qubits, int32_t n_gates,
+                        const tq_meas_desc* meas, int32_t which, int32_t* tensor_rank, int32_t* tensor_idx,
+                        int32_t tensor_cap, int32_t* out_idx, int32_t* n_out);
+/* unicode code point of symbol i (tensor_network.py:1109-1127) */
+int32_t tq_tn_symbol(int32_t i);
+
+/* One lowered pairwise-contraction step.  All extents are 2, so every tensor is
+ * addressed by a bit-string; a mode permutation is a bit permutation. */
+typedef struct tq_tn_step {
+  int32_t lhs, rhs, out;  /* ssa ids: inputs 0..n_in-1, step s produces n_in+s           */
+  int32_t n_batch, n_m, n_n, n_k; /* log2 of batch / M / N / K extents                   */
+  /* for each output-side role, the bit position (0 = fastest) inside the source tensor:
+   * lhs_bits = [k bits..., m bits..., batch bits...] (fast->slow), same for rhs with n bits;
+   * the output is laid out [n bits, m bits, batch bits] fast->slow. */
+  int8_t lhs_bits[64];
+  int8_t rhs_bits[64];
+  int32_t out_idx[64];    /* index id of each output bit, fast -> slow                   */
+  int32_t out_rank;
+  int32_t conj_lhs, conj_rhs;
+} tq_tn_step;
+
+/* Lower an ssa path (pairs of ssa ids) over `n_in` input tensors into steps.
+ * tensor_idx uses stride 8 as above but slow -> fast order (C order, as the
+ * reference lists them).  sliced[] index ids are dropped from every tensor.
+ * Returns number of steps or <0. */
+int32_t tq_tn_lower(const int32_t* tensor_rank, const int32_t* tensor_idx, int32_t n_in, const int32_t* out_idx,
+                    int32_t n_out, const int32_t* ssa_path /* 2*n_steps */, int32_t n_steps,
+                    const int32_t* sliced, int32_t n_sliced, tq_tn_step* steps);
+
+typedef struct tq_tn_plan tq_tn_plan;
+
+/* Build an executable contraction plan. input_param_dep[t] != 0 marks inputs that differ per parameter set
+ * (they carry a leading batch dimension of `batch` in tq_tn_contract). */
+int tq_tn_plan_create(const int32_t* tensor_rank, const int32_t* tensor_idx, int32_t n_in, const int32_t* out_idx,
+                      int32_t n_out, const int32_t* ssa_path, int32_t n_steps, const int32_t* sliced,
+                      int32_t n_sliced, int32_t dtype, tq_tn_plan** out);
+void tq_tn_plan_destroy(tq_tn_plan* plan);
+int32_t tq_tn_plan_num_steps(const tq_tn_plan* plan);
+int32_t tq_tn_plan_num_slices(const tq_tn_plan* plan);
+double tq_tn_plan_flops(const tq_tn_plan* plan);        /* 8*M*N*K summed over steps, ONE slice */
+int32_t tq_tn_plan_width(const tq_tn_plan* plan);       /* log2 of the largest intermediate     */
+size_t tq_tn_workspace_bytes(const tq_tn_plan* plan);
+int32_t tq_tn_plan_get_step(const tq_tn_plan* plan, int32_t s, tq_tn_step* out);
+
+/* Contract slices [slice_begin, slice_end) and ACCUMULATE their sum into `out`
+ * (device, 2^n_out complex, caller zeroes it).  inputs[t] = device pointer of
+ * input tensor t (C order, complex).  Multi-GPU: each rank takes a slice range
+ * and the caller all-reduces `out` (one NCCL allreduce). */
+int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, int64_t slice_begin, int64_t slice_end,
+                   void* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEDQ_B200_H */

@@ -1,0 +1,238 @@
+"""ctypes binding of include/tedq_b200.h (the C-ABI is the product boundary; torch only lends
+device memory and the current stream).  There is no CPU fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import build as _build
+from .ir import CircuitIR
+
+TQ_C64, TQ_C128 = 0, 1
+MAX_MEAS_QUBITS = 64
+
+
+class GateDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("nq", C.c_int32), ("qubits", C.c_int32 * 4),
+        ("param_idx", C.c_int32 * 3), ("_pad", C.c_int32),
+        ("param_const", C.c_double * 3), ("matrix_off", C.c_int64),
+    ]
+
+
+class MeasDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("flags", C.c_int32), ("nq", C.c_int32), ("_pad", C.c_int32),
+        ("qubits", C.c_int32 * MAX_MEAS_QUBITS), ("matrix_off", C.c_int64),
+    ]
+
+
+class PlanOpts(C.Structure):
+    _fields_ = [
+        ("max_local_qubits_fwd", C.c_int32), ("max_local_qubits_bwd", C.c_int32),
+        ("coalesce_bits", C.c_int32), ("threads", C.c_int32), ("fuse", C.c_int32),
+        ("reserved", C.c_int32 * 3),
+    ]
+
+
+class TnStep(C.Structure):
+    _fields_ = [
+        ("lhs", C.c_int32), ("rhs", C.c_int32), ("out", C.c_int32),
+        ("n_batch", C.c_int32), ("n_m", C.c_int32), ("n_n", C.c_int32), ("n_k", C.c_int32),
+        ("lhs_bits", C.c_int8 * 64), ("rhs_bits", C.c_int8 * 64),
+        ("out_idx", C.c_int32 * 64), ("out_rank", C.c_int32),
+        ("conj_lhs", C.c_int32), ("conj_rhs", C.c_int32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load (building in-tree first if needed) libtedq_b200.so; fail loudly otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build_library()
+    L = C.CDLL(path)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    L.tq_abi_version.restype = i32
+    L.tq_last_error.restype = C.c_char_p
+    L.tq_plan_create.restype = i32
+    L.tq_plan_create.argtypes = [C.POINTER(GateDesc), i32, C.POINTER(MeasDesc), i32, C.POINTER(C.c_double), i64, i32,
+                                 i32, i32, C.POINTER(C.c_double), C.POINTER(PlanOpts), C.POINTER(vp)]
+    L.tq_plan_destroy.argtypes = [vp]
+    L.tq_plan_destroy.restype = None
+    for name in ("tq_plan_num_qubits", "tq_plan_num_params"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = i32
+    L.tq_plan_num_sweeps.argtypes = [vp, i32]
+    L.tq_plan_num_sweeps.restype = i32
+    L.tq_plan_sweep_bits.argtypes = [vp, i32, i32, C.POINTER(i32), i32]
+    L.tq_plan_sweep_bits.restype = i32
+    L.tq_plan_sweep_num_gates.argtypes = [vp, i32, i32]
+    L.tq_plan_sweep_num_gates.restype = i32
+    L.tq_plan_out_reals.argtypes = [vp]
+    L.tq_plan_out_reals.restype = i64
+    L.tq_plan_hbm_bytes.argtypes = [vp, i32]
+    L.tq_plan_hbm_bytes.restype = i64
+    L.tq_plan_launches.argtypes = [vp, i32]
+    L.tq_plan_launches.restype = i64
+    L.tq_workspace_bytes.argtypes = [vp, i64, i32]
+    L.tq_workspace_bytes.restype = sz
+    L.tq_forward.argtypes = [vp, vp, i64, vp, vp, sz, i32, vp]
+    L.tq_forward.restype = i32
+    L.tq_backward.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
+    L.tq_backward.restype = i32
+    L.tq_workspace_state.argtypes = [vp, vp, i64]
+    L.tq_workspace_state.restype = vp
+    L.tq_execute_host.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.tq_execute_host.restype = i32
+    L.tq_sv_axes_perm.argtypes = [i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(i32)]
+    L.tq_sv_axes_perm.restype = i32
+    if L.tq_abi_version() != 1:
+        raise EngineError("libtedq_b200.so ABI version mismatch: rebuild with `python -m tedq_b200.build --force`")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().tq_last_error().decode(errors="replace")
+        raise EngineError(f"{what} failed ({rc}): {msg}")
+
+
+def sv_axes_perm(n_qubits, qubits):
+    k = len(qubits)
+    q = (C.c_int32 * k)(*qubits)
+    gp = (C.c_int32 * k)()
+    pm = (C.c_int32 * n_qubits)()
+    check(lib().tq_sv_axes_perm(n_qubits, q, k, gp, pm), "tq_sv_axes_perm")
+    return list(gp), list(pm)
+
+
+class Plan:
+    """Owns a tq_plan*."""
+
+    def __init__(self, ir: CircuitIR, dtype: int = TQ_C64, opts: Optional[dict] = None):
+        L = lib()
+        self.ir = ir
+        self.dtype = dtype
+        pool = []
+        off = 0
+        gates = (GateDesc * max(1, len(ir.gates)))()
+        for i, g in enumerate(ir.gates):
+            d = gates[i]
+            d.kind = g.kind
+            d.nq = len(g.qubits)
+            if d.nq > 3:
+                raise NotImplementedError(f"{g.name}: gates on more than 3 qubits are not supported")
+            for j, q in enumerate(g.qubits):
+                d.qubits[j] = q
+            for j in range(3):
+                d.param_idx[j] = g.param_idx[j] if j < len(g.param_idx) else -1
+                d.param_const[j] = g.param_const[j] if j < len(g.param_const) else 0.0
+            d.matrix_off = -1
+            if g.matrix is not None:
+                d.matrix_off = off
+                m = np.ascontiguousarray(g.matrix, dtype=np.complex128).reshape(-1)
+                pool.append(m)
+                off += m.size
+        meas = (MeasDesc * len(ir.meas))()
+        for i, ms in enumerate(ir.meas):
+            d = meas[i]
+            d.kind = ms.kind
+            d.flags = ms.flags
+            d.nq = len(ms.qubits)
+            for j, q in enumerate(ms.qubits):
+                d.qubits[j] = q
+            d.matrix_off = -1
+            if ms.matrix is not None:
+                d.matrix_off = off
+                m = np.ascontiguousarray(ms.matrix, dtype=np.complex128).reshape(-1)
+                pool.append(m)
+                off += m.size
+        poolarr = np.concatenate(pool) if pool else np.zeros(1, dtype=np.complex128)
+        poolarr = np.ascontiguousarray(poolarr.view(np.float64))
+        init_ptr = None
+        if ir.init_state is not None:
+            self._init = np.ascontiguousarray(ir.init_state.astype(np.complex128).view(np.float64))
+            init_ptr = self._init.ctypes.data_as(C.POINTER(C.c_double))
+        o = PlanOpts()
+        o.coalesce_bits = -1
+        o.fuse = -1
+        for k, v in (opts or {}).items():
+            setattr(o, k, v)
+        handle = C.c_void_p()
+        check(L.tq_plan_create(gates, len(ir.gates), meas, len(ir.meas), poolarr.ctypes.data_as(C.POINTER(C.c_double)),
+                               off, ir.num_qubits, ir.n_params, dtype, init_ptr, C.byref(o), C.byref(handle)),
+              "tq_plan_create")
+        self.handle = handle
+        self.out_reals = int(L.tq_plan_out_reals(handle))
+        self.n_params = ir.n_params
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and _lib is not None:
+            _lib.tq_plan_destroy(h)
+            self.handle = None
+
+    # -- introspection -----------------------------------------------------
+    def num_sweeps(self, backward=False) -> int:
+        return int(lib().tq_plan_num_sweeps(self.handle, int(backward)))
+
+    def sweep_bits(self, s, backward=False):
+        buf = (C.c_int32 * 32)()
+        n = lib().tq_plan_sweep_bits(self.handle, int(backward), s, buf, 32)
+        return list(buf[:n])
+
+    def sweep_num_gates(self, s, backward=False) -> int:
+        return int(lib().tq_plan_sweep_num_gates(self.handle, int(backward), s))
+
+    def hbm_bytes(self, backward=False) -> int:
+        return int(lib().tq_plan_hbm_bytes(self.handle, int(backward)))
+
+    def launches(self, backward=False) -> int:
+        return int(lib().tq_plan_launches(self.handle, int(backward)))
+
+    def workspace_bytes(self, batch: int, with_backward: bool) -> int:
+        return int(lib().tq_workspace_bytes(self.handle, batch, int(with_backward)))
+
+    # -- execution on raw device pointers ------------------------------------
+    def forward(self, params_ptr, batch, out_ptr, ws_ptr, ws_bytes, with_backward, stream):
+        check(lib().tq_forward(self.handle, params_ptr, batch, out_ptr, ws_ptr, ws_bytes, int(with_backward), stream),
+              "tq_forward")
+
+    def backward(self, params_ptr, batch, grad_out_ptr, grad_params_ptr, ws_ptr, ws_bytes, stream):
+        check(lib().tq_backward(self.handle, params_ptr, batch, grad_out_ptr, grad_params_ptr, ws_ptr, ws_bytes,
+                                stream), "tq_backward")
+
+    def execute_host(self, params: np.ndarray, grad_out: Optional[np.ndarray] = None):
+        """HOST buffers in, HOST buffers out (H2D + kernels + D2H inside)."""
+        rdt = np.float32 if self.dtype == TQ_C64 else np.float64
+        params = np.ascontiguousarray(params, dtype=rdt)
+        batch = params.shape[0] if params.ndim == 2 else 1
+        out = np.empty((batch, self.out_reals), dtype=rdt)
+        gp = None
+        go_ptr = gp_ptr = None
+        if grad_out is not None:
+            grad_out = np.ascontiguousarray(grad_out, dtype=rdt)
+            gp = np.empty((batch, self.n_params), dtype=rdt)
+            go_ptr = grad_out.ctypes.data
+            gp_ptr = gp.ctypes.data
+        check(lib().tq_execute_host(self.handle, params.ctypes.data, batch, out.ctypes.data, go_ptr, gp_ptr),
+              "tq_execute_host")
+        return out, gp

@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+import torch
+
+import tedq_b200 as qb
+from tedq_b200 import workloads as W
+
+# north_star tolerances: complex64 results/gradients within 1e-5, complex128 within 1e-11.
+# Values are O(1) sums of products of unit-modulus amplitudes; the reference itself rounds its
+# goldens to 5 decimals (test_pytorch_backend.py:406-409), so the bound is applied as
+# |a-b| <= tol * max(1, |b|).
+TOL = {"c64": 1e-5, "c128": 1e-11}
+
+
+def rdtype(dtype):
+    return torch.float32 if dtype == "c64" else torch.float64
+
+
+def cdtype(dtype):
+    return torch.complex64 if dtype == "c64" else torch.complex128
+
+
+def golden_out(case):
+    out = np.asarray(case["out"], dtype=np.float64)
+    if case["spec"]["meas"][0][0] == "state":
+        out = out[..., 0] + 1j * out[..., 1]
+    return out
+
+
+def build(case_or_spec, dtype="c64", flat=None):
+    spec = case_or_spec.get("spec", case_or_spec)
+    wrap = lambda v: torch.tensor(float(v), dtype=rdtype(dtype))
+    return W.build_circuit(spec, qb, flat, tensor_fn=wrap)
+
+
+def assert_close(a, b, tol, what=""):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    err = np.abs(a - b)
+    bound = tol * np.maximum(1.0, np.abs(b))
+    worst = float(np.max(err - bound)) if err.size else 0.0
+    assert worst <= 0, f"{what}: max |a-b| = {float(err.max()):.3e} exceeds {tol:g}*max(1,|b|)"

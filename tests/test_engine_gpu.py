@@ -1,0 +1,176 @@
+"""GPU parity tests proper: the CUDA engine (through the C ABI) against fixtures produced by the reference
+and against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import tedq_b200 as qb
+from conftest import case_id, load_golden
+from helpers import TOL, assert_close, build, cdtype, golden_out, rdtype
+from tedq_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+CASES = load_golden("sv_cases.json")
+
+
+def run_engine(case, plan_opts=None, via="batched"):
+    dt = case["dtype"]
+    flat0 = case["flat"][0] if case["flat"] and case["flat"][0] else None
+    cc = build(case, dt, flat0).compilecircuit(backend="pytorch_b200", dtype=cdtype(dt), plan_opts=plan_opts)
+    flat = torch.tensor(case["flat"], dtype=rdtype(dt), device="cuda").reshape(len(case["flat"]), -1)
+    if flat.shape[1] == 0:
+        out = cc()
+        return out.unsqueeze(0).cpu().numpy(), None
+    flat.requires_grad_(True)
+    out = cc.batched(flat)
+    grad = None
+    if case["cotangent"]:
+        ct = torch.tensor(case["cotangent"], dtype=rdtype(dt), device="cuda")
+        if out.is_complex():
+            loss = torch.sum(torch.view_as_real(out) * ct)
+        else:
+            loss = torch.sum(out * ct)
+        loss.backward()
+        grad = flat.grad.cpu().numpy()
+    return out.detach().cpu().numpy(), grad
+
+
+@pytest.mark.parametrize("case", CASES, ids=case_id)
+def test_engine_matches_reference_fixture(case):
+    out, grad = run_engine(case)
+    assert_close(out, golden_out(case), TOL[case["dtype"]], "out")
+    if grad is not None:
+        assert_close(grad, np.asarray(case["grad"]), TOL[case["dtype"]], "grad")
+
+
+TILED = [c for c in CASES if 5 <= c["spec"]["num_qubits"] <= 12]
+
+
+@pytest.mark.parametrize("case", TILED, ids=case_id)
+@pytest.mark.parametrize("m", [(5, 5, 2), (6, 4, 1)])
+def test_tiled_sweeps_match_reference_fixture(case, m):
+    """Force the HBM-tiled forward/backward sweeps on small circuits (tile of 2^m amplitudes)."""
+    if case["spec"]["num_qubits"] <= max(m[0], m[1]):
+        pytest.skip("state fits one tile")
+    opts = {"max_local_qubits_fwd": m[0], "max_local_qubits_bwd": m[1], "coalesce_bits": m[2]}
+    out, grad = run_engine(case, opts)
+    assert_close(out, golden_out(case), TOL[case["dtype"]], "out")
+    if grad is not None:
+        assert_close(grad, np.asarray(case["grad"]), TOL[case["dtype"]], "grad")
+
+
+def test_reference_style_call_and_backward():
+    """Reads like test/test_pytorch_backend.py:386-584, on CUDA tensors."""
+    def circuitDef(*params):
+        qb.RX(params[0], qubits=[0])
+        qb.RY(params[1], qubits=[0])
+        return [qb.expval(qb.PauliZ(qubits=[0])), qb.expval(qb.PauliX(qubits=[1]))]
+
+    for method in ("back_prop", "param_shift"):
+        a = torch.tensor([0.54], dtype=torch.float32, requires_grad=True, device="cuda")
+        b = torch.tensor([0.12], dtype=torch.float32, requires_grad=True, device="cuda")
+        circuit = qb.Circuit(circuitDef, 2, a, b)
+        cc = circuit.compilecircuit(backend="pytorch_b200", diff_method=method)
+        res = cc(a, b)
+        assert res.shape == (2,)
+        assert np.array_equal(np.round(res.detach().cpu().numpy(), 5), np.round(np.float32([0.85154057, 0.0]), 5))
+        res[0].backward()
+        assert np.array_equal(np.round(a.grad.cpu().numpy(), 5), np.round(np.float32([-0.5104387]), 5))
+        assert np.array_equal(np.round(b.grad.cpu().numpy(), 5), np.round(np.float32([-0.10267819]), 5))
+        a2 = torch.tensor([0.54], requires_grad=True, device="cuda")
+        b2 = torch.tensor([0.12], requires_grad=True, device="cuda")
+        cc(a2, b2)[1].backward()
+        assert np.array_equal(np.round(a2.grad.cpu().numpy(), 5), np.float32([0.0]))
+        assert np.array_equal(np.round(b2.grad.cpu().numpy(), 5), np.float32([0.0]))
+
+
+def test_param_shift_four_term_gates():
+    spec = W.random_circuit(4, 24, seed=11, gate_pool=["CRX", "CRY", "CRZ", "RX", "Hadamard", "ControlledPhaseShift",
+                                                        "PhaseShift", "RZ", "Rot"],
+                            meas=[["expval", [["PauliZ", [0]]]], ["expval", [["PauliX", [2]]]]])
+    circ = W.build_circuit(spec, qb)
+    x = torch.rand(spec["n_params"], device="cuda") * 3
+    grads = []
+    for method in ("back_prop", "param_shift"):
+        cc = circ.compilecircuit(backend="pytorch_b200", diff_method=method)
+        xx = x.clone().requires_grad_(True)
+        (cc(xx) * torch.tensor([0.7, -1.3], device="cuda")).sum().backward()
+        grads.append(xx.grad.cpu().numpy())
+    assert_close(grads[1], grads[0], 2e-5, "param-shift vs adjoint")
+
+
+def test_vmap_and_shared_parameters():
+    """C1 usage: vmap over data rows with shared weights (Hessian_&_batch notebook cells 19-22)."""
+    spec = W.qnn4()
+    circ = W.build_circuit(spec, qb)
+    cc = circ.compilecircuit(backend="pytorch_b200")
+    X = torch.rand(8, 4, device="cuda")
+    w = torch.rand(2, 4, 2, device="cuda", requires_grad=True)
+    y_v = torch.func.vmap(lambda x: cc(x, w))(X)
+    y_b = cc.batched(X, w, in_dims=(0, None))
+    y_l = torch.stack([cc(X[i], w) for i in range(8)])
+    assert torch.equal(y_v, y_b)
+    assert torch.allclose(y_v, y_l, atol=1e-6)
+    y_v.sum().backward()
+    g_v = w.grad.clone()
+    w.grad = None
+    y_l.sum().backward()
+    assert torch.allclose(g_v, w.grad, atol=1e-5)
+
+
+def test_errors_match_reference():
+    def circuitDef(*params):
+        qb.RY(params[0], qubits=[0])
+        qb.RZ(params[1], qubits=[1])
+        return qb.expval(qb.PauliZ(qubits=[0]))
+
+    circuit = qb.Circuit(circuitDef, 2, 0.3, 0.4)
+    with pytest.raises(ValueError):
+        circuit.compilecircuit(backend="pytorch_b200", interface="jax")
+    with pytest.raises(ValueError, match="Error!!!! can not use contengra, opt_einsum and cyc at the same time!"):
+        circuit.compilecircuit(backend="pytorch_b200", use_cotengra=True, use_jdopttn=True)
+    with pytest.raises(ValueError):
+        circuit.compilecircuit(backend="nope")
+    cc = circuit.compilecircuit(backend="pytorch_b200")
+    a = torch.tensor([0.1], device="cuda")
+    with pytest.raises(ValueError, match="number of parameters are not matched"):
+        cc(a)
+    with pytest.raises(ValueError, match="must be type of pytorch tensor"):
+        cc(0.1, 0.2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc(torch.tensor([0.1]), torch.tensor([0.2]))
+    cc2 = circuit.compilecircuit(backend="pytorch_b200", diff_method="param_shift")
+    with pytest.raises(ValueError, match="must have the same data type"):
+        cc2(a, torch.tensor([0.1], device="cuda", dtype=torch.float64))
+    cc3 = circuit.compilecircuit(backend="pytorch_b200", diff_method="arbitrary")
+    with pytest.raises(Exception, match="is not supported"):
+        cc3(a, a)
+
+
+def test_host_entry_point_matches_device_path():
+    case = [c for c in CASES if c["spec"]["name"].startswith("mbl1d_8")][0]
+    cc = build(case).compilecircuit(backend="pytorch_b200")
+    flat = np.asarray(case["flat"], dtype=np.float32)
+    ct = np.asarray(case["cotangent"], dtype=np.float32)
+    out, grad = cc.execute_host(flat, ct.reshape(len(flat), -1))
+    assert_close(out, golden_out(case), 1e-5, "out")
+    assert_close(grad, np.asarray(case["grad"]), 1e-5, "grad")
+
+
+def test_user_initial_state():
+    rng = np.random.RandomState(3)
+    v = rng.randn(8) + 1j * rng.randn(8)
+    v /= np.linalg.norm(v)
+
+    def circuitDef(t):
+        qb.InitStateVector(v)
+        qb.RX(t[0], qubits=[1])
+        qb.CNOT(qubits=[1, 2])
+        return qb.state()
+
+    from oracle import sv_ref
+    circ = qb.Circuit(circuitDef, 3, torch.tensor([0.3]))
+    cc = circ.compilecircuit(backend="pytorch_b200")
+    got = cc(torch.tensor([0.3], device="cuda")).cpu().numpy()
+    ref = sv_ref.run_sv(circ, torch.tensor([0.3])).numpy()
+    assert_close(got, ref, 1e-6, "state")
