@@ -846,6 +846,23 @@ static void classify_fixed(const zc* U, int k, const int32_t* qubits, HostOp& op
       }
     is_ctrl[t] = ok;
   }
+  {
+    // exact identity: nothing to do.  Otherwise at least one qubit must stay a target: a gate whose
+    // every qubit qualifies as a control (Z, S, T, CZ, ...) is a phase on the all-ones subspace.
+    bool ident = true;
+    for (int r = 0; r < D && ident; ++r)
+      for (int c = 0; c < D && ident; ++c)
+        if (U[r * D + c] != (r == c ? zc(1, 0) : zc(0, 0))) ident = false;
+    if (ident) {
+      op.targets.clear();
+      op.controls.clear();
+      op.noop = true;
+      return;
+    }
+    bool all = true;
+    for (int t = 0; t < k; ++t) all = all && is_ctrl[t];
+    if (all) is_ctrl[k - 1] = 0;
+  }
   // controls must be peeled consistently: after fixing control bits to 1 the block is the reduced matrix
   std::vector<int> tq_, cq_;
   for (int t = 0; t < k; ++t) (is_ctrl[t] ? cq_ : tq_).push_back(t);
