@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — circuit evaluations/s of the compiled-circuit hot path on N B200s (one rank per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4] [--impl b200|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic parameter sets: forward through the
+whole circuit including measurements, and the backward (adjoint) pass for the gradient of sum(outputs)
+w.r.t. every flat parameter.  An *evaluation* = one parameter set through one step.
+Default workload = BASELINE.json configs[1]: 12-qubit 1-D many-body-localisation circuit, complex64,
+batch 256 parameter sets per GPU (weak scaling: every rank runs its own 256 sets, no collective on the
+data path; rank 0 reduces the timings).  Rank 0 prints ONE JSON line.
+
+Timed region: per step a CUDA-event pair on the launching stream; between steps L2 is flushed by writing
+a 256 MiB buffer (outside the event pair).  `value` has inputs resident in HBM; `e2e` goes through the
+C-ABI host entry point (tq_execute_host) with HOST buffers: H2D of parameters and cotangent and D2H of
+results and gradients are inside its timed region.  `--impl reference` times the CPU restatement of the
+reference's own pytorch path (oracle/sv_ref.py: the reference is pure Python and cannot travel to the
+box; same torch ops, same python loop) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload(name):
+    """-> (spec, inputs [B, P] float np array, complex dtype string, description)"""
+    from tedq_b200 import workloads as W
+
+    rng = np.random.RandomState(0)
+    if name == "c2":
+        spec = W.mbl_1d(12)
+        return spec, W.c2_inputs(256, 12, 0), "c64", "c2: 12-qubit MBL-1D (860 gates, 61 params), probs(q11), batch 256, fwd+bwd"
+    if name == "c1":
+        spec = W.qnn4()
+        return spec, rng.uniform(0, 1, size=(64, spec["n_params"])).astype(np.float32), "c64", \
+            "c1: 4-qubit QNN (26 gates, 20 params), 4 Z expvals, batch 64, fwd+bwd"
+    if name == "c3":
+        spec = W.hea(20, 10)
+        b = int(os.environ.get("TQ_C3_BATCH", "128"))
+        return spec, rng.uniform(0, 1, size=(b, spec["n_params"])).astype(np.float32), "c64", \
+            f"c3: 20-qubit HEA depth 10 (630 gates, 440 params), 20 Z expvals, batch {b} per GPU, fwd+bwd"
+    if name == "c4":
+        spec = W.mbl_2d(4, 1)
+        return spec, rng.uniform(0, 1, size=(64, spec["n_params"])).astype(np.float64), "c128", \
+            "c4: 16-qubit MBL-2D 4x4 depth-1 (1835 gates, 99 params), probs(q15), complex128, batch 64, fwd+bwd"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def time_cpu_reference(spec, flat, cdt, budget_s, max_sets):
+    """Reference CPU path (oracle port): python loop over parameter sets, forward + backward each."""
+    import tedq_b200 as qb
+    from oracle import sv_ref
+    from tedq_b200 import workloads as W
+
+    rd = torch.float32 if cdt == "c64" else torch.float64
+    cd = torch.complex64 if cdt == "c64" else torch.complex128
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=rd))
+    sv_ref.run_batch(circ, torch.tensor(flat[:1], dtype=rd), cd, torch.ones(()))  # warm-up (allocator, threads)
+    outs = []
+    n = 0
+    t0 = time.perf_counter()
+    while n < max_sets:
+        xg = torch.tensor(flat[n], dtype=rd, requires_grad=True)
+        y = sv_ref.run_sv(circ, xg, cd)
+        (torch.view_as_real(y).sum() if y.is_complex() else y.sum()).backward()
+        outs.append(y.detach())
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, (torch.stack(outs) if outs else None)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, flat, cdt, desc = workload(args.workload)
+    per_step_budget = float(os.environ.get("TQ_REF_STEP_SECONDS", "8"))
+    rates, sets = [], 0
+    for _ in range(args.warmup):
+        time_cpu_reference(spec, flat, cdt, 1.0, 2)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        r, n, dt, _ = time_cpu_reference(spec, flat, cdt, per_step_budget, len(flat))
+        rates.append(r)
+        sets = n
+    total = time.perf_counter() - t_all
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "circuit_evals_per_sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cdt, "data": "synthetic",
+        "config": {"workload": desc, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sets} parameter sets per step, python loop fwd+bwd (the reference has no batch entry); "
+                                   f"host has {os.cpu_count()} logical cores"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def measure_workload(name, steps, warmup, device, dist_on, world, do_e2e=True, do_cpu=True, kernel_timing=True):
+    import tedq_b200 as qb
+    from tedq_b200 import workloads as W
+
+    spec, flat_np, cdt, desc = workload(name)
+    rd = torch.float32 if cdt == "c64" else torch.float64
+    cd = torch.complex64 if cdt == "c64" else torch.complex128
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=rd))
+    cc = circ.compilecircuit(backend="pytorch_b200", dtype=cd)
+    plan = cc.plan()
+    B, P = flat_np.shape
+    flat = torch.tensor(flat_np, dtype=rd, device=device)
+    out = torch.empty((B, plan.out_reals), dtype=rd, device=device)
+    dy = torch.ones((B, plan.out_reals), dtype=rd, device=device)
+    grad = torch.empty((B, P), dtype=rd, device=device)
+    ws_bytes = plan.workspace_bytes(B, True)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+
+    def step():
+        plan.forward(flat.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws_bytes, True, stream)
+        plan.backward(flat.data_ptr(), B, dy.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    evf = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    t_wall = time.perf_counter()
+    for i in range(steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event pair)
+        ev[i][0].record()
+        plan.forward(flat.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws_bytes, True, stream)
+        evf[i].record()
+        plan.backward(flat.data_ptr(), B, dy.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+        ev[i][1].record()
+    torch.cuda.synchronize(device)
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    wall = time.perf_counter() - t_wall
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    fwd_ms = [a.elapsed_time(f) for (a, _), f in zip(ev, evf)]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if dist_on:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = B * steps * world / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the adjoint sweep): algorithmic HBM bytes / measured duration
+    hbm_peak, peak_kind = load_peaks()
+    bwd_ms = float(np.mean([s - f for s, f in zip(step_ms, fwd_ms)]))
+    fwd_avg = float(np.mean(fwd_ms))
+    bytes_b = plan.hbm_bytes(True) * B
+    bytes_f = plan.hbm_bytes(False) * B
+    n_sweeps_b = max(1, plan.num_sweeps(True))
+    roof = {
+        "bound": "hbm", "kernel": "k_sweep_bwd",
+        "achieved": bytes_b / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": bytes_b / (bwd_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+        "algorithmic_bytes_per_step": bytes_b + bytes_f,
+        "launch_ms": bwd_ms / n_sweeps_b, "sweeps_bwd": plan.num_sweeps(True), "sweeps_fwd": plan.num_sweeps(False),
+        "fwd_ms": fwd_avg, "bwd_ms": bwd_ms,
+        "fwd_achieved_gbs": bytes_f / (fwd_avg * 1e-3) / 1e9,
+        "note": ("state resident in shared memory for the whole circuit: HBM sees parameters, outputs and gradients "
+                 "only; the kernel is shared-memory/issue bound, see DESIGN.md" if plan.num_sweeps(True) == 1 and
+                 spec["num_qubits"] <= 13 else "tiled sweeps: each sweep reads+writes psi and lambda once"),
+    }
+    res = {"value": value, "ms_per_step": total_ms / steps, "B": B, "P": P, "desc": desc, "roofline": roof,
+           "clocks": sampler.summary(), "wall_s": wall,
+           "gpu_launches": int((plan.launches(False) + plan.launches(True)) * steps), "dtype": cdt}
+
+    # ---- e2e: HOST buffers through the C-ABI host entry point
+    if do_e2e:
+        hp = np.ascontiguousarray(flat_np, dtype=np.float32 if cdt == "c64" else np.float64)
+        hdy = np.ones((B, plan.out_reals), dtype=hp.dtype)
+        for _ in range(max(1, warmup)):
+            plan.execute_host(hp, hdy)
+        if dist_on:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            plan.execute_host(hp, hdy)
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        if dist_on:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        item = hp.dtype.itemsize
+        res["e2e"] = {"value": B * steps * world / e2e_s, "unit": "evals/s",
+                      "h2d_bytes_per_step": int(B * (P + plan.out_reals) * item),
+                      "d2h_bytes_per_step": int(B * (P + plan.out_reals) * item),
+                      "api": "tq_execute_host (C ABI, host buffers)"}
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 only, with a parity check
+    if do_cpu:
+        budget = float(os.environ.get("TQ_CPU_BASELINE_SECONDS", "12"))
+        rate, n, dt, ref_out = time_cpu_reference(spec, flat_np, cdt, budget, B)
+        got = out[:n].reshape(ref_out.shape if not ref_out.is_complex() else (n, -1)).cpu() if ref_out is not None else None
+        err = None
+        if ref_out is not None and not ref_out.is_complex():
+            err = float((got.double() - ref_out.double()).abs().max())
+        res["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n} of {B} parameter sets, python loop fwd+bwd, {dt:.1f} s; "
+                                         f"host has {os.cpu_count()} logical cores; max |gpu-cpu| on those sets = {err}"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c1,c3,c4"),
+                    help="other BASELINE configs measured briefly and reported inside the same JSON line")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist_on = world > 1
+    if dist_on:
+        torch.distributed.init_process_group("nccl", device_id=device)
+
+    main_res = measure_workload(args.workload, args.steps, args.warmup, device, dist_on, world,
+                                do_e2e=True, do_cpu=(rank == 0 and world == 1))
+    extras = {}
+    if world == 1 and args.extras:
+        for name in [e for e in args.extras.split(",") if e and e != args.workload]:
+            r = measure_workload(name, max(2, min(5, args.steps)), 3, device, False, 1, do_e2e=False,
+                                 do_cpu=os.environ.get("TQ_EXTRAS_CPU", "0") == "1")
+            extras[name] = {"value": r["value"], "unit": "evals/s", "ms_per_step": r["ms_per_step"], "workload": r["desc"],
+                            "roofline": r["roofline"], "dtype": r["dtype"]}
+            if "cpu_baseline" in r:
+                extras[name]["cpu_baseline"] = r["cpu_baseline"]
+
+    if rank == 0:
+        # TeD-Q tensor-network mode, CPU, n=12: 2000 evals / 370 s = 5.4 evals/s (draw_comparison.ipynb:67)
+        published = 2000.0 / 370.0 if args.workload == "c2" else None
+        line = {
+            "metric": "circuit_evals_per_sec", "value": main_res["value"], "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (main_res["value"] / published) if published else None,
+            "dtype": main_res["dtype"], "data": "synthetic",
+            "config": {"workload": main_res["desc"], "sets_per_gpu": main_res["B"], "params_per_set": main_res["P"],
+                       "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"dp{world} (sets sharded)",
+                       "published_baseline": "TeD-Q TN-mode CPU n=12: 5.4 evals/s, hardware unstated (BASELINE.md A2)"},
+            "roofline": main_res["roofline"], "clocks": main_res["clocks"], "e2e": main_res.get("e2e"),
+            "gpu_launches": main_res["gpu_launches"],
+        }
+        if "cpu_baseline" in main_res:
+            line["cpu_baseline"] = main_res["cpu_baseline"]
+        if extras:
+            line["other_configs"] = extras
+        print(json.dumps(line))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
