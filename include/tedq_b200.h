@@ -121,6 +121,8 @@ void tq_plan_destroy(tq_plan* plan);
 int32_t tq_plan_num_qubits(const tq_plan* plan);
 int32_t tq_plan_num_params(const tq_plan* plan);
 int32_t tq_plan_num_sweeps(const tq_plan* plan, int32_t backward);
+/* ops after gate fusion (runs of gates inside one qubit / one qubit pair become one dense block) */
+int32_t tq_plan_num_blocks(const tq_plan* plan);
 /* local amplitude-index bit positions of sweep s; returns count, writes up to cap entries */
 int32_t tq_plan_sweep_bits(const tq_plan* plan, int32_t backward, int32_t s, int32_t* bits, int32_t cap);
 int32_t tq_plan_sweep_num_gates(const tq_plan* plan, int32_t backward, int32_t s);

@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     for name in ("tq_plan_num_qubits", "tq_plan_num_params"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = i32
+    L.tq_plan_num_blocks.argtypes = [vp]
+    L.tq_plan_num_blocks.restype = i32
     L.tq_plan_num_sweeps.argtypes = [vp, i32]
     L.tq_plan_num_sweeps.restype = i32
     L.tq_plan_sweep_bits.argtypes = [vp, i32, i32, C.POINTER(i32), i32]
@@ -193,6 +195,9 @@ class Plan:
     # -- introspection -----------------------------------------------------
     def num_sweeps(self, backward=False) -> int:
         return int(lib().tq_plan_num_sweeps(self.handle, int(backward)))
+
+    def num_blocks(self) -> int:
+        return int(lib().tq_plan_num_blocks(self.handle))
 
     def sweep_bits(self, s, backward=False):
         buf = (C.c_int32 * 32)()

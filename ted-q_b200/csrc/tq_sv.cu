@@ -1,17 +1,9 @@
-// tq_sv.cu — state-vector engine of tedq_b200 (sm_100a).
+// tq_sv.cu — host side of the state-vector engine: plan construction (gate structure,
+// fusion, sweep scheduling, op/payload streams) and kernel orchestration behind the C ABI.
 //
 // Replaces, for backend="pytorch_b200", the reference's per-call Python loop
 //   psi <- permute(tensordot(G, psi, axes))      tedq/backends/pytorch_backend.py:358-380
-// its 23 gate-tensor builders (:579-1188), its measurements (:393-498) and autograd
-// through all of that with:
-//   k_materialize   gate matrices (and d/dtheta) from the flat parameter vector
-//   k_sweep_fwd     a shared-memory tile of 2^m amplitudes; runs EVERY gate of a
-//                   scheduled segment on it before the tile goes back to HBM
-//                   (n <= m: the state never touches HBM, measurements fused)
-//   k_measure       all measurements in one pass over psi (n > m)
-//   k_seed          lambda = dL/dpsi from the output cotangent
-//   k_sweep_bwd     adjoint-method sweep: psi <- G^dag psi, grad += Re<lambda|dG|psi>,
-//                   lambda <- G^dag lambda, both tiles resident in shared memory
+// its gate-tensor builders (:579-1188), measurements (:393-498) and autograd through them.
 // Amplitude index bit b (0 = fastest) <-> qubit n-1-b  (pytorch_backend.py:513-522).
 #include <math.h>
 #include <stdarg.h>
@@ -21,7 +13,7 @@
 #include <memory>
 #include <vector>
 
-#include "tq_common.h"
+#include "tq_sv_kernels.cuh"
 
 namespace tq {
 
@@ -32,763 +24,45 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+const char* last_error() { return g_err; }
 
-// ---------------------------------------------------------------------------
-// device-side tables
-// ---------------------------------------------------------------------------
-enum { OP_DENSE = 0, OP_DIAG = 1 };
-
-struct DevOp {
-  int32_t cls;      // OP_DENSE / OP_DIAG
-  int32_t k;        // number of target bits (dense: 1..3, diag: 1..3)
-  int32_t nins;     // number of bit positions to insert (dense: targets+controls, diag: controls)
-  int32_t ins[6];   // ascending tile-local bit positions to insert
-  uint32_t cmask;   // tile-local control bits (must be 1)
-  int32_t toff[8];  // dense: tile offset of matrix index r (gate qubit 0 = MSB of r)
-  int32_t tpos[3];  // diag: tile-local bit of target t (t = 0 is the MSB of the diag index)
-  int32_t mat_off;  // complex entries; per-set buffer when batched, fixed pool otherwise
-  int32_t batched;
-  int32_t nderiv;    // trainable parameters of this gate
-  int32_t dmat_off;  // per-set derivative buffer offset (nderiv matrices back to back)
-  int32_t dslot;     // first gradient slot of this op inside its backward sweep
-};
-
-struct DevGateMat {
-  int32_t kind;
-  int32_t pidx[3];
-  double pconst[3];
-  int32_t mat_off;
-  int32_t dmat_off;
-  int32_t dsel[3];  // derivative matrix index for parameter i, -1 = not trainable
-};
-
-struct DevMeas {
-  int32_t kind, flags, nq;
-  int32_t slot_base;  // first scalar slot (EXPVAL: 1 slot; PROBS with nq <= 6: 2^nq slots), -1 = none
-  int64_t out_off;    // offset in reals inside one parameter set's output
-  uint32_t zmask;     // ZSTRING amplitude mask
-  int32_t mat_off;    // dense observable (fixed pool)
-  int8_t pos[32];     // EXPVAL dense: amplitude bit of obs qubit t; PROBS: amplitude bit of kept qubit j
-};
-
-struct Geom {
-  int32_t m, n;
-  int32_t nl;
-  int8_t lsrc[16], llen[16], ldst[16];  // tile-local index -> amplitude bits
-  int32_t nt;
-  int8_t tsrc[32], tlen[32], tdst[32];  // tile number -> amplitude bits
-};
-
-__device__ __forceinline__ uint32_t dep_local(const Geom& g, uint32_t l) {
-  uint32_t r = 0;
-  for (int i = 0; i < g.nl; ++i) r |= ((l >> g.lsrc[i]) & ((1u << g.llen[i]) - 1u)) << g.ldst[i];
-  return r;
-}
-__device__ __forceinline__ uint32_t dep_tile(const Geom& g, uint32_t t) {
-  uint32_t r = 0;
-  for (int i = 0; i < g.nt; ++i) r |= ((t >> g.tsrc[i]) & ((1u << g.tlen[i]) - 1u)) << g.tdst[i];
-  return r;
-}
-
-enum { SW_INIT = 1, SW_STORE = 2, SW_MEASURE = 4, SW_FULL = 8 };
-
-// ---------------------------------------------------------------------------
-// gate matrices from theta  (pytorch_backend.py:866-1188; derivative = d/dtheta)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
-__device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
-
-template <typename R>
-__global__ void k_materialize(const R* __restrict__ params, int n_params, int64_t batch,
-                              const DevGateMat* __restrict__ tab, int n_tab, cx<R>* __restrict__ mats,
-                              int mat_stride, cx<R>* __restrict__ dmats, int dmat_stride, int with_deriv) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= batch * n_tab) return;
-  int64_t b = t / n_tab;
-  int gi = (int)(t - b * n_tab);
-  DevGateMat g = tab[gi];
-  R p[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    p[i] = g.pidx[i] >= 0 ? params[b * n_params + g.pidx[i]] : (R)g.pconst[i];
-  cx<R>* M = mats + b * mat_stride + g.mat_off;
-  cx<R>* D = with_deriv ? dmats + b * dmat_stride + g.dmat_off : nullptr;
-  const R h = (R)0.5;
-  R s, c;
-  switch (g.kind) {
-    case TQ_G_RX:
-    case TQ_G_CRX: {  // [[c, -i s], [-i s, c]]
-      sincos_(p[0] * h, &s, &c);
-      M[0] = mk<R>(c, 0);
-      M[1] = mk<R>(0, -s);
-      M[2] = mk<R>(0, -s);
-      M[3] = mk<R>(c, 0);
-      if (D && g.dsel[0] >= 0) {
-        D[0] = mk<R>(-h * s, 0);
-        D[1] = mk<R>(0, -h * c);
-        D[2] = mk<R>(0, -h * c);
-        D[3] = mk<R>(-h * s, 0);
-      }
-    } break;
-    case TQ_G_RY:
-    case TQ_G_CRY: {  // [[c, -s], [s, c]]
-      sincos_(p[0] * h, &s, &c);
-      M[0] = mk<R>(c, 0);
-      M[1] = mk<R>(-s, 0);
-      M[2] = mk<R>(s, 0);
-      M[3] = mk<R>(c, 0);
-      if (D && g.dsel[0] >= 0) {
-        D[0] = mk<R>(-h * s, 0);
-        D[1] = mk<R>(-h * c, 0);
-        D[2] = mk<R>(h * c, 0);
-        D[3] = mk<R>(-h * s, 0);
-      }
-    } break;
-    case TQ_G_RZ:
-    case TQ_G_CRZ: {  // diag(e^{-i t/2}, e^{+i t/2})
-      sincos_(p[0] * h, &s, &c);
-      M[0] = mk<R>(c, -s);
-      M[1] = mk<R>(c, s);
-      if (D && g.dsel[0] >= 0) {
-        D[0] = mk<R>(-h * s, -h * c);
-        D[1] = mk<R>(-h * s, h * c);
-      }
-    } break;
-    case TQ_G_PHASESHIFT:
-    case TQ_G_CPHASE: {  // diag(1, e^{i phi})
-      sincos_(p[0], &s, &c);
-      M[0] = mk<R>(1, 0);
-      M[1] = mk<R>(c, s);
-      if (D && g.dsel[0] >= 0) {
-        D[0] = mk<R>(0, 0);
-        D[1] = mk<R>(-s, c);
-      }
-    } break;
-    case TQ_G_ROT: {
-      // [[e^{-i(a+w)/2} c, -e^{i(a-w)/2} s], [e^{-i(a-w)/2} s, e^{i(a+w)/2} c]], c = cos(b/2)
-      R sp, cp, sm, cm;
-      sincos_(p[1] * h, &s, &c);
-      sincos_((p[0] + p[2]) * h, &sp, &cp);
-      sincos_((p[0] - p[2]) * h, &sm, &cm);
-      cx<R> e_pp = mk<R>(cp, sp), e_np = mk<R>(cp, -sp);  // e^{+i(a+w)/2}, e^{-i(a+w)/2}
-      cx<R> e_pm = mk<R>(cm, sm), e_nm = mk<R>(cm, -sm);  // e^{+i(a-w)/2}, e^{-i(a-w)/2}
-      M[0] = mk<R>(e_np.x * c, e_np.y * c);
-      M[1] = mk<R>(-e_pm.x * s, -e_pm.y * s);
-      M[2] = mk<R>(e_nm.x * s, e_nm.y * s);
-      M[3] = mk<R>(e_pp.x * c, e_pp.y * c);
-      if (D) {
-        // multiply by +-i/2:  (x,y)*(i/2) = (-y/2, x/2)
-        if (g.dsel[0] >= 0) {  // d/da
-          cx<R>* d = D + 4 * g.dsel[0];
-          d[0] = mk<R>(h * M[0].y, -h * M[0].x);   // -i/2 * M00
-          d[1] = mk<R>(-h * M[1].y, h * M[1].x);   // +i/2 * M01
-          d[2] = mk<R>(h * M[2].y, -h * M[2].x);   // -i/2 * M10
-          d[3] = mk<R>(-h * M[3].y, h * M[3].x);   // +i/2 * M11
-        }
-        if (g.dsel[1] >= 0) {  // d/db
-          cx<R>* d = D + 4 * g.dsel[1];
-          d[0] = mk<R>(-h * e_np.x * s, -h * e_np.y * s);
-          d[1] = mk<R>(-h * e_pm.x * c, -h * e_pm.y * c);
-          d[2] = mk<R>(h * e_nm.x * c, h * e_nm.y * c);
-          d[3] = mk<R>(-h * e_pp.x * s, -h * e_pp.y * s);
-        }
-        if (g.dsel[2] >= 0) {  // d/dw
-          cx<R>* d = D + 4 * g.dsel[2];
-          d[0] = mk<R>(h * M[0].y, -h * M[0].x);   // -i/2 * M00
-          d[1] = mk<R>(h * M[1].y, -h * M[1].x);   // -i/2 * M01
-          d[2] = mk<R>(-h * M[2].y, h * M[2].x);   // +i/2 * M10
-          d[3] = mk<R>(-h * M[3].y, h * M[3].x);   // +i/2 * M11
-        }
-      }
-    } break;
-    default:
-      break;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// gate application on a tile resident in shared memory
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t expand_idx(const DevOp& op, uint32_t g) {
-  uint32_t idx = g;
-  for (int j = 0; j < op.nins; ++j) idx = insert_zero_bit(idx, op.ins[j]);
-  return idx | op.cmask;
-}
-
-template <typename R>
-__device__ __forceinline__ const cx<R>* op_matrix(const DevOp& op, const cx<R>* mats_b, const cx<R>* fixed) {
-  return op.batched ? mats_b + op.mat_off : fixed + op.mat_off;
-}
-
-// ADJ: apply G^dagger instead of G
-template <typename R, int K, bool ADJ>
-__device__ __forceinline__ void dense_apply(cx<R>* sm, const DevOp& op, const cx<R>* __restrict__ M, int m) {
-  constexpr int D = 1 << K;
-  cx<R> Mr[D * D];
-#pragma unroll
-  for (int r = 0; r < D; ++r)
-#pragma unroll
-    for (int c = 0; c < D; ++c) Mr[r * D + c] = ADJ ? conj_(M[c * D + r]) : M[r * D + c];
-  int off[D];
-#pragma unroll
-  for (int r = 0; r < D; ++r) off[r] = op.toff[r];
-  const uint32_t ngroups = 1u << (m - op.nins);
-  for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-    uint32_t idx = expand_idx(op, g);
-    cx<R> a[D], b[D];
-#pragma unroll
-    for (int r = 0; r < D; ++r) a[r] = sm[idx + off[r]];
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-      cx<R> acc = mk<R>(0, 0);
-#pragma unroll
-      for (int c = 0; c < D; ++c) acc = cfma(Mr[r * D + c], a[c], acc);
-      b[r] = acc;
-    }
-#pragma unroll
-    for (int r = 0; r < D; ++r) sm[idx + off[r]] = b[r];
-  }
-}
-
-// 3-qubit dense gates do not occur in the reference gate set once controls are
-// peeled off; keep a correct, register-light path (matrix stays in global/L1).
-template <typename R, bool ADJ>
-__device__ void dense3_apply(cx<R>* sm, const DevOp& op, const cx<R>* __restrict__ M, int m) {
-  const uint32_t ngroups = 1u << (m - op.nins);
-  for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-    uint32_t idx = expand_idx(op, g);
-    cx<R> a[8], b[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = sm[idx + op.toff[r]];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      cx<R> acc = mk<R>(0, 0);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc = cfma(ADJ ? conj_(M[c * 8 + r]) : M[r * 8 + c], a[c], acc);
-      b[r] = acc;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) sm[idx + op.toff[r]] = b[r];
-  }
-}
-
-__device__ __forceinline__ int diag_index(const DevOp& op, uint32_t idx) {
-  int d = 0;
-  for (int t = 0; t < op.k; ++t) d = (d << 1) | ((idx >> op.tpos[t]) & 1u);
-  return d;
-}
-
-template <typename R, bool ADJ>
-__device__ __forceinline__ void diag_apply(cx<R>* sm, const DevOp& op, const cx<R>* __restrict__ M, int m) {
-  const uint32_t ngroups = 1u << (m - op.nins);
-  if (op.k == 1) {
-    cx<R> d0 = M[0], d1 = M[1];
-    if (ADJ) {
-      d0 = conj_(d0);
-      d1 = conj_(d1);
-    }
-    const int tp = op.tpos[0];
-    for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-      uint32_t idx = expand_idx(op, g);
-      cx<R> a = sm[idx];
-      sm[idx] = cmul(((idx >> tp) & 1u) ? d1 : d0, a);
-    }
-  } else {
-    for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-      uint32_t idx = expand_idx(op, g);
-      cx<R> d = M[diag_index(op, idx)];
-      if (ADJ) d = conj_(d);
-      sm[idx] = cmul(d, sm[idx]);
-    }
-  }
-}
-
-template <typename R, bool ADJ>
-__device__ __forceinline__ void apply_op(cx<R>* sm, const DevOp& op, const cx<R>* mats_b, const cx<R>* fixed,
-                                         int m) {
-  const cx<R>* M = op_matrix(op, mats_b, fixed);
-  if (op.cls == OP_DIAG) {
-    diag_apply<R, ADJ>(sm, op, M, m);
-  } else if (op.k == 1) {
-    dense_apply<R, 1, ADJ>(sm, op, M, m);
-  } else if (op.k == 2) {
-    dense_apply<R, 2, ADJ>(sm, op, M, m);
-  } else {
-    dense3_apply<R, ADJ>(sm, op, M, m);
-  }
-}
-
-// adjoint-method step for one gate on the (psi, lambda) tile pair:
-//   psi <- G^dag psi ; grad_d += Re <lambda | dG_d | psi> ; lambda <- G^dag lambda
-template <typename R, int K>
-__device__ __forceinline__ void dense_bwd(cx<R>* sp, cx<R>* sl, const DevOp& op, const cx<R>* __restrict__ M,
-                                          const cx<R>* __restrict__ Dm, R* s_grad, int m) {
-  constexpr int D = 1 << K;
-  cx<R> Mh[D * D];
-#pragma unroll
-  for (int r = 0; r < D; ++r)
-#pragma unroll
-    for (int c = 0; c < D; ++c) Mh[r * D + c] = conj_(M[c * D + r]);
-  int off[D];
-#pragma unroll
-  for (int r = 0; r < D; ++r) off[r] = op.toff[r];
-  R acc[3] = {0, 0, 0};
-  const uint32_t ngroups = 1u << (m - op.nins);
-  const int nd = op.nderiv;
-  for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-    uint32_t idx = expand_idx(op, g);
-    cx<R> a[D], l[D], pa[D], pl[D];
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-      a[r] = sp[idx + off[r]];
-      l[r] = sl[idx + off[r]];
-    }
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-      cx<R> x = mk<R>(0, 0), y = mk<R>(0, 0);
-#pragma unroll
-      for (int c = 0; c < D; ++c) {
-        x = cfma(Mh[r * D + c], a[c], x);
-        y = cfma(Mh[r * D + c], l[c], y);
-      }
-      pa[r] = x;
-      pl[r] = y;
-    }
-    for (int d = 0; d < nd; ++d) {
-      const cx<R>* Dd = Dm + d * D * D;
-      R s = 0;
-#pragma unroll
-      for (int r = 0; r < D; ++r) {
-        cx<R> x = mk<R>(0, 0);
-#pragma unroll
-        for (int c = 0; c < D; ++c) x = cfma(Dd[r * D + c], pa[c], x);
-        s += re_conj_mul(l[r], x);
-      }
-      acc[d] += s;
-    }
-#pragma unroll
-    for (int r = 0; r < D; ++r) {
-      sp[idx + off[r]] = pa[r];
-      sl[idx + off[r]] = pl[r];
-    }
-  }
-  for (int d = 0; d < nd; ++d) {
-    R v = warp_sum(acc[d]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[op.dslot + d], v);
-  }
-}
-
-template <typename R>
-__device__ void dense3_bwd(cx<R>* sp, cx<R>* sl, const DevOp& op, const cx<R>* __restrict__ M, int m) {
-  // fixed 3-qubit dense gates carry no parameters: un-apply on both tiles
-  dense3_apply<R, true>(sp, op, M, m);
-  dense3_apply<R, true>(sl, op, M, m);
-}
-
-template <typename R>
-__device__ __forceinline__ void diag_bwd(cx<R>* sp, cx<R>* sl, const DevOp& op, const cx<R>* __restrict__ M,
-                                         const cx<R>* __restrict__ Dm, R* s_grad, int m) {
-  const uint32_t ngroups = 1u << (m - op.nins);
-  R acc = 0;
-  const int nd = op.nderiv;  // diag gates have at most one parameter
-  for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
-    uint32_t idx = expand_idx(op, g);
-    int di = diag_index(op, idx);
-    cx<R> dh = conj_(M[di]);
-    cx<R> a = sp[idx], l = sl[idx];
-    cx<R> pa = cmul(dh, a);
-    if (nd) acc += re_conj_mul(l, cmul(Dm[di], pa));
-    sp[idx] = pa;
-    sl[idx] = cmul(dh, l);
-  }
-  if (nd) {
-    R v = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[op.dslot], v);
-  }
-}
-
-template <typename R>
-__device__ __forceinline__ void bwd_op(cx<R>* sp, cx<R>* sl, const DevOp& op, const cx<R>* mats_b,
-                                       const cx<R>* dmats_b, const cx<R>* fixed, R* s_grad, int m) {
-  const cx<R>* M = op_matrix(op, mats_b, fixed);
-  const cx<R>* Dm = op.nderiv ? dmats_b + op.dmat_off : nullptr;
-  if (op.cls == OP_DIAG) {
-    diag_bwd<R>(sp, sl, op, M, Dm, s_grad, m);
-  } else if (op.k == 1) {
-    dense_bwd<R, 1>(sp, sl, op, M, Dm, s_grad, m);
-  } else if (op.k == 2) {
-    dense_bwd<R, 2>(sp, sl, op, M, Dm, s_grad, m);
-  } else {
-    dense3_bwd<R>(sp, sl, op, M, m);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// measurements / cotangent seed over an array holding the WHOLE state of one
-// parameter set (shared memory when n <= m, global memory otherwise).
-// Reference semantics: pytorch_backend.py:393-498.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gather_bits(uint32_t i, const int8_t* pos, int nq) {
-  uint32_t r = 0;
-  for (int t = 0; t < nq; ++t) r = (r << 1) | ((i >> pos[t]) & 1u);
-  return r;
-}
-
-template <typename R>
-__device__ __forceinline__ cx<R> obs_row_dot(const cx<R>* __restrict__ arr, uint32_t i, const DevMeas& ms,
-                                             const cx<R>* __restrict__ O) {
-  // (O psi)_i for a dense observable on ms.nq qubits
-  const int nq = ms.nq;
-  const int D = 1 << nq;
-  uint32_t r = gather_bits(i, ms.pos, nq);
-  uint32_t base = i;
-  for (int t = 0; t < nq; ++t) base &= ~(1u << ms.pos[t]);
-  cx<R> acc = mk<R>(0, 0);
-  for (int j = 0; j < D; ++j) {
-    uint32_t idx = base;
-    for (int t = 0; t < nq; ++t) idx |= ((j >> (nq - 1 - t)) & 1u) << ms.pos[t];
-    acc = cfma(O[r * D + j], arr[idx], acc);
-  }
-  return acc;
-}
-
-// Block-cooperative: the block covers amplitudes [i0, i0+cnt) of arr (arr indexed by amplitude).
-// s_acc: n_slots scalars in shared memory, zeroed by the caller before, synced after.
-template <typename R>
-__device__ void measure_block(const cx<R>* __restrict__ arr, uint32_t i0, uint32_t cnt,
-                              const DevMeas* __restrict__ meas, int n_meas, const cx<R>* __restrict__ fixed,
-                              R* __restrict__ out_b, R* s_acc, bool atomic_out) {
-  for (int mi = 0; mi < n_meas; ++mi) {
-    const DevMeas& ms = meas[mi];
-    if (ms.kind == TQ_M_EXPVAL) {
-      R acc = 0;
-      if (ms.flags & TQ_MF_ZSTRING) {
-        const uint32_t zm = ms.zmask;
-        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-          uint32_t i = i0 + j;
-          cx<R> a = arr[i];
-          R p = a.x * a.x + a.y * a.y;
-          acc += (__popc(i & zm) & 1) ? -p : p;
-        }
-      } else {
-        const cx<R>* O = fixed + ms.mat_off;
-        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-          uint32_t i = i0 + j;
-          acc += re_conj_mul(arr[i], obs_row_dot<R>(arr, i, ms, O));
-        }
-      }
-      acc = warp_sum(acc);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[ms.slot_base], acc);
-    } else if (ms.kind == TQ_M_PROBS) {
-      if (ms.slot_base >= 0) {  // few bins: reduce each bin inside the block
-        const int nb = 1 << ms.nq;
-        for (int bin = 0; bin < nb; ++bin) {
-          R acc = 0;
-          for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-            uint32_t i = i0 + j;
-            if ((int)gather_bits(i, ms.pos, ms.nq) == bin) {
-              cx<R> a = arr[i];
-              acc += a.x * a.x + a.y * a.y;
-            }
-          }
-          acc = warp_sum(acc);
-          if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[ms.slot_base + bin], acc);
-        }
-      } else {
-        R* o = out_b + ms.out_off;
-        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-          uint32_t i = i0 + j;
-          cx<R> a = arr[i];
-          R p = a.x * a.x + a.y * a.y;
-          if (ms.nq == 0) {
-            o[i] = p;  // full distribution: one writer per element
-          } else {
-            atomicAdd(&o[gather_bits(i, ms.pos, ms.nq)], p);
-          }
-        }
-      }
-    } else {  // TQ_M_STATE
-      R* o = out_b + ms.out_off;
-      for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-        uint32_t i = i0 + j;
-        cx<R> a = arr[i];
-        o[2 * (size_t)i] = a.x;
-        o[2 * (size_t)i + 1] = a.y;
-      }
-    }
-  }
-  __syncthreads();
-  for (int mi = 0; mi < n_meas; ++mi) {
-    const DevMeas& ms = meas[mi];
-    if (ms.slot_base < 0) continue;
-    int ns = ms.kind == TQ_M_EXPVAL ? 1 : (1 << ms.nq);
-    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
-      R v = s_acc[ms.slot_base + s];
-      if (atomic_out)
-        atomicAdd(&out_b[ms.out_off + s], v);
-      else
-        out_b[ms.out_off + s] = v;
-    }
-  }
-}
-
-// torch-convention cotangent of amplitude i: g_i = dL/dRe(psi_i) + i dL/dIm(psi_i)
-template <typename R>
-__device__ __forceinline__ cx<R> seed_amp(const cx<R>* __restrict__ arr, uint32_t i,
-                                          const DevMeas* __restrict__ meas, int n_meas,
-                                          const cx<R>* __restrict__ fixed, const R* __restrict__ dy_b) {
-  cx<R> g = mk<R>(0, 0);
-  const cx<R> a = arr[i];
-  for (int mi = 0; mi < n_meas; ++mi) {
-    const DevMeas& ms = meas[mi];
-    if (ms.kind == TQ_M_EXPVAL) {
-      R w = (R)2 * dy_b[ms.out_off];
-      if (ms.flags & TQ_MF_ZSTRING) {
-        if (__popc(i & ms.zmask) & 1) w = -w;
-        g.x += w * a.x;
-        g.y += w * a.y;
-      } else {
-        cx<R> v = obs_row_dot<R>(arr, i, ms, fixed + ms.mat_off);
-        g.x += w * v.x;
-        g.y += w * v.y;
-      }
-    } else if (ms.kind == TQ_M_PROBS) {
-      uint32_t bin = ms.nq == 0 ? i : gather_bits(i, ms.pos, ms.nq);
-      R w = (R)2 * dy_b[ms.out_off + bin];
-      g.x += w * a.x;
-      g.y += w * a.y;
-    } else {
-      g.x += dy_b[ms.out_off + 2 * (size_t)i];
-      g.y += dy_b[ms.out_off + 2 * (size_t)i + 1];
-    }
-  }
-  return g;
-}
-
-// ---------------------------------------------------------------------------
-// kernels
-// ---------------------------------------------------------------------------
-template <typename R>
-struct FwdArgs {
-  cx<R>* psi;               // [batch, 2^n]   (may be null when neither loaded nor stored)
-  const cx<R>* init_state;  // [2^n] or null (|0...0>)
-  const cx<R>* mats;        // [batch, mat_stride]
-  const cx<R>* fixed;
-  const DevOp* ops;
-  const DevMeas* meas;
-  R* out;  // [batch, out_reals]
-  int64_t out_reals;
-  int32_t mat_stride;
-  int32_t op_begin, op_end;
-  int32_t n_meas, n_slots;
-  int32_t flags;
-  int32_t tiles_log2;
-  Geom geom;
-};
-
-extern __shared__ __align__(16) unsigned char tq_smem[];
-
-template <typename R>
-__global__ void __launch_bounds__(512) k_sweep_fwd(const __grid_constant__ FwdArgs<R> a) {
-  cx<R>* sm = reinterpret_cast<cx<R>*>(tq_smem);
-  const int m = a.geom.m;
-  const uint32_t tile_n = 1u << m;
-  const int64_t b = (int64_t)(blockIdx.x >> a.tiles_log2);
-  const uint32_t tile = blockIdx.x & ((1u << a.tiles_log2) - 1u);
-  const uint32_t tbase = dep_tile(a.geom, tile);
-  const size_t sv = (size_t)1 << a.geom.n;
-  cx<R>* psi_b = a.psi ? a.psi + (size_t)b * sv : nullptr;
-
-  if (a.flags & SW_INIT) {
-    if (a.init_state) {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = a.init_state[tbase | dep_local(a.geom, l)];
-    } else {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = mk<R>(0, 0);
-      __syncthreads();
-      if (threadIdx.x == 0 && tbase == 0) sm[0] = mk<R>(1, 0);
-    }
-  } else {
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = psi_b[tbase | dep_local(a.geom, l)];
-  }
-  __syncthreads();
-
-  const cx<R>* mats_b = a.mats + (size_t)b * a.mat_stride;
-  for (int o = a.op_begin; o < a.op_end; ++o) {
-    apply_op<R, false>(sm, a.ops[o], mats_b, a.fixed, m);
-    __syncthreads();
-  }
-
-  if (a.flags & SW_STORE) {
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) psi_b[tbase | dep_local(a.geom, l)] = sm[l];
-  }
-  if (a.flags & SW_MEASURE) {  // only with m == n: tile index == amplitude index
-    R* s_acc = reinterpret_cast<R*>(sm + tile_n);
-    for (int s = threadIdx.x; s < a.n_slots; s += blockDim.x) s_acc[s] = 0;
-    __syncthreads();
-    measure_block<R>(sm, 0, tile_n, a.meas, a.n_meas, a.fixed, a.out + (size_t)b * a.out_reals, s_acc, false);
-  }
-}
-
-template <typename R>
-struct MeasArgs {
-  const cx<R>* psi;
-  const cx<R>* fixed;
-  const DevMeas* meas;
-  R* out;
-  int64_t out_reals;
-  int32_t n_meas, n_slots, n;
-  int32_t chunk_log2;  // amplitudes per block
-};
-
-template <typename R>
-__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ MeasArgs<R> a) {
-  R* s_acc = reinterpret_cast<R*>(tq_smem);
-  const int cl = a.n - a.chunk_log2;  // log2(chunks per set)
-  const int64_t b = (int64_t)(blockIdx.x >> cl);
-  const uint32_t chunk = blockIdx.x & ((1u << cl) - 1u);
-  for (int s = threadIdx.x; s < a.n_slots; s += blockDim.x) s_acc[s] = 0;
-  __syncthreads();
-  measure_block<R>(a.psi + ((size_t)b << a.n), chunk << a.chunk_log2, 1u << a.chunk_log2, a.meas, a.n_meas,
-                   a.fixed, a.out + (size_t)b * a.out_reals, s_acc, true);
-}
-
-template <typename R>
-struct SeedArgs {
-  const cx<R>* psi;
-  cx<R>* lam;
-  const cx<R>* fixed;
-  const DevMeas* meas;
-  const R* dy;
-  int64_t out_reals;
-  int64_t total;  // batch * 2^n
-  int32_t n_meas, n;
-};
-
-template <typename R>
-__global__ void __launch_bounds__(256) k_seed(const __grid_constant__ SeedArgs<R> a) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = t >> a.n;
-    uint32_t i = (uint32_t)(t & (((int64_t)1 << a.n) - 1));
-    a.lam[t] = seed_amp<R>(a.psi + ((size_t)b << a.n), i, a.meas, a.n_meas, a.fixed, a.dy + b * a.out_reals);
-  }
-}
-
-template <typename R>
-struct BwdArgs {
-  cx<R>* psi;  // [batch, 2^n] (tiled mode)
-  cx<R>* lam;
-  const cx<R>* init_state;
-  const cx<R>* mats;
-  const cx<R>* dmats;
-  const cx<R>* fixed;
-  const DevOp* ops_b;  // backward-ordered ops of this sweep
-  const DevOp* ops_f;  // full mode: forward ops (recompute)
-  const DevMeas* meas;
-  const R* dy;
-  R* grad;                  // [batch, n_params]
-  const int32_t* slot_pidx;  // gradient slot -> flat parameter index (this sweep)
-  int64_t out_reals;
-  int32_t mat_stride, dmat_stride;
-  int32_t opb_begin, opb_end;
-  int32_t opf_begin, opf_end;
-  int32_t n_meas, n_params, n_dslots;
-  int32_t flags;
-  int32_t tiles_log2;
-  Geom geom;
-};
-
-template <typename R>
-__global__ void __launch_bounds__(512) k_sweep_bwd(const __grid_constant__ BwdArgs<R> a) {
-  const int m = a.geom.m;
-  const uint32_t tile_n = 1u << m;
-  cx<R>* sp = reinterpret_cast<cx<R>*>(tq_smem);
-  cx<R>* sl = sp + tile_n;
-  R* s_grad = reinterpret_cast<R*>(sl + tile_n);
-  const int64_t b = (int64_t)(blockIdx.x >> a.tiles_log2);
-  const uint32_t tile = blockIdx.x & ((1u << a.tiles_log2) - 1u);
-  const uint32_t tbase = dep_tile(a.geom, tile);
-  const size_t sv = (size_t)1 << a.geom.n;
-  const cx<R>* mats_b = a.mats + (size_t)b * a.mat_stride;
-  const cx<R>* dmats_b = a.dmats + (size_t)b * a.dmat_stride;
-
-  for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) s_grad[s] = 0;
-
-  if (a.flags & SW_FULL) {
-    // recompute the forward state in shared memory, then seed lambda from it
-    if (a.init_state) {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = a.init_state[l];
-    } else {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = mk<R>(0, 0);
-      __syncthreads();
-      if (threadIdx.x == 0) sp[0] = mk<R>(1, 0);
-    }
-    __syncthreads();
-    for (int o = a.opf_begin; o < a.opf_end; ++o) {
-      apply_op<R, false>(sp, a.ops_f[o], mats_b, a.fixed, m);
-      __syncthreads();
-    }
-    const R* dy_b = a.dy + b * a.out_reals;
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x)
-      sl[l] = seed_amp<R>(sp, l, a.meas, a.n_meas, a.fixed, dy_b);
-  } else {
-    cx<R>* psi_b = a.psi + (size_t)b * sv;
-    cx<R>* lam_b = a.lam + (size_t)b * sv;
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) {
-      uint32_t gi = tbase | dep_local(a.geom, l);
-      sp[l] = psi_b[gi];
-      sl[l] = lam_b[gi];
-    }
-  }
-  __syncthreads();
-
-  for (int o = a.opb_begin; o < a.opb_end; ++o) {
-    bwd_op<R>(sp, sl, a.ops_b[o], mats_b, dmats_b, a.fixed, s_grad, m);
-    __syncthreads();
-  }
-
-  if (!(a.flags & SW_FULL) && (a.flags & SW_STORE)) {
-    cx<R>* psi_b = a.psi + (size_t)b * sv;
-    cx<R>* lam_b = a.lam + (size_t)b * sv;
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) {
-      uint32_t gi = tbase | dep_local(a.geom, l);
-      psi_b[gi] = sp[l];
-      lam_b[gi] = sl[l];
-    }
-  }
-  R* grad_b = a.grad + b * a.n_params;
-  for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) {
-    if (a.flags & SW_FULL)
-      grad_b[a.slot_pidx[s]] = s_grad[s];
-    else
-      atomicAdd(&grad_b[a.slot_pidx[s]], s_grad[s]);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// host side: plan
-// ---------------------------------------------------------------------------
 typedef std::complex<double> zc;
 
-struct HostOp {     // one circuit gate, structure resolved
-  int cls = OP_DENSE;
-  std::vector<int> targets;   // qubits, matrix MSB first
-  std::vector<int> controls;  // qubits
+struct HostGate {  // one circuit gate, structure resolved
+  int kind = 0, nq = 0;
+  int qubits[3] = {0, 0, 0};
+  int pidx[3] = {-1, -1, -1};
+  double pconst[3] = {0, 0, 0};
+  int nparams = 0;   // parameter slots of the kind
+  int ntrain = 0;    // trainable slots
   bool noop = false;
-  bool batched = false;
-  int mat_off = 0;  // fixed pool offset or per-set offset
+  int full_off = -1;  // FIXED: full matrix in the fixed pool
+  // structure of the gate on its own (single-member block)
+  int cls = OP_DENSE;
+  std::vector<int> targets, controls;  // qubits
+  int red_off = -1;                    // FIXED: reduced matrix (dense block or diagonal) in the fixed pool
+  int red_count = 0;
+};
+
+struct HostBlock {
+  std::vector<int> qubits;   // block qubit order (MSB first)
+  std::vector<int> members;  // gate indices, circuit order
+  bool alive = true;
   int nderiv = 0;
-  int dmat_off = 0;
-  int pidx[3] = {-1, -1, -1};  // flat parameter of derivative d
-  std::vector<int> qubits;     // all qubits touched
+  // resolved op
+  int cls = OP_DENSE;
+  std::vector<int> targets, controls;
+  int count = 0;  // matrix entries
+  int pidx[MAX_BLOCK_DERIV];
+  int mat_block = -1;  // index into MatBlock table
 };
 
 struct Sweep {
   Geom geom;
-  std::vector<int> bits;  // ascending amplitude bits kept in the tile
-  int op_begin = 0, op_end = 0;
-  int n_gates = 0;
+  std::vector<int> bits;
+  int op_begin = 0, op_end = 0, n_gates = 0;
   int slot_begin = 0, n_dslots = 0;
+  int chunk_begin = 0, n_chunks = 0;
 };
 
 }  // namespace tq
@@ -797,23 +71,28 @@ using namespace tq;
 
 struct tq_plan {
   int n = 0, n_params = 0, dtype = TQ_C64, n_gates = 0;
-  std::vector<HostOp> hops;
-  std::vector<DevGateMat> gmats;
-  int mat_stride = 0, dmat_stride = 0;
+  std::vector<HostGate> gates;
+  std::vector<HostBlock> blocks;  // alive blocks only, execution order
+  std::vector<MatBlock> mblocks;
+  std::vector<MatInstr> minstrs;
+  int64_t stride_f = 0, stride_b = 0;  // payload entries per parameter set
   std::vector<tq_meas_desc> meas;
   std::vector<DevMeas> dmeas;
   int n_slots = 0;
   int64_t out_reals = 0;
-  std::vector<zc> fixed;  // host copy (double)
+  std::vector<zc> fixed;
   bool fwd_full = false, bwd_full = false;
-  int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256;
+  int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256, fuse = 1;
   std::vector<Sweep> fwd, bwd;
   // device
   void* d_fixed = nullptr;
   void* d_init = nullptr;
-  DevOp* d_ops_f = nullptr;
-  DevOp* d_ops_b = nullptr;
-  DevGateMat* d_gmats = nullptr;
+  OpDesc* d_ops_f = nullptr;
+  OpDesc* d_ops_b = nullptr;
+  ChunkInfo* d_chunks_f = nullptr;
+  ChunkInfo* d_chunks_b = nullptr;
+  MatBlock* d_mblocks = nullptr;
+  MatInstr* d_minstrs = nullptr;
   DevMeas* d_meas = nullptr;
   int32_t* d_slot_pidx = nullptr;
   // scratch for tq_execute_host
@@ -828,8 +107,16 @@ static size_t csize(int dtype) { return dtype == TQ_C64 ? 8 : 16; }
 static size_t rsize(int dtype) { return dtype == TQ_C64 ? 4 : 8; }
 
 // Peel control qubits off a fixed matrix, classify the rest (dense / diagonal).
-static void classify_fixed(const zc* U, int k, const int32_t* qubits, HostOp& op, std::vector<zc>& reduced) {
+static void classify_fixed(const zc* U, int k, const int* qubits, HostGate& g, std::vector<zc>& reduced) {
   const int D = 1 << k;
+  bool ident = true;
+  for (int r = 0; r < D && ident; ++r)
+    for (int c = 0; c < D && ident; ++c)
+      if (U[r * D + c] != (r == c ? zc(1, 0) : zc(0, 0))) ident = false;
+  if (ident) {
+    g.noop = true;
+    return;
+  }
   std::vector<int> is_ctrl(k, 0);
   for (int t = 0; t < k; ++t) {
     const int bt = k - 1 - t;
@@ -846,24 +133,11 @@ static void classify_fixed(const zc* U, int k, const int32_t* qubits, HostOp& op
       }
     is_ctrl[t] = ok;
   }
-  {
-    // exact identity: nothing to do.  Otherwise at least one qubit must stay a target: a gate whose
-    // every qubit qualifies as a control (Z, S, T, CZ, ...) is a phase on the all-ones subspace.
-    bool ident = true;
-    for (int r = 0; r < D && ident; ++r)
-      for (int c = 0; c < D && ident; ++c)
-        if (U[r * D + c] != (r == c ? zc(1, 0) : zc(0, 0))) ident = false;
-    if (ident) {
-      op.targets.clear();
-      op.controls.clear();
-      op.noop = true;
-      return;
-    }
-    bool all = true;
-    for (int t = 0; t < k; ++t) all = all && is_ctrl[t];
-    if (all) is_ctrl[k - 1] = 0;
-  }
-  // controls must be peeled consistently: after fixing control bits to 1 the block is the reduced matrix
+  // a gate whose every qubit qualifies as a control (Z, S, T, CZ, ...) is a phase on the
+  // all-ones subspace: keep the last qubit as the (diagonal) target
+  bool all = true;
+  for (int t = 0; t < k; ++t) all = all && is_ctrl[t];
+  if (all) is_ctrl[k - 1] = 0;
   std::vector<int> tq_, cq_;
   for (int t = 0; t < k; ++t) (is_ctrl[t] ? cq_ : tq_).push_back(t);
   const int kt = (int)tq_.size();
@@ -882,21 +156,17 @@ static void classify_fixed(const zc* U, int k, const int32_t* qubits, HostOp& op
   for (int r = 0; r < Dt && diag; ++r)
     for (int c = 0; c < Dt && diag; ++c)
       if (r != c && reduced[r * Dt + c] != zc(0, 0)) diag = false;
-  op.targets.clear();
-  op.controls.clear();
-  for (int t : tq_) op.targets.push_back(qubits[t]);
-  for (int t : cq_) op.controls.push_back(qubits[t]);
-  if (kt == 0) {
-    op.noop = true;
-    return;
-  }
+  g.targets.clear();
+  g.controls.clear();
+  for (int t : tq_) g.targets.push_back(qubits[t]);
+  for (int t : cq_) g.controls.push_back(qubits[t]);
   if (diag) {
-    op.cls = OP_DIAG;
+    g.cls = OP_DIAG;
     std::vector<zc> d(Dt);
     for (int r = 0; r < Dt; ++r) d[r] = reduced[r * Dt + r];
     reduced = d;
   } else {
-    op.cls = OP_DENSE;
+    g.cls = OP_DENSE;
   }
 }
 
@@ -904,7 +174,6 @@ static void build_geom(int n, const std::vector<int>& bits, Geom& g) {
   memset(&g, 0, sizeof(g));
   g.n = n;
   g.m = (int)bits.size();
-  // local runs
   int i = 0;
   while (i < g.m) {
     int j = i;
@@ -933,25 +202,24 @@ static void build_geom(int n, const std::vector<int>& bits, Geom& g) {
   }
 }
 
-// Greedy segment scheduler: walk the not-yet-run gates in order; a gate joins the
-// sweep when its qubits fit into the tile and none of them is blocked by an
-// earlier gate that had to be deferred.
-static void schedule(int n, int m, int coalesce, const std::vector<HostOp>& hops, const std::vector<int>& order,
-                     std::vector<std::vector<int>>& seg_gates, std::vector<std::vector<int>>& seg_bits) {
-  seg_gates.clear();
+// Greedy segment scheduler over blocks: walk the not-yet-run blocks in order; a block joins the
+// sweep when its qubits fit into the tile and none of them is blocked by an earlier deferred block.
+static void schedule(int n, int m, int coalesce, const std::vector<HostBlock>& blocks, const std::vector<int>& order,
+                     std::vector<std::vector<int>>& seg_ops, std::vector<std::vector<int>>& seg_bits) {
+  seg_ops.clear();
   seg_bits.clear();
   const int G = (int)order.size();
-  std::vector<char> done(G, 0);
-  int remaining = G;
   if (n <= m) {
     std::vector<int> bits(n);
     for (int b = 0; b < n; ++b) bits[b] = b;
     seg_bits.push_back(bits);
-    seg_gates.push_back(order);
+    seg_ops.push_back(order);
     return;
   }
+  std::vector<char> done(G, 0);
+  int remaining = G;
   while (remaining > 0) {
-    std::vector<char> in_s(n, 0), blocked(n, 0);  // indexed by amplitude bit
+    std::vector<char> in_s(n, 0), blocked(n, 0);
     int ns = 0;
     for (int b = 0; b < coalesce; ++b) {
       in_s[b] = 1;
@@ -961,7 +229,7 @@ static void schedule(int n, int m, int coalesce, const std::vector<HostOp>& hops
     std::vector<int> gl;
     for (int oi = 0; oi < G && nblocked < n; ++oi) {
       if (done[oi]) continue;
-      const HostOp& op = hops[order[oi]];
+      const HostBlock& op = blocks[order[oi]];
       bool blk = false;
       int need = 0;
       for (int q : op.qubits) {
@@ -999,11 +267,11 @@ static void schedule(int n, int m, int coalesce, const std::vector<HostOp>& hops
     for (int b = 0; b < n; ++b)
       if (in_s[b]) bits.push_back(b);
     seg_bits.push_back(bits);
-    seg_gates.push_back(gl);
+    seg_ops.push_back(gl);
   }
 }
 
-static void make_dev_op(const HostOp& h, int n, const std::vector<int>& bits, DevOp& d) {
+static void make_desc(const HostBlock& h, int n, const std::vector<int>& bits, bool c64, OpDesc& d) {
   memset(&d, 0, sizeof(d));
   auto local = [&](int q) {
     int b = n - 1 - q;
@@ -1011,33 +279,69 @@ static void make_dev_op(const HostOp& h, int n, const std::vector<int>& bits, De
       if (bits[j] == b) return (int)j;
     return -1;
   };
-  d.cls = h.cls;
-  d.k = (int)h.targets.size();
-  d.mat_off = h.mat_off;
-  d.batched = h.batched ? 1 : 0;
-  d.nderiv = h.nderiv;
-  d.dmat_off = h.dmat_off;
+  std::vector<int> lt, lc;
+  for (int q : h.targets) lt.push_back(local(q));
+  for (int q : h.controls) lc.push_back(local(q));
+  const int k = (int)lt.size();
+  bool bit0_ctrl = false, bit0_tgt = false;
+  for (int b : lc) bit0_ctrl |= (b == 0);
+  for (int b : lt) bit0_tgt |= (b == 0);
+  d.k = (uint8_t)k;
+  d.nderiv = (uint8_t)h.nderiv;
+  d.count = (uint32_t)h.count;
+  d.pad = (uint32_t)h.cls;
+  int shift = 0;
   std::vector<int> ins;
-  for (int q : h.controls) {
-    int lb = local(q);
-    d.cmask |= 1u << lb;
-    ins.push_back(lb);
-  }
   if (h.cls == OP_DENSE) {
-    for (int q : h.targets) ins.push_back(local(q));
-    const int D = 1 << d.k;
-    for (int r = 0; r < D; ++r) {
-      int off = 0;
-      for (int t = 0; t < d.k; ++t)
-        if ((r >> (d.k - 1 - t)) & 1) off |= 1 << local(h.targets[t]);
-      d.toff[r] = off;
+    if (k == 1) {
+      if (c64 && lt[0] == 0) {
+        d.path = P_D1P;
+        shift = 1;
+        ins = lc;
+      } else if (c64 && !bit0_ctrl) {
+        d.path = P_D1V;
+        shift = 1;
+        ins = lc;
+        ins.push_back(lt[0]);
+      } else {
+        d.path = P_D1S;
+        ins = lc;
+        ins.push_back(lt[0]);
+      }
+    } else if (k == 2) {
+      d.path = (c64 && !bit0_ctrl && !bit0_tgt) ? P_D2V : P_D2S;
+      shift = d.path == P_D2V ? 1 : 0;
+      ins = lc;
+      ins.push_back(lt[0]);
+      ins.push_back(lt[1]);
+    } else {
+      d.path = P_GEN;
+      ins = lc;
+      for (int b : lt) ins.push_back(b);
     }
   } else {
-    for (int t = 0; t < d.k; ++t) d.tpos[t] = local(h.targets[t]);
+    if (k == 1) {
+      if (c64 && !bit0_ctrl) {
+        d.path = P_G1V;
+        shift = 1;
+        ins = lc;
+      } else {
+        d.path = P_G1S;
+        ins = lc;
+      }
+    } else {
+      d.path = P_GEN;
+      ins = lc;
+    }
   }
   std::sort(ins.begin(), ins.end());
-  d.nins = (int)ins.size();
-  for (int j = 0; j < d.nins; ++j) d.ins[j] = ins[j];
+  d.nins = (uint8_t)ins.size();
+  for (size_t j = 0; j < ins.size() && j < 4; ++j) d.ins[j] = (uint8_t)(ins[j] - shift);
+  for (int b : lc) d.cmask |= 1u << (b - shift);
+  for (int t = 0; t < k && t < 4; ++t) {
+    // P_G1V keeps the target in amplitude-bit units (it may be bit 0); every other path in path units
+    d.tpos[t] = (uint8_t)(d.path == P_G1V ? lt[t] : lt[t] - shift);
+  }
 }
 
 template <typename T>
@@ -1066,9 +370,9 @@ static int upload_complex(const zc* src, size_t count, int dtype, void** dptr) {
   return TQ_OK;
 }
 
-static int default_threads(int m) {
-  int t = 1 << std::max(5, m - 3);
-  return std::min(512, std::max(32, t));
+static int block_pay_entries(int count, int nderiv, bool backward) {
+  int e = count * (1 + (backward ? nderiv : 0));
+  return (e + 1) & ~1;  // 16-byte granularity for complex64
 }
 
 }  // namespace tq
@@ -1079,10 +383,10 @@ int tq_abi_version(void) { return TQ_ABI_VERSION; }
 const char* tq_last_error(void) { return tq::g_err; }
 
 int tq_sv_axes_perm(int32_t n_qubits, const int32_t* qubits, int32_t nq, int32_t* gate_pos, int32_t* perm) {
-  // tensordot puts the gate's output axes first, followed by the untouched state
-  // axes in ascending order; perm sends every qubit axis back to its place.
+  // tensordot puts the gate's output axes first, followed by the untouched state axes in
+  // ascending order; perm sends every qubit axis back to its place (compiled_circuit.py:126-198).
   TQ_REQUIRE(n_qubits > 0 && nq > 0 && nq <= n_qubits, TQ_E_INVALID, "tq_sv_axes_perm: bad sizes");
-  for (int i = 0; i < nq; ++i) gate_pos[i] = nq + i;
+  for (int i = 0; i < nq; ++i) gate_pos[i] = nq == 1 ? 1 : nq + i;
   std::vector<int> where(n_qubits, -1);
   for (int i = 0; i < nq; ++i) {
     TQ_REQUIRE(qubits[i] >= 0 && qubits[i] < n_qubits, TQ_E_INVALID, "tq_sv_axes_perm: qubit out of range");
@@ -1101,7 +405,10 @@ void tq_plan_destroy(tq_plan* p) {
   cudaFree(p->d_init);
   cudaFree(p->d_ops_f);
   cudaFree(p->d_ops_b);
-  cudaFree(p->d_gmats);
+  cudaFree(p->d_chunks_f);
+  cudaFree(p->d_chunks_b);
+  cudaFree(p->d_mblocks);
+  cudaFree(p->d_minstrs);
   cudaFree(p->d_meas);
   cudaFree(p->d_slot_pidx);
   cudaFree(p->h_dev);
@@ -1126,18 +433,20 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   p->n_gates = n_gates;
   const int n = n_qubits;
   const zc* zpool = reinterpret_cast<const zc*>(pool);
+  const bool c64 = dtype == TQ_C64;
 
   // ---- options -------------------------------------------------------------
-  const bool c64 = dtype == TQ_C64;
-  int full_f = c64 ? 14 : 13, full_b = c64 ? 13 : 12;  // whole state in <= 128 KiB (fwd) / 2 x 64 KiB (bwd)
-  int m_f = c64 ? 13 : 12, m_b = c64 ? 12 : 11;        // tiled: 64 KiB per CTA -> 3 CTAs per SM
+  int full_f = c64 ? 14 : 13, full_b = c64 ? 13 : 12;  // whole state: <= 128 KiB (fwd) / 2 x 64 KiB (bwd)
+  int m_f = c64 ? 13 : 12, m_b = c64 ? 12 : 11;        // tiled: 64 KiB of amplitudes per CTA -> 3 CTAs per SM
   int coalesce = c64 ? 3 : 2;                          // 64-byte contiguous runs
   int threads = 0;
+  int fuse = 1;
   if (opts) {
     if (opts->max_local_qubits_fwd > 0) m_f = full_f = opts->max_local_qubits_fwd;
     if (opts->max_local_qubits_bwd > 0) m_b = full_b = opts->max_local_qubits_bwd;
     if (opts->coalesce_bits >= 0) coalesce = opts->coalesce_bits;
     threads = opts->threads;
+    if (opts->fuse >= 0) fuse = opts->fuse;
   }
   TQ_REQUIRE(m_f <= (c64 ? 14 : 13) && m_b <= (c64 ? 13 : 12), TQ_E_INVALID,
              "tq_plan_create: tile exceeds shared memory");
@@ -1152,44 +461,56 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   p->m_f = m_f;
   p->m_b = m_b;
   p->coalesce = coalesce;
-  p->threads_f = threads > 0 ? threads : default_threads(m_f);
-  p->threads_b = threads > 0 ? threads : default_threads(m_b);
-  TQ_REQUIRE(p->threads_f % 32 == 0 && p->threads_f <= 512 && p->threads_b % 32 == 0 && p->threads_b <= 512,
-             TQ_E_INVALID, "tq_plan_create: threads must be a multiple of 32, <= 512");
+  p->fuse = fuse;
+  auto pick_threads = [&](int m) {
+    if (threads > 0) return threads;
+    int t = 1 << std::max(5, m - 3);
+    return std::min(256, std::max(32, t));
+  };
+  p->threads_f = pick_threads(m_f);
+  p->threads_b = pick_threads(m_b);
+  TQ_REQUIRE(p->threads_f % 32 == 0 && p->threads_f <= 256 && p->threads_b % 32 == 0 && p->threads_b <= 256,
+             TQ_E_INVALID, "tq_plan_create: threads must be a multiple of 32, <= 256");
 
   // ---- gates ----------------------------------------------------------------
-  p->hops.resize(n_gates);
+  p->gates.resize(n_gates);
   std::vector<char> param_seen(n_params, 0);
   for (int gi = 0; gi < n_gates; ++gi) {
     const tq_gate_desc& g = gates[gi];
-    HostOp& h = p->hops[gi];
+    HostGate& h = p->gates[gi];
     TQ_REQUIRE(g.nq >= 1 && g.nq <= TQ_MAX_GATE_QUBITS, TQ_E_UNSUPPORTED, "gate %d: %d qubits unsupported", gi, g.nq);
+    h.kind = g.kind;
+    h.nq = g.nq;
     for (int i = 0; i < g.nq; ++i) {
       TQ_REQUIRE(g.qubits[i] >= 0 && g.qubits[i] < n, TQ_E_INVALID, "gate %d: qubit %d out of range", gi, g.qubits[i]);
       for (int j = 0; j < i; ++j)
         TQ_REQUIRE(g.qubits[i] != g.qubits[j], TQ_E_INVALID, "gate %d: repeated qubit", gi);
-      h.qubits.push_back(g.qubits[i]);
+      h.qubits[i] = g.qubits[i];
     }
     if (g.kind == TQ_G_FIXED) {
       const int D = 1 << g.nq;
       TQ_REQUIRE(g.matrix_off >= 0 && g.matrix_off + (int64_t)D * D <= pool_len, TQ_E_INVALID,
                  "gate %d: matrix outside pool", gi);
       std::vector<zc> red;
-      classify_fixed(zpool + g.matrix_off, g.nq, g.qubits, h, red);
+      classify_fixed(zpool + g.matrix_off, g.nq, h.qubits, h, red);
       if (!h.noop) {
-        h.mat_off = (int)p->fixed.size();
+        h.full_off = (int)p->fixed.size();
+        p->fixed.insert(p->fixed.end(), zpool + g.matrix_off, zpool + g.matrix_off + D * D);
+        h.red_off = (int)p->fixed.size();
+        h.red_count = (int)red.size();
         p->fixed.insert(p->fixed.end(), red.begin(), red.end());
+        if (p->fixed.size() & 1) p->fixed.push_back(zc(0, 0));
       }
       continue;
     }
-    int np = 1, nqexp = 1, msize = 4;
+    int np = 1, nqexp = 1;
     bool ctrl = false;
     switch (g.kind) {
       case TQ_G_RX: case TQ_G_RY: h.cls = OP_DENSE; break;
       case TQ_G_ROT: h.cls = OP_DENSE; np = 3; break;
-      case TQ_G_RZ: case TQ_G_PHASESHIFT: h.cls = OP_DIAG; msize = 2; break;
+      case TQ_G_RZ: case TQ_G_PHASESHIFT: h.cls = OP_DIAG; break;
       case TQ_G_CRX: case TQ_G_CRY: h.cls = OP_DENSE; ctrl = true; nqexp = 2; break;
-      case TQ_G_CRZ: case TQ_G_CPHASE: h.cls = OP_DIAG; ctrl = true; nqexp = 2; msize = 2; break;
+      case TQ_G_CRZ: case TQ_G_CPHASE: h.cls = OP_DIAG; ctrl = true; nqexp = 2; break;
       default: TQ_REQUIRE(false, TQ_E_INVALID, "gate %d: unknown kind %d", gi, g.kind);
     }
     TQ_REQUIRE(g.nq == nqexp, TQ_E_INVALID, "gate %d: kind %d needs %d qubits", gi, g.kind, nqexp);
@@ -1199,23 +520,11 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     } else {
       h.targets.push_back(g.qubits[0]);
     }
-    h.batched = true;
-    DevGateMat gm;
-    memset(&gm, 0, sizeof(gm));
-    gm.kind = g.kind;
-    gm.mat_off = p->mat_stride;
-    h.mat_off = p->mat_stride;
-    p->mat_stride += msize;
-    gm.dmat_off = p->dmat_stride;
-    h.dmat_off = p->dmat_stride;
-    for (int i = 0; i < 3; ++i) {
-      gm.pidx[i] = -1;
-      gm.dsel[i] = -1;
-      gm.pconst[i] = 0.0;
-    }
+    h.nparams = np;
+    h.red_count = h.cls == OP_DIAG ? 2 : 4;
     for (int i = 0; i < np; ++i) {
-      gm.pidx[i] = g.param_idx[i];
-      gm.pconst[i] = g.param_const[i];
+      h.pidx[i] = g.param_idx[i];
+      h.pconst[i] = g.param_const[i];
       if (g.param_idx[i] >= 0) {
         TQ_REQUIRE(g.param_idx[i] < n_params, TQ_E_INVALID, "gate %d: parameter index %d out of range", gi,
                    g.param_idx[i]);
@@ -1223,13 +532,133 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
                    "gate %d: flat parameter %d bound twice (binding is positional, one slot each)", gi,
                    g.param_idx[i]);
         param_seen[g.param_idx[i]] = 1;
-        gm.dsel[i] = h.nderiv;
-        h.pidx[h.nderiv] = g.param_idx[i];
-        ++h.nderiv;
+        ++h.ntrain;
       }
     }
-    p->dmat_stride += msize * h.nderiv;
-    p->gmats.push_back(gm);
+  }
+
+  // ---- fusion: runs of gates inside one qubit or one qubit pair become one dense block -------------
+  const int pay_cap_entries = CHUNK_PAY_BYTES / (int)csize(dtype);
+  std::vector<HostBlock> all;
+  {
+    std::vector<int> owner(n, -1);
+    auto can_add = [&](const HostBlock& b, const HostGate& g, int extra_deriv) {
+      if (!fuse) return false;
+      int nd = b.nderiv + g.ntrain + extra_deriv;
+      if (nd > MAX_BLOCK_DERIV) return false;
+      int dim = 1 << std::max<int>((int)b.qubits.size(), g.nq);
+      if (block_pay_entries(dim * dim, nd, true) > pay_cap_entries) return false;
+      return b.members.size() < 256;
+    };
+    for (int gi = 0; gi < n_gates; ++gi) {
+      const HostGate& g = p->gates[gi];
+      if (g.noop) continue;
+      auto fresh = [&]() {
+        HostBlock b;
+        for (int i = 0; i < g.nq; ++i) b.qubits.push_back(g.qubits[i]);
+        b.members.push_back(gi);
+        b.nderiv = g.ntrain;
+        all.push_back(b);
+        for (int i = 0; i < g.nq; ++i) owner[g.qubits[i]] = (int)all.size() - 1;
+      };
+      if (!fuse || g.nq == 3) {
+        fresh();
+        continue;
+      }
+      if (g.nq == 1) {
+        int o = owner[g.qubits[0]];
+        if (o >= 0 && all[o].qubits.size() <= 2 && can_add(all[o], g, 0)) {
+          all[o].members.push_back(gi);
+          all[o].nderiv += g.ntrain;
+        } else {
+          fresh();
+        }
+        continue;
+      }
+      // two-qubit gate
+      int o0 = owner[g.qubits[0]], o1 = owner[g.qubits[1]];
+      if (o0 >= 0 && o0 == o1 && all[o0].qubits.size() == 2 && can_add(all[o0], g, 0)) {
+        all[o0].members.push_back(gi);
+        all[o0].nderiv += g.ntrain;
+        continue;
+      }
+      HostBlock b;
+      b.qubits.push_back(g.qubits[0]);
+      b.qubits.push_back(g.qubits[1]);
+      for (int side = 0; side < 2; ++side) {
+        int o = side == 0 ? o0 : o1;
+        if (o >= 0 && all[o].alive && all[o].qubits.size() == 1) {
+          if (can_add(b, g, all[o].nderiv)) {
+            for (int mgi : all[o].members) b.members.push_back(mgi);
+            b.nderiv += all[o].nderiv;
+            all[o].alive = false;
+          }
+        }
+      }
+      b.members.push_back(gi);
+      b.nderiv += g.ntrain;
+      all.push_back(b);
+      owner[g.qubits[0]] = owner[g.qubits[1]] = (int)all.size() - 1;
+    }
+  }
+  // resolve blocks -> ops + materialisation program
+  for (HostBlock& b : all) {
+    if (!b.alive) continue;
+    MatBlock mb;
+    memset(&mb, 0, sizeof(mb));
+    mb.instr_begin = (int)p->minstrs.size();
+    int dcount = 0;
+    const bool single = b.members.size() == 1;
+    for (int gi : b.members) {
+      const HostGate& g = p->gates[gi];
+      MatInstr mi;
+      memset(&mi, 0, sizeof(mi));
+      mi.kind = g.kind;
+      mi.nq = g.nq;
+      mi.fixed_off = single ? g.red_off : g.full_off;
+      for (int i = 0; i < 3; ++i) {
+        mi.pidx[i] = g.pidx[i];
+        mi.pconst[i] = g.pconst[i];
+        mi.dsel[i] = -1;
+        if (i < g.nparams && g.pidx[i] >= 0) {
+          b.pidx[dcount] = g.pidx[i];
+          mi.dsel[i] = dcount++;
+        }
+      }
+      if (!single) {
+        if (b.qubits.size() == 1) {
+          mi.embed = 0;
+        } else if (g.nq == 1) {
+          mi.embed = g.qubits[0] == b.qubits[0] ? 0 : 1;
+        } else {
+          mi.embed = g.qubits[0] == b.qubits[0] ? 2 : 3;
+        }
+      }
+      p->minstrs.push_back(mi);
+    }
+    mb.instr_end = (int)p->minstrs.size();
+    mb.nderiv = b.nderiv;
+    if (single) {
+      const HostGate& g = p->gates[b.members[0]];
+      b.cls = g.cls;
+      b.targets = g.targets;
+      b.controls = g.controls;
+      b.count = g.red_count;
+      mb.mode = g.kind == TQ_G_FIXED ? MB_FIXED : MB_NATIVE;
+      mb.diag = g.cls == OP_DIAG;
+      mb.dim = 1 << (int)g.targets.size();
+    } else {
+      b.cls = OP_DENSE;
+      b.targets = b.qubits;
+      b.controls.clear();
+      mb.dim = 1 << (int)b.qubits.size();
+      b.count = mb.dim * mb.dim;
+      mb.mode = MB_FUSED;
+    }
+    mb.count = b.count;
+    b.mat_block = (int)p->mblocks.size();
+    p->mblocks.push_back(mb);
+    p->blocks.push_back(b);
   }
 
   // ---- measurements ------------------------------------------------------------
@@ -1286,18 +715,23 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     }
   }
 
-  // ---- schedule ------------------------------------------------------------------
-  std::vector<int> order_f, order_b;
-  for (int gi = 0; gi < n_gates; ++gi)
-    if (!p->hops[gi].noop) order_f.push_back(gi);
-  order_b.assign(order_f.rbegin(), order_f.rend());
-  std::vector<DevOp> ops_f, ops_b;
+  // ---- schedule, descriptors, payload streams, chunk tables -----------------------------------------
+  const int nb = (int)p->blocks.size();
+  std::vector<int> order_f(nb), order_b(nb);
+  for (int i = 0; i < nb; ++i) {
+    order_f[i] = i;
+    order_b[i] = nb - 1 - i;
+  }
+  std::vector<OpDesc> ops_f, ops_b;
+  std::vector<ChunkInfo> chunks_f, chunks_b;
   std::vector<int32_t> slot_pidx;
   for (int dir = 0; dir < 2; ++dir) {
     std::vector<std::vector<int>> sg, sb;
-    schedule(n, dir ? m_b : m_f, coalesce, p->hops, dir ? order_b : order_f, sg, sb);
+    schedule(n, dir ? m_b : m_f, coalesce, p->blocks, dir ? order_b : order_f, sg, sb);
     std::vector<Sweep>& sweeps = dir ? p->bwd : p->fwd;
-    std::vector<DevOp>& ops = dir ? ops_b : ops_f;
+    std::vector<OpDesc>& ops = dir ? ops_b : ops_f;
+    std::vector<ChunkInfo>& chunks = dir ? chunks_b : chunks_f;
+    int64_t& stride = dir ? p->stride_b : p->stride_f;
     for (size_t s = 0; s < sg.size(); ++s) {
       Sweep sw;
       sw.bits = sb[s];
@@ -1305,21 +739,47 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       TQ_REQUIRE(sw.geom.nl <= 16 && sw.geom.nt <= 32, TQ_E_UNSUPPORTED, "tile geometry too fragmented");
       sw.op_begin = (int)ops.size();
       sw.slot_begin = (int)slot_pidx.size();
-      for (int gi : sg[s]) {
-        DevOp d;
-        make_dev_op(p->hops[gi], n, sb[s], d);
+      sw.chunk_begin = (int)chunks.size();
+      ChunkInfo cur = {0, 0, 0, 0};
+      bool open = false;
+      for (int bi : sg[s]) {
+        HostBlock& hb = p->blocks[bi];
+        OpDesc d;
+        make_desc(hb, n, sb[s], c64, d);
+        const int pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
+        TQ_REQUIRE(pe <= pay_cap_entries, TQ_E_UNSUPPORTED, "block payload exceeds the prefetch buffer");
+        d.pay_off = (uint32_t)stride;
+        (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
         if (dir) {
-          d.dslot = (int)slot_pidx.size() - sw.slot_begin;
-          for (int k = 0; k < d.nderiv; ++k) slot_pidx.push_back(p->hops[gi].pidx[k]);
+          d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
+          for (int k = 0; k < hb.nderiv; ++k) slot_pidx.push_back(hb.pidx[k]);
         }
+        if (open && (cur.op_count >= (uint32_t)CHUNK_OPS || (int)cur.pay_count + pe > pay_cap_entries)) {
+          chunks.push_back(cur);
+          open = false;
+        }
+        if (!open) {
+          cur.op_begin = (uint32_t)ops.size();
+          cur.op_count = 0;
+          cur.pay_begin = (uint32_t)stride;
+          cur.pay_count = 0;
+          open = true;
+        }
+        cur.op_count += 1;
+        cur.pay_count += (uint32_t)pe;
+        stride += pe;
         ops.push_back(d);
       }
+      if (open) chunks.push_back(cur);
       sw.op_end = (int)ops.size();
       sw.n_gates = (int)sg[s].size();
       sw.n_dslots = dir ? (int)slot_pidx.size() - sw.slot_begin : 0;
+      sw.n_chunks = (int)chunks.size() - sw.chunk_begin;
       sweeps.push_back(sw);
     }
+    stride = (stride + 31) & ~(int64_t)31;  // keep every set's stream 256-byte aligned
   }
+  TQ_REQUIRE(p->stride_f < ((int64_t)1 << 31) && p->stride_b < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "circuit too long");
 
   // ---- upload ---------------------------------------------------------------------
   int rc;
@@ -1329,7 +789,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   }
   if ((rc = upload(ops_f, &p->d_ops_f))) return rc;
   if ((rc = upload(ops_b, &p->d_ops_b))) return rc;
-  if ((rc = upload(p->gmats, &p->d_gmats))) return rc;
+  if ((rc = upload(chunks_f, &p->d_chunks_f))) return rc;
+  if ((rc = upload(chunks_b, &p->d_chunks_b))) return rc;
+  if ((rc = upload(p->mblocks, &p->d_mblocks))) return rc;
+  if ((rc = upload(p->minstrs, &p->d_minstrs))) return rc;
   if ((rc = upload(p->dmeas, &p->d_meas))) return rc;
   if ((rc = upload(slot_pidx, &p->d_slot_pidx))) return rc;
   *out = P.release();
@@ -1354,20 +817,24 @@ int32_t tq_plan_sweep_num_gates(const tq_plan* p, int32_t backward, int32_t s) {
   if (s < 0 || s >= (int)v.size()) return -1;
   return v[s].n_gates;
 }
+int32_t tq_plan_num_blocks(const tq_plan* p) { return p ? (int32_t)p->blocks.size() : -1; }
 int64_t tq_plan_out_reals(const tq_plan* p) { return p ? p->out_reals : -1; }
 
 int64_t tq_plan_hbm_bytes(const tq_plan* p, int32_t backward) {
   if (!p) return -1;
-  const int64_t sv = ((int64_t)1 << p->n) * (int64_t)csize(p->dtype);
+  const int64_t cs = (int64_t)csize(p->dtype);
+  const int64_t sv = ((int64_t)1 << p->n) * cs;
   const int64_t io = (int64_t)rsize(p->dtype) * (p->n_params + p->out_reals);
   if (!backward) {
-    if (p->fwd_full) return io;
-    // first sweep synthesises |0..0> (no read); every sweep writes; measurement reads once
-    return io + sv * (2 * (int64_t)p->fwd.size() - 1 + 1);
+    // payload stream written once and read once; first sweep synthesises |0..0> (no read);
+    // every sweep writes; the measurement pass reads once
+    const int64_t pay = 2 * p->stride_f * cs;
+    if (p->fwd_full) return io + pay;
+    return io + pay + sv * (2 * (int64_t)p->fwd.size());
   }
-  if (p->bwd_full) return io + (int64_t)rsize(p->dtype) * p->n_params;
-  // seed: read psi, write lambda; each sweep reads and writes both
-  return io + sv * (2 + 4 * (int64_t)p->bwd.size());
+  const int64_t pay = 2 * (p->stride_b + (p->bwd_full ? p->stride_f : 0)) * cs;
+  if (p->bwd_full) return io + pay + (int64_t)rsize(p->dtype) * p->n_params;
+  return io + pay + sv * (2 + 4 * (int64_t)p->bwd.size());
 }
 
 int64_t tq_plan_launches(const tq_plan* p, int32_t backward) {
@@ -1384,7 +851,7 @@ int64_t tq_plan_launches(const tq_plan* p, int32_t backward) {
 namespace tq {
 
 struct WsLayout {
-  size_t mats = 0, dmats = 0, psi = 0, lam = 0, total = 0;
+  size_t sf = 0, sb = 0, psi = 0, lam = 0, total = 0;
   bool has_psi = false, has_lam = false;
 };
 
@@ -1394,10 +861,10 @@ static WsLayout ws_layout(const tq_plan* p, int64_t B, int with_backward) {
   WsLayout w;
   const size_t cs = csize(p->dtype);
   size_t off = 0;
-  w.mats = off;
-  off += align_up((size_t)B * p->mat_stride * cs);
-  w.dmats = off;
-  if (with_backward) off += align_up((size_t)B * p->dmat_stride * cs);
+  w.sf = off;
+  off += align_up((size_t)B * p->stride_f * cs);
+  w.sb = off;
+  if (with_backward) off += align_up((size_t)B * p->stride_b * cs);
   w.has_psi = !p->fwd_full || (with_backward && !p->bwd_full);
   w.has_lam = with_backward && !p->bwd_full;
   w.psi = off;
@@ -1408,25 +875,35 @@ static WsLayout ws_layout(const tq_plan* p, int64_t B, int with_backward) {
   return w;
 }
 
-template <typename R>
-static int set_smem(void (*k)(const FwdArgs<R>), size_t bytes) {
-  TQ_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+template <typename K>
+static int prep_kernel(K kernel, size_t smem) {
+  TQ_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TQ_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
   return TQ_OK;
 }
 
 template <typename R>
 static int run_materialize(const tq_plan* p, const void* params, int64_t B, char* ws, const WsLayout& L,
                            int with_deriv, cudaStream_t st) {
-  const int ng = (int)p->gmats.size();
-  if (ng == 0) return TQ_OK;
-  int64_t total = B * ng;
-  int threads = 128;
+  const int nbk = (int)p->mblocks.size();
+  if (nbk == 0) return TQ_OK;
+  int64_t total = B * nbk;
+  int threads = 64;
   int64_t blocks = (total + threads - 1) / threads;
   k_materialize<R><<<(unsigned)blocks, threads, 0, st>>>(
-      (const R*)params, p->n_params, B, p->d_gmats, ng, (cx<R>*)(ws + L.mats), p->mat_stride,
-      (cx<R>*)(ws + L.dmats), p->dmat_stride, with_deriv);
+      (const R*)params, p->n_params, B, p->d_mblocks, nbk, p->d_minstrs, (const cx<R>*)p->d_fixed,
+      (cx<R>*)(ws + L.sf), p->stride_f, (cx<R>*)(ws + L.sb), p->stride_b, with_deriv);
   TQ_CUDA_OK(cudaGetLastError());
   return TQ_OK;
+}
+
+static StreamRef stream_ref(const OpDesc* ops, const ChunkInfo* chunks, const Sweep& sw) {
+  StreamRef r;
+  r.ops = ops;
+  r.chunks = chunks + sw.chunk_begin;
+  r.n_chunks = sw.n_chunks;
+  return r;
 }
 
 template <typename R>
@@ -1443,58 +920,40 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
   memset(&a, 0, sizeof(a));
   a.psi = psi;
   a.init_state = (const cx<R>*)p->d_init;
-  a.mats = (const cx<R>*)(ws + L.mats);
+  a.stream = (const cx<R>*)(ws + L.sf);
+  a.stride = p->stride_f;
   a.fixed = (const cx<R>*)p->d_fixed;
-  a.ops = p->d_ops_f;
   a.meas = p->d_meas;
   a.out = (R*)out;
   a.out_reals = p->out_reals;
-  a.mat_stride = p->mat_stride;
   a.n_meas = (int)p->dmeas.size();
   a.n_slots = p->n_slots;
+  TQ_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)B * p->out_reals * sizeof(R), st));
   if (p->fwd_full) {
     const Sweep& sw = p->fwd[0];
-    a.op_begin = sw.op_begin;
-    a.op_end = sw.op_end;
+    a.st = stream_ref(p->d_ops_f, p->d_chunks_f, sw);
     a.geom = sw.geom;
     a.tiles_log2 = 0;
     a.flags = SW_INIT | SW_MEASURE | (L.has_psi ? SW_STORE : 0);
-    size_t smem = ((size_t)sizeof(cx<R>) << n) + sizeof(R) * p->n_slots;
-    TQ_CUDA_OK(cudaFuncSetAttribute(k_sweep_fwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // a probs() over many bins writes with atomics / direct stores: clear first
-    TQ_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)B * p->out_reals * sizeof(R), st));
+    size_t smem = ((size_t)sizeof(cx<R>) << n) + RING_BYTES + sizeof(R) * p->n_slots;
+    if ((rc = prep_kernel(k_sweep_fwd<R>, smem))) return rc;
     k_sweep_fwd<R><<<(unsigned)B, p->threads_f, smem, st>>>(a);
     TQ_CUDA_OK(cudaGetLastError());
     return TQ_OK;
   }
   for (size_t s = 0; s < p->fwd.size(); ++s) {
     const Sweep& sw = p->fwd[s];
-    a.op_begin = sw.op_begin;
-    a.op_end = sw.op_end;
+    a.st = stream_ref(p->d_ops_f, p->d_chunks_f, sw);
     a.geom = sw.geom;
     a.tiles_log2 = n - sw.geom.m;
     a.flags = SW_STORE | (s == 0 ? SW_INIT : 0);
-    size_t smem = (size_t)sizeof(cx<R>) << sw.geom.m;
-    TQ_CUDA_OK(cudaFuncSetAttribute(k_sweep_fwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = ((size_t)sizeof(cx<R>) << sw.geom.m) + RING_BYTES;
+    if ((rc = prep_kernel(k_sweep_fwd<R>, smem))) return rc;
     int64_t blocks = B << a.tiles_log2;
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_forward: batch too large for one launch");
     k_sweep_fwd<R><<<(unsigned)blocks, p->threads_f, smem, st>>>(a);
     TQ_CUDA_OK(cudaGetLastError());
   }
-  if (p->fwd.empty()) {  // no gates at all: materialise the initial state
-    FwdArgs<R> z = a;
-    std::vector<int> bits(std::min(n, p->m_f));
-    for (size_t i = 0; i < bits.size(); ++i) bits[i] = (int)i;
-    build_geom(n, bits, z.geom);
-    z.op_begin = z.op_end = 0;
-    z.tiles_log2 = n - z.geom.m;
-    z.flags = SW_STORE | SW_INIT;
-    size_t smem = (size_t)sizeof(cx<R>) << z.geom.m;
-    TQ_CUDA_OK(cudaFuncSetAttribute(k_sweep_fwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sweep_fwd<R><<<(unsigned)(B << z.tiles_log2), p->threads_f, smem, st>>>(z);
-    TQ_CUDA_OK(cudaGetLastError());
-  }
-  TQ_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)B * p->out_reals * sizeof(R), st));
   MeasArgs<R> ma;
   memset(&ma, 0, sizeof(ma));
   ma.psi = psi;
@@ -1528,38 +987,33 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
   a.psi = L.has_psi ? (cx<R>*)(ws + L.psi) : nullptr;
   a.lam = L.has_lam ? (cx<R>*)(ws + L.lam) : nullptr;
   a.init_state = (const cx<R>*)p->d_init;
-  a.mats = (const cx<R>*)(ws + L.mats);
-  a.dmats = (const cx<R>*)(ws + L.dmats);
+  a.stream_f = (const cx<R>*)(ws + L.sf);
+  a.stream_b = (const cx<R>*)(ws + L.sb);
+  a.stride_f = p->stride_f;
+  a.stride_b = p->stride_b;
   a.fixed = (const cx<R>*)p->d_fixed;
-  a.ops_b = p->d_ops_b;
-  a.ops_f = p->d_ops_f;
   a.meas = p->d_meas;
   a.dy = (const R*)grad_out;
   a.grad = (R*)grad_params;
   a.out_reals = p->out_reals;
-  a.mat_stride = p->mat_stride;
-  a.dmat_stride = p->dmat_stride;
   a.n_meas = (int)p->dmeas.size();
   a.n_params = p->n_params;
   if (p->bwd_full) {
     const Sweep& sb = p->bwd[0];
     const Sweep& sf = p->fwd[0];
-    a.opb_begin = sb.op_begin;
-    a.opb_end = sb.op_end;
-    a.opf_begin = sf.op_begin;
-    a.opf_end = sf.op_end;
+    a.st_b = stream_ref(p->d_ops_b, p->d_chunks_b, sb);
+    a.st_f = stream_ref(p->d_ops_f, p->d_chunks_f, sf);
     a.geom = sb.geom;
     a.slot_pidx = p->d_slot_pidx + sb.slot_begin;
     a.n_dslots = sb.n_dslots;
     a.flags = SW_FULL;
     a.tiles_log2 = 0;
-    size_t smem = ((size_t)2 * sizeof(cx<R>) << n) + sizeof(R) * sb.n_dslots;
-    TQ_CUDA_OK(cudaFuncSetAttribute(k_sweep_bwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = ((size_t)2 * sizeof(cx<R>) << n) + RING_BYTES + sizeof(R) * sb.n_dslots;
+    if ((rc = prep_kernel(k_sweep_bwd<R>, smem))) return rc;
     k_sweep_bwd<R><<<(unsigned)B, p->threads_b, smem, st>>>(a);
     TQ_CUDA_OK(cudaGetLastError());
     return TQ_OK;
   }
-  // tiled: seed lambda from the stored final state, then sweep backwards
   SeedArgs<R> sa;
   memset(&sa, 0, sizeof(sa));
   sa.psi = a.psi;
@@ -1576,15 +1030,14 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
   TQ_CUDA_OK(cudaGetLastError());
   for (size_t s = 0; s < p->bwd.size(); ++s) {
     const Sweep& sb = p->bwd[s];
-    a.opb_begin = sb.op_begin;
-    a.opb_end = sb.op_end;
+    a.st_b = stream_ref(p->d_ops_b, p->d_chunks_b, sb);
     a.geom = sb.geom;
     a.slot_pidx = p->d_slot_pidx + sb.slot_begin;
     a.n_dslots = sb.n_dslots;
     a.flags = SW_STORE;
     a.tiles_log2 = n - sb.geom.m;
-    size_t smem = ((size_t)2 * sizeof(cx<R>) << sb.geom.m) + sizeof(R) * sb.n_dslots;
-    TQ_CUDA_OK(cudaFuncSetAttribute(k_sweep_bwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = ((size_t)2 * sizeof(cx<R>) << sb.geom.m) + RING_BYTES + sizeof(R) * sb.n_dslots;
+    if ((rc = prep_kernel(k_sweep_bwd<R>, smem))) return rc;
     int64_t blocks = B << a.tiles_log2;
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_backward: batch too large for one launch");
     k_sweep_bwd<R><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
@@ -1624,8 +1077,6 @@ int tq_backward(const tq_plan* p, const void* params, int64_t batch, const void*
 void* tq_workspace_state(const tq_plan* p, void* workspace, int64_t batch) {
   if (!p || !workspace) return nullptr;
   WsLayout L = ws_layout(p, batch, 1);
-  WsLayout L0 = ws_layout(p, batch, 0);
-  (void)L0;
   return L.has_psi ? (char*)workspace + L.psi : nullptr;
 }
 

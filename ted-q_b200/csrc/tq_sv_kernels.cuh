@@ -1,0 +1,1284 @@
+// tq_sv_kernels.cuh — device side of the state-vector engine (sm_100a).
+//
+// Kernels (all hand-written, no library calls):
+//   k_materialize  one thread per (parameter set, fused block): gate matrices from theta
+//                  (pytorch_backend.py:866-1188), products of fused runs, and d/dtheta of the
+//                  fused product for every trainable slot; written as a contiguous per-set
+//                  *payload stream* in the exact order the sweeps consume it
+//   k_sweep_fwd    a tile of 2^m amplitudes in shared memory; op descriptors and payload are
+//                  prefetched chunk-by-chunk with cp.async (LDGSTS) into a 2-deep ring while the
+//                  current chunk's gates run; 128-bit shared-memory accesses on the hot paths
+//   k_sweep_bwd    adjoint sweep on the (psi, lambda) tile pair
+//   k_measure / k_seed   measurements and cotangent seed over a state in HBM
+#pragma once
+#include "tq_common.h"
+
+namespace tq {
+
+// ---------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------
+enum { OP_DENSE = 0, OP_DIAG = 1 };
+
+// execution paths of one op on a shared-memory tile
+enum {
+  P_D1V = 0,  // dense 1 target, complex64, bit 0 free: two groups per thread, 128-bit accesses
+  P_D1P = 1,  // dense 1 target on amplitude bit 0, complex64: the pair is one 128-bit word
+  P_D1S = 2,  // dense 1 target, scalar accesses (complex128, or bit 0 is a control)
+  P_D2V = 3,  // dense 2 targets, complex64, bit 0 free
+  P_D2S = 4,  // dense 2 targets, scalar
+  P_G1V = 5,  // diagonal 1 target, complex64, bit 0 not a control
+  P_G1S = 6,  // diagonal 1 target, scalar
+  P_GEN = 7   // anything else (3-target dense, multi-target diagonal): correct, not tuned
+};
+
+struct __align__(16) OpDesc {  // 32 bytes
+  uint8_t path, k, nins, nderiv;
+  uint8_t ins[4];    // ascending bit positions to insert (units of the path: V/P paths count 128-bit words)
+  uint8_t tpos[4];   // target bit positions, tpos[0] = most significant bit of the matrix index
+  uint32_t cmask;    // control bits (same units as ins)
+  uint32_t pay_off;  // payload offset inside the per-set stream (complex entries)
+  uint32_t dslot;    // first gradient slot inside the sweep
+  uint32_t count;    // entries per matrix in the payload (4, 16, 64 dense; 2, 4, 8 diagonal)
+  uint32_t pad;
+};
+static_assert(sizeof(OpDesc) == 32, "OpDesc must be 32 bytes");
+
+constexpr int CHUNK_OPS = 16;          // ops per prefetch chunk
+constexpr int CHUNK_PAY_BYTES = 2048;  // payload bytes per chunk buffer
+constexpr int MAX_CHUNKS_SMEM = 128;   // chunk table entries staged in shared memory
+constexpr int MAX_BLOCK_DERIV = 8;     // trainable slots per fused block
+
+struct ChunkInfo {  // 16 bytes
+  uint32_t op_begin, op_count, pay_begin, pay_count;  // payload in complex entries
+};
+
+struct MatInstr {  // one member gate of a block
+  int32_t kind, nq, embed, fixed_off;
+  int32_t pidx[3];
+  int32_t dsel[3];  // derivative slot inside the block, -1 = not trainable
+  double pconst[3];
+};
+
+enum { MB_FIXED = 0, MB_NATIVE = 1, MB_FUSED = 2 };
+
+struct MatBlock {
+  int32_t mode, dim, count, nderiv;
+  int32_t instr_begin, instr_end;
+  int32_t off_f, off_b;  // payload offsets in the forward / backward streams (complex entries)
+  int32_t diag;          // MB_NATIVE: payload is the diagonal (2 entries)
+  int32_t pad[3];
+};
+
+struct DevMeas {
+  int32_t kind, flags, nq;
+  int32_t slot_base;
+  int64_t out_off;
+  uint32_t zmask;
+  int32_t mat_off;
+  int8_t pos[32];
+};
+
+struct Geom {
+  int32_t m, n;
+  int32_t nl;
+  int8_t lsrc[16], llen[16], ldst[16];
+  int32_t nt;
+  int8_t tsrc[32], tlen[32], tdst[32];
+};
+
+__device__ __forceinline__ uint32_t dep_local(const Geom& g, uint32_t l) {
+  uint32_t r = 0;
+  for (int i = 0; i < g.nl; ++i) r |= ((l >> g.lsrc[i]) & ((1u << g.llen[i]) - 1u)) << g.ldst[i];
+  return r;
+}
+__device__ __forceinline__ uint32_t dep_tile(const Geom& g, uint32_t t) {
+  uint32_t r = 0;
+  for (int i = 0; i < g.nt; ++i) r |= ((t >> g.tsrc[i]) & ((1u << g.tlen[i]) - 1u)) << g.tdst[i];
+  return r;
+}
+
+enum { SW_INIT = 1, SW_STORE = 2, SW_MEASURE = 4, SW_FULL = 8 };
+
+// ---------------------------------------------------------------------------
+// k_materialize
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+
+// 2x2 target block M (row-major) and d/dp_i of it for a parametrised kind.
+template <typename R>
+__device__ void param_gate(int kind, const R* p, cx<R>* M, cx<R> (*D)[4]) {
+  const R h = (R)0.5;
+  const cx<R> z = mk<R>(0, 0);
+  R s, c;
+  switch (kind) {
+    case TQ_G_RX:
+    case TQ_G_CRX:  // [[c, -i s], [-i s, c]]
+      sincos_(p[0] * h, &s, &c);
+      M[0] = mk<R>(c, 0); M[1] = mk<R>(0, -s); M[2] = mk<R>(0, -s); M[3] = mk<R>(c, 0);
+      D[0][0] = mk<R>(-h * s, 0); D[0][1] = mk<R>(0, -h * c); D[0][2] = mk<R>(0, -h * c); D[0][3] = mk<R>(-h * s, 0);
+      break;
+    case TQ_G_RY:
+    case TQ_G_CRY:  // [[c, -s], [s, c]]
+      sincos_(p[0] * h, &s, &c);
+      M[0] = mk<R>(c, 0); M[1] = mk<R>(-s, 0); M[2] = mk<R>(s, 0); M[3] = mk<R>(c, 0);
+      D[0][0] = mk<R>(-h * s, 0); D[0][1] = mk<R>(-h * c, 0); D[0][2] = mk<R>(h * c, 0); D[0][3] = mk<R>(-h * s, 0);
+      break;
+    case TQ_G_RZ:
+    case TQ_G_CRZ:  // diag(e^{-i t/2}, e^{+i t/2})
+      sincos_(p[0] * h, &s, &c);
+      M[0] = mk<R>(c, -s); M[1] = z; M[2] = z; M[3] = mk<R>(c, s);
+      D[0][0] = mk<R>(-h * s, -h * c); D[0][1] = z; D[0][2] = z; D[0][3] = mk<R>(-h * s, h * c);
+      break;
+    case TQ_G_PHASESHIFT:
+    case TQ_G_CPHASE:  // diag(1, e^{i phi})
+      sincos_(p[0], &s, &c);
+      M[0] = mk<R>(1, 0); M[1] = z; M[2] = z; M[3] = mk<R>(c, s);
+      D[0][0] = z; D[0][1] = z; D[0][2] = z; D[0][3] = mk<R>(-s, c);
+      break;
+    case TQ_G_ROT: {
+      // [[e^{-i(a+w)/2} c, -e^{i(a-w)/2} s], [e^{-i(a-w)/2} s, e^{i(a+w)/2} c]],  c = cos(b/2)
+      R sp, cp, sm, cm;
+      sincos_(p[1] * h, &s, &c);
+      sincos_((p[0] + p[2]) * h, &sp, &cp);
+      sincos_((p[0] - p[2]) * h, &sm, &cm);
+      M[0] = mk<R>(cp * c, -sp * c);
+      M[1] = mk<R>(-cm * s, -sm * s);
+      M[2] = mk<R>(cm * s, -sm * s);
+      M[3] = mk<R>(cp * c, sp * c);
+      // (x, y) * (+i/2) = (-y/2, x/2);  (x, y) * (-i/2) = (y/2, -x/2)
+      D[0][0] = mk<R>(h * M[0].y, -h * M[0].x);   // d/da: -i/2, +i/2, -i/2, +i/2
+      D[0][1] = mk<R>(-h * M[1].y, h * M[1].x);
+      D[0][2] = mk<R>(h * M[2].y, -h * M[2].x);
+      D[0][3] = mk<R>(-h * M[3].y, h * M[3].x);
+      D[1][0] = mk<R>(-h * cp * s, h * sp * s);   // d/db
+      D[1][1] = mk<R>(-h * cm * c, -h * sm * c);
+      D[1][2] = mk<R>(h * cm * c, -h * sm * c);
+      D[1][3] = mk<R>(-h * cp * s, -h * sp * s);
+      D[2][0] = mk<R>(h * M[0].y, -h * M[0].x);   // d/dw: -i/2, -i/2, +i/2, +i/2
+      D[2][1] = mk<R>(h * M[1].y, -h * M[1].x);
+      D[2][2] = mk<R>(-h * M[2].y, h * M[2].x);
+      D[2][3] = mk<R>(-h * M[3].y, h * M[3].x);
+    } break;
+    default:
+      M[0] = mk<R>(1, 0); M[1] = z; M[2] = z; M[3] = mk<R>(1, 0);
+      break;
+  }
+}
+
+__device__ __forceinline__ bool kind_controlled(int kind) {
+  return kind == TQ_G_CRX || kind == TQ_G_CRY || kind == TQ_G_CRZ || kind == TQ_G_CPHASE;
+}
+
+// E (Dd x Dd, Dd = 2 or 4) = embedding of a member's matrix G into the block.
+//   gdim 2: embed 0 -> acts on block qubit 0 (MSB), 1 -> block qubit 1
+//   gdim 4: embed 2 -> same qubit order, 3 -> swapped
+// `ctl`: G is the 2x2 target block of a controlled gate (control = member qubit 0); `deriv`: the
+// identity part of a controlled gate differentiates to zero.
+template <typename R>
+__device__ void embed_member(const cx<R>* G, int gdim, bool ctl, bool deriv, int embed, int Dd, cx<R>* E) {
+  const cx<R> z = mk<R>(0, 0), one = mk<R>(1, 0);
+  if (Dd == 2) {
+    for (int i = 0; i < 4; ++i) E[i] = G[i];
+    return;
+  }
+  cx<R> F[16];
+  if (ctl) {  // full 4x4 of a controlled 2x2 block, member order (control, target)
+    for (int i = 0; i < 16; ++i) F[i] = z;
+    if (!deriv) {
+      F[0] = one;
+      F[5] = one;
+    }
+    F[10] = G[0]; F[11] = G[1]; F[14] = G[2]; F[15] = G[3];
+    gdim = 4;
+  } else if (gdim == 4) {
+    for (int i = 0; i < 16; ++i) F[i] = G[i];
+  }
+  if (gdim == 2) {
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        int r0 = r >> 1, r1 = r & 1, c0 = c >> 1, c1 = c & 1;
+        if (embed == 0)
+          E[r * 4 + c] = (r1 == c1) ? G[r0 * 2 + c0] : z;
+        else
+          E[r * 4 + c] = (r0 == c0) ? G[r1 * 2 + c1] : z;
+      }
+  } else {
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        int rr = r, cc = c;
+        if (embed == 3) {
+          rr = ((r & 1) << 1) | (r >> 1);
+          cc = ((c & 1) << 1) | (c >> 1);
+        }
+        E[r * 4 + c] = F[rr * 4 + cc];
+      }
+  }
+}
+
+template <typename R>
+__device__ void matmul_small(const cx<R>* A, const cx<R>* B, int Dd, cx<R>* C) {  // C = A*B
+  for (int r = 0; r < Dd; ++r)
+    for (int c = 0; c < Dd; ++c) {
+      cx<R> acc = mk<R>(0, 0);
+      for (int k = 0; k < Dd; ++k) acc = cfma(A[r * Dd + k], B[k * Dd + c], acc);
+      C[r * Dd + c] = acc;
+    }
+}
+
+template <typename R>
+__device__ void member_eval(const MatInstr& ins, const R* params_b, const cx<R>* fixed, cx<R>* G, cx<R> (*D)[4],
+                            int* gdim, bool* ctl) {
+  if (ins.kind == TQ_G_FIXED) {
+    const int d = 1 << ins.nq;
+    for (int i = 0; i < d * d; ++i) G[i] = fixed[ins.fixed_off + i];
+    *gdim = d;
+    *ctl = false;
+    return;
+  }
+  R p[3];
+  for (int i = 0; i < 3; ++i) p[i] = ins.pidx[i] >= 0 ? params_b[ins.pidx[i]] : (R)ins.pconst[i];
+  param_gate<R>(ins.kind, p, G, D);
+  *gdim = 2;
+  *ctl = kind_controlled(ins.kind);
+}
+
+template <typename R>
+__global__ void k_materialize(const R* __restrict__ params, int n_params, int64_t batch,
+                              const MatBlock* __restrict__ blocks, int n_blocks, const MatInstr* __restrict__ instrs,
+                              const cx<R>* __restrict__ fixed, cx<R>* __restrict__ stream_f, int64_t stride_f,
+                              cx<R>* __restrict__ stream_b, int64_t stride_b, int with_deriv) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * n_blocks) return;
+  const int64_t b = t / n_blocks;
+  const MatBlock blk = blocks[(int)(t - b * n_blocks)];
+  const R* pb = params + b * n_params;
+  cx<R>* of = stream_f + b * stride_f + blk.off_f;
+  cx<R>* ob = with_deriv ? stream_b + b * stride_b + blk.off_b : nullptr;
+
+  if (blk.mode == MB_FIXED) {
+    const MatInstr& ins = instrs[blk.instr_begin];
+    for (int i = 0; i < blk.count; ++i) {
+      cx<R> v = fixed[ins.fixed_off + i];
+      of[i] = v;
+      if (ob) ob[i] = v;
+    }
+    return;
+  }
+  if (blk.mode == MB_NATIVE) {
+    const MatInstr& ins = instrs[blk.instr_begin];
+    cx<R> G[4], D[3][4];
+    int gdim;
+    bool ctl;
+    member_eval<R>(ins, pb, fixed, G, D, &gdim, &ctl);
+    if (blk.diag) {
+      of[0] = G[0];
+      of[1] = G[3];
+      if (ob) {
+        ob[0] = G[0];
+        ob[1] = G[3];
+        for (int i = 0; i < 3; ++i)
+          if (ins.dsel[i] >= 0) {
+            ob[2 + 2 * ins.dsel[i]] = D[i][0];
+            ob[3 + 2 * ins.dsel[i]] = D[i][3];
+          }
+      }
+    } else {
+      for (int i = 0; i < 4; ++i) of[i] = G[i];
+      if (ob) {
+        for (int i = 0; i < 4; ++i) ob[i] = G[i];
+        for (int i = 0; i < 3; ++i)
+          if (ins.dsel[i] >= 0)
+            for (int j = 0; j < 4; ++j) ob[4 + 4 * ins.dsel[i] + j] = D[i][j];
+      }
+    }
+    return;
+  }
+  // MB_FUSED: U = E_k ... E_1 ; dU_s = (E_k ... E_{i+1}) dE_i (E_{i-1} ... E_1)
+  const int Dd = blk.dim;
+  const int DD = Dd * Dd;
+  cx<R> U[16], E[16], T[16], G[16], D[3][4];
+  cx<R> Pre[MAX_BLOCK_DERIV][16];
+  for (int i = 0; i < DD; ++i) U[i] = mk<R>((i / Dd) == (i % Dd) ? (R)1 : (R)0, 0);
+  for (int mi = blk.instr_begin; mi < blk.instr_end; ++mi) {
+    const MatInstr& ins = instrs[mi];
+    int gdim;
+    bool ctl;
+    member_eval<R>(ins, pb, fixed, G, D, &gdim, &ctl);
+    if (ob)
+      for (int i = 0; i < 3; ++i)
+        if (ins.dsel[i] >= 0)
+          for (int j = 0; j < DD; ++j) Pre[ins.dsel[i]][j] = U[j];
+    embed_member<R>(G, gdim, ctl, false, ins.embed, Dd, E);
+    matmul_small<R>(E, U, Dd, T);
+    for (int j = 0; j < DD; ++j) U[j] = T[j];
+  }
+  for (int j = 0; j < DD; ++j) of[j] = U[j];
+  if (!ob) return;
+  for (int j = 0; j < DD; ++j) ob[j] = U[j];
+  if (blk.nderiv == 0) return;
+  cx<R> S[16];
+  for (int i = 0; i < DD; ++i) S[i] = mk<R>((i / Dd) == (i % Dd) ? (R)1 : (R)0, 0);
+  for (int mi = blk.instr_end - 1; mi >= blk.instr_begin; --mi) {
+    const MatInstr& ins = instrs[mi];
+    int gdim;
+    bool ctl;
+    member_eval<R>(ins, pb, fixed, G, D, &gdim, &ctl);
+    for (int i = 0; i < 3; ++i)
+      if (ins.dsel[i] >= 0) {
+        embed_member<R>(D[i], 2, ctl, true, ins.embed, Dd, E);
+        matmul_small<R>(E, Pre[ins.dsel[i]], Dd, T);
+        matmul_small<R>(S, T, Dd, E);
+        cx<R>* dst = ob + DD * (1 + ins.dsel[i]);
+        for (int j = 0; j < DD; ++j) dst[j] = E[j];
+      }
+    embed_member<R>(G, gdim, ctl, false, ins.embed, Dd, E);
+    matmul_small<R>(S, E, Dd, T);
+    for (int j = 0; j < DD; ++j) S[j] = T[j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// op application on shared-memory tiles
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand_ins(const OpDesc& d, uint32_t g) {
+  uint32_t idx = g;
+  if (d.nins > 0) idx = insert_zero_bit(idx, d.ins[0]);
+  if (d.nins > 1) idx = insert_zero_bit(idx, d.ins[1]);
+  if (d.nins > 2) idx = insert_zero_bit(idx, d.ins[2]);
+  if (d.nins > 3) idx = insert_zero_bit(idx, d.ins[3]);
+  return idx | d.cmask;
+}
+
+typedef cx<float> cf;
+
+__device__ __forceinline__ cf lo(const float4& v) { return mk<float>(v.x, v.y); }
+__device__ __forceinline__ cf hi(const float4& v) { return mk<float>(v.z, v.w); }
+__device__ __forceinline__ float4 pack(cf a, cf b) { return make_float4(a.x, a.y, b.x, b.y); }
+
+// ---- forward paths (ADJ: apply the conjugate transpose) -------------------------
+template <bool ADJ>
+__device__ __forceinline__ void ld2x2(const cf* M, cf* m) {
+  if (ADJ) {
+    m[0] = conj_(M[0]); m[1] = conj_(M[2]); m[2] = conj_(M[1]); m[3] = conj_(M[3]);
+  } else {
+    m[0] = M[0]; m[1] = M[1]; m[2] = M[2]; m[3] = M[3];
+  }
+}
+
+__device__ __forceinline__ void mv2(const cf* m, cf a0, cf a1, cf& b0, cf& b1) {
+  b0 = cfma(m[1], a1, cmul(m[0], a0));
+  b1 = cfma(m[3], a1, cmul(m[2], a0));
+}
+
+template <bool ADJ>
+__device__ __forceinline__ void fwd_d1v(float4* s4, const OpDesc& d, const cf* M, int m) {
+  cf mm[4];
+  ld2x2<ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  // low target bits: half of every 8-lane group starts on the partner word so the 8 lanes of one
+  // 128-bit wavefront fall into 8 distinct bank groups
+  const uint32_t sw = (d.tpos[0] < 3 && (threadIdx.x & 4)) ? tb : 0u;
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = s4[c ^ sw], y = s4[c ^ sw ^ tb];
+    if (sw) {
+      float4 t = x;
+      x = y;
+      y = t;
+    }
+    cf b0, b1, c0, c1;
+    mv2(mm, lo(x), lo(y), b0, b1);
+    mv2(mm, hi(x), hi(y), c0, c1);
+    s4[c] = pack(b0, c0);
+    s4[c | tb] = pack(b1, c1);
+  }
+}
+
+template <bool ADJ>
+__device__ __forceinline__ void fwd_d1p(float4* s4, const OpDesc& d, const cf* M, int m) {
+  cf mm[4];
+  ld2x2<ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = s4[c];
+    cf b0, b1;
+    mv2(mm, lo(x), hi(x), b0, b1);
+    s4[c] = pack(b0, b1);
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void fwd_d1s(cx<R>* s, const OpDesc& d, const cx<R>* M, int m) {
+  cx<R> m0, m1, m2, m3;
+  if (ADJ) {
+    m0 = conj_(M[0]); m1 = conj_(M[2]); m2 = conj_(M[1]); m3 = conj_(M[3]);
+  } else {
+    m0 = M[0]; m1 = M[1]; m2 = M[2]; m3 = M[3];
+  }
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a0 = s[i], a1 = s[i | tb];
+    s[i] = cfma(m1, a1, cmul(m0, a0));
+    s[i | tb] = cfma(m3, a1, cmul(m2, a0));
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void ld4x4(const cx<R>* M, cx<R>* mm) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mm[r * 4 + c] = ADJ ? conj_(M[c * 4 + r]) : M[r * 4 + c];
+}
+
+template <typename R>
+__device__ __forceinline__ void mv4(const cx<R>* mm, const cx<R>* a, cx<R>* b) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    cx<R> acc = cmul(mm[r * 4], a[0]);
+#pragma unroll
+    for (int c = 1; c < 4; ++c) acc = cfma(mm[r * 4 + c], a[c], acc);
+    b[r] = acc;
+  }
+}
+
+template <bool ADJ>
+__device__ __forceinline__ void fwd_d2v(float4* s4, const OpDesc& d, const cf* M, int m) {
+  cf mm[16];
+  ld4x4<float, ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 v0 = s4[c], v1 = s4[c | o1], v2 = s4[c | o2], v3 = s4[c | o1 | o2];
+    cf a[4] = {lo(v0), lo(v1), lo(v2), lo(v3)}, b[4];
+    cf e[4] = {hi(v0), hi(v1), hi(v2), hi(v3)}, f[4];
+    mv4<float>(mm, a, b);
+    mv4<float>(mm, e, f);
+    s4[c] = pack(b[0], f[0]);
+    s4[c | o1] = pack(b[1], f[1]);
+    s4[c | o2] = pack(b[2], f[2]);
+    s4[c | o1 | o2] = pack(b[3], f[3]);
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void fwd_d2s(cx<R>* s, const OpDesc& d, const cx<R>* M, int m) {
+  cx<R> mm[16];
+  ld4x4<R, ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a[4] = {s[i], s[i | o1], s[i | o2], s[i | o1 | o2]}, b[4];
+    mv4<R>(mm, a, b);
+    s[i] = b[0];
+    s[i | o1] = b[1];
+    s[i | o2] = b[2];
+    s[i | o1 | o2] = b[3];
+  }
+}
+
+template <bool ADJ>
+__device__ __forceinline__ void fwd_g1v(float4* s4, const OpDesc& d, const cf* M, int m) {
+  cf d0 = M[0], d1 = M[1];
+  if (ADJ) {
+    d0 = conj_(d0);
+    d1 = conj_(d1);
+  }
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const int tp = d.tpos[0];  // amplitude-bit position of the target
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = s4[c];
+    cf da, db;
+    if (tp == 0) {
+      da = d0;
+      db = d1;
+    } else {
+      da = db = ((c >> (tp - 1)) & 1u) ? d1 : d0;
+    }
+    s4[c] = pack(cmul(da, lo(x)), cmul(db, hi(x)));
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void fwd_g1s(cx<R>* s, const OpDesc& d, const cx<R>* M, int m) {
+  cx<R> d0 = M[0], d1 = M[1];
+  if (ADJ) {
+    d0 = conj_(d0);
+    d1 = conj_(d1);
+  }
+  const uint32_t ng = 1u << (m - d.nins);
+  const int tp = d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    s[i] = cmul(((i >> tp) & 1u) ? d1 : d0, s[i]);
+  }
+}
+
+// generic: dense with k targets (k <= 3) or diagonal with k targets; ins = all inserted bits (amplitude units)
+template <typename R, bool ADJ>
+__device__ void fwd_gen(cx<R>* s, const OpDesc& d, const cx<R>* M, int m, int cls) {
+  const int k = d.k;
+  const int Dd = 1 << k;
+  const uint32_t ng = 1u << (m - d.nins);
+  if (cls == OP_DIAG) {
+    for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+      const uint32_t i = expand_ins(d, g);
+      int di = 0;
+      for (int t = 0; t < k; ++t) di = (di << 1) | ((i >> d.tpos[t]) & 1u);
+      cx<R> v = M[di];
+      if (ADJ) v = conj_(v);
+      s[i] = cmul(v, s[i]);
+    }
+    return;
+  }
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a[8], b[8];
+    for (int r = 0; r < Dd; ++r) {
+      uint32_t off = 0;
+      for (int t = 0; t < k; ++t) off |= ((r >> (k - 1 - t)) & 1u) << d.tpos[t];
+      a[r] = s[i | off];
+    }
+    for (int r = 0; r < Dd; ++r) {
+      cx<R> acc = mk<R>(0, 0);
+      for (int c = 0; c < Dd; ++c) acc = cfma(ADJ ? conj_(M[c * Dd + r]) : M[r * Dd + c], a[c], acc);
+      b[r] = acc;
+    }
+    for (int r = 0; r < Dd; ++r) {
+      uint32_t off = 0;
+      for (int t = 0; t < k; ++t) off |= ((r >> (k - 1 - t)) & 1u) << d.tpos[t];
+      s[i | off] = b[r];
+    }
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void apply_op(cx<R>* s, const OpDesc& d, const cx<R>* pay, int m) {
+  const cx<R>* M = pay;
+  switch (d.path) {
+    case P_D1S: fwd_d1s<R, ADJ>(s, d, M, m); break;
+    case P_D2S: fwd_d2s<R, ADJ>(s, d, M, m); break;
+    case P_G1S: fwd_g1s<R, ADJ>(s, d, M, m); break;
+    default: fwd_gen<R, ADJ>(s, d, M, m, d.pad); break;
+  }
+}
+template <bool ADJ>
+__device__ __forceinline__ void apply_op_f32(cf* s, const OpDesc& d, const cf* pay, int m) {
+  float4* s4 = reinterpret_cast<float4*>(s);
+  switch (d.path) {
+    case P_D1V: fwd_d1v<ADJ>(s4, d, pay, m); break;
+    case P_D1P: fwd_d1p<ADJ>(s4, d, pay, m); break;
+    case P_D2V: fwd_d2v<ADJ>(s4, d, pay, m); break;
+    case P_G1V: fwd_g1v<ADJ>(s4, d, pay, m); break;
+    default: apply_op<float, ADJ>(s, d, pay, m); break;
+  }
+}
+template <typename R, bool ADJ>
+__device__ __forceinline__ void run_op(cx<R>* s, const OpDesc& d, const cx<R>* pay, int m);
+template <>
+__device__ __forceinline__ void run_op<float, false>(cf* s, const OpDesc& d, const cf* pay, int m) {
+  apply_op_f32<false>(s, d, pay, m);
+}
+template <>
+__device__ __forceinline__ void run_op<float, true>(cf* s, const OpDesc& d, const cf* pay, int m) {
+  apply_op_f32<true>(s, d, pay, m);
+}
+template <>
+__device__ __forceinline__ void run_op<double, false>(cx<double>* s, const OpDesc& d, const cx<double>* pay, int m) {
+  apply_op<double, false>(s, d, pay, m);
+}
+template <>
+__device__ __forceinline__ void run_op<double, true>(cx<double>* s, const OpDesc& d, const cx<double>* pay, int m) {
+  apply_op<double, true>(s, d, pay, m);
+}
+
+// ---- adjoint step: psi <- G^dag psi ; grad_d += Re <lambda | dG_d psi> ; lambda <- G^dag lambda -----------
+template <typename R>
+__device__ __forceinline__ void grad_flush(const R* acc, int nd, R* s_grad, uint32_t dslot) {
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) {
+    if (e < nd) {
+      R v = warp_sum(acc[e]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[dslot + e], v);
+    }
+  }
+}
+
+// one 2-amplitude group
+template <typename R>
+__device__ __forceinline__ void bwd2_group(const cx<R>* mh, const cx<R>* Dm, int nd, cx<R>& a0, cx<R>& a1, cx<R>& l0,
+                                           cx<R>& l1, R* acc) {
+  cx<R> p0 = cfma(mh[1], a1, cmul(mh[0], a0));
+  cx<R> p1 = cfma(mh[3], a1, cmul(mh[2], a0));
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) {  // predicated + unrolled: acc[] stays in registers
+    if (e < nd) {
+      const cx<R>* De = Dm + 4 * e;
+      cx<R> x0 = cfma(De[1], p1, cmul(De[0], p0));
+      cx<R> x1 = cfma(De[3], p1, cmul(De[2], p0));
+      acc[e] += re_conj_mul(l0, x0) + re_conj_mul(l1, x1);
+    }
+  }
+  cx<R> q0 = cfma(mh[1], l1, cmul(mh[0], l0));
+  cx<R> q1 = cfma(mh[3], l1, cmul(mh[2], l0));
+  a0 = p0;
+  a1 = p1;
+  l0 = q0;
+  l1 = q1;
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd4_group(const cx<R>* mh, const cx<R>* Dm, int nd, cx<R>* a, cx<R>* l, R* acc) {
+  cx<R> p[4], q[4];
+  mv4<R>(mh, a, p);
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) {
+    if (e < nd) {
+      const cx<R>* De = Dm + 16 * e;
+      R sacc = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        cx<R> x = cmul(De[r * 4], p[0]);
+#pragma unroll
+        for (int c = 1; c < 4; ++c) x = cfma(De[r * 4 + c], p[c], x);
+        sacc += re_conj_mul(l[r], x);
+      }
+      acc[e] += sacc;
+    }
+  }
+  mv4<R>(mh, l, q);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    a[r] = p[r];
+    l[r] = q[r];
+  }
+}
+
+__device__ __forceinline__ void bwd_d1v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  cf mh[4];
+  ld2x2<true>(pay, mh);
+  const cf* Dm = pay + 4;
+  const int nd = d.nderiv;
+  float acc[MAX_BLOCK_DERIV];
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0.f;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  const uint32_t sw = (d.tpos[0] < 3 && (threadIdx.x & 4)) ? tb : 0u;
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = p4[c ^ sw], y = p4[c ^ sw ^ tb], u = l4[c ^ sw], v = l4[c ^ sw ^ tb];
+    if (sw) {
+      float4 t = x; x = y; y = t;
+      t = u; u = v; v = t;
+    }
+    cf a0 = lo(x), a1 = lo(y), b0 = hi(x), b1 = hi(y);
+    cf k0 = lo(u), k1 = lo(v), n0 = hi(u), n1 = hi(v);
+    bwd2_group<float>(mh, Dm, nd, a0, a1, k0, k1, acc);
+    bwd2_group<float>(mh, Dm, nd, b0, b1, n0, n1, acc);
+    p4[c] = pack(a0, b0);
+    p4[c | tb] = pack(a1, b1);
+    l4[c] = pack(k0, n0);
+    l4[c | tb] = pack(k1, n1);
+  }
+  grad_flush<float>(acc, nd, s_grad, d.dslot);
+}
+
+__device__ __forceinline__ void bwd_d1p(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  cf mh[4];
+  ld2x2<true>(pay, mh);
+  const cf* Dm = pay + 4;
+  const int nd = d.nderiv;
+  float acc[MAX_BLOCK_DERIV];
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0.f;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = p4[c], u = l4[c];
+    cf a0 = lo(x), a1 = hi(x), k0 = lo(u), k1 = hi(u);
+    bwd2_group<float>(mh, Dm, nd, a0, a1, k0, k1, acc);
+    p4[c] = pack(a0, a1);
+    l4[c] = pack(k0, k1);
+  }
+  grad_flush<float>(acc, nd, s_grad, d.dslot);
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_d1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  cx<R> mh[4] = {conj_(pay[0]), conj_(pay[2]), conj_(pay[1]), conj_(pay[3])};
+  const cx<R>* Dm = pay + 4;
+  const int nd = d.nderiv;
+  R acc[MAX_BLOCK_DERIV];
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0;
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a0 = sp[i], a1 = sp[i | tb], l0 = sl[i], l1 = sl[i | tb];
+    bwd2_group<R>(mh, Dm, nd, a0, a1, l0, l1, acc);
+    sp[i] = a0;
+    sp[i | tb] = a1;
+    sl[i] = l0;
+    sl[i | tb] = l1;
+  }
+  grad_flush<R>(acc, nd, s_grad, d.dslot);
+}
+
+__device__ __forceinline__ void bwd_d2v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  cf mh[16];
+  ld4x4<float, true>(pay, mh);
+  const cf* Dm = pay + 16;
+  const int nd = d.nderiv;
+  float acc[MAX_BLOCK_DERIV];
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0.f;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 v0 = p4[c], v1 = p4[c | o1], v2 = p4[c | o2], v3 = p4[c | o1 | o2];
+    float4 w0 = l4[c], w1 = l4[c | o1], w2 = l4[c | o2], w3 = l4[c | o1 | o2];
+    cf a[4] = {lo(v0), lo(v1), lo(v2), lo(v3)}, l[4] = {lo(w0), lo(w1), lo(w2), lo(w3)};
+    bwd4_group<float>(mh, Dm, nd, a, l, acc);
+    cf e[4] = {hi(v0), hi(v1), hi(v2), hi(v3)}, f[4] = {hi(w0), hi(w1), hi(w2), hi(w3)};
+    bwd4_group<float>(mh, Dm, nd, e, f, acc);
+    p4[c] = pack(a[0], e[0]);
+    p4[c | o1] = pack(a[1], e[1]);
+    p4[c | o2] = pack(a[2], e[2]);
+    p4[c | o1 | o2] = pack(a[3], e[3]);
+    l4[c] = pack(l[0], f[0]);
+    l4[c | o1] = pack(l[1], f[1]);
+    l4[c | o2] = pack(l[2], f[2]);
+    l4[c | o1 | o2] = pack(l[3], f[3]);
+  }
+  grad_flush<float>(acc, nd, s_grad, d.dslot);
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_d2s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  cx<R> mh[16];
+  ld4x4<R, true>(pay, mh);
+  const cx<R>* Dm = pay + 16;
+  const int nd = d.nderiv;
+  R acc[MAX_BLOCK_DERIV];
+#pragma unroll
+  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0;
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a[4] = {sp[i], sp[i | o1], sp[i | o2], sp[i | o1 | o2]};
+    cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]};
+    bwd4_group<R>(mh, Dm, nd, a, l, acc);
+    sp[i] = a[0]; sp[i | o1] = a[1]; sp[i | o2] = a[2]; sp[i | o1 | o2] = a[3];
+    sl[i] = l[0]; sl[i | o1] = l[1]; sl[i | o2] = l[2]; sl[i | o1 | o2] = l[3];
+  }
+  grad_flush<R>(acc, nd, s_grad, d.dslot);
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_g1_amp(cx<R> dh, cx<R> dd, bool has_d, cx<R>& a, cx<R>& l, R& acc) {
+  cx<R> pa = cmul(dh, a);
+  if (has_d) acc += re_conj_mul(l, cmul(dd, pa));
+  a = pa;
+  l = cmul(dh, l);
+}
+
+__device__ __forceinline__ void bwd_g1v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  const cf h0 = conj_(pay[0]), h1 = conj_(pay[1]);
+  const bool has_d = d.nderiv > 0;
+  const cf e0 = has_d ? pay[2] : mk<float>(0, 0), e1 = has_d ? pay[3] : mk<float>(0, 0);
+  float acc = 0.f;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const int tp = d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = p4[c], u = l4[c];
+    const bool b1 = tp == 0 ? false : ((c >> (tp - 1)) & 1u);
+    const bool b2 = tp == 0 ? true : b1;
+    cf a0 = lo(x), a1 = hi(x), k0 = lo(u), k1 = hi(u);
+    bwd_g1_amp<float>(b1 ? h1 : h0, b1 ? e1 : e0, has_d, a0, k0, acc);
+    bwd_g1_amp<float>(b2 ? h1 : h0, b2 ? e1 : e0, has_d, a1, k1, acc);
+    p4[c] = pack(a0, a1);
+    l4[c] = pack(k0, k1);
+  }
+  if (has_d) grad_flush<float>(&acc, 1, s_grad, d.dslot);
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_g1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  const cx<R> h0 = conj_(pay[0]), h1 = conj_(pay[1]);
+  const bool has_d = d.nderiv > 0;
+  const cx<R> e0 = has_d ? pay[2] : mk<R>(0, 0), e1 = has_d ? pay[3] : mk<R>(0, 0);
+  R acc = 0;
+  const uint32_t ng = 1u << (m - d.nins);
+  const int tp = d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    const bool b1 = (i >> tp) & 1u;
+    cx<R> a = sp[i], l = sl[i];
+    bwd_g1_amp<R>(b1 ? h1 : h0, b1 ? e1 : e0, has_d, a, l, acc);
+    sp[i] = a;
+    sl[i] = l;
+  }
+  if (has_d) grad_flush<R>(&acc, 1, s_grad, d.dslot);
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_op_scalar(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  switch (d.path) {
+    case P_D1S: bwd_d1s<R>(sp, sl, d, pay, s_grad, m); break;
+    case P_D2S: bwd_d2s<R>(sp, sl, d, pay, s_grad, m); break;
+    case P_G1S: bwd_g1s<R>(sp, sl, d, pay, s_grad, m); break;
+    default:  // generic ops are fixed gates (no parameters): un-apply on both tiles
+      fwd_gen<R, true>(sp, d, pay, m, d.pad);
+      fwd_gen<R, true>(sl, d, pay, m, d.pad);
+      break;
+  }
+}
+template <typename R>
+__device__ __forceinline__ void bwd_op(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m);
+template <>
+__device__ __forceinline__ void bwd_op<float>(cf* sp, cf* sl, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  float4* p4 = reinterpret_cast<float4*>(sp);
+  float4* l4 = reinterpret_cast<float4*>(sl);
+  switch (d.path) {
+    case P_D1V: bwd_d1v(p4, l4, d, pay, s_grad, m); break;
+    case P_D1P: bwd_d1p(p4, l4, d, pay, s_grad, m); break;
+    case P_D2V: bwd_d2v(p4, l4, d, pay, s_grad, m); break;
+    case P_G1V: bwd_g1v(p4, l4, d, pay, s_grad, m); break;
+    default: bwd_op_scalar<float>(sp, sl, d, pay, s_grad, m); break;
+  }
+}
+template <>
+__device__ __forceinline__ void bwd_op<double>(cx<double>* sp, cx<double>* sl, const OpDesc& d, const cx<double>* pay,
+                                               double* s_grad, int m) {
+  bwd_op_scalar<double>(sp, sl, d, pay, s_grad, m);
+}
+
+// ---------------------------------------------------------------------------
+// chunked op stream: descriptors + payload prefetched with cp.async into a 2-deep ring
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+struct StreamRef {
+  const OpDesc* ops;        // descriptors of the whole direction (global)
+  const ChunkInfo* chunks;  // chunk table of this sweep (global)
+  int32_t n_chunks;
+};
+
+template <typename R>
+struct Ring {
+  OpDesc* desc[2];
+  cx<R>* pay[2];
+  ChunkInfo* table;  // staged chunk table (first MAX_CHUNKS_SMEM entries)
+};
+
+template <typename R>
+__device__ __forceinline__ Ring<R> ring_carve(unsigned char* base) {
+  Ring<R> r;
+  r.desc[0] = reinterpret_cast<OpDesc*>(base);
+  r.desc[1] = r.desc[0] + CHUNK_OPS;
+  r.pay[0] = reinterpret_cast<cx<R>*>(base + 2 * CHUNK_OPS * sizeof(OpDesc));
+  r.pay[1] = reinterpret_cast<cx<R>*>(base + 2 * CHUNK_OPS * sizeof(OpDesc) + CHUNK_PAY_BYTES);
+  r.table = reinterpret_cast<ChunkInfo*>(base + 2 * CHUNK_OPS * sizeof(OpDesc) + 2 * CHUNK_PAY_BYTES);
+  return r;
+}
+constexpr int RING_BYTES = 2 * CHUNK_OPS * 32 + 2 * CHUNK_PAY_BYTES + MAX_CHUNKS_SMEM * 16;
+
+template <typename R>
+__device__ __forceinline__ ChunkInfo chunk_info(const Ring<R>& ring, const StreamRef& st, int c) {
+  return c < MAX_CHUNKS_SMEM ? ring.table[c] : st.chunks[c];
+}
+
+template <typename R>
+__device__ __forceinline__ void ring_issue(const Ring<R>& ring, const StreamRef& st, const cx<R>* pay_b, int c) {
+  // payload offsets are multiples of 16 bytes by construction (host pads every op)
+  const ChunkInfo ci = chunk_info<R>(ring, st, c);
+  const int buf = c & 1;
+  const char* dsrc = reinterpret_cast<const char*>(st.ops + ci.op_begin);
+  char* ddst = reinterpret_cast<char*>(ring.desc[buf]);
+  const int dbytes = ci.op_count * (int)sizeof(OpDesc);
+  for (int o = threadIdx.x * 16; o < dbytes; o += blockDim.x * 16) cp_async16(ddst + o, dsrc + o);
+  const char* psrc = reinterpret_cast<const char*>(pay_b + ci.pay_begin);
+  char* pdst = reinterpret_cast<char*>(ring.pay[buf]);
+  const int pbytes = ci.pay_count * (int)sizeof(cx<R>);
+  for (int o = threadIdx.x * 16; o < pbytes; o += blockDim.x * 16) cp_async16(pdst + o, psrc + o);
+  cp_async_commit();
+}
+
+template <typename R>
+__device__ __forceinline__ void ring_start(const Ring<R>& ring, const StreamRef& st, const cx<R>* pay_b) {
+  const int nt = st.n_chunks < MAX_CHUNKS_SMEM ? st.n_chunks : MAX_CHUNKS_SMEM;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) ring.table[i] = st.chunks[i];
+  __syncthreads();
+  if (st.n_chunks > 0) ring_issue<R>(ring, st, pay_b, 0);
+}
+
+// ---------------------------------------------------------------------------
+// measurements / cotangent seed (unchanged semantics: pytorch_backend.py:393-498)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gather_bits(uint32_t i, const int8_t* pos, int nq) {
+  uint32_t r = 0;
+  for (int t = 0; t < nq; ++t) r = (r << 1) | ((i >> pos[t]) & 1u);
+  return r;
+}
+
+template <typename R>
+__device__ __forceinline__ cx<R> obs_row_dot(const cx<R>* __restrict__ arr, uint32_t i, const DevMeas& ms,
+                                             const cx<R>* __restrict__ O) {
+  const int nq = ms.nq;
+  const int Dd = 1 << nq;
+  uint32_t r = gather_bits(i, ms.pos, nq);
+  uint32_t base = i;
+  for (int t = 0; t < nq; ++t) base &= ~(1u << ms.pos[t]);
+  cx<R> acc = mk<R>(0, 0);
+  for (int j = 0; j < Dd; ++j) {
+    uint32_t idx = base;
+    for (int t = 0; t < nq; ++t) idx |= ((j >> (nq - 1 - t)) & 1u) << ms.pos[t];
+    acc = cfma(O[r * Dd + j], arr[idx], acc);
+  }
+  return acc;
+}
+
+template <typename R>
+__device__ void measure_block(const cx<R>* __restrict__ arr, uint32_t i0, uint32_t cnt,
+                              const DevMeas* __restrict__ meas, int n_meas, const cx<R>* __restrict__ fixed,
+                              R* __restrict__ out_b, R* s_acc, bool atomic_out) {
+  for (int mi = 0; mi < n_meas; ++mi) {
+    const DevMeas& ms = meas[mi];
+    if (ms.kind == TQ_M_EXPVAL) {
+      R acc = 0;
+      if (ms.flags & TQ_MF_ZSTRING) {
+        const uint32_t zm = ms.zmask;
+        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+          uint32_t i = i0 + j;
+          cx<R> a = arr[i];
+          R p = a.x * a.x + a.y * a.y;
+          acc += (__popc(i & zm) & 1) ? -p : p;
+        }
+      } else {
+        const cx<R>* O = fixed + ms.mat_off;
+        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+          uint32_t i = i0 + j;
+          acc += re_conj_mul(arr[i], obs_row_dot<R>(arr, i, ms, O));
+        }
+      }
+      acc = warp_sum(acc);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[ms.slot_base], acc);
+    } else if (ms.kind == TQ_M_PROBS) {
+      if (ms.slot_base >= 0) {
+        const int nb = 1 << ms.nq;
+        for (int bin = 0; bin < nb; ++bin) {
+          R acc = 0;
+          for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+            uint32_t i = i0 + j;
+            if ((int)gather_bits(i, ms.pos, ms.nq) == bin) {
+              cx<R> a = arr[i];
+              acc += a.x * a.x + a.y * a.y;
+            }
+          }
+          acc = warp_sum(acc);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[ms.slot_base + bin], acc);
+        }
+      } else {
+        R* o = out_b + ms.out_off;
+        for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+          uint32_t i = i0 + j;
+          cx<R> a = arr[i];
+          R p = a.x * a.x + a.y * a.y;
+          if (ms.nq == 0)
+            o[i] = p;
+          else
+            atomicAdd(&o[gather_bits(i, ms.pos, ms.nq)], p);
+        }
+      }
+    } else {
+      R* o = out_b + ms.out_off;
+      for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+        uint32_t i = i0 + j;
+        cx<R> a = arr[i];
+        o[2 * (size_t)i] = a.x;
+        o[2 * (size_t)i + 1] = a.y;
+      }
+    }
+  }
+  __syncthreads();
+  for (int mi = 0; mi < n_meas; ++mi) {
+    const DevMeas& ms = meas[mi];
+    if (ms.slot_base < 0) continue;
+    int ns = ms.kind == TQ_M_EXPVAL ? 1 : (1 << ms.nq);
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+      R v = s_acc[ms.slot_base + s];
+      if (atomic_out)
+        atomicAdd(&out_b[ms.out_off + s], v);
+      else
+        out_b[ms.out_off + s] = v;
+    }
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ cx<R> seed_amp(const cx<R>* __restrict__ arr, uint32_t i,
+                                          const DevMeas* __restrict__ meas, int n_meas,
+                                          const cx<R>* __restrict__ fixed, const R* __restrict__ dy_b) {
+  cx<R> g = mk<R>(0, 0);
+  const cx<R> a = arr[i];
+  for (int mi = 0; mi < n_meas; ++mi) {
+    const DevMeas& ms = meas[mi];
+    if (ms.kind == TQ_M_EXPVAL) {
+      R w = (R)2 * dy_b[ms.out_off];
+      if (ms.flags & TQ_MF_ZSTRING) {
+        if (__popc(i & ms.zmask) & 1) w = -w;
+        g.x += w * a.x;
+        g.y += w * a.y;
+      } else {
+        cx<R> v = obs_row_dot<R>(arr, i, ms, fixed + ms.mat_off);
+        g.x += w * v.x;
+        g.y += w * v.y;
+      }
+    } else if (ms.kind == TQ_M_PROBS) {
+      uint32_t bin = ms.nq == 0 ? i : gather_bits(i, ms.pos, ms.nq);
+      R w = (R)2 * dy_b[ms.out_off + bin];
+      g.x += w * a.x;
+      g.y += w * a.y;
+    } else {
+      g.x += dy_b[ms.out_off + 2 * (size_t)i];
+      g.y += dy_b[ms.out_off + 2 * (size_t)i + 1];
+    }
+  }
+  return g;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+template <typename R>
+struct FwdArgs {
+  cx<R>* psi;
+  const cx<R>* init_state;
+  const cx<R>* stream;  // forward payload stream [batch, stride]
+  const cx<R>* fixed;
+  const DevMeas* meas;
+  R* out;
+  int64_t out_reals;
+  int64_t stride;
+  StreamRef st;
+  int32_t n_meas, n_slots;
+  int32_t flags;
+  int32_t tiles_log2;
+  Geom geom;
+};
+
+extern __shared__ __align__(16) unsigned char tq_smem[];
+
+template <typename R>
+__device__ __forceinline__ void run_stream_fwd(cx<R>* sm, const Ring<R>& ring, const StreamRef& st, const cx<R>* pay_b,
+                                               int m) {
+  ring_start<R>(ring, st, pay_b);
+  for (int c = 0; c < st.n_chunks; ++c) {
+    cp_async_wait_all();
+    __syncthreads();  // chunk c landed; everyone is done with the buffer chunk c+1 will overwrite
+    if (c + 1 < st.n_chunks) ring_issue<R>(ring, st, pay_b, c + 1);
+    const ChunkInfo ci = chunk_info<R>(ring, st, c);
+    const OpDesc* dd = ring.desc[c & 1];
+    const cx<R>* pp = ring.pay[c & 1];
+    for (uint32_t o = 0; o < ci.op_count; ++o) {
+      const OpDesc d = dd[o];
+      run_op<R, false>(sm, d, pp + (d.pay_off - ci.pay_begin), m);
+      __syncthreads();
+    }
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256, 2) k_sweep_fwd(const __grid_constant__ FwdArgs<R> a) {
+  const int m = a.geom.m;
+  const uint32_t tile_n = 1u << m;
+  cx<R>* sm = reinterpret_cast<cx<R>*>(tq_smem);
+  Ring<R> ring = ring_carve<R>(tq_smem + sizeof(cx<R>) * tile_n);
+  const int64_t b = (int64_t)(blockIdx.x >> a.tiles_log2);
+  const uint32_t tile = blockIdx.x & ((1u << a.tiles_log2) - 1u);
+  const uint32_t tbase = dep_tile(a.geom, tile);
+  const size_t sv = (size_t)1 << a.geom.n;
+  cx<R>* psi_b = a.psi ? a.psi + (size_t)b * sv : nullptr;
+
+  if (a.flags & SW_INIT) {
+    if (a.init_state) {
+      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = a.init_state[tbase | dep_local(a.geom, l)];
+    } else {
+      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = mk<R>(0, 0);
+      __syncthreads();
+      if (threadIdx.x == 0 && tbase == 0) sm[0] = mk<R>(1, 0);
+    }
+  } else {
+    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = psi_b[tbase | dep_local(a.geom, l)];
+  }
+  run_stream_fwd<R>(sm, ring, a.st, a.stream + b * a.stride, m);  // begins with a __syncthreads
+
+  if (a.flags & SW_STORE) {
+    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) psi_b[tbase | dep_local(a.geom, l)] = sm[l];
+  }
+  if (a.flags & SW_MEASURE) {
+    R* s_acc = reinterpret_cast<R*>(tq_smem + sizeof(cx<R>) * tile_n + RING_BYTES);
+    for (int s = threadIdx.x; s < a.n_slots; s += blockDim.x) s_acc[s] = 0;
+    __syncthreads();
+    measure_block<R>(sm, 0, tile_n, a.meas, a.n_meas, a.fixed, a.out + (size_t)b * a.out_reals, s_acc, false);
+  }
+}
+
+template <typename R>
+struct MeasArgs {
+  const cx<R>* psi;
+  const cx<R>* fixed;
+  const DevMeas* meas;
+  R* out;
+  int64_t out_reals;
+  int32_t n_meas, n_slots, n;
+  int32_t chunk_log2;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ MeasArgs<R> a) {
+  R* s_acc = reinterpret_cast<R*>(tq_smem);
+  const int cl = a.n - a.chunk_log2;
+  const int64_t b = (int64_t)(blockIdx.x >> cl);
+  const uint32_t chunk = blockIdx.x & ((1u << cl) - 1u);
+  for (int s = threadIdx.x; s < a.n_slots; s += blockDim.x) s_acc[s] = 0;
+  __syncthreads();
+  measure_block<R>(a.psi + ((size_t)b << a.n), chunk << a.chunk_log2, 1u << a.chunk_log2, a.meas, a.n_meas,
+                   a.fixed, a.out + (size_t)b * a.out_reals, s_acc, true);
+}
+
+template <typename R>
+struct SeedArgs {
+  const cx<R>* psi;
+  cx<R>* lam;
+  const cx<R>* fixed;
+  const DevMeas* meas;
+  const R* dy;
+  int64_t out_reals;
+  int64_t total;
+  int32_t n_meas, n;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_seed(const __grid_constant__ SeedArgs<R> a) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t >> a.n;
+    uint32_t i = (uint32_t)(t & (((int64_t)1 << a.n) - 1));
+    a.lam[t] = seed_amp<R>(a.psi + ((size_t)b << a.n), i, a.meas, a.n_meas, a.fixed, a.dy + b * a.out_reals);
+  }
+}
+
+template <typename R>
+struct BwdArgs {
+  cx<R>* psi;
+  cx<R>* lam;
+  const cx<R>* init_state;
+  const cx<R>* stream_f;  // forward payload stream (full mode: recompute)
+  const cx<R>* stream_b;  // backward payload stream
+  const cx<R>* fixed;
+  const DevMeas* meas;
+  const R* dy;
+  R* grad;
+  const int32_t* slot_pidx;
+  int64_t out_reals;
+  int64_t stride_f, stride_b;
+  StreamRef st_f, st_b;
+  int32_t n_meas, n_params, n_dslots;
+  int32_t flags;
+  int32_t tiles_log2;
+  Geom geom;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256, 2) k_sweep_bwd(const __grid_constant__ BwdArgs<R> a) {
+  const int m = a.geom.m;
+  const uint32_t tile_n = 1u << m;
+  cx<R>* sp = reinterpret_cast<cx<R>*>(tq_smem);
+  cx<R>* sl = sp + tile_n;
+  Ring<R> ring = ring_carve<R>(tq_smem + 2 * sizeof(cx<R>) * tile_n);
+  R* s_grad = reinterpret_cast<R*>(tq_smem + 2 * sizeof(cx<R>) * tile_n + RING_BYTES);
+  const int64_t b = (int64_t)(blockIdx.x >> a.tiles_log2);
+  const uint32_t tile = blockIdx.x & ((1u << a.tiles_log2) - 1u);
+  const uint32_t tbase = dep_tile(a.geom, tile);
+  const size_t sv = (size_t)1 << a.geom.n;
+
+  for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) s_grad[s] = 0;
+
+  if (a.flags & SW_FULL) {
+    if (a.init_state) {
+      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = a.init_state[l];
+    } else {
+      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = mk<R>(0, 0);
+      __syncthreads();
+      if (threadIdx.x == 0) sp[0] = mk<R>(1, 0);
+    }
+    run_stream_fwd<R>(sp, ring, a.st_f, a.stream_f + b * a.stride_f, m);
+    const R* dy_b = a.dy + b * a.out_reals;
+    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x)
+      sl[l] = seed_amp<R>(sp, l, a.meas, a.n_meas, a.fixed, dy_b);
+  } else {
+    cx<R>* psi_b = a.psi + (size_t)b * sv;
+    cx<R>* lam_b = a.lam + (size_t)b * sv;
+    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) {
+      uint32_t gi = tbase | dep_local(a.geom, l);
+      sp[l] = psi_b[gi];
+      sl[l] = lam_b[gi];
+    }
+  }
+  __syncthreads();
+
+  const cx<R>* pay_b = a.stream_b + b * a.stride_b;
+  ring_start<R>(ring, a.st_b, pay_b);
+  for (int c = 0; c < a.st_b.n_chunks; ++c) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (c + 1 < a.st_b.n_chunks) ring_issue<R>(ring, a.st_b, pay_b, c + 1);
+    const ChunkInfo ci = chunk_info<R>(ring, a.st_b, c);
+    const OpDesc* dd = ring.desc[c & 1];
+    const cx<R>* pp = ring.pay[c & 1];
+    for (uint32_t o = 0; o < ci.op_count; ++o) {
+      const OpDesc d = dd[o];
+      bwd_op<R>(sp, sl, d, pp + (d.pay_off - ci.pay_begin), s_grad, m);
+      __syncthreads();
+    }
+  }
+
+  if (!(a.flags & SW_FULL) && (a.flags & SW_STORE)) {
+    cx<R>* psi_b = a.psi + (size_t)b * sv;
+    cx<R>* lam_b = a.lam + (size_t)b * sv;
+    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) {
+      uint32_t gi = tbase | dep_local(a.geom, l);
+      psi_b[gi] = sp[l];
+      lam_b[gi] = sl[l];
+    }
+  }
+  R* grad_b = a.grad + b * a.n_params;
+  for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) {
+    if (a.flags & SW_FULL)
+      grad_b[a.slot_pidx[s]] = s_grad[s];
+    else
+      atomicAdd(&grad_b[a.slot_pidx[s]], s_grad[s]);
+  }
+}
+
+}  // namespace tq
