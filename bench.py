@@ -300,7 +300,7 @@ def main():
     main_res = measure_workload(args.workload, args.steps, args.warmup, device, dist_on, world,
                                 do_e2e=True, do_cpu=(rank == 0 and world == 1))
     extras = {}
-    if world == 1 and args.extras:
+    if world == 1 and args.extras and args.extras != "none":
         for name in [e for e in args.extras.split(",") if e and e != args.workload]:
             r = measure_workload(name, max(2, min(5, args.steps)), 3, device, False, 1, do_e2e=False,
                                  do_cpu=os.environ.get("TQ_EXTRAS_CPU", "0") == "1")

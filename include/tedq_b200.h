@@ -167,60 +167,78 @@ int tq_sv_axes_perm(int32_t n_qubits, const int32_t* qubits, int32_t nq, int32_t
  *      tensor_network.py:850-1099, and the third-party tree.contract call sites
  *      pytorch_backend.py:276,:339 / oe_wrapper.py:59-65) -------------------- */
 
-/* Index maps.  gate_nq[g], gate_qubits[g*4+i]; meas as in tq_plan_create.
- * For measurement `which` writes, per tensor t, its rank into tensor_rank[t] and
- * its integer index ids into tensor_idx[t*8 + i] (id -> symbol via tq_tn_symbol).
- * Returns the number of tensors, or <0. out_idx gets the open indices (count in *n_out). */
-int32_t tq_tn_index_map(int32_t n_qubits, const int32_t* gate_nq, const int32_t* gate_qubits, int32_t n_gates,
-                        const tq_meas_desc* meas, int32_t which, int32_t* tensor_rank, int32_t* tensor_idx,
-                        int32_t tensor_cap, int32_t* out_idx, int32_t* n_out);
-/* unicode code point of symbol i (tensor_network.py:1109-1127) */
+#define TQ_TN_MAX_RANK 32
+
+/* unicode code point of symbol i (get_symbol, tensor_network.py:1109-1127) */
 int32_t tq_tn_symbol(int32_t i);
 
-/* One lowered pairwise-contraction step.  All extents are 2, so every tensor is
- * addressed by a bit-string; a mode permutation is a bit permutation. */
+/* Index maps of ONE measurement's network (host only, no GPU needed).
+ *   gate_nq[g], gate_qubits[g*4 + i]: the circuit's gates in order.
+ *   meas_kind: TQ_M_*; obs_nq[j] / obs_qubits[j*4 + i]: the observable tensors of an EXPVAL (one entry per
+ *   observable of a list observable); kept_qubits / n_kept: PROBS (n_kept < 0 means qubits=None).
+ * Writes tensor t's index ids, slow -> fast (the reference's list order), at
+ * tensor_idx[tensor_off[t] .. tensor_off[t+1]) and the open indices to out_idx.
+ * Returns the number of tensors, or a negative tq_status. */
+int32_t tq_tn_index_map(int32_t n_qubits, const int32_t* gate_nq, const int32_t* gate_qubits, int32_t n_gates,
+                        int32_t meas_kind, const int32_t* obs_nq, const int32_t* obs_qubits, int32_t n_obs,
+                        const int32_t* kept_qubits, int32_t n_kept, int32_t* tensor_off, int32_t* tensor_idx,
+                        int32_t tensor_cap, int32_t idx_cap, int32_t* out_idx, int32_t* n_out);
+
+/* One lowered pairwise-contraction step  C[b, m, n] = sum_k A[b, m, k] * B[b, k, n].
+ * Every extent is 2: tensors are addressed by bit strings, a mode permutation is a bit permutation.
+ * lhs_bits = physical bit positions inside A of [k..., m..., b...] (each group fast -> slow),
+ * rhs_bits = the same for B with n instead of m.  The result is dense, laid out [b | m | n] slow -> fast;
+ * out_idx[j] = index id of result bit j (fast -> slow). */
 typedef struct tq_tn_step {
-  int32_t lhs, rhs, out;  /* ssa ids: inputs 0..n_in-1, step s produces n_in+s           */
-  int32_t n_batch, n_m, n_n, n_k; /* log2 of batch / M / N / K extents                   */
-  /* for each output-side role, the bit position (0 = fastest) inside the source tensor:
-   * lhs_bits = [k bits..., m bits..., batch bits...] (fast->slow), same for rhs with n bits;
-   * the output is laid out [n bits, m bits, batch bits] fast->slow. */
-  int8_t lhs_bits[64];
-  int8_t rhs_bits[64];
-  int32_t out_idx[64];    /* index id of each output bit, fast -> slow                   */
-  int32_t out_rank;
-  int32_t conj_lhs, conj_rhs;
+  int32_t lhs, rhs;               /* ssa ids: inputs are 0..n_in-1, step s produces n_in+s */
+  int32_t n_k, n_m, n_n, n_b;     /* log2 extents                                           */
+  int8_t lhs_bits[TQ_TN_MAX_RANK];
+  int8_t rhs_bits[TQ_TN_MAX_RANK];
+  int32_t out_idx[TQ_TN_MAX_RANK];
 } tq_tn_step;
 
-/* Lower an ssa path (pairs of ssa ids) over `n_in` input tensors into steps.
- * tensor_idx uses stride 8 as above but slow -> fast order (C order, as the
- * reference lists them).  sliced[] index ids are dropped from every tensor.
- * Returns number of steps or <0. */
-int32_t tq_tn_lower(const int32_t* tensor_rank, const int32_t* tensor_idx, int32_t n_in, const int32_t* out_idx,
-                    int32_t n_out, const int32_t* ssa_path /* 2*n_steps */, int32_t n_steps,
-                    const int32_t* sliced, int32_t n_sliced, tq_tn_step* steps);
+/* Lower an ssa path over n_in input tensors into steps (host only).  sliced[] index ids become per-slice base
+ * offsets of the inputs that carry them: slice_tensor[i], slice_ord[i], slice_bit[i] (count returned in
+ * *n_slice_entries, capacity slice_cap).  final_perm[j] = bit of the last tensor that becomes output bit j
+ * (output order = out_idx listed slow -> fast).  Returns the number of steps or a negative tq_status. */
+int32_t tq_tn_lower(const int32_t* tensor_off, const int32_t* tensor_idx, int32_t n_in, const int32_t* out_idx,
+                    int32_t n_out, const int32_t* ssa_path /* 2 per step */, int32_t n_steps,
+                    const int32_t* sliced, int32_t n_sliced, tq_tn_step* steps, int32_t* slice_tensor,
+                    int32_t* slice_ord, int32_t* slice_bit, int32_t slice_cap, int32_t* n_slice_entries,
+                    int32_t* final_perm);
 
 typedef struct tq_tn_plan tq_tn_plan;
 
-/* Build an executable contraction plan. input_param_dep[t] != 0 marks inputs that differ per parameter set
- * (they carry a leading batch dimension of `batch` in tq_tn_contract). */
-int tq_tn_plan_create(const int32_t* tensor_rank, const int32_t* tensor_idx, int32_t n_in, const int32_t* out_idx,
+/* Executable contraction plan.  input_batched[t] != 0: input t differs per parameter set (it carries a
+ * leading batch dimension in tq_tn_contract). */
+int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int32_t n_in, const int32_t* out_idx,
                       int32_t n_out, const int32_t* ssa_path, int32_t n_steps, const int32_t* sliced,
-                      int32_t n_sliced, int32_t dtype, tq_tn_plan** out);
+                      int32_t n_sliced, const int32_t* input_batched, int32_t dtype, tq_tn_plan** out);
 void tq_tn_plan_destroy(tq_tn_plan* plan);
 int32_t tq_tn_plan_num_steps(const tq_tn_plan* plan);
-int32_t tq_tn_plan_num_slices(const tq_tn_plan* plan);
-double tq_tn_plan_flops(const tq_tn_plan* plan);        /* 8*M*N*K summed over steps, ONE slice */
-int32_t tq_tn_plan_width(const tq_tn_plan* plan);       /* log2 of the largest intermediate     */
-size_t tq_tn_workspace_bytes(const tq_tn_plan* plan);
+int64_t tq_tn_plan_num_slices(const tq_tn_plan* plan);
+double tq_tn_plan_flops(const tq_tn_plan* plan);  /* sum over steps of 8*2^(k+m+n+b), ONE slice, one set */
+int32_t tq_tn_plan_width(const tq_tn_plan* plan); /* log2 of the largest tensor of one slice           */
 int32_t tq_tn_plan_get_step(const tq_tn_plan* plan, int32_t s, tq_tn_step* out);
+size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
 
-/* Contract slices [slice_begin, slice_end) and ACCUMULATE their sum into `out`
- * (device, 2^n_out complex, caller zeroes it).  inputs[t] = device pointer of
- * input tensor t (C order, complex).  Multi-GPU: each rank takes a slice range
- * and the caller all-reduces `out` (one NCCL allreduce). */
-int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, int64_t slice_begin, int64_t slice_end,
-                   void* out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+/* Contract slices [slice_begin, slice_end) and ACCUMULATE their sum into out (device,
+ * [batch or 1][2^n_out] complex; the caller zeroes it).  inputs[t] = device pointer of input tensor t
+ * (C order, complex); input_strides[t] = complex entries between consecutive parameter sets of input t
+ * (0 for inputs shared by every set).  Multi-GPU: each rank takes a slice range and the
+ * caller all-reduces out with ONE ncclAllReduce (the reference's analogue is jdtensorpath's RPC slice sum,
+ * examples/qubit_rpc.py:110-126). */
+int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
+                   int64_t slice_begin, int64_t slice_end, void* out, void* workspace, size_t workspace_bytes,
+                   void* cuda_stream);
+
+/* Operand tensors of a circuit's network on the device (replaces _parse_circuit_cotengra + the arrays
+ * assembly, compiled_circuit.py:442-467, pytorch_backend.py:311-336, :524-546): for every gate of `plan`
+ * writes G (row-major [out..., in...]) and G^dagger, per parameter set.
+ *   gate_mats / adj_mats: device [batch][total] complex, gate g at offset tq_tn_gate_offset(plan, g). */
+int64_t tq_tn_gate_offset(const tq_plan* plan, int32_t gate);   /* gate == n_gates -> total entries */
+int tq_tn_operands(const tq_plan* plan, const void* params, int64_t batch, void* gate_mats, void* adj_mats,
+                   void* cuda_stream);
 
 #ifdef __cplusplus
 }

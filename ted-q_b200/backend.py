@@ -360,6 +360,22 @@ class B200Backend:
                 return self._run(flat, fn)
         return self._run(flat, fn)
 
+    def amplitude(self, bits, *params, batched=False, slice_range=None):
+        """<bits| U(params) |0...0> by sliced tensor-network contraction (BASELINE config 5).  Needs a
+        tensor-network mode backend (``tn_mode=True`` or a planner); ``bits[q]`` is the value of qubit q."""
+        if self._tn is None:
+            raise ValueError("amplitude() needs tensor-network mode: compile with tn_mode=True (or use_jdopttn=...)")
+        self.check_parameters_torch_device(params)
+        if params:
+            self._require_cuda(self._device)
+        if batched:
+            flat = torch.cat([p.reshape(p.shape[0], -1).to(self._rdtype) for p in params], dim=1)
+        else:
+            flat = self._flatten(params)
+        with torch.no_grad():
+            amp = self._tn.amplitude(flat.contiguous(), bits, slice_range)
+        return amp if batched else amp[0]
+
     def execute_host(self, params: np.ndarray, grad_out: Optional[np.ndarray] = None):
         """HOST numpy [B, P] -> (out [B, n_meas, ...], grad [B, P] or None); copies are inside the call."""
         out, grad = self.plan().execute_host(params, grad_out)

@@ -38,13 +38,15 @@ class PlanOpts(C.Structure):
     ]
 
 
+TN_MAX_RANK = 32
+
+
 class TnStep(C.Structure):
     _fields_ = [
-        ("lhs", C.c_int32), ("rhs", C.c_int32), ("out", C.c_int32),
-        ("n_batch", C.c_int32), ("n_m", C.c_int32), ("n_n", C.c_int32), ("n_k", C.c_int32),
-        ("lhs_bits", C.c_int8 * 64), ("rhs_bits", C.c_int8 * 64),
-        ("out_idx", C.c_int32 * 64), ("out_rank", C.c_int32),
-        ("conj_lhs", C.c_int32), ("conj_rhs", C.c_int32),
+        ("lhs", C.c_int32), ("rhs", C.c_int32),
+        ("n_k", C.c_int32), ("n_m", C.c_int32), ("n_n", C.c_int32), ("n_b", C.c_int32),
+        ("lhs_bits", C.c_int8 * TN_MAX_RANK), ("rhs_bits", C.c_int8 * TN_MAX_RANK),
+        ("out_idx", C.c_int32 * TN_MAX_RANK),
     ]
 
 
@@ -105,6 +107,36 @@ def lib() -> C.CDLL:
     L.tq_execute_host.restype = i32
     L.tq_sv_axes_perm.argtypes = [i32, C.POINTER(i32), i32, C.POINTER(i32), C.POINTER(i32)]
     L.tq_sv_axes_perm.restype = i32
+    pi32 = C.POINTER(i32)
+    L.tq_tn_symbol.argtypes = [i32]
+    L.tq_tn_symbol.restype = i32
+    L.tq_tn_index_map.argtypes = [i32, pi32, pi32, i32, i32, pi32, pi32, i32, pi32, i32, pi32, pi32, i32, i32, pi32, pi32]
+    L.tq_tn_index_map.restype = i32
+    L.tq_tn_lower.argtypes = [pi32, pi32, i32, pi32, i32, pi32, i32, pi32, i32, C.POINTER(TnStep), pi32, pi32, pi32,
+                              i32, pi32, pi32]
+    L.tq_tn_lower.restype = i32
+    L.tq_tn_plan_create.argtypes = [pi32, pi32, i32, pi32, i32, pi32, i32, pi32, i32, pi32, i32, C.POINTER(vp)]
+    L.tq_tn_plan_create.restype = i32
+    L.tq_tn_plan_destroy.argtypes = [vp]
+    L.tq_tn_plan_destroy.restype = None
+    L.tq_tn_plan_num_steps.argtypes = [vp]
+    L.tq_tn_plan_num_steps.restype = i32
+    L.tq_tn_plan_num_slices.argtypes = [vp]
+    L.tq_tn_plan_num_slices.restype = i64
+    L.tq_tn_plan_flops.argtypes = [vp]
+    L.tq_tn_plan_flops.restype = C.c_double
+    L.tq_tn_plan_width.argtypes = [vp]
+    L.tq_tn_plan_width.restype = i32
+    L.tq_tn_plan_get_step.argtypes = [vp, i32, C.POINTER(TnStep)]
+    L.tq_tn_plan_get_step.restype = i32
+    L.tq_tn_workspace_bytes.argtypes = [vp, i64]
+    L.tq_tn_workspace_bytes.restype = sz
+    L.tq_tn_contract.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
+    L.tq_tn_contract.restype = i32
+    L.tq_tn_gate_offset.argtypes = [vp, i32]
+    L.tq_tn_gate_offset.restype = i64
+    L.tq_tn_operands.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.tq_tn_operands.restype = i32
     if L.tq_abi_version() != 1:
         raise EngineError("libtedq_b200.so ABI version mismatch: rebuild with `python -m tedq_b200.build --force`")
     _lib = L
@@ -241,3 +273,112 @@ class Plan:
         check(lib().tq_execute_host(self.handle, params.ctypes.data, batch, out.ctypes.data, go_ptr, gp_ptr),
               "tq_execute_host")
         return out, gp
+
+
+# ---------------------------------------------------------------------------
+# tensor-network side
+# ---------------------------------------------------------------------------
+def _i32(seq):
+    seq = list(seq)
+    return (C.c_int32 * max(1, len(seq)))(*seq)
+
+
+def _flatten_inputs(inputs):
+    off = [0]
+    flat = []
+    for t in inputs:
+        flat.extend(int(i) for i in t)
+        off.append(len(flat))
+    return _i32(off), _i32(flat)
+
+
+def tn_symbol(i: int) -> str:
+    return chr(lib().tq_tn_symbol(i))
+
+
+def tn_index_map(n_qubits, gate_qubits, kind, obs_qubits=(), kept=None):
+    """C mirror of tn_index.index_maps for ONE measurement -> (inputs, output)."""
+    kinds = {"expval": 0, "probs": 1, "state": 2}
+    gnq = _i32([len(q) for q in gate_qubits])
+    gq = _i32([(list(q) + [0, 0, 0, 0])[j] for q in gate_qubits for j in range(4)])
+    onq = _i32([len(q) for q in obs_qubits])
+    oq = _i32([(list(q) + [0, 0, 0, 0])[j] for q in obs_qubits for j in range(4)])
+    kq = _i32(kept or [])
+    n_t = 2 * n_qubits + 2 * len(gate_qubits) + len(obs_qubits) + 4
+    cap_idx = 8 * n_t
+    toff = (C.c_int32 * (n_t + 1))()
+    tidx = (C.c_int32 * cap_idx)()
+    oidx = (C.c_int32 * max(1, n_qubits))()
+    nout = C.c_int32()
+    nt = lib().tq_tn_index_map(n_qubits, gnq, gq, len(gate_qubits), kinds[kind], onq, oq, len(obs_qubits), kq,
+                               -1 if kept is None else len(kept), toff, tidx, n_t, cap_idx, oidx, C.byref(nout))
+    if nt < 0:
+        check(nt, "tq_tn_index_map")
+    inputs = [[tidx[j] for j in range(toff[t], toff[t + 1])] for t in range(nt)]
+    return inputs, [oidx[j] for j in range(nout.value)]
+
+
+def _step_tuple(st: TnStep):
+    na = st.n_k + st.n_m + st.n_b
+    nb = st.n_k + st.n_n + st.n_b
+    no = st.n_m + st.n_n + st.n_b
+    return (st.lhs, st.rhs, st.n_k, st.n_m, st.n_n, st.n_b, tuple(st.lhs_bits[:na]), tuple(st.rhs_bits[:nb]),
+            tuple(st.out_idx[:no]))
+
+
+def tn_lower(inputs, output, path, sliced=()):
+    """C lowering (host only) -> (step tuples, slice entries [(tensor, ord, bit)], final_perm)."""
+    toff, tidx = _flatten_inputs(inputs)
+    n_steps = len(path)
+    steps = (TnStep * max(1, n_steps))()
+    cap = 64 * max(1, len(sliced)) + 8
+    st_, so_, sb_ = (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_int32 * cap)()
+    ne = C.c_int32()
+    fperm = (C.c_int32 * max(1, len(output)))()
+    rc = lib().tq_tn_lower(toff, tidx, len(inputs), _i32(output), len(output), _i32([x for p in path for x in p]),
+                           n_steps, _i32(sliced), len(sliced), steps, st_, so_, sb_, cap, C.byref(ne), fperm)
+    if rc < 0:
+        check(rc, "tq_tn_lower")
+    return ([_step_tuple(steps[i]) for i in range(n_steps)], [(st_[i], so_[i], sb_[i]) for i in range(ne.value)],
+            [fperm[j] for j in range(len(output))])
+
+
+class TnPlan:
+    """Owns a tq_tn_plan*."""
+
+    def __init__(self, inputs, output, path, sliced, input_batched, dtype=TQ_C64):
+        toff, tidx = _flatten_inputs(inputs)
+        handle = C.c_void_p()
+        check(lib().tq_tn_plan_create(toff, tidx, len(inputs), _i32(output), len(output),
+                                      _i32([x for p in path for x in p]), len(path), _i32(sliced), len(sliced),
+                                      _i32([1 if b else 0 for b in input_batched]), dtype, C.byref(handle)),
+              "tq_tn_plan_create")
+        self.handle = handle
+        self.n_inputs = len(inputs)
+        self.n_out = len(output)
+        self.dtype = dtype
+        self.n_slices = int(lib().tq_tn_plan_num_slices(handle))
+        self.flops = float(lib().tq_tn_plan_flops(handle))
+        self.width = int(lib().tq_tn_plan_width(handle))
+        self.n_steps = int(lib().tq_tn_plan_num_steps(handle))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and _lib is not None:
+            _lib.tq_tn_plan_destroy(h)
+            self.handle = None
+
+    def step(self, s):
+        st = TnStep()
+        check(lib().tq_tn_plan_get_step(self.handle, s, C.byref(st)), "tq_tn_plan_get_step")
+        return _step_tuple(st)
+
+    def workspace_bytes(self, batch):
+        return int(lib().tq_tn_workspace_bytes(self.handle, batch))
+
+    def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
+        n = self.n_inputs
+        ptrs = (C.c_void_p * n)(*input_ptrs)
+        strides = (C.c_int64 * n)(*input_strides)
+        check(lib().tq_tn_contract(self.handle, ptrs, strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes,
+                                   stream), "tq_tn_contract")

@@ -95,6 +95,9 @@ struct tq_plan {
   MatInstr* d_minstrs = nullptr;
   DevMeas* d_meas = nullptr;
   int32_t* d_slot_pidx = nullptr;
+  std::vector<GateT> gate_t;
+  int64_t gate_t_total = 0;
+  GateT* d_gate_t = nullptr;
   // scratch for tq_execute_host
   void* h_dev = nullptr;
   size_t h_dev_bytes = 0;
@@ -370,6 +373,31 @@ static int upload_complex(const zc* src, size_t count, int dtype, void** dptr) {
   return TQ_OK;
 }
 
+// host mirror of the device embedding (tq_sv_kernels.cuh: embed_elem) for constant folding
+static void host_embed(const zc* G, int gdim, int embed, int Dd, zc* E) {
+  if (Dd == 2) {
+    for (int i = 0; i < 4; ++i) E[i] = G[i];
+    return;
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      const int r0 = r >> 1, r1 = r & 1, c0 = c >> 1, c1 = c & 1;
+      if (gdim == 2) {
+        if (embed == 0)
+          E[r * 4 + c] = (r1 == c1) ? G[r0 * 2 + c0] : zc(0, 0);
+        else
+          E[r * 4 + c] = (r0 == c0) ? G[r1 * 2 + c1] : zc(0, 0);
+      } else {
+        int rr = r, cc = c;
+        if (embed == 3) {
+          rr = (r1 << 1) | r0;
+          cc = (c1 << 1) | c0;
+        }
+        E[r * 4 + c] = G[rr * 4 + cc];
+      }
+    }
+}
+
 static int block_pay_entries(int count, int nderiv, bool backward) {
   int e = count * (1 + (backward ? nderiv : 0));
   return (e + 1) & ~1;  // 16-byte granularity for complex64
@@ -411,6 +439,7 @@ void tq_plan_destroy(tq_plan* p) {
   cudaFree(p->d_minstrs);
   cudaFree(p->d_meas);
   cudaFree(p->d_slot_pidx);
+  cudaFree(p->d_gate_t);
   cudaFree(p->h_dev);
   if (p->h_stream) cudaStreamDestroy(p->h_stream);
   delete p;
@@ -493,9 +522,9 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
                  "gate %d: matrix outside pool", gi);
       std::vector<zc> red;
       classify_fixed(zpool + g.matrix_off, g.nq, h.qubits, h, red);
+      h.full_off = (int)p->fixed.size();
+      p->fixed.insert(p->fixed.end(), zpool + g.matrix_off, zpool + g.matrix_off + D * D);
       if (!h.noop) {
-        h.full_off = (int)p->fixed.size();
-        p->fixed.insert(p->fixed.end(), zpool + g.matrix_off, zpool + g.matrix_off + D * D);
         h.red_off = (int)p->fixed.size();
         h.red_count = (int)red.size();
         p->fixed.insert(p->fixed.end(), red.begin(), red.end());
@@ -535,6 +564,27 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
         ++h.ntrain;
       }
     }
+  }
+
+  // ---- operand table for the tensor-network path (every gate as a full [out..., in...] tensor) ------
+  {
+    int64_t off = 0;
+    for (int gi = 0; gi < n_gates; ++gi) {
+      const HostGate& g = p->gates[gi];
+      GateT t;
+      memset(&t, 0, sizeof(t));
+      t.kind = g.kind;
+      t.nq = g.nq;
+      t.fixed_off = g.full_off;
+      t.out_off = off;
+      for (int i = 0; i < 3; ++i) {
+        t.pidx[i] = g.pidx[i];
+        t.pconst[i] = g.pconst[i];
+      }
+      p->gate_t.push_back(t);
+      off += (int64_t)1 << (2 * g.nq);
+    }
+    p->gate_t_total = off;
   }
 
   // ---- fusion: runs of gates inside one qubit or one qubit pair become one dense block -------------
@@ -609,13 +659,59 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     mb.instr_begin = (int)p->minstrs.size();
     int dcount = 0;
     const bool single = b.members.size() == 1;
+    const int Dd_blk = 1 << (int)b.qubits.size();
+    std::vector<zc> fold;  // running product of consecutive FIXED members (host, double precision)
+    int n_instr = 0;
+    auto flush_fold = [&]() {
+      if (fold.empty()) return;
+      MatInstr mi;
+      memset(&mi, 0, sizeof(mi));
+      mi.kind = TQ_G_FIXED;
+      mi.nq = (int)b.qubits.size();
+      mi.embed = Dd_blk == 4 ? 2 : 0;
+      mi.fixed_off = (int)p->fixed.size();
+      for (int i = 0; i < 3; ++i) mi.pidx[i] = mi.dsel[i] = -1;
+      p->fixed.insert(p->fixed.end(), fold.begin(), fold.end());
+      if (p->fixed.size() & 1) p->fixed.push_back(zc(0, 0));
+      p->minstrs.push_back(mi);
+      ++n_instr;
+      fold.clear();
+    };
     for (int gi : b.members) {
       const HostGate& g = p->gates[gi];
+      int embed = 0;
+      if (!single) {
+        if (b.qubits.size() == 1) {
+          embed = 0;
+        } else if (g.nq == 1) {
+          embed = g.qubits[0] == b.qubits[0] ? 0 : 1;
+        } else {
+          embed = g.qubits[0] == b.qubits[0] ? 2 : 3;
+        }
+      }
+      if (!single && g.kind == TQ_G_FIXED) {
+        zc E[16], T[16];
+        host_embed(p->fixed.data() + g.full_off, 1 << g.nq, embed, Dd_blk, E);
+        if (fold.empty()) {
+          fold.assign(E, E + Dd_blk * Dd_blk);
+        } else {
+          for (int r = 0; r < Dd_blk; ++r)
+            for (int c = 0; c < Dd_blk; ++c) {
+              zc acc(0, 0);
+              for (int k = 0; k < Dd_blk; ++k) acc += E[r * Dd_blk + k] * fold[k * Dd_blk + c];
+              T[r * Dd_blk + c] = acc;
+            }
+          fold.assign(T, T + Dd_blk * Dd_blk);
+        }
+        continue;
+      }
+      flush_fold();
       MatInstr mi;
       memset(&mi, 0, sizeof(mi));
       mi.kind = g.kind;
       mi.nq = g.nq;
       mi.fixed_off = single ? g.red_off : g.full_off;
+      mi.embed = embed;
       for (int i = 0; i < 3; ++i) {
         mi.pidx[i] = g.pidx[i];
         mi.pconst[i] = g.pconst[i];
@@ -625,17 +721,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
           mi.dsel[i] = dcount++;
         }
       }
-      if (!single) {
-        if (b.qubits.size() == 1) {
-          mi.embed = 0;
-        } else if (g.nq == 1) {
-          mi.embed = g.qubits[0] == b.qubits[0] ? 0 : 1;
-        } else {
-          mi.embed = g.qubits[0] == b.qubits[0] ? 2 : 3;
-        }
-      }
       p->minstrs.push_back(mi);
+      ++n_instr;
     }
+    flush_fold();
     mb.instr_end = (int)p->minstrs.size();
     mb.nderiv = b.nderiv;
     if (single) {
@@ -653,7 +742,8 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       b.controls.clear();
       mb.dim = 1 << (int)b.qubits.size();
       b.count = mb.dim * mb.dim;
-      mb.mode = MB_FUSED;
+      // a run of fixed gates folds into one constant matrix: nothing to compute per parameter set
+      mb.mode = (n_instr == 1 && p->minstrs.back().kind == TQ_G_FIXED) ? MB_FIXED : MB_FUSED;
     }
     mb.count = b.count;
     b.mat_block = (int)p->mblocks.size();
@@ -795,6 +885,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   if ((rc = upload(p->minstrs, &p->d_minstrs))) return rc;
   if ((rc = upload(p->dmeas, &p->d_meas))) return rc;
   if ((rc = upload(slot_pidx, &p->d_slot_pidx))) return rc;
+  if ((rc = upload(p->gate_t, &p->d_gate_t))) return rc;
   *out = P.release();
   return TQ_OK;
 }
@@ -888,8 +979,8 @@ static int run_materialize(const tq_plan* p, const void* params, int64_t B, char
                            int with_deriv, cudaStream_t st) {
   const int nbk = (int)p->mblocks.size();
   if (nbk == 0) return TQ_OK;
-  int64_t total = B * nbk;
-  int threads = 64;
+  int64_t total = B * nbk * MAT_LANES;
+  int threads = 128;
   int64_t blocks = (total + threads - 1) / threads;
   k_materialize<R><<<(unsigned)blocks, threads, 0, st>>>(
       (const R*)params, p->n_params, B, p->d_mblocks, nbk, p->d_minstrs, (const cx<R>*)p->d_fixed,
@@ -1118,6 +1209,39 @@ int tq_execute_host(tq_plan* p, const void* params, int64_t batch, void* out, co
     TQ_CUDA_OK(cudaMemcpyAsync(grad_params, d_gparams, (size_t)batch * p->n_params * rs, cudaMemcpyDeviceToHost, st));
   }
   TQ_CUDA_OK(cudaStreamSynchronize(st));
+  return TQ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// operand tensors for the tensor-network path
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int64_t tq_tn_gate_offset(const tq_plan* p, int32_t gate) {
+  if (!p || gate < 0 || gate > (int)p->gate_t.size()) return -1;
+  return gate == (int)p->gate_t.size() ? p->gate_t_total : p->gate_t[gate].out_off;
+}
+
+int tq_tn_operands(const tq_plan* p, const void* params, int64_t batch, void* gate_mats, void* adj_mats,
+                   void* stream) {
+  TQ_REQUIRE(p && gate_mats && adj_mats && batch > 0, TQ_E_INVALID, "tq_tn_operands: null argument");
+  TQ_REQUIRE(params || p->n_params == 0, TQ_E_INVALID, "tq_tn_operands: params is null");
+  const int ng = (int)p->gate_t.size();
+  if (ng == 0) return TQ_OK;
+  const int64_t total = batch * ng;
+  const int threads = 128;
+  const int64_t blocks = (total + threads - 1) / threads;
+  if (p->dtype == TQ_C64)
+    k_gate_tensors<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        (const float*)params, p->n_params, batch, p->d_gate_t, ng, (const cx<float>*)p->d_fixed,
+        (cx<float>*)gate_mats, (cx<float>*)adj_mats, p->gate_t_total);
+  else
+    k_gate_tensors<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        (const double*)params, p->n_params, batch, p->d_gate_t, ng, (const cx<double>*)p->d_fixed,
+        (cx<double>*)gate_mats, (cx<double>*)adj_mats, p->gate_t_total);
+  TQ_CUDA_OK(cudaGetLastError());
   return TQ_OK;
 }
 

@@ -171,77 +171,63 @@ __device__ __forceinline__ bool kind_controlled(int kind) {
   return kind == TQ_G_CRX || kind == TQ_G_CRY || kind == TQ_G_CRZ || kind == TQ_G_CPHASE;
 }
 
-// E (Dd x Dd, Dd = 2 or 4) = embedding of a member's matrix G into the block.
-//   gdim 2: embed 0 -> acts on block qubit 0 (MSB), 1 -> block qubit 1
-//   gdim 4: embed 2 -> same qubit order, 3 -> swapped
-// `ctl`: G is the 2x2 target block of a controlled gate (control = member qubit 0); `deriv`: the
-// identity part of a controlled gate differentiates to zero.
+// One (parameter set, block) item is handled by a 16-lane group: lane e owns element (e / Dd, e % Dd)
+// of every Dd x Dd matrix (Dd = 2 or 4), products go through intra-group shuffles.
+constexpr int MAT_LANES = 16;
+
 template <typename R>
-__device__ void embed_member(const cx<R>* G, int gdim, bool ctl, bool deriv, int embed, int Dd, cx<R>* E) {
-  const cx<R> z = mk<R>(0, 0), one = mk<R>(1, 0);
-  if (Dd == 2) {
-    for (int i = 0; i < 4; ++i) E[i] = G[i];
-    return;
+__device__ __forceinline__ cx<R> shfl16(cx<R> v, int src, unsigned mask) {
+  return mk<R>(__shfl_sync(mask, v.x, src, MAT_LANES), __shfl_sync(mask, v.y, src, MAT_LANES));
+}
+
+// my element of A*B, where a / b are my elements of A / B
+template <typename R>
+__device__ __forceinline__ cx<R> mm_elem(cx<R> a, cx<R> b, int Dd, int r, int c, unsigned mask) {
+  cx<R> acc = mk<R>(0, 0);
+  for (int k = 0; k < 4; ++k) {  // Dd <= 4; every lane of the group runs all 4 shuffles
+    cx<R> x = shfl16(a, (r * Dd + k) & 15, mask);
+    cx<R> y = shfl16(b, (k * Dd + c) & 15, mask);
+    if (k < Dd) acc = cfma(x, y, acc);
   }
-  cx<R> F[16];
-  if (ctl) {  // full 4x4 of a controlled 2x2 block, member order (control, target)
-    for (int i = 0; i < 16; ++i) F[i] = z;
-    if (!deriv) {
-      F[0] = one;
-      F[5] = one;
-    }
-    F[10] = G[0]; F[11] = G[1]; F[14] = G[2]; F[15] = G[3];
-    gdim = 4;
-  } else if (gdim == 4) {
-    for (int i = 0; i < 16; ++i) F[i] = G[i];
-  }
-  if (gdim == 2) {
-    for (int r = 0; r < 4; ++r)
-      for (int c = 0; c < 4; ++c) {
-        int r0 = r >> 1, r1 = r & 1, c0 = c >> 1, c1 = c & 1;
-        if (embed == 0)
-          E[r * 4 + c] = (r1 == c1) ? G[r0 * 2 + c0] : z;
-        else
-          E[r * 4 + c] = (r0 == c0) ? G[r1 * 2 + c1] : z;
-      }
-  } else {
-    for (int r = 0; r < 4; ++r)
-      for (int c = 0; c < 4; ++c) {
-        int rr = r, cc = c;
-        if (embed == 3) {
-          rr = ((r & 1) << 1) | (r >> 1);
-          cc = ((c & 1) << 1) | (c >> 1);
-        }
-        E[r * 4 + c] = F[rr * 4 + cc];
-      }
-  }
+  return acc;
 }
 
 template <typename R>
-__device__ void matmul_small(const cx<R>* A, const cx<R>* B, int Dd, cx<R>* C) {  // C = A*B
-  for (int r = 0; r < Dd; ++r)
-    for (int c = 0; c < Dd; ++c) {
-      cx<R> acc = mk<R>(0, 0);
-      for (int k = 0; k < Dd; ++k) acc = cfma(A[r * Dd + k], B[k * Dd + c], acc);
-      C[r * Dd + c] = acc;
-    }
+__device__ __forceinline__ cx<R> pick4(const cx<R>* G, int i) {
+  cx<R> v = G[0];
+  if (i == 1) v = G[1];
+  if (i == 2) v = G[2];
+  if (i == 3) v = G[3];
+  return v;
 }
 
+// Element (r, c) of the Dd x Dd embedding of one member gate.
+//   G2: the member's 2x2 (1-qubit gate, or target block of a controlled gate when ctl)
+//   fx: FIXED member, full matrix in the pool (gdim = 2 or 4)
+//   embed: gdim 2 -> 0 acts on block qubit 0 (MSB), 1 on block qubit 1; gdim 4 -> 2 same order, 3 swapped
 template <typename R>
-__device__ void member_eval(const MatInstr& ins, const R* params_b, const cx<R>* fixed, cx<R>* G, cx<R> (*D)[4],
-                            int* gdim, bool* ctl) {
-  if (ins.kind == TQ_G_FIXED) {
-    const int d = 1 << ins.nq;
-    for (int i = 0; i < d * d; ++i) G[i] = fixed[ins.fixed_off + i];
-    *gdim = d;
-    *ctl = false;
-    return;
+__device__ __forceinline__ cx<R> embed_elem(const cx<R>* G2, const cx<R>* fx, int gdim, bool ctl, bool deriv,
+                                            int embed, int Dd, int r, int c) {
+  const cx<R> z = mk<R>(0, 0);
+  if (Dd == 2) return fx ? fx[r * 2 + c] : pick4(G2, r * 2 + c);
+  if (gdim == 2 && !ctl) {
+    const int r0 = r >> 1, r1 = r & 1, c0 = c >> 1, c1 = c & 1;
+    if (embed == 0) {
+      if (r1 != c1) return z;
+      return fx ? fx[r0 * 2 + c0] : pick4(G2, r0 * 2 + c0);
+    }
+    if (r0 != c0) return z;
+    return fx ? fx[r1 * 2 + c1] : pick4(G2, r1 * 2 + c1);
   }
-  R p[3];
-  for (int i = 0; i < 3; ++i) p[i] = ins.pidx[i] >= 0 ? params_b[ins.pidx[i]] : (R)ins.pconst[i];
-  param_gate<R>(ins.kind, p, G, D);
-  *gdim = 2;
-  *ctl = kind_controlled(ins.kind);
+  int rr = r, cc = c;
+  if (embed == 3) {
+    rr = ((r & 1) << 1) | (r >> 1);
+    cc = ((c & 1) << 1) | (c >> 1);
+  }
+  if (!ctl) return fx[rr * 4 + cc];
+  // controlled: diag(I, G2) in member order (control, target); the identity part has zero derivative
+  if (rr < 2 || cc < 2) return (rr == cc && !deriv) ? mk<R>(1, 0) : z;
+  return pick4(G2, (rr - 2) * 2 + (cc - 2));
 }
 
 template <typename R>
@@ -249,17 +235,20 @@ __global__ void k_materialize(const R* __restrict__ params, int n_params, int64_
                               const MatBlock* __restrict__ blocks, int n_blocks, const MatInstr* __restrict__ instrs,
                               const cx<R>* __restrict__ fixed, cx<R>* __restrict__ stream_f, int64_t stride_f,
                               cx<R>* __restrict__ stream_b, int64_t stride_b, int with_deriv) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= batch * n_blocks) return;
-  const int64_t b = t / n_blocks;
-  const MatBlock blk = blocks[(int)(t - b * n_blocks)];
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = t / MAT_LANES;
+  const int e = (int)(t % MAT_LANES);
+  if (item >= batch * n_blocks) return;  // whole 16-lane groups leave together
+  const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+  const int64_t b = item / n_blocks;
+  const MatBlock blk = blocks[(int)(item - b * n_blocks)];
   const R* pb = params + b * n_params;
   cx<R>* of = stream_f + b * stride_f + blk.off_f;
   cx<R>* ob = with_deriv ? stream_b + b * stride_b + blk.off_b : nullptr;
 
   if (blk.mode == MB_FIXED) {
     const MatInstr& ins = instrs[blk.instr_begin];
-    for (int i = 0; i < blk.count; ++i) {
+    for (int i = e; i < blk.count; i += MAT_LANES) {
       cx<R> v = fixed[ins.fixed_off + i];
       of[i] = v;
       if (ob) ob[i] = v;
@@ -267,17 +256,19 @@ __global__ void k_materialize(const R* __restrict__ params, int n_params, int64_
     return;
   }
   if (blk.mode == MB_NATIVE) {
+    if (e != 0) return;
     const MatInstr& ins = instrs[blk.instr_begin];
     cx<R> G[4], D[3][4];
-    int gdim;
-    bool ctl;
-    member_eval<R>(ins, pb, fixed, G, D, &gdim, &ctl);
+    R p[3];
+    for (int i = 0; i < 3; ++i) p[i] = ins.pidx[i] >= 0 ? pb[ins.pidx[i]] : (R)ins.pconst[i];
+    param_gate<R>(ins.kind, p, G, D);
     if (blk.diag) {
       of[0] = G[0];
       of[1] = G[3];
       if (ob) {
         ob[0] = G[0];
         ob[1] = G[3];
+#pragma unroll
         for (int i = 0; i < 3; ++i)
           if (ins.dsel[i] >= 0) {
             ob[2 + 2 * ins.dsel[i]] = D[i][0];
@@ -285,12 +276,17 @@ __global__ void k_materialize(const R* __restrict__ params, int n_params, int64_
           }
       }
     } else {
+#pragma unroll
       for (int i = 0; i < 4; ++i) of[i] = G[i];
       if (ob) {
+#pragma unroll
         for (int i = 0; i < 4; ++i) ob[i] = G[i];
+#pragma unroll
         for (int i = 0; i < 3; ++i)
-          if (ins.dsel[i] >= 0)
+          if (ins.dsel[i] >= 0) {
+#pragma unroll
             for (int j = 0; j < 4; ++j) ob[4 + 4 * ins.dsel[i] + j] = D[i][j];
+          }
       }
     }
     return;
@@ -298,45 +294,132 @@ __global__ void k_materialize(const R* __restrict__ params, int n_params, int64_
   // MB_FUSED: U = E_k ... E_1 ; dU_s = (E_k ... E_{i+1}) dE_i (E_{i-1} ... E_1)
   const int Dd = blk.dim;
   const int DD = Dd * Dd;
-  cx<R> U[16], E[16], T[16], G[16], D[3][4];
-  cx<R> Pre[MAX_BLOCK_DERIV][16];
-  for (int i = 0; i < DD; ++i) U[i] = mk<R>((i / Dd) == (i % Dd) ? (R)1 : (R)0, 0);
+  const bool live = e < DD;
+  const int r = live ? e / Dd : 0, c = live ? e % Dd : 0;
+  const cx<R> ident = mk<R>(r == c ? (R)1 : (R)0, 0);
+  cx<R> U = ident;
+  cx<R> Pre[MAX_BLOCK_DERIV];
+#pragma unroll
+  for (int s = 0; s < MAX_BLOCK_DERIV; ++s) Pre[s] = mk<R>(0, 0);
   for (int mi = blk.instr_begin; mi < blk.instr_end; ++mi) {
-    const MatInstr& ins = instrs[mi];
-    int gdim;
-    bool ctl;
-    member_eval<R>(ins, pb, fixed, G, D, &gdim, &ctl);
-    if (ob)
-      for (int i = 0; i < 3; ++i)
-        if (ins.dsel[i] >= 0)
-          for (int j = 0; j < DD; ++j) Pre[ins.dsel[i]][j] = U[j];
-    embed_member<R>(G, gdim, ctl, false, ins.embed, Dd, E);
-    matmul_small<R>(E, U, Dd, T);
-    for (int j = 0; j < DD; ++j) U[j] = T[j];
-  }
-  for (int j = 0; j < DD; ++j) of[j] = U[j];
-  if (!ob) return;
-  for (int j = 0; j < DD; ++j) ob[j] = U[j];
-  if (blk.nderiv == 0) return;
-  cx<R> S[16];
-  for (int i = 0; i < DD; ++i) S[i] = mk<R>((i / Dd) == (i % Dd) ? (R)1 : (R)0, 0);
-  for (int mi = blk.instr_end - 1; mi >= blk.instr_begin; --mi) {
-    const MatInstr& ins = instrs[mi];
-    int gdim;
-    bool ctl;
-    member_eval<R>(ins, pb, fixed, G, D, &gdim, &ctl);
-    for (int i = 0; i < 3; ++i)
-      if (ins.dsel[i] >= 0) {
-        embed_member<R>(D[i], 2, ctl, true, ins.embed, Dd, E);
-        matmul_small<R>(E, Pre[ins.dsel[i]], Dd, T);
-        matmul_small<R>(S, T, Dd, E);
-        cx<R>* dst = ob + DD * (1 + ins.dsel[i]);
-        for (int j = 0; j < DD; ++j) dst[j] = E[j];
+    const MatInstr ins = instrs[mi];
+    cx<R> G[4], D[3][4];
+    const cx<R>* fx = nullptr;
+    bool ctl = false;
+    int gdim = 2;
+    if (ins.kind == TQ_G_FIXED) {
+      fx = fixed + ins.fixed_off;
+      gdim = 1 << ins.nq;
+    } else {
+      R p[3];
+      for (int i = 0; i < 3; ++i) p[i] = ins.pidx[i] >= 0 ? pb[ins.pidx[i]] : (R)ins.pconst[i];
+      param_gate<R>(ins.kind, p, G, D);
+      ctl = kind_controlled(ins.kind);
+      if (ob) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int s = 0; s < MAX_BLOCK_DERIV; ++s)
+            if (ins.dsel[i] == s) Pre[s] = U;
       }
-    embed_member<R>(G, gdim, ctl, false, ins.embed, Dd, E);
-    matmul_small<R>(S, E, Dd, T);
-    for (int j = 0; j < DD; ++j) S[j] = T[j];
+    }
+    cx<R> E = embed_elem<R>(G, fx, gdim, ctl, false, ins.embed, Dd, r, c);
+    U = mm_elem<R>(E, U, Dd, r, c, mask);
   }
+  if (live) {
+    of[e] = U;
+    if (ob) ob[e] = U;
+  }
+  if (!ob || blk.nderiv == 0) return;
+  cx<R> S = ident;
+  for (int mi = blk.instr_end - 1; mi >= blk.instr_begin; --mi) {
+    const MatInstr ins = instrs[mi];
+    cx<R> G[4], D[3][4];
+    const cx<R>* fx = nullptr;
+    bool ctl = false;
+    int gdim = 2;
+    if (ins.kind == TQ_G_FIXED) {
+      fx = fixed + ins.fixed_off;
+      gdim = 1 << ins.nq;
+    } else {
+      R p[3];
+      for (int i = 0; i < 3; ++i) p[i] = ins.pidx[i] >= 0 ? pb[ins.pidx[i]] : (R)ins.pconst[i];
+      param_gate<R>(ins.kind, p, G, D);
+      ctl = kind_controlled(ins.kind);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (ins.dsel[i] >= 0) {  // uniform across the 16-lane group
+          cx<R> pre = mk<R>(0, 0);
+#pragma unroll
+          for (int s = 0; s < MAX_BLOCK_DERIV; ++s)
+            if (ins.dsel[i] == s) pre = Pre[s];
+          cx<R> dE = embed_elem<R>(D[i], nullptr, 2, ctl, true, ins.embed, Dd, r, c);
+          cx<R> T = mm_elem<R>(dE, pre, Dd, r, c, mask);
+          cx<R> dU = mm_elem<R>(S, T, Dd, r, c, mask);
+          if (live) ob[DD * (1 + ins.dsel[i]) + e] = dU;
+        }
+      }
+    }
+    cx<R> E = embed_elem<R>(G, fx, gdim, ctl, false, ins.embed, Dd, r, c);
+    S = mm_elem<R>(S, E, Dd, r, c, mask);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// full gate tensors G [out..., in...] and G^dagger for the tensor-network operands
+// (compiled_circuit.py:442-467; adjoint = reshape(d,d).T.conj(), pytorch_backend.py:524-546)
+// ---------------------------------------------------------------------------
+struct GateT {
+  int32_t kind, nq, fixed_off, pad;
+  int32_t pidx[3];
+  int32_t pad2;
+  double pconst[3];
+  int64_t out_off;
+};
+
+template <typename R>
+__global__ void k_gate_tensors(const R* __restrict__ params, int n_params, int64_t batch,
+                               const GateT* __restrict__ tab, int n_gates, const cx<R>* __restrict__ fixed,
+                               cx<R>* __restrict__ gm, cx<R>* __restrict__ am, int64_t total) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * n_gates) return;
+  const int64_t b = t / n_gates;
+  const GateT g = tab[(int)(t - b * n_gates)];
+  const int Dd = 1 << g.nq;
+  cx<R>* G = gm + b * total + g.out_off;
+  cx<R>* A = am + b * total + g.out_off;
+  if (g.kind == TQ_G_FIXED) {
+    for (int r = 0; r < Dd; ++r)
+      for (int c = 0; c < Dd; ++c) {
+        cx<R> v = fixed[g.fixed_off + r * Dd + c];
+        G[r * Dd + c] = v;
+        A[c * Dd + r] = conj_(v);
+      }
+    return;
+  }
+  R p[3];
+  for (int i = 0; i < 3; ++i) p[i] = g.pidx[i] >= 0 ? params[b * n_params + g.pidx[i]] : (R)g.pconst[i];
+  cx<R> M[4], D[3][4];
+  param_gate<R>(g.kind, p, M, D);
+  if (!kind_controlled(g.kind)) {
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 2; ++c) {
+        G[r * 2 + c] = M[r * 2 + c];
+        A[c * 2 + r] = conj_(M[r * 2 + c]);
+      }
+    return;
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      cx<R> v = mk<R>(0, 0);
+      if (r < 2 || c < 2) {
+        if (r == c) v = mk<R>(1, 0);
+      } else {
+        v = M[(r - 2) * 2 + (c - 2)];
+      }
+      G[r * 4 + c] = v;
+      A[c * 4 + r] = conj_(v);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -602,32 +685,39 @@ __device__ __forceinline__ void run_op<double, true>(cx<double>* s, const OpDesc
 }
 
 // ---- adjoint step: psi <- G^dag psi ; grad_d += Re <lambda | dG_d psi> ; lambda <- G^dag lambda -----------
+// The derivative matrices are the same for every amplitude group of the tile, so the groups only
+// accumulate W[r][c] = sum_groups psi_prev[c] * conj(lambda[r]); the per-parameter contraction
+// grad_d = Re sum_rc dG_d[r][c] W[r][c] happens once per thread and op, whatever the number of
+// trainable slots fused into the block.
 template <typename R>
-__device__ __forceinline__ void grad_flush(const R* acc, int nd, R* s_grad, uint32_t dslot) {
+__device__ __forceinline__ void wacc(cx<R>& w, cx<R> p, cx<R> l) {  // w += p * conj(l)
+  w.x += p.x * l.x;
+  w.x += p.y * l.y;
+  w.y += p.y * l.x;
+  w.y -= p.x * l.y;
+}
+
+template <typename R, int DD>
+__device__ __forceinline__ void grad_contract(const cx<R>* W, const cx<R>* Dm, int nd, R* s_grad, uint32_t dslot) {
+  for (int e = 0; e < nd; ++e) {
+    const cx<R>* De = Dm + DD * e;
+    R v = 0;
 #pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) {
-    if (e < nd) {
-      R v = warp_sum(acc[e]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[dslot + e], v);
-    }
+    for (int i = 0; i < DD; ++i) v += De[i].x * W[i].x - De[i].y * W[i].y;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[dslot + e], v);
   }
 }
 
 // one 2-amplitude group
 template <typename R>
-__device__ __forceinline__ void bwd2_group(const cx<R>* mh, const cx<R>* Dm, int nd, cx<R>& a0, cx<R>& a1, cx<R>& l0,
-                                           cx<R>& l1, R* acc) {
+__device__ __forceinline__ void bwd2_group(const cx<R>* mh, cx<R>& a0, cx<R>& a1, cx<R>& l0, cx<R>& l1, cx<R>* W) {
   cx<R> p0 = cfma(mh[1], a1, cmul(mh[0], a0));
   cx<R> p1 = cfma(mh[3], a1, cmul(mh[2], a0));
-#pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) {  // predicated + unrolled: acc[] stays in registers
-    if (e < nd) {
-      const cx<R>* De = Dm + 4 * e;
-      cx<R> x0 = cfma(De[1], p1, cmul(De[0], p0));
-      cx<R> x1 = cfma(De[3], p1, cmul(De[2], p0));
-      acc[e] += re_conj_mul(l0, x0) + re_conj_mul(l1, x1);
-    }
-  }
+  wacc(W[0], p0, l0);
+  wacc(W[1], p1, l0);
+  wacc(W[2], p0, l1);
+  wacc(W[3], p1, l1);
   cx<R> q0 = cfma(mh[1], l1, cmul(mh[0], l0));
   cx<R> q1 = cfma(mh[3], l1, cmul(mh[2], l0));
   a0 = p0;
@@ -637,24 +727,13 @@ __device__ __forceinline__ void bwd2_group(const cx<R>* mh, const cx<R>* Dm, int
 }
 
 template <typename R>
-__device__ __forceinline__ void bwd4_group(const cx<R>* mh, const cx<R>* Dm, int nd, cx<R>* a, cx<R>* l, R* acc) {
+__device__ __forceinline__ void bwd4_group(const cx<R>* mh, cx<R>* a, cx<R>* l, cx<R>* W) {
   cx<R> p[4], q[4];
   mv4<R>(mh, a, p);
 #pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) {
-    if (e < nd) {
-      const cx<R>* De = Dm + 16 * e;
-      R sacc = 0;
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        cx<R> x = cmul(De[r * 4], p[0]);
-#pragma unroll
-        for (int c = 1; c < 4; ++c) x = cfma(De[r * 4 + c], p[c], x);
-        sacc += re_conj_mul(l[r], x);
-      }
-      acc[e] += sacc;
-    }
-  }
+    for (int c = 0; c < 4; ++c) wacc(W[r * 4 + c], p[c], l[r]);
   mv4<R>(mh, l, q);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -663,14 +742,16 @@ __device__ __forceinline__ void bwd4_group(const cx<R>* mh, const cx<R>* Dm, int
   }
 }
 
-__device__ __forceinline__ void bwd_d1v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
-  cf mh[4];
-  ld2x2<true>(pay, mh);
-  const cf* Dm = pay + 4;
-  const int nd = d.nderiv;
-  float acc[MAX_BLOCK_DERIV];
+template <typename R, int DD>
+__device__ __forceinline__ void wzero(cx<R>* W) {
 #pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0.f;
+  for (int i = 0; i < DD; ++i) W[i] = mk<R>(0, 0);
+}
+
+__device__ __forceinline__ void bwd_d1v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  cf mh[4], W[4];
+  ld2x2<true>(pay, mh);
+  wzero<float, 4>(W);
   const uint32_t ng = 1u << (m - 1 - d.nins);
   const uint32_t tb = 1u << d.tpos[0];
   const uint32_t sw = (d.tpos[0] < 3 && (threadIdx.x & 4)) ? tb : 0u;
@@ -683,66 +764,55 @@ __device__ __forceinline__ void bwd_d1v(float4* p4, float4* l4, const OpDesc& d,
     }
     cf a0 = lo(x), a1 = lo(y), b0 = hi(x), b1 = hi(y);
     cf k0 = lo(u), k1 = lo(v), n0 = hi(u), n1 = hi(v);
-    bwd2_group<float>(mh, Dm, nd, a0, a1, k0, k1, acc);
-    bwd2_group<float>(mh, Dm, nd, b0, b1, n0, n1, acc);
+    bwd2_group<float>(mh, a0, a1, k0, k1, W);
+    bwd2_group<float>(mh, b0, b1, n0, n1, W);
     p4[c] = pack(a0, b0);
     p4[c | tb] = pack(a1, b1);
     l4[c] = pack(k0, n0);
     l4[c | tb] = pack(k1, n1);
   }
-  grad_flush<float>(acc, nd, s_grad, d.dslot);
+  grad_contract<float, 4>(W, pay + 4, d.nderiv, s_grad, d.dslot);
 }
 
 __device__ __forceinline__ void bwd_d1p(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
-  cf mh[4];
+  cf mh[4], W[4];
   ld2x2<true>(pay, mh);
-  const cf* Dm = pay + 4;
-  const int nd = d.nderiv;
-  float acc[MAX_BLOCK_DERIV];
-#pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0.f;
+  wzero<float, 4>(W);
   const uint32_t ng = 1u << (m - 1 - d.nins);
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
     const uint32_t c = expand_ins(d, g);
     float4 x = p4[c], u = l4[c];
     cf a0 = lo(x), a1 = hi(x), k0 = lo(u), k1 = hi(u);
-    bwd2_group<float>(mh, Dm, nd, a0, a1, k0, k1, acc);
+    bwd2_group<float>(mh, a0, a1, k0, k1, W);
     p4[c] = pack(a0, a1);
     l4[c] = pack(k0, k1);
   }
-  grad_flush<float>(acc, nd, s_grad, d.dslot);
+  grad_contract<float, 4>(W, pay + 4, d.nderiv, s_grad, d.dslot);
 }
 
 template <typename R>
 __device__ __forceinline__ void bwd_d1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
   cx<R> mh[4] = {conj_(pay[0]), conj_(pay[2]), conj_(pay[1]), conj_(pay[3])};
-  const cx<R>* Dm = pay + 4;
-  const int nd = d.nderiv;
-  R acc[MAX_BLOCK_DERIV];
-#pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0;
+  cx<R> W[4];
+  wzero<R, 4>(W);
   const uint32_t ng = 1u << (m - d.nins);
   const uint32_t tb = 1u << d.tpos[0];
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
     const uint32_t i = expand_ins(d, g);
     cx<R> a0 = sp[i], a1 = sp[i | tb], l0 = sl[i], l1 = sl[i | tb];
-    bwd2_group<R>(mh, Dm, nd, a0, a1, l0, l1, acc);
+    bwd2_group<R>(mh, a0, a1, l0, l1, W);
     sp[i] = a0;
     sp[i | tb] = a1;
     sl[i] = l0;
     sl[i | tb] = l1;
   }
-  grad_flush<R>(acc, nd, s_grad, d.dslot);
+  grad_contract<R, 4>(W, pay + 4, d.nderiv, s_grad, d.dslot);
 }
 
 __device__ __forceinline__ void bwd_d2v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
-  cf mh[16];
+  cf mh[16], W[16];
   ld4x4<float, true>(pay, mh);
-  const cf* Dm = pay + 16;
-  const int nd = d.nderiv;
-  float acc[MAX_BLOCK_DERIV];
-#pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0.f;
+  wzero<float, 16>(W);
   const uint32_t ng = 1u << (m - 1 - d.nins);
   const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
@@ -750,9 +820,9 @@ __device__ __forceinline__ void bwd_d2v(float4* p4, float4* l4, const OpDesc& d,
     float4 v0 = p4[c], v1 = p4[c | o1], v2 = p4[c | o2], v3 = p4[c | o1 | o2];
     float4 w0 = l4[c], w1 = l4[c | o1], w2 = l4[c | o2], w3 = l4[c | o1 | o2];
     cf a[4] = {lo(v0), lo(v1), lo(v2), lo(v3)}, l[4] = {lo(w0), lo(w1), lo(w2), lo(w3)};
-    bwd4_group<float>(mh, Dm, nd, a, l, acc);
+    bwd4_group<float>(mh, a, l, W);
     cf e[4] = {hi(v0), hi(v1), hi(v2), hi(v3)}, f[4] = {hi(w0), hi(w1), hi(w2), hi(w3)};
-    bwd4_group<float>(mh, Dm, nd, e, f, acc);
+    bwd4_group<float>(mh, e, f, W);
     p4[c] = pack(a[0], e[0]);
     p4[c | o1] = pack(a[1], e[1]);
     p4[c | o2] = pack(a[2], e[2]);
@@ -762,77 +832,109 @@ __device__ __forceinline__ void bwd_d2v(float4* p4, float4* l4, const OpDesc& d,
     l4[c | o2] = pack(l[2], f[2]);
     l4[c | o1 | o2] = pack(l[3], f[3]);
   }
-  grad_flush<float>(acc, nd, s_grad, d.dslot);
+  grad_contract<float, 16>(W, pay + 16, d.nderiv, s_grad, d.dslot);
+}
+
+// y = G^dag x with G read from shared memory on every use (complex128: 16 matrix entries would
+// cost 64 registers on top of the 64 of W and spill)
+template <typename R>
+__device__ __forceinline__ void mv4_adj_smem(const cx<R>* M, const cx<R>* x, cx<R>* y) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    cx<R> acc = mk<R>(0, 0);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc = cfma_conj(M[c * 4 + r], x[c], acc);
+    y[r] = acc;
+  }
 }
 
 template <typename R>
 __device__ __forceinline__ void bwd_d2s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
-  cx<R> mh[16];
-  ld4x4<R, true>(pay, mh);
-  const cx<R>* Dm = pay + 16;
-  const int nd = d.nderiv;
-  R acc[MAX_BLOCK_DERIV];
-#pragma unroll
-  for (int e = 0; e < MAX_BLOCK_DERIV; ++e) acc[e] = 0;
+  cx<R> W[16];
+  wzero<R, 16>(W);
   const uint32_t ng = 1u << (m - d.nins);
   const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
-  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
-    const uint32_t i = expand_ins(d, g);
-    cx<R> a[4] = {sp[i], sp[i | o1], sp[i | o2], sp[i | o1 | o2]};
-    cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]};
-    bwd4_group<R>(mh, Dm, nd, a, l, acc);
-    sp[i] = a[0]; sp[i | o1] = a[1]; sp[i | o2] = a[2]; sp[i | o1 | o2] = a[3];
-    sl[i] = l[0]; sl[i | o1] = l[1]; sl[i | o2] = l[2]; sl[i | o1 | o2] = l[3];
+  if (sizeof(R) == 8) {
+    for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+      const uint32_t i = expand_ins(d, g);
+      cx<R> a[4] = {sp[i], sp[i | o1], sp[i | o2], sp[i | o1 | o2]}, pa[4];
+      mv4_adj_smem<R>(pay, a, pa);
+      sp[i] = pa[0]; sp[i | o1] = pa[1]; sp[i | o2] = pa[2]; sp[i | o1 | o2] = pa[3];
+      cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wacc(W[r * 4 + c], pa[c], l[r]);
+      mv4_adj_smem<R>(pay, l, a);
+      sl[i] = a[0]; sl[i | o1] = a[1]; sl[i | o2] = a[2]; sl[i | o1 | o2] = a[3];
+    }
+  } else {
+    cx<R> mh[16];
+    ld4x4<R, true>(pay, mh);
+    for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+      const uint32_t i = expand_ins(d, g);
+      cx<R> a[4] = {sp[i], sp[i | o1], sp[i | o2], sp[i | o1 | o2]};
+      cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]};
+      bwd4_group<R>(mh, a, l, W);
+      sp[i] = a[0]; sp[i | o1] = a[1]; sp[i | o2] = a[2]; sp[i | o1 | o2] = a[3];
+      sl[i] = l[0]; sl[i | o1] = l[1]; sl[i | o2] = l[2]; sl[i | o1 | o2] = l[3];
+    }
   }
-  grad_flush<R>(acc, nd, s_grad, d.dslot);
+  grad_contract<R, 16>(W, pay + 16, d.nderiv, s_grad, d.dslot);
 }
 
 template <typename R>
-__device__ __forceinline__ void bwd_g1_amp(cx<R> dh, cx<R> dd, bool has_d, cx<R>& a, cx<R>& l, R& acc) {
+__device__ __forceinline__ void bwd_g1_amp(cx<R> dh, cx<R>& a, cx<R>& l, cx<R>& w) {
   cx<R> pa = cmul(dh, a);
-  if (has_d) acc += re_conj_mul(l, cmul(dd, pa));
+  wacc(w, pa, l);
   a = pa;
   l = cmul(dh, l);
 }
 
 __device__ __forceinline__ void bwd_g1v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
   const cf h0 = conj_(pay[0]), h1 = conj_(pay[1]);
-  const bool has_d = d.nderiv > 0;
-  const cf e0 = has_d ? pay[2] : mk<float>(0, 0), e1 = has_d ? pay[3] : mk<float>(0, 0);
-  float acc = 0.f;
+  cf W[2];
+  wzero<float, 2>(W);
   const uint32_t ng = 1u << (m - 1 - d.nins);
   const int tp = d.tpos[0];
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
     const uint32_t c = expand_ins(d, g);
     float4 x = p4[c], u = l4[c];
-    const bool b1 = tp == 0 ? false : ((c >> (tp - 1)) & 1u);
-    const bool b2 = tp == 0 ? true : b1;
     cf a0 = lo(x), a1 = hi(x), k0 = lo(u), k1 = hi(u);
-    bwd_g1_amp<float>(b1 ? h1 : h0, b1 ? e1 : e0, has_d, a0, k0, acc);
-    bwd_g1_amp<float>(b2 ? h1 : h0, b2 ? e1 : e0, has_d, a1, k1, acc);
+    if (tp == 0) {
+      bwd_g1_amp<float>(h0, a0, k0, W[0]);
+      bwd_g1_amp<float>(h1, a1, k1, W[1]);
+    } else if ((c >> (tp - 1)) & 1u) {
+      bwd_g1_amp<float>(h1, a0, k0, W[1]);
+      bwd_g1_amp<float>(h1, a1, k1, W[1]);
+    } else {
+      bwd_g1_amp<float>(h0, a0, k0, W[0]);
+      bwd_g1_amp<float>(h0, a1, k1, W[0]);
+    }
     p4[c] = pack(a0, a1);
     l4[c] = pack(k0, k1);
   }
-  if (has_d) grad_flush<float>(&acc, 1, s_grad, d.dslot);
+  grad_contract<float, 2>(W, pay + 2, d.nderiv, s_grad, d.dslot);
 }
 
 template <typename R>
 __device__ __forceinline__ void bwd_g1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
   const cx<R> h0 = conj_(pay[0]), h1 = conj_(pay[1]);
-  const bool has_d = d.nderiv > 0;
-  const cx<R> e0 = has_d ? pay[2] : mk<R>(0, 0), e1 = has_d ? pay[3] : mk<R>(0, 0);
-  R acc = 0;
+  cx<R> W[2];
+  wzero<R, 2>(W);
   const uint32_t ng = 1u << (m - d.nins);
   const int tp = d.tpos[0];
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
     const uint32_t i = expand_ins(d, g);
-    const bool b1 = (i >> tp) & 1u;
     cx<R> a = sp[i], l = sl[i];
-    bwd_g1_amp<R>(b1 ? h1 : h0, b1 ? e1 : e0, has_d, a, l, acc);
+    if ((i >> tp) & 1u)
+      bwd_g1_amp<R>(h1, a, l, W[1]);
+    else
+      bwd_g1_amp<R>(h0, a, l, W[0]);
     sp[i] = a;
     sl[i] = l;
   }
-  if (has_d) grad_flush<R>(&acc, 1, s_grad, d.dslot);
+  grad_contract<R, 2>(W, pay + 2, d.nderiv, s_grad, d.dslot);
 }
 
 template <typename R>

@@ -1,0 +1,89 @@
+"""GPU: tensor-network contraction mode of the engine against the oracle and against the state-vector engine."""
+import numpy as np
+import pytest
+import torch
+
+import tedq_b200 as qb
+from conftest import load_golden
+from helpers import TOL, assert_close, build, cdtype, golden_out, rdtype
+from oracle import sv_ref, tn_ref
+from tedq_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+CASES = load_golden("sv_cases.json")
+TN_CASES = [c for c in CASES if c["spec"]["num_qubits"] <= 8 and c["spec"]["n_params"] > 0
+            and not (c["spec"]["meas"][0][0] == "probs" and c["spec"]["meas"][0][1] is None)][:40]
+
+
+def _case_id(c):
+    return f'{c["spec"]["name"]}-{c["spec"]["meas"][0][0]}-{c["dtype"]}'
+
+
+@pytest.mark.parametrize("case", TN_CASES, ids=_case_id)
+@pytest.mark.parametrize("slices", [1, 4])
+def test_tn_mode_matches_reference_fixture(case, slices):
+    """TN-mode values equal the reference's results (same circuit, same parameters) for every measurement kind;
+    sliced plans give the same sum."""
+    dt = case["dtype"]
+    hyper = {"max_repeats": 4, "slicing_opts": {"target_num_slices": slices}}
+    cc = build(case, dt, case["flat"][0]).compilecircuit(backend="pytorch_b200", tn_mode=True, hyper_opt=hyper,
+                                                          tn_simplify=False, dtype=cdtype(dt))
+    flat = torch.tensor(case["flat"], dtype=rdtype(dt), device="cuda")
+    out = cc.batched(flat).cpu().numpy()
+    ref = golden_out(case)
+    ms = case["spec"]["meas"]
+    if ms[0][0] == "probs":   # TN branch keeps the listed qubit order, SV branch sorts ascending
+        axes = []
+        for m in ms:
+            axes.append(np.argsort(np.argsort(m[1])))
+        ref = np.stack([np.transpose(ref[:, i], [0] + [1 + a for a in axes[i]]) for i in range(len(ms))], 1)
+    assert_close(out, ref, TOL[dt], "tn out")
+
+
+def test_tn_mode_gradients_match_sv_mode():
+    spec = W.mbl_1d(6)
+    circ = W.build_circuit(spec, qb)
+    x = torch.tensor(W.c2_inputs(4, 6, 3), device="cuda")
+    outs, grads = [], []
+    for kw in ({}, {"tn_mode": True, "tn_simplify": False}):
+        cc = circ.compilecircuit(backend="pytorch_b200", **kw)
+        xx = x.clone().requires_grad_(True)
+        y = cc.batched(xx)
+        (y * torch.tensor([0.3, -0.8], device="cuda")).sum().backward()
+        outs.append(y.detach().cpu().numpy())
+        grads.append(xx.grad.cpu().numpy())
+    assert_close(outs[1], outs[0], 1e-5, "out")
+    assert_close(grads[1], grads[0], 1e-5, "grad")
+
+
+@pytest.mark.parametrize("n,cycles", [(3 * 3, 4), (3 * 4, 6), (4 * 4, 5)])
+def test_amplitudes_match_state_vector(n, cycles):
+    """C5 parity (i): the lattice generator at sizes the SV oracle can run; every slice count gives the same sum."""
+    rows = 3 if n < 16 else 4
+    spec = W.lattice_rcs(rows, n // rows, cycles, seed=5, measure="state")
+    circ = W.build_circuit(spec, qb)
+    ref = sv_ref.run_sv(circ, torch.zeros(0), torch.complex64, return_state=True).numpy().reshape(-1)
+    rng = np.random.RandomState(0)
+    for slices in (1, 8):
+        cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                                 hyper_opt={"max_repeats": 8, "slicing_opts": {"target_num_slices": slices}})
+        for bits in ([0] * n, rng.randint(0, 2, n).tolist()):
+            amp = complex(cc.amplitude(bits).cpu())
+            idx = int("".join(str(b) for b in bits), 2)
+            assert abs(amp - ref[idx]) <= 1e-5 * max(1.0, abs(ref[idx])), (slices, bits, amp, ref[idx])
+        if slices > 1:
+            # slice-sum invariance: two halves add up to the whole
+            ns = cc._tn._amplitude_plan()[2].n_slices
+            a = cc.amplitude(bits, slice_range=(0, ns // 2)) + cc.amplitude(bits, slice_range=(ns // 2, ns))
+            assert abs(complex(a.cpu()) - ref[idx]) <= 1e-5 * max(1.0, abs(ref[idx]))
+
+
+def test_tn_mode_complex128_mbl2d():
+    spec = W.mbl_2d(2, 1)
+    wrap = lambda v: torch.tensor(float(v), dtype=torch.float64)
+    circ = W.build_circuit(spec, qb, tensor_fn=wrap)
+    x = torch.rand(2, spec["n_params"], dtype=torch.float64)
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, dtype=torch.complex128)
+    got = cc.batched(x.cuda()).cpu().numpy()
+    ref, _ = sv_ref.run_batch(circ, x, torch.complex128)
+    assert_close(got, ref.numpy(), 1e-11, "c128 tn")
