@@ -270,6 +270,61 @@ def measure_workload(name, steps, warmup, device, dist_on, world, do_e2e=True, d
     return res
 
 
+def measure_c5(steps, warmup, device, dist_on, world):
+    """BASELINE config 5: 40-qubit lattice random circuit (5x8, 12 cycles), single amplitude <0..0|U|0..0>, sliced
+    contraction; slices are sharded over ranks and combined with one all-reduce (strong scaling)."""
+    import tedq_b200 as qb
+    from tedq_b200 import workloads as W
+
+    spec = W.lattice_rcs(5, 8, 12, seed=0)
+    circ = W.build_circuit(spec, qb)
+    hyper = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "64")),
+             "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64, "contract_parallel": dist_on}}
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
+    bits = [0] * 40
+    for _ in range(max(1, warmup)):
+        amp = cc.amplitude(bits)
+    torch.cuda.synchronize(device)
+    plan = cc._tn._amplitude_plan()[2]
+    if dist_on:
+        torch.distributed.barrier()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        amp = cc.amplitude(bits)
+    ev1.record()
+    torch.cuda.synchronize(device)
+    if dist_on:
+        torch.distributed.barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    if dist_on:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    total_ms = float(t.item())
+    flops = plan.flops * plan.n_slices
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            tf32_peak = float(json.load(fh)["bf16_tflops"]) / 2.0
+        kind = "derived: measured bf16 burst / 2 (no TF32 figure in MEASURED_PEAKS.json)"
+    except Exception:
+        tf32_peak, kind = 1590.0 / 2.0, "derived from fallback"
+    ach = flops * steps / (total_ms * 1e-3) / 1e12
+    return {
+        "value": steps / (total_ms * 1e-3), "unit": "evals/s", "ms_per_step": total_ms / steps, "dtype": "c64",
+        "desc": f"c5: 40-qubit 5x8 lattice random circuit, 12 cycles, amplitude <0|U|0>, {plan.n_slices} slices, "
+                f"width {plan.width}, {plan.n_steps} pairwise steps, {flops:.3e} flop per amplitude",
+        "amplitude": [float(amp.real), float(amp.imag)],
+        "roofline": {"bound": "tensor", "kernel": "k_tn_gemm", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": ach / tf32_peak, "traffic": None, "peak_kind": kind,
+                     "note": "8*M*N*K flops per complex GEMM step summed over the lowered plan"},
+        "clocks": sampler.summary(), "gpu_launches": int((plan.n_steps + 1) * plan.n_slices * steps),
+        "scaling": "strong",
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,7 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c1,c3,c4"),
+    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c1,c3,c4,c5"),
                     help="other BASELINE configs measured briefly and reported inside the same JSON line")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
@@ -297,11 +352,30 @@ def main():
     if dist_on:
         torch.distributed.init_process_group("nccl", device_id=device)
 
+    if args.workload == "c5":
+        r = measure_c5(max(1, min(args.steps, 5)), 1, device, dist_on, world)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "circuit_evals_per_sec", "value": r["value"], "unit": r["unit"], "n_gpus": world,
+                "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+                "config": {"workload": r["desc"], "parallelism": f"slices sharded over {world} GPU(s), one all-reduce",
+                           "l2": "intermediates (2^23..2^27 complex) exceed L2 between steps"},
+                "roofline": r["roofline"], "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
+                "amplitude": r["amplitude"], "e2e": None}))
+        if dist_on:
+            torch.distributed.destroy_process_group()
+        return
     main_res = measure_workload(args.workload, args.steps, args.warmup, device, dist_on, world,
                                 do_e2e=True, do_cpu=(rank == 0 and world == 1))
     extras = {}
     if world == 1 and args.extras and args.extras != "none":
         for name in [e for e in args.extras.split(",") if e and e != args.workload]:
+            if name == "c5":
+                r = measure_c5(1, 1, device, False, 1)
+                extras[name] = {"value": r["value"], "unit": "evals/s", "ms_per_step": r["ms_per_step"],
+                                "workload": r["desc"], "roofline": r["roofline"], "dtype": "c64"}
+                continue
             r = measure_workload(name, max(2, min(5, args.steps)), 3, device, False, 1, do_e2e=False,
                                  do_cpu=os.environ.get("TQ_EXTRAS_CPU", "0") == "1")
             extras[name] = {"value": r["value"], "unit": "evals/s", "ms_per_step": r["ms_per_step"], "workload": r["desc"],

@@ -81,7 +81,7 @@ struct tq_plan {
   int n_slots = 0;
   int64_t out_reals = 0;
   std::vector<zc> fixed;
-  bool fwd_full = false, bwd_full = false;
+  bool fwd_full = false, bwd_full = false, sv_ok = true;
   int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256, fuse = 1;
   std::vector<Sweep> fwd, bwd;
   // device
@@ -450,8 +450,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
                    const double* init_state, const tq_plan_opts* opts, tq_plan** out) {
   TQ_REQUIRE(out, TQ_E_INVALID, "tq_plan_create: out is null");
   *out = nullptr;
-  TQ_REQUIRE(n_qubits >= 1 && n_qubits <= 30, TQ_E_UNSUPPORTED, "tq_plan_create: n_qubits=%d outside [1,30]",
-             n_qubits);
+  // beyond 30 qubits a state vector does not fit: the plan then only serves the tensor-network entry points
+  // (tq_tn_operands); tq_forward / tq_backward refuse it
+  TQ_REQUIRE(n_qubits >= 1 && n_qubits <= 4096, TQ_E_UNSUPPORTED, "tq_plan_create: n_qubits=%d unsupported", n_qubits);
+  const bool sv_ok = n_qubits <= 30;
   TQ_REQUIRE(dtype == TQ_C64 || dtype == TQ_C128, TQ_E_INVALID, "tq_plan_create: bad dtype %d", dtype);
   TQ_REQUIRE(n_gates >= 0 && n_meas >= 1 && n_params >= 0, TQ_E_INVALID, "tq_plan_create: bad counts");
   std::unique_ptr<tq_plan, void (*)(tq_plan*)> P(new tq_plan(), tq_plan_destroy);
@@ -460,6 +462,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   p->n_params = n_params;
   p->dtype = dtype;
   p->n_gates = n_gates;
+  p->sv_ok = sv_ok;
   const int n = n_qubits;
   const zc* zpool = reinterpret_cast<const zc*>(pool);
   const bool c64 = dtype == TQ_C64;
@@ -479,6 +482,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   }
   TQ_REQUIRE(m_f <= (c64 ? 14 : 13) && m_b <= (c64 ? 13 : 12), TQ_E_INVALID,
              "tq_plan_create: tile exceeds shared memory");
+  if (!sv_ok) {
+    m_f = std::min(m_f, 12);
+    m_b = std::min(m_b, 11);
+  }
   p->fwd_full = n <= full_f;
   p->bwd_full = n <= full_b;
   if (p->fwd_full) m_f = n;
@@ -585,6 +592,13 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       off += (int64_t)1 << (2 * g.nq);
     }
     p->gate_t_total = off;
+  }
+  if (!sv_ok) {
+    int rc0;
+    if ((rc0 = upload_complex(p->fixed.data(), p->fixed.size(), dtype, &p->d_fixed))) return rc0;
+    if ((rc0 = upload(p->gate_t, &p->d_gate_t))) return rc0;
+    *out = P.release();
+    return TQ_OK;
   }
 
   // ---- fusion: runs of gates inside one qubit or one qubit pair become one dense block -------------
@@ -1150,6 +1164,7 @@ int tq_forward(const tq_plan* p, const void* params, int64_t batch, void* out, v
                int32_t with_backward, void* stream) {
   TQ_REQUIRE(p && out && workspace && batch > 0, TQ_E_INVALID, "tq_forward: null argument or empty batch");
   TQ_REQUIRE(params || p->n_params == 0, TQ_E_INVALID, "tq_forward: params is null");
+  TQ_REQUIRE(p->sv_ok, TQ_E_UNSUPPORTED, "tq_forward: %d qubits exceed the state-vector limit of 30; use the tensor-network entry points", p->n);
   if (p->dtype == TQ_C64)
     return forward_impl<float>(p, params, batch, out, workspace, ws_bytes, with_backward, (cudaStream_t)stream);
   return forward_impl<double>(p, params, batch, out, workspace, ws_bytes, with_backward, (cudaStream_t)stream);
@@ -1160,6 +1175,7 @@ int tq_backward(const tq_plan* p, const void* params, int64_t batch, const void*
   TQ_REQUIRE(p && grad_out && grad_params && workspace && batch > 0, TQ_E_INVALID,
              "tq_backward: null argument or empty batch");
   TQ_REQUIRE(p->n_params > 0, TQ_E_INVALID, "tq_backward: circuit has no parameters");
+  TQ_REQUIRE(p->sv_ok, TQ_E_UNSUPPORTED, "tq_backward: %d qubits exceed the state-vector limit of 30", p->n);
   if (p->dtype == TQ_C64)
     return backward_impl<float>(p, params, batch, grad_out, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
   return backward_impl<double>(p, params, batch, grad_out, grad_params, workspace, ws_bytes, (cudaStream_t)stream);

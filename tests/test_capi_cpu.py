@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, exports every symbol the header declares; host-only entry
+points give the reference's integers.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, load_golden
+from tedq_b200 import build, capi
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tedq_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build_library()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/tedq_b200.h but not exported: {missing}"
+    assert capi.lib().tq_abi_version() == 1
+
+
+def test_library_contains_sm100a_code():
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", build.build_library()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.parametrize("case", load_golden("sv_cases.json")[:30], ids=lambda c: c["spec"]["name"])
+def test_c_sv_plan_integers_match_reference(case):
+    """tq_sv_axes_perm reproduces the reference's per-gate (axes, permutation) (compiled_circuit.py:126-202)."""
+    n = case["spec"]["num_qubits"]
+    gates = case["spec"]["gates"]
+    axes = list(reversed(case["axeslist"]))
+    perms = list(reversed(case["permutationlist"]))
+    for (name, qubits, _), a, p in zip(gates, axes, perms):
+        gp, pm = capi.sv_axes_perm(n, qubits)
+        assert gp == a[0] and list(qubits) == a[1] and pm == p
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+
+    import tedq_b200 as qb
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+
+    def circuit_def(t):
+        qb.RX(t[0], qubits=[0])
+        return qb.expval(qb.PauliZ(qubits=[0]))
+
+    cc = qb.Circuit(circuit_def, 1, torch.tensor([0.1])).compilecircuit(backend="pytorch_b200")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc(torch.tensor([0.1]))
