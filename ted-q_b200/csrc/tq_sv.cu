@@ -934,11 +934,11 @@ int64_t tq_plan_hbm_bytes(const tq_plan* p, int32_t backward) {
     // payload stream written once and read once; first sweep synthesises |0..0> (no read);
     // every sweep writes; the measurement pass reads once
     const int64_t pay = 2 * p->stride_f * cs;
-    if (p->fwd_full) return io + pay;
+    if (p->fwd_full) return io + pay;  // (+ one write of psi when a backward follows, counted there)
     return io + pay + sv * (2 * (int64_t)p->fwd.size());
   }
-  const int64_t pay = 2 * (p->stride_b + (p->bwd_full ? p->stride_f : 0)) * cs;
-  if (p->bwd_full) return io + pay + (int64_t)rsize(p->dtype) * p->n_params;
+  const int64_t pay = 2 * p->stride_b * cs;
+  if (p->bwd_full) return io + pay + (int64_t)rsize(p->dtype) * p->n_params + 2 * sv;  // psi stored + re-read
   return io + pay + sv * (2 + 4 * (int64_t)p->bwd.size());
 }
 
@@ -970,7 +970,7 @@ static WsLayout ws_layout(const tq_plan* p, int64_t B, int with_backward) {
   off += align_up((size_t)B * p->stride_f * cs);
   w.sb = off;
   if (with_backward) off += align_up((size_t)B * p->stride_b * cs);
-  w.has_psi = !p->fwd_full || (with_backward && !p->bwd_full);
+  w.has_psi = !p->fwd_full || with_backward;  // the adjoint pass starts from the stored final state
   w.has_lam = with_backward && !p->bwd_full;
   w.psi = off;
   if (w.has_psi) off += align_up(((size_t)B << p->n) * cs);

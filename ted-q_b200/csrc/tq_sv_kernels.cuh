@@ -711,13 +711,16 @@ __device__ __forceinline__ void grad_contract(const cx<R>* W, const cx<R>* Dm, i
 
 // one 2-amplitude group
 template <typename R>
-__device__ __forceinline__ void bwd2_group(const cx<R>* mh, cx<R>& a0, cx<R>& a1, cx<R>& l0, cx<R>& l1, cx<R>* W) {
+__device__ __forceinline__ void bwd2_group(const cx<R>* mh, cx<R>& a0, cx<R>& a1, cx<R>& l0, cx<R>& l1, cx<R>* W,
+                                           bool has_d) {
   cx<R> p0 = cfma(mh[1], a1, cmul(mh[0], a0));
   cx<R> p1 = cfma(mh[3], a1, cmul(mh[2], a0));
-  wacc(W[0], p0, l0);
-  wacc(W[1], p1, l0);
-  wacc(W[2], p0, l1);
-  wacc(W[3], p1, l1);
+  if (has_d) {  // uniform per op: fixed blocks carry no gradient
+    wacc(W[0], p0, l0);
+    wacc(W[1], p1, l0);
+    wacc(W[2], p0, l1);
+    wacc(W[3], p1, l1);
+  }
   cx<R> q0 = cfma(mh[1], l1, cmul(mh[0], l0));
   cx<R> q1 = cfma(mh[3], l1, cmul(mh[2], l0));
   a0 = p0;
@@ -727,13 +730,15 @@ __device__ __forceinline__ void bwd2_group(const cx<R>* mh, cx<R>& a0, cx<R>& a1
 }
 
 template <typename R>
-__device__ __forceinline__ void bwd4_group(const cx<R>* mh, cx<R>* a, cx<R>* l, cx<R>* W) {
+__device__ __forceinline__ void bwd4_group(const cx<R>* mh, cx<R>* a, cx<R>* l, cx<R>* W, bool has_d) {
   cx<R> p[4], q[4];
   mv4<R>(mh, a, p);
+  if (has_d) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) wacc(W[r * 4 + c], p[c], l[r]);
+      for (int c = 0; c < 4; ++c) wacc(W[r * 4 + c], p[c], l[r]);
+  }
   mv4<R>(mh, l, q);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -752,6 +757,7 @@ __device__ __forceinline__ void bwd_d1v(float4* p4, float4* l4, const OpDesc& d,
   cf mh[4], W[4];
   ld2x2<true>(pay, mh);
   wzero<float, 4>(W);
+  const bool has_d = d.nderiv > 0;
   const uint32_t ng = 1u << (m - 1 - d.nins);
   const uint32_t tb = 1u << d.tpos[0];
   const uint32_t sw = (d.tpos[0] < 3 && (threadIdx.x & 4)) ? tb : 0u;
@@ -764,8 +770,8 @@ __device__ __forceinline__ void bwd_d1v(float4* p4, float4* l4, const OpDesc& d,
     }
     cf a0 = lo(x), a1 = lo(y), b0 = hi(x), b1 = hi(y);
     cf k0 = lo(u), k1 = lo(v), n0 = hi(u), n1 = hi(v);
-    bwd2_group<float>(mh, a0, a1, k0, k1, W);
-    bwd2_group<float>(mh, b0, b1, n0, n1, W);
+    bwd2_group<float>(mh, a0, a1, k0, k1, W, has_d);
+    bwd2_group<float>(mh, b0, b1, n0, n1, W, has_d);
     p4[c] = pack(a0, b0);
     p4[c | tb] = pack(a1, b1);
     l4[c] = pack(k0, n0);
@@ -778,12 +784,13 @@ __device__ __forceinline__ void bwd_d1p(float4* p4, float4* l4, const OpDesc& d,
   cf mh[4], W[4];
   ld2x2<true>(pay, mh);
   wzero<float, 4>(W);
+  const bool has_d = d.nderiv > 0;
   const uint32_t ng = 1u << (m - 1 - d.nins);
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
     const uint32_t c = expand_ins(d, g);
     float4 x = p4[c], u = l4[c];
     cf a0 = lo(x), a1 = hi(x), k0 = lo(u), k1 = hi(u);
-    bwd2_group<float>(mh, a0, a1, k0, k1, W);
+    bwd2_group<float>(mh, a0, a1, k0, k1, W, has_d);
     p4[c] = pack(a0, a1);
     l4[c] = pack(k0, k1);
   }
@@ -795,12 +802,13 @@ __device__ __forceinline__ void bwd_d1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, c
   cx<R> mh[4] = {conj_(pay[0]), conj_(pay[2]), conj_(pay[1]), conj_(pay[3])};
   cx<R> W[4];
   wzero<R, 4>(W);
+  const bool has_d = d.nderiv > 0;
   const uint32_t ng = 1u << (m - d.nins);
   const uint32_t tb = 1u << d.tpos[0];
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
     const uint32_t i = expand_ins(d, g);
     cx<R> a0 = sp[i], a1 = sp[i | tb], l0 = sl[i], l1 = sl[i | tb];
-    bwd2_group<R>(mh, a0, a1, l0, l1, W);
+    bwd2_group<R>(mh, a0, a1, l0, l1, W, has_d);
     sp[i] = a0;
     sp[i | tb] = a1;
     sl[i] = l0;
@@ -813,6 +821,7 @@ __device__ __forceinline__ void bwd_d2v(float4* p4, float4* l4, const OpDesc& d,
   cf mh[16], W[16];
   ld4x4<float, true>(pay, mh);
   wzero<float, 16>(W);
+  const bool has_d = d.nderiv > 0;
   const uint32_t ng = 1u << (m - 1 - d.nins);
   const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
@@ -820,9 +829,9 @@ __device__ __forceinline__ void bwd_d2v(float4* p4, float4* l4, const OpDesc& d,
     float4 v0 = p4[c], v1 = p4[c | o1], v2 = p4[c | o2], v3 = p4[c | o1 | o2];
     float4 w0 = l4[c], w1 = l4[c | o1], w2 = l4[c | o2], w3 = l4[c | o1 | o2];
     cf a[4] = {lo(v0), lo(v1), lo(v2), lo(v3)}, l[4] = {lo(w0), lo(w1), lo(w2), lo(w3)};
-    bwd4_group<float>(mh, a, l, W);
+    bwd4_group<float>(mh, a, l, W, has_d);
     cf e[4] = {hi(v0), hi(v1), hi(v2), hi(v3)}, f[4] = {hi(w0), hi(w1), hi(w2), hi(w3)};
-    bwd4_group<float>(mh, e, f, W);
+    bwd4_group<float>(mh, e, f, W, has_d);
     p4[c] = pack(a[0], e[0]);
     p4[c | o1] = pack(a[1], e[1]);
     p4[c | o2] = pack(a[2], e[2]);
@@ -852,6 +861,7 @@ template <typename R>
 __device__ __forceinline__ void bwd_d2s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
   cx<R> W[16];
   wzero<R, 16>(W);
+  const bool has_d = d.nderiv > 0;
   const uint32_t ng = 1u << (m - d.nins);
   const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
   if (sizeof(R) == 8) {
@@ -861,10 +871,12 @@ __device__ __forceinline__ void bwd_d2s(cx<R>* sp, cx<R>* sl, const OpDesc& d, c
       mv4_adj_smem<R>(pay, a, pa);
       sp[i] = pa[0]; sp[i | o1] = pa[1]; sp[i | o2] = pa[2]; sp[i | o1 | o2] = pa[3];
       cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]};
+      if (has_d) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wacc(W[r * 4 + c], pa[c], l[r]);
+          for (int c = 0; c < 4; ++c) wacc(W[r * 4 + c], pa[c], l[r]);
+      }
       mv4_adj_smem<R>(pay, l, a);
       sl[i] = a[0]; sl[i | o1] = a[1]; sl[i | o2] = a[2]; sl[i | o1 | o2] = a[3];
     }
@@ -875,7 +887,7 @@ __device__ __forceinline__ void bwd_d2s(cx<R>* sp, cx<R>* sl, const OpDesc& d, c
       const uint32_t i = expand_ins(d, g);
       cx<R> a[4] = {sp[i], sp[i | o1], sp[i | o2], sp[i | o1 | o2]};
       cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]};
-      bwd4_group<R>(mh, a, l, W);
+      bwd4_group<R>(mh, a, l, W, has_d);
       sp[i] = a[0]; sp[i | o1] = a[1]; sp[i | o2] = a[2]; sp[i | o1 | o2] = a[3];
       sl[i] = l[0]; sl[i | o1] = l[1]; sl[i | o2] = l[2]; sl[i | o1 | o2] = l[3];
     }
@@ -1327,14 +1339,20 @@ __global__ void __launch_bounds__(256, 2) k_sweep_bwd(const __grid_constant__ Bw
   for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) s_grad[s] = 0;
 
   if (a.flags & SW_FULL) {
-    if (a.init_state) {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = a.init_state[l];
-    } else {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = mk<R>(0, 0);
+    if (a.psi) {  // tq_forward(with_backward) left psi_final in the workspace: 2^n * 8 B per set, no recompute
+      const cx<R>* psi_b = a.psi + (size_t)b * sv;
+      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = psi_b[l];
       __syncthreads();
-      if (threadIdx.x == 0) sp[0] = mk<R>(1, 0);
+    } else {
+      if (a.init_state) {
+        for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = a.init_state[l];
+      } else {
+        for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = mk<R>(0, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) sp[0] = mk<R>(1, 0);
+      }
+      run_stream_fwd<R>(sp, ring, a.st_f, a.stream_f + b * a.stride_f, m);
     }
-    run_stream_fwd<R>(sp, ring, a.st_f, a.stream_f + b * a.stride_f, m);
     const R* dy_b = a.dy + b * a.out_reals;
     for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x)
       sl[l] = seed_amp<R>(sp, l, a.meas, a.n_meas, a.fixed, dy_b);
