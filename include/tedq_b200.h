@@ -222,6 +222,23 @@ int32_t tq_tn_plan_width(const tq_tn_plan* plan); /* log2 of the largest tensor 
 int32_t tq_tn_plan_get_step(const tq_tn_plan* plan, int32_t s, tq_tn_step* out);
 size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
 
+/* Execution options (set before tq_tn_workspace_bytes / tq_tn_contract).
+ *   TQ_TN_OPT_TENSOR_CORE (default 1): complex64 steps with >= 128 x 16 free extents and
+ *     k + m + n + b >= TQ_TN_OPT_TC_MIN_LOG2 (default 20) run on tcgen05 tensor cores as a 4M real GEMM with
+ *     error-compensated split-TF32 (x = hi + lo; hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM);
+ *     0 keeps every step on the fp32 FMA kernels (used by the parity tests to compare the two paths).
+ *   TQ_TN_OPT_TC_CHUNK (default 2): k-blocks (16 complex k each) accumulated inside the tensor core between
+ *     drains.  tcgen05 accumulates with round-toward-zero (a bias linear in K); partial sums are therefore
+ *     drained every `chunk` k-blocks and added to fp32 registers with round-to-nearest. */
+enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2 };
+int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
+/* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,
+ * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096) */
+int32_t tq_tn_plan_step_kernel(const tq_tn_plan* plan, int32_t s);
+/* bit 0: step s repeats for every slice (it depends on a sliced index); bit 1: it carries the parameter-set
+ * batch dimension.  Steps with neither bit run once per call, outside the slice loop. */
+int32_t tq_tn_plan_step_flags(const tq_tn_plan* plan, int32_t s);
+
 /* Contract slices [slice_begin, slice_end) and ACCUMULATE their sum into out (device,
  * [batch or 1][2^n_out] complex; the caller zeroes it).  inputs[t] = device pointer of input tensor t
  * (C order, complex); input_strides[t] = complex entries between consecutive parameter sets of input t
@@ -231,6 +248,13 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
 int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
                    int64_t slice_begin, int64_t slice_end, void* out, void* workspace, size_t workspace_bytes,
                    void* cuda_stream);
+
+/* Profiling twin of tq_tn_contract for ONE slice: same work, plus CUDA events around every step.
+ * step_ms[2*s] = milliseconds of step s, step_ms[2*s+1] = the part spent packing operand images (tensor-core
+ * steps only).  Synchronises the stream.  Feeds bench.py's per-step roofline table. */
+int tq_tn_profile(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
+                  int64_t slice, void* out, void* workspace, size_t workspace_bytes, void* cuda_stream,
+                  float* step_ms);
 
 /* Operand tensors of a circuit's network on the device (replaces _parse_circuit_cotengra + the arrays
  * assembly, compiled_circuit.py:442-467, pytorch_backend.py:311-336, :524-546): for every gate of `plan`

@@ -39,6 +39,7 @@ class PlanOpts(C.Structure):
 
 
 TN_MAX_RANK = 32
+TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK = 0, 1, 2
 
 
 class TnStep(C.Structure):
@@ -133,6 +134,14 @@ def lib() -> C.CDLL:
     L.tq_tn_workspace_bytes.restype = sz
     L.tq_tn_contract.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
     L.tq_tn_contract.restype = i32
+    L.tq_tn_plan_set_option.argtypes = [vp, i32, i32]
+    L.tq_tn_plan_set_option.restype = i32
+    L.tq_tn_plan_step_kernel.argtypes = [vp, i32]
+    L.tq_tn_plan_step_kernel.restype = i32
+    L.tq_tn_plan_step_flags.argtypes = [vp, i32]
+    L.tq_tn_plan_step_flags.restype = i32
+    L.tq_tn_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, vp, sz, vp, C.POINTER(C.c_float)]
+    L.tq_tn_profile.restype = i32
     L.tq_tn_gate_offset.argtypes = [vp, i32]
     L.tq_tn_gate_offset.restype = i64
     L.tq_tn_operands.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -375,6 +384,27 @@ class TnPlan:
 
     def workspace_bytes(self, batch):
         return int(lib().tq_tn_workspace_bytes(self.handle, batch))
+
+    def set_option(self, option, value):
+        check(lib().tq_tn_plan_set_option(self.handle, option, value), "tq_tn_plan_set_option")
+
+    def step_kernel(self, s):
+        """0: per-element kernel, 1: tiled fp32 FMA GEMM, 2: tcgen05 split-TF32 GEMM."""
+        return int(lib().tq_tn_plan_step_kernel(self.handle, s))
+
+    def step_flags(self, s):
+        """bit 0: repeats per slice, bit 1: batched over parameter sets."""
+        return int(lib().tq_tn_plan_step_flags(self.handle, s))
+
+    def profile(self, input_ptrs, input_strides, batch, slice_id, out_ptr, ws_ptr, ws_bytes, stream):
+        """Per-step milliseconds of one slice: array [n_steps, 2] = (whole step, operand packing part)."""
+        n = self.n_inputs
+        ptrs = (C.c_void_p * n)(*input_ptrs)
+        strides = (C.c_int64 * n)(*input_strides)
+        ms = (C.c_float * (2 * self.n_steps))()
+        check(lib().tq_tn_profile(self.handle, ptrs, strides, batch, slice_id, out_ptr, ws_ptr, ws_bytes, stream, ms),
+              "tq_tn_profile")
+        return np.asarray(ms, dtype=np.float32).reshape(self.n_steps, 2)
 
     def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
         n = self.n_inputs

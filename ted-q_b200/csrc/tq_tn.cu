@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "tq_common.h"
+#include "tq_tn_tc.cuh"
 
 namespace tq {
 
@@ -165,9 +166,10 @@ struct StepDev {
   int32_t n_k, n_m, n_n, n_b;
   int8_t a_m[TQ_TN_MAX_RANK], a_b[TQ_TN_MAX_RANK];  // scatter of m / kept-shared bits into A
   int8_t b_n[TQ_TN_MAX_RANK], b_b[TQ_TN_MAX_RANK];  // scatter of n / kept-shared bits into B
-  const int32_t* ka;                                // K offset tables, 2^n_k entries each
+  const int32_t* ka;                                // K offset tables, 2^n_k entries each (2^10 for reductions)
   const int32_t* kb;
   int32_t a_k_fast, b_k_fast;  // the fastest physical bit of A / B is a K bit
+  int8_t a_k[TQ_TN_MAX_RANK], b_k[TQ_TN_MAX_RANK];  // scatter of k bits into A / B
 };
 
 __device__ __forceinline__ uint32_t scat(uint32_t v, const int8_t* pos, int n) {
@@ -194,6 +196,60 @@ k_tn_step(const cx<R>* __restrict__ A, int64_t sA, const cx<R>* __restrict__ B, 
   const int K = 1 << d.n_k;
   for (int k = 0; k < K; ++k) acc = cfma(a[d.ka[k]], b[d.kb[k]], acc);
   C[set * sC + o] = acc;
+}
+
+// Split-K reduction for steps with a handful of output elements and a long contracted extent (the closing
+// steps of an amplitude network: a 2^21-term dot product).  Block (x, o, set) reduces K range x of output
+// element o into partial[set][o][x]; k_tn_dot_sum adds the partials in a fixed order (deterministic).
+constexpr int DOT_LO = 10;  // k bits resolved through the offset tables; the rest by bit scatter per 1024-chunk
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_tn_dot(const cx<R>* __restrict__ A, int64_t sA, const cx<R>* __restrict__ B, int64_t sB,
+         cx<R>* __restrict__ partial, const __grid_constant__ StepDev d) {
+  const uint32_t o = blockIdx.y, set = blockIdx.z;
+  const uint32_t n = o & ((1u << d.n_n) - 1u);
+  const uint32_t m = (o >> d.n_n) & ((1u << d.n_m) - 1u);
+  const uint32_t bb = o >> (d.n_n + d.n_m);
+  const cx<R>* a = A + (int64_t)set * sA + (scat(m, d.a_m, d.n_m) | scat(bb, d.a_b, d.n_b));
+  const cx<R>* b = B + (int64_t)set * sB + (scat(n, d.b_n, d.n_n) | scat(bb, d.b_b, d.n_b));
+  const int chunks = 1 << (d.n_k - DOT_LO);
+  cx<R> acc = mk<R>(0, 0);
+  for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+    const uint32_t ah = scat((uint32_t)ch, d.a_k + DOT_LO, d.n_k - DOT_LO);
+    const uint32_t bh = scat((uint32_t)ch, d.b_k + DOT_LO, d.n_k - DOT_LO);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kl = threadIdx.x + 256 * i;
+      acc = cfma(a[ah | (uint32_t)d.ka[kl]], b[bh | (uint32_t)d.kb[kl]], acc);
+    }
+  }
+  acc.x = warp_sum(acc.x);
+  acc.y = warp_sum(acc.y);
+  __shared__ cx<R> part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cx<R> t = part[0];
+    for (int w = 1; w < 8; ++w) {
+      t.x += part[w].x;
+      t.y += part[w].y;
+    }
+    partial[((int64_t)set * gridDim.y + o) * gridDim.x + blockIdx.x] = t;
+  }
+}
+template <typename R>
+__global__ void k_tn_dot_sum(const cx<R>* __restrict__ partial, int n_part, cx<R>* __restrict__ C, int64_t sC,
+                             int n_out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const int64_t set = blockIdx.y;
+  const cx<R>* src = partial + (set * n_out + o) * n_part;
+  cx<R> t = mk<R>(0, 0);
+  for (int i = 0; i < n_part; ++i) {
+    t.x += src[i].x;
+    t.y += src[i].y;
+  }
+  C[set * sC + o] = t;
 }
 
 // Tiled complex GEMM with the permutation folded into the gathers: a CTA owns a 64 x 64 tile of
@@ -294,6 +350,40 @@ __global__ void k_tn_final(const cx<R>* __restrict__ last, int64_t sL, cx<R>* __
   dst->y += v.y;
 }
 
+constexpr int DOT_MAX_OUT_LOG2 = 6, DOT_MIN_K_LOG2 = 12, DOT_BLOCKS = 128;
+
+// Tensor-core lowering of one step: which operand provides accumulator rows, image geometry, pack tables.
+struct TcStep {
+  bool shape_ok = false;  // rows >= 128, columns >= 16
+  bool swap = false;      // accumulator rows come from the rhs (its free indices outnumber the lhs's)
+  int c_t = 0, kblocks = 0, tiles_a = 0, tiles_b = 0, stages = 0;
+  int64_t img_a_z = 0, img_b_z = 0;  // image bytes per z (= parameter set x kept-shared index value)
+  tc::PackParams pa, pb;
+};
+
+static void tc_pack_tables(tc::PackParams& P, const int8_t* row_bits, int n_row, const int8_t* k_bits, int n_k,
+                           const int8_t* b_bits, int n_b, bool is_b, int rows_t_log2) {
+  memset(&P, 0, sizeof(P));
+  P.n_row = n_row;
+  P.n_k = n_k;
+  P.n_b = n_b;
+  P.is_b = is_b ? 1 : 0;
+  P.rows_t_log2 = rows_t_log2;
+  P.kblocks = n_k > 4 ? 1 << (n_k - 4) : 1;
+  for (int j = 0; j < n_row; ++j) P.row_bits[j] = row_bits[j];
+  for (int j = 0; j < n_k; ++j) P.k_bits[j] = k_bits[j];
+  for (int j = 0; j < n_b; ++j) P.b_bits[j] = b_bits[j];
+  std::vector<std::pair<int, int>> loc;  // (source bit, value in r << 4 | kk)
+  for (int j = 0; j < rows_t_log2; ++j) loc.push_back({row_bits[j], 1 << (4 + j)});
+  for (int j = 0; j < std::min(n_k, 4); ++j) loc.push_back({k_bits[j], 1 << j});
+  std::sort(loc.begin(), loc.end());
+  P.n_local = (int)loc.size();
+  for (size_t j = 0; j < loc.size(); ++j) {
+    P.local_src[j] = (int8_t)loc[j].first;
+    P.local_dst[j] = (int16_t)loc[j].second;
+  }
+}
+
 }  // namespace tq
 
 using namespace tq;
@@ -313,6 +403,12 @@ struct tq_tn_plan {
   std::vector<StepDev> dev;
   double flops = 0;
   int width = 0;
+  // tensor-core path (complex64 only): per-step operand-image descriptions
+  std::vector<TcStep> tc;
+  int tc_enabled = 1;      // TQ_TN_OPT_TENSOR_CORE
+  int tc_min_log2 = 20;    // TQ_TN_OPT_TC_MIN_LOG2: a step runs on tensor cores when k+m+n+b >= this
+  int tc_chunk = 2;        // TQ_TN_OPT_TC_CHUNK: k-blocks accumulated in TMEM between round-to-nearest drains
+  int num_sms = 148;
 };
 
 extern "C" {
@@ -534,12 +630,18 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
     d.n_m = st.n_m;
     d.n_n = st.n_n;
     d.n_b = st.n_b;
-    TQ_REQUIRE(st.n_k <= 24, TQ_E_UNSUPPORTED, "tq_tn_plan_create: step %d contracts 2^%d terms", s, st.n_k);
+    TQ_REQUIRE(st.n_k <= 24 || st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2, TQ_E_UNSUPPORTED,
+               "tq_tn_plan_create: step %d contracts 2^%d terms", s, st.n_k);
     for (int j = 0; j < st.n_m; ++j) d.a_m[j] = st.lhs_bits[st.n_k + j];
     for (int j = 0; j < st.n_b; ++j) d.a_b[j] = st.lhs_bits[st.n_k + st.n_m + j];
     for (int j = 0; j < st.n_n; ++j) d.b_n[j] = st.rhs_bits[st.n_k + j];
     for (int j = 0; j < st.n_b; ++j) d.b_b[j] = st.rhs_bits[st.n_k + st.n_n + j];
-    const int K = 1 << st.n_k;
+    for (int j = 0; j < st.n_k; ++j) {
+      d.a_k[j] = st.lhs_bits[j];
+      d.b_k[j] = st.rhs_bits[j];
+    }
+    const bool is_dot = st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2;
+    const int K = 1 << (is_dot ? DOT_LO : st.n_k);
     std::vector<int32_t> ka(K), kb(K);
     for (int k = 0; k < K; ++k) {
       uint32_t a = 0, b = 0;
@@ -562,8 +664,75 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
     d.ka = p->d_ka[s];
     d.kb = p->d_kb[s];
   }
+  // tensor-core lowering (complex64): the operand with more free indices provides the 128 accumulator rows
+  p->tc.resize(n_steps);
+  {
+    int dev_id = 0, sms = 0;
+    if (cudaGetDevice(&dev_id) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id) == cudaSuccess && sms > 0)
+      p->num_sms = sms;
+    (void)cudaGetLastError();
+  }
+  for (int s = 0; s < n_steps && dtype == TQ_C64; ++s) {
+    const tq_tn_step& st = p->steps[s];
+    TcStep& T = p->tc[s];
+    T.swap = st.n_n > st.n_m;
+    const int n_row = T.swap ? st.n_n : st.n_m, n_col = T.swap ? st.n_m : st.n_n;
+    T.shape_ok = n_row >= 7 && n_col >= 4 && n_row + n_col + st.n_b <= 31;
+    if (!T.shape_ok) continue;
+    const int col_t_log2 = std::min(n_col, 7);
+    T.c_t = 1 << col_t_log2;
+    T.kblocks = st.n_k > 4 ? 1 << (st.n_k - 4) : 1;
+    T.tiles_a = 1 << (n_row - 7);
+    T.tiles_b = 1 << (n_col - col_t_log2);
+    T.stages = tc::num_stages(T.c_t);
+    T.img_a_z = (int64_t)T.tiles_a * T.kblocks * tc::A_CHUNK;
+    T.img_b_z = (int64_t)T.tiles_b * T.kblocks * tc::b_chunk_bytes(T.c_t);
+    const int8_t* lhs_k = st.lhs_bits;
+    const int8_t* lhs_m = st.lhs_bits + st.n_k;
+    const int8_t* lhs_b = st.lhs_bits + st.n_k + st.n_m;
+    const int8_t* rhs_k = st.rhs_bits;
+    const int8_t* rhs_n = st.rhs_bits + st.n_k;
+    const int8_t* rhs_b = st.rhs_bits + st.n_k + st.n_n;
+    if (!T.swap) {
+      tc_pack_tables(T.pa, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, false, 7);
+      tc_pack_tables(T.pb, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, true, col_t_log2);
+    } else {
+      tc_pack_tables(T.pa, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, false, 7);
+      tc_pack_tables(T.pb, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, true, col_t_log2);
+    }
+  }
   *out = P.release();
   return TQ_OK;
+}
+
+int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
+  TQ_REQUIRE(p, TQ_E_INVALID, "tq_tn_plan_set_option: null plan");
+  switch (option) {
+    case TQ_TN_OPT_TENSOR_CORE:
+      p->tc_enabled = value != 0;
+      return TQ_OK;
+    case TQ_TN_OPT_TC_MIN_LOG2:
+      p->tc_min_log2 = value;
+      return TQ_OK;
+    case TQ_TN_OPT_TC_CHUNK:
+      TQ_REQUIRE(value >= 1, TQ_E_INVALID, "tq_tn_plan_set_option: chunk must be >= 1");
+      p->tc_chunk = value;
+      return TQ_OK;
+    default:
+      TQ_REQUIRE(false, TQ_E_INVALID, "tq_tn_plan_set_option: unknown option %d", option);
+  }
+}
+
+/* 0: one thread per output element, 1: tiled fp32 FMA GEMM, 2: tcgen05 split-TF32 GEMM, 3: split-K reduction */
+int32_t tq_tn_plan_step_kernel(const tq_tn_plan* p, int32_t s) {
+  if (!p || s < 0 || s >= (int)p->steps.size()) return TQ_E_INVALID;
+  const tq_tn_step& st = p->steps[s];
+  if (st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2) return 3;
+  if (p->dtype == TQ_C64 && p->tc_enabled && p->tc[s].shape_ok &&
+      st.n_k + st.n_m + st.n_n + st.n_b >= p->tc_min_log2)
+    return 2;
+  return (st.n_m >= 6 && st.n_n >= 6 && st.n_k >= 4) ? 1 : 0;
 }
 
 int32_t tq_tn_plan_num_steps(const tq_tn_plan* p) { return p ? (int32_t)p->steps.size() : -1; }
@@ -576,28 +745,126 @@ int32_t tq_tn_plan_get_step(const tq_tn_plan* p, int32_t s, tq_tn_step* out) {
   return TQ_OK;
 }
 
+/* bit 0: the step repeats for every slice, bit 1: it carries the parameter-set batch dimension */
+int32_t tq_tn_plan_step_flags(const tq_tn_plan* p, int32_t s) {
+  if (!p || s < 0 || s >= (int)p->steps.size()) return TQ_E_INVALID;
+  return (p->dep_slice[s] ? 1 : 0) | (p->dep_batch[s] ? 2 : 0);
+}
+
+static size_t tn_image_bytes(const tq_tn_plan* p, int64_t batch) {
+  size_t need = 0;
+  for (size_t s = 0; s < p->steps.size(); ++s) {
+    const int kernel = tq_tn_plan_step_kernel(p, (int32_t)s);
+    if (kernel == 3) {  // partial sums of the split-K reduction
+      const tq_tn_step& st = p->steps[s];
+      const size_t cs = p->dtype == TQ_C64 ? 8 : 16;
+      need = std::max(need, (size_t)(p->dep_batch[s] ? batch : 1) * ((size_t)DOT_BLOCKS << (st.n_m + st.n_n + st.n_b)) * cs);
+    }
+    if (kernel != 2) continue;
+    const int64_t nz = (p->dep_batch[s] ? batch : 1) << p->steps[s].n_b;
+    need = std::max(need, (size_t)((p->tc[s].img_a_z + p->tc[s].img_b_z) * nz));
+  }
+  return need;
+}
+
 size_t tq_tn_workspace_bytes(const tq_tn_plan* p, int64_t batch) {
   if (!p || batch <= 0) return 0;
   const size_t cs = p->dtype == TQ_C64 ? 8 : 16;
-  return (size_t)(p->arena_shared + p->arena_set * batch) * cs + 512;
+  const size_t arenas = ((size_t)(p->arena_shared + p->arena_set * batch) * cs + 1023) & ~(size_t)1023;
+  return arenas + tn_image_bytes(p, batch) + 1024;
 }
 
 }  // extern "C"
 
 namespace tq {
 
+static int tc_setup_once() {
+  static int done = 0;
+  if (done) return TQ_OK;
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::SMEM_BUDGET + 1024));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::SMEM_BUDGET + 1024));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::SMEM_BUDGET + 1024));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  tc::SMEM_BUDGET + 1024));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_pack<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  done = 1;
+  return TQ_OK;
+}
+
+// pack both operands into images, then one persistent tcgen05 GEMM over all (z, row tile, column tile)
+static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t sa, const cx<float>* b, int64_t sb,
+                       cx<float>* c, int64_t sc, int64_t sets, uint8_t* images, cudaStream_t st,
+                       cudaEvent_t ev_packed) {
+  int rc = tc_setup_once();
+  if (rc) return rc;
+  const tq_tn_step& stp = p->steps[s];
+  const TcStep& T = p->tc[s];
+  const int64_t nz = sets << stp.n_b;
+  TQ_REQUIRE(nz < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step %d has %lld batched GEMMs", s, (long long)nz);
+  tc::PackParams pa = T.pa, pb = T.pb;
+  pa.src = reinterpret_cast<const float2*>(T.swap ? b : a);
+  pa.src_set_stride = T.swap ? sb : sa;
+  pa.img = images;
+  pa.img_z_stride = T.img_a_z;
+  pb.src = reinterpret_cast<const float2*>(T.swap ? a : b);
+  pb.src_set_stride = T.swap ? sa : sb;
+  pb.img = images + T.img_a_z * nz;
+  pb.img_z_stride = T.img_b_z;
+  tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_a * T.kblocks), (unsigned)nz), 256, tc::A_CHUNK, st>>>(pa);
+  tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_b * T.kblocks), (unsigned)nz), 256, tc::b_chunk_bytes(T.c_t), st>>>(pb);
+  TQ_CUDA_OK(cudaGetLastError());
+  if (ev_packed) TQ_CUDA_OK(cudaEventRecord(ev_packed, st));
+  tc::GemmParams g;
+  memset(&g, 0, sizeof(g));
+  g.img_a = pa.img;
+  g.img_b = pb.img;
+  g.c = reinterpret_cast<float2*>(c);
+  g.img_a_z = T.img_a_z;
+  g.img_b_z = T.img_b_z;
+  g.c_set_stride = sc;
+  g.c_rs = T.swap ? 1 : ((int64_t)1 << stp.n_n);
+  g.c_cs = T.swap ? ((int64_t)1 << stp.n_n) : 1;
+  g.tiles_a = T.tiles_a;
+  g.tiles_b = T.tiles_b;
+  g.kblocks = T.kblocks;
+  g.chunk = std::max(1, p->tc_chunk);
+  g.n_z = (int32_t)nz;
+  g.n_b_log2 = stp.n_b;
+  g.stages = T.stages;
+  g.c_bb_stride = (int64_t)1 << (stp.n_m + stp.n_n);
+  const int64_t total = (int64_t)T.tiles_a * T.tiles_b * nz;
+  const unsigned grid = (unsigned)std::min<int64_t>(total, p->num_sms);
+  const size_t smem = tc::SMEM_BUDGET + 1024;
+  switch (T.c_t) {
+    case 16: tc::k_tc_gemm<16><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+    case 32: tc::k_tc_gemm<32><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+    case 64: tc::k_tc_gemm<64><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+    default: tc::k_tc_gemm<128><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+  }
+  TQ_CUDA_OK(cudaGetLastError());
+  return TQ_OK;
+}
+
+// step_ms (optional, profiling): 2 floats per step = [whole step, of which operand packing] in milliseconds,
+// for the slice-invariant steps and the steps of slice s_begin; forces a synchronisation.
 template <typename R>
 static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const int64_t* strides, int64_t B,
                          int64_t s_begin, int64_t s_end, void* out, void* workspace, size_t ws_bytes,
-                         cudaStream_t st) {
+                         cudaStream_t st, float* step_ms) {
   TQ_REQUIRE(ws_bytes >= tq_tn_workspace_bytes(p, B), TQ_E_WORKSPACE, "tq_tn_contract: workspace too small");
   const int n_in = p->n_in;
   const int n_steps = (int)p->steps.size();
   cx<R>* shared = (cx<R>*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   cx<R>* perset = shared + p->arena_shared;
-  bool any_batch = false;
-  for (int t = 0; t < n_in; ++t) any_batch |= p->in_batched[t] != 0;
-  const int64_t out_sets = any_batch ? B : 1;
+  uint8_t* images = (uint8_t*)(((uintptr_t)(perset + p->arena_set * B) + 1023) & ~(uintptr_t)1023);
+  std::vector<cudaEvent_t> ev;
+  if (step_ms) {
+    ev.resize(3 * (size_t)n_steps);
+    for (auto& e : ev) TQ_CUDA_OK(cudaEventCreate(&e));
+  }
 
   auto tensor_ptr = [&](int t, int64_t slice, const cx<R>*& ptr, int64_t& stride) {
     if (t < n_in) {
@@ -628,7 +895,22 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     cx<R>* c = const_cast<cx<R>*>(c0);
     const int64_t sets = p->dep_batch[s] ? B : 1;
     const int64_t n_out_elems = (int64_t)1 << (stp.n_m + stp.n_n + stp.n_b);
-    if (stp.n_m >= 6 && stp.n_n >= 6 && stp.n_k >= 4) {
+    const int kernel = tq_tn_plan_step_kernel(p, s);
+    const bool timed = step_ms && (slice == s_begin || !p->dep_slice[s]);
+    if (timed) TQ_CUDA_OK(cudaEventRecord(ev[3 * s], st));
+    if (kernel == 2) {
+      if constexpr (sizeof(R) == 4) {
+        int rc = run_step_tc(p, s, a, sa, b, sb, c, sc, sets, images, st, timed ? ev[3 * s + 1] : nullptr);
+        if (rc) return rc;
+      }
+    } else if (kernel == 3) {
+      const int nblk = std::min(DOT_BLOCKS, 1 << (stp.n_k - DOT_LO));
+      TQ_REQUIRE(sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");
+      cx<R>* partial = reinterpret_cast<cx<R>*>(images);
+      k_tn_dot<R><<<dim3((unsigned)nblk, (unsigned)n_out_elems, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, partial, d);
+      k_tn_dot_sum<R><<<dim3((unsigned)((n_out_elems + 63) / 64), (unsigned)sets), 64, 0, st>>>(
+          partial, nblk, c, sc, (int)n_out_elems);
+    } else if (kernel == 1) {
       const int64_t blocks = n_out_elems >> 12;
       TQ_REQUIRE(blocks < ((int64_t)1 << 31) && sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");
       k_tn_gemm<R><<<dim3((unsigned)blocks, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, c, sc, d);
@@ -638,6 +920,10 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
       k_tn_step<R><<<dim3((unsigned)blocks, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, c, sc, d, n_out_elems);
     }
     TQ_CUDA_OK(cudaGetLastError());
+    if (timed) {
+      if (kernel != 2) TQ_CUDA_OK(cudaEventRecord(ev[3 * s + 1], st));
+      TQ_CUDA_OK(cudaEventRecord(ev[3 * s + 2], st));
+    }
     return TQ_OK;
   };
   int rc;
@@ -657,20 +943,30 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     int64_t sl;
     tensor_ptr(n_in + n_steps - 1, slice, last, sl);
     const int64_t sets = p->dep_batch[n_steps - 1] ? B : 1;
-    (void)out_sets;
     k_tn_final<R><<<dim3((unsigned)((n_final + 255) / 256), (unsigned)sets), 256, 0, st>>>(last, sl, (cx<R>*)out,
                                                                                           n_final, f, n_final);
     TQ_CUDA_OK(cudaGetLastError());
     if (!last_dep_slice) break;  // nothing depends on the slice index: one pass is the whole sum
+  }
+  if (step_ms) {
+    TQ_CUDA_OK(cudaStreamSynchronize(st));
+    for (int s = 0; s < n_steps; ++s) {
+      float whole = 0, pack = 0;
+      TQ_CUDA_OK(cudaEventElapsedTime(&whole, ev[3 * s], ev[3 * s + 2]));
+      if (tq_tn_plan_step_kernel(p, s) == 2) TQ_CUDA_OK(cudaEventElapsedTime(&pack, ev[3 * s], ev[3 * s + 1]));
+      step_ms[2 * s] = whole;
+      step_ms[2 * s + 1] = pack;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
   }
   return TQ_OK;
 }
 
 }  // namespace tq
 
-extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
-                              int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
+                           int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
+                           size_t workspace_bytes, void* stream, float* step_ms) {
   TQ_REQUIRE(p && inputs && out && workspace && batch > 0, TQ_E_INVALID, "tq_tn_contract: null argument");
   TQ_REQUIRE(!p->steps.empty(), TQ_E_INVALID, "tq_tn_contract: empty plan");
   const int64_t ns = (int64_t)1 << p->n_sliced;
@@ -679,7 +975,22 @@ extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, co
              (long long)slice_end, (long long)ns);
   if (p->dtype == TQ_C64)
     return contract_impl<float>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
-                                workspace_bytes, (cudaStream_t)stream);
+                                workspace_bytes, (cudaStream_t)stream, step_ms);
   return contract_impl<double>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
-                               workspace_bytes, (cudaStream_t)stream);
+                               workspace_bytes, (cudaStream_t)stream, step_ms);
+}
+
+extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
+                              int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return tn_contract_any(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace, workspace_bytes,
+                         stream, nullptr);
+}
+
+extern "C" int tq_tn_profile(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
+                             int64_t batch, int64_t slice, void* out, void* workspace, size_t workspace_bytes,
+                             void* stream, float* step_ms) {
+  TQ_REQUIRE(step_ms, TQ_E_INVALID, "tq_tn_profile: step_ms is null");
+  return tn_contract_any(p, inputs, input_strides, batch, slice, slice + 1, out, workspace, workspace_bytes, stream,
+                         step_ms);
 }

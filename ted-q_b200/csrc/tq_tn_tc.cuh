@@ -1,0 +1,378 @@
+// tq_tn_tc.cuh — tensor-core path of the contraction executor (complex64 steps, sm_100a only).
+//
+// Replaces the arithmetic of the third-party tree.contract call (pytorch_backend.py:276,:339 hand every
+// pairwise step to torch.tensordot = cgemm) for the GEMM-shaped steps of a plan.
+//
+// One complex GEMM  C[r, c] = sum_k A[r, k] * B[c, k]  (A = the operand with more free indices) is run as ONE
+// real TF32 GEMM on tcgen05 with fp32 accumulation in TMEM:
+//
+//   A'' [R][2K]   row r        = (Re A[r,0], Im A[r,0], Re A[r,1], Im A[r,1], ...)          (native complex layout)
+//   B'' [2C][2K]  row c        = (Re B, -Im B, ...)   -> accumulator column c       = Re C[r, c]
+//                 row C_t + c  = (Im B,  Re B, ...)   -> accumulator column C_t + c = Im C[r, c]       ("4M")
+//
+// and every fp32 operand is split  x = hi + lo  (hi = tf32(x), lo = tf32(x - hi)); the accumulator receives
+// hi*hi + hi*lo + lo*hi  (error-compensated split-TF32: the dropped lo*lo term is 2^-22 relative).  A complex
+// MAC therefore costs 3 x 8 = 24 TF32 flops for 8 algorithmic flops.
+//
+// Data movement: a pack kernel folds the step's bit permutation, the hi/lo split and the 128-byte shared-memory
+// swizzle into "operand images" — every (row tile, k block) is one contiguous chunk in HBM that is exactly the
+// shared-memory image the MMA wants, so the GEMM kernel's producer is two bulk-async (TMA engine) copies per
+// stage, no tensor maps.  GEMM kernel: persistent, warp-specialised (bulk-copy producer / single-thread MMA
+// issuer / 4 epilogue warps), 2-4 smem stages, double-buffered TMEM accumulator (2 x 256 columns).
+#pragma once
+#include "tq_common.h"
+
+namespace tq {
+namespace tc {
+
+constexpr int ROWS = 128;                 // accumulator rows per tile (TMEM lanes)
+constexpr int KB_CPLX = 16;               // complex k per k-block  (= 32 reals = one 128-byte swizzle row)
+constexpr int ROW_BYTES = 128;
+constexpr int A_PLANE = ROWS * ROW_BYTES; // 16 KiB: one plane (hi or lo) of an A tile
+constexpr int A_CHUNK = 2 * A_PLANE;      // hi + lo
+constexpr int ACC_WARPS = 8;              // accumulation / epilogue warps (two per TMEM lane quadrant)
+constexpr int GEMM_THREADS = 64 + 32 * ACC_WARPS;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 accumulate
+constexpr int SMEM_BUDGET = 220 * 1024;
+
+__host__ __device__ inline int b_plane_bytes(int c_t) { return 2 * c_t * ROW_BYTES; }  // Re rows + Im rows
+__host__ __device__ inline int b_chunk_bytes(int c_t) { return 2 * b_plane_bytes(c_t); }
+__host__ __device__ inline int stage_bytes(int c_t) { return A_CHUNK + b_chunk_bytes(c_t); }
+inline int num_stages(int c_t) {
+  int s = SMEM_BUDGET / stage_bytes(c_t);
+  return s > 4 ? 4 : s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must become a launch error, never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin)
+    if ((spin & 1023u) == 0 && clock64() - t0 > 6000000000ll) __trap();  // ~3 s
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups of 1024 B (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pack: bit-permuted complex operand -> operand image
+// ---------------------------------------------------------------------------------------------------------
+struct PackParams {
+  const float2* src;
+  uint8_t* img;
+  int64_t src_set_stride;   // complex entries between parameter sets (0: shared)
+  int64_t img_z_stride;     // bytes between consecutive z (= set * 2^n_b + bb) images
+  int32_t n_row, n_k, n_b;  // log2 extents
+  int32_t is_b;             // 0: A image (ROWS rows per tile), 1: B image (c_t rows -> 2 c_t image rows)
+  int32_t rows_t_log2;      // log2 rows per tile (7 for A, log2(c_t) for B)
+  int32_t kblocks;          // max(1, K / 16)
+  int32_t n_local;          // local bits handled inside one block = rows_t_log2 + min(n_k, 4)
+  int8_t row_bits[32], k_bits[32], b_bits[32];  // source bit of row / k / kept-shared index bit j
+  int8_t local_src[16];     // source bit of local element bit j (sorted: ascending source position)
+  int16_t local_dst[16];    // its value in (r << 4 | kk)
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_tc_pack(const __grid_constant__ PackParams p) {
+  extern __shared__ __align__(16) uint8_t pk_smem[];
+  const int tid = threadIdx.x;
+  const int rows_t = 1 << p.rows_t_log2;
+  const int plane = p.is_b ? b_plane_bytes(rows_t) : A_PLANE;
+  const int chunk = 2 * plane;
+  uint32_t blk = blockIdx.x;
+  const uint32_t kb = blk % (uint32_t)p.kblocks;
+  const uint32_t tile = blk / (uint32_t)p.kblocks;
+  const uint32_t z = blockIdx.y;
+  const uint32_t bb = z & ((1u << p.n_b) - 1u);
+  const uint32_t set = z >> p.n_b;
+  // base source offset of this (set, bb, tile, kb)
+  int64_t base = (int64_t)set * p.src_set_stride;
+  for (int j = 0; j < p.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << p.b_bits[j];
+  for (int j = p.rows_t_log2; j < p.n_row; ++j) base |= (int64_t)((tile >> (j - p.rows_t_log2)) & 1u) << p.row_bits[j];
+  for (int j = 4; j < p.n_k; ++j) base |= (int64_t)((kb >> (j - 4)) & 1u) << p.k_bits[j];
+  if (p.n_k < 4) {  // K padded to one k-block: the missing columns are zero
+    for (int i = tid; i < chunk / 16; i += THREADS) reinterpret_cast<float4*>(pk_smem)[i] = make_float4(0, 0, 0, 0);
+    __syncthreads();
+  }
+  const float2* src = p.src + base;
+  const int n_el = 1 << p.n_local;
+  for (int e = tid; e < n_el; e += THREADS) {
+    uint32_t so = 0, d = 0;
+    for (int j = 0; j < p.n_local; ++j)
+      if ((e >> j) & 1) {
+        so |= 1u << p.local_src[j];
+        d |= (uint32_t)p.local_dst[j];
+      }
+    const float2 v = __ldg(src + so);
+    const uint32_t r = d >> 4, kk = d & 15u;
+    const float hr = to_tf32(v.x), hi = to_tf32(v.y);
+    const float lr = to_tf32(v.x - hr), li = to_tf32(v.y - hi);
+    const uint32_t in_row = ((((kk >> 1) ^ (r & 7u)) << 4) | ((kk & 1u) << 3));
+    if (!p.is_b) {
+      const uint32_t o = r * ROW_BYTES + in_row;
+      *reinterpret_cast<float2*>(pk_smem + o) = make_float2(hr, hi);
+      *reinterpret_cast<float2*>(pk_smem + plane + o) = make_float2(lr, li);
+    } else {
+      const uint32_t o_re = r * ROW_BYTES + in_row;             // -> Re C
+      const uint32_t o_im = (rows_t + r) * ROW_BYTES + in_row;  // -> Im C  ((rows_t + r) & 7 == r & 7)
+      *reinterpret_cast<float2*>(pk_smem + o_re) = make_float2(hr, -hi);
+      *reinterpret_cast<float2*>(pk_smem + o_im) = make_float2(hi, hr);
+      *reinterpret_cast<float2*>(pk_smem + plane + o_re) = make_float2(lr, -li);
+      *reinterpret_cast<float2*>(pk_smem + plane + o_im) = make_float2(li, lr);
+    }
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(p.img + (int64_t)z * p.img_z_stride +
+                                          ((int64_t)tile * p.kblocks + kb) * (int64_t)chunk);
+  for (int i = tid; i < chunk / 16; i += THREADS) dst[i] = reinterpret_cast<const float4*>(pk_smem)[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GEMM over operand images
+// ---------------------------------------------------------------------------------------------------------
+struct GemmParams {
+  const uint8_t* img_a;
+  const uint8_t* img_b;
+  float2* c;
+  int64_t img_a_z, img_b_z;  // bytes between z images
+  int64_t c_set_stride;      // complex entries between parameter sets of C
+  int64_t c_rs, c_cs;        // complex-entry stride of an accumulator row / column inside C
+  int32_t tiles_a, tiles_b, kblocks, n_z, n_b_log2, stages;
+  int32_t chunk;             // k-blocks accumulated inside the tensor core before a drain (see below)
+  int64_t c_bb_stride;       // complex entries between kept-shared index values (2^(n_m + n_n))
+};
+
+// Accumulation is two-level.  tcgen05 adds into its fp32 accumulator with round-toward-zero, a bias of about
+// 2e-8 per MMA that grows linearly with K (measured: 6e-5 at K = 4096).  So only `chunk` k-blocks (12 MMAs each)
+// are accumulated in TMEM; the 8 accumulation warps then drain that partial sum and add it to fp32 registers with
+// round-to-nearest while the MMA issuer fills the other TMEM buffer (Ootomo & Yokota's error-compensated scheme,
+// moved from mma.sync registers to TMEM).
+template <int C_T>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_tc_gemm(const __grid_constant__ GemmParams p) {
+  constexpr int HALF = C_T / 2;  // complex columns owned by one accumulation warp
+  extern __shared__ __align__(1024) uint8_t g_smem[];
+  __shared__ __align__(8) uint64_t bars[4 + 4 + 2 + 2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(g_smem) + 1023u) & ~1023u;
+  const int S = p.stages;
+  constexpr uint32_t sbytes = (uint32_t)(A_CHUNK + 4 * C_T * ROW_BYTES);
+  constexpr uint32_t b_plane = (uint32_t)(2 * C_T * ROW_BYTES);
+  constexpr uint32_t b_chunk = 2 * b_plane;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (10 + s); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), ACC_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int64_t tiles_per_z = (int64_t)p.tiles_a * p.tiles_b;
+  const int64_t total = tiles_per_z * p.n_z;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const int64_t z = t / tiles_per_z;
+        const int64_t r = t - z * tiles_per_z;
+        const int64_t tb = r / p.tiles_a, ta = r - tb * p.tiles_a;
+        const uint8_t* ga = p.img_a + z * p.img_a_z + ta * (int64_t)p.kblocks * A_CHUNK;
+        const uint8_t* gb = p.img_b + z * p.img_b_z + tb * (int64_t)p.kblocks * b_chunk;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), sbytes);
+          const uint32_t sa = smem0 + (uint32_t)stage * sbytes;
+          bulk_g2s(sa, ga + (int64_t)kb * A_CHUNK, A_CHUNK, full_bar(stage));
+          bulk_g2s(sa + A_CHUNK, gb + (int64_t)kb * b_chunk, b_chunk, full_bar(stage));
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc =
+          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * C_T >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk) {
+          const int kb1 = min(kb0 + p.chunk, p.kblocks);
+          mbar_wait(tempty_bar(as), aphase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem0 + (uint32_t)stage * sbytes;
+            const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_PLANE);
+            const uint64_t b_hi = smem_desc(sa + A_CHUNK), b_lo = smem_desc(sa + A_CHUNK + b_plane);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {  // 8 reals (32 B) of K per instruction
+              const uint64_t adv = (uint64_t)(ks * 2);
+              tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (uint32_t)((kb > kb0) | (ks > 0)));
+              tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc_mma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
+            tc_commit(empty_bar(stage));
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc_commit(tfull_bar(as));
+          if (++as == 2) {
+            as = 0;
+            aphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;           // TMEM lane quadrant this warp may read
+    const int h = (warp - 2) >> 2;    // which half of the complex columns it accumulates
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint32_t bb_mask = (1u << p.n_b_log2) - 1u;
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+      float acc_re[HALF], acc_im[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) acc_re[j] = acc_im[j] = 0.f;
+      for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk) {
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HALF);
+#pragma unroll
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
+          uint32_t re[16], im[16];
+          tc_ld16(taddr + (uint32_t)c0, re);
+          tc_ld16(taddr + (uint32_t)(C_T + c0), im);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < HALF) {
+              acc_re[c0 + j] += __uint_as_float(re[j]);
+              acc_im[c0 + j] += __uint_as_float(im[j]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+      const int64_t z = t / tiles_per_z;
+      const int64_t r = t - z * tiles_per_z;
+      const int64_t tb = r / p.tiles_a, ta = r - tb * p.tiles_a;
+      const int64_t set = z >> p.n_b_log2, bb = z & bb_mask;
+      const int64_t row = ta * ROWS + q * 32 + lane;
+      const int64_t col0 = tb * C_T + h * HALF;
+      float2* dst = p.c + set * p.c_set_stride + bb * p.c_bb_stride + row * p.c_rs + col0 * p.c_cs;
+      if (p.c_cs == 1) {
+#pragma unroll
+        for (int j = 0; j < HALF; j += 2)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(acc_re[j], acc_im[j], acc_re[j + 1], acc_im[j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) dst[j * p.c_cs] = make_float2(acc_re[j], acc_im[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+}  // namespace tc
+}  // namespace tq

@@ -161,9 +161,8 @@ class TNExecutor:
             self._amp = [net, info, None]
         return self._amp
 
-    def amplitude(self, flat: torch.Tensor, bits, slice_range=None):
-        """<bits| U(params) |0...0> for every parameter set -> complex [B].  Slices are sharded over ranks
-        (contract_parallel) and combined with one all-reduce."""
+    def _amplitude_operands(self, flat: torch.Tensor, bits):
+        """-> (plan, input pointers, strides, output tensor, workspace, keep-alive list)."""
         be = self.backend
         amp = self._amplitude_plan()
         net, info = amp[0], amp[1]
@@ -171,6 +170,8 @@ class TNExecutor:
             batched = [kind == OPD_GATE and self.gate_batched[ref] for kind, ref in net.operands]
             dt = capi.TQ_C64 if be._cdtype == torch.complex64 else capi.TQ_C128
             amp[2] = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
+            for opt, val in (self.ho.get("engine_opts") or {}).items():
+                amp[2].set_option(int(opt), int(val))
         plan = amp[2]
         plan_sv = be.plan()
         L = capi.lib()
@@ -199,7 +200,18 @@ class TNExecutor:
         any_b = any(st != 0 for st in strides)
         out = torch.zeros((B if any_b else 1, 1), dtype=cd, device=dev)
         ws_bytes = plan.workspace_bytes(B)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = getattr(self, "_amp_ws", None)
+        if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+            ws = self._amp_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        return plan, ptrs, strides, out, ws, ws_bytes, any_b, (gm, am)
+
+    def amplitude(self, flat: torch.Tensor, bits, slice_range=None):
+        """<bits| U(params) |0...0> for every parameter set -> complex [B].  Slices are sharded over ranks
+        (contract_parallel) and combined with one all-reduce."""
+        plan, ptrs, strides, out, ws, ws_bytes, any_b, _keep = self._amplitude_operands(flat, bits)
+        B = flat.shape[0]
+        dev = flat.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
         if slice_range is None:
             s0, s1, dist_on = self._slice_range(plan.n_slices)
         else:
@@ -212,6 +224,22 @@ class TNExecutor:
                 out.zero_()
             torch.distributed.all_reduce(torch.view_as_real(out))
         return out.reshape(-1).expand(B) if not any_b else out.reshape(-1)
+
+    def amplitude_profile(self, flat: torch.Tensor, bits, slice_id=0):
+        """Per-step timing of ONE slice of the amplitude contraction (tq_tn_profile): list of dicts with the step's
+        log2 extents, the kernel that ran it, milliseconds (whole / operand packing) and whether it repeats per
+        slice."""
+        plan, ptrs, strides, out, ws, ws_bytes, _, _keep = self._amplitude_operands(flat, bits)
+        dev = flat.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            ms = plan.profile(ptrs, strides, flat.shape[0], slice_id, out.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+        rows = []
+        for s in range(plan.n_steps):
+            st = plan.step(s)
+            rows.append({"step": s, "k": st[2], "m": st[3], "n": st[4], "b": st[5], "kernel": plan.step_kernel(s),
+                         "per_slice": bool(plan.step_flags(s) & 1), "ms": float(ms[s, 0]), "pack_ms": float(ms[s, 1])})
+        return rows
 
     def run(self, flat: torch.Tensor) -> torch.Tensor:
         be = self.backend

@@ -1,0 +1,135 @@
+"""GPU: the tcgen05 split-TF32 contraction kernel against a complex128 einsum of the same step, and against the
+fp32 FMA kernels it replaces (north_star: complex64 amplitudes within relative 1e-5).
+
+Every case is a two-tensor network handed to the C ABI (tq_tn_plan_create / tq_tn_contract) with the tensor-core
+threshold forced to zero, so that shapes the planner would normally leave on the FMA path run on tensor cores too:
+ragged K (padding), either operand providing the accumulator rows, permuted index orders (the pack kernel's bit
+permutation), kept-shared indices and batched parameter sets."""
+import numpy as np
+import pytest
+import torch
+
+from tedq_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _contract(inputs, output, arrays, batched, tensor_core, B=1, min_log2=0, chunk=None, c128=False):
+    plan = capi.TnPlan(inputs, output, [(0, 1)], [], batched, capi.TQ_C128 if c128 else capi.TQ_C64)
+    plan.set_option(capi.TN_OPT_TENSOR_CORE, 1 if tensor_core else 0)
+    plan.set_option(capi.TN_OPT_TC_MIN_LOG2, min_log2)
+    if chunk is not None:
+        plan.set_option(capi.TN_OPT_TC_CHUNK, chunk)
+    kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
+    dev = "cuda"
+    cd = torch.complex128 if c128 else torch.complex64
+    ts = [torch.tensor(a, dtype=cd, device=dev).contiguous() for a in arrays]
+    ptrs = [t.data_ptr() for t in ts]
+    strides = [int(np.prod(a.shape[1:])) if b else 0 for a, b in zip(arrays, batched)]
+    out = torch.zeros((B if any(batched) else 1, 1 << len(output)), dtype=cd, device=dev)
+    ws_bytes = plan.workspace_bytes(B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    plan.contract(ptrs, strides, B, 0, 1, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                  torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), kinds
+
+
+def _rand(rng, shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+
+def _case(rng, n_m, n_n, n_k, n_b, shuffle=True):
+    ids = list(range(n_m + n_n + n_k + n_b))
+    M, N, K, Bt = ids[:n_m], ids[n_m:n_m + n_n], ids[n_m + n_n:n_m + n_n + n_k], ids[n_m + n_n + n_k:]
+    a_idx, b_idx, o_idx = M + K + Bt, K + N + Bt, M + N + Bt
+    if shuffle:
+        for l in (a_idx, b_idx, o_idx):
+            rng.shuffle(l)
+    return a_idx, b_idx, o_idx
+
+
+def _einsum(a_idx, b_idx, o_idx, A, B, batch_a=False, batch_b=False):
+    sub = lambda idx, batched: ([51] if batched else []) + list(idx)
+    out_b = batch_a or batch_b
+    return np.einsum(A.astype(np.complex128), sub(a_idx, batch_a), B.astype(np.complex128), sub(b_idx, batch_b),
+                     sub(o_idx, out_b))
+
+
+SHAPES = [  # (n_m, n_n, n_k, n_b)
+    (7, 4, 0, 0), (7, 4, 3, 0), (7, 7, 4, 0), (8, 7, 5, 0), (4, 9, 6, 0), (10, 10, 8, 0), (7, 5, 1, 0),
+    (9, 8, 7, 0), (7, 6, 4, 2), (5, 8, 5, 1), (11, 7, 6, 0), (7, 11, 9, 0), (8, 8, 12, 0),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "m%d_n%d_k%d_b%d" % s)
+@pytest.mark.parametrize("shuffle", [False, True], ids=["canonical", "permuted"])
+def test_tc_step_matches_einsum(shape, shuffle):
+    n_m, n_n, n_k, n_b = shape
+    rng = np.random.RandomState(hash(shape) % 10000 + int(shuffle))
+    a_idx, b_idx, o_idx = _case(rng, n_m, n_n, n_k, n_b, shuffle)
+    A = _rand(rng, (2,) * len(a_idx))
+    B = _rand(rng, (2,) * len(b_idx))
+    ref = _einsum(a_idx, b_idx, o_idx, A, B).reshape(-1)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True)
+    assert kinds == [2], kinds                      # the tensor-core kernel really ran
+    scale = np.abs(ref).max()
+    assert np.abs(got.reshape(-1) - ref).max() <= 1e-5 * scale, np.abs(got.reshape(-1) - ref).max() / scale
+    fma, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], False)
+    assert 2 not in kinds
+    assert np.abs(fma.reshape(-1) - ref).max() <= 1e-5 * scale
+
+
+def test_tc_error_is_fp32_class():
+    """Split-TF32 with round-to-nearest drains keeps fp32-class accuracy at K = 4096 (a plain TF32 GEMM sits near
+    1e-3; accumulating the whole K inside the tensor core shows its round-toward-zero bias, ~6e-5)."""
+    rng = np.random.RandomState(3)
+    a_idx, b_idx, o_idx = _case(rng, 8, 8, 12, 0)
+    A, B = _rand(rng, (2,) * 20), _rand(rng, (2,) * 20)
+    ref = _einsum(a_idx, b_idx, o_idx, A, B).reshape(-1)
+    got, _ = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True)
+    rel = np.abs(got.reshape(-1) - ref).max() / np.abs(ref).max()
+    assert rel < 2e-6, rel
+    biased, _ = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, chunk=1 << 20)
+    rel_biased = np.abs(biased.reshape(-1) - ref).max() / np.abs(ref).max()
+    assert rel_biased > 4 * rel, (rel, rel_biased)
+
+
+@pytest.mark.parametrize("which", ["a", "b", "both"])
+def test_tc_step_batched_parameter_sets(which):
+    rng = np.random.RandomState(11)
+    n_sets = 3
+    a_idx, b_idx, o_idx = _case(rng, 8, 5, 6, 1)
+    ba, bb = which in ("a", "both"), which in ("b", "both")
+    A = _rand(rng, ((n_sets,) if ba else ()) + (2,) * len(a_idx))
+    B = _rand(rng, ((n_sets,) if bb else ()) + (2,) * len(b_idx))
+    ref = _einsum(a_idx, b_idx, o_idx, A, B, ba, bb).reshape(n_sets, -1)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [ba, bb], True, B=n_sets)
+    assert kinds == [2]
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_default_threshold_keeps_small_steps_off_tensor_cores():
+    rng = np.random.RandomState(5)
+    a_idx, b_idx, o_idx = _case(rng, 7, 4, 3, 0)
+    A, B = _rand(rng, (2,) * len(a_idx)), _rand(rng, (2,) * len(b_idx))
+    _, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, min_log2=20)
+    assert kinds == [0]
+
+
+@pytest.mark.parametrize("shape", [(0, 0, 13, 0), (2, 1, 14, 0), (0, 3, 12, 1), (0, 0, 21, 0)],
+                         ids=lambda s: "m%d_n%d_k%d_b%d" % s)
+@pytest.mark.parametrize("c128", [False, True], ids=["c64", "c128"])
+def test_split_k_reduction(shape, c128):
+    """The closing steps of an amplitude network: a few outputs, a long contracted extent."""
+    n_m, n_n, n_k, n_b = shape
+    rng = np.random.RandomState(n_k)
+    a_idx, b_idx, o_idx = _case(rng, n_m, n_n, n_k, n_b)
+    A, B = _rand(rng, (2,) * len(a_idx)), _rand(rng, (2,) * len(b_idx))
+    if c128:
+        A, B = A.astype(np.complex128) + 1e-9, B.astype(np.complex128) - 1e-9j
+    ref = _einsum(a_idx, b_idx, o_idx, A, B).reshape(-1)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, min_log2=20, c128=c128)
+    assert kinds == [3], kinds
+    tol = 1e-11 if c128 else 1e-5
+    assert np.abs(got.reshape(-1) - ref).max() <= tol * max(1.0, np.abs(ref).max())
