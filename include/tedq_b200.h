@@ -250,8 +250,10 @@ int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int6
                    void* cuda_stream);
 
 /* Profiling twin of tq_tn_contract for ONE slice: same work, plus CUDA events around every step.
- * step_ms[2*s] = milliseconds of step s, step_ms[2*s+1] = the part spent packing operand images (tensor-core
- * steps only).  Synchronises the stream.  Feeds bench.py's per-step roofline table. */
+ * step_ms has 2 * n_steps + 2 entries: step_ms[2*s] = milliseconds of step s, step_ms[2*s+1] = the part spent
+ * packing operand images (tensor-core steps only); step_ms[2*n_steps] = once-per-call packing of the
+ * slice-invariant operand images that per-slice steps reuse.  Synchronises the stream.  Feeds bench.py's per-step
+ * roofline table. */
 int tq_tn_profile(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
                   int64_t slice, void* out, void* workspace, size_t workspace_bytes, void* cuda_stream,
                   float* step_ms);

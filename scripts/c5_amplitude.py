@@ -44,6 +44,7 @@ tot = sum(r["ms"] for r in rows)
 print("one slice (+ invariant part): %.3f ms over %d steps; by kernel:" % (tot, len(rows)),
       {k: round(sum(r["ms"] for r in rows if r["kernel"] == k), 3) for k in (0, 1, 2)},
       "counts", {k: sum(1 for r in rows if r["kernel"] == k) for k in (0, 1, 2)})
+print("once-per-call packing of slice-invariant operand images: %.3f ms" % plan.last_pinned_pack_ms)
 per = [r for r in rows if r["per_slice"]]
 print("per-slice steps: %d, %.3f ms; invariant steps: %d, %.3f ms" % (
     len(per), sum(r["ms"] for r in per), len(rows) - len(per), sum(r["ms"] for r in rows if not r["per_slice"])))

@@ -401,10 +401,12 @@ class TnPlan:
         n = self.n_inputs
         ptrs = (C.c_void_p * n)(*input_ptrs)
         strides = (C.c_int64 * n)(*input_strides)
-        ms = (C.c_float * (2 * self.n_steps))()
+        ms = (C.c_float * (2 * self.n_steps + 2))()
         check(lib().tq_tn_profile(self.handle, ptrs, strides, batch, slice_id, out_ptr, ws_ptr, ws_bytes, stream, ms),
               "tq_tn_profile")
-        return np.asarray(ms, dtype=np.float32).reshape(self.n_steps, 2)
+        arr = np.asarray(ms, dtype=np.float32)
+        self.last_pinned_pack_ms = float(arr[2 * self.n_steps])
+        return arr[:2 * self.n_steps].reshape(self.n_steps, 2)
 
     def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
         n = self.n_inputs

@@ -358,6 +358,8 @@ struct TcStep {
   bool swap = false;      // accumulator rows come from the rhs (its free indices outnumber the lhs's)
   int c_t = 0, kblocks = 0, tiles_a = 0, tiles_b = 0, stages = 0;
   int64_t img_a_z = 0, img_b_z = 0;  // image bytes per z (= parameter set x kept-shared index value)
+  // a slice-invariant operand of a per-slice step is packed ONCE per call into a pinned image
+  bool pin_a = false, pin_b = false;
   tc::PackParams pa, pb;
 };
 
@@ -676,8 +678,18 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
   for (int s = 0; s < n_steps && dtype == TQ_C64; ++s) {
     const tq_tn_step& st = p->steps[s];
     TcStep& T = p->tc[s];
+    // Accumulator rows (2x image expansion) come from the operand with more free indices, unless exactly one
+    // operand changes per slice and is tall enough: then that one takes the rows (its per-slice image is the
+    // cheaper one to write) and the invariant operand's 4x image is packed once.
+    const bool lhs_var = t_slice[st.lhs] != 0, rhs_var = t_slice[st.rhs] != 0;
     T.swap = st.n_n > st.n_m;
+    if (lhs_var != rhs_var && std::min(st.n_m, st.n_n) >= 7) T.swap = rhs_var;
     const int n_row = T.swap ? st.n_n : st.n_m, n_col = T.swap ? st.n_m : st.n_n;
+    {
+      const bool a_var = T.swap ? rhs_var : lhs_var, b_var = T.swap ? lhs_var : rhs_var;
+      T.pin_a = p->dep_slice[s] && !a_var;
+      T.pin_b = p->dep_slice[s] && !b_var;
+    }
     T.shape_ok = n_row >= 7 && n_col >= 4 && n_row + n_col + st.n_b <= 31;
     if (!T.shape_ok) continue;
     const int col_t_log2 = std::min(n_col, 7);
@@ -751,6 +763,26 @@ int32_t tq_tn_plan_step_flags(const tq_tn_plan* p, int32_t s) {
   return (p->dep_slice[s] ? 1 : 0) | (p->dep_batch[s] ? 2 : 0);
 }
 
+// pinned images (slice-invariant operands of per-slice tensor-core steps): total bytes; offsets[2*s], [2*s+1]
+static size_t tn_pinned_bytes(const tq_tn_plan* p, int64_t batch, std::vector<int64_t>* offsets) {
+  size_t top = 0;
+  if (offsets) offsets->assign(2 * p->steps.size(), -1);
+  for (size_t s = 0; s < p->steps.size(); ++s) {
+    if (tq_tn_plan_step_kernel(p, (int32_t)s) != 2) continue;
+    const int64_t nz = (p->dep_batch[s] ? batch : 1) << p->steps[s].n_b;
+    const TcStep& T = p->tc[s];
+    if (T.pin_a) {
+      if (offsets) (*offsets)[2 * s] = (int64_t)top;
+      top += (size_t)(T.img_a_z * nz);
+    }
+    if (T.pin_b) {
+      if (offsets) (*offsets)[2 * s + 1] = (int64_t)top;
+      top += (size_t)(T.img_b_z * nz);
+    }
+  }
+  return top;
+}
+
 static size_t tn_image_bytes(const tq_tn_plan* p, int64_t batch) {
   size_t need = 0;
   for (size_t s = 0; s < p->steps.size(); ++s) {
@@ -762,9 +794,10 @@ static size_t tn_image_bytes(const tq_tn_plan* p, int64_t batch) {
     }
     if (kernel != 2) continue;
     const int64_t nz = (p->dep_batch[s] ? batch : 1) << p->steps[s].n_b;
-    need = std::max(need, (size_t)((p->tc[s].img_a_z + p->tc[s].img_b_z) * nz));
+    const TcStep& T = p->tc[s];
+    need = std::max(need, (size_t)(((T.pin_a ? 0 : T.img_a_z) + (T.pin_b ? 0 : T.img_b_z)) * nz));
   }
-  return need;
+  return need + tn_pinned_bytes(p, batch, nullptr);
 }
 
 size_t tq_tn_workspace_bytes(const tq_tn_plan* p, int64_t batch) {
@@ -794,33 +827,41 @@ static int tc_setup_once() {
   return TQ_OK;
 }
 
-// pack both operands into images, then one persistent tcgen05 GEMM over all (z, row tile, column tile)
+// Pack operands into images (mode bit 0), run one persistent tcgen05 GEMM over all (z, row tile, column tile)
+// (mode bit 1).  img_a / img_b: where each operand's image lives (scratch or pinned); skip_a / skip_b: that image
+// is pinned and already packed.
 static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t sa, const cx<float>* b, int64_t sb,
-                       cx<float>* c, int64_t sc, int64_t sets, uint8_t* images, cudaStream_t st,
-                       cudaEvent_t ev_packed) {
+                       cx<float>* c, int64_t sc, int64_t sets, uint8_t* img_a, uint8_t* img_b, bool pack_a,
+                       bool pack_b, bool gemm, cudaStream_t st, cudaEvent_t ev_packed) {
   int rc = tc_setup_once();
   if (rc) return rc;
   const tq_tn_step& stp = p->steps[s];
   const TcStep& T = p->tc[s];
   const int64_t nz = sets << stp.n_b;
   TQ_REQUIRE(nz < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step %d has %lld batched GEMMs", s, (long long)nz);
-  tc::PackParams pa = T.pa, pb = T.pb;
-  pa.src = reinterpret_cast<const float2*>(T.swap ? b : a);
-  pa.src_set_stride = T.swap ? sb : sa;
-  pa.img = images;
-  pa.img_z_stride = T.img_a_z;
-  pb.src = reinterpret_cast<const float2*>(T.swap ? a : b);
-  pb.src_set_stride = T.swap ? sa : sb;
-  pb.img = images + T.img_a_z * nz;
-  pb.img_z_stride = T.img_b_z;
-  tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_a * T.kblocks), (unsigned)nz), 256, tc::A_CHUNK, st>>>(pa);
-  tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_b * T.kblocks), (unsigned)nz), 256, tc::b_chunk_bytes(T.c_t), st>>>(pb);
+  if (pack_a) {
+    tc::PackParams pa = T.pa;
+    pa.src = reinterpret_cast<const float2*>(T.swap ? b : a);
+    pa.src_set_stride = T.swap ? sb : sa;
+    pa.img = img_a;
+    pa.img_z_stride = T.img_a_z;
+    tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_a * T.kblocks), (unsigned)nz), 256, tc::A_CHUNK, st>>>(pa);
+  }
+  if (pack_b) {
+    tc::PackParams pb = T.pb;
+    pb.src = reinterpret_cast<const float2*>(T.swap ? a : b);
+    pb.src_set_stride = T.swap ? sa : sb;
+    pb.img = img_b;
+    pb.img_z_stride = T.img_b_z;
+    tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_b * T.kblocks), (unsigned)nz), 256, tc::b_chunk_bytes(T.c_t), st>>>(pb);
+  }
   TQ_CUDA_OK(cudaGetLastError());
   if (ev_packed) TQ_CUDA_OK(cudaEventRecord(ev_packed, st));
+  if (!gemm) return TQ_OK;
   tc::GemmParams g;
   memset(&g, 0, sizeof(g));
-  g.img_a = pa.img;
-  g.img_b = pb.img;
+  g.img_a = img_a;
+  g.img_b = img_b;
   g.c = reinterpret_cast<float2*>(c);
   g.img_a_z = T.img_a_z;
   g.img_b_z = T.img_b_z;
@@ -859,10 +900,12 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   const int n_steps = (int)p->steps.size();
   cx<R>* shared = (cx<R>*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   cx<R>* perset = shared + p->arena_shared;
-  uint8_t* images = (uint8_t*)(((uintptr_t)(perset + p->arena_set * B) + 1023) & ~(uintptr_t)1023);
+  uint8_t* pinned = (uint8_t*)(((uintptr_t)(perset + p->arena_set * B) + 1023) & ~(uintptr_t)1023);
+  std::vector<int64_t> pin_off;
+  uint8_t* images = pinned + tn_pinned_bytes(p, B, &pin_off);
   std::vector<cudaEvent_t> ev;
   if (step_ms) {
-    ev.resize(3 * (size_t)n_steps);
+    ev.resize(3 * (size_t)n_steps + 2);
     for (auto& e : ev) TQ_CUDA_OK(cudaEventCreate(&e));
   }
 
@@ -884,7 +927,8 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
       }
     }
   };
-  auto run_step = [&](int s, int64_t slice) -> int {
+  // pin_only: pack the pinned (slice-invariant) operand images of step s and return
+  auto run_step = [&](int s, int64_t slice, bool pin_only) -> int {
     const tq_tn_step& stp = p->steps[s];
     const StepDev& d = p->dev[s];
     const cx<R>*a, *b, *c0;
@@ -896,11 +940,25 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     const int64_t sets = p->dep_batch[s] ? B : 1;
     const int64_t n_out_elems = (int64_t)1 << (stp.n_m + stp.n_n + stp.n_b);
     const int kernel = tq_tn_plan_step_kernel(p, s);
+    if (pin_only) {
+      if constexpr (sizeof(R) == 4) {
+        const TcStep& T = p->tc[s];
+        if (kernel == 2 && (T.pin_a || T.pin_b))
+          return run_step_tc(p, s, a, sa, b, sb, c, sc, sets, pinned + std::max<int64_t>(0, pin_off[2 * s]),
+                             pinned + std::max<int64_t>(0, pin_off[2 * s + 1]), T.pin_a, T.pin_b, false, st, nullptr);
+      }
+      return TQ_OK;
+    }
     const bool timed = step_ms && (slice == s_begin || !p->dep_slice[s]);
     if (timed) TQ_CUDA_OK(cudaEventRecord(ev[3 * s], st));
     if (kernel == 2) {
       if constexpr (sizeof(R) == 4) {
-        int rc = run_step_tc(p, s, a, sa, b, sb, c, sc, sets, images, st, timed ? ev[3 * s + 1] : nullptr);
+        const TcStep& T = p->tc[s];
+        const int64_t nz = sets << stp.n_b;
+        uint8_t* img_a = T.pin_a ? pinned + pin_off[2 * s] : images;
+        uint8_t* img_b = T.pin_b ? pinned + pin_off[2 * s + 1] : images + (T.pin_a ? 0 : T.img_a_z * nz);
+        int rc = run_step_tc(p, s, a, sa, b, sb, c, sc, sets, img_a, img_b, !T.pin_a, !T.pin_b, true, st,
+                             timed ? ev[3 * s + 1] : nullptr);
         if (rc) return rc;
       }
     } else if (kernel == 3) {
@@ -929,7 +987,11 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   int rc;
   // slice-invariant steps once, then the slice loop
   for (int s = 0; s < n_steps; ++s)
-    if (!p->dep_slice[s] && (rc = run_step(s, 0))) return rc;
+    if (!p->dep_slice[s] && (rc = run_step(s, 0, false))) return rc;
+  if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps], st));
+  for (int s = 0; s < n_steps; ++s)
+    if (p->dep_slice[s] && (rc = run_step(s, s_begin, true))) return rc;
+  if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps + 1], st));
   FinalDev f;
   memset(&f, 0, sizeof(f));
   f.rank = p->n_out;
@@ -938,7 +1000,7 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   const bool last_dep_slice = n_steps ? p->dep_slice[n_steps - 1] != 0 : false;
   for (int64_t slice = s_begin; slice < s_end; ++slice) {
     for (int s = 0; s < n_steps; ++s)
-      if (p->dep_slice[s] && (rc = run_step(s, slice))) return rc;
+      if (p->dep_slice[s] && (rc = run_step(s, slice, false))) return rc;
     const cx<R>* last;
     int64_t sl;
     tensor_ptr(n_in + n_steps - 1, slice, last, sl);
@@ -957,6 +1019,8 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
       step_ms[2 * s] = whole;
       step_ms[2 * s + 1] = pack;
     }
+    TQ_CUDA_OK(cudaEventElapsedTime(&step_ms[2 * n_steps], ev[3 * n_steps], ev[3 * n_steps + 1]));
+    step_ms[2 * n_steps + 1] = 0.f;
     for (auto& e : ev) cudaEventDestroy(e);
   }
   return TQ_OK;

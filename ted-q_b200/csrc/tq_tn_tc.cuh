@@ -136,7 +136,8 @@ struct PackParams {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_tc_pack(const __grid_constant__ PackParams p) {
-  extern __shared__ __align__(16) uint8_t pk_smem[];
+  static_assert(THREADS == 256, "element = tid + 256 * i");
+  extern __shared__ __align__(128) uint8_t pk_smem[];
   const int tid = threadIdx.x;
   const int rows_t = 1 << p.rows_t_log2;
   const int plane = p.is_b ? b_plane_bytes(rows_t) : A_PLANE;
@@ -157,36 +158,65 @@ k_tc_pack(const __grid_constant__ PackParams p) {
     __syncthreads();
   }
   const float2* src = p.src + base;
-  const int n_el = 1 << p.n_local;
-  for (int e = tid; e < n_el; e += THREADS) {
-    uint32_t so = 0, d = 0;
-    for (int j = 0; j < p.n_local; ++j)
-      if ((e >> j) & 1) {
-        so |= 1u << p.local_src[j];
-        d |= (uint32_t)p.local_dst[j];
-      }
-    const float2 v = __ldg(src + so);
-    const uint32_t r = d >> 4, kk = d & 15u;
-    const float hr = to_tf32(v.x), hi = to_tf32(v.y);
-    const float lr = to_tf32(v.x - hr), li = to_tf32(v.y - hi);
-    const uint32_t in_row = ((((kk >> 1) ^ (r & 7u)) << 4) | ((kk & 1u) << 3));
-    if (!p.is_b) {
-      const uint32_t o = r * ROW_BYTES + in_row;
-      *reinterpret_cast<float2*>(pk_smem + o) = make_float2(hr, hi);
-      *reinterpret_cast<float2*>(pk_smem + plane + o) = make_float2(lr, li);
-    } else {
-      const uint32_t o_re = r * ROW_BYTES + in_row;             // -> Re C
-      const uint32_t o_im = (rows_t + r) * ROW_BYTES + in_row;  // -> Im C  ((rows_t + r) & 7 == r & 7)
-      *reinterpret_cast<float2*>(pk_smem + o_re) = make_float2(hr, -hi);
-      *reinterpret_cast<float2*>(pk_smem + o_im) = make_float2(hi, hr);
-      *reinterpret_cast<float2*>(pk_smem + plane + o_re) = make_float2(lr, -li);
-      *reinterpret_cast<float2*>(pk_smem + plane + o_im) = make_float2(li, lr);
+  // element e = tid + 256 i: bits 0..7 come from tid (resolved once), bits 8.. from i.  Local bits are sorted by
+  // source position, so consecutive threads read ascending source addresses.
+  uint32_t so_t = 0, d_t = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < p.n_local && ((tid >> j) & 1)) {
+      so_t |= 1u << p.local_src[j];
+      d_t |= (uint32_t)p.local_dst[j];
+    }
+  const int iters = p.n_local > 8 ? 1 << (p.n_local - 8) : 1;
+  const bool active = p.n_local >= 8 || tid < (1 << p.n_local);
+  float2 v[8];
+  uint32_t dd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < iters && active) {
+      uint32_t so = so_t, d = d_t;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (8 + j < p.n_local && ((i >> j) & 1)) {
+          so |= 1u << p.local_src[8 + j];
+          d |= (uint32_t)p.local_dst[8 + j];
+        }
+      v[i] = __ldg(src + so);
+      dd[i] = d;
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < iters && active) {
+      const uint32_t r = dd[i] >> 4, kk = dd[i] & 15u;
+      const float hr = to_tf32(v[i].x), hi = to_tf32(v[i].y);
+      const float lr = to_tf32(v[i].x - hr), li = to_tf32(v[i].y - hi);
+      const uint32_t in_row = ((((kk >> 1) ^ (r & 7u)) << 4) | ((kk & 1u) << 3));
+      if (!p.is_b) {
+        const uint32_t o = r * ROW_BYTES + in_row;
+        *reinterpret_cast<float2*>(pk_smem + o) = make_float2(hr, hi);
+        *reinterpret_cast<float2*>(pk_smem + plane + o) = make_float2(lr, li);
+      } else {
+        const uint32_t o_re = r * ROW_BYTES + in_row;             // -> Re C
+        const uint32_t o_im = (rows_t + r) * ROW_BYTES + in_row;  // -> Im C  ((rows_t + r) & 7 == r & 7)
+        *reinterpret_cast<float2*>(pk_smem + o_re) = make_float2(hr, -hi);
+        *reinterpret_cast<float2*>(pk_smem + o_im) = make_float2(hi, hr);
+        *reinterpret_cast<float2*>(pk_smem + plane + o_re) = make_float2(lr, -li);
+        *reinterpret_cast<float2*>(pk_smem + plane + o_im) = make_float2(li, lr);
+      }
+    }
+  }
+  // the finished chunk leaves through the bulk-copy engine: one contiguous store per block
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  float4* dst = reinterpret_cast<float4*>(p.img + (int64_t)z * p.img_z_stride +
-                                          ((int64_t)tile * p.kblocks + kb) * (int64_t)chunk);
-  for (int i = tid; i < chunk / 16; i += THREADS) dst[i] = reinterpret_cast<const float4*>(pk_smem)[i];
+  if (tid == 0) {
+    uint8_t* dst = p.img + (int64_t)z * p.img_z_stride + ((int64_t)tile * p.kblocks + kb) * (int64_t)chunk;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(pk_smem)),
+                 "r"((uint32_t)chunk)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
