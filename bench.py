@@ -127,6 +127,28 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "c5":
+        n_timed = int(os.environ.get("TQ_C5_CPU_SLICES", "4"))
+        vals = []
+        t_all = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            dt, amps, n_slices, fl_slice = c5_cpu_slices(n_timed)
+            vals.append(1.0 / (dt * n_slices))
+        total = time.perf_counter() - t_all
+        value = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": "circuit_evals_per_sec", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+            "config": {"workload": "c5: 40-qubit 5x8 lattice random circuit, 12 cycles, amplitude <0|U|0>, "
+                                   f"{n_slices} slices", "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{n_timed} of {n_slices} slices per step with torch.tensordot complex64, "
+                                       f"extrapolated x{n_slices}; host has {os.cpu_count()} logical cores"},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
     spec, flat, cdt, desc = workload(args.workload)
     per_step_budget = float(os.environ.get("TQ_REF_STEP_SECONDS", "8"))
     rates, sets = [], 0
@@ -270,7 +292,48 @@ def measure_workload(name, steps, warmup, device, dist_on, world, do_e2e=True, d
     return res
 
 
-def measure_c5(steps, warmup, device, dist_on, world):
+C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "16")),
+            "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64}}
+
+
+def tf32_peak():
+    """No TF32 figure in MEASURED_PEAKS.json: half the measured bf16 burst (tcgen05 kind::tf32 runs at half the
+    kind::f16 rate), labelled derived."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["bf16_tflops"]) / 2.0, "derived: measured bf16 burst / 2"
+    except Exception:
+        return 1590.0 / 2.0, "derived from the fallback bf16 figure / 2"
+
+
+def c5_cpu_slices(n_slices_timed, slice_ids=None):
+    """Reference CPU arm of config 5: the same circuit, the same path and sliced indices, contracted slice by slice
+    with torch.tensordot on the host cores (what tree.contract(arrays, backend='torch') does,
+    pytorch_backend.py:339).  -> (seconds per slice, [slice amplitudes], n_slices, flops per slice)"""
+    import tedq_b200 as qb
+    from oracle import tn_ref
+    from tedq_b200 import planner, workloads as W
+
+    spec = W.lattice_rcs(5, 8, 12, seed=0, measure="state")
+    circ = W.build_circuit(spec, qb)
+    inputs, output = tn_ref.index_maps(circ)[0]
+    arrays = tn_ref.operands(circ, torch.zeros(0), torch.complex64)[0]
+    cap0 = np.array([1, 0], dtype=np.complex64)
+    inputs = [list(t) for t in inputs] + [[ix] for ix in output]
+    arrays = list(arrays) + [cap0] * 40
+    info = planner.find_path(inputs, [], repeats=C5_HYPER["max_repeats"], seed=0)
+    info = planner.slice_path(inputs, [], info, target_size_log2=27, target_num_slices=64)
+    ids = list(slice_ids) if slice_ids is not None else list(range(n_slices_timed))
+    tn_ref.contract_slice_torch(arrays, inputs, [], info.path, info.sliced, 0)   # warm-up (threads, allocator)
+    amps = []
+    t0 = time.perf_counter()
+    for sid in ids:
+        amps.append(complex(tn_ref.contract_slice_torch(arrays, inputs, [], info.path, info.sliced, sid)))
+    dt = (time.perf_counter() - t0) / max(1, len(ids))
+    return dt, amps, info.n_slices, 2.0 ** info.flops_log2
+
+
+def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
     """BASELINE config 5: 40-qubit lattice random circuit (5x8, 12 cycles), single amplitude <0..0|U|0..0>, sliced
     contraction; slices are sharded over ranks and combined with one all-reduce (strong scaling)."""
     import tedq_b200 as qb
@@ -278,8 +341,8 @@ def measure_c5(steps, warmup, device, dist_on, world):
 
     spec = W.lattice_rcs(5, 8, 12, seed=0)
     circ = W.build_circuit(spec, qb)
-    hyper = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "64")),
-             "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64, "contract_parallel": dist_on}}
+    hyper = {"max_repeats": C5_HYPER["max_repeats"],
+             "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=dist_on)}
     cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
     bits = [0] * 40
     for _ in range(max(1, warmup)):
@@ -305,24 +368,107 @@ def measure_c5(steps, warmup, device, dist_on, world):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     total_ms = float(t.item())
     flops = plan.flops * plan.n_slices
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            tf32_peak = float(json.load(fh)["bf16_tflops"]) / 2.0
-        kind = "derived: measured bf16 burst / 2 (no TF32 figure in MEASURED_PEAKS.json)"
-    except Exception:
-        tf32_peak, kind = 1590.0 / 2.0, "derived from fallback"
+    peak, kind = tf32_peak()
+    hbm_peak, _ = load_peaks()
     ach = flops * steps / (total_ms * 1e-3) / 1e12
-    return {
+
+    # per-step table of one slice (tq_tn_profile: CUDA events around every step)
+    rows = cc._tn.amplitude_profile(torch.zeros((1, 0), device=device), bits, 0)
+    per_slice = [r for r in rows if r["per_slice"]]
+    slice_ms = sum(r["ms"] for r in per_slice)
+    table = []
+    tc_flops = tc_ms = tc_gemm_ms = 0.0
+    for r in sorted(per_slice, key=lambda r: -r["ms"]):
+        if r["ms"] < 0.01 * slice_ms:
+            break
+        fl = 8.0 * 2.0 ** (r["k"] + r["m"] + r["n"] + r["b"])
+        byts = 8.0 * (2.0 ** (r["k"] + r["m"] + r["b"]) + 2.0 ** (r["k"] + r["n"] + r["b"]) + 2.0 ** (r["m"] + r["n"] + r["b"]))
+        t_fl = 3.0 * fl / (peak * 1e12)          # 4M x 3-term split-TF32: 24 TF32 flops per 8 algorithmic
+        t_by = byts / (hbm_peak * 1e9)
+        roof_ms = max(t_fl, t_by) * 1e3
+        table.append({"M": 2 ** r["m"], "N": 2 ** r["n"], "K": 2 ** r["k"], "batch": 2 ** r["b"],
+                      "kernel": ["k_tn_step", "k_tn_gemm", "k_tc_pack+k_tc_gemm", "k_tn_dot"][r["kernel"]],
+                      "ms": round(r["ms"], 4), "pack_ms": round(r["pack_ms"], 4),
+                      "algorithmic_tflops": round(fl / (r["ms"] * 1e-3) / 1e12, 2),
+                      "bound": "tensor" if t_fl > t_by else "hbm", "roofline_ms": round(roof_ms, 4),
+                      "frac": round(roof_ms / r["ms"], 3)})
+        if r["kernel"] == 2 and t_fl > t_by:
+            tc_flops += fl
+            tc_ms += r["ms"]
+            tc_gemm_ms += r["ms"] - r["pack_ms"]
+    res = {
         "value": steps / (total_ms * 1e-3), "unit": "evals/s", "ms_per_step": total_ms / steps, "dtype": "c64",
         "desc": f"c5: 40-qubit 5x8 lattice random circuit, 12 cycles, amplitude <0|U|0>, {plan.n_slices} slices, "
                 f"width {plan.width}, {plan.n_steps} pairwise steps, {flops:.3e} flop per amplitude",
         "amplitude": [float(amp.real), float(amp.imag)],
-        "roofline": {"bound": "tensor", "kernel": "k_tn_gemm", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": ach / tf32_peak, "traffic": None, "peak_kind": kind,
-                     "note": "8*M*N*K flops per complex GEMM step summed over the lowered plan"},
-        "clocks": sampler.summary(), "gpu_launches": int((plan.n_steps + 1) * plan.n_slices * steps),
+        "roofline": {
+            "bound": "tensor", "kernel": "k_tc_gemm", "unit": "TFLOP/s", "peak": peak, "peak_kind": kind,
+            # whole contraction (all 760 steps x 64 slices, packing and launch gaps included), algorithmic 8MNK flops
+            "achieved": ach, "frac": ach / peak, "traffic": None,
+            # the tensor-core-bound dominant steps of one slice
+            "dominant_steps_algorithmic_tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+            "dominant_steps_tf32_executed_tflops": 3 * tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+            "dominant_steps_frac_of_complex_gemm_roofline": 3 * tc_flops / (tc_ms * 1e-3) / 1e12 / peak if tc_ms else None,
+            "gemm_kernel_only_tf32_executed_tflops": 3 * tc_flops / (tc_gemm_ms * 1e-3) / 1e12 if tc_gemm_ms else None,
+            "note": "achieved/frac count ALGORITHMIC flops (8*M*N*K per complex GEMM) over the whole amplitude against "
+                    "the TF32 peak. A complex64 GEMM at fp32 accuracy on TF32 tensor cores executes 24*M*N*K TF32 flops "
+                    "(4M real decomposition x 3-term error-compensated split), so the complex-GEMM tensor-core "
+                    "roofline is peak/3: dominant_steps_frac_of_complex_gemm_roofline = executed TF32 flops / time "
+                    "(operand packing included) / peak for the tensor-bound steps.",
+        },
+        "per_slice_ms_profiled": slice_ms, "steps_per_slice": len(per_slice), "steps_once_per_call": len(rows) - len(per_slice),
+        "step_table": table,
+        "clocks": sampler.summary(),
+        "gpu_launches": int(sum((3 if r["kernel"] == 2 else 2 if r["kernel"] == 3 else 1) for r in per_slice)
+                            * plan.n_slices * steps / max(1, world)),
         "scaling": "strong",
     }
+    if do_cpu:
+        dt, amps, n_slices, fl_slice = c5_cpu_slices(int(os.environ.get("TQ_C5_CPU_SLICES", "4")))
+        got = [complex(cc.amplitude(bits, slice_range=(i, i + 1)).cpu()) for i in range(len(amps))]
+        err = max(abs(g - a) / abs(a) for g, a in zip(got, amps))
+        res["cpu_baseline"] = {
+            "value": 1.0 / (dt * n_slices), "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(amps)} of {n_slices} slices contracted with torch.tensordot complex64 on the host "
+                      f"({dt:.2f} s per slice, {fl_slice / dt / 1e9:.0f} GFLOP/s), extrapolated x{n_slices}; host has "
+                      f"{os.cpu_count()} logical cores; max relative |gpu-cpu| on those slice amplitudes = {err:.2e}"}
+    return res
+
+
+def measure_c2_tn(steps, warmup, device):
+    """BASELINE config 2 in the mode it names: tensor-network contraction (tn_mode=True) through the public API —
+    values from the contraction plan (1744 tensors per network, batched gate operands), gradient from the adjoint
+    sweeps (tn_backend._TNExecute)."""
+    import tedq_b200 as qb
+    from tedq_b200 import workloads as W
+
+    spec = W.mbl_1d(12)
+    circ = W.build_circuit(spec, qb)
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                             hyper_opt={"max_repeats": 8})
+    x = torch.tensor(W.c2_inputs(256, 12, 0), device=device)
+
+    def step():
+        xx = x.clone().requires_grad_(True)
+        y = cc.batched(xx)
+        y.sum().backward()
+        return y
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        y = step()
+    ev1.record()
+    torch.cuda.synchronize(device)
+    ms = ev0.elapsed_time(ev1) / steps
+    plan = cc._tn._plan(0)
+    return {"value": 256 / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms,
+            "workload": f"c2 in tensor-network mode: 12-qubit MBL-1D, batch 256, fwd (contraction plan: {plan.n_steps} "
+                        f"pairwise steps, width {plan.width}, {plan.flops:.3e} flop per set) + bwd (adjoint sweeps)",
+            "dtype": "c64"}
 
 
 def main():
@@ -332,7 +478,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c1,c3,c4,c5"),
+    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c5"),
                     help="other BASELINE configs measured briefly and reported inside the same JSON line")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
@@ -353,16 +499,21 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=device)
 
     if args.workload == "c5":
-        r = measure_c5(max(1, min(args.steps, 5)), 1, device, dist_on, world)
+        r = measure_c5(max(1, min(args.steps, 5)), 1, device, dist_on, world, do_cpu=(rank == 0 and world == 1))
         if rank == 0:
-            print(json.dumps({
+            extra = {k: r[k] for k in ("cpu_baseline", "step_table", "per_slice_ms_profiled", "steps_per_slice",
+                                       "steps_once_per_call") if k in r}
+            print(json.dumps({**extra, 
                 "metric": "circuit_evals_per_sec", "value": r["value"], "unit": r["unit"], "n_gpus": world,
                 "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
                 "config": {"workload": r["desc"], "parallelism": f"slices sharded over {world} GPU(s), one all-reduce",
                            "l2": "intermediates (2^23..2^27 complex) exceed L2 between steps"},
                 "roofline": r["roofline"], "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
-                "amplitude": r["amplitude"], "e2e": None}))
+                "amplitude": r["amplitude"],
+                "e2e": {"value": r["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+                        "note": "the circuit has no runtime inputs (fixed random angles); the timed call is the "
+                                "public cc.amplitude(bits), only the 8-byte amplitude returns to the host"}}))
         if dist_on:
             torch.distributed.destroy_process_group()
         return
@@ -372,9 +523,16 @@ def main():
     if world == 1 and args.extras and args.extras != "none":
         for name in [e for e in args.extras.split(",") if e and e != args.workload]:
             if name == "c5":
-                r = measure_c5(1, 1, device, False, 1)
+                r = measure_c5(3, 1, device, False, 1, do_cpu=os.environ.get("TQ_EXTRAS_CPU", "1") == "1")
                 extras[name] = {"value": r["value"], "unit": "evals/s", "ms_per_step": r["ms_per_step"],
-                                "workload": r["desc"], "roofline": r["roofline"], "dtype": "c64"}
+                                "workload": r["desc"], "roofline": r["roofline"], "dtype": "c64",
+                                "step_table": r["step_table"], "per_slice_ms_profiled": r["per_slice_ms_profiled"],
+                                "steps_per_slice": r["steps_per_slice"], "amplitude": r["amplitude"]}
+                if "cpu_baseline" in r:
+                    extras[name]["cpu_baseline"] = r["cpu_baseline"]
+                continue
+            if name == "c2tn":
+                extras[name] = measure_c2_tn(5, 3, device)
                 continue
             r = measure_workload(name, max(2, min(5, args.steps)), 3, device, False, 1, do_e2e=False,
                                  do_cpu=os.environ.get("TQ_EXTRAS_CPU", "0") == "1")

@@ -227,9 +227,9 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
  *     k + m + n + b >= TQ_TN_OPT_TC_MIN_LOG2 (default 20) run on tcgen05 tensor cores as a 4M real GEMM with
  *     error-compensated split-TF32 (x = hi + lo; hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM);
  *     0 keeps every step on the fp32 FMA kernels (used by the parity tests to compare the two paths).
- *   TQ_TN_OPT_TC_CHUNK (default 2): k-blocks (16 complex k each) accumulated inside the tensor core between
- *     drains.  tcgen05 accumulates with round-toward-zero (a bias linear in K); partial sums are therefore
- *     drained every `chunk` k-blocks and added to fp32 registers with round-to-nearest. */
+ *   TQ_TN_OPT_TC_CHUNK (default 32): complex k accumulated inside the tensor core between drains.  tcgen05
+ *     accumulates with round-toward-zero (a bias linear in K); partial sums are therefore drained every
+ *     `chunk` complex k and added to fp32 registers with round-to-nearest. */
 enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2 };
 int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
 /* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,

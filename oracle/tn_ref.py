@@ -118,6 +118,54 @@ def contract_path(arrays, inputs, output, path):
     return np.transpose(T, [ix.index(i) for i in output]) if output else T
 
 
+def contract_slice_torch(arrays, inputs, output, path, sliced=(), slice_id=0, dtype=torch.complex64):
+    """One slice of a sliced contraction the way the reference's planners run it on the CPU
+    (``tree.contract(arrays, backend='torch')``, pytorch_backend.py:339: every pairwise step is a
+    ``torch.tensordot`` = one cgemm on the host cores; PathOptimizer.rst:38-63: a sliced index is fixed to
+    one value per slice and the slice results are summed).  ``sliced[j]`` takes bit j of ``slice_id``."""
+    fixed = {ix: (slice_id >> j) & 1 for j, ix in enumerate(sliced)}
+    live = {}
+    for i, (a, ix) in enumerate(zip(arrays, inputs)):
+        t = torch.as_tensor(np.asarray(a)).to(dtype)
+        keep = []
+        sel = []
+        for ax in ix:
+            if ax in fixed:
+                sel.append(fixed[ax])
+            else:
+                sel.append(slice(None))
+                keep.append(ax)
+        live[i] = (t[tuple(sel)], keep)
+    count = {}
+    for _, ix in live.values():
+        for ax in ix:
+            count[ax] = count.get(ax, 0) + 1
+    for ax in output:
+        count[ax] = count.get(ax, 0) + 1
+    nxt = len(arrays)
+    for a, b in path:
+        A, ia = live.pop(a)
+        B, ib = live.pop(b)
+        shared = [ax for ax in ia if ax in ib]
+        contract = [ax for ax in shared if count[ax] == 2]
+        if len(contract) == len(shared):
+            T = torch.tensordot(A, B, dims=([ia.index(ax) for ax in contract], [ib.index(ax) for ax in contract]))
+            keep = [ax for ax in ia if ax not in contract] + [ax for ax in ib if ax not in contract]
+        else:   # an index shared with a third tensor survives: einsum keeps it
+            keep = [ax for ax in dict.fromkeys(ia + ib) if ax not in contract]
+            sym = {ax: j for j, ax in enumerate(dict.fromkeys(ia + ib))}
+            T = torch.einsum(A, [sym[ax] for ax in ia], B, [sym[ax] for ax in ib], [sym[ax] for ax in keep])
+            for ax in shared:
+                if ax not in contract:
+                    count[ax] -= 1
+        for ax in contract:
+            count[ax] = 0
+        live[nxt] = (T, keep)
+        nxt += 1
+    (T, ix), = live.values()
+    return T.permute([ix.index(ax) for ax in output]) if output else T
+
+
 def greedy_path(inputs, output):
     """Smallest-result-first pairwise order; only used to contract oracle networks on the CPU."""
     live = {i: set(ix) for i, ix in enumerate(inputs)}

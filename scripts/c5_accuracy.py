@@ -12,13 +12,13 @@ bits = [0] * 40
 t = time.time(); ref = complex(cc.amplitude(bits).cpu()); print("c128", ref, time.time() - t)
 circ32 = W.build_circuit(spec, qb)
 for tc in (0, 1):
-    for chunk in ((2,) if tc == 0 else (1, 2, 4)):
+    for chunk in ((32,) if tc == 0 else (16, 32, 64)):
         h = dict(ho); h["engine_opts"] = {capi.TN_OPT_TENSOR_CORE: tc, capi.TN_OPT_TC_CHUNK: chunk}
         c32 = circ32.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=h)
         a = complex(c32.amplitude(bits).cpu())
         print("tc", tc, "chunk", chunk, a, "rel err vs c128 %.3e" % (abs(a - ref) / abs(ref)))
         # per-slice relative errors
-        if tc == 1 and chunk == 2:
+        if tc == 1 and chunk == 32:
             errs = []
             for s in range(0, 64, 8):
                 r = complex(cc.amplitude(bits, slice_range=(s, s + 1)).cpu()); x = complex(c32.amplitude(bits, slice_range=(s, s + 1)).cpu())

@@ -7,6 +7,7 @@
 // permutation folded into the address computation of the contraction kernel itself (no transposed
 // copy of either operand is ever materialised).
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <set>
@@ -371,13 +372,13 @@ static void tc_pack_tables(tc::PackParams& P, const int8_t* row_bits, int n_row,
   P.n_b = n_b;
   P.is_b = is_b ? 1 : 0;
   P.rows_t_log2 = rows_t_log2;
-  P.kblocks = n_k > 4 ? 1 << (n_k - 4) : 1;
+  P.kblocks = n_k > tc::KB_LOG ? 1 << (n_k - tc::KB_LOG) : 1;
   for (int j = 0; j < n_row; ++j) P.row_bits[j] = row_bits[j];
   for (int j = 0; j < n_k; ++j) P.k_bits[j] = k_bits[j];
   for (int j = 0; j < n_b; ++j) P.b_bits[j] = b_bits[j];
   std::vector<std::pair<int, int>> loc;  // (source bit, value in r << 4 | kk)
   for (int j = 0; j < rows_t_log2; ++j) loc.push_back({row_bits[j], 1 << (4 + j)});
-  for (int j = 0; j < std::min(n_k, 4); ++j) loc.push_back({k_bits[j], 1 << j});
+  for (int j = 0; j < std::min(n_k, tc::KB_LOG); ++j) loc.push_back({k_bits[j], 1 << j});
   std::sort(loc.begin(), loc.end());
   P.n_local = (int)loc.size();
   for (size_t j = 0; j < loc.size(); ++j) {
@@ -409,7 +410,7 @@ struct tq_tn_plan {
   std::vector<TcStep> tc;
   int tc_enabled = 1;      // TQ_TN_OPT_TENSOR_CORE
   int tc_min_log2 = 20;    // TQ_TN_OPT_TC_MIN_LOG2: a step runs on tensor cores when k+m+n+b >= this
-  int tc_chunk = 2;        // TQ_TN_OPT_TC_CHUNK: k-blocks accumulated in TMEM between round-to-nearest drains
+  int tc_chunk = 32;       // TQ_TN_OPT_TC_CHUNK: complex k accumulated in TMEM between round-to-nearest drains
   int num_sms = 148;
 };
 
@@ -694,7 +695,7 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
     if (!T.shape_ok) continue;
     const int col_t_log2 = std::min(n_col, 7);
     T.c_t = 1 << col_t_log2;
-    T.kblocks = st.n_k > 4 ? 1 << (st.n_k - 4) : 1;
+    T.kblocks = st.n_k > tc::KB_LOG ? 1 << (st.n_k - tc::KB_LOG) : 1;
     T.tiles_a = 1 << (n_row - 7);
     T.tiles_b = 1 << (n_col - col_t_log2);
     T.stages = tc::num_stages(T.c_t);
@@ -728,7 +729,7 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
       p->tc_min_log2 = value;
       return TQ_OK;
     case TQ_TN_OPT_TC_CHUNK:
-      TQ_REQUIRE(value >= 1, TQ_E_INVALID, "tq_tn_plan_set_option: chunk must be >= 1");
+      TQ_REQUIRE(value >= 8, TQ_E_INVALID, "tq_tn_plan_set_option: chunk must be >= 8 complex k");
       p->tc_chunk = value;
       return TQ_OK;
     default:
@@ -871,7 +872,11 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   g.tiles_a = T.tiles_a;
   g.tiles_b = T.tiles_b;
   g.kblocks = T.kblocks;
-  g.chunk = std::max(1, p->tc_chunk);
+  g.chunk = std::max(1, p->tc_chunk / tc::KB_CPLX);  // in k-blocks
+  {
+    const char* dbg = getenv("TQ_TC_DEBUG");
+    g.debug = dbg ? atoi(dbg) : 0;
+  }
   g.n_z = (int32_t)nz;
   g.n_b_log2 = stp.n_b;
   g.stages = T.stages;

@@ -26,9 +26,17 @@ namespace tq {
 namespace tc {
 
 constexpr int ROWS = 128;                 // accumulator rows per tile (TMEM lanes)
-constexpr int KB_CPLX = 16;               // complex k per k-block  (= 32 reals = one 128-byte swizzle row)
-constexpr int ROW_BYTES = 128;
-constexpr int A_PLANE = ROWS * ROW_BYTES; // 16 KiB: one plane (hi or lo) of an A tile
+#ifndef TQ_TC_KB_LOG
+#define TQ_TC_KB_LOG 3
+#endif
+// A k-block is one swizzle row of an operand tile: 2^KB_LOG complex k.  KB_LOG 4 = 128-byte rows (SWIZZLE_128B,
+// 96 KiB per stage at 128 columns: 2 stages); KB_LOG 3 = 64-byte rows (SWIZZLE_64B, 48 KiB per stage: 4 stages,
+// which covers the fill latency of a stage with three others in flight).
+constexpr int KB_LOG = TQ_TC_KB_LOG;
+constexpr int KB_CPLX = 1 << KB_LOG;
+constexpr int ROW_BYTES = 8 * KB_CPLX;
+constexpr int K_STEPS = ROW_BYTES / 32;   // tcgen05 kind::tf32 consumes 8 reals (32 B) of K per instruction
+constexpr int A_PLANE = ROWS * ROW_BYTES; // one plane (hi or lo) of an A tile
 constexpr int A_CHUNK = 2 * A_PLANE;      // hi + lo
 constexpr int ACC_WARPS = 8;              // accumulation / epilogue warps (two per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 64 + 32 * ACC_WARPS;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 accumulate
@@ -104,10 +112,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups of 1024 B (SBO), descriptor version 1.
+// K-major operand tile, rows of ROW_BYTES, matching swizzle: 8-row groups (SBO = 8 rows), descriptor version 1,
+// layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = (8 * ROW_BYTES) >> 4, layout = ROW_BYTES == 128 ? 2 : 4;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+// 16-byte chunk c of row r sits at chunk c ^ swz(r): Swizzle<3,4,3> (128 B rows) / Swizzle<2,4,3> (64 B rows)
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t r) { return ROW_BYTES == 128 ? (r & 7u) : ((r >> 1) & 3u); }
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -126,8 +138,8 @@ struct PackParams {
   int32_t n_row, n_k, n_b;  // log2 extents
   int32_t is_b;             // 0: A image (ROWS rows per tile), 1: B image (c_t rows -> 2 c_t image rows)
   int32_t rows_t_log2;      // log2 rows per tile (7 for A, log2(c_t) for B)
-  int32_t kblocks;          // max(1, K / 16)
-  int32_t n_local;          // local bits handled inside one block = rows_t_log2 + min(n_k, 4)
+  int32_t kblocks;          // max(1, K / KB_CPLX)
+  int32_t n_local;          // local bits handled inside one block = rows_t_log2 + min(n_k, KB_LOG)
   int8_t row_bits[32], k_bits[32], b_bits[32];  // source bit of row / k / kept-shared index bit j
   int8_t local_src[16];     // source bit of local element bit j (sorted: ascending source position)
   int16_t local_dst[16];    // its value in (r << 4 | kk)
@@ -152,8 +164,8 @@ k_tc_pack(const __grid_constant__ PackParams p) {
   int64_t base = (int64_t)set * p.src_set_stride;
   for (int j = 0; j < p.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << p.b_bits[j];
   for (int j = p.rows_t_log2; j < p.n_row; ++j) base |= (int64_t)((tile >> (j - p.rows_t_log2)) & 1u) << p.row_bits[j];
-  for (int j = 4; j < p.n_k; ++j) base |= (int64_t)((kb >> (j - 4)) & 1u) << p.k_bits[j];
-  if (p.n_k < 4) {  // K padded to one k-block: the missing columns are zero
+  for (int j = KB_LOG; j < p.n_k; ++j) base |= (int64_t)((kb >> (j - KB_LOG)) & 1u) << p.k_bits[j];
+  if (p.n_k < KB_LOG) {  // K padded to one k-block: the missing columns are zero
     for (int i = tid; i < chunk / 16; i += THREADS) reinterpret_cast<float4*>(pk_smem)[i] = make_float4(0, 0, 0, 0);
     __syncthreads();
   }
@@ -191,14 +203,14 @@ k_tc_pack(const __grid_constant__ PackParams p) {
       const uint32_t r = dd[i] >> 4, kk = dd[i] & 15u;
       const float hr = to_tf32(v[i].x), hi = to_tf32(v[i].y);
       const float lr = to_tf32(v[i].x - hr), li = to_tf32(v[i].y - hi);
-      const uint32_t in_row = ((((kk >> 1) ^ (r & 7u)) << 4) | ((kk & 1u) << 3));
+      const uint32_t in_row = ((((kk >> 1) ^ swz(r)) << 4) | ((kk & 1u) << 3));
       if (!p.is_b) {
         const uint32_t o = r * ROW_BYTES + in_row;
         *reinterpret_cast<float2*>(pk_smem + o) = make_float2(hr, hi);
         *reinterpret_cast<float2*>(pk_smem + plane + o) = make_float2(lr, li);
       } else {
         const uint32_t o_re = r * ROW_BYTES + in_row;             // -> Re C
-        const uint32_t o_im = (rows_t + r) * ROW_BYTES + in_row;  // -> Im C  ((rows_t + r) & 7 == r & 7)
+        const uint32_t o_im = (rows_t + r) * ROW_BYTES + in_row;  // -> Im C  (swz(rows_t + r) == swz(r))
         *reinterpret_cast<float2*>(pk_smem + o_re) = make_float2(hr, -hi);
         *reinterpret_cast<float2*>(pk_smem + o_im) = make_float2(hi, hr);
         *reinterpret_cast<float2*>(pk_smem + plane + o_re) = make_float2(lr, -li);
@@ -231,6 +243,7 @@ struct GemmParams {
   int64_t c_rs, c_cs;        // complex-entry stride of an accumulator row / column inside C
   int32_t tiles_a, tiles_b, kblocks, n_z, n_b_log2, stages;
   int32_t chunk;             // k-blocks accumulated inside the tensor core before a drain (see below)
+  int32_t debug;             // experiments only: bit 0 = drains skip their TMEM loads (wrong results)
   int64_t c_bb_stride;       // complex entries between kept-shared index values (2^(n_m + n_n))
 };
 
@@ -324,7 +337,7 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
             const uint64_t a_hi = smem_desc(sa), a_lo = smem_desc(sa + A_PLANE);
             const uint64_t b_hi = smem_desc(sa + A_CHUNK), b_lo = smem_desc(sa + A_CHUNK + b_plane);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {  // 8 reals (32 B) of K per instruction
+            for (int ks = 0; ks < K_STEPS; ++ks) {  // 8 reals (32 B) of K per instruction
               const uint64_t adv = (uint64_t)(ks * 2);
               tc_mma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (uint32_t)((kb > kb0) | (ks > 0)));
               tc_mma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -360,6 +373,7 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HALF);
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 16) {
+          if (p.debug & 1) break;
           uint32_t re[16], im[16];
           tc_ld16(taddr + (uint32_t)c0, re);
           tc_ld16(taddr + (uint32_t)(C_T + c0), im);

@@ -87,3 +87,26 @@ def test_tn_mode_complex128_mbl2d():
     got = cc.batched(x.cuda()).cpu().numpy()
     ref, _ = sv_ref.run_batch(circ, x, torch.complex128)
     assert_close(got, ref.numpy(), 1e-11, "c128 tn")
+
+
+def test_c5_amplitude_tensor_core_matches_complex128():
+    """C5 at full size (40 qubits, 64 slices): the tcgen05 split-TF32 path against the complex128 FMA path of the
+    same plan (north_star: complex64 amplitudes within relative 1e-5), and slice-sum invariance."""
+    spec = W.lattice_rcs(5, 8, 12, seed=0)
+    ho = {"max_repeats": 16, "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64}}
+    c128 = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64)).compilecircuit(
+        backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=ho, dtype=torch.complex128)
+    c64 = W.build_circuit(spec, qb).compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                                                   hyper_opt=ho)
+    bits = [0] * 40
+    ref = complex(c128.amplitude(bits).cpu())
+    got = complex(c64.amplitude(bits).cpu())
+    plan = c64._tn._amplitude_plan()[2]
+    assert sum(1 for s in range(plan.n_steps) if plan.step_kernel(s) == 2) >= 5
+    assert abs(got - ref) <= 1e-5 * abs(ref), (got, ref, abs(got - ref) / abs(ref))
+    ns = plan.n_slices
+    halves = complex((c64.amplitude(bits, slice_range=(0, ns // 2)) + c64.amplitude(bits, slice_range=(ns // 2, ns))).cpu())
+    assert abs(halves - got) <= 1e-5 * abs(ref)
+    one = [0, 1] * 20
+    r1, g1 = complex(c128.amplitude(one).cpu()), complex(c64.amplitude(one).cpu())
+    assert abs(g1 - r1) <= 1e-5 * abs(r1), (g1, r1)
