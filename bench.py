@@ -464,8 +464,20 @@ def measure_c2_tn(steps, warmup, device):
     ev1.record()
     torch.cuda.synchronize(device)
     ms = ev0.elapsed_time(ev1) / steps
+    with torch.no_grad():
+        cc.batched(x)
+        torch.cuda.synchronize(device)
+        ev0.record()
+        for _ in range(steps):
+            cc.batched(x)
+        ev1.record()
+        torch.cuda.synchronize(device)
+    fwd_ms = ev0.elapsed_time(ev1) / steps
     plan = cc._tn._plan(0)
-    return {"value": 256 / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms,
+    kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
+    return {"value": 256 / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "fwd_only_ms": fwd_ms,
+            "fwd_only_evals_per_s": 256 / (fwd_ms * 1e-3),
+            "steps_by_kernel": {k: kinds.count(k) for k in sorted(set(kinds))},
             "workload": f"c2 in tensor-network mode: 12-qubit MBL-1D, batch 256, fwd (contraction plan: {plan.n_steps} "
                         f"pairwise steps, width {plan.width}, {plan.flops:.3e} flop per set) + bwd (adjoint sweeps)",
             "dtype": "c64"}

@@ -229,11 +229,16 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
  *     0 keeps every step on the fp32 FMA kernels (used by the parity tests to compare the two paths).
  *   TQ_TN_OPT_TC_CHUNK (default 32): complex k accumulated inside the tensor core between drains.  tcgen05
  *     accumulates with round-toward-zero (a bias linear in K); partial sums are therefore drained every
- *     `chunk` complex k and added to fp32 registers with round-to-nearest. */
-enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2 };
+ *     `chunk` complex k and added to fp32 registers with round-to-nearest.
+ *   TQ_TN_OPT_FUSE_SMALL (default 1): steps with k + m + n + b <= 18 (batched over parameter sets) or <= 14
+ *     (shared) are grouped into fused runs — ONE launch walks a dependency-closed set of small steps level by
+ *     level, one CTA per parameter set, tiny steps one per warp; 0 launches every step on its own. */
+enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2,
+                    TQ_TN_OPT_FUSE_SMALL = 3 };
 int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
 /* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,
- * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096) */
+ * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096),
+ * 4 = member of a fused run of small steps */
 int32_t tq_tn_plan_step_kernel(const tq_tn_plan* plan, int32_t s);
 /* bit 0: step s repeats for every slice (it depends on a sliced index); bit 1: it carries the parameter-set
  * batch dimension.  Steps with neither bit run once per call, outside the slice loop. */

@@ -39,7 +39,7 @@ class PlanOpts(C.Structure):
 
 
 TN_MAX_RANK = 32
-TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK = 0, 1, 2
+TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK, TN_OPT_FUSE_SMALL = 0, 1, 2, 3
 
 
 class TnStep(C.Structure):
@@ -410,7 +410,13 @@ class TnPlan:
 
     def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
         n = self.n_inputs
-        ptrs = (C.c_void_p * n)(*input_ptrs)
-        strides = (C.c_int64 * n)(*input_strides)
+        if isinstance(input_ptrs, np.ndarray):   # int64 arrays go straight through, no per-element conversion
+            ptrs_np = np.ascontiguousarray(input_ptrs, dtype=np.int64)
+            strides_np = np.ascontiguousarray(input_strides, dtype=np.int64)
+            ptrs = ptrs_np.ctypes.data_as(C.POINTER(C.c_void_p))
+            strides = strides_np.ctypes.data_as(C.POINTER(C.c_int64))
+        else:
+            ptrs = (C.c_void_p * n)(*input_ptrs)
+            strides = (C.c_int64 * n)(*input_strides)
         check(lib().tq_tn_contract(self.handle, ptrs, strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes,
                                    stream), "tq_tn_contract")

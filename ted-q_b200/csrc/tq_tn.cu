@@ -253,6 +253,133 @@ __global__ void k_tn_dot_sum(const cx<R>* __restrict__ partial, int n_part, cx<R
   C[set * sC + o] = t;
 }
 
+// ---------------------------------------------------------------------------
+// Fused executor for the small steps of a plan (the bandwidth/latency-bound early part of every network:
+// 1700 of the 1743 steps of the 12-qubit MBL network have <= 16 output elements).  One launch runs a whole
+// dependency-closed set of small steps: one CTA per parameter set walks the run level by level (steps of a
+// level are independent); within a level the larger steps are done by the whole CTA one after the other and
+// the tiny ones are dealt out one per warp; one __syncthreads per level.  Output elements with few MACs are
+// split over up to 32 adjacent lanes along K and combined with warp shuffles.  Intermediates stay in the
+// (L1/L2-resident) arenas, so the larger kernels read them unchanged.
+// ---------------------------------------------------------------------------
+constexpr int FUSE_MAX_RANK = 16, FUSE_MAX_SLICE_BITS = 4;
+struct FusedStep {
+  int64_t a_off, b_off, c_off;  // complex-entry offsets inside their space
+  int32_t a_in, b_in;           // >= 0: input tensor id, -1: shared arena, -2: per-set arena
+  int32_t c_space;              // -1 / -2
+  int8_t n_k, n_m, n_n, n_b;
+  int8_t is_cta, pad[3];
+  int8_t a_bits[FUSE_MAX_RANK];  // bit positions inside A of [k..., m..., b...]
+  int8_t b_bits[FUSE_MAX_RANK];  // bit positions inside B of [k..., n..., b...]
+  int8_t a_sl_ord[FUSE_MAX_SLICE_BITS], a_sl_bit[FUSE_MAX_SLICE_BITS];  // sliced bits of an input operand (-1: none)
+  int8_t b_sl_ord[FUSE_MAX_SLICE_BITS], b_sl_bit[FUSE_MAX_SLICE_BITS];
+};
+struct InputRef {
+  const void* ptr;
+  int64_t stride;  // complex entries between parameter sets (0: shared)
+};
+
+template <typename R>
+__device__ __forceinline__ const cx<R>* fused_operand(const InputRef* __restrict__ inputs, cx<R>* shared, cx<R>* perset,
+                                                      int64_t set, int64_t slice, int32_t in, int64_t off,
+                                                      const int8_t* ord, const int8_t* bit) {
+  if (in == -1) return shared + off;
+  if (in == -2) return perset + off;
+  int64_t so = 0;
+#pragma unroll
+  for (int j = 0; j < FUSE_MAX_SLICE_BITS; ++j)
+    if (ord[j] >= 0) so |= (int64_t)((slice >> ord[j]) & 1) << bit[j];
+  return reinterpret_cast<const cx<R>*>(inputs[in].ptr) + set * inputs[in].stride + so + off;
+}
+
+// One small step by a group of G threads (a warp, or the whole CTA when KTAB is set).  KTAB: the K offsets of
+// both operands come from shared-memory tables built once per step (low FUSE_KTAB_LOG2 bits; higher bits by
+// scatter per outer iteration) — the inner loop is 2 LDS + 2 LDG + 4 FMA instead of two bit-scatter loops.
+constexpr int FUSE_KTAB_LOG2 = 10;
+template <typename R, bool KTAB>
+__device__ __forceinline__ void fused_exec(const FusedStep& f, const InputRef* __restrict__ inputs, cx<R>* shared,
+                                           cx<R>* perset, int64_t set, int64_t slice, int t, int G, int log2G,
+                                           const uint32_t* ktab_a, const uint32_t* ktab_b) {
+  const cx<R>* a = fused_operand<R>(inputs, shared, perset, set, slice, f.a_in, f.a_off, f.a_sl_ord, f.a_sl_bit);
+  const cx<R>* b = fused_operand<R>(inputs, shared, perset, set, slice, f.b_in, f.b_off, f.b_sl_ord, f.b_sl_bit);
+  cx<R>* c = (f.c_space == -1 ? shared : perset) + f.c_off;
+  const int n_k = f.n_k, n_m = f.n_m, n_n = f.n_n, n_b = f.n_b;
+  // lanes per output element: split K over adjacent lanes when the step has fewer outputs than the group
+  const int lpo_log2 = max(0, min(min(n_k, 5), log2G - (n_m + n_n + n_b)));
+  const int lpo = 1 << lpo_log2;
+  const int items = 1 << (n_m + n_n + n_b + lpo_log2);
+  const int K = 1 << n_k;
+  const int n_lo = min(n_k, FUSE_KTAB_LOG2), K_lo = 1 << n_lo;
+  for (int base = 0; base < items; base += G) {
+    const int it = base + t;
+    const bool valid = it < items;
+    const uint32_t o = (uint32_t)(it >> lpo_log2), kp = (uint32_t)(it & (lpo - 1));
+    const uint32_t n = o & ((1u << n_n) - 1u);
+    const uint32_t m = (o >> n_n) & ((1u << n_m) - 1u);
+    const uint32_t bb = o >> (n_n + n_m);
+    cx<R> acc = mk<R>(0, 0);
+    if (valid) {
+      const uint32_t ao = scat(m, f.a_bits + n_k, n_m) | scat(bb, f.a_bits + n_k + n_m, n_b);
+      const uint32_t bo = scat(n, f.b_bits + n_k, n_n) | scat(bb, f.b_bits + n_k + n_n, n_b);
+      if (KTAB) {
+        for (int kh = 0; kh < (K >> n_lo); ++kh) {
+          const uint32_t ah = ao | scat((uint32_t)kh, f.a_bits + n_lo, n_k - n_lo);
+          const uint32_t bh = bo | scat((uint32_t)kh, f.b_bits + n_lo, n_k - n_lo);
+          for (int k = (int)kp; k < K_lo; k += lpo) acc = cfma(a[ah | ktab_a[k]], b[bh | ktab_b[k]], acc);
+        }
+      } else {
+        for (int k = (int)kp; k < K; k += lpo)
+          acc = cfma(a[ao | scat((uint32_t)k, f.a_bits, n_k)], b[bo | scat((uint32_t)k, f.b_bits, n_k)], acc);
+      }
+    }
+    for (int d = lpo >> 1; d > 0; d >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+    }
+    if (valid && kp == 0) c[o] = acc;
+  }
+}
+
+constexpr int FUSE_STAGE = 128;  // step descriptors staged in shared memory per chunk
+template <typename R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ level_off,
+           const int32_t* __restrict__ level_ncta, int n_levels, const InputRef* __restrict__ inputs, cx<R>* shared,
+           cx<R>* perset_base, int64_t set_stride, int64_t slice) {
+  static_assert(sizeof(FusedStep) % 16 == 0, "descriptors are staged with 16-byte copies");
+  __shared__ __align__(16) FusedStep sdesc[FUSE_STAGE];
+  __shared__ uint32_t ktab_a[1 << FUSE_KTAB_LOG2], ktab_b[1 << FUSE_KTAB_LOG2];
+  const int64_t set = blockIdx.x;
+  cx<R>* perset = perset_base + set * set_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = THREADS / 32, V = sizeof(FusedStep) / 16;
+  constexpr int LOG2T = THREADS == 1024 ? 10 : THREADS == 512 ? 9 : 8;
+  for (int L = 0; L < n_levels; ++L) {
+    const int beg = level_off[L], end = level_off[L + 1], cta_end = beg + level_ncta[L];
+    for (int c0 = beg; c0 < end; c0 += FUSE_STAGE) {
+      const int c1 = min(end, c0 + FUSE_STAGE);
+      const uint4* src = reinterpret_cast<const uint4*>(steps + c0);
+      for (int i = threadIdx.x; i < (c1 - c0) * V; i += THREADS) reinterpret_cast<uint4*>(sdesc)[i] = src[i];
+      __syncthreads();
+      const int ncta = max(0, min(cta_end, c1) - c0);  // cta steps come first inside a level
+      for (int i = 0; i < ncta; ++i) {
+        const FusedStep& f = sdesc[i];
+        const int n_lo = min((int)f.n_k, FUSE_KTAB_LOG2);
+        for (int k = threadIdx.x; k < (1 << n_lo); k += THREADS) {
+          ktab_a[k] = scat((uint32_t)k, f.a_bits, n_lo);
+          ktab_b[k] = scat((uint32_t)k, f.b_bits, n_lo);
+        }
+        __syncthreads();
+        fused_exec<R, true>(f, inputs, shared, perset, set, slice, (int)threadIdx.x, THREADS, LOG2T, ktab_a, ktab_b);
+        __syncthreads();
+      }
+      for (int i = ncta + warp; i < c1 - c0; i += NW)
+        fused_exec<R, false>(sdesc[i], inputs, shared, perset, set, slice, lane, 32, 5, nullptr, nullptr);
+      __syncthreads();  // level boundary (data) and descriptor buffer reuse
+    }
+  }
+}
+
 // Tiled complex GEMM with the permutation folded into the gathers: a CTA owns a 64 x 64 tile of
 // C[m, n] for one kept-shared index value and one parameter set; A and B tiles are gathered through
 // per-CTA offset tables into shared memory (K tile = 16), each thread accumulates a 4 x 4 block.
@@ -352,6 +479,17 @@ __global__ void k_tn_final(const cx<R>* __restrict__ last, int64_t sL, cx<R>* __
 }
 
 constexpr int DOT_MAX_OUT_LOG2 = 6, DOT_MIN_K_LOG2 = 12, DOT_BLOCKS = 128;
+// a step joins a fused run when k+m+n+b <= this (one CTA per parameter set does the whole step)
+constexpr int FUSE_MAX_WORK_BATCHED = 18, FUSE_MAX_WORK_SHARED = 14, FUSE_CTA_WORK = 11;
+
+struct SchedItem {
+  int step = -1;                       // >= 0: one step on its own kernel(s)
+  int fs_begin = 0, n_fsteps = 0;      // else: a fused run = d_fsteps[fs_begin .. +n_fsteps)
+  int lv_begin = 0, n_levels = 0;      // its level table: d_levels[lv_begin .. +n_levels+1) offsets (relative to
+                                       // fs_begin), then n_levels cta-step counts
+  bool batched = false;
+  std::vector<int> members;            // steps of the run, in execution order
+};
 
 // Tensor-core lowering of one step: which operand provides accumulator rows, image geometry, pack tables.
 struct TcStep {
@@ -406,6 +544,14 @@ struct tq_tn_plan {
   std::vector<StepDev> dev;
   double flops = 0;
   int width = 0;
+  // schedule: what runs, in which order (rebuilt when an option changes)
+  std::vector<int> kind;            // per step: 0 per-element, 1 FMA GEMM, 2 tcgen05 GEMM, 3 split-K, 4 fused run
+  std::vector<SchedItem> items[2];  // phase 0: once per call; phase 1: every slice
+  std::vector<char> t_slice;        // per tensor id: depends on a sliced index
+  std::vector<int> t_rank;
+  FusedStep* d_fsteps = nullptr;
+  int32_t* d_levels = nullptr;      // [level_off (n+1 per run) | level_ncta] blocks, see SchedItem
+  int fuse_enabled = 1;             // TQ_TN_OPT_FUSE_SMALL
   // tensor-core path (complex64 only): per-step operand-image descriptions
   std::vector<TcStep> tc;
   int tc_enabled = 1;      // TQ_TN_OPT_TENSOR_CORE
@@ -413,6 +559,221 @@ struct tq_tn_plan {
   int tc_chunk = 32;       // TQ_TN_OPT_TC_CHUNK: complex k accumulated in TMEM between round-to-nearest drains
   int num_sms = 148;
 };
+
+// Decide which kernel runs every step, group the small ones into fused runs, fix the execution order of both
+// phases (once per call / every slice) and lay the intermediates out in the two arenas for that order.
+static int build_schedule(tq_tn_plan* p) {
+  const int n_in = p->n_in, n_steps = (int)p->steps.size();
+  std::vector<int> in_slice_bits(n_in, 0);
+  for (int t : p->slice_tensor) in_slice_bits[t]++;
+  p->kind.assign(n_steps, 0);
+  for (int s = 0; s < n_steps; ++s) {
+    const tq_tn_step& st = p->steps[s];
+    const int work = st.n_k + st.n_m + st.n_n + st.n_b, outl = st.n_m + st.n_n + st.n_b;
+    const bool tc_ok = p->dtype == TQ_C64 && p->tc_enabled && p->tc[s].shape_ok && work >= p->tc_min_log2;
+    auto opnd_ok = [&](int t, int rank) {
+      return rank <= FUSE_MAX_RANK && (t >= n_in || in_slice_bits[t] <= FUSE_MAX_SLICE_BITS);
+    };
+    const bool small = p->fuse_enabled && work <= (p->dep_batch[s] ? FUSE_MAX_WORK_BATCHED : FUSE_MAX_WORK_SHARED) &&
+                       opnd_ok(st.lhs, st.n_k + st.n_m + st.n_b) && opnd_ok(st.rhs, st.n_k + st.n_n + st.n_b);
+    p->kind[s] = tc_ok ? 2 : small ? 4 : (outl <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2) ? 3
+                 : (st.n_m >= 6 && st.n_n >= 6 && st.n_k >= 4) ? 1 : 0;
+  }
+  // ---- execution order
+  std::vector<char> done(n_in + n_steps, 0);
+  for (int t = 0; t < n_in; ++t) done[t] = 1;
+  std::vector<FusedStep> fsteps;
+  std::vector<int32_t> levels;
+  for (int phase = 0; phase < 2; ++phase) {
+    p->items[phase].clear();
+    std::vector<int> remaining;
+    for (int s = 0; s < n_steps; ++s)
+      if ((p->dep_slice[s] != 0) == (phase == 1)) remaining.push_back(s);
+    while (!remaining.empty()) {
+      bool progressed = false;
+      for (int batched = 0; batched < 2; ++batched) {
+        std::vector<int> run;
+        std::vector<int> level(n_in + n_steps, 0);
+        std::vector<char> in_run(n_in + n_steps, 0);
+        for (int s : remaining) {
+          const tq_tn_step& st = p->steps[s];
+          if (p->kind[s] != 4 || (p->dep_batch[s] != 0) != (batched == 1)) continue;
+          if (!(done[st.lhs] || in_run[st.lhs]) || !(done[st.rhs] || in_run[st.rhs])) continue;
+          run.push_back(s);
+          in_run[n_in + s] = 1;
+          level[n_in + s] = 1 + std::max(in_run[st.lhs] ? level[st.lhs] : 0, in_run[st.rhs] ? level[st.rhs] : 0);
+        }
+        if (run.empty()) continue;
+        progressed = true;
+        auto is_cta = [&](int s) {
+          const tq_tn_step& st = p->steps[s];
+          return st.n_k + st.n_m + st.n_n + st.n_b >= FUSE_CTA_WORK;
+        };
+        std::stable_sort(run.begin(), run.end(), [&](int x, int y) {
+          if (level[n_in + x] != level[n_in + y]) return level[n_in + x] < level[n_in + y];
+          return is_cta(x) > is_cta(y);
+        });
+        SchedItem it;
+        it.batched = batched == 1;
+        it.members = run;
+        it.fs_begin = (int)fsteps.size();
+        it.n_fsteps = (int)run.size();
+        it.n_levels = level[n_in + run.back()];
+        it.lv_begin = (int)levels.size();
+        std::vector<int32_t> off(it.n_levels + 1, 0), ncta(it.n_levels, 0);
+        for (int s : run) {
+          off[level[n_in + s]] += 1;  // counts, shifted by one level
+          if (is_cta(s)) ncta[level[n_in + s] - 1] += 1;
+        }
+        for (int L = 0; L < it.n_levels; ++L) off[L + 1] += off[L];
+        levels.insert(levels.end(), off.begin(), off.end());
+        levels.insert(levels.end(), ncta.begin(), ncta.end());
+        fsteps.resize(fsteps.size() + run.size());  // filled once the arena offsets are known
+        for (int s : run) done[n_in + s] = 1;
+        std::vector<int> rest;
+        for (int s : remaining)
+          if (!in_run[n_in + s]) rest.push_back(s);
+        remaining.swap(rest);
+        p->items[phase].push_back(std::move(it));
+      }
+      std::vector<int> rest;
+      for (int s : remaining) {
+        const tq_tn_step& st = p->steps[s];
+        if (p->kind[s] != 4 && done[st.lhs] && done[st.rhs]) {
+          SchedItem it;
+          it.step = s;
+          it.batched = p->dep_batch[s] != 0;
+          p->items[phase].push_back(it);
+          done[n_in + s] = 1;
+          progressed = true;
+        } else {
+          rest.push_back(s);
+        }
+      }
+      remaining.swap(rest);
+      TQ_REQUIRE(progressed, TQ_E_INVALID, "tq_tn_plan: the contraction path is not a valid ssa order");
+    }
+  }
+  // ---- arena layout: best-fit over a free list, simulated in execution order.  Outputs of once-per-call steps
+  // that feed per-slice steps stay pinned for the whole slice loop; nothing is recycled inside a fused run.
+  std::vector<int> item_of(n_steps, 0);
+  std::vector<const SchedItem*> order;
+  for (int phase = 0; phase < 2; ++phase)
+    for (const SchedItem& it : p->items[phase]) {
+      const int pos = (int)order.size();
+      order.push_back(&it);
+      if (it.step >= 0) item_of[it.step] = pos;
+      for (int s : it.members) item_of[s] = pos;
+    }
+  std::vector<int> last_pos(n_in + n_steps, -1);
+  for (int s = 0; s < n_steps; ++s) {
+    last_pos[p->steps[s].lhs] = std::max(last_pos[p->steps[s].lhs], item_of[s]);
+    last_pos[p->steps[s].rhs] = std::max(last_pos[p->steps[s].rhs], item_of[s]);
+  }
+  p->arena_off.assign(n_steps, 0);
+  for (int arena = 0; arena < 2; ++arena) {  // 0: per-set, 1: shared
+    struct Blk {
+      int64_t off, size;
+    };
+    std::vector<Blk> freel;
+    int64_t top = 0;
+    std::vector<std::pair<int, Blk>> live;  // (tensor id, block)
+    for (size_t pos = 0; pos < order.size(); ++pos) {
+      const SchedItem& it = *order[pos];
+      std::vector<int> members = it.members;
+      if (it.step >= 0) members.push_back(it.step);
+      for (int s : members) {
+        if ((int)p->arena_const[s] != arena) continue;
+        int64_t size = ((int64_t)1 << p->t_rank[n_in + s]);
+        size = (size + 15) & ~(int64_t)15;
+        int best = -1;
+        for (size_t j = 0; j < freel.size(); ++j)
+          if (freel[j].size >= size && (best < 0 || freel[j].size < freel[best].size)) best = (int)j;
+        Blk b;
+        if (best >= 0) {
+          b.off = freel[best].off;
+          b.size = size;
+          if (freel[best].size > size) {
+            freel[best].off += size;
+            freel[best].size -= size;
+          } else {
+            freel.erase(freel.begin() + best);
+          }
+        } else {
+          b.off = top;
+          b.size = size;
+          top += size;
+        }
+        p->arena_off[s] = b.off;
+        live.push_back({n_in + s, b});
+      }
+      for (int s : members) {
+        const tq_tn_step& st = p->steps[s];
+        for (int opnd : {st.lhs, st.rhs}) {
+          if (opnd < n_in || last_pos[opnd] != (int)pos) continue;
+          const int ps = opnd - n_in;
+          if ((int)p->arena_const[ps] != arena) continue;
+          if (!p->dep_slice[ps] && p->dep_slice[s]) continue;  // pinned across the slice loop
+          for (size_t j = 0; j < live.size(); ++j)
+            if (live[j].first == opnd) {
+              freel.push_back(live[j].second);
+              live.erase(live.begin() + j);
+              break;
+            }
+        }
+      }
+    }
+    (arena ? p->arena_shared : p->arena_set) = top;
+  }
+  // ---- device tables of the fused runs
+  for (int phase = 0; phase < 2; ++phase)
+    for (const SchedItem& it : p->items[phase]) {
+      for (size_t i = 0; i < it.members.size(); ++i) {
+        const int s = it.members[i];
+        const tq_tn_step& st = p->steps[s];
+        FusedStep& f = fsteps[it.fs_begin + i];
+        memset(&f, 0, sizeof(f));
+        auto space = [&](int t) { return t < n_in ? t : (p->arena_const[t - n_in] ? -1 : -2); };
+        f.a_in = space(st.lhs);
+        f.b_in = space(st.rhs);
+        f.a_off = st.lhs < n_in ? 0 : p->arena_off[st.lhs - n_in];
+        f.b_off = st.rhs < n_in ? 0 : p->arena_off[st.rhs - n_in];
+        f.c_space = p->arena_const[s] ? -1 : -2;
+        f.c_off = p->arena_off[s];
+        f.n_k = (int8_t)st.n_k;
+        f.n_m = (int8_t)st.n_m;
+        f.n_n = (int8_t)st.n_n;
+        f.n_b = (int8_t)st.n_b;
+        const int outl = st.n_m + st.n_n + st.n_b;
+        f.is_cta = st.n_k + outl >= FUSE_CTA_WORK;
+        for (int j = 0; j < st.n_k + st.n_m + st.n_b; ++j) f.a_bits[j] = st.lhs_bits[j];
+        for (int j = 0; j < st.n_k + st.n_n + st.n_b; ++j) f.b_bits[j] = st.rhs_bits[j];
+        for (int j = 0; j < FUSE_MAX_SLICE_BITS; ++j) f.a_sl_ord[j] = f.b_sl_ord[j] = -1;
+        int na = 0, nb = 0;
+        for (size_t e = 0; e < p->slice_tensor.size(); ++e) {
+          if (p->slice_tensor[e] == st.lhs) {
+            f.a_sl_ord[na] = (int8_t)p->slice_ord[e];
+            f.a_sl_bit[na++] = (int8_t)p->slice_bit[e];
+          }
+          if (p->slice_tensor[e] == st.rhs) {
+            f.b_sl_ord[nb] = (int8_t)p->slice_ord[e];
+            f.b_sl_bit[nb++] = (int8_t)p->slice_bit[e];
+          }
+        }
+      }
+    }
+  cudaFree(p->d_fsteps);
+  cudaFree(p->d_levels);
+  p->d_fsteps = nullptr;
+  p->d_levels = nullptr;
+  if (!fsteps.empty()) {
+    TQ_CUDA_OK(cudaMalloc((void**)&p->d_fsteps, fsteps.size() * sizeof(FusedStep)));
+    TQ_CUDA_OK(cudaMemcpy(p->d_fsteps, fsteps.data(), fsteps.size() * sizeof(FusedStep), cudaMemcpyHostToDevice));
+    TQ_CUDA_OK(cudaMalloc((void**)&p->d_levels, levels.size() * sizeof(int32_t)));
+    TQ_CUDA_OK(cudaMemcpy(p->d_levels, levels.data(), levels.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  return TQ_OK;
+}
 
 extern "C" {
 
@@ -500,6 +861,8 @@ void tq_tn_plan_destroy(tq_tn_plan* p) {
   if (!p) return;
   for (int32_t* q : p->d_ka) cudaFree(q);
   for (int32_t* q : p->d_kb) cudaFree(q);
+  cudaFree(p->d_fsteps);
+  cudaFree(p->d_levels);
   delete p;
 }
 
@@ -554,73 +917,10 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
     last_use[st.lhs] = s;
     last_use[st.rhs] = s;
   }
-  // arena layout: best-fit over a free list, simulated in EXECUTION order (slice-invariant steps first,
-  // then the slice-dependent ones, which re-run for every slice).  Outputs of slice-invariant steps that
-  // feed slice-dependent steps stay pinned for the whole slice loop.
-  p->arena_off.assign(n_steps, 0);
+  p->t_slice.assign(t_slice.begin(), t_slice.end());
+  p->t_rank = t_rank;
   p->arena_const.assign(n_steps, 0);
-  std::vector<int> exec_order;
-  for (int s = 0; s < n_steps; ++s)
-    if (!p->dep_slice[s]) exec_order.push_back(s);
-  for (int s = 0; s < n_steps; ++s)
-    if (p->dep_slice[s]) exec_order.push_back(s);
-  std::vector<int> exec_pos(n_steps, 0), last_pos(n_in + n_steps, -1);
-  for (int i = 0; i < n_steps; ++i) exec_pos[exec_order[i]] = i;
-  for (int s = 0; s < n_steps; ++s) {
-    last_pos[p->steps[s].lhs] = std::max(last_pos[p->steps[s].lhs], exec_pos[s]);
-    last_pos[p->steps[s].rhs] = std::max(last_pos[p->steps[s].rhs], exec_pos[s]);
-  }
   for (int s = 0; s < n_steps; ++s) p->arena_const[s] = !t_batch[n_in + s];
-  for (int arena = 0; arena < 2; ++arena) {  // 0: per-set, 1: shared
-    struct Blk {
-      int64_t off, size;
-    };
-    std::vector<Blk> freel;
-    int64_t top = 0;
-    std::vector<std::pair<int, Blk>> live;  // (tensor id, block)
-    for (int i = 0; i < n_steps; ++i) {
-      const int s = exec_order[i];
-      const int o = n_in + s;
-      if ((int)p->arena_const[s] == arena) {
-        int64_t size = ((int64_t)1 << t_rank[o]);
-        size = (size + 15) & ~(int64_t)15;
-        int best = -1;
-        for (size_t j = 0; j < freel.size(); ++j)
-          if (freel[j].size >= size && (best < 0 || freel[j].size < freel[best].size)) best = (int)j;
-        Blk b;
-        if (best >= 0) {
-          b.off = freel[best].off;
-          b.size = size;
-          if (freel[best].size > size) {
-            freel[best].off += size;
-            freel[best].size -= size;
-          } else {
-            freel.erase(freel.begin() + best);
-          }
-        } else {
-          b.off = top;
-          b.size = size;
-          top += size;
-        }
-        p->arena_off[s] = b.off;
-        live.push_back({o, b});
-      }
-      const tq_tn_step& st = p->steps[s];
-      for (int opnd : {st.lhs, st.rhs}) {
-        if (opnd < n_in || last_pos[opnd] != i) continue;
-        const int ps = opnd - n_in;
-        if ((int)p->arena_const[ps] != arena) continue;
-        if (!p->dep_slice[ps] && p->dep_slice[s]) continue;  // pinned across the slice loop
-        for (size_t j = 0; j < live.size(); ++j)
-          if (live[j].first == opnd) {
-            freel.push_back(live[j].second);
-            live.erase(live.begin() + j);
-            break;
-          }
-      }
-    }
-    (arena ? p->arena_shared : p->arena_set) = top;
-  }
   // device step tables
   p->dev.resize(n_steps);
   p->d_ka.assign(n_steps, nullptr);
@@ -715,6 +1015,8 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
       tc_pack_tables(T.pb, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, true, col_t_log2);
     }
   }
+  rc = build_schedule(p);
+  if (rc) return rc;
   *out = P.release();
   return TQ_OK;
 }
@@ -724,10 +1026,13 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
   switch (option) {
     case TQ_TN_OPT_TENSOR_CORE:
       p->tc_enabled = value != 0;
-      return TQ_OK;
+      return build_schedule(p);
     case TQ_TN_OPT_TC_MIN_LOG2:
       p->tc_min_log2 = value;
-      return TQ_OK;
+      return build_schedule(p);
+    case TQ_TN_OPT_FUSE_SMALL:
+      p->fuse_enabled = value != 0;
+      return build_schedule(p);
     case TQ_TN_OPT_TC_CHUNK:
       TQ_REQUIRE(value >= 8, TQ_E_INVALID, "tq_tn_plan_set_option: chunk must be >= 8 complex k");
       p->tc_chunk = value;
@@ -737,15 +1042,11 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
   }
 }
 
-/* 0: one thread per output element, 1: tiled fp32 FMA GEMM, 2: tcgen05 split-TF32 GEMM, 3: split-K reduction */
+/* 0: one thread per output element, 1: tiled FMA GEMM, 2: tcgen05 split-TF32 GEMM, 3: split-K reduction,
+ * 4: member of a fused run of small steps */
 int32_t tq_tn_plan_step_kernel(const tq_tn_plan* p, int32_t s) {
   if (!p || s < 0 || s >= (int)p->steps.size()) return TQ_E_INVALID;
-  const tq_tn_step& st = p->steps[s];
-  if (st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2) return 3;
-  if (p->dtype == TQ_C64 && p->tc_enabled && p->tc[s].shape_ok &&
-      st.n_k + st.n_m + st.n_n + st.n_b >= p->tc_min_log2)
-    return 2;
-  return (st.n_m >= 6 && st.n_n >= 6 && st.n_k >= 4) ? 1 : 0;
+  return p->kind[s];
 }
 
 int32_t tq_tn_plan_num_steps(const tq_tn_plan* p) { return p ? (int32_t)p->steps.size() : -1; }
@@ -801,11 +1102,15 @@ static size_t tn_image_bytes(const tq_tn_plan* p, int64_t batch) {
   return need + tn_pinned_bytes(p, batch, nullptr);
 }
 
+static size_t tn_table_bytes(const tq_tn_plan* p) {  // input pointer table read by the fused runs
+  return ((size_t)p->n_in * sizeof(InputRef) + 255) & ~(size_t)255;
+}
+
 size_t tq_tn_workspace_bytes(const tq_tn_plan* p, int64_t batch) {
   if (!p || batch <= 0) return 0;
   const size_t cs = p->dtype == TQ_C64 ? 8 : 16;
   const size_t arenas = ((size_t)(p->arena_shared + p->arena_set * batch) * cs + 1023) & ~(size_t)1023;
-  return arenas + tn_image_bytes(p, batch) + 1024;
+  return tn_table_bytes(p) + arenas + tn_image_bytes(p, batch) + 1024;
 }
 
 }  // extern "C"
@@ -903,8 +1208,17 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   TQ_REQUIRE(ws_bytes >= tq_tn_workspace_bytes(p, B), TQ_E_WORKSPACE, "tq_tn_contract: workspace too small");
   const int n_in = p->n_in;
   const int n_steps = (int)p->steps.size();
-  cx<R>* shared = (cx<R>*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  InputRef* table = (InputRef*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  cx<R>* shared = (cx<R>*)((uint8_t*)table + tn_table_bytes(p));
   cx<R>* perset = shared + p->arena_shared;
+  if (p->d_fsteps) {
+    std::vector<InputRef> host(n_in);
+    for (int t = 0; t < n_in; ++t) {
+      host[t].ptr = inputs[t];
+      host[t].stride = p->in_batched[t] ? strides[t] : 0;
+    }
+    TQ_CUDA_OK(cudaMemcpyAsync(table, host.data(), n_in * sizeof(InputRef), cudaMemcpyHostToDevice, st));
+  }
   uint8_t* pinned = (uint8_t*)(((uintptr_t)(perset + p->arena_set * B) + 1023) & ~(uintptr_t)1023);
   std::vector<int64_t> pin_off;
   uint8_t* images = pinned + tn_pinned_bytes(p, B, &pin_off);
@@ -989,10 +1303,32 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     }
     return TQ_OK;
   };
+  auto run_item = [&](const SchedItem& it, int64_t slice) -> int {
+    if (it.step >= 0) return run_step(it.step, slice, false);
+    const int first = it.members.front();
+    const bool timed = step_ms && (slice == s_begin || !p->dep_slice[first]);
+    if (timed) TQ_CUDA_OK(cudaEventRecord(ev[3 * first], st));
+    const int64_t sets = it.batched ? B : 1;
+    // one CTA per parameter set; a lone CTA gets 32 warps (latency-bound), many sets get 2 CTAs per SM
+    if (sets == 1)
+      k_tn_fused<R, 1024><<<1, 1024, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
+                                              p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels, table, shared,
+                                              perset, p->arena_set, slice);
+    else
+      k_tn_fused<R, 512><<<(unsigned)sets, 512, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
+                                                         p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels,
+                                                         table, shared, perset, p->arena_set, slice);
+    TQ_CUDA_OK(cudaGetLastError());
+    if (timed) {
+      TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 1], st));
+      TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 2], st));
+    }
+    return TQ_OK;
+  };
   int rc;
-  // slice-invariant steps once, then the slice loop
-  for (int s = 0; s < n_steps; ++s)
-    if (!p->dep_slice[s] && (rc = run_step(s, 0, false))) return rc;
+  // once-per-call items, then the slice loop
+  for (const SchedItem& it : p->items[0])
+    if ((rc = run_item(it, 0))) return rc;
   if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps], st));
   for (int s = 0; s < n_steps; ++s)
     if (p->dep_slice[s] && (rc = run_step(s, s_begin, true))) return rc;
@@ -1004,8 +1340,8 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   const int64_t n_final = (int64_t)1 << p->n_out;
   const bool last_dep_slice = n_steps ? p->dep_slice[n_steps - 1] != 0 : false;
   for (int64_t slice = s_begin; slice < s_end; ++slice) {
-    for (int s = 0; s < n_steps; ++s)
-      if (p->dep_slice[s] && (rc = run_step(s, slice, false))) return rc;
+    for (const SchedItem& it : p->items[1])
+      if ((rc = run_item(it, slice))) return rc;
     const cx<R>* last;
     int64_t sl;
     tensor_ptr(n_in + n_steps - 1, slice, last, sl);
@@ -1017,8 +1353,16 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   }
   if (step_ms) {
     TQ_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<char> has_ev(n_steps, 1);
+    for (int phase = 0; phase < 2; ++phase)
+      for (const SchedItem& it : p->items[phase])
+        for (size_t i = 1; i < it.members.size(); ++i) has_ev[it.members[i]] = 0;  // a run is timed on its first step
     for (int s = 0; s < n_steps; ++s) {
       float whole = 0, pack = 0;
+      if (!has_ev[s]) {
+        step_ms[2 * s] = step_ms[2 * s + 1] = 0.f;
+        continue;
+      }
       TQ_CUDA_OK(cudaEventElapsedTime(&whole, ev[3 * s], ev[3 * s + 2]));
       if (tq_tn_plan_step_kernel(p, s) == 2) TQ_CUDA_OK(cudaEventElapsedTime(&pack, ev[3 * s], ev[3 * s + 1]));
       step_ms[2 * s] = whole;

@@ -93,6 +93,26 @@ class TNExecutor:
             return min(n_slices, r * per), min(n_slices, (r + 1) * per), True
         return 0, n_slices, False
 
+    def _operand_tables(self, i, net, plan_sv, total):
+        """Per network, once: for every operand the base buffer (0 cap, 1 gate matrices, 2 adjoint matrices,
+        3 + j observable j), its element offset inside that buffer and its parameter-set stride."""
+        cache = self.__dict__.setdefault("_opd_tables", {})
+        if i not in cache:
+            L = capi.lib()
+            base, off, stride = [], [], []
+            for kind, ref in net.operands:
+                if kind == OPD_CAP:
+                    base.append(0), off.append(0), stride.append(0)
+                elif kind == OPD_OBS:
+                    base.append(3 + ref), off.append(0), stride.append(0)
+                else:
+                    base.append(1 if kind == OPD_GATE else 2)
+                    off.append(int(L.tq_tn_gate_offset(plan_sv.handle, ref)))
+                    stride.append(total if self.gate_batched[ref] else 0)
+            cache[i] = {"base": np.asarray(base, dtype=np.int64), "off": np.asarray(off, dtype=np.int64),
+                        "stride": np.asarray(stride, dtype=np.int64), "any_batched": any(st != 0 for st in stride)}
+        return cache[i]
+
     def contract_values(self, flat: torch.Tensor):
         """-> list of complex tensors [B or 1, 2^n_out] (one per measurement)."""
         be = self.backend
@@ -113,20 +133,13 @@ class TNExecutor:
         results = []
         for i, net in enumerate(self.networks):
             plan = self._plan(i)
-            ptrs, strides = [], []
-            for kind, ref in net.operands:
-                if kind == OPD_CAP:
-                    ptrs.append(cap0.data_ptr())
-                    strides.append(0)
-                elif kind == OPD_OBS:
-                    ptrs.append(obs[i][ref].data_ptr())
-                    strides.append(0)
-                else:
-                    base = gm if kind == OPD_GATE else am
-                    off = int(L.tq_tn_gate_offset(plan_sv.handle, ref))
-                    ptrs.append(base.data_ptr() + off * esz)
-                    strides.append(total if self.gate_batched[ref] else 0)
-            any_b = any(s != 0 for s in strides)
+            # operand pointers = base[kind] + offset * element size: vectorised, tables built once per network
+            tab = self._operand_tables(i, net, plan_sv, total)
+            bases = np.array([cap0.data_ptr(), gm.data_ptr(), am.data_ptr()] + [o.data_ptr() for o in obs[i]],
+                             dtype=np.int64)
+            ptrs = bases[tab["base"]] + tab["off"] * esz
+            strides = tab["stride"]
+            any_b = bool(tab["any_batched"])
             out = torch.zeros((B if any_b else 1, 1 << plan.n_out), dtype=cd, device=dev)
             ws_bytes = plan.workspace_bytes(B)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
