@@ -381,6 +381,9 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
     for r in sorted(per_slice, key=lambda r: -r["ms"]):
         if r["ms"] < 0.01 * slice_ms:
             break
+        if r["kernel"] == 4:   # a fused run of small steps is timed as one launch (on its first member)
+            table.append({"kernel": "k_tn_fused (run of small steps)", "ms": round(r["ms"], 4)})
+            continue
         fl = 8.0 * 2.0 ** (r["k"] + r["m"] + r["n"] + r["b"])
         byts = 8.0 * (2.0 ** (r["k"] + r["m"] + r["b"]) + 2.0 ** (r["k"] + r["n"] + r["b"]) + 2.0 ** (r["m"] + r["n"] + r["b"]))
         t_fl = 3.0 * fl / (peak * 1e12)          # 4M x 3-term split-TF32: 24 TF32 flops per 8 algorithmic
@@ -419,8 +422,8 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
         "per_slice_ms_profiled": slice_ms, "steps_per_slice": len(per_slice), "steps_once_per_call": len(rows) - len(per_slice),
         "step_table": table,
         "clocks": sampler.summary(),
-        "gpu_launches": int(sum((3 if r["kernel"] == 2 else 2 if r["kernel"] == 3 else 1) for r in per_slice)
-                            * plan.n_slices * steps / max(1, world)),
+        "gpu_launches": int(sum((3 if r["kernel"] == 2 else 2 if r["kernel"] == 3 else 1 if r["kernel"] < 4 else
+                                 (1 if r["ms"] > 0 else 0)) for r in per_slice) * plan.n_slices * steps / max(1, world)),
         "scaling": "strong",
     }
     if do_cpu:
@@ -435,18 +438,21 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
     return res
 
 
-def measure_c2_tn(steps, warmup, device):
-    """BASELINE config 2 in the mode it names: tensor-network contraction (tn_mode=True) through the public API —
-    values from the contraction plan (1744 tensors per network, batched gate operands), gradient from the adjoint
-    sweeps (tn_backend._TNExecute)."""
+def measure_tn_mode(name, steps, warmup, device):
+    """BASELINE configs 2 and 4 in the mode they name: tensor-network contraction (tn_mode=True) through the public
+    API — values from the contraction plan (one network per measurement, batched gate operands), gradient from the
+    adjoint sweeps (tn_backend._TNExecute)."""
     import tedq_b200 as qb
     from tedq_b200 import workloads as W
 
-    spec = W.mbl_1d(12)
-    circ = W.build_circuit(spec, qb)
-    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+    spec, flat_np, cdt, desc = workload(name)
+    rd = torch.float32 if cdt == "c64" else torch.float64
+    cd = torch.complex64 if cdt == "c64" else torch.complex128
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=rd))
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, dtype=cd,
                              hyper_opt={"max_repeats": 8})
-    x = torch.tensor(W.c2_inputs(256, 12, 0), device=device)
+    x = torch.tensor(flat_np, dtype=rd, device=device)
+    nb = x.shape[0]
 
     def step():
         xx = x.clone().requires_grad_(True)
@@ -475,12 +481,13 @@ def measure_c2_tn(steps, warmup, device):
     fwd_ms = ev0.elapsed_time(ev1) / steps
     plan = cc._tn._plan(0)
     kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
-    return {"value": 256 / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "fwd_only_ms": fwd_ms,
-            "fwd_only_evals_per_s": 256 / (fwd_ms * 1e-3),
+    return {"value": nb / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "fwd_only_ms": fwd_ms,
+            "fwd_only_evals_per_s": nb / (fwd_ms * 1e-3),
             "steps_by_kernel": {k: kinds.count(k) for k in sorted(set(kinds))},
-            "workload": f"c2 in tensor-network mode: 12-qubit MBL-1D, batch 256, fwd (contraction plan: {plan.n_steps} "
-                        f"pairwise steps, width {plan.width}, {plan.flops:.3e} flop per set) + bwd (adjoint sweeps)",
-            "dtype": "c64"}
+            "workload": f"{desc.split(',')[0]} in tensor-network mode, batch {nb}: fwd = contraction plan "
+                        f"({plan.n_steps} pairwise steps, width {plan.width}, {plan.flops:.3e} flop per set, "
+                        f"in-repo planner) + bwd = adjoint sweeps",
+            "dtype": cdt}
 
 
 def main():
@@ -490,7 +497,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c5"),
+    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c4tn,c5"),
                     help="other BASELINE configs measured briefly and reported inside the same JSON line")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
@@ -508,6 +515,7 @@ def main():
     torch.cuda.set_device(device)
     dist_on = world > 1
     if dist_on:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: ONE JSON line
         torch.distributed.init_process_group("nccl", device_id=device)
 
     if args.workload == "c5":
@@ -543,8 +551,8 @@ def main():
                 if "cpu_baseline" in r:
                     extras[name]["cpu_baseline"] = r["cpu_baseline"]
                 continue
-            if name == "c2tn":
-                extras[name] = measure_c2_tn(5, 3, device)
+            if name in ("c2tn", "c4tn"):
+                extras[name] = measure_tn_mode(name[:2], 5, 3, device)
                 continue
             r = measure_workload(name, max(2, min(5, args.steps)), 3, device, False, 1, do_e2e=False,
                                  do_cpu=os.environ.get("TQ_EXTRAS_CPU", "0") == "1")

@@ -147,11 +147,28 @@ def path_cost(inputs, output, path, sliced=()):
     return width, (math.log2(total * 8.0) if total > 0 else 0.0), unions, results
 
 
+def sequential_path(n_inputs: int):
+    """Contract the inputs left to right: ((t0 t1) t2) t3 ...  For a circuit network whose operands are listed
+    in time order (caps, gates, observable, adjoint gates, caps: tensor_network.py:850-1099) this is state-vector
+    evolution written as a contraction path: width = number of qubits (+1), 2^(n+k) MACs per k-qubit gate."""
+    path = []
+    cur = 0
+    for t in range(1, n_inputs):
+        path.append((cur, t))
+        cur = n_inputs + t - 1
+    return path
+
+
 def find_path(inputs, output, repeats: int = 16, seed: int = 0, minimize: str = "flops",
               alphas=(1.0, 0.5, 0.0), temperatures=(0.0, 0.3, 1.0)) -> PathInfo:
-    """Best of ``repeats`` randomised greedy runs (first run is the deterministic alpha=1, T=0 greedy)."""
+    """Best of ``repeats`` randomised greedy runs (first run is the deterministic alpha=1, T=0 greedy) and the
+    time-ordered sequential path (deep circuits on few qubits: greedy merges wide, the sweep stays at width n)."""
     rng = random.Random(seed)
     best = None
+    if len(inputs) > 1:
+        path = sequential_path(len(inputs))
+        width, fl, _, _ = path_cost(inputs, output, path)
+        best = ((fl, width) if minimize == "flops" else (width, fl), path, width, fl)
     for r in range(max(1, repeats)):
         alpha = alphas[0] if r == 0 else rng.choice(alphas)
         temp = temperatures[0] if r == 0 else rng.choice(temperatures[1:])
