@@ -1,8 +1,7 @@
 set -x
-timeout 900 python bench.py > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err; tail -c 300 gpurun_out/bench_v7.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_v7.json'))
-print(d['value'], d['e2e']['value'], d['cpu_baseline']['value'])
-for k,v in d['other_configs'].items(): print(k, round(v['value'],2), round(v['ms_per_step'],3), v.get('fwd_only_ms'), v.get('steps_by_kernel'))
-PY
+timeout 300 python -m pytest tests/test_tn_tc_gpu.py -x -q -k "complex128" 2>&1 | tail -3
+timeout 100 python scripts/tc_gemm_single.py 11 10 10 32 3 c128 | tail -1
+timeout 100 python scripts/tc_gemm_single.py 12 12 8 32 3 c128 | tail -1
+TQ_TN_NO_DMMA=1 timeout 100 python scripts/tc_gemm_single.py 11 10 10 32 3 c128 | tail -1
+TQ_TN_NO_DMMA=1 timeout 100 python scripts/tc_gemm_single.py 12 12 8 32 3 c128 | tail -1
+timeout 300 python -m pytest tests/test_tn_gpu.py -x -q -k "c5 or complex128" 2>&1 | tail -3

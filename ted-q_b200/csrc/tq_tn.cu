@@ -461,6 +461,112 @@ k_tn_gemm(const cx<R>* __restrict__ A, int64_t sA, const cx<R>* __restrict__ B, 
   }
 }
 
+// complex128 GEMM-shaped steps on the FP64 tensor cores (DMMA): same tiling and gathers as k_tn_gemm (a CTA owns
+// a 64 x 64 tile of C[m, n]; permutation folded into the gathers; K tile = 16), operands staged PLANAR (re / im)
+// in shared memory, each warp owns 16 x 32 outputs = 2 x 4 mma.m8n8k4 blocks and issues the 4M real products
+//   Cr += Ar Br + (-Ai) Bi,   Ci += Ar Bi + Ai Br
+// as four mma.sync.m8n8k4.f64 per block and k4 step; fp64 accumulation in registers (round-to-nearest).
+constexpr int DLD = 68;  // leading dimension of the staged tiles: 2*DLD mod 32 == 8 -> conflict-free fragment loads
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256)
+k_tn_gemm_dmma(const cx<double>* __restrict__ A, int64_t sA, const cx<double>* __restrict__ B, int64_t sB,
+               cx<double>* __restrict__ C, int64_t sC, const __grid_constant__ StepDev d) {
+  __shared__ double As_re[TK][DLD], As_im[TK][DLD], Bs_re[TK][DLD], Bs_im[TK][DLD];
+  __shared__ uint32_t offm[TM], offn[TN];
+  const int tiles_n = 1 << (d.n_n - 6);
+  const int tiles_m = 1 << (d.n_m - 6);
+  uint32_t bid = blockIdx.x;
+  const uint32_t tn = bid % tiles_n;
+  bid /= tiles_n;
+  const uint32_t tm = bid % tiles_m;
+  const uint32_t bb = bid / tiles_m;
+  const int64_t set = blockIdx.y;
+  const int tid = threadIdx.x;
+  if (tid < TM) offm[tid] = scat(tm * TM + tid, d.a_m, d.n_m) | scat(bb, d.a_b, d.n_b);
+  if (tid >= 64 && tid < 64 + TN) offn[tid - 64] = scat(tn * TN + (tid - 64), d.b_n, d.n_n) | scat(bb, d.b_b, d.n_b);
+  __syncthreads();
+  const cx<double>* a = A + set * sA;
+  const cx<double>* b = B + set * sB;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;  // warp tile origin inside the CTA tile
+  const int fr = lane >> 2, fk = lane & 3;                // fragment row (or column) / k index of this lane
+  double cr[2][4][2], ci[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+  const int K = 1 << d.n_k;
+  for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int l = tid + e * 256;
+      int mi, ki;
+      if (d.a_k_fast) {
+        ki = l & (TK - 1);
+        mi = l >> 4;
+      } else {
+        mi = l & (TM - 1);
+        ki = l >> 6;
+      }
+      const cx<double> av = a[offm[mi] + d.ka[k0 + ki]];
+      As_re[ki][mi] = av.x;
+      As_im[ki][mi] = av.y;
+      int ni, kj;
+      if (d.b_k_fast) {
+        kj = l & (TK - 1);
+        ni = l >> 4;
+      } else {
+        ni = l & (TN - 1);
+        kj = l >> 6;
+      }
+      const cx<double> bv = b[offn[ni] + d.kb[k0 + kj]];
+      Bs_re[kj][ni] = bv.x;
+      Bs_im[kj][ni] = bv.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < TK; k4 += 4) {
+      double ar[2], ai[2], nai[2], br[4], bi[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        ar[i] = As_re[k4 + fk][wm + i * 8 + fr];
+        ai[i] = As_im[k4 + fk][wm + i * 8 + fr];
+        nai[i] = -ai[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        br[j] = Bs_re[k4 + fk][wn + j * 8 + fr];
+        bi[j] = Bs_im[k4 + fk][wn + j * 8 + fr];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+          dmma884(cr[i][j][0], cr[i][j][1], nai[i], bi[j]);
+          dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+          dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+        }
+    }
+    __syncthreads();
+  }
+  cx<double>* c = C + set * sC + ((int64_t)bb << (d.n_m + d.n_n));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int64_t m = (int64_t)tm * TM + wm + i * 8 + fr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cx<double>* dst = c + (m << d.n_n) + tn * TN + wn + j * 8 + 2 * fk;
+      dst[0] = mk<double>(cr[i][j][0], ci[i][j][0]);
+      dst[1] = mk<double>(cr[i][j][1], ci[i][j][1]);
+    }
+  }
+}
+
 // out[set][perm(o)] += last[set][o]
 struct FinalDev {
   int32_t rank;
@@ -1290,7 +1396,13 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     } else if (kernel == 1) {
       const int64_t blocks = n_out_elems >> 12;
       TQ_REQUIRE(blocks < ((int64_t)1 << 31) && sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");
-      k_tn_gemm<R><<<dim3((unsigned)blocks, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, c, sc, d);
+      static const bool no_dmma = getenv("TQ_TN_NO_DMMA") != nullptr;  // A/B experiments only
+      if (sizeof(R) == 8 && !no_dmma) {  // complex128: FP64 tensor cores
+        if constexpr (sizeof(R) == 8)
+          k_tn_gemm_dmma<<<dim3((unsigned)blocks, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, c, sc, d);
+      } else {
+        k_tn_gemm<R><<<dim3((unsigned)blocks, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, c, sc, d);
+      }
     } else {
       const int64_t blocks = (n_out_elems + 255) / 256;
       TQ_REQUIRE(blocks < ((int64_t)1 << 31) && sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");

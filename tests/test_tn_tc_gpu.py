@@ -133,3 +133,19 @@ def test_split_k_reduction(shape, c128):
     assert kinds == [3], kinds
     tol = 1e-11 if c128 else 1e-5
     assert np.abs(got.reshape(-1) - ref).max() <= tol * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("shape", [(6, 6, 4, 0), (7, 8, 5, 0), (8, 6, 6, 1), (6, 9, 7, 0), (10, 10, 8, 0)],
+                         ids=lambda s: "m%d_n%d_k%d_b%d" % s)
+@pytest.mark.parametrize("shuffle", [False, True], ids=["canonical", "permuted"])
+def test_complex128_gemm_steps_on_fp64_tensor_cores(shape, shuffle):
+    """complex128 GEMM-shaped steps run on k_tn_gemm_dmma (mma.sync m8n8k4 f64, 4M real products): 1e-11."""
+    n_m, n_n, n_k, n_b = shape
+    rng = np.random.RandomState(sum(shape) * 7 + int(shuffle))
+    a_idx, b_idx, o_idx = _case(rng, n_m, n_n, n_k, n_b, shuffle)
+    A = (rng.standard_normal((2,) * len(a_idx)) + 1j * rng.standard_normal((2,) * len(a_idx)))
+    B = (rng.standard_normal((2,) * len(b_idx)) + 1j * rng.standard_normal((2,) * len(b_idx)))
+    ref = _einsum(a_idx, b_idx, o_idx, A, B).reshape(-1)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, c128=True)
+    assert kinds == [1], kinds
+    assert np.abs(got.reshape(-1) - ref).max() <= 1e-11 * np.abs(ref).max()
