@@ -62,6 +62,11 @@ def workload(name):
         spec = W.mbl_2d(4, 1)
         return spec, rng.uniform(0, 1, size=(64, spec["n_params"])).astype(np.float64), "c128", \
             "c4: 16-qubit MBL-2D 4x4 depth-1 (1835 gates, 99 params), probs(q15), complex128, batch 64, fwd+bwd"
+    if name == "c4d20":
+        spec = W.mbl_2d(4, 10)
+        return spec, rng.uniform(0, 1, size=(64, spec["n_params"])).astype(np.float64), "c128", \
+            (f"c4 at depth 20: 16-qubit MBL-2D 4x4, 10 Hd + 10 H0 Trotter sweeps ({len(spec['gates'])} gates, "
+             f"{spec['n_params']} params), probs(q15), complex128, batch 64, fwd+bwd")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -438,6 +443,36 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
     return res
 
 
+def measure_c5_simplified(steps, warmup, device):
+    """Config 5 again with tn_simplify=True (the reference's default flag; its own simplifier does not work):
+    CNOT controls and RZ gates stay on shared wire indices, the plan needs no slicing."""
+    import tedq_b200 as qb
+    from tedq_b200 import workloads as W
+
+    spec = W.lattice_rcs(5, 8, 12, seed=0)
+    cc = W.build_circuit(spec, qb).compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=True,
+                                                  hyper_opt={"max_repeats": 64})
+    bits = [0] * 40
+    for _ in range(max(1, warmup)):
+        amp = cc.amplitude(bits)
+    torch.cuda.synchronize(device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        amp = cc.amplitude(bits)
+    ev1.record()
+    torch.cuda.synchronize(device)
+    ms = ev0.elapsed_time(ev1) / steps
+    plan = cc._tn._amplitude_plan()[2]
+    kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
+    return {"value": 1e3 / ms, "unit": "evals/s", "ms_per_step": ms, "dtype": "c64",
+            "amplitude": [float(amp.real), float(amp.imag)],
+            "steps_by_kernel": {k: kinds.count(k) for k in sorted(set(kinds))},
+            "workload": f"c5 with tn_simplify=True: same circuit and amplitude, diagonal / controlled gates on shared "
+                        f"wire indices: {plan.n_slices} slice(s), width {plan.width}, "
+                        f"{plan.flops * plan.n_slices:.3e} flop per amplitude (dense network: 1.9e13)"}
+
+
 def measure_tn_mode(name, steps, warmup, device):
     """BASELINE configs 2 and 4 in the mode they name: tensor-network contraction (tn_mode=True) through the public
     API — values from the contraction plan (one network per measurement, batched gate operands), gradient from the
@@ -497,7 +532,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c4tn,c5"),
+    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c4d20,c4tn,c5,c5s"),
                     help="other BASELINE configs measured briefly and reported inside the same JSON line")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
@@ -550,6 +585,9 @@ def main():
                                 "steps_per_slice": r["steps_per_slice"], "amplitude": r["amplitude"]}
                 if "cpu_baseline" in r:
                     extras[name]["cpu_baseline"] = r["cpu_baseline"]
+                continue
+            if name == "c5s":
+                extras[name] = measure_c5_simplified(20, 3, device)
                 continue
             if name in ("c2tn", "c4tn"):
                 extras[name] = measure_tn_mode(name[:2], 5, 3, device)

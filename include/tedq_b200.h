@@ -271,6 +271,14 @@ int64_t tq_tn_gate_offset(const tq_plan* plan, int32_t gate);   /* gate == n_gat
 int tq_tn_operands(const tq_plan* plan, const void* params, int64_t batch, void* gate_mats, void* adj_mats,
                    void* cuda_stream);
 
+/* Operands of a structure-aware ("simplified", tn_simplify=True) network: diagonal gates keep only their diagonal,
+ * controlled gates only the entries with equal control bits on both sides — sub-sets of the tensors written by
+ * tq_tn_operands.  dst[set][i] = gate_mats[set][idx[i]] for idx[i] >= 0, adj_mats[set][-idx[i]-1] otherwise
+ * (idx: device int32[n]; src_stride = entries per parameter set of both source buffers; dst: [batch][n]).
+ * The reference's own simplifier (tensor_network.py:90-129) is the non-working counterpart. */
+int tq_tn_gather(const void* gate_mats, const void* adj_mats, int64_t src_stride, const int32_t* idx, int64_t n,
+                 void* dst, int64_t batch, int32_t dtype, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
     L.tq_tn_workspace_bytes.restype = sz
     L.tq_tn_contract.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
     L.tq_tn_contract.restype = i32
+    L.tq_tn_gather.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp]
+    L.tq_tn_gather.restype = i32
     L.tq_tn_plan_set_option.argtypes = [vp, i32, i32]
     L.tq_tn_plan_set_option.restype = i32
     L.tq_tn_plan_step_kernel.argtypes = [vp, i32]

@@ -567,6 +567,17 @@ k_tn_gemm_dmma(const cx<double>* __restrict__ A, int64_t sA, const cx<double>* _
   }
 }
 
+// operands of a simplified network: dst[set][i] = (idx[i] >= 0 ? gates[set][idx[i]] : adjoints[set][-idx[i]-1])
+template <typename R>
+__global__ void k_tn_gather(const cx<R>* __restrict__ g, const cx<R>* __restrict__ a, int64_t src_stride,
+                            const int32_t* __restrict__ idx, int64_t n, cx<R>* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t set = blockIdx.y;
+  const int32_t j = idx[i];
+  dst[set * n + i] = j >= 0 ? g[set * src_stride + j] : a[set * src_stride + (-j - 1)];
+}
+
 // out[set][perm(o)] += last[set][o]
 struct FinalDev {
   int32_t rank;
@@ -1503,6 +1514,22 @@ static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const
                                 workspace_bytes, (cudaStream_t)stream, step_ms);
   return contract_impl<double>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
                                workspace_bytes, (cudaStream_t)stream, step_ms);
+}
+
+extern "C" int tq_tn_gather(const void* gate_mats, const void* adj_mats, int64_t src_stride, const int32_t* idx,
+                            int64_t n, void* dst, int64_t batch, int32_t dtype, void* stream) {
+  TQ_REQUIRE(gate_mats && adj_mats && idx && dst && n > 0 && batch > 0 && batch < 65536, TQ_E_INVALID,
+             "tq_tn_gather: bad arguments");
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)batch);
+  if (dtype == TQ_C64)
+    k_tn_gather<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const cx<float>*)gate_mats, (const cx<float>*)adj_mats,
+                                                               src_stride, idx, n, (cx<float>*)dst);
+  else
+    k_tn_gather<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const cx<double>*)gate_mats,
+                                                                (const cx<double>*)adj_mats, src_stride, idx, n,
+                                                                (cx<double>*)dst);
+  TQ_CUDA_OK(cudaGetLastError());
+  return TQ_OK;
 }
 
 extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,

@@ -22,7 +22,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from . import capi, planner, tn_index
+from . import capi, planner, tn_index, tn_simplify
 from .tn_index import OPD_ADJ, OPD_CAP, OPD_GATE, OPD_OBS
 
 
@@ -32,7 +32,11 @@ class TNExecutor:
         self.ho = hyper_opt or {}
         circuit = backend._circuit
         self.n = circuit.num_qubits
-        self.networks = tn_index.networks_of_circuit(circuit)
+        # tn_simplify=True (the reference's default; its own simplifier does not work, tensor_network.py:94):
+        # diagonal / controlled gates enter with shared wire indices and reduced tensors (tn_simplify.py)
+        self.simplify = bool(getattr(backend, "_tn_simplify", False))
+        self.networks = (tn_simplify if self.simplify else tn_index).networks_of_circuit(circuit)
+        self.gate_structs = tn_simplify.gate_structures(circuit) if self.simplify else [None] * len(circuit.operators)
         self.gate_batched = [any(i >= 0 for i in g.param_idx) for g in backend._ir.gates]
         self.infos: List[planner.PathInfo] = []
         self.plans: List[Optional[capi.TnPlan]] = []
@@ -79,8 +83,12 @@ class TNExecutor:
                 rt = getattr(ms.return_type, "value", ms.return_type)
                 if rt == "expval":
                     lst = ms.obs if isinstance(ms.obs, list) else [ms.obs]
-                    obs.append([torch.tensor(np.asarray(o.matrix, dtype=np.complex128).reshape(-1), dtype=cd,
-                                             device=device) for o in lst])
+                    mats = []
+                    for o in lst:
+                        m = np.asarray(o.matrix, dtype=np.complex128).reshape(-1)
+                        st = tn_simplify.verified_structure(o.name, len(o.qubits), o.matrix) if self.simplify else None
+                        mats.append(torch.tensor(m[list(st[2])] if st else m, dtype=cd, device=device))
+                    obs.append(mats)
                 else:
                     obs.append([])
             self._const[key] = (cap0, cap1, obs)
@@ -93,18 +101,61 @@ class TNExecutor:
             return min(n_slices, r * per), min(n_slices, (r + 1) * per), True
         return 0, n_slices, False
 
+    def _reduced(self, plan_sv, device):
+        """Once: gather list of the reduced gate / adjoint tensors (simplified networks).  -> dict with the device
+        index array for tq_tn_gather, the number of reduced entries per parameter set and, per gate, the offset of
+        its reduced tensor (ket half, adjoint half) inside the reduced buffer."""
+        cache = self.__dict__.setdefault("_red_cache", {})
+        key = str(device)
+        if key not in cache:
+            L = capi.lib()
+            idx, off_g, off_a = [], {}, {}
+            for g, st in enumerate(self.gate_structs):
+                if st is None:
+                    continue
+                base = int(L.tq_tn_gate_offset(plan_sv.handle, g))
+                off_g[g] = len(idx)
+                idx += [base + o for o in st[2]]
+            for g, st in enumerate(self.gate_structs):
+                if st is None:
+                    continue
+                base = int(L.tq_tn_gate_offset(plan_sv.handle, g))
+                off_a[g] = len(idx)
+                idx += [-(base + o) - 1 for o in st[2]]
+            cache[key] = {"idx": torch.tensor(idx, dtype=torch.int32, device=device) if idx else None,
+                          "n": len(idx), "off_g": off_g, "off_a": off_a}
+        return cache[key]
+
+    def _gather_reduced(self, plan_sv, gm, am, total, B, stream):
+        """Reduced operand buffer [B, n_red] of this call (None when nothing is reduced)."""
+        red = self._reduced(plan_sv, gm.device)
+        if not red["n"]:
+            return None
+        buf = torch.empty((B, red["n"]), dtype=gm.dtype, device=gm.device)
+        dt = capi.TQ_C64 if gm.dtype == torch.complex64 else capi.TQ_C128
+        capi.check(capi.lib().tq_tn_gather(gm.data_ptr(), am.data_ptr(), total, red["idx"].data_ptr(), red["n"],
+                                           buf.data_ptr(), B, dt, stream), "tq_tn_gather")
+        return buf
+
     def _operand_tables(self, i, net, plan_sv, total):
         """Per network, once: for every operand the base buffer (0 cap, 1 gate matrices, 2 adjoint matrices,
-        3 + j observable j), its element offset inside that buffer and its parameter-set stride."""
+        3 reduced tensors, 4 + j observable j), its element offset inside that buffer and its parameter-set
+        stride."""
         cache = self.__dict__.setdefault("_opd_tables", {})
         if i not in cache:
             L = capi.lib()
+            red = self._reduced(plan_sv, self._table_device) if self.simplify else None
+            reductions = net.reductions or [None] * len(net.operands)
             base, off, stride = [], [], []
-            for kind, ref in net.operands:
+            for (kind, ref), rd in zip(net.operands, reductions):
                 if kind == OPD_CAP:
                     base.append(0), off.append(0), stride.append(0)
                 elif kind == OPD_OBS:
-                    base.append(3 + ref), off.append(0), stride.append(0)
+                    base.append(4 + ref), off.append(0), stride.append(0)
+                elif rd is not None:
+                    base.append(3)
+                    off.append(red["off_g"][ref] if kind == OPD_GATE else red["off_a"][ref])
+                    stride.append(red["n"] if self.gate_batched[ref] else 0)
                 else:
                     base.append(1 if kind == OPD_GATE else 2)
                     off.append(int(L.tq_tn_gate_offset(plan_sv.handle, ref)))
@@ -130,12 +181,16 @@ class TNExecutor:
                        "tq_tn_operands")
         cap0, cap1, obs = self._constants(dev)
         esz = gm.element_size()
+        with torch.cuda.device(dev):
+            red_buf = self._gather_reduced(plan_sv, gm, am, total, B, stream) if self.simplify else None
         results = []
         for i, net in enumerate(self.networks):
             plan = self._plan(i)
             # operand pointers = base[kind] + offset * element size: vectorised, tables built once per network
+            self._table_device = dev
             tab = self._operand_tables(i, net, plan_sv, total)
-            bases = np.array([cap0.data_ptr(), gm.data_ptr(), am.data_ptr()] + [o.data_ptr() for o in obs[i]],
+            bases = np.array([cap0.data_ptr(), gm.data_ptr(), am.data_ptr(),
+                              red_buf.data_ptr() if red_buf is not None else 0] + [o.data_ptr() for o in obs[i]],
                              dtype=np.int64)
             ptrs = bases[tab["base"]] + tab["off"] * esz
             strides = tab["stride"]
@@ -160,7 +215,11 @@ class TNExecutor:
     def _amplitude_plan(self):
         if getattr(self, "_amp", None) is None:
             circuit = self.backend._circuit
-            net0 = tn_index.index_maps(self.n, [list(op.qubits) for op in circuit.operators], [("state", None)])[0]
+            gq = [list(op.qubits) for op in circuit.operators]
+            if self.simplify:
+                net0 = tn_simplify.index_maps(self.n, gq, self.gate_structs, [("state", None)])[0]
+            else:
+                net0 = tn_index.index_maps(self.n, gq, [("state", None)])[0]
             net = amplitude_network(net0, [0] * self.n)
             so = self.ho.get("slicing_opts") or {}
             info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
@@ -200,12 +259,19 @@ class TNExecutor:
                        "tq_tn_operands")
         cap0, cap1, _ = self._constants(dev)
         esz = gm.element_size()
+        red = self._reduced(plan_sv, dev) if self.simplify else None
+        with torch.cuda.device(dev):
+            red_buf = self._gather_reduced(plan_sv, gm, am, total, B, stream) if self.simplify else None
+        reductions = net.reductions or [None] * len(net.operands)
         ptrs, strides = [], []
-        for kind, ref in net.operands:
+        for (kind, ref), rd in zip(net.operands, reductions):
             if kind == OPD_CAP:
                 one = isinstance(ref, tuple) and int(bits[ref[0]]) == 1
                 ptrs.append((cap1 if one else cap0).data_ptr())
                 strides.append(0)
+            elif rd is not None:
+                ptrs.append(red_buf.data_ptr() + red["off_g"][ref] * esz)
+                strides.append(red["n"] if self.gate_batched[ref] else 0)
             else:
                 off = int(L.tq_tn_gate_offset(plan_sv.handle, ref))
                 ptrs.append(gm.data_ptr() + off * esz)
@@ -216,7 +282,7 @@ class TNExecutor:
         ws = getattr(self, "_amp_ws", None)
         if ws is None or ws.numel() < ws_bytes or ws.device != dev:
             ws = self._amp_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        return plan, ptrs, strides, out, ws, ws_bytes, any_b, (gm, am)
+        return plan, ptrs, strides, out, ws, ws_bytes, any_b, (gm, am, red_buf)
 
     def amplitude(self, flat: torch.Tensor, bits, slice_range=None):
         """<bits| U(params) |0...0> for every parameter set -> complex [B].  Slices are sharded over ranks
@@ -302,7 +368,10 @@ def amplitude_network(net: tn_index.Network, bits):
     no amplitude measurement; this is its state network plus one cap per wire."""
     inputs = [list(t) for t in net.inputs]
     ops = list(net.operands)
+    red = list(net.reductions) if net.reductions else []
     for q, ix in enumerate(net.output):
         inputs.append([ix])
         ops.append((OPD_CAP, (q, int(bits[q]))))
-    return tn_index.Network(inputs, [], ops)
+        if red:
+            red.append(None)
+    return tn_index.Network(inputs, [], ops, red)

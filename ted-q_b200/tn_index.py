@@ -31,6 +31,8 @@ class Network:
     inputs: List[List[int]]                 # index ids per tensor, slow -> fast (C order)
     output: List[int]
     operands: List[Tuple[int, int]] = field(default_factory=list)  # (OPD_*, gate index | obs index | wire)
+    # tn_simplify.py only: per operand, the entries of the full tensor it keeps (None = the whole tensor)
+    reductions: List = field(default_factory=list)
 
     def symbols(self):
         return [[symbol(i) for i in t] for t in self.inputs], [symbol(i) for i in self.output]

@@ -21,13 +21,15 @@ def _case_id(c):
 
 @pytest.mark.parametrize("case", TN_CASES, ids=_case_id)
 @pytest.mark.parametrize("slices", [1, 4])
-def test_tn_mode_matches_reference_fixture(case, slices):
+@pytest.mark.parametrize("simplify", [False, True], ids=["dense", "simplified"])
+def test_tn_mode_matches_reference_fixture(case, slices, simplify):
     """TN-mode values equal the reference's results (same circuit, same parameters) for every measurement kind;
-    sliced plans give the same sum."""
+    sliced plans give the same sum; tn_simplify=True (diagonal / controlled gates on shared wire indices) gives
+    the same numbers as the reference-exact network."""
     dt = case["dtype"]
     hyper = {"max_repeats": 4, "slicing_opts": {"target_num_slices": slices}}
     cc = build(case, dt, case["flat"][0]).compilecircuit(backend="pytorch_b200", tn_mode=True, hyper_opt=hyper,
-                                                          tn_simplify=False, dtype=cdtype(dt))
+                                                          tn_simplify=simplify, dtype=cdtype(dt))
     flat = torch.tensor(case["flat"], dtype=rdtype(dt), device="cuda")
     out = cc.batched(flat).cpu().numpy()
     ref = golden_out(case)
@@ -64,8 +66,8 @@ def test_amplitudes_match_state_vector(n, cycles):
     circ = W.build_circuit(spec, qb)
     ref = sv_ref.run_sv(circ, torch.zeros(0), torch.complex64, return_state=True).numpy().reshape(-1)
     rng = np.random.RandomState(0)
-    for slices in (1, 8):
-        cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+    for slices, simplify in ((1, False), (8, False), (1, True), (8, True)):
+        cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=simplify,
                                  hyper_opt={"max_repeats": 8, "slicing_opts": {"target_num_slices": slices}})
         for bits in ([0] * n, rng.randint(0, 2, n).tolist()):
             amp = complex(cc.amplitude(bits).cpu())
@@ -110,3 +112,8 @@ def test_c5_amplitude_tensor_core_matches_complex128():
     one = [0, 1] * 20
     r1, g1 = complex(c128.amplitude(one).cpu()), complex(c64.amplitude(one).cpu())
     assert abs(g1 - r1) <= 1e-5 * abs(r1), (g1, r1)
+    # the simplified network (CNOT controls and RZ on shared wire indices: 2^44 -> 2^31 flops) gives the same amplitudes
+    simp = W.build_circuit(spec, qb).compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=True,
+                                                    hyper_opt={"max_repeats": 16})
+    assert abs(complex(simp.amplitude(bits).cpu()) - ref) <= 1e-5 * abs(ref)
+    assert abs(complex(simp.amplitude(one).cpu()) - r1) <= 1e-5 * abs(r1)
