@@ -297,7 +297,7 @@ def measure_workload(name, steps, warmup, device, dist_on, world, do_e2e=True, d
     return res
 
 
-C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "16")),
+C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "64")),
             "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64}}
 
 

@@ -39,7 +39,7 @@ class PlanOpts(C.Structure):
 
 
 TN_MAX_RANK = 32
-TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK, TN_OPT_FUSE_SMALL = 0, 1, 2, 3
+TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK, TN_OPT_FUSE_SMALL, TN_OPT_TC_SPLITK = 0, 1, 2, 3, 4
 
 
 class TnStep(C.Structure):

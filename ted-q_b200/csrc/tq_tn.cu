@@ -674,6 +674,7 @@ struct tq_tn_plan {
   int tc_enabled = 1;      // TQ_TN_OPT_TENSOR_CORE
   int tc_min_log2 = 20;    // TQ_TN_OPT_TC_MIN_LOG2: a step runs on tensor cores when k+m+n+b >= this
   int tc_chunk = 32;       // TQ_TN_OPT_TC_CHUNK: complex k accumulated in TMEM between round-to-nearest drains
+  int tc_splitk = 1;       // TQ_TN_OPT_TC_SPLITK
   int num_sms = 148;
 };
 
@@ -1147,6 +1148,9 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
     case TQ_TN_OPT_TC_MIN_LOG2:
       p->tc_min_log2 = value;
       return build_schedule(p);
+    case TQ_TN_OPT_TC_SPLITK:
+      p->tc_splitk = value != 0;
+      return TQ_OK;
     case TQ_TN_OPT_FUSE_SMALL:
       p->fuse_enabled = value != 0;
       return build_schedule(p);
@@ -1182,6 +1186,17 @@ int32_t tq_tn_plan_step_flags(const tq_tn_plan* p, int32_t s) {
   return (p->dep_slice[s] ? 1 : 0) | (p->dep_batch[s] ? 2 : 0);
 }
 
+// split-K factor of tensor-core step s at a given batch: power of two, >= 16 k-blocks (128 complex k) per split,
+// only when the step has tiles for at most half of the SMs
+static int tc_splits(const tq_tn_plan* p, int s, int64_t sets) {
+  const TcStep& T = p->tc[s];
+  const int64_t nz = sets << p->steps[s].n_b;
+  const int64_t tiles = (int64_t)T.tiles_a * T.tiles_b * nz;
+  int splits = 1;
+  while (p->tc_splitk && tiles * splits * 2 <= p->num_sms && T.kblocks / (splits * 2) >= 16) splits *= 2;
+  return splits;
+}
+
 // pinned images (slice-invariant operands of per-slice tensor-core steps): total bytes; offsets[2*s], [2*s+1]
 static size_t tn_pinned_bytes(const tq_tn_plan* p, int64_t batch, std::vector<int64_t>* offsets) {
   size_t top = 0;
@@ -1214,7 +1229,9 @@ static size_t tn_image_bytes(const tq_tn_plan* p, int64_t batch) {
     if (kernel != 2) continue;
     const int64_t nz = (p->dep_batch[s] ? batch : 1) << p->steps[s].n_b;
     const TcStep& T = p->tc[s];
-    need = std::max(need, (size_t)(((T.pin_a ? 0 : T.img_a_z) + (T.pin_b ? 0 : T.img_b_z)) * nz));
+    const int splits = tc_splits(p, (int)s, p->dep_batch[s] ? batch : 1);
+    const size_t partials = splits > 1 ? (size_t)splits * (((size_t)(p->dep_batch[s] ? batch : 1)) << p->t_rank[p->n_in + s]) * 8 : 0;
+    need = std::max(need, (size_t)(((T.pin_a ? 0 : T.img_a_z) + (T.pin_b ? 0 : T.img_b_z)) * nz) + partials + 1024);
   }
   return need + tn_pinned_bytes(p, batch, nullptr);
 }
@@ -1254,8 +1271,8 @@ static int tc_setup_once() {
 // (mode bit 1).  img_a / img_b: where each operand's image lives (scratch or pinned); skip_a / skip_b: that image
 // is pinned and already packed.
 static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t sa, const cx<float>* b, int64_t sb,
-                       cx<float>* c, int64_t sc, int64_t sets, uint8_t* img_a, uint8_t* img_b, bool pack_a,
-                       bool pack_b, bool gemm, cudaStream_t st, cudaEvent_t ev_packed) {
+                       cx<float>* c, int64_t sc, int64_t sets, uint8_t* img_a, uint8_t* img_b, uint8_t* partials,
+                       bool pack_a, bool pack_b, bool gemm, cudaStream_t st, cudaEvent_t ev_packed) {
   int rc = tc_setup_once();
   if (rc) return rc;
   const tq_tn_step& stp = p->steps[s];
@@ -1303,7 +1320,16 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   g.n_b_log2 = stp.n_b;
   g.stages = T.stages;
   g.c_bb_stride = (int64_t)1 << (stp.n_m + stp.n_n);
-  const int64_t total = (int64_t)T.tiles_a * T.tiles_b * nz;
+  const int splits = tc_splits(p, s, sets);
+  const int64_t c_elems = (int64_t)1 << (stp.n_m + stp.n_n + stp.n_b);
+  g.splits = splits;
+  g.kb_per_split = T.kblocks / splits;
+  if (splits > 1) {  // partial sums: [split][set][C], summed in order afterwards
+    g.c = reinterpret_cast<float2*>(partials);
+    g.c_set_stride = c_elems;
+    g.c_split_stride = sets * c_elems;
+  }
+  const int64_t total = (int64_t)T.tiles_a * T.tiles_b * nz * splits;
   const unsigned grid = (unsigned)std::min<int64_t>(total, p->num_sms);
   const size_t smem = tc::SMEM_BUDGET + 1024;
   switch (T.c_t) {
@@ -1311,6 +1337,11 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
     case 32: tc::k_tc_gemm<32><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
     case 64: tc::k_tc_gemm<64><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
     default: tc::k_tc_gemm<128><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+  }
+  if (splits > 1) {
+    const int64_t n4 = c_elems / 2;
+    tc::k_tc_splitk_sum<<<dim3((unsigned)((n4 + 255) / 256), (unsigned)sets), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(partials), splits, sets * n4, n4, reinterpret_cast<float4*>(c), sc / 2, n4);
   }
   TQ_CUDA_OK(cudaGetLastError());
   return TQ_OK;
@@ -1381,7 +1412,8 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
         const TcStep& T = p->tc[s];
         if (kernel == 2 && (T.pin_a || T.pin_b))
           return run_step_tc(p, s, a, sa, b, sb, c, sc, sets, pinned + std::max<int64_t>(0, pin_off[2 * s]),
-                             pinned + std::max<int64_t>(0, pin_off[2 * s + 1]), T.pin_a, T.pin_b, false, st, nullptr);
+                             pinned + std::max<int64_t>(0, pin_off[2 * s + 1]), nullptr, T.pin_a, T.pin_b, false, st,
+                             nullptr);
       }
       return TQ_OK;
     }
@@ -1393,7 +1425,9 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
         const int64_t nz = sets << stp.n_b;
         uint8_t* img_a = T.pin_a ? pinned + pin_off[2 * s] : images;
         uint8_t* img_b = T.pin_b ? pinned + pin_off[2 * s + 1] : images + (T.pin_a ? 0 : T.img_a_z * nz);
-        int rc = run_step_tc(p, s, a, sa, b, sb, c, sc, sets, img_a, img_b, !T.pin_a, !T.pin_b, true, st,
+        uint8_t* partials = images + (T.pin_a ? 0 : T.img_a_z * nz) + (T.pin_b ? 0 : T.img_b_z * nz);
+        partials = (uint8_t*)(((uintptr_t)partials + 255) & ~(uintptr_t)255);
+        int rc = run_step_tc(p, s, a, sa, b, sb, c, sc, sets, img_a, img_b, partials, !T.pin_a, !T.pin_b, true, st,
                              timed ? ev[3 * s + 1] : nullptr);
         if (rc) return rc;
       }

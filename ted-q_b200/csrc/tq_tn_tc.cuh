@@ -244,6 +244,10 @@ struct GemmParams {
   int32_t tiles_a, tiles_b, kblocks, n_z, n_b_log2, stages;
   int32_t chunk;             // k-blocks accumulated inside the tensor core before a drain (see below)
   int32_t debug;             // experiments only: bit 0 = drains skip their TMEM loads (wrong results)
+  // split-K: a step with few output tiles and a long K is cut into `splits` K ranges per tile so that every SM
+  // has work; split s writes its partial sums to c + s * c_split_stride, k_tc_splitk_sum adds them in order
+  int32_t splits, kb_per_split;
+  int64_t c_split_stride;
   int64_t c_bb_stride;       // complex entries between kept-shared index values (2^(n_m + n_n))
 };
 
@@ -293,19 +297,21 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
   const uint32_t tmem_base = tmem_base_s;
 
   const int64_t tiles_per_z = (int64_t)p.tiles_a * p.tiles_b;
-  const int64_t total = tiles_per_z * p.n_z;
+  const int64_t total = tiles_per_z * p.n_z * p.splits;  // work item = (tile, K range), K range fastest
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int64_t t = w / p.splits;
+        const int kbeg = (int)(w - t * p.splits) * p.kb_per_split;
         const int64_t z = t / tiles_per_z;
         const int64_t r = t - z * tiles_per_z;
         const int64_t tb = r / p.tiles_a, ta = r - tb * p.tiles_a;
         const uint8_t* ga = p.img_a + z * p.img_a_z + ta * (int64_t)p.kblocks * A_CHUNK;
         const uint8_t* gb = p.img_b + z * p.img_b_z + tb * (int64_t)p.kblocks * b_chunk;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int kb = kbeg; kb < kbeg + p.kb_per_split; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), sbytes);
           const uint32_t sa = smem0 + (uint32_t)stage * sbytes;
@@ -324,9 +330,9 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * C_T >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
-        for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk) {
-          const int kb1 = min(kb0 + p.chunk, p.kblocks);
+      for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int kb0 = 0; kb0 < p.kb_per_split; kb0 += p.chunk) {
+          const int kb1 = min(kb0 + p.chunk, p.kb_per_split);
           mbar_wait(tempty_bar(as), aphase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
@@ -363,11 +369,13 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t bb_mask = (1u << p.n_b_log2) - 1u;
-    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      const int64_t t = w / p.splits;
+      const int64_t split = w - t * p.splits;
       float acc_re[HALF], acc_im[HALF];
 #pragma unroll
       for (int j = 0; j < HALF; ++j) acc_re[j] = acc_im[j] = 0.f;
-      for (int kb0 = 0; kb0 < p.kblocks; kb0 += p.chunk) {
+      for (int kb0 = 0; kb0 < p.kb_per_split; kb0 += p.chunk) {
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)as * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * HALF);
@@ -400,7 +408,8 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
       const int64_t set = z >> p.n_b_log2, bb = z & bb_mask;
       const int64_t row = ta * ROWS + q * 32 + lane;
       const int64_t col0 = tb * C_T + h * HALF;
-      float2* dst = p.c + set * p.c_set_stride + bb * p.c_bb_stride + row * p.c_rs + col0 * p.c_cs;
+      float2* dst = p.c + split * p.c_split_stride + set * p.c_set_stride + bb * p.c_bb_stride + row * p.c_rs +
+                    col0 * p.c_cs;
       if (p.c_cs == 1) {
 #pragma unroll
         for (int j = 0; j < HALF; j += 2)
@@ -416,6 +425,23 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+}
+
+// C[set][i] = sum over splits of part[split][set][i], fixed order (deterministic); float4 = 2 complex
+__global__ void k_tc_splitk_sum(const float4* __restrict__ part, int splits, int64_t split_stride4,
+                                int64_t part_set_stride4, float4* __restrict__ c, int64_t c_set_stride4, int64_t n4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  part += blockIdx.y * part_set_stride4;
+  float4 acc = part[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = part[s * split_stride4 + i];
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  c[blockIdx.y * c_set_stride4 + i] = acc;
 }
 
 }  // namespace tc

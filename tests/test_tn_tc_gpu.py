@@ -14,12 +14,14 @@ from tedq_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
-def _contract(inputs, output, arrays, batched, tensor_core, B=1, min_log2=0, chunk=None, c128=False):
+def _contract(inputs, output, arrays, batched, tensor_core, B=1, min_log2=0, chunk=None, c128=False, splitk=True):
     plan = capi.TnPlan(inputs, output, [(0, 1)], [], batched, capi.TQ_C128 if c128 else capi.TQ_C64)
     plan.set_option(capi.TN_OPT_TENSOR_CORE, 1 if tensor_core else 0)
     plan.set_option(capi.TN_OPT_TC_MIN_LOG2, min_log2)
     if chunk is not None:
         plan.set_option(capi.TN_OPT_TC_CHUNK, chunk)
+    if not splitk:
+        plan.set_option(capi.TN_OPT_TC_SPLITK, 0)
     kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
     dev = "cuda"
     cd = torch.complex128 if c128 else torch.complex64
@@ -59,6 +61,7 @@ def _einsum(a_idx, b_idx, o_idx, A, B, batch_a=False, batch_b=False):
 SHAPES = [  # (n_m, n_n, n_k, n_b)
     (7, 4, 0, 0), (7, 4, 3, 0), (7, 7, 4, 0), (8, 7, 5, 0), (4, 9, 6, 0), (10, 10, 8, 0), (7, 5, 1, 0),
     (9, 8, 7, 0), (7, 6, 4, 2), (5, 8, 5, 1), (11, 7, 6, 0), (7, 11, 9, 0), (8, 8, 12, 0),
+    (7, 7, 12, 0), (8, 7, 11, 0), (7, 4, 11, 1),     # few tiles, long K: split-K partial sums
 ]
 
 
@@ -90,16 +93,19 @@ def test_tc_error_is_fp32_class():
     got, _ = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True)
     rel = np.abs(got.reshape(-1) - ref).max() / np.abs(ref).max()
     assert rel < 2e-6, rel
-    biased, _ = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, chunk=1 << 20)
+    got, _ = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, splitk=False)
+    assert np.abs(got.reshape(-1) - ref).max() / np.abs(ref).max() < 2e-6
+    biased, _ = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, chunk=1 << 20, splitk=False)
     rel_biased = np.abs(biased.reshape(-1) - ref).max() / np.abs(ref).max()
     assert rel_biased > 4 * rel, (rel, rel_biased)
 
 
 @pytest.mark.parametrize("which", ["a", "b", "both"])
-def test_tc_step_batched_parameter_sets(which):
+@pytest.mark.parametrize("shape", [(8, 5, 6, 1), (7, 6, 11, 0)], ids=["plain", "splitk"])
+def test_tc_step_batched_parameter_sets(which, shape):
     rng = np.random.RandomState(11)
     n_sets = 3
-    a_idx, b_idx, o_idx = _case(rng, 8, 5, 6, 1)
+    a_idx, b_idx, o_idx = _case(rng, *shape)
     ba, bb = which in ("a", "both"), which in ("b", "both")
     A = _rand(rng, ((n_sets,) if ba else ()) + (2,) * len(a_idx))
     B = _rand(rng, ((n_sets,) if bb else ()) + (2,) * len(b_idx))
