@@ -263,12 +263,15 @@ __global__ void k_tn_dot_sum(const cx<R>* __restrict__ partial, int n_part, cx<R
 // (L1/L2-resident) arenas, so the larger kernels read them unchanged.
 // ---------------------------------------------------------------------------
 constexpr int FUSE_MAX_RANK = 16, FUSE_MAX_SLICE_BITS = 4;
-struct FusedStep {
+struct alignas(16) FusedStep {
   int64_t a_off, b_off, c_off;  // complex-entry offsets inside their space
   int32_t a_in, b_in;           // >= 0: input tensor id, -1: shared arena, -2: per-set arena
   int32_t c_space;              // -1 / -2
   int8_t n_k, n_m, n_n, n_b;
-  int8_t is_cta, pad[3];
+  int8_t is_cta;
+  int8_t micro_iters;           // > 0: a "micro" step — <= 32 (output, K-part) items, <= 8 K iterations per lane;
+  int8_t micro_lpo, pad;        //      every lane's operand offsets are precomputed on the host (micro_row)
+  int32_t micro_row;            //      first row of its [micro_iters][32] table of (a_off | b_off << 16)
   int8_t a_bits[FUSE_MAX_RANK];  // bit positions inside A of [k..., m..., b...]
   int8_t b_bits[FUSE_MAX_RANK];  // bit positions inside B of [k..., n..., b...]
   int8_t a_sl_ord[FUSE_MAX_SLICE_BITS], a_sl_bit[FUSE_MAX_SLICE_BITS];  // sliced bits of an input operand (-1: none)
@@ -286,9 +289,11 @@ __device__ __forceinline__ const cx<R>* fused_operand(const InputRef* __restrict
   if (in == -1) return shared + off;
   if (in == -2) return perset + off;
   int64_t so = 0;
+  if (*reinterpret_cast<const int32_t*>(ord) != -1) {  // any sliced bit at all? (four int8 entries, -1 = none)
 #pragma unroll
-  for (int j = 0; j < FUSE_MAX_SLICE_BITS; ++j)
-    if (ord[j] >= 0) so |= (int64_t)((slice >> ord[j]) & 1) << bit[j];
+    for (int j = 0; j < FUSE_MAX_SLICE_BITS; ++j)
+      if (ord[j] >= 0) so |= (int64_t)((slice >> ord[j]) & 1) << bit[j];
+  }
   return reinterpret_cast<const cx<R>*>(inputs[in].ptr) + set * inputs[in].stride + so + off;
 }
 
@@ -299,7 +304,8 @@ constexpr int FUSE_KTAB_LOG2 = 10;
 template <typename R, bool KTAB>
 __device__ __forceinline__ void fused_exec(const FusedStep& f, const InputRef* __restrict__ inputs, cx<R>* shared,
                                            cx<R>* perset, int64_t set, int64_t slice, int t, int G, int log2G,
-                                           const uint32_t* ktab_a, const uint32_t* ktab_b) {
+                                           const uint32_t* ktab_a, const uint32_t* ktab_b, const uint32_t* mtab,
+                                           const uint32_t* ntab) {
   const cx<R>* a = fused_operand<R>(inputs, shared, perset, set, slice, f.a_in, f.a_off, f.a_sl_ord, f.a_sl_bit);
   const cx<R>* b = fused_operand<R>(inputs, shared, perset, set, slice, f.b_in, f.b_off, f.b_sl_ord, f.b_sl_bit);
   cx<R>* c = (f.c_space == -1 ? shared : perset) + f.c_off;
@@ -319,16 +325,44 @@ __device__ __forceinline__ void fused_exec(const FusedStep& f, const InputRef* _
     const uint32_t bb = o >> (n_n + n_m);
     cx<R> acc = mk<R>(0, 0);
     if (valid) {
-      const uint32_t ao = scat(m, f.a_bits + n_k, n_m) | scat(bb, f.a_bits + n_k + n_m, n_b);
-      const uint32_t bo = scat(n, f.b_bits + n_k, n_n) | scat(bb, f.b_bits + n_k + n_n, n_b);
+      uint32_t ao, bo;
+      if (KTAB) {  // m / n offsets from the per-step tables (low FUSE_KTAB_LOG2 bits), the rest by scatter
+        const int m_lo = min(n_m, FUSE_KTAB_LOG2), n_lo2 = min(n_n, FUSE_KTAB_LOG2);
+        ao = mtab[m & ((1u << m_lo) - 1u)] | scat(m >> m_lo, f.a_bits + n_k + m_lo, n_m - m_lo) |
+             scat(bb, f.a_bits + n_k + n_m, n_b);
+        bo = ntab[n & ((1u << n_lo2) - 1u)] | scat(n >> n_lo2, f.b_bits + n_k + n_lo2, n_n - n_lo2) |
+             scat(bb, f.b_bits + n_k + n_n, n_b);
+      } else {
+        ao = scat(m, f.a_bits + n_k, n_m) | scat(bb, f.a_bits + n_k + n_m, n_b);
+        bo = scat(n, f.b_bits + n_k, n_n) | scat(bb, f.b_bits + n_k + n_n, n_b);
+      }
       if (KTAB) {
         for (int kh = 0; kh < (K >> n_lo); ++kh) {
           const uint32_t ah = ao | scat((uint32_t)kh, f.a_bits + n_lo, n_k - n_lo);
           const uint32_t bh = bo | scat((uint32_t)kh, f.b_bits + n_lo, n_k - n_lo);
-          for (int k = (int)kp; k < K_lo; k += lpo) acc = cfma(a[ah | ktab_a[k]], b[bh | ktab_b[k]], acc);
+          int k = (int)kp;
+          for (; k + 3 * lpo < K_lo; k += 4 * lpo) {  // four independent operand pairs in flight
+            const cx<R> a0 = a[ah | ktab_a[k]], b0 = b[bh | ktab_b[k]];
+            const cx<R> a1 = a[ah | ktab_a[k + lpo]], b1 = b[bh | ktab_b[k + lpo]];
+            const cx<R> a2 = a[ah | ktab_a[k + 2 * lpo]], b2 = b[bh | ktab_b[k + 2 * lpo]];
+            const cx<R> a3 = a[ah | ktab_a[k + 3 * lpo]], b3 = b[bh | ktab_b[k + 3 * lpo]];
+            acc = cfma(a0, b0, acc);
+            acc = cfma(a1, b1, acc);
+            acc = cfma(a2, b2, acc);
+            acc = cfma(a3, b3, acc);
+          }
+          for (; k < K_lo; k += lpo) acc = cfma(a[ah | ktab_a[k]], b[bh | ktab_b[k]], acc);
         }
       } else {
-        for (int k = (int)kp; k < K; k += lpo)
+        int k = (int)kp;
+        for (; k + lpo < K; k += 2 * lpo) {  // two independent operand pairs in flight
+          const cx<R> a0 = a[ao | scat((uint32_t)k, f.a_bits, n_k)], b0 = b[bo | scat((uint32_t)k, f.b_bits, n_k)];
+          const cx<R> a1 = a[ao | scat((uint32_t)(k + lpo), f.a_bits, n_k)];
+          const cx<R> b1 = b[bo | scat((uint32_t)(k + lpo), f.b_bits, n_k)];
+          acc = cfma(a0, b0, acc);
+          acc = cfma(a1, b1, acc);
+        }
+        for (; k < K; k += lpo)
           acc = cfma(a[ao | scat((uint32_t)k, f.a_bits, n_k)], b[bo | scat((uint32_t)k, f.b_bits, n_k)], acc);
       }
     }
@@ -340,15 +374,44 @@ __device__ __forceinline__ void fused_exec(const FusedStep& f, const InputRef* _
   }
 }
 
+// Micro step: the 1700-of-1743 kind (a handful of outputs, K <= 32).  Nothing is decoded on the device: lane l
+// reads its operand offsets for K iteration j from table[j][l] (one coalesced 128-byte load per iteration).
+template <typename R>
+__device__ __forceinline__ void fused_micro(const FusedStep& f, const uint32_t* __restrict__ table,
+                                            const InputRef* __restrict__ inputs, cx<R>* shared, cx<R>* perset,
+                                            int64_t set, int64_t slice, int lane) {
+  const cx<R>* a = fused_operand<R>(inputs, shared, perset, set, slice, f.a_in, f.a_off, f.a_sl_ord, f.a_sl_bit);
+  const cx<R>* b = fused_operand<R>(inputs, shared, perset, set, slice, f.b_in, f.b_off, f.b_sl_ord, f.b_sl_bit);
+  const uint32_t* row = table + (int64_t)f.micro_row * 32 + lane;
+  uint32_t off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) off[j] = j < f.micro_iters ? row[j * 32] : 0xffffffffu;
+  cx<R> acc = mk<R>(0, 0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (off[j] != 0xffffffffu) acc = cfma(a[off[j] & 0xffffu], b[off[j] >> 16], acc);
+  const int lpo = 1 << f.micro_lpo;
+  for (int d = lpo >> 1; d > 0; d >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+  }
+  if (off[0] != 0xffffffffu && (lane & (lpo - 1)) == 0) {
+    cx<R>* c = (f.c_space == -1 ? shared : perset) + f.c_off;
+    c[lane >> f.micro_lpo] = acc;
+  }
+}
+
 constexpr int FUSE_STAGE = 128;  // step descriptors staged in shared memory per chunk
 template <typename R, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ level_off,
-           const int32_t* __restrict__ level_ncta, int n_levels, const InputRef* __restrict__ inputs, cx<R>* shared,
-           cx<R>* perset_base, int64_t set_stride, int64_t slice) {
+           const int32_t* __restrict__ level_ncta, int n_levels, const uint32_t* __restrict__ micro,
+           const InputRef* __restrict__ inputs, cx<R>* shared, cx<R>* perset_base, int64_t set_stride,
+           int64_t slice) {
   static_assert(sizeof(FusedStep) % 16 == 0, "descriptors are staged with 16-byte copies");
   __shared__ __align__(16) FusedStep sdesc[FUSE_STAGE];
   __shared__ uint32_t ktab_a[1 << FUSE_KTAB_LOG2], ktab_b[1 << FUSE_KTAB_LOG2];
+  __shared__ uint32_t mtab[1 << FUSE_KTAB_LOG2], ntab[1 << FUSE_KTAB_LOG2];
   const int64_t set = blockIdx.x;
   cx<R>* perset = perset_base + set * set_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,12 +432,21 @@ k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ leve
           ktab_a[k] = scat((uint32_t)k, f.a_bits, n_lo);
           ktab_b[k] = scat((uint32_t)k, f.b_bits, n_lo);
         }
+        const int m_lo = min((int)f.n_m, FUSE_KTAB_LOG2), n_lo2 = min((int)f.n_n, FUSE_KTAB_LOG2);
+        for (int v = threadIdx.x; v < (1 << m_lo); v += THREADS) mtab[v] = scat((uint32_t)v, f.a_bits + f.n_k, m_lo);
+        for (int v = threadIdx.x; v < (1 << n_lo2); v += THREADS) ntab[v] = scat((uint32_t)v, f.b_bits + f.n_k, n_lo2);
         __syncthreads();
-        fused_exec<R, true>(f, inputs, shared, perset, set, slice, (int)threadIdx.x, THREADS, LOG2T, ktab_a, ktab_b);
+        fused_exec<R, true>(f, inputs, shared, perset, set, slice, (int)threadIdx.x, THREADS, LOG2T, ktab_a, ktab_b,
+                            mtab, ntab);
         __syncthreads();
       }
-      for (int i = ncta + warp; i < c1 - c0; i += NW)
-        fused_exec<R, false>(sdesc[i], inputs, shared, perset, set, slice, lane, 32, 5, nullptr, nullptr);
+      for (int i = ncta + warp; i < c1 - c0; i += NW) {
+        if (sdesc[i].micro_iters > 0)
+          fused_micro<R>(sdesc[i], micro, inputs, shared, perset, set, slice, lane);
+        else
+          fused_exec<R, false>(sdesc[i], inputs, shared, perset, set, slice, lane, 32, 5, nullptr, nullptr, nullptr,
+                               nullptr);
+      }
       __syncthreads();  // level boundary (data) and descriptor buffer reuse
     }
   }
@@ -597,7 +669,7 @@ __global__ void k_tn_final(const cx<R>* __restrict__ last, int64_t sL, cx<R>* __
 
 constexpr int DOT_MAX_OUT_LOG2 = 6, DOT_MIN_K_LOG2 = 12, DOT_BLOCKS = 128;
 // a step joins a fused run when k+m+n+b <= this (one CTA per parameter set does the whole step)
-constexpr int FUSE_MAX_WORK_BATCHED = 18, FUSE_MAX_WORK_SHARED = 14, FUSE_CTA_WORK = 11;
+constexpr int FUSE_MAX_WORK_BATCHED = 18, FUSE_MAX_WORK_SHARED = 14, FUSE_CTA_WORK = 8;
 
 struct SchedItem {
   int step = -1;                       // >= 0: one step on its own kernel(s)
@@ -667,6 +739,7 @@ struct tq_tn_plan {
   std::vector<char> t_slice;        // per tensor id: depends on a sliced index
   std::vector<int> t_rank;
   FusedStep* d_fsteps = nullptr;
+  uint32_t* d_micro = nullptr;      // offset tables of the micro steps
   int32_t* d_levels = nullptr;      // [level_off (n+1 per run) | level_ncta] blocks, see SchedItem
   int fuse_enabled = 1;             // TQ_TN_OPT_FUSE_SMALL
   // tensor-core path (complex64 only): per-step operand-image descriptions
@@ -702,6 +775,7 @@ static int build_schedule(tq_tn_plan* p) {
   for (int t = 0; t < n_in; ++t) done[t] = 1;
   std::vector<FusedStep> fsteps;
   std::vector<int32_t> levels;
+  std::vector<uint32_t> microtab;
   for (int phase = 0; phase < 2; ++phase) {
     p->items[phase].clear();
     std::vector<int> remaining;
@@ -864,6 +938,35 @@ static int build_schedule(tq_tn_plan* p) {
         f.n_b = (int8_t)st.n_b;
         const int outl = st.n_m + st.n_n + st.n_b;
         f.is_cta = st.n_k + outl >= FUSE_CTA_WORK;
+        {  // micro step: everything a lane needs is tabulated here
+          const int lpo_log2 = std::max(0, std::min({(int)st.n_k, 5, 5 - outl}));
+          const int items = 1 << (outl + lpo_log2), iters = (1 << st.n_k) >> lpo_log2;
+          if (!f.is_cta && outl + lpo_log2 <= 5 && iters <= 8) {
+            f.micro_iters = (int8_t)iters;
+            f.micro_lpo = (int8_t)lpo_log2;
+            f.micro_row = (int32_t)(microtab.size() / 32);
+            auto sc = [](uint32_t v, const int8_t* pos, int n) {
+              uint32_t r = 0;
+              for (int j = 0; j < n; ++j) r |= ((v >> j) & 1u) << pos[j];
+              return r;
+            };
+            for (int j = 0; j < iters; ++j)
+              for (int l = 0; l < 32; ++l) {
+                if (l >= items) {
+                  microtab.push_back(0xffffffffu);
+                  continue;
+                }
+                const uint32_t o = (uint32_t)l >> lpo_log2, k = ((uint32_t)l & ((1u << lpo_log2) - 1u)) + ((uint32_t)j << lpo_log2);
+                const uint32_t n = o & ((1u << st.n_n) - 1u), m = (o >> st.n_n) & ((1u << st.n_m) - 1u);
+                const uint32_t bb = o >> (st.n_n + st.n_m);
+                const uint32_t ao = sc(k, st.lhs_bits, st.n_k) | sc(m, st.lhs_bits + st.n_k, st.n_m) |
+                                    sc(bb, st.lhs_bits + st.n_k + st.n_m, st.n_b);
+                const uint32_t bo = sc(k, st.rhs_bits, st.n_k) | sc(n, st.rhs_bits + st.n_k, st.n_n) |
+                                    sc(bb, st.rhs_bits + st.n_k + st.n_n, st.n_b);
+                microtab.push_back(ao | (bo << 16));
+              }
+          }
+        }
         for (int j = 0; j < st.n_k + st.n_m + st.n_b; ++j) f.a_bits[j] = st.lhs_bits[j];
         for (int j = 0; j < st.n_k + st.n_n + st.n_b; ++j) f.b_bits[j] = st.rhs_bits[j];
         for (int j = 0; j < FUSE_MAX_SLICE_BITS; ++j) f.a_sl_ord[j] = f.b_sl_ord[j] = -1;
@@ -882,8 +985,14 @@ static int build_schedule(tq_tn_plan* p) {
     }
   cudaFree(p->d_fsteps);
   cudaFree(p->d_levels);
+  cudaFree(p->d_micro);
   p->d_fsteps = nullptr;
   p->d_levels = nullptr;
+  p->d_micro = nullptr;
+  if (!microtab.empty()) {
+    TQ_CUDA_OK(cudaMalloc((void**)&p->d_micro, microtab.size() * sizeof(uint32_t)));
+    TQ_CUDA_OK(cudaMemcpy(p->d_micro, microtab.data(), microtab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   if (!fsteps.empty()) {
     TQ_CUDA_OK(cudaMalloc((void**)&p->d_fsteps, fsteps.size() * sizeof(FusedStep)));
     TQ_CUDA_OK(cudaMemcpy(p->d_fsteps, fsteps.data(), fsteps.size() * sizeof(FusedStep), cudaMemcpyHostToDevice));
@@ -981,6 +1090,7 @@ void tq_tn_plan_destroy(tq_tn_plan* p) {
   for (int32_t* q : p->d_kb) cudaFree(q);
   cudaFree(p->d_fsteps);
   cudaFree(p->d_levels);
+  cudaFree(p->d_micro);
   delete p;
 }
 
@@ -1469,12 +1579,12 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     // one CTA per parameter set; a lone CTA gets 32 warps (latency-bound), many sets get 2 CTAs per SM
     if (sets == 1)
       k_tn_fused<R, 1024><<<1, 1024, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
-                                              p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels, table, shared,
-                                              perset, p->arena_set, slice);
+                                              p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels, p->d_micro,
+                                              table, shared, perset, p->arena_set, slice);
     else
       k_tn_fused<R, 512><<<(unsigned)sets, 512, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
                                                          p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels,
-                                                         table, shared, perset, p->arena_set, slice);
+                                                         p->d_micro, table, shared, perset, p->arena_set, slice);
     TQ_CUDA_OK(cudaGetLastError());
     if (timed) {
       TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 1], st));
