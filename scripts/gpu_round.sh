@@ -1,10 +1,16 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_v9.json 2> gpurun_out/bench_v9.err; tail -c 300 gpurun_out/bench_v9.err
+timeout 600 python -m pytest tests/test_tn_fused_gpu.py tests/test_tn_gpu.py tests/test_tn_tc_gpu.py -x -q 2>&1 | tail -3
+timeout 300 python scripts/c2tn_run.py
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 10 --csv --log-file gpurun_out/launches_c2tn.csv python scripts/c2tn_run.py > /dev/null 2>&1
 python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_v9.json'))
-print(d['value'], d['e2e']['value'], d['cpu_baseline']['value'])
-for k,v in d['other_configs'].items(): print(k, round(v['value'],2), round(v['ms_per_step'],3), v.get('fwd_only_ms'), v.get('steps_by_kernel'))
+import csv
+rows=list(csv.reader(open('gpurun_out/launches_c2tn.csv')))
+hi=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
+hdr=rows[hi]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value'); gi=hdr.index('Grid Size') if 'Grid Size' in hdr else None
+for r in rows[hi+2:hi+12]:
+    print(r[ki][:50], r[vi], r[gi] if gi else '')
 PY
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_tn_gemm_dmma -s 1 -c 1 -o gpurun_out/prof_dmma python scripts/tc_gemm_single.py 11 10 10 32 2 c128 > gpurun_out/ncu_dmma.log 2>&1; tail -1 gpurun_out/ncu_dmma.log
+timeout 300 python scripts/c5_simplified.py 64 1 2>&1 | grep -E "amp|profiled" | tail -2
+timeout 100 python scripts/tc_gemm_single.py 11 10 10 32 3 c128 | tail -1
+timeout 100 python scripts/tc_gemm_single.py 12 12 8 32 3 c128 | tail -1
+timeout 300 python scripts/c5_amplitude.py 64 1 2>&1 | sed -n 3,9p

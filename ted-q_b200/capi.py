@@ -398,11 +398,20 @@ class TnPlan:
         """bit 0: repeats per slice, bit 1: batched over parameter sets."""
         return int(lib().tq_tn_plan_step_flags(self.handle, s))
 
+    def _ptr_arrays(self, input_ptrs, input_strides):
+        """ctypes views of the operand pointer / stride tables; int64 numpy arrays go straight through."""
+        n = self.n_inputs
+        if isinstance(input_ptrs, np.ndarray):
+            ptrs_np = np.ascontiguousarray(input_ptrs, dtype=np.int64)
+            strides_np = np.ascontiguousarray(input_strides, dtype=np.int64)
+            assert ptrs_np.shape == (n,) and strides_np.shape == (n,)
+            return (ptrs_np.ctypes.data_as(C.POINTER(C.c_void_p)), strides_np.ctypes.data_as(C.POINTER(C.c_int64)),
+                    (ptrs_np, strides_np))
+        return (C.c_void_p * n)(*input_ptrs), (C.c_int64 * n)(*input_strides), None
+
     def profile(self, input_ptrs, input_strides, batch, slice_id, out_ptr, ws_ptr, ws_bytes, stream):
         """Per-step milliseconds of one slice: array [n_steps, 2] = (whole step, operand packing part)."""
-        n = self.n_inputs
-        ptrs = (C.c_void_p * n)(*input_ptrs)
-        strides = (C.c_int64 * n)(*input_strides)
+        ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
         ms = (C.c_float * (2 * self.n_steps + 2))()
         check(lib().tq_tn_profile(self.handle, ptrs, strides, batch, slice_id, out_ptr, ws_ptr, ws_bytes, stream, ms),
               "tq_tn_profile")
@@ -411,14 +420,6 @@ class TnPlan:
         return arr[:2 * self.n_steps].reshape(self.n_steps, 2)
 
     def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
-        n = self.n_inputs
-        if isinstance(input_ptrs, np.ndarray):   # int64 arrays go straight through, no per-element conversion
-            ptrs_np = np.ascontiguousarray(input_ptrs, dtype=np.int64)
-            strides_np = np.ascontiguousarray(input_strides, dtype=np.int64)
-            ptrs = ptrs_np.ctypes.data_as(C.POINTER(C.c_void_p))
-            strides = strides_np.ctypes.data_as(C.POINTER(C.c_int64))
-        else:
-            ptrs = (C.c_void_p * n)(*input_ptrs)
-            strides = (C.c_int64 * n)(*input_strides)
+        ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
         check(lib().tq_tn_contract(self.handle, ptrs, strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes,
                                    stream), "tq_tn_contract")

@@ -402,7 +402,12 @@ __device__ __forceinline__ void fused_micro(const FusedStep& f, const uint32_t* 
 }
 
 constexpr int FUSE_STAGE = 128;  // step descriptors staged in shared memory per chunk
-template <typename R, int THREADS>
+constexpr int FUSE_CLUSTER = 8;  // CTAs that share a run common to every parameter set
+// CLUSTER > 1 (runs shared by every parameter set: ONE set of steps for the whole GPU): a thread-block cluster
+// of CLUSTER CTAs works on the run together — CTA steps are dealt round-robin to the CTAs, warp steps to all
+// CLUSTER x NW warps — and the level boundary is a hardware cluster barrier (release / acquire) instead of
+// __syncthreads.  Intermediates are written once and read in a later level, in 128-byte-aligned blocks.
+template <typename R, int THREADS, int CLUSTER>
 __global__ void __launch_bounds__(THREADS)
 k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ level_off,
            const int32_t* __restrict__ level_ncta, int n_levels, const uint32_t* __restrict__ micro,
@@ -412,7 +417,9 @@ k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ leve
   __shared__ __align__(16) FusedStep sdesc[FUSE_STAGE];
   __shared__ uint32_t ktab_a[1 << FUSE_KTAB_LOG2], ktab_b[1 << FUSE_KTAB_LOG2];
   __shared__ uint32_t mtab[1 << FUSE_KTAB_LOG2], ntab[1 << FUSE_KTAB_LOG2];
-  const int64_t set = blockIdx.x;
+  uint32_t crank = 0;
+  if (CLUSTER > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int64_t set = blockIdx.x / CLUSTER;
   cx<R>* perset = perset_base + set * set_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NW = THREADS / 32, V = sizeof(FusedStep) / 16;
@@ -425,7 +432,7 @@ k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ leve
       for (int i = threadIdx.x; i < (c1 - c0) * V; i += THREADS) reinterpret_cast<uint4*>(sdesc)[i] = src[i];
       __syncthreads();
       const int ncta = max(0, min(cta_end, c1) - c0);  // cta steps come first inside a level
-      for (int i = 0; i < ncta; ++i) {
+      for (int i = (int)crank; i < ncta; i += CLUSTER) {
         const FusedStep& f = sdesc[i];
         const int n_lo = min((int)f.n_k, FUSE_KTAB_LOG2);
         for (int k = threadIdx.x; k < (1 << n_lo); k += THREADS) {
@@ -440,14 +447,18 @@ k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ leve
                             mtab, ntab);
         __syncthreads();
       }
-      for (int i = ncta + warp; i < c1 - c0; i += NW) {
+      for (int i = ncta + (int)crank * NW + warp; i < c1 - c0; i += NW * CLUSTER) {
         if (sdesc[i].micro_iters > 0)
           fused_micro<R>(sdesc[i], micro, inputs, shared, perset, set, slice, lane);
         else
           fused_exec<R, false>(sdesc[i], inputs, shared, perset, set, slice, lane, 32, 5, nullptr, nullptr, nullptr,
                                nullptr);
       }
-      __syncthreads();  // level boundary (data) and descriptor buffer reuse
+      __syncthreads();  // descriptor buffer reuse (and the level boundary when one CTA owns the run)
+    }
+    if (CLUSTER > 1) {  // level boundary across the cluster
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
   }
 }
@@ -544,7 +555,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_tn_gemm_dmma(const cx<double>* __restrict__ A, int64_t sA, const cx<double>* __restrict__ B, int64_t sB,
                cx<double>* __restrict__ C, int64_t sC, const __grid_constant__ StepDev d) {
   __shared__ double As_re[TK][DLD], As_im[TK][DLD], Bs_re[TK][DLD], Bs_im[TK][DLD];
@@ -1576,15 +1587,30 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     const bool timed = step_ms && (slice == s_begin || !p->dep_slice[first]);
     if (timed) TQ_CUDA_OK(cudaEventRecord(ev[3 * first], st));
     const int64_t sets = it.batched ? B : 1;
-    // one CTA per parameter set; a lone CTA gets 32 warps (latency-bound), many sets get 2 CTAs per SM
-    if (sets == 1)
-      k_tn_fused<R, 1024><<<1, 1024, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
-                                              p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels, p->d_micro,
-                                              table, shared, perset, p->arena_set, slice);
-    else
-      k_tn_fused<R, 512><<<(unsigned)sets, 512, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
-                                                         p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels,
-                                                         p->d_micro, table, shared, perset, p->arena_set, slice);
+    // one CTA per parameter set (2 CTAs per SM); a run shared by all sets gets a cluster of FUSE_CLUSTER CTAs
+    if (sets == 1) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(FUSE_CLUSTER);
+      cfg.blockDim = dim3(1024);
+      cfg.stream = st;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = FUSE_CLUSTER;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      TQ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tn_fused<R, 1024, FUSE_CLUSTER>, (const FusedStep*)(p->d_fsteps + it.fs_begin),
+                                    (const int32_t*)(p->d_levels + it.lv_begin),
+                                    (const int32_t*)(p->d_levels + it.lv_begin + it.n_levels + 1), it.n_levels,
+                                    (const uint32_t*)p->d_micro, (const InputRef*)table, shared, perset, p->arena_set,
+                                    slice));
+    } else {
+      k_tn_fused<R, 512, 1><<<(unsigned)sets, 512, 0, st>>>(p->d_fsteps + it.fs_begin, p->d_levels + it.lv_begin,
+                                                            p->d_levels + it.lv_begin + it.n_levels + 1, it.n_levels,
+                                                            p->d_micro, table, shared, perset, p->arena_set, slice);
+    }
     TQ_CUDA_OK(cudaGetLastError());
     if (timed) {
       TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 1], st));

@@ -262,21 +262,33 @@ class TNExecutor:
         red = self._reduced(plan_sv, dev) if self.simplify else None
         with torch.cuda.device(dev):
             red_buf = self._gather_reduced(plan_sv, gm, am, total, B, stream) if self.simplify else None
-        reductions = net.reductions or [None] * len(net.operands)
-        ptrs, strides = [], []
-        for (kind, ref), rd in zip(net.operands, reductions):
-            if kind == OPD_CAP:
-                one = isinstance(ref, tuple) and int(bits[ref[0]]) == 1
-                ptrs.append((cap1 if one else cap0).data_ptr())
-                strides.append(0)
-            elif rd is not None:
-                ptrs.append(red_buf.data_ptr() + red["off_g"][ref] * esz)
-                strides.append(red["n"] if self.gate_batched[ref] else 0)
-            else:
-                off = int(L.tq_tn_gate_offset(plan_sv.handle, ref))
-                ptrs.append(gm.data_ptr() + off * esz)
-                strides.append(total if self.gate_batched[ref] else 0)
-        any_b = any(st != 0 for st in strides)
+        # operand pointers, vectorised: table (base buffer, element offset, stride, closing-cap qubit) built once
+        tab = amp[3] if len(amp) > 3 else None
+        if tab is None:
+            reductions = net.reductions or [None] * len(net.operands)
+            base, off, stride, capq = [], [], [], []
+            for (kind, ref), rd in zip(net.operands, reductions):
+                if kind == OPD_CAP:
+                    base.append(0), off.append(0), stride.append(0)
+                    capq.append(ref[0] if isinstance(ref, tuple) else -1)
+                elif rd is not None:
+                    base.append(2), off.append(red["off_g"][ref]), capq.append(-1)
+                    stride.append(red["n"] if self.gate_batched[ref] else 0)
+                else:
+                    base.append(1), off.append(int(L.tq_tn_gate_offset(plan_sv.handle, ref))), capq.append(-1)
+                    stride.append(total if self.gate_batched[ref] else 0)
+            tab = {"base": np.asarray(base, dtype=np.int64), "off": np.asarray(off, dtype=np.int64),
+                   "stride": np.asarray(stride, dtype=np.int64), "capq": np.asarray(capq, dtype=np.int64)}
+            amp.append(tab)
+        bases = np.array([cap0.data_ptr(), gm.data_ptr(), red_buf.data_ptr() if red_buf is not None else 0],
+                         dtype=np.int64)
+        ptrs = bases[tab["base"]] + tab["off"] * esz
+        closing = tab["capq"] >= 0
+        if closing.any():
+            bit_arr = np.asarray(bits, dtype=np.int64)[tab["capq"][closing]]
+            ptrs[closing] = np.where(bit_arr == 1, cap1.data_ptr(), cap0.data_ptr())
+        strides = tab["stride"]
+        any_b = bool((strides != 0).any())
         out = torch.zeros((B if any_b else 1, 1), dtype=cd, device=dev)
         ws_bytes = plan.workspace_bytes(B)
         ws = getattr(self, "_amp_ws", None)
