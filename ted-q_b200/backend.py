@@ -16,6 +16,8 @@ Additions the reference does not have (SURVEY.md 8b "Batch"):
 """
 from __future__ import annotations
 
+import dataclasses
+
 import math
 from typing import List, Optional, Sequence
 
@@ -23,7 +25,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .ir import MEAS_STATE, CircuitIR, build_ir
+from .ir import MEAS_PROBS, MEAS_STATE, CircuitIR, MeasRec, build_ir
 
 BACKEND_NAME = "pytorch_b200"
 
@@ -438,4 +440,39 @@ class B200Backend:
 
     @property
     def states_after_measurement(self):
-        raise ValueError("no states after measurement found! please measure probs with qubits.")
+        """Post-measurement states of the last call for ``probs(qubits, after_state=True)``
+        (pytorch_backend.py:474-493, :555-560): {"01..": rescaled slice of the final state with the measured qubits
+        fixed to that outcome}.  The reference stores them as a side effect of every call; here the final state is
+        produced on demand by an auxiliary plan with a ``state()`` measurement, from the last call's parameters,
+        so that calls which never read the dictionary pay nothing."""
+        target = None
+        for ms in self._ir.meas:      # the reference keeps the dictionary of the LAST such measurement
+            if ms.kind == MEAS_PROBS and ms.after_state and ms.qubits:
+                target = ms
+        flat = getattr(self, "_last_flat", None)
+        if target is None or flat is None:
+            raise ValueError("no states after measurement found! please measure probs with qubits.")
+        if getattr(self, "_state_plan", None) is None:
+            n = self._ir.num_qubits
+            ir_state = dataclasses.replace(self._ir, meas=[MeasRec(MEAS_STATE, 0, (), shape=(2,) * n, is_complex=True)])
+            dt = capi.TQ_C64 if self._cdtype == torch.complex64 else capi.TQ_C128
+            self._state_plan = capi.Plan(ir_state, dt, self._plan_opts)
+        plan = self._state_plan
+        flat = flat[:1].detach().contiguous()
+        out = torch.empty((1, plan.out_reals), dtype=self._rdtype, device=flat.device)
+        ws_bytes = plan.workspace_bytes(1, False)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=flat.device)
+        with torch.cuda.device(flat.device):
+            plan.forward(flat.data_ptr(), 1, out.data_ptr(), ws.data_ptr(), ws_bytes, False,
+                         torch.cuda.current_stream(flat.device).cuda_stream)
+        n = self._ir.num_qubits
+        state = torch.view_as_complex(out.reshape((2,) * n + (2,)))
+        qs = list(target.qubits)
+        res = {}
+        for i in range(2 ** len(qs)):
+            outcome = [int(c) for c in bin(i)[2:].zfill(len(qs))]            # dec_to_bin, tools/helpers.py:22-40
+            loc = dict(zip(qs, outcome))
+            part = state[tuple(loc.get(ix, slice(None)) for ix in range(n))]
+            scale = torch.sqrt(torch.sum(torch.abs(part) ** 2))             # rescale_state, tools/helpers.py:43-51
+            res["".join(str(b) for b in outcome)] = [s / scale for s in part]
+        return res

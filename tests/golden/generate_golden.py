@@ -174,6 +174,22 @@ def main():
         json.dump(tn, fh, ensure_ascii=True)
     print("tn maps:", len(tn))
 
+    # 6. post-measurement states: probs(qubits, after_state=True), pytorch_backend.py:474-493 (the reference's
+    #    probs() helper drops the flag, measurement.py:206, so it is set on the returned object)
+    def after_def(a, b, c):
+        qai.RX(a, qubits=[0]); qai.RY(b, qubits=[1]); qai.CNOT(qubits=[0, 2]); qai.RZ(c, qubits=[2])
+        qai.Hadamard(qubits=[1]); qai.CNOT(qubits=[1, 2])
+        m = qai.measurement.probs(qubits=[0, 2])
+        m.after_state = True
+        return m
+    pa = [torch.tensor(0.54), torch.tensor(0.12), torch.tensor(-0.8)]
+    cc = qai.Circuit(after_def, 3, *pa).compilecircuit(backend="pytorch")
+    y = cc(*pa)
+    states = {k: [[float(x.real), float(x.imag)] for x in torch.stack(v).reshape(-1)]
+              for k, v in cc.states_after_measurement.items()}
+    with open(os.path.join(HERE, "after_state.json"), "w") as fh:
+        json.dump({"params": [0.54, 0.12, -0.8], "probs": y.detach().numpy().tolist(), "states": states}, fh)
+
 
 W_GATES = ["I", "Hadamard", "PauliX", "PauliY", "PauliZ", "S", "T", "SX", "CNOT", "CZ", "CY", "SWAP", "CSWAP", "Toffoli",
            "RX", "RY", "RZ", "Rot", "PhaseShift", "ControlledPhaseShift", "CRX", "CRY", "CRZ"]

@@ -174,3 +174,30 @@ def test_user_initial_state():
     got = cc(torch.tensor([0.3], device="cuda")).cpu().numpy()
     ref = sv_ref.run_sv(circ, torch.tensor([0.3])).numpy()
     assert_close(got, ref, 1e-6, "state")
+
+
+def test_states_after_measurement_match_reference():
+    """probs(qubits, after_state=True): the post-measurement state dictionary of pytorch_backend.py:474-493
+    (golden produced by the unmodified reference, tests/golden/after_state.json)."""
+    g = load_golden("after_state.json")
+
+    def circuit_def(a, b, c):
+        qb.RX(a, qubits=[0]); qb.RY(b, qubits=[1]); qb.CNOT(qubits=[0, 2]); qb.RZ(c, qubits=[2])
+        qb.Hadamard(qubits=[1]); qb.CNOT(qubits=[1, 2])
+        getattr(qb, "measurement", qb).probs(qubits=[0, 2], after_state=True)
+
+    pa = [torch.tensor(v) for v in g["params"]]
+    cc = qb.Circuit(circuit_def, 3, *pa).compilecircuit(backend="pytorch_b200")
+    y = cc(*[p.cuda() for p in pa])
+    assert_close(y.cpu().numpy(), np.asarray(g["probs"]), 1e-6, "probs")
+    got = cc.states_after_measurement
+    assert sorted(got) == sorted(g["states"])
+    for key, ref in g["states"].items():
+        ref = np.asarray(ref)
+        arr = torch.stack(got[key]).reshape(-1).cpu().numpy()
+        assert_close(arr, ref[:, 0] + 1j * ref[:, 1], 1e-6, "state after " + key)
+    plain = qb.Circuit(lambda a: (qb.RX(a, qubits=[0]), getattr(qb, "measurement", qb).probs(qubits=[0])), 1, pa[0]).compilecircuit(
+        backend="pytorch_b200")
+    plain(pa[0].cuda())
+    with pytest.raises(ValueError):
+        plain.states_after_measurement
