@@ -395,7 +395,7 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
         t_by = byts / (hbm_peak * 1e9)
         roof_ms = max(t_fl, t_by) * 1e3
         table.append({"M": 2 ** r["m"], "N": 2 ** r["n"], "K": 2 ** r["k"], "batch": 2 ** r["b"],
-                      "kernel": ["k_tn_step", "k_tn_gemm", "k_tc_pack+k_tc_gemm", "k_tn_dot"][r["kernel"]],
+                      "kernel": ["k_tn_step", "k_tn_gemm", "k_tc_pack+k_tc_gemm", "k_tn_dot", "k_tn_fused", "k_tn_apply"][r["kernel"]],
                       "ms": round(r["ms"], 4), "pack_ms": round(r["pack_ms"], 4),
                       "algorithmic_tflops": round(fl / (r["ms"] * 1e-3) / 1e12, 2),
                       "bound": "tensor" if t_fl > t_by else "hbm", "roofline_ms": round(roof_ms, 4),

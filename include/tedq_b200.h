@@ -241,7 +241,7 @@ enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_
 int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
 /* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,
  * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096),
- * 4 = member of a fused run of small steps */
+ * 4 = member of a fused run of small steps, 5 = apply kernel (one gate-sized operand, one large operand) */
 int32_t tq_tn_plan_step_kernel(const tq_tn_plan* plan, int32_t s);
 /* bit 0: step s repeats for every slice (it depends on a sliced index); bit 1: it carries the parameter-set
  * batch dimension.  Steps with neither bit run once per call, outside the slice loop. */

@@ -199,6 +199,63 @@ k_tn_step(const cx<R>* __restrict__ A, int64_t sA, const cx<R>* __restrict__ B, 
   C[set * sC + o] = acc;
 }
 
+// "Apply" kernel: one operand is gate-sized (<= 4 free indices, <= 4 contracted), the other is large — the shape
+// of every step of a state-vector-like plan and of the mid-size steps between the fused runs and the GEMMs.  One
+// thread per (large free index value f, kept-shared value bb): it loads the 2^k entries of the large operand it
+// needs ONCE, keeps them in registers, and produces all 2^s outputs; the small operand sits in shared memory in
+// [bb][s][k] order.  Traffic: the large operand read once, the result written once.
+constexpr int APPLY_MAX = 4;  // log2 of the largest small-operand extents handled (k and s each)
+struct ApplyDev {
+  int32_t n_k, n_s, n_f, n_b;
+  int32_t s_shift, f_shift;  // result element = bb << (n_s + n_f) | s << s_shift | f << f_shift
+  int8_t small_k[APPLY_MAX], small_s[APPLY_MAX], small_b[8];
+  int8_t big_k[APPLY_MAX], big_f[TQ_TN_MAX_RANK], big_b[8];
+};
+template <typename R, int KMAX, int SMAX>
+__global__ void __launch_bounds__(256)
+k_tn_apply(const cx<R>* __restrict__ S, int64_t sS, const cx<R>* __restrict__ T, int64_t sT, cx<R>* __restrict__ C,
+           int64_t sC, const __grid_constant__ ApplyDev d, int64_t n_threads) {
+  __shared__ cx<R> small[1 << (2 * APPLY_MAX + 2)];  // [bb' ][s][k], bb' = low 2 kept-shared bits at most staged
+  const int64_t set = blockIdx.y;
+  const int K = 1 << d.n_k, Sn = 1 << d.n_s;
+  const int nb_st = min(d.n_b, 2);  // kept-shared bits resolved through the staged copy
+  const cx<R>* sp = S + set * sS;
+  for (int i = threadIdx.x; i < (1 << (d.n_k + d.n_s + nb_st)); i += 256) {
+    const uint32_t k = i & (K - 1), sv = (i >> d.n_k) & (Sn - 1), bl = i >> (d.n_k + d.n_s);
+    small[i] = sp[scat(k, d.small_k, d.n_k) | scat(sv, d.small_s, d.n_s) | scat(bl, d.small_b, nb_st)];
+  }
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n_threads) return;
+  const uint32_t f = (uint32_t)(t & (((int64_t)1 << d.n_f) - 1)), bb = (uint32_t)(t >> d.n_f);
+  const cx<R>* tp = T + set * sT + (scat(f, d.big_f, d.n_f) | scat(bb, d.big_b, d.n_b));
+  cx<R> v[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) v[k] = tp[scat((uint32_t)k, d.big_k, d.n_k)];
+  // kept-shared bits beyond the staged two select a different small tensor: read it from global memory
+  const uint32_t b_lo = bb & ((1u << nb_st) - 1u), b_hi = bb >> nb_st;
+  const cx<R>* sm = small + ((int64_t)b_lo << (d.n_k + d.n_s));
+  const cx<R>* sg = sp + scat(b_hi, d.small_b + nb_st, d.n_b - nb_st);
+  cx<R>* cp = C + set * sC + ((int64_t)bb << (d.n_s + d.n_f)) + ((int64_t)f << d.f_shift);
+#pragma unroll
+  for (int sv = 0; sv < SMAX; ++sv) {
+    if (sv < Sn) {
+      cx<R> acc = mk<R>(0, 0);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+          const cx<R> a = d.n_b > nb_st
+                              ? sg[scat((uint32_t)k, d.small_k, d.n_k) | scat((uint32_t)sv, d.small_s, d.n_s) |
+                                   scat(b_lo, d.small_b, nb_st)]
+                              : sm[(sv << d.n_k) | k];
+          acc = cfma(a, v[k], acc);
+        }
+      cp[(int64_t)sv << d.s_shift] = acc;
+    }
+  }
+}
+
 // Split-K reduction for steps with a handful of output elements and a long contracted extent (the closing
 // steps of an amplitude network: a 2^21-term dot product).  Block (x, o, set) reduces K range x of output
 // element o into partial[set][o][x]; k_tn_dot_sum adds the partials in a fixed order (deterministic).
@@ -680,7 +737,7 @@ __global__ void k_tn_final(const cx<R>* __restrict__ last, int64_t sL, cx<R>* __
 
 constexpr int DOT_MAX_OUT_LOG2 = 6, DOT_MIN_K_LOG2 = 12, DOT_BLOCKS = 128;
 // a step joins a fused run when k+m+n+b <= this (one CTA per parameter set does the whole step)
-constexpr int FUSE_MAX_WORK_BATCHED = 18, FUSE_MAX_WORK_SHARED = 14, FUSE_CTA_WORK = 8;
+constexpr int FUSE_MAX_WORK_BATCHED = 18, FUSE_MAX_WORK_SHARED = 14, FUSE_CTA_WORK = 8, FUSE_MAX_OUT_LOG2 = 12;
 
 struct SchedItem {
   int step = -1;                       // >= 0: one step on its own kernel(s)
@@ -749,6 +806,8 @@ struct tq_tn_plan {
   std::vector<SchedItem> items[2];  // phase 0: once per call; phase 1: every slice
   std::vector<char> t_slice;        // per tensor id: depends on a sliced index
   std::vector<int> t_rank;
+  std::vector<ApplyDev> apply;      // per step (kind 5 only)
+  std::vector<char> apply_small_rhs;
   FusedStep* d_fsteps = nullptr;
   uint32_t* d_micro = nullptr;      // offset tables of the micro steps
   int32_t* d_levels = nullptr;      // [level_off (n+1 per run) | level_ncta] blocks, see SchedItem
@@ -769,6 +828,8 @@ static int build_schedule(tq_tn_plan* p) {
   std::vector<int> in_slice_bits(n_in, 0);
   for (int t : p->slice_tensor) in_slice_bits[t]++;
   p->kind.assign(n_steps, 0);
+  p->apply.resize(n_steps);
+  p->apply_small_rhs.assign(n_steps, 0);
   for (int s = 0; s < n_steps; ++s) {
     const tq_tn_step& st = p->steps[s];
     const int work = st.n_k + st.n_m + st.n_n + st.n_b, outl = st.n_m + st.n_n + st.n_b;
@@ -776,10 +837,38 @@ static int build_schedule(tq_tn_plan* p) {
     auto opnd_ok = [&](int t, int rank) {
       return rank <= FUSE_MAX_RANK && (t >= n_in || in_slice_bits[t] <= FUSE_MAX_SLICE_BITS);
     };
+    // fused: little work AND a small result (a 2^16-element state update is a whole-GPU job, not one CTA's)
     const bool small = p->fuse_enabled && work <= (p->dep_batch[s] ? FUSE_MAX_WORK_BATCHED : FUSE_MAX_WORK_SHARED) &&
+                       outl <= FUSE_MAX_OUT_LOG2 &&
                        opnd_ok(st.lhs, st.n_k + st.n_m + st.n_b) && opnd_ok(st.rhs, st.n_k + st.n_n + st.n_b);
+    const bool lhs_small = st.n_m <= APPLY_MAX && st.n_k <= APPLY_MAX, rhs_small = st.n_n <= APPLY_MAX && st.n_k <= APPLY_MAX;
+    const bool apply_ok = (lhs_small || rhs_small) && outl >= 10 && st.n_b <= 8;
     p->kind[s] = tc_ok ? 2 : small ? 4 : (outl <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2) ? 3
-                 : (st.n_m >= 6 && st.n_n >= 6 && st.n_k >= 4) ? 1 : 0;
+                 : (st.n_m >= 6 && st.n_n >= 6 && st.n_k >= 4) ? 1 : apply_ok ? 5 : 0;
+    if (p->kind[s] == 5) {
+      const bool small_rhs = !lhs_small || (rhs_small && st.n_n < st.n_m);
+      ApplyDev& a = p->apply[s];
+      memset(&a, 0, sizeof(a));
+      p->apply_small_rhs[s] = small_rhs;
+      const int8_t* sb = small_rhs ? st.rhs_bits : st.lhs_bits;
+      const int8_t* bbits = small_rhs ? st.lhs_bits : st.rhs_bits;
+      a.n_k = st.n_k;
+      a.n_b = st.n_b;
+      a.n_s = small_rhs ? st.n_n : st.n_m;
+      a.n_f = small_rhs ? st.n_m : st.n_n;
+      a.s_shift = small_rhs ? 0 : st.n_n;
+      a.f_shift = small_rhs ? st.n_n : 0;
+      for (int j = 0; j < st.n_k; ++j) {
+        a.small_k[j] = sb[j];
+        a.big_k[j] = bbits[j];
+      }
+      for (int j = 0; j < a.n_s; ++j) a.small_s[j] = sb[st.n_k + j];
+      for (int j = 0; j < a.n_f; ++j) a.big_f[j] = bbits[st.n_k + j];
+      for (int j = 0; j < st.n_b; ++j) {
+        a.small_b[j] = sb[st.n_k + a.n_s + j];
+        a.big_b[j] = bbits[st.n_k + a.n_f + j];
+      }
+    }
   }
   // ---- execution order
   std::vector<char> done(n_in + n_steps, 0);
@@ -1552,6 +1641,29 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
                              timed ? ev[3 * s + 1] : nullptr);
         if (rc) return rc;
       }
+    } else if (kernel == 5) {
+      const ApplyDev& ad = p->apply[s];
+      const bool srhs = p->apply_small_rhs[s] != 0;
+      const cx<R>* sm = srhs ? b : a;
+      const cx<R>* bg = srhs ? a : b;
+      const int64_t ssm = srhs ? sb : sa, sbg = srhs ? sa : sb;
+      const int64_t nthr = (int64_t)1 << (ad.n_f + ad.n_b);
+      const dim3 grid((unsigned)((nthr + 255) / 256), (unsigned)sets);
+      TQ_REQUIRE(sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");
+      const int kc = ad.n_k <= 1 ? 0 : ad.n_k <= 2 ? 1 : 2, sc2 = ad.n_s <= 1 ? 0 : ad.n_s <= 2 ? 1 : 2;
+#define TQ_APPLY(KM, SM) k_tn_apply<R, KM, SM><<<grid, 256, 0, st>>>(sm, ssm, bg, sbg, c, sc, ad, nthr)
+      switch (kc * 3 + sc2) {
+        case 0: TQ_APPLY(2, 2); break;
+        case 1: TQ_APPLY(2, 4); break;
+        case 2: TQ_APPLY(2, 16); break;
+        case 3: TQ_APPLY(4, 2); break;
+        case 4: TQ_APPLY(4, 4); break;
+        case 5: TQ_APPLY(4, 16); break;
+        case 6: TQ_APPLY(16, 2); break;
+        case 7: TQ_APPLY(16, 4); break;
+        default: TQ_APPLY(16, 16); break;
+      }
+#undef TQ_APPLY
     } else if (kernel == 3) {
       const int nblk = std::min(DOT_BLOCKS, 1 << (stp.n_k - DOT_LO));
       TQ_REQUIRE(sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");

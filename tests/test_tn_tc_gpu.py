@@ -155,3 +155,33 @@ def test_complex128_gemm_steps_on_fp64_tensor_cores(shape, shuffle):
     got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, c128=True)
     assert kinds == [1], kinds
     assert np.abs(got.reshape(-1) - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 2, 0), (13, 1, 1, 0), (3, 10, 4, 1), (1, 14, 3, 3), (4, 11, 4, 0),
+                                   (13, 4, 2, 0), (2, 9, 1, 4), (0, 12, 3, 0), (3, 12, 0, 0)],
+                         ids=lambda s: "m%d_n%d_k%d_b%d" % s)
+@pytest.mark.parametrize("c128", [False, True], ids=["c64", "c128"])
+def test_apply_kernel_small_times_large(shape, c128):
+    """Gate-sized operand times a large operand (k_tn_apply): either side small, kept-shared indices, both dtypes."""
+    n_m, n_n, n_k, n_b = shape
+    rng = np.random.RandomState(sum(shape) * 13 + n_m)
+    a_idx, b_idx, o_idx = _case(rng, n_m, n_n, n_k, n_b, True)
+    A = (rng.standard_normal((2,) * len(a_idx)) + 1j * rng.standard_normal((2,) * len(a_idx)))
+    B = (rng.standard_normal((2,) * len(b_idx)) + 1j * rng.standard_normal((2,) * len(b_idx)))
+    ref = _einsum(a_idx, b_idx, o_idx, A, B).reshape(-1)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], False, min_log2=20, c128=c128)
+    assert kinds == [5], kinds
+    tol = 1e-11 if c128 else 1e-5
+    assert np.abs(got.reshape(-1) - ref).max() <= tol * np.abs(ref).max()
+
+
+def test_apply_kernel_batched_sets():
+    rng = np.random.RandomState(77)
+    a_idx, b_idx, o_idx = _case(rng, 2, 13, 2, 1, True)
+    n_sets = 4
+    A = (rng.standard_normal((n_sets,) + (2,) * len(a_idx)) + 1j * rng.standard_normal((n_sets,) + (2,) * len(a_idx)))
+    B = (rng.standard_normal((n_sets,) + (2,) * len(b_idx)) + 1j * rng.standard_normal((n_sets,) + (2,) * len(b_idx)))
+    ref = _einsum(a_idx, b_idx, o_idx, A, B, True, True).reshape(n_sets, -1)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [True, True], False, B=n_sets, min_log2=20)
+    assert kinds == [5]
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
