@@ -28,7 +28,7 @@ bits = [0] * 40
 flat = torch.zeros((1, 0), device="cuda")
 amp = cc.amplitude(bits)
 torch.cuda.synchronize()
-net, info, plan = cc._tn._amplitude_plan()
+net, info, plan = cc._tn._amplitude_plan()[:3]
 print(info, "flops/slice %.3e" % plan.flops, "slices", plan.n_slices, "width", plan.width, "steps", plan.n_steps)
 for _ in range(2):
     torch.cuda.synchronize()

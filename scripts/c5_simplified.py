@@ -14,7 +14,7 @@ cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=True,
 bits = [0] * 40
 amp = cc.amplitude(bits); torch.cuda.synchronize()
 print("compile+first %.2fs" % (time.time() - t))
-net, info, plan = cc._tn._amplitude_plan()
+net, info, plan = cc._tn._amplitude_plan()[:3]
 kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
 print(info, "flops %.3e" % (plan.flops * plan.n_slices), {k: kinds.count(k) for k in sorted(set(kinds))})
 for _ in range(3):

@@ -1472,7 +1472,7 @@ static int tc_setup_once() {
                                   tc::SMEM_BUDGET + 1024));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   tc::SMEM_BUDGET + 1024));
-  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_pack<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_pack<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   done = 1;
   return TQ_OK;
 }
@@ -1489,21 +1489,29 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   const TcStep& T = p->tc[s];
   const int64_t nz = sets << stp.n_b;
   TQ_REQUIRE(nz < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step %d has %lld batched GEMMs", s, (long long)nz);
-  if (pack_a) {
-    tc::PackParams pa = T.pa;
-    pa.src = reinterpret_cast<const float2*>(T.swap ? b : a);
-    pa.src_set_stride = T.swap ? sb : sa;
-    pa.img = img_a;
-    pa.img_z_stride = T.img_a_z;
-    tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_a * T.kblocks), (unsigned)nz), 256, tc::A_CHUNK, st>>>(pa);
-  }
-  if (pack_b) {
-    tc::PackParams pb = T.pb;
-    pb.src = reinterpret_cast<const float2*>(T.swap ? a : b);
-    pb.src_set_stride = T.swap ? sa : sb;
-    pb.img = img_b;
-    pb.img_z_stride = T.img_b_z;
-    tc::k_tc_pack<256><<<dim3((unsigned)(T.tiles_b * T.kblocks), (unsigned)nz), 256, tc::b_chunk_bytes(T.c_t), st>>>(pb);
+  if (pack_a || pack_b) {
+    tc::PackPair pp;
+    memset(&pp, 0, sizeof(pp));
+    size_t smem = 0;
+    if (pack_a) {
+      pp.a = T.pa;
+      pp.a.src = reinterpret_cast<const float2*>(T.swap ? b : a);
+      pp.a.src_set_stride = T.swap ? sb : sa;
+      pp.a.img = img_a;
+      pp.a.img_z_stride = T.img_a_z;
+      pp.blocks_a = tc::pack_blocks(T.tiles_a, T.kblocks);
+      smem = 2 * (size_t)tc::A_CHUNK;
+    }
+    if (pack_b) {
+      pp.b = T.pb;
+      pp.b.src = reinterpret_cast<const float2*>(T.swap ? a : b);
+      pp.b.src_set_stride = T.swap ? sa : sb;
+      pp.b.img = img_b;
+      pp.b.img_z_stride = T.img_b_z;
+      pp.blocks_b = tc::pack_blocks(T.tiles_b, T.kblocks);
+      smem = std::max(smem, 2 * (size_t)tc::b_chunk_bytes(T.c_t));
+    }
+    tc::k_tc_pack<256><<<dim3((unsigned)(pp.blocks_a + pp.blocks_b), (unsigned)nz), 256, smem, st>>>(pp);
   }
   TQ_CUDA_OK(cudaGetLastError());
   if (ev_packed) TQ_CUDA_OK(cudaEventRecord(ev_packed, st));

@@ -145,31 +145,44 @@ struct PackParams {
   int16_t local_dst[16];    // its value in (r << 4 | kk)
 };
 
+// Both operands of a step are packed by ONE launch (blocks [0, blocks_a) take operand A, the rest operand B; either
+// count may be zero when that image is pinned).  A block packs PACK_NCH consecutive k-blocks of one row tile, so
+// that the per-block address set-up is paid once per 8 chunks; chunks alternate between two shared-memory buffers
+// and leave through the bulk-copy engine while the next one is being gathered.
+constexpr int PACK_NCH = 8;
+struct PackPair {
+  PackParams a, b;
+  int32_t blocks_a, blocks_b;
+};
+inline int pack_blocks(int tiles, int kblocks) { return tiles * ((kblocks + PACK_NCH - 1) / PACK_NCH); }
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_tc_pack(const __grid_constant__ PackParams p) {
+k_tc_pack(const __grid_constant__ PackPair pp) {
   static_assert(THREADS == 256, "element = tid + 256 * i");
   extern __shared__ __align__(128) uint8_t pk_smem[];
+  const bool second = (int)blockIdx.x >= pp.blocks_a;
+  const PackParams& p = second ? pp.b : pp.a;
   const int tid = threadIdx.x;
   const int rows_t = 1 << p.rows_t_log2;
   const int plane = p.is_b ? b_plane_bytes(rows_t) : A_PLANE;
   const int chunk = 2 * plane;
-  uint32_t blk = blockIdx.x;
-  const uint32_t kb = blk % (uint32_t)p.kblocks;
-  const uint32_t tile = blk / (uint32_t)p.kblocks;
+  const uint32_t blk = blockIdx.x - (second ? (uint32_t)pp.blocks_a : 0u);
+  const uint32_t groups = ((uint32_t)p.kblocks + PACK_NCH - 1) / PACK_NCH;
+  const uint32_t kb0 = (blk % groups) * PACK_NCH;
+  const uint32_t tile = blk / groups;
+  const int nch = min(PACK_NCH, p.kblocks - (int)kb0);
   const uint32_t z = blockIdx.y;
   const uint32_t bb = z & ((1u << p.n_b) - 1u);
   const uint32_t set = z >> p.n_b;
-  // base source offset of this (set, bb, tile, kb)
+  // base source offset of this (set, bb, tile)
   int64_t base = (int64_t)set * p.src_set_stride;
   for (int j = 0; j < p.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << p.b_bits[j];
   for (int j = p.rows_t_log2; j < p.n_row; ++j) base |= (int64_t)((tile >> (j - p.rows_t_log2)) & 1u) << p.row_bits[j];
-  for (int j = KB_LOG; j < p.n_k; ++j) base |= (int64_t)((kb >> (j - KB_LOG)) & 1u) << p.k_bits[j];
-  if (p.n_k < KB_LOG) {  // K padded to one k-block: the missing columns are zero
+  if (p.n_k < KB_LOG) {  // K padded to one k-block: the missing columns are zero (nch == 1)
     for (int i = tid; i < chunk / 16; i += THREADS) reinterpret_cast<float4*>(pk_smem)[i] = make_float4(0, 0, 0, 0);
     __syncthreads();
   }
-  const float2* src = p.src + base;
   // element e = tid + 256 i: bits 0..7 come from tid (resolved once), bits 8.. from i.  Local bits are sorted by
   // source position, so consecutive threads read ascending source addresses.
   uint32_t so_t = 0, d_t = 0;
@@ -181,54 +194,63 @@ k_tc_pack(const __grid_constant__ PackParams p) {
     }
   const int iters = p.n_local > 8 ? 1 << (p.n_local - 8) : 1;
   const bool active = p.n_local >= 8 || tid < (1 << p.n_local);
-  float2 v[8];
-  uint32_t dd[8];
+  uint32_t so_i[8], d_i[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (i < iters && active) {
-      uint32_t so = so_t, d = d_t;
+    uint32_t so = so_t, d = d_t;
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        if (8 + j < p.n_local && ((i >> j) & 1)) {
-          so |= 1u << p.local_src[8 + j];
-          d |= (uint32_t)p.local_dst[8 + j];
-        }
-      v[i] = __ldg(src + so);
-      dd[i] = d;
-    }
+    for (int j = 0; j < 3; ++j)
+      if (8 + j < p.n_local && ((i >> j) & 1)) {
+        so |= 1u << p.local_src[8 + j];
+        d |= (uint32_t)p.local_dst[8 + j];
+      }
+    so_i[i] = so;
+    const uint32_t r = d >> 4, kk = d & 15u;
+    d_i[i] = r * ROW_BYTES + ((((kk >> 1) ^ swz(r)) << 4) | ((kk & 1u) << 3));  // byte offset inside a plane
   }
+  uint8_t* img = p.img + (int64_t)z * p.img_z_stride + ((int64_t)tile * p.kblocks + kb0) * (int64_t)chunk;
+  for (int c = 0; c < nch; ++c) {
+    const uint32_t kb = kb0 + (uint32_t)c;
+    int64_t kbase = 0;
+    for (int j = KB_LOG; j < p.n_k; ++j) kbase |= (int64_t)((kb >> (j - KB_LOG)) & 1u) << p.k_bits[j];
+    const float2* src = p.src + base + kbase;
+    uint8_t* buf = pk_smem + (c & 1) * chunk;
+    if (c >= 2) {  // the store issued two chunks ago must have finished reading this buffer
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+    }
+    float2 v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i < iters && active) {
-      const uint32_t r = dd[i] >> 4, kk = dd[i] & 15u;
-      const float hr = to_tf32(v[i].x), hi = to_tf32(v[i].y);
-      const float lr = to_tf32(v[i].x - hr), li = to_tf32(v[i].y - hi);
-      const uint32_t in_row = ((((kk >> 1) ^ swz(r)) << 4) | ((kk & 1u) << 3));
-      if (!p.is_b) {
-        const uint32_t o = r * ROW_BYTES + in_row;
-        *reinterpret_cast<float2*>(pk_smem + o) = make_float2(hr, hi);
-        *reinterpret_cast<float2*>(pk_smem + plane + o) = make_float2(lr, li);
-      } else {
-        const uint32_t o_re = r * ROW_BYTES + in_row;             // -> Re C
-        const uint32_t o_im = (rows_t + r) * ROW_BYTES + in_row;  // -> Im C  (swz(rows_t + r) == swz(r))
-        *reinterpret_cast<float2*>(pk_smem + o_re) = make_float2(hr, -hi);
-        *reinterpret_cast<float2*>(pk_smem + o_im) = make_float2(hi, hr);
-        *reinterpret_cast<float2*>(pk_smem + plane + o_re) = make_float2(lr, -li);
-        *reinterpret_cast<float2*>(pk_smem + plane + o_im) = make_float2(li, lr);
+    for (int i = 0; i < 8; ++i)
+      if (i < iters && active) v[i] = __ldg(src + so_i[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < iters && active) {
+        const float hr = to_tf32(v[i].x), hi = to_tf32(v[i].y);
+        const float lr = to_tf32(v[i].x - hr), li = to_tf32(v[i].y - hi);
+        if (!p.is_b) {
+          *reinterpret_cast<float2*>(buf + d_i[i]) = make_float2(hr, hi);
+          *reinterpret_cast<float2*>(buf + plane + d_i[i]) = make_float2(lr, li);
+        } else {
+          const uint32_t o_im = d_i[i] + (uint32_t)rows_t * ROW_BYTES;  // -> Im C  (swz(rows_t + r) == swz(r))
+          *reinterpret_cast<float2*>(buf + d_i[i]) = make_float2(hr, -hi);
+          *reinterpret_cast<float2*>(buf + o_im) = make_float2(hi, hr);
+          *reinterpret_cast<float2*>(buf + plane + d_i[i]) = make_float2(lr, -li);
+          *reinterpret_cast<float2*>(buf + plane + o_im) = make_float2(li, lr);
+        }
       }
     }
+    // the finished chunk leaves through the bulk-copy engine: one contiguous store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(img + (int64_t)c * chunk),
+                   "r"(smem_u32(buf)), "r"((uint32_t)chunk)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
   }
-  // the finished chunk leaves through the bulk-copy engine: one contiguous store per block
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (tid == 0) {
-    uint8_t* dst = p.img + (int64_t)z * p.img_z_stride + ((int64_t)tile * p.kblocks + kb) * (int64_t)chunk;
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(pk_smem)),
-                 "r"((uint32_t)chunk)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
