@@ -5,7 +5,10 @@ The hot path shards in two natural ways:
     outputs are all-gathered only when the caller wants the full batch on every rank
     (reference analogue: QUDIOBackend's DataParallel scatter/cat, qudio_backend.py:86-102);
   * sliced contraction indices — every rank contracts a contiguous range of slices and the partial sums are
-    combined with ONE all-reduce (reference analogue: jdtensorpath RPC slice workers, examples/qubit_rpc.py:110-126).
+    combined with ONE all-reduce (reference analogue: jdtensorpath RPC slice workers, examples/qubit_rpc.py:110-126);
+  * measurements in tensor-network mode — one network per measurement (tensor_network.py:940-1097): rank r
+    contracts networks r, r + W, r + 2W, ... and the rows are combined with ONE all-reduce of the (zero-filled)
+    result tensor.
 A single state vector is never split across GPUs.
 """
 from __future__ import annotations
@@ -58,3 +61,18 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if world()[1] > 1:
         dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t)
     return t
+
+
+def my_measurements(n_meas: int):
+    """Measurement (network) ids this rank contracts: round-robin over ranks."""
+    rank, ws = world()
+    return list(range(rank, n_meas, ws))
+
+
+def combine_measurements(rows: dict, n_meas: int, like: torch.Tensor) -> torch.Tensor:
+    """rows: {measurement id: tensor [B, ...]} computed on this rank -> [B, n_meas, ...] on every rank.
+    Missing rows are zero on this rank; ONE all-reduce(sum) fills them in."""
+    out = torch.zeros((like.shape[0], n_meas) + tuple(like.shape[1:]), dtype=like.dtype, device=like.device)
+    for i, r in rows.items():
+        out[:, i] = r
+    return allreduce_sum_(out)

@@ -42,6 +42,8 @@ class TNExecutor:
         self.plans: List[Optional[capi.TnPlan]] = []
         so = self.ho.get("slicing_opts") or {}
         self.contract_parallel = bool(so.get("contract_parallel", False))
+        # hyper_opt["measurement_parallel"]: networks (one per measurement) are dealt round-robin to the ranks
+        self.measurement_parallel = bool(self.ho.get("measurement_parallel", False))
         ext = backend._use_jdopttn or backend._use_cotengra
         for net in self.networks:
             info = None
@@ -184,7 +186,14 @@ class TNExecutor:
         with torch.cuda.device(dev):
             red_buf = self._gather_reduced(plan_sv, gm, am, total, B, stream) if self.simplify else None
         results = []
+        mine = None
+        if self.measurement_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
+            from . import dist as tqd
+            mine = set(tqd.my_measurements(len(self.networks)))
         for i, net in enumerate(self.networks):
+            if mine is not None and i not in mine:
+                results.append(None)
+                continue
             plan = self._plan(i)
             # operand pointers = base[kind] + offset * element size: vectorised, tables built once per network
             self._table_device = dev
@@ -346,12 +355,23 @@ class TNExecutor:
         res = []
         B = flat.shape[0]
         for ms, v, net in zip(be._ir.meas, vals, self.networks):
+            if v is None:      # another rank's measurement (measurement_parallel)
+                res.append(None)
+                continue
             # the network's open legs define the result shape (probs() with qubits=None contracts to a scalar
             # in the reference's TN branch: tensor_network.py:1017-1019 leaves the output empty)
             v = v.reshape((B,) + (2,) * len(net.output))
             res.append(v if ms.is_complex else v.real)   # torch.squeeze(result.real), pytorch_backend.py:340,:348
         if not be._shapes_ok:
             raise ValueError("You can not have multiple measurements with different shapes!!")
+        if any(r is None for r in res):
+            from . import dist as tqd
+            like = next((r for r in res if r is not None), None)
+            if like is None:   # more ranks than measurements: this rank only joins the all-reduce
+                ms0, net0 = be._ir.meas[0], self.networks[0]
+                like = torch.zeros((B,) + (2,) * len(net0.output), device=flat.device,
+                                   dtype=be._cdtype if ms0.is_complex else be._rdtype)
+            return tqd.combine_measurements({i: r for i, r in enumerate(res) if r is not None}, len(res), like)
         return torch.stack(res, 1)
 
 

@@ -46,7 +46,12 @@ def _worker(rank, world_size, port, ret):
         rows = list(range(*tqd.shard_range(11, rank, world_size)))
         gathered = [None] * world_size
         dist.all_gather_object(gathered, rows)
-        ret[rank] = (complex(t[0]), full, gathered, info.n_slices)
+        # measurements dealt round-robin, combined with one all-reduce (TN mode: one network per measurement)
+        n_meas = 5
+        mine = tqd.my_measurements(n_meas)
+        truth = torch.arange(3 * n_meas * 2, dtype=torch.float64).reshape(3, n_meas, 2)
+        combined = tqd.combine_measurements({i: truth[:, i] for i in mine}, n_meas, truth[:, 0])
+        ret[rank] = (complex(t[0]), full, gathered, info.n_slices, mine, bool(torch.equal(combined, truth)))
     finally:
         dist.destroy_process_group()
 
@@ -57,7 +62,8 @@ def test_slice_sharding_and_allreduce_world2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     for rank in range(2):
-        total, full, gathered, n_slices = ret[rank]
+        total, full, gathered, n_slices, mine, combined_ok = ret[rank]
         assert n_slices >= 8
         assert abs(total - full) < 1e-12
         assert sorted(x for part in gathered for x in part) == list(range(11))
+        assert mine == list(range(rank, 5, 2)) and combined_ok
