@@ -6,5 +6,6 @@ from .backend import BACKEND_NAME, B200Backend, B200Execute, B200ParamShift  # n
 from .frontend import *  # noqa: F401,F403
 from .frontend import Circuit  # noqa: F401
 from .register import register_backend  # noqa: F401
+from .tree_compat import B200OptTN, ctg_compat  # noqa: F401
 
 __version__ = "0.1.0"

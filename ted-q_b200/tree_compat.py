@@ -1,0 +1,110 @@
+"""Second drop-in boundary: the planner / contraction-tree plug-in the reference already has.
+
+``PyTorchBackend`` hands every network to a third-party tree object and calls
+``tree.contract(arrays, backend='torch')`` (pytorch_backend.py:276, :339); the tree classes are injected through
+``use_jdopttn=`` / ``use_cotengra=`` (compiled_circuit.py:356-393).  The two classes here have those constructors
+and that method, and run the contraction on the B200 engine, so the REFERENCE'S OWN backend can use it unchanged:
+
+    circuit.compilecircuit(backend="pytorch", use_jdopttn=tedq_b200.B200OptTN, requires_grad=False,
+                           hyper_opt={"max_repeats": 64, "slicing_opts": {"target_num_slices": 8}})
+    circuit.compilecircuit(backend="pytorch", use_cotengra=tedq_b200.ctg_compat, requires_grad=False)
+
+Forward values only: the reference differentiates through its tree with the autograd tape of torch.tensordot;
+this engine has no backward through the contraction tree yet (gradients: ``backend="pytorch_b200"``, whose
+backward is the adjoint sweep), so arrays that require grad are refused instead of silently detached.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi, planner
+
+
+class B200OptTN:
+    """``JDOptTN(input_indices, size_dict, output=..., imbalance=..., max_repeats=..., search_parallel=...,
+    slicing_opts=...)`` -> object with ``contract(arrays, backend='torch')`` (compiled_circuit.py:388-393)."""
+
+    def __init__(self, input_indices: Sequence[Sequence], size_dict: Optional[Dict] = None, output: Sequence = (),
+                 imbalance: float = 0.2, max_repeats: int = 128, search_parallel: bool = True,
+                 slicing_opts: Optional[dict] = None, **_ignored):
+        ids: Dict[object, int] = {}
+        for t in input_indices:
+            for ix in t:
+                ids.setdefault(ix, len(ids))
+        for ix in output:
+            ids.setdefault(ix, len(ids))
+        if size_dict:
+            bad = [k for k, v in size_dict.items() if int(v) != 2]
+            if bad:
+                raise ValueError(f"B200OptTN contracts qubit networks: every index has size 2 (got {bad[:3]})")
+        self.inputs: List[List[int]] = [[ids[ix] for ix in t] for t in input_indices]
+        self.output: List[int] = [ids[ix] for ix in output]
+        info = planner.find_path(self.inputs, self.output, repeats=min(int(max_repeats), 64), seed=0)
+        so = slicing_opts or {}
+        tsize = so.get("target_size")
+        tnum = int(so.get("target_num_slices", 1) or 1)
+        if tsize or tnum > 1:
+            info = planner.slice_path(self.inputs, self.output, info,
+                                      target_size_log2=int(np.log2(tsize)) if tsize else None, target_num_slices=tnum)
+        self.info = info
+        self._plans: Dict[int, capi.TnPlan] = {}
+
+    def _plan(self, dtype) -> capi.TnPlan:
+        key = capi.TQ_C64 if dtype == torch.complex64 else capi.TQ_C128
+        if key not in self._plans:
+            self._plans[key] = capi.TnPlan(self.inputs, self.output, self.info.path, self.info.sliced,
+                                           [False] * len(self.inputs), key)
+        return self._plans[key]
+
+    def contract(self, arrays, backend: str = "torch", prefer_einsum: bool = True, **_ignored) -> torch.Tensor:
+        if backend != "torch":
+            raise ValueError("B200OptTN.contract: only backend='torch' (device tensors) is supported")
+        if len(arrays) != len(self.inputs):
+            raise ValueError(f"expected {len(self.inputs)} arrays, got {len(arrays)}")
+        if any(getattr(a, "requires_grad", False) for a in arrays) and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "B200OptTN.contract is forward-only: compile the reference backend with requires_grad=False, or use "
+                "backend='pytorch_b200' (adjoint-sweep gradients)")
+        dtype = arrays[0].dtype
+        if dtype not in (torch.complex64, torch.complex128):
+            raise ValueError(f"complex64 / complex128 operands expected, got {dtype}")
+        dev = arrays[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("B200OptTN.contract needs CUDA tensors: the engine has no CPU fallback")
+        keep = [a.detach().to(dtype).contiguous() for a in arrays]
+        for a, ix in zip(keep, self.inputs):
+            if a.numel() != 1 << len(ix):
+                raise ValueError(f"operand with {a.numel()} entries for {len(ix)} indices of size 2")
+        plan = self._plan(dtype)
+        out = torch.zeros((1, 1 << len(self.output)), dtype=dtype, device=dev)
+        ws_bytes = plan.workspace_bytes(1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ptrs = np.array([a.data_ptr() for a in keep], dtype=np.int64)
+        with torch.cuda.device(dev):
+            plan.contract(ptrs, np.zeros(len(keep), dtype=np.int64), 1, 0, plan.n_slices, out.data_ptr(), ws.data_ptr(),
+                          ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
+        return out.reshape((2,) * len(self.output)) if self.output else out.reshape(())
+
+
+class _HyperOptimizer:
+    """``ctg.HyperOptimizer(methods, max_repeats, progbar, minimize, score_compression, slicing_opts)
+    .search(inputs, output, size_dict)`` -> tree (compiled_circuit.py:359-368)."""
+
+    def __init__(self, methods=None, max_repeats: int = 128, progbar: bool = False, minimize: str = "flops",
+                 score_compression: float = 0.5, slicing_opts: Optional[dict] = None, **_ignored):
+        self.max_repeats = max_repeats
+        self.slicing_opts = slicing_opts
+
+    def search(self, inputs, output, size_dict) -> B200OptTN:
+        return B200OptTN(inputs, size_dict, output=output, max_repeats=self.max_repeats, slicing_opts=self.slicing_opts)
+
+
+class _CtgCompat:
+    """Module-shaped object for ``use_cotengra=``: the reference reads ``.HyperOptimizer`` from it."""
+    HyperOptimizer = _HyperOptimizer
+
+
+ctg_compat = _CtgCompat()

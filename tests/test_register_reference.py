@@ -70,3 +70,28 @@ def test_frontend_traces_the_same_gate_table_as_the_reference(qai):
             if ga.matrix is not None:
                 assert abs(ga.matrix - gb.matrix).max() < 1e-15
         assert a.axeslist == b.axeslist and a.permutationlist == b.permutationlist
+
+
+def test_reference_backend_accepts_b200_tree_plugins(qai):
+    """The reference's OWN PyTorchBackend, with the B200 contraction tree injected through use_jdopttn= /
+    use_cotengra= (compiled_circuit.py:356-393): constructors are called with the reference's arguments and build
+    one plan per measurement network; the contraction itself needs a GPU (no CPU fallback: loud error here)."""
+    import tedq_b200
+
+    def circuitDef(a, b):
+        qai.RX(a, qubits=[0])
+        qai.Hadamard(qubits=[1])
+        qai.CNOT(qubits=[0, 1])
+        qai.RY(b, qubits=[1])
+        return [qai.expval(qai.PauliZ(qubits=[0])), qai.expval(qai.PauliZ(qubits=[1]))]
+
+    a, b = torch.tensor([0.3]), torch.tensor([0.7])
+    circuit = qai.Circuit(circuitDef, 2, a, b)
+    for kw in ({"use_jdopttn": tedq_b200.B200OptTN}, {"use_cotengra": tedq_b200.ctg_compat}):
+        cc = circuit.compilecircuit(backend="pytorch", requires_grad=False, tn_simplify=False,
+                                    hyper_opt={"max_repeats": 4, "slicing_opts": {"target_num_slices": 2}}, **kw)
+        trees = cc._optimize_order_trees
+        assert len(trees) == 2 and all(isinstance(t, tedq_b200.B200OptTN) for t in trees)
+        assert all(t.info.n_slices >= 2 and len(t.inputs) == 2 + 4 + 1 + 4 + 2 for t in trees)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            cc(a, b)

@@ -117,3 +117,33 @@ def test_c5_amplitude_tensor_core_matches_complex128():
                                                     hyper_opt={"max_repeats": 16})
     assert abs(complex(simp.amplitude(bits).cpu()) - ref) <= 1e-5 * abs(ref)
     assert abs(complex(simp.amplitude(one).cpu()) - r1) <= 1e-5 * abs(r1)
+
+
+def test_reference_tree_plugin_boundary():
+    """The planner plug-in boundary of the reference (use_jdopttn= / use_cotengra=, compiled_circuit.py:356-393):
+    B200OptTN has JDOptTN's constructor and contract(arrays, backend='torch'); called the way pytorch_backend.py:339
+    calls it (symbol strings, torch operands in network order) it reproduces the reference fixture."""
+    case = next(c for c in CASES if c["spec"]["num_qubits"] >= 4 and c["spec"]["meas"][0][0] == "expval"
+                and c["dtype"] == "c64" and c["spec"]["n_params"] > 0)
+    circ = build(case, "c64", case["flat"][0])
+    from tedq_b200 import tn_index
+    flat = torch.tensor(case["flat"][0], dtype=torch.float32)
+    arrays_all = tn_ref.operands(circ, flat.double(), torch.complex128)
+    nets = tn_index.networks_of_circuit(circ)
+    got = []
+    for net, arrs in zip(nets, arrays_all):
+        inputs, output = net.symbols()                      # what gen_tensor_networks hands to JDOptTN
+        size_dict = {s: 2 for s in net.size_keys()}
+        for tree in (qb.B200OptTN(inputs, size_dict, output=output, imbalance=0.2, max_repeats=8, search_parallel=True,
+                                  slicing_opts={"target_num_slices": 2}),
+                     qb.ctg_compat.HyperOptimizer(methods=["kahypar"], max_repeats=8, progbar=False, minimize="flops",
+                                                  score_compression=0.5, slicing_opts=None).search(inputs, output,
+                                                                                                  size_dict)):
+            ops = [torch.tensor(np.asarray(a), dtype=torch.complex64, device="cuda") for a in arrs]
+            r = tree.contract(ops, backend="torch")
+            got.append(float(torch.squeeze(r.real).cpu()))
+    ref = np.repeat(golden_out(case)[0].reshape(-1), 2)
+    assert_close(np.asarray(got), ref, 1e-5, "tree plug-in")
+    with pytest.raises(NotImplementedError):
+        ops[0].requires_grad_(True)
+        tree.contract(ops, backend="torch")
