@@ -257,6 +257,28 @@ int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int6
                    int64_t slice_begin, int64_t slice_end, void* out, void* workspace, size_t workspace_bytes,
                    void* cuda_stream);
 
+/* ---- reverse mode through the contraction tree (the reference differentiates through tree.contract with torch's
+ *      tape, pytorch_backend.py:276/:339 under back_prop) ------------------------------------------------------
+ * tq_tn_plan_enable_backward appends, for every forward step C = A x B on the way to an input that needs a
+ * gradient, the two contractions  g_A = g_C x B  and  g_B = A x g_C  of the CONJUGATED gradients g = conj(dL/dT)
+ * (so that no operand has to be conjugated), plus the seed g_out = conj(grad_out); the schedule, the fused runs and
+ * the arena layout are rebuilt for the combined list, forward intermediates that the reverse pass reads stay
+ * alive.  Unsliced plans only.  Usage: tq_tn_contract(..., slices [0, 1), workspace W) then
+ * tq_tn_backward(..., grad_out, the SAME workspace W).  Gradients stay in the workspace:
+ *   tq_tn_workspace_layout -> byte offsets of the shared / per-set arenas and the per-set stride (complex entries)
+ *   tq_tn_grad_info(t)     -> element offset, arena (-1 shared, -2 per set) and, for the i-th index of input t's
+ *                             own list, its bit inside the gradient tensor (entries are conj(dL/dT)).
+ * tq_tn_param_grads (circuit networks) applies the chain rule to the flat parameters: off_g / off_a are device
+ * int32 [n_gates][16] tables of per-set-arena element offsets of the gradient entries of G / G^dagger (-1: none);
+ * grad_params [batch][n_params] is accumulated (+=), the caller zeroes it. */
+int tq_tn_plan_enable_backward(tq_tn_plan* plan, const int32_t* input_needs_grad);
+int tq_tn_backward(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
+                   const void* grad_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+int tq_tn_grad_info(const tq_tn_plan* plan, int32_t t, int64_t* offset, int32_t* space, int32_t* bits);
+int tq_tn_workspace_layout(const tq_tn_plan* plan, int64_t* shared_off, int64_t* perset_off, int64_t* set_stride);
+int tq_tn_param_grads(const tq_plan* plan, const void* params, int64_t batch, const void* arena, int64_t set_stride,
+                      const int32_t* off_g, const int32_t* off_a, void* grad_params, void* cuda_stream);
+
 /* Profiling twin of tq_tn_contract for ONE slice: same work, plus CUDA events around every step.
  * step_ms has 2 * n_steps + 2 entries: step_ms[2*s] = milliseconds of step s, step_ms[2*s+1] = the part spent
  * packing operand images (tensor-core steps only); step_ms[2*n_steps] = once-per-call packing of the

@@ -1,2 +1,2 @@
 set -x
-timeout 600 python -m pytest tests/test_tn_gpu.py -x -q -k "plugin or c5" 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12

@@ -134,6 +134,16 @@ def lib() -> C.CDLL:
     L.tq_tn_workspace_bytes.restype = sz
     L.tq_tn_contract.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
     L.tq_tn_contract.restype = i32
+    L.tq_tn_plan_enable_backward.argtypes = [vp, pi32]
+    L.tq_tn_plan_enable_backward.restype = i32
+    L.tq_tn_backward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, vp, vp, sz, vp]
+    L.tq_tn_backward.restype = i32
+    L.tq_tn_grad_info.argtypes = [vp, i32, C.POINTER(i64), pi32, pi32]
+    L.tq_tn_grad_info.restype = i32
+    L.tq_tn_workspace_layout.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.tq_tn_workspace_layout.restype = i32
+    L.tq_tn_param_grads.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.tq_tn_param_grads.restype = i32
     L.tq_tn_gather.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp]
     L.tq_tn_gather.restype = i32
     L.tq_tn_plan_set_option.argtypes = [vp, i32, i32]
@@ -386,6 +396,30 @@ class TnPlan:
 
     def workspace_bytes(self, batch):
         return int(lib().tq_tn_workspace_bytes(self.handle, batch))
+
+    def enable_backward(self, input_needs_grad):
+        """Append the reverse pass (unsliced plans): see tq_tn_plan_enable_backward."""
+        check(lib().tq_tn_plan_enable_backward(self.handle, _i32([1 if b else 0 for b in input_needs_grad])),
+              "tq_tn_plan_enable_backward")
+        self.has_backward = True
+
+    def backward(self, input_ptrs, input_strides, batch, grad_out_ptr, ws_ptr, ws_bytes, stream):
+        ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
+        check(lib().tq_tn_backward(self.handle, ptrs, strides, batch, grad_out_ptr, ws_ptr, ws_bytes, stream),
+              "tq_tn_backward")
+
+    def grad_info(self, t, rank):
+        """-> (element offset, space (-1 shared / -2 per set), bit of every index of input t inside its gradient)."""
+        off, space = C.c_int64(), C.c_int32()
+        bits = (C.c_int32 * max(1, rank))()
+        check(lib().tq_tn_grad_info(self.handle, t, C.byref(off), C.byref(space), bits), "tq_tn_grad_info")
+        return int(off.value), int(space.value), [int(bits[i]) for i in range(rank)]
+
+    def workspace_layout(self):
+        """-> (byte offset of the shared arena, byte offset of the per-set arenas, per-set stride in entries)."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().tq_tn_workspace_layout(self.handle, C.byref(a), C.byref(b), C.byref(c)), "tq_tn_workspace_layout")
+        return int(a.value), int(b.value), int(c.value)
 
     def set_option(self, option, value):
         check(lib().tq_tn_plan_set_option(self.handle, option, value), "tq_tn_plan_set_option")

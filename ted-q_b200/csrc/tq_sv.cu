@@ -948,6 +948,28 @@ int64_t tq_plan_launches(const tq_plan* p, int32_t backward) {
   return 1 + (p->bwd_full ? 1 : (int64_t)p->bwd.size() + 1);
 }
 
+int tq_tn_param_grads(const tq_plan* p, const void* params, int64_t batch, const void* arena, int64_t set_stride,
+                      const int32_t* off_g, const int32_t* off_a, void* grad_params, void* stream) {
+  TQ_REQUIRE(p && arena && off_g && off_a && grad_params && batch > 0, TQ_E_INVALID,
+             "tq_tn_param_grads: null argument");
+  TQ_REQUIRE(params || p->n_params == 0, TQ_E_INVALID, "tq_tn_param_grads: params is null");
+  const int ng = (int)p->gate_t.size();
+  if (ng == 0 || p->n_params == 0) return TQ_OK;
+  const int64_t total = batch * ng;
+  const int threads = 128;
+  const int64_t blocks = (total + threads - 1) / threads;
+  if (p->dtype == TQ_C64)
+    k_gate_tensor_grads<float><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        (const float*)params, p->n_params, batch, p->d_gate_t, ng, (const cx<float>*)arena, set_stride, off_g, off_a,
+        (float*)grad_params);
+  else
+    k_gate_tensor_grads<double><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        (const double*)params, p->n_params, batch, p->d_gate_t, ng, (const cx<double>*)arena, set_stride, off_g,
+        off_a, (double*)grad_params);
+  TQ_CUDA_OK(cudaGetLastError());
+  return TQ_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------

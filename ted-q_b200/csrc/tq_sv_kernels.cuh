@@ -422,6 +422,54 @@ __global__ void k_gate_tensors(const R* __restrict__ params, int n_params, int64
     }
 }
 
+// Chain rule from the gradients of a network's gate operands to the flat parameters (tensor-network mode
+// backward): one thread per (parameter set, gate).  g holds CONJUGATED operand gradients inside the per-set
+// arena of tq_tn_backward; off_g[gate][e] / off_a[gate][e] = element offset of entry e of the gradient of G
+// (ket half) / G^dagger (bra half), -1 where the network has no such entry (constant operands, entries removed
+// by tn_simplify).  dL/dtheta = Re sum_e g_e * dT_e/dtheta; the thread owns its parameter slots (one flat slot
+// belongs to exactly one gate), so += needs no atomics and accumulates over measurement networks.
+template <typename R>
+__global__ void k_gate_tensor_grads(const R* __restrict__ params, int n_params, int64_t batch,
+                                    const GateT* __restrict__ tab, int n_gates, const cx<R>* __restrict__ arena,
+                                    int64_t set_stride, const int32_t* __restrict__ off_g,
+                                    const int32_t* __restrict__ off_a, R* __restrict__ grad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * n_gates) return;
+  const int64_t b = t / n_gates;
+  const int gi = (int)(t - b * n_gates);
+  const GateT g = tab[gi];
+  if (g.kind == TQ_G_FIXED || (g.pidx[0] < 0 && g.pidx[1] < 0 && g.pidx[2] < 0)) return;
+  R p[3];
+  for (int i = 0; i < 3; ++i) p[i] = g.pidx[i] >= 0 ? params[b * n_params + g.pidx[i]] : (R)g.pconst[i];
+  cx<R> M[4], D[3][4];
+  for (int i = 0; i < 3; ++i)
+    for (int e = 0; e < 4; ++e) D[i][e] = mk<R>(0, 0);
+  param_gate<R>(g.kind, p, M, D);
+  const bool ctl = kind_controlled(g.kind);
+  const int Dd = ctl ? 4 : 2, base = ctl ? 2 : 0;
+  const cx<R>* a = arena + b * set_stride;
+  const int32_t* og = off_g + gi * 16;
+  const int32_t* oa = off_a + gi * 16;
+  for (int i = 0; i < 3; ++i) {
+    if (g.pidx[i] < 0) continue;
+    R acc = 0;
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 2; ++c) {
+        const cx<R> d = D[i][r * 2 + c];
+        const int eg = (base + r) * Dd + (base + c), ea = (base + c) * Dd + (base + r);
+        if (og[eg] >= 0) {  // Re(g * d)
+          const cx<R> gv = a[og[eg]];
+          acc += gv.x * d.x - gv.y * d.y;
+        }
+        if (oa[ea] >= 0) {  // adjoint operand entry = conj(d): Re(g * conj(d))
+          const cx<R> gv = a[oa[ea]];
+          acc += gv.x * d.x + gv.y * d.y;
+        }
+      }
+    grad[b * n_params + g.pidx[i]] += acc;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // op application on shared-memory tiles
 // ---------------------------------------------------------------------------

@@ -735,6 +735,18 @@ __global__ void k_tn_final(const cx<R>* __restrict__ last, int64_t sL, cx<R>* __
   dst->y += v.y;
 }
 
+// gradient seed of the reverse pass: g[set][o] = conj(grad_out[set][perm(o)]) in the layout of the last forward tensor
+template <typename R>
+__global__ void k_tn_seed(const cx<R>* __restrict__ gout, int64_t sO, cx<R>* __restrict__ g, int64_t sG,
+                          const __grid_constant__ FinalDev f, int64_t n) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const int64_t set = blockIdx.y;
+  const cx<R> v = gout[set * sO + scat((uint32_t)o, f.pos, f.rank)];
+  g[set * sG + o] = mk<R>(v.x, -v.y);
+}
+
+
 constexpr int DOT_MAX_OUT_LOG2 = 6, DOT_MIN_K_LOG2 = 12, DOT_BLOCKS = 128;
 // a step joins a fused run when k+m+n+b <= this (one CTA per parameter set does the whole step)
 constexpr int FUSE_MAX_WORK_BATCHED = 18, FUSE_MAX_WORK_SHARED = 14, FUSE_CTA_WORK = 8, FUSE_MAX_OUT_LOG2 = 12;
@@ -802,10 +814,19 @@ struct tq_tn_plan {
   double flops = 0;
   int width = 0;
   // schedule: what runs, in which order (rebuilt when an option changes)
-  std::vector<int> kind;            // per step: 0 per-element, 1 FMA GEMM, 2 tcgen05 GEMM, 3 split-K, 4 fused run
-  std::vector<SchedItem> items[2];  // phase 0: once per call; phase 1: every slice
+  std::vector<int> kind;            // per step: 0 per-element, 1 FMA GEMM, 2 tcgen05 GEMM, 3 split-K, 4 fused run,
+                                    //           5 apply, 6 gradient seed
+  std::vector<SchedItem> items[3];  // phase 0: once per call; phase 1: every slice; phase 2: backward pass
+  std::vector<char> phase;          // per step
   std::vector<char> t_slice;        // per tensor id: depends on a sliced index
+  std::vector<char> t_batch;        // per tensor id: differs per parameter set
   std::vector<int> t_rank;
+  // reverse mode (tq_tn_plan_enable_backward): forward steps [0, n_fwd), then the seed step, then two
+  // contractions per forward step (conjugated gradients, see tq_tn_backward)
+  int n_fwd = 0;                    // number of forward steps (== steps.size() until backward is enabled)
+  int seed_step = -1;
+  std::vector<std::vector<int>> layout;  // per tensor id: index id of every bit (fast -> slow)
+  std::vector<int> grad_of;              // per tensor id: tensor id of its (conjugated) gradient, -1 if none
   std::vector<ApplyDev> apply;      // per step (kind 5 only)
   std::vector<char> apply_small_rhs;
   FusedStep* d_fsteps = nullptr;
@@ -820,6 +841,120 @@ struct tq_tn_plan {
   int tc_splitk = 1;       // TQ_TN_OPT_TC_SPLITK
   int num_sms = 148;
 };
+
+// Per-step derived data for steps [first, end): dependency flags, ranks, layouts, K tables, tensor-core lowering.
+static int setup_steps(tq_tn_plan* p, int first) {
+  const int n_in = p->n_in, n_steps = (int)p->steps.size();
+  p->dep_batch.resize(n_steps);
+  p->dep_slice.resize(n_steps);
+  p->arena_const.resize(n_steps);
+  p->t_batch.resize(n_in + n_steps);
+  p->t_slice.resize(n_in + n_steps);
+  p->t_rank.resize(n_in + n_steps);
+  p->layout.resize(n_in + n_steps);
+  for (int s = first; s < n_steps; ++s) {
+    const tq_tn_step& st = p->steps[s];
+    const int o = n_in + s;
+    p->t_batch[o] = p->t_batch[st.lhs] || p->t_batch[st.rhs];
+    p->t_slice[o] = p->t_slice[st.lhs] || p->t_slice[st.rhs];
+    p->t_rank[o] = s == p->seed_step ? p->n_out : st.n_m + st.n_n + st.n_b;
+    p->dep_batch[s] = p->t_batch[o];
+    p->dep_slice[s] = p->t_slice[o];
+    p->arena_const[s] = !p->t_batch[o];
+    p->width = std::max(p->width, p->t_rank[o]);
+    p->layout[o].assign(st.out_idx, st.out_idx + p->t_rank[o]);
+  }
+  // device step tables
+  p->dev.resize(n_steps);
+  p->d_ka.resize(n_steps, nullptr);
+  p->d_kb.resize(n_steps, nullptr);
+  for (int s = first; s < n_steps; ++s) {
+    if (s == p->seed_step) continue;
+    const tq_tn_step& st = p->steps[s];
+    StepDev& d = p->dev[s];
+    memset(&d, 0, sizeof(d));
+    d.n_k = st.n_k;
+    d.n_m = st.n_m;
+    d.n_n = st.n_n;
+    d.n_b = st.n_b;
+    TQ_REQUIRE(st.n_k <= 24 || st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2, TQ_E_UNSUPPORTED,
+               "tq_tn_plan_create: step %d contracts 2^%d terms", s, st.n_k);
+    for (int j = 0; j < st.n_m; ++j) d.a_m[j] = st.lhs_bits[st.n_k + j];
+    for (int j = 0; j < st.n_b; ++j) d.a_b[j] = st.lhs_bits[st.n_k + st.n_m + j];
+    for (int j = 0; j < st.n_n; ++j) d.b_n[j] = st.rhs_bits[st.n_k + j];
+    for (int j = 0; j < st.n_b; ++j) d.b_b[j] = st.rhs_bits[st.n_k + st.n_n + j];
+    for (int j = 0; j < st.n_k; ++j) {
+      d.a_k[j] = st.lhs_bits[j];
+      d.b_k[j] = st.rhs_bits[j];
+    }
+    const bool is_dot = st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2;
+    const int K = 1 << (is_dot ? DOT_LO : st.n_k);
+    std::vector<int32_t> ka(K), kb(K);
+    for (int k = 0; k < K; ++k) {
+      uint32_t a = 0, b = 0;
+      for (int j = 0; j < st.n_k; ++j)
+        if ((k >> j) & 1) {
+          a |= 1u << st.lhs_bits[j];
+          b |= 1u << st.rhs_bits[j];
+        }
+      ka[k] = (int32_t)a;
+      kb[k] = (int32_t)b;
+    }
+    for (int j = 0; j < st.n_k; ++j) {
+      if (st.lhs_bits[j] == 0) d.a_k_fast = 1;
+      if (st.rhs_bits[j] == 0) d.b_k_fast = 1;
+    }
+    TQ_CUDA_OK(cudaMalloc((void**)&p->d_ka[s], K * sizeof(int32_t)));
+    TQ_CUDA_OK(cudaMalloc((void**)&p->d_kb[s], K * sizeof(int32_t)));
+    TQ_CUDA_OK(cudaMemcpy(p->d_ka[s], ka.data(), K * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TQ_CUDA_OK(cudaMemcpy(p->d_kb[s], kb.data(), K * sizeof(int32_t), cudaMemcpyHostToDevice));
+    d.ka = p->d_ka[s];
+    d.kb = p->d_kb[s];
+  }
+  // tensor-core lowering (complex64): the operand with more free indices provides the 128 accumulator rows
+  p->tc.resize(n_steps);
+  for (int s = first; s < n_steps && p->dtype == TQ_C64; ++s) {
+    if (s == p->seed_step) continue;
+    const tq_tn_step& st = p->steps[s];
+    TcStep& T = p->tc[s];
+    // Accumulator rows (2x image expansion) come from the operand with more free indices, unless exactly one
+    // operand changes per slice and is tall enough: then that one takes the rows (its per-slice image is the
+    // cheaper one to write) and the invariant operand's 4x image is packed once.
+    const bool lhs_var = p->t_slice[st.lhs] != 0, rhs_var = p->t_slice[st.rhs] != 0;
+    T.swap = st.n_n > st.n_m;
+    if (lhs_var != rhs_var && std::min(st.n_m, st.n_n) >= 7) T.swap = rhs_var;
+    const int n_row = T.swap ? st.n_n : st.n_m, n_col = T.swap ? st.n_m : st.n_n;
+    {
+      const bool a_var = T.swap ? rhs_var : lhs_var, b_var = T.swap ? lhs_var : rhs_var;
+      T.pin_a = p->dep_slice[s] && !a_var;
+      T.pin_b = p->dep_slice[s] && !b_var;
+    }
+    T.shape_ok = n_row >= 7 && n_col >= 4 && n_row + n_col + st.n_b <= 31;
+    if (!T.shape_ok) continue;
+    const int col_t_log2 = std::min(n_col, 7);
+    T.c_t = 1 << col_t_log2;
+    T.kblocks = st.n_k > tc::KB_LOG ? 1 << (st.n_k - tc::KB_LOG) : 1;
+    T.tiles_a = 1 << (n_row - 7);
+    T.tiles_b = 1 << (n_col - col_t_log2);
+    T.stages = tc::num_stages(T.c_t);
+    T.img_a_z = (int64_t)T.tiles_a * T.kblocks * tc::A_CHUNK;
+    T.img_b_z = (int64_t)T.tiles_b * T.kblocks * tc::b_chunk_bytes(T.c_t);
+    const int8_t* lhs_k = st.lhs_bits;
+    const int8_t* lhs_m = st.lhs_bits + st.n_k;
+    const int8_t* lhs_b = st.lhs_bits + st.n_k + st.n_m;
+    const int8_t* rhs_k = st.rhs_bits;
+    const int8_t* rhs_n = st.rhs_bits + st.n_k;
+    const int8_t* rhs_b = st.rhs_bits + st.n_k + st.n_n;
+    if (!T.swap) {
+      tc_pack_tables(T.pa, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, false, 7);
+      tc_pack_tables(T.pb, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, true, col_t_log2);
+    } else {
+      tc_pack_tables(T.pa, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, false, 7);
+      tc_pack_tables(T.pb, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, true, col_t_log2);
+    }
+  }
+  return TQ_OK;
+}
 
 // Decide which kernel runs every step, group the small ones into fused runs, fix the execution order of both
 // phases (once per call / every slice) and lay the intermediates out in the two arenas for that order.
@@ -845,6 +980,7 @@ static int build_schedule(tq_tn_plan* p) {
     const bool apply_ok = (lhs_small || rhs_small) && outl >= 10 && st.n_b <= 8;
     p->kind[s] = tc_ok ? 2 : small ? 4 : (outl <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2) ? 3
                  : (st.n_m >= 6 && st.n_n >= 6 && st.n_k >= 4) ? 1 : apply_ok ? 5 : 0;
+    if (s == p->seed_step) p->kind[s] = 6;
     if (p->kind[s] == 5) {
       const bool small_rhs = !lhs_small || (rhs_small && st.n_n < st.n_m);
       ApplyDev& a = p->apply[s];
@@ -876,11 +1012,11 @@ static int build_schedule(tq_tn_plan* p) {
   std::vector<FusedStep> fsteps;
   std::vector<int32_t> levels;
   std::vector<uint32_t> microtab;
-  for (int phase = 0; phase < 2; ++phase) {
+  for (int phase = 0; phase < 3; ++phase) {
     p->items[phase].clear();
     std::vector<int> remaining;
     for (int s = 0; s < n_steps; ++s)
-      if ((p->dep_slice[s] != 0) == (phase == 1)) remaining.push_back(s);
+      if (p->phase[s] == phase) remaining.push_back(s);
     while (!remaining.empty()) {
       bool progressed = false;
       for (int batched = 0; batched < 2; ++batched) {
@@ -950,7 +1086,7 @@ static int build_schedule(tq_tn_plan* p) {
   // that feed per-slice steps stay pinned for the whole slice loop; nothing is recycled inside a fused run.
   std::vector<int> item_of(n_steps, 0);
   std::vector<const SchedItem*> order;
-  for (int phase = 0; phase < 2; ++phase)
+  for (int phase = 0; phase < 3; ++phase)
     for (const SchedItem& it : p->items[phase]) {
       const int pos = (int)order.size();
       order.push_back(&it);
@@ -1018,7 +1154,7 @@ static int build_schedule(tq_tn_plan* p) {
     (arena ? p->arena_shared : p->arena_set) = top;
   }
   // ---- device tables of the fused runs
-  for (int phase = 0; phase < 2; ++phase)
+  for (int phase = 0; phase < 3; ++phase)
     for (const SchedItem& it : p->items[phase]) {
       for (size_t i = 0; i < it.members.size(); ++i) {
         const int s = it.members[i];
@@ -1218,85 +1354,21 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
   p->final_perm = R.final_perm;
   p->in_rank.resize(n_in);
   p->in_batched.resize(n_in);
-  std::vector<char> t_batch(n_in + n_steps, 0), t_slice(n_in + n_steps, 0);
-  std::vector<int> t_rank(n_in + n_steps, 0);
+  p->t_batch.assign(n_in, 0);
+  p->t_slice.assign(n_in, 0);
+  p->t_rank.assign(n_in, 0);
+  p->layout.assign(n_in, {});
   for (int t = 0; t < n_in; ++t) {
     p->in_rank[t] = tensor_off[t + 1] - tensor_off[t];
     p->in_batched[t] = input_batched && input_batched[t];
-    t_batch[t] = p->in_batched[t];
-    t_rank[t] = p->in_rank[t];
+    p->t_batch[t] = p->in_batched[t];
+    p->t_rank[t] = p->in_rank[t];
     p->width = std::max(p->width, p->in_rank[t]);
+    for (int pos = p->in_rank[t] - 1; pos >= 0; --pos) p->layout[t].push_back(tensor_idx[tensor_off[t] + pos]);
   }
-  for (int t : p->slice_tensor) t_slice[t] = 1;
-  // dependencies, sizes, flops
-  p->dep_batch.resize(n_steps);
-  p->dep_slice.resize(n_steps);
-  std::vector<int> last_use(n_in + n_steps, -1);
-  for (int s = 0; s < n_steps; ++s) {
-    const tq_tn_step& st = p->steps[s];
-    const int o = n_in + s;
-    t_batch[o] = t_batch[st.lhs] || t_batch[st.rhs];
-    t_slice[o] = t_slice[st.lhs] || t_slice[st.rhs];
-    t_rank[o] = st.n_m + st.n_n + st.n_b;
-    p->dep_batch[s] = t_batch[o];
-    p->dep_slice[s] = t_slice[o];
-    p->width = std::max(p->width, t_rank[o]);
-    p->flops += 8.0 * (double)((int64_t)1 << (st.n_k + st.n_m + st.n_n + st.n_b));
-    last_use[st.lhs] = s;
-    last_use[st.rhs] = s;
-  }
-  p->t_slice.assign(t_slice.begin(), t_slice.end());
-  p->t_rank = t_rank;
-  p->arena_const.assign(n_steps, 0);
-  for (int s = 0; s < n_steps; ++s) p->arena_const[s] = !t_batch[n_in + s];
-  // device step tables
-  p->dev.resize(n_steps);
-  p->d_ka.assign(n_steps, nullptr);
-  p->d_kb.assign(n_steps, nullptr);
-  for (int s = 0; s < n_steps; ++s) {
-    const tq_tn_step& st = p->steps[s];
-    StepDev& d = p->dev[s];
-    memset(&d, 0, sizeof(d));
-    d.n_k = st.n_k;
-    d.n_m = st.n_m;
-    d.n_n = st.n_n;
-    d.n_b = st.n_b;
-    TQ_REQUIRE(st.n_k <= 24 || st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2, TQ_E_UNSUPPORTED,
-               "tq_tn_plan_create: step %d contracts 2^%d terms", s, st.n_k);
-    for (int j = 0; j < st.n_m; ++j) d.a_m[j] = st.lhs_bits[st.n_k + j];
-    for (int j = 0; j < st.n_b; ++j) d.a_b[j] = st.lhs_bits[st.n_k + st.n_m + j];
-    for (int j = 0; j < st.n_n; ++j) d.b_n[j] = st.rhs_bits[st.n_k + j];
-    for (int j = 0; j < st.n_b; ++j) d.b_b[j] = st.rhs_bits[st.n_k + st.n_n + j];
-    for (int j = 0; j < st.n_k; ++j) {
-      d.a_k[j] = st.lhs_bits[j];
-      d.b_k[j] = st.rhs_bits[j];
-    }
-    const bool is_dot = st.n_m + st.n_n + st.n_b <= DOT_MAX_OUT_LOG2 && st.n_k >= DOT_MIN_K_LOG2;
-    const int K = 1 << (is_dot ? DOT_LO : st.n_k);
-    std::vector<int32_t> ka(K), kb(K);
-    for (int k = 0; k < K; ++k) {
-      uint32_t a = 0, b = 0;
-      for (int j = 0; j < st.n_k; ++j)
-        if ((k >> j) & 1) {
-          a |= 1u << st.lhs_bits[j];
-          b |= 1u << st.rhs_bits[j];
-        }
-      ka[k] = (int32_t)a;
-      kb[k] = (int32_t)b;
-    }
-    for (int j = 0; j < st.n_k; ++j) {
-      if (st.lhs_bits[j] == 0) d.a_k_fast = 1;
-      if (st.rhs_bits[j] == 0) d.b_k_fast = 1;
-    }
-    TQ_CUDA_OK(cudaMalloc((void**)&p->d_ka[s], K * sizeof(int32_t)));
-    TQ_CUDA_OK(cudaMalloc((void**)&p->d_kb[s], K * sizeof(int32_t)));
-    TQ_CUDA_OK(cudaMemcpy(p->d_ka[s], ka.data(), K * sizeof(int32_t), cudaMemcpyHostToDevice));
-    TQ_CUDA_OK(cudaMemcpy(p->d_kb[s], kb.data(), K * sizeof(int32_t), cudaMemcpyHostToDevice));
-    d.ka = p->d_ka[s];
-    d.kb = p->d_kb[s];
-  }
-  // tensor-core lowering (complex64): the operand with more free indices provides the 128 accumulator rows
-  p->tc.resize(n_steps);
+  for (int t : p->slice_tensor) p->t_slice[t] = 1;
+  p->n_fwd = n_steps;
+  p->phase.assign(n_steps, 0);
   {
     int dev_id = 0, sms = 0;
     if (cudaGetDevice(&dev_id) == cudaSuccess &&
@@ -1304,48 +1376,140 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
       p->num_sms = sms;
     (void)cudaGetLastError();
   }
-  for (int s = 0; s < n_steps && dtype == TQ_C64; ++s) {
+  rc = setup_steps(p, 0);
+  if (rc) return rc;
+  for (int s = 0; s < n_steps; ++s) {
+    p->phase[s] = p->dep_slice[s] ? 1 : 0;
     const tq_tn_step& st = p->steps[s];
-    TcStep& T = p->tc[s];
-    // Accumulator rows (2x image expansion) come from the operand with more free indices, unless exactly one
-    // operand changes per slice and is tall enough: then that one takes the rows (its per-slice image is the
-    // cheaper one to write) and the invariant operand's 4x image is packed once.
-    const bool lhs_var = t_slice[st.lhs] != 0, rhs_var = t_slice[st.rhs] != 0;
-    T.swap = st.n_n > st.n_m;
-    if (lhs_var != rhs_var && std::min(st.n_m, st.n_n) >= 7) T.swap = rhs_var;
-    const int n_row = T.swap ? st.n_n : st.n_m, n_col = T.swap ? st.n_m : st.n_n;
-    {
-      const bool a_var = T.swap ? rhs_var : lhs_var, b_var = T.swap ? lhs_var : rhs_var;
-      T.pin_a = p->dep_slice[s] && !a_var;
-      T.pin_b = p->dep_slice[s] && !b_var;
-    }
-    T.shape_ok = n_row >= 7 && n_col >= 4 && n_row + n_col + st.n_b <= 31;
-    if (!T.shape_ok) continue;
-    const int col_t_log2 = std::min(n_col, 7);
-    T.c_t = 1 << col_t_log2;
-    T.kblocks = st.n_k > tc::KB_LOG ? 1 << (st.n_k - tc::KB_LOG) : 1;
-    T.tiles_a = 1 << (n_row - 7);
-    T.tiles_b = 1 << (n_col - col_t_log2);
-    T.stages = tc::num_stages(T.c_t);
-    T.img_a_z = (int64_t)T.tiles_a * T.kblocks * tc::A_CHUNK;
-    T.img_b_z = (int64_t)T.tiles_b * T.kblocks * tc::b_chunk_bytes(T.c_t);
-    const int8_t* lhs_k = st.lhs_bits;
-    const int8_t* lhs_m = st.lhs_bits + st.n_k;
-    const int8_t* lhs_b = st.lhs_bits + st.n_k + st.n_m;
-    const int8_t* rhs_k = st.rhs_bits;
-    const int8_t* rhs_n = st.rhs_bits + st.n_k;
-    const int8_t* rhs_b = st.rhs_bits + st.n_k + st.n_n;
-    if (!T.swap) {
-      tc_pack_tables(T.pa, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, false, 7);
-      tc_pack_tables(T.pb, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, true, col_t_log2);
-    } else {
-      tc_pack_tables(T.pa, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, false, 7);
-      tc_pack_tables(T.pb, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, true, col_t_log2);
-    }
+    p->flops += 8.0 * (double)((int64_t)1 << (st.n_k + st.n_m + st.n_n + st.n_b));
   }
   rc = build_schedule(p);
   if (rc) return rc;
   *out = P.release();
+  return TQ_OK;
+}
+
+// one pairwise step lhs x rhs -> tensor with index set `target` (every shared index outside target is summed)
+static int make_grad_step(tq_tn_plan* p, int lhs, int rhs, const std::vector<int>& target, tq_tn_step& st,
+                          std::vector<int>& out_layout) {
+  const std::vector<int>&L = p->layout[lhs], &Rr = p->layout[rhs];
+  std::map<int, int> posR;
+  for (size_t i = 0; i < Rr.size(); ++i) posR[Rr[i]] = (int)i;
+  std::set<int> inL(L.begin(), L.end()), tgt(target.begin(), target.end());
+  memset(&st, 0, sizeof(st));
+  st.lhs = lhs;
+  st.rhs = rhs;
+  std::vector<int> K, M, Bt, N;  // bit positions in L (K, M, Bt) / in R (N)
+  for (size_t i = 0; i < L.size(); ++i) {
+    if (posR.count(L[i])) (tgt.count(L[i]) ? Bt : K).push_back((int)i);
+    else M.push_back((int)i);
+  }
+  for (size_t i = 0; i < Rr.size(); ++i)
+    if (!inL.count(Rr[i])) N.push_back((int)i);
+  st.n_k = (int)K.size();
+  st.n_m = (int)M.size();
+  st.n_n = (int)N.size();
+  st.n_b = (int)Bt.size();
+  TQ_REQUIRE(st.n_k + st.n_m + st.n_b <= TQ_TN_MAX_RANK && st.n_k + st.n_n + st.n_b <= TQ_TN_MAX_RANK &&
+                 st.n_m + st.n_n + st.n_b <= TQ_TN_MAX_RANK,
+             TQ_E_UNSUPPORTED, "tq_tn_plan_enable_backward: a gradient step exceeds rank %d", TQ_TN_MAX_RANK);
+  TQ_REQUIRE((size_t)(st.n_m + st.n_n + st.n_b) == tgt.size(), TQ_E_INVALID,
+             "tq_tn_plan_enable_backward: gradient step does not produce the operand's index set");
+  int w = 0;
+  for (int i : K) st.lhs_bits[w++] = (int8_t)i;
+  for (int i : M) st.lhs_bits[w++] = (int8_t)i;
+  for (int i : Bt) st.lhs_bits[w++] = (int8_t)i;
+  w = 0;
+  for (int i : K) st.rhs_bits[w++] = (int8_t)posR[L[i]];
+  for (int i : N) st.rhs_bits[w++] = (int8_t)i;
+  for (int i : Bt) st.rhs_bits[w++] = (int8_t)posR[L[i]];
+  out_layout.clear();
+  for (int i : N) out_layout.push_back(Rr[i]);
+  for (int i : M) out_layout.push_back(L[i]);
+  for (int i : Bt) out_layout.push_back(L[i]);
+  for (size_t j = 0; j < out_layout.size(); ++j) {
+    TQ_REQUIRE(tgt.count(out_layout[j]), TQ_E_INVALID, "tq_tn_plan_enable_backward: stray index in a gradient step");
+    st.out_idx[j] = out_layout[j];
+  }
+  return TQ_OK;
+}
+
+int tq_tn_plan_enable_backward(tq_tn_plan* p, const int32_t* input_needs_grad) {
+  TQ_REQUIRE(p && input_needs_grad, TQ_E_INVALID, "tq_tn_plan_enable_backward: null argument");
+  TQ_REQUIRE(p->n_sliced == 0, TQ_E_UNSUPPORTED, "tq_tn_plan_enable_backward: sliced plans have no reverse pass");
+  TQ_REQUIRE(p->seed_step < 0, TQ_E_INVALID, "tq_tn_plan_enable_backward: already enabled");
+  const int n_in = p->n_in, nf = p->n_fwd;
+  std::vector<char> needs(n_in + nf, 0);
+  for (int t = 0; t < n_in; ++t) needs[t] = input_needs_grad[t] != 0;
+  for (int s = 0; s < nf; ++s) needs[n_in + s] = needs[p->steps[s].lhs] || needs[p->steps[s].rhs];
+  const int final_t = n_in + nf - 1;
+  TQ_REQUIRE(needs[final_t], TQ_E_INVALID, "tq_tn_plan_enable_backward: no input needs a gradient");
+  p->grad_of.assign(n_in + nf, -1);
+  // seed: conj(grad_out) in the layout of the last forward tensor
+  tq_tn_step seed;
+  memset(&seed, 0, sizeof(seed));
+  seed.lhs = seed.rhs = final_t;
+  for (size_t j = 0; j < p->layout[final_t].size(); ++j) seed.out_idx[j] = p->layout[final_t][j];
+  p->seed_step = (int)p->steps.size();
+  p->steps.push_back(seed);
+  p->layout.push_back(p->layout[final_t]);
+  p->grad_of[final_t] = n_in + p->seed_step;
+  int rc;
+  for (int s = nf - 1; s >= 0; --s) {
+    const int C = n_in + s;
+    if (!needs[C]) continue;
+    const int gC = p->grad_of[C];
+    const int A = p->steps[s].lhs, B = p->steps[s].rhs;
+    for (int side = 0; side < 2; ++side) {
+      const int T = side == 0 ? A : B, other = side == 0 ? B : A;
+      if (!needs[T]) continue;
+      tq_tn_step st;
+      std::vector<int> lay;
+      // g_A = g_C x B summed over C's indices that A lacks;  g_B = A x g_C likewise (conjugated gradients:
+      // no operand needs conjugating)
+      if ((rc = side == 0 ? make_grad_step(p, gC, other, p->layout[T], st, lay)
+                          : make_grad_step(p, other, gC, p->layout[T], st, lay)))
+        return rc;
+      p->grad_of[T] = n_in + (int)p->steps.size();
+      p->steps.push_back(st);
+      p->layout.push_back(lay);
+    }
+  }
+  p->grad_of.resize(n_in + p->steps.size(), -1);
+  p->phase.resize(p->steps.size(), 2);
+  if ((rc = setup_steps(p, nf))) return rc;
+  return build_schedule(p);
+}
+
+/* Where the (conjugated) gradient of input t lives after tq_tn_backward: element offset inside its arena,
+ * space (-1 shared arena, -2 per-set arena) and, for the i-th index of the input's own index list
+ * (slow -> fast, as given to tq_tn_plan_create), its bit position inside the gradient tensor. */
+int tq_tn_grad_info(const tq_tn_plan* p, int32_t t, int64_t* offset, int32_t* space, int32_t* bits) {
+  TQ_REQUIRE(p && offset && space && bits && t >= 0 && t < p->n_in, TQ_E_INVALID, "tq_tn_grad_info: bad argument");
+  TQ_REQUIRE(p->seed_step >= 0 && p->grad_of[t] >= 0, TQ_E_INVALID, "tq_tn_grad_info: input %d has no gradient", t);
+  const int g = p->grad_of[t], sidx = g - p->n_in;
+  *offset = p->arena_off[sidx];
+  *space = p->arena_const[sidx] ? -1 : -2;
+  const std::vector<int>& lay = p->layout[g];
+  const std::vector<int>& mine = p->layout[t];  // fast -> slow
+  const int r = (int)mine.size();
+  for (int i = 0; i < r; ++i) {
+    const int ix = mine[r - 1 - i];
+    bits[i] = -1;
+    for (size_t j = 0; j < lay.size(); ++j)
+      if (lay[j] == ix) bits[i] = (int32_t)j;
+    TQ_REQUIRE(bits[i] >= 0, TQ_E_INVALID, "tq_tn_grad_info: index missing from the gradient tensor");
+  }
+  return TQ_OK;
+}
+
+/* byte offsets of the two arenas inside an (aligned) workspace and the per-set stride in complex entries */
+int tq_tn_workspace_layout(const tq_tn_plan* p, int64_t* shared_off, int64_t* perset_off, int64_t* set_stride) {
+  TQ_REQUIRE(p && shared_off && perset_off && set_stride, TQ_E_INVALID, "tq_tn_workspace_layout: null argument");
+  const int64_t cs = p->dtype == TQ_C64 ? 8 : 16;
+  *shared_off = (int64_t)(((size_t)p->n_in * sizeof(InputRef) + 255) & ~(size_t)255);
+  *perset_off = *shared_off + p->arena_shared * cs;
+  *set_stride = p->arena_set;
   return TQ_OK;
 }
 
@@ -1570,7 +1734,7 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
 template <typename R>
 static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const int64_t* strides, int64_t B,
                          int64_t s_begin, int64_t s_end, void* out, void* workspace, size_t ws_bytes,
-                         cudaStream_t st, float* step_ms) {
+                         cudaStream_t st, float* step_ms, bool backward) {
   TQ_REQUIRE(ws_bytes >= tq_tn_workspace_bytes(p, B), TQ_E_WORKSPACE, "tq_tn_contract: workspace too small");
   const int n_in = p->n_in;
   const int n_steps = (int)p->steps.size();
@@ -1637,7 +1801,15 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     }
     const bool timed = step_ms && (slice == s_begin || !p->dep_slice[s]);
     if (timed) TQ_CUDA_OK(cudaEventRecord(ev[3 * s], st));
-    if (kernel == 2) {
+    if (kernel == 6) {  // gradient seed: `out` is grad_out in this mode
+      FinalDev fs;
+      memset(&fs, 0, sizeof(fs));
+      fs.rank = p->n_out;
+      for (int j = 0; j < p->n_out; ++j) fs.pos[p->final_perm[j]] = (int8_t)j;
+      const int64_t n_f = (int64_t)1 << p->n_out;
+      k_tn_seed<R><<<dim3((unsigned)((n_f + 255) / 256), (unsigned)sets), 256, 0, st>>>((const cx<R>*)out, n_f, c, sc,
+                                                                                      fs, n_f);
+    } else if (kernel == 2) {
       if constexpr (sizeof(R) == 4) {
         const TcStep& T = p->tc[s];
         const int64_t nz = sets << stp.n_b;
@@ -1739,6 +1911,11 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     return TQ_OK;
   };
   int rc;
+  if (backward) {  // reverse pass over the intermediates the forward call left in this workspace
+    for (const SchedItem& it : p->items[2])
+      if ((rc = run_item(it, 0))) return rc;
+    return TQ_OK;
+  }
   // once-per-call items, then the slice loop
   for (const SchedItem& it : p->items[0])
     if ((rc = run_item(it, 0))) return rc;
@@ -1751,14 +1928,15 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   f.rank = p->n_out;
   for (int j = 0; j < p->n_out; ++j) f.pos[p->final_perm[j]] = (int8_t)j;
   const int64_t n_final = (int64_t)1 << p->n_out;
-  const bool last_dep_slice = n_steps ? p->dep_slice[n_steps - 1] != 0 : false;
+  const int n_fwd = p->n_fwd;  // the result is the last FORWARD tensor (a reverse pass may follow in the step list)
+  const bool last_dep_slice = n_fwd ? p->dep_slice[n_fwd - 1] != 0 : false;
   for (int64_t slice = s_begin; slice < s_end; ++slice) {
     for (const SchedItem& it : p->items[1])
       if ((rc = run_item(it, slice))) return rc;
     const cx<R>* last;
     int64_t sl;
-    tensor_ptr(n_in + n_steps - 1, slice, last, sl);
-    const int64_t sets = p->dep_batch[n_steps - 1] ? B : 1;
+    tensor_ptr(n_in + n_fwd - 1, slice, last, sl);
+    const int64_t sets = p->dep_batch[n_fwd - 1] ? B : 1;
     k_tn_final<R><<<dim3((unsigned)((n_final + 255) / 256), (unsigned)sets), 256, 0, st>>>(last, sl, (cx<R>*)out,
                                                                                           n_final, f, n_final);
     TQ_CUDA_OK(cudaGetLastError());
@@ -1767,9 +1945,11 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   if (step_ms) {
     TQ_CUDA_OK(cudaStreamSynchronize(st));
     std::vector<char> has_ev(n_steps, 1);
-    for (int phase = 0; phase < 2; ++phase)
+    for (int phase = 0; phase < 3; ++phase)
       for (const SchedItem& it : p->items[phase])
-        for (size_t i = 1; i < it.members.size(); ++i) has_ev[it.members[i]] = 0;  // a run is timed on its first step
+        for (size_t i = (phase == 2 ? 0 : 1); i < it.members.size(); ++i) has_ev[it.members[i]] = 0;
+    for (size_t s2 = 0; s2 < p->phase.size(); ++s2)
+      if (p->phase[s2] == 2) has_ev[s2] = 0;  // the profiling twin times the forward pass only
     for (int s = 0; s < n_steps; ++s) {
       float whole = 0, pack = 0;
       if (!has_ev[s]) {
@@ -1792,7 +1972,7 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
 
 static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
                            int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
-                           size_t workspace_bytes, void* stream, float* step_ms) {
+                           size_t workspace_bytes, void* stream, float* step_ms, bool backward = false) {
   TQ_REQUIRE(p && inputs && out && workspace && batch > 0, TQ_E_INVALID, "tq_tn_contract: null argument");
   TQ_REQUIRE(!p->steps.empty(), TQ_E_INVALID, "tq_tn_contract: empty plan");
   const int64_t ns = (int64_t)1 << p->n_sliced;
@@ -1801,9 +1981,9 @@ static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const
              (long long)slice_end, (long long)ns);
   if (p->dtype == TQ_C64)
     return contract_impl<float>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
-                                workspace_bytes, (cudaStream_t)stream, step_ms);
+                                workspace_bytes, (cudaStream_t)stream, step_ms, backward);
   return contract_impl<double>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
-                               workspace_bytes, (cudaStream_t)stream, step_ms);
+                               workspace_bytes, (cudaStream_t)stream, step_ms, backward);
 }
 
 extern "C" int tq_tn_gather(const void* gate_mats, const void* adj_mats, int64_t src_stride, const int32_t* idx,
@@ -1827,6 +2007,15 @@ extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, co
                               size_t workspace_bytes, void* stream) {
   return tn_contract_any(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace, workspace_bytes,
                          stream, nullptr);
+}
+
+extern "C" int tq_tn_backward(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
+                              int64_t batch, const void* grad_out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  TQ_REQUIRE(p && p->seed_step >= 0, TQ_E_INVALID, "tq_tn_backward: call tq_tn_plan_enable_backward first");
+  TQ_REQUIRE(grad_out, TQ_E_INVALID, "tq_tn_backward: grad_out is null");
+  return tn_contract_any(p, inputs, input_strides, batch, 0, 1, const_cast<void*>(grad_out), workspace,
+                         workspace_bytes, stream, nullptr, true);
 }
 
 extern "C" int tq_tn_profile(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,

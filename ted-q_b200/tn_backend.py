@@ -166,8 +166,60 @@ class TNExecutor:
                         "stride": np.asarray(stride, dtype=np.int64), "any_batched": any(st != 0 for st in stride)}
         return cache[i]
 
-    def contract_values(self, flat: torch.Tensor):
-        """-> list of complex tensors [B or 1, 2^n_out] (one per measurement)."""
+    def tree_backward_available(self) -> bool:
+        """Reverse mode through the contraction tree needs unsliced plans on one rank (hyper_opt["tn_backward"] =
+        "tree" | "adjoint" forces one of the two gradient paths; default: tree when available)."""
+        mode = self.ho.get("tn_backward")
+        if mode == "adjoint":
+            return False
+        ok = all(not info.sliced for info in self.infos) and not self.measurement_parallel and \
+            any(self.gate_batched)
+        if mode == "tree" and not ok:
+            raise ValueError("tn_backward='tree' needs unsliced plans, trainable parameters and no measurement_parallel")
+        return ok
+
+    def _plan_bwd(self, i) -> capi.TnPlan:
+        """Plan of network i with the reverse pass appended (forward-only calls keep the leaner plan)."""
+        cache = self.__dict__.setdefault("_plans_bwd", {})
+        if i not in cache:
+            net, info = self.networks[i], self.infos[i]
+            batched = [kind in (OPD_GATE, OPD_ADJ) and self.gate_batched[ref] for kind, ref in net.operands]
+            dt = capi.TQ_C64 if self.backend._cdtype == torch.complex64 else capi.TQ_C128
+            plan = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
+            for opt, val in (self.ho.get("engine_opts") or {}).items():
+                plan.set_option(int(opt), int(val))
+            plan.enable_backward(batched)
+            cache[i] = plan
+        return cache[i]
+
+    def _grad_tables(self, i, device):
+        """Per network, once: device int32 [n_gates, 16] tables (ket half, bra half) of the per-set-arena element
+        offset of every gate-tensor entry's gradient (-1: no such entry) for tq_tn_param_grads."""
+        cache = self.__dict__.setdefault("_grad_tabs", {})
+        key = (i, str(device))
+        if key not in cache:
+            net, plan = self.networks[i], self._plan_bwd(i)
+            ng = len(self.backend._ir.gates)
+            og = np.full((ng, 16), -1, dtype=np.int32)
+            oa = np.full((ng, 16), -1, dtype=np.int32)
+            reductions = net.reductions or [None] * len(net.operands)
+            for t, ((kind, ref), rd) in enumerate(zip(net.operands, reductions)):
+                if kind not in (OPD_GATE, OPD_ADJ) or not self.gate_batched[ref]:
+                    continue
+                rank = len(net.inputs[t])
+                off, space, bits = plan.grad_info(t, rank)
+                assert space == -2, "a batched operand's gradient lives in the per-set arena"
+                tab = og if kind == OPD_GATE else oa
+                for j in range(1 << rank):          # entry j of the (possibly reduced) operand tensor, C order
+                    e = off + sum(((j >> (rank - 1 - q)) & 1) << bits[q] for q in range(rank))
+                    full = rd[j] if rd is not None else j
+                    tab[ref, full] = e
+            cache[key] = (torch.tensor(og, device=device), torch.tensor(oa, device=device))
+        return cache[key]
+
+    def contract_values(self, flat: torch.Tensor, keep=None):
+        """-> list of complex tensors [B or 1, 2^n_out] (one per measurement).  ``keep`` (a list): use the plans with
+        a reverse pass and append (network id, plan, ptrs, strides, workspace, keep-alive) for tree_backward."""
         be = self.backend
         plan_sv = be.plan()
         L = capi.lib()
@@ -194,10 +246,11 @@ class TNExecutor:
             if mine is not None and i not in mine:
                 results.append(None)
                 continue
-            plan = self._plan(i)
             # operand pointers = base[kind] + offset * element size: vectorised, tables built once per network
             self._table_device = dev
             tab = self._operand_tables(i, net, plan_sv, total)
+            use_bwd = keep is not None and bool(tab["any_batched"])   # a constant network has no gradient
+            plan = self._plan_bwd(i) if use_bwd else self._plan(i)
             bases = np.array([cap0.data_ptr(), gm.data_ptr(), am.data_ptr(),
                               red_buf.data_ptr() if red_buf is not None else 0] + [o.data_ptr() for o in obs[i]],
                              dtype=np.int64)
@@ -215,10 +268,34 @@ class TNExecutor:
                 if plan.n_slices == 1 and torch.distributed.get_rank() != 0:
                     out.zero_()
                 torch.distributed.all_reduce(torch.view_as_real(out))
+            if use_bwd:
+                keep.append((i, plan, ptrs, strides, ws, (gm, am, red_buf)))
             if not any_b and B > 1:
                 out = out.expand(B, -1)
             results.append(out)
         return results
+
+    def tree_backward(self, flat: torch.Tensor, dy: torch.Tensor, kept) -> torch.Tensor:
+        """dL/dparams [B, P] by reverse mode through every network's contraction tree (tq_tn_backward) and the
+        chain rule of the gate tensors (tq_tn_param_grads).  dy: [B, n_meas, ...] cotangent of the stacked result."""
+        be = self.backend
+        B = flat.shape[0]
+        dev = flat.device
+        L = capi.lib()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        grad = torch.zeros((B, be._ir.n_params), dtype=be._rdtype, device=dev)
+        plan_sv = be.plan()
+        for i, plan, ptrs, strides, ws, _alive in kept:
+            gi = dy[:, i].reshape(B, -1)
+            gout = (gi if gi.is_complex() else gi.to(be._rdtype) + 0j).to(be._cdtype).contiguous()
+            og, oa = self._grad_tables(i, dev)
+            _, perset_off, set_stride = plan.workspace_layout()
+            with torch.cuda.device(dev):
+                plan.backward(ptrs, strides, B, gout.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                base = (ws.data_ptr() + 255) // 256 * 256 + perset_off
+                capi.check(L.tq_tn_param_grads(plan_sv.handle, flat.data_ptr(), B, base, set_stride, og.data_ptr(),
+                                               oa.data_ptr(), grad.data_ptr(), stream), "tq_tn_param_grads")
+        return grad
 
     # ------------------------------------------------------------------ amplitudes (C5)
     def _amplitude_plan(self):
@@ -349,9 +426,9 @@ class TNExecutor:
         with torch.no_grad():
             return self._forward_values(flat)
 
-    def _forward_values(self, flat):
+    def _forward_values(self, flat, keep=None):
         be = self.backend
-        vals = self.contract_values(flat.contiguous())
+        vals = self.contract_values(flat.contiguous(), keep)
         res = []
         B = flat.shape[0]
         for ms, v, net in zip(be._ir.meas, vals, self.networks):
@@ -376,21 +453,27 @@ class TNExecutor:
 
 
 class _TNExecute(torch.autograd.Function):
-    """Values from the contraction; gradient from the adjoint state-vector sweeps of the same engine."""
+    """Values from the contraction.  Gradient: reverse mode through the same contraction trees (unsliced plans:
+    tq_tn_backward + tq_tn_param_grads, any number of qubits), otherwise the adjoint state-vector sweeps of the
+    same engine (<= 26 qubits)."""
 
     @staticmethod
     def forward(ctx, run_kwargs, flat):
         ctx.backend = run_kwargs["backend"]
+        ctx.executor = run_kwargs["executor"]
         ctx.save_for_backward(flat)
-        return run_kwargs["executor"]._forward_values(flat)
+        ctx.kept = [] if ctx.executor.tree_backward_available() else None
+        return ctx.executor._forward_values(flat, ctx.kept)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         (flat,) = ctx.saved_tensors
         be = ctx.backend
+        if ctx.kept is not None:
+            return None, ctx.executor.tree_backward(flat.contiguous(), dy, ctx.kept)
         if be._num_qubits > 26:
-            raise NotImplementedError("gradients of networks beyond 26 qubits are not implemented")
+            raise NotImplementedError("gradients of sliced networks beyond 26 qubits are not implemented")
         _, ws = be._forward_device(flat, True)
         return None, be._backward_device(flat, dy, ws)
 

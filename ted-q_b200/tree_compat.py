@@ -9,9 +9,10 @@ and that method, and run the contraction on the B200 engine, so the REFERENCE'S 
                            hyper_opt={"max_repeats": 64, "slicing_opts": {"target_num_slices": 8}})
     circuit.compilecircuit(backend="pytorch", use_cotengra=tedq_b200.ctg_compat, requires_grad=False)
 
-Forward values only: the reference differentiates through its tree with the autograd tape of torch.tensordot;
-this engine has no backward through the contraction tree yet (gradients: ``backend="pytorch_b200"``, whose
-backward is the adjoint sweep), so arrays that require grad are refused instead of silently detached.
+``contract`` is differentiable with respect to every operand that requires grad (the reference's back_prop runs
+torch's tape through tree.contract): the backward is the engine's reverse pass over the same tree
+(tq_tn_plan_enable_backward / tq_tn_backward), unsliced plans only — a sliced tree refuses operands that require
+grad instead of silently detaching them.
 """
 from __future__ import annotations
 
@@ -59,15 +60,29 @@ class B200OptTN:
                                            [False] * len(self.inputs), key)
         return self._plans[key]
 
+    def _plan_bwd(self, dtype, needs) -> capi.TnPlan:
+        key = (capi.TQ_C64 if dtype == torch.complex64 else capi.TQ_C128, tuple(bool(b) for b in needs))
+        if key not in self._plans:
+            plan = capi.TnPlan(self.inputs, self.output, self.info.path, self.info.sliced, [False] * len(self.inputs),
+                               key[0])
+            plan.enable_backward(key[1])
+            self._plans[key] = plan
+        return self._plans[key]
+
     def contract(self, arrays, backend: str = "torch", prefer_einsum: bool = True, **_ignored) -> torch.Tensor:
         if backend != "torch":
             raise ValueError("B200OptTN.contract: only backend='torch' (device tensors) is supported")
         if len(arrays) != len(self.inputs):
             raise ValueError(f"expected {len(self.inputs)} arrays, got {len(arrays)}")
         if any(getattr(a, "requires_grad", False) for a in arrays) and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "B200OptTN.contract is forward-only: compile the reference backend with requires_grad=False, or use "
-                "backend='pytorch_b200' (adjoint-sweep gradients)")
+            if self.info.sliced:
+                raise NotImplementedError(
+                    "B200OptTN.contract: a sliced tree has no reverse pass; drop slicing_opts, compile the reference "
+                    "backend with requires_grad=False, or use backend='pytorch_b200'")
+            return _TreeContract.apply(self, *arrays)
+        return self._contract_values(arrays)
+
+    def _contract_values(self, arrays) -> torch.Tensor:
         dtype = arrays[0].dtype
         if dtype not in (torch.complex64, torch.complex128):
             raise ValueError(f"complex64 / complex128 operands expected, got {dtype}")
@@ -87,6 +102,57 @@ class B200OptTN:
             plan.contract(ptrs, np.zeros(len(keep), dtype=np.int64), 1, 0, plan.n_slices, out.data_ptr(), ws.data_ptr(),
                           ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
         return out.reshape((2,) * len(self.output)) if self.output else out.reshape(())
+
+
+class _TreeContract(torch.autograd.Function):
+    """tree.contract with a backward: the reverse pass of the engine over the same contraction tree."""
+
+    @staticmethod
+    def forward(ctx, tree, *arrays):
+        dtype = arrays[0].dtype
+        dev = arrays[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("B200OptTN.contract needs CUDA tensors: the engine has no CPU fallback")
+        needs = [bool(a.requires_grad) for a in arrays]
+        plan = tree._plan_bwd(dtype, needs)
+        keep = [a.detach().to(dtype).contiguous() for a in arrays]
+        out = torch.zeros((1, 1 << len(tree.output)), dtype=dtype, device=dev)
+        ws_bytes = plan.workspace_bytes(1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ptrs = np.array([a.data_ptr() for a in keep], dtype=np.int64)
+        strides = np.zeros(len(keep), dtype=np.int64)
+        with torch.cuda.device(dev):
+            plan.contract(ptrs, strides, 1, 0, 1, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                          torch.cuda.current_stream(dev).cuda_stream)
+        ctx.tree, ctx.plan, ctx.keep, ctx.ws, ctx.needs = tree, plan, keep, ws, needs
+        ctx.ptrs, ctx.strides, ctx.shapes = ptrs, strides, [tuple(a.shape) for a in arrays]
+        return out.reshape((2,) * len(tree.output)) if tree.output else out.reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        tree, plan, ws = ctx.tree, ctx.plan, ctx.ws
+        dev = ws.device
+        dtype = ctx.keep[0].dtype
+        gout = dout.to(dtype).contiguous().reshape(1, -1)
+        with torch.cuda.device(dev):
+            plan.backward(ctx.ptrs, ctx.strides, 1, gout.data_ptr(), ws.data_ptr(), ws.numel(),
+                          torch.cuda.current_stream(dev).cuda_stream)
+        shared_off, perset_off, _ = plan.workspace_layout()
+        pad = (-ws.data_ptr()) % 256
+        esz = ctx.keep[0].element_size()
+        flat = ws[pad:pad + (ws.numel() - pad) // esz * esz].view(dtype)
+        grads = []
+        for t, need in enumerate(ctx.needs):
+            if not need:
+                grads.append(None)
+                continue
+            rank = len(tree.inputs[t])
+            off, space, bits = plan.grad_info(t, rank)
+            base = (shared_off if space == -1 else perset_off) // esz + off
+            g = torch.as_strided(flat, (2,) * rank, tuple(1 << b for b in bits), base)
+            grads.append(g.conj().resolve_conj().reshape(ctx.shapes[t]).clone())   # the arena holds conj(dL/dT)
+        return (None, *grads)
 
 
 class _HyperOptimizer:
