@@ -516,7 +516,25 @@ def measure_tn_mode(name, steps, warmup, device):
     fwd_ms = ev0.elapsed_time(ev1) / steps
     plan = cc._tn._plan(0)
     kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
+    # the same step with the gradient taken by reverse mode through the contraction tree (tq_tn_backward)
+    cc_tree = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, dtype=cd,
+                                  hyper_opt={"max_repeats": 8, "tn_backward": "tree"})
+
+    def step_tree():
+        xx = x.clone().requires_grad_(True)
+        cc_tree.batched(xx).sum().backward()
+
+    for _ in range(warmup):
+        step_tree()
+    torch.cuda.synchronize(device)
+    ev0.record()
+    for _ in range(steps):
+        step_tree()
+    ev1.record()
+    torch.cuda.synchronize(device)
+    tree_ms = ev0.elapsed_time(ev1) / steps
     return {"value": nb / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "fwd_only_ms": fwd_ms,
+            "tree_backward_ms_per_step": tree_ms,
             "fwd_only_evals_per_s": nb / (fwd_ms * 1e-3),
             "steps_by_kernel": {k: kinds.count(k) for k in sorted(set(kinds))},
             "workload": f"{desc.split(',')[0]} in tensor-network mode, batch {nb}: fwd = contraction plan "

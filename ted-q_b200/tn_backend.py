@@ -167,8 +167,9 @@ class TNExecutor:
         return cache[i]
 
     def tree_backward_available(self) -> bool:
-        """Reverse mode through the contraction tree needs unsliced plans on one rank (hyper_opt["tn_backward"] =
-        "tree" | "adjoint" forces one of the two gradient paths; default: tree when available)."""
+        """Reverse mode through the contraction tree needs unsliced plans on one rank.  hyper_opt["tn_backward"] =
+        "tree" | "adjoint" forces one of the two gradient paths; default: the adjoint state-vector sweeps while a
+        state vector fits comfortably (<= 26 qubits: they are the cheaper gradient there), the tree beyond."""
         mode = self.ho.get("tn_backward")
         if mode == "adjoint":
             return False
@@ -176,7 +177,7 @@ class TNExecutor:
             any(self.gate_batched)
         if mode == "tree" and not ok:
             raise ValueError("tn_backward='tree' needs unsliced plans, trainable parameters and no measurement_parallel")
-        return ok
+        return ok and (mode == "tree" or self.n > 26)
 
     def _plan_bwd(self, i) -> capi.TnPlan:
         """Plan of network i with the reverse pass appended (forward-only calls keep the leaner plan)."""
