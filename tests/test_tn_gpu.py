@@ -238,3 +238,20 @@ def test_tree_backward_beyond_state_vector_reach():
         with torch.no_grad():
             fd = ((cc.batched(xp) - cc.batched(xm)) / (2 * eps)).reshape(2).cpu().numpy()
         assert np.abs(fd - g[:, j]).max() < 1e-7, (j, fd, g[:, j])
+
+
+@pytest.mark.parametrize("simplify", [False, True], ids=["dense", "simplified"])
+def test_tn_mode_without_parameters(simplify):
+    """Edge cases of the call contract in tensor-network mode: a circuit with zero parameters (called with no
+    arguments, compiled_circuit.py:412-413), every operand constant, one qubit untouched by any gate."""
+    b = W._Builder("noparam", 4)
+    for name, qs in (("Hadamard", [0]), ("CNOT", [0, 1]), ("T", [1]), ("SX", [2]), ("CZ", [1, 2]), ("S", [0])):
+        b.g(name, qs)
+    b.state()
+    spec = b.spec
+    circ = W.build_circuit(spec, qb)
+    ref = sv_ref.run_sv(circ, torch.zeros(0), torch.complex64, return_state=True).numpy()
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=simplify, hyper_opt={"max_repeats": 2})
+    got = cc().cpu().numpy()
+    assert got.shape == (1, 2, 2, 2, 2)
+    assert_close(got[0], ref.reshape(2, 2, 2, 2), 1e-6, "state")
