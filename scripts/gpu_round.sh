@@ -1,6 +1,9 @@
 set -x
-export TQ_BENCH_EXTRAS=none
-N=${NGPU:-8}
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 1 --workload c5 > gpurun_out/bench_n${N}_c5.json 2> gpurun_out/bench_n${N}_c5.err; tail -c 300 gpurun_out/bench_n${N}_c5.err; tail -1 gpurun_out/bench_n${N}_c5.json | cut -c 1-300
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n${N}_c2.json 2> gpurun_out/bench_n${N}_c2.err; tail -c 300 gpurun_out/bench_n${N}_c2.err; tail -1 gpurun_out/bench_n${N}_c2.json | cut -c 1-200
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 3 --warmup 3 --workload c3 > gpurun_out/bench_n${N}_c3.json 2> gpurun_out/bench_n${N}_c3.err; tail -c 300 gpurun_out/bench_n${N}_c3.err; tail -1 gpurun_out/bench_n${N}_c3.json | cut -c 1-200
+timeout 600 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -2
+TQ_BENCH_EXTRAS=c1,c3 timeout 600 python bench.py --steps 10 > gpurun_out/bench_v12.json 2> gpurun_out/bench_v12.err; tail -c 300 gpurun_out/bench_v12.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_v12.json'))
+print('c2', d['value'], d['ms_per_step'], d['roofline']['fwd_ms'], d['roofline']['bwd_ms'])
+for k,v in d['other_configs'].items(): print(k, round(v['value'],2), round(v['ms_per_step'],3), v['roofline']['fwd_ms'], v['roofline']['bwd_ms'])
+PY

