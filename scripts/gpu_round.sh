@@ -1,9 +1,9 @@
 set -x
-timeout 600 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -2
-TQ_BENCH_EXTRAS=c1,c3 timeout 600 python bench.py --steps 10 > gpurun_out/bench_v12.json 2> gpurun_out/bench_v12.err; tail -c 300 gpurun_out/bench_v12.err
+timeout 600 python -m pytest tests/test_tn_tc_gpu.py -x -q 2>&1 | tail -2
+timeout 300 python bench.py --workload c5 --steps 5 > gpurun_out/bench_c5_x.json 2> gpurun_out/bench_c5_x.err; tail -c 200 gpurun_out/bench_c5_x.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_v12.json'))
-print('c2', d['value'], d['ms_per_step'], d['roofline']['fwd_ms'], d['roofline']['bwd_ms'])
-for k,v in d['other_configs'].items(): print(k, round(v['value'],2), round(v['ms_per_step'],3), v['roofline']['fwd_ms'], v['roofline']['bwd_ms'])
+d=json.load(open('gpurun_out/bench_c5_x.json'))
+print(d['value'], d['ms_per_step'], d['per_slice_ms_profiled'])
+for r in d['step_table'][:9]: print(r.get('ms'), r.get('pack_ms'), r.get('M'), r.get('N'), r.get('K'))
 PY

@@ -1663,7 +1663,8 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
       pp.a.src_set_stride = T.swap ? sb : sa;
       pp.a.img = img_a;
       pp.a.img_z_stride = T.img_a_z;
-      pp.blocks_a = tc::pack_blocks(T.tiles_a, T.kblocks);
+      pp.nch_a = tc::pack_nch((int64_t)T.tiles_a * T.kblocks * nz, p->num_sms);
+      pp.blocks_a = tc::pack_blocks(T.tiles_a, T.kblocks, pp.nch_a);
       smem = 2 * (size_t)tc::A_CHUNK;
     }
     if (pack_b) {
@@ -1672,7 +1673,8 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
       pp.b.src_set_stride = T.swap ? sa : sb;
       pp.b.img = img_b;
       pp.b.img_z_stride = T.img_b_z;
-      pp.blocks_b = tc::pack_blocks(T.tiles_b, T.kblocks);
+      pp.nch_b = tc::pack_nch((int64_t)T.tiles_b * T.kblocks * nz, p->num_sms);
+      pp.blocks_b = tc::pack_blocks(T.tiles_b, T.kblocks, pp.nch_b);
       smem = std::max(smem, 2 * (size_t)tc::b_chunk_bytes(T.c_t));
     }
     tc::k_tc_pack<256><<<dim3((unsigned)(pp.blocks_a + pp.blocks_b), (unsigned)nz), 256, smem, st>>>(pp);

@@ -153,8 +153,15 @@ constexpr int PACK_NCH = 8;
 struct PackPair {
   PackParams a, b;
   int32_t blocks_a, blocks_b;
+  int32_t nch_a, nch_b;  // k-blocks per block (<= PACK_NCH): fewer when the operand is small, so that the grid
+                         // still covers the GPU several times over
 };
-inline int pack_blocks(int tiles, int kblocks) { return tiles * ((kblocks + PACK_NCH - 1) / PACK_NCH); }
+inline int pack_nch(int64_t chunks, int num_sms) {
+  int nch = PACK_NCH;
+  while (nch > 1 && chunks / nch < 6 * (int64_t)num_sms) nch >>= 1;
+  return nch;
+}
+inline int pack_blocks(int tiles, int kblocks, int nch) { return tiles * ((kblocks + nch - 1) / nch); }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
@@ -168,10 +175,11 @@ k_tc_pack(const __grid_constant__ PackPair pp) {
   const int plane = p.is_b ? b_plane_bytes(rows_t) : A_PLANE;
   const int chunk = 2 * plane;
   const uint32_t blk = blockIdx.x - (second ? (uint32_t)pp.blocks_a : 0u);
-  const uint32_t groups = ((uint32_t)p.kblocks + PACK_NCH - 1) / PACK_NCH;
-  const uint32_t kb0 = (blk % groups) * PACK_NCH;
+  const uint32_t per = (uint32_t)(second ? pp.nch_b : pp.nch_a);
+  const uint32_t groups = ((uint32_t)p.kblocks + per - 1) / per;
+  const uint32_t kb0 = (blk % groups) * per;
   const uint32_t tile = blk / groups;
-  const int nch = min(PACK_NCH, p.kblocks - (int)kb0);
+  const int nch = min((int)per, p.kblocks - (int)kb0);
   const uint32_t z = blockIdx.y;
   const uint32_t bb = z & ((1u << p.n_b) - 1u);
   const uint32_t set = z >> p.n_b;
