@@ -263,8 +263,10 @@ int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int6
  * gradient, the two contractions  g_A = g_C x B  and  g_B = A x g_C  of the CONJUGATED gradients g = conj(dL/dT)
  * (so that no operand has to be conjugated), plus the seed g_out = conj(grad_out); the schedule, the fused runs and
  * the arena layout are rebuilt for the combined list, forward intermediates that the reverse pass reads stay
- * alive.  Unsliced plans only.  Usage: tq_tn_contract(..., slices [0, 1), workspace W) then
- * tq_tn_backward(..., grad_out, the SAME workspace W).  Gradients stay in the workspace:
+ * alive.  Usage, per slice s: tq_tn_contract(..., slices [s, s + 1), workspace W) then
+ * tq_tn_backward(..., s, grad_out, the SAME workspace W); gradients of the slices add up (the contraction is a sum
+ * over slices), a sliced index of an input is fixed per slice and absent from its gradient tensor (bit -1 in
+ * tq_tn_grad_info).  Gradients stay in the workspace:
  *   tq_tn_workspace_layout -> byte offsets of the shared / per-set arenas and the per-set stride (complex entries)
  *   tq_tn_grad_info(t)     -> element offset, arena (-1 shared, -2 per set) and, for the i-th index of input t's
  *                             own list, its bit inside the gradient tensor (entries are conj(dL/dT)).
@@ -273,7 +275,7 @@ int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int6
  * grad_params [batch][n_params] is accumulated (+=), the caller zeroes it. */
 int tq_tn_plan_enable_backward(tq_tn_plan* plan, const int32_t* input_needs_grad);
 int tq_tn_backward(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
-                   const void* grad_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+                   int64_t slice, const void* grad_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 int tq_tn_grad_info(const tq_tn_plan* plan, int32_t t, int64_t* offset, int32_t* space, int32_t* bits);
 int tq_tn_workspace_layout(const tq_tn_plan* plan, int64_t* shared_off, int64_t* perset_off, int64_t* set_stride);
 int tq_tn_param_grads(const tq_plan* plan, const void* params, int64_t batch, const void* arena, int64_t set_stride,

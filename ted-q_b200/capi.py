@@ -136,7 +136,7 @@ def lib() -> C.CDLL:
     L.tq_tn_contract.restype = i32
     L.tq_tn_plan_enable_backward.argtypes = [vp, pi32]
     L.tq_tn_plan_enable_backward.restype = i32
-    L.tq_tn_backward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, vp, vp, sz, vp]
+    L.tq_tn_backward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, vp, sz, vp]
     L.tq_tn_backward.restype = i32
     L.tq_tn_grad_info.argtypes = [vp, i32, C.POINTER(i64), pi32, pi32]
     L.tq_tn_grad_info.restype = i32
@@ -403,9 +403,9 @@ class TnPlan:
               "tq_tn_plan_enable_backward")
         self.has_backward = True
 
-    def backward(self, input_ptrs, input_strides, batch, grad_out_ptr, ws_ptr, ws_bytes, stream):
+    def backward(self, input_ptrs, input_strides, batch, grad_out_ptr, ws_ptr, ws_bytes, stream, slice_id=0):
         ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
-        check(lib().tq_tn_backward(self.handle, ptrs, strides, batch, grad_out_ptr, ws_ptr, ws_bytes, stream),
+        check(lib().tq_tn_backward(self.handle, ptrs, strides, batch, slice_id, grad_out_ptr, ws_ptr, ws_bytes, stream),
               "tq_tn_backward")
 
     def grad_info(self, t, rank):

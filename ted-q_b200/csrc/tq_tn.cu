@@ -1364,7 +1364,12 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
     p->t_batch[t] = p->in_batched[t];
     p->t_rank[t] = p->in_rank[t];
     p->width = std::max(p->width, p->in_rank[t]);
-    for (int pos = p->in_rank[t] - 1; pos >= 0; --pos) p->layout[t].push_back(tensor_idx[tensor_off[t] + pos]);
+    for (int pos = p->in_rank[t] - 1; pos >= 0; --pos) {  // a sliced index keeps its physical bit: placeholder -1
+      const int ix = tensor_idx[tensor_off[t] + pos];
+      bool is_sliced = false;
+      for (int j = 0; j < n_sliced; ++j) is_sliced |= sliced[j] == ix;
+      p->layout[t].push_back(is_sliced ? -1 : ix);
+    }
   }
   for (int t : p->slice_tensor) p->t_slice[t] = 1;
   p->n_fwd = n_steps;
@@ -1394,18 +1399,21 @@ static int make_grad_step(tq_tn_plan* p, int lhs, int rhs, const std::vector<int
                           std::vector<int>& out_layout) {
   const std::vector<int>&L = p->layout[lhs], &Rr = p->layout[rhs];
   std::map<int, int> posR;
-  for (size_t i = 0; i < Rr.size(); ++i) posR[Rr[i]] = (int)i;
+  for (size_t i = 0; i < Rr.size(); ++i)
+    if (Rr[i] >= 0) posR[Rr[i]] = (int)i;
   std::set<int> inL(L.begin(), L.end()), tgt(target.begin(), target.end());
+  tgt.erase(-1);  // sliced indices of an input are fixed per slice: not part of its gradient tensor
   memset(&st, 0, sizeof(st));
   st.lhs = lhs;
   st.rhs = rhs;
   std::vector<int> K, M, Bt, N;  // bit positions in L (K, M, Bt) / in R (N)
   for (size_t i = 0; i < L.size(); ++i) {
+    if (L[i] < 0) continue;
     if (posR.count(L[i])) (tgt.count(L[i]) ? Bt : K).push_back((int)i);
     else M.push_back((int)i);
   }
   for (size_t i = 0; i < Rr.size(); ++i)
-    if (!inL.count(Rr[i])) N.push_back((int)i);
+    if (Rr[i] >= 0 && !inL.count(Rr[i])) N.push_back((int)i);
   st.n_k = (int)K.size();
   st.n_m = (int)M.size();
   st.n_n = (int)N.size();
@@ -1436,7 +1444,6 @@ static int make_grad_step(tq_tn_plan* p, int lhs, int rhs, const std::vector<int
 
 int tq_tn_plan_enable_backward(tq_tn_plan* p, const int32_t* input_needs_grad) {
   TQ_REQUIRE(p && input_needs_grad, TQ_E_INVALID, "tq_tn_plan_enable_backward: null argument");
-  TQ_REQUIRE(p->n_sliced == 0, TQ_E_UNSUPPORTED, "tq_tn_plan_enable_backward: sliced plans have no reverse pass");
   TQ_REQUIRE(p->seed_step < 0, TQ_E_INVALID, "tq_tn_plan_enable_backward: already enabled");
   const int n_in = p->n_in, nf = p->n_fwd;
   std::vector<char> needs(n_in + nf, 0);
@@ -1495,7 +1502,8 @@ int tq_tn_grad_info(const tq_tn_plan* p, int32_t t, int64_t* offset, int32_t* sp
   const int r = (int)mine.size();
   for (int i = 0; i < r; ++i) {
     const int ix = mine[r - 1 - i];
-    bits[i] = -1;
+    bits[i] = -1;  // stays -1 for a sliced index (fixed per slice, absent from the gradient tensor)
+    if (ix < 0) continue;
     for (size_t j = 0; j < lay.size(); ++j)
       if (lay[j] == ix) bits[i] = (int32_t)j;
     TQ_REQUIRE(bits[i] >= 0, TQ_E_INVALID, "tq_tn_grad_info: index missing from the gradient tensor");
@@ -1913,9 +1921,9 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     return TQ_OK;
   };
   int rc;
-  if (backward) {  // reverse pass over the intermediates the forward call left in this workspace
+  if (backward) {  // reverse pass of slice s_begin over the intermediates its forward call left in this workspace
     for (const SchedItem& it : p->items[2])
-      if ((rc = run_item(it, 0))) return rc;
+      if ((rc = run_item(it, s_begin))) return rc;
     return TQ_OK;
   }
   // once-per-call items, then the slice loop
@@ -2012,11 +2020,11 @@ extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, co
 }
 
 extern "C" int tq_tn_backward(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
-                              int64_t batch, const void* grad_out, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              int64_t batch, int64_t slice, const void* grad_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   TQ_REQUIRE(p && p->seed_step >= 0, TQ_E_INVALID, "tq_tn_backward: call tq_tn_plan_enable_backward first");
   TQ_REQUIRE(grad_out, TQ_E_INVALID, "tq_tn_backward: grad_out is null");
-  return tn_contract_any(p, inputs, input_strides, batch, 0, 1, const_cast<void*>(grad_out), workspace,
+  return tn_contract_any(p, inputs, input_strides, batch, slice, slice + 1, const_cast<void*>(grad_out), workspace,
                          workspace_bytes, stream, nullptr, true);
 }
 

@@ -173,10 +173,10 @@ class TNExecutor:
         mode = self.ho.get("tn_backward")
         if mode == "adjoint":
             return False
-        ok = all(not info.sliced for info in self.infos) and not self.measurement_parallel and \
-            any(self.gate_batched)
+        ok = not self.contract_parallel and not self.measurement_parallel and any(self.gate_batched)
         if mode == "tree" and not ok:
-            raise ValueError("tn_backward='tree' needs unsliced plans, trainable parameters and no measurement_parallel")
+            raise ValueError("tn_backward='tree' needs trainable parameters and a single rank (no contract_parallel / "
+                             "measurement_parallel)")
         return ok and (mode == "tree" or self.n > 26)
 
     def _plan_bwd(self, i) -> capi.TnPlan:
@@ -193,13 +193,15 @@ class TNExecutor:
             cache[i] = plan
         return cache[i]
 
-    def _grad_tables(self, i, device):
-        """Per network, once: device int32 [n_gates, 16] tables (ket half, bra half) of the per-set-arena element
-        offset of every gate-tensor entry's gradient (-1: no such entry) for tq_tn_param_grads."""
+    def _grad_tables(self, i, device, slice_id=0):
+        """Per network and slice, once: device int32 [n_gates, 16] tables (ket half, bra half) of the per-set-arena
+        element offset of every gate-tensor entry's gradient (-1: no such entry — constant operand, entry removed
+        by tn_simplify, or an entry whose sliced index bits differ from this slice) for tq_tn_param_grads."""
         cache = self.__dict__.setdefault("_grad_tabs", {})
-        key = (i, str(device))
+        key = (i, str(device), int(slice_id))
         if key not in cache:
             net, plan = self.networks[i], self._plan_bwd(i)
+            sliced = list(self.infos[i].sliced)
             ng = len(self.backend._ir.gates)
             og = np.full((ng, 16), -1, dtype=np.int32)
             oa = np.full((ng, 16), -1, dtype=np.int32)
@@ -211,10 +213,17 @@ class TNExecutor:
                 off, space, bits = plan.grad_info(t, rank)
                 assert space == -2, "a batched operand's gradient lives in the per-set arena"
                 tab = og if kind == OPD_GATE else oa
+                ix = net.inputs[t]
                 for j in range(1 << rank):          # entry j of the (possibly reduced) operand tensor, C order
-                    e = off + sum(((j >> (rank - 1 - q)) & 1) << bits[q] for q in range(rank))
-                    full = rd[j] if rd is not None else j
-                    tab[ref, full] = e
+                    e, present = off, True
+                    for q in range(rank):
+                        bit = (j >> (rank - 1 - q)) & 1
+                        if bits[q] >= 0:
+                            e += bit << bits[q]
+                        elif bit != ((slice_id >> sliced.index(ix[q])) & 1):   # sliced index: fixed by the slice
+                            present = False
+                    if present:
+                        tab[ref, rd[j] if rd is not None else j] = e
             cache[key] = (torch.tensor(og, device=device), torch.tensor(oa, device=device))
         return cache[key]
 
@@ -251,7 +260,8 @@ class TNExecutor:
             self._table_device = dev
             tab = self._operand_tables(i, net, plan_sv, total)
             use_bwd = keep is not None and bool(tab["any_batched"])   # a constant network has no gradient
-            plan = self._plan_bwd(i) if use_bwd else self._plan(i)
+            # a sliced plan re-runs its forward slice by slice inside tree_backward: plain forward here
+            plan = self._plan_bwd(i) if use_bwd and not self.infos[i].sliced else self._plan(i)
             bases = np.array([cap0.data_ptr(), gm.data_ptr(), am.data_ptr(),
                               red_buf.data_ptr() if red_buf is not None else 0] + [o.data_ptr() for o in obs[i]],
                              dtype=np.int64)
@@ -270,7 +280,8 @@ class TNExecutor:
                     out.zero_()
                 torch.distributed.all_reduce(torch.view_as_real(out))
             if use_bwd:
-                keep.append((i, plan, ptrs, strides, ws, (gm, am, red_buf)))
+                keep.append((i, self._plan_bwd(i), ptrs, strides, None if self.infos[i].sliced else ws,
+                             (gm, am, red_buf)))
             if not any_b and B > 1:
                 out = out.expand(B, -1)
             results.append(out)
@@ -289,13 +300,21 @@ class TNExecutor:
         for i, plan, ptrs, strides, ws, _alive in kept:
             gi = dy[:, i].reshape(B, -1)
             gout = (gi if gi.is_complex() else gi.to(be._rdtype) + 0j).to(be._cdtype).contiguous()
-            og, oa = self._grad_tables(i, dev)
             _, perset_off, set_stride = plan.workspace_layout()
+            scratch = None
+            if ws is None:      # sliced plan: forward + reverse pass slice by slice, gradients add up
+                ws_bytes = plan.workspace_bytes(B)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                scratch = torch.zeros((B, 1 << plan.n_out), dtype=be._cdtype, device=dev)
+            base = (ws.data_ptr() + 255) // 256 * 256 + perset_off
             with torch.cuda.device(dev):
-                plan.backward(ptrs, strides, B, gout.data_ptr(), ws.data_ptr(), ws.numel(), stream)
-                base = (ws.data_ptr() + 255) // 256 * 256 + perset_off
-                capi.check(L.tq_tn_param_grads(plan_sv.handle, flat.data_ptr(), B, base, set_stride, og.data_ptr(),
-                                               oa.data_ptr(), grad.data_ptr(), stream), "tq_tn_param_grads")
+                for sl in range(plan.n_slices):
+                    if scratch is not None:
+                        plan.contract(ptrs, strides, B, sl, sl + 1, scratch.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+                    og, oa = self._grad_tables(i, dev, sl)
+                    plan.backward(ptrs, strides, B, gout.data_ptr(), ws.data_ptr(), ws.numel(), stream, sl)
+                    capi.check(L.tq_tn_param_grads(plan_sv.handle, flat.data_ptr(), B, base, set_stride, og.data_ptr(),
+                                                   oa.data_ptr(), grad.data_ptr(), stream), "tq_tn_param_grads")
         return grad
 
     # ------------------------------------------------------------------ amplitudes (C5)

@@ -196,7 +196,10 @@ def test_tree_backward_matches_adjoint_sweeps(seed, simplify, dt):
     circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=rd))
     x = torch.rand(3, spec["n_params"], dtype=rd, device="cuda") * 2 - 1
     res = []
-    for kw in ({}, {"tn_mode": True, "tn_simplify": simplify, "hyper_opt": {"max_repeats": 2, "tn_backward": "tree"}}):
+    slices = 4 if seed % 2 else 1     # odd seeds: sliced plans (forward + reverse pass slice by slice)
+    for kw in ({}, {"tn_mode": True, "tn_simplify": simplify,
+                    "hyper_opt": {"max_repeats": 2, "tn_backward": "tree",
+                                  "slicing_opts": {"target_num_slices": slices}}}):
         cc = circ.compilecircuit(backend="pytorch_b200", dtype=cdtype(dt), **kw)
         xx = x.clone().requires_grad_(True)
         y = cc.batched(xx)
@@ -210,9 +213,11 @@ def test_tree_backward_matches_adjoint_sweeps(seed, simplify, dt):
     assert_close(res[1][1], res[0][1], TOL[dt] * 4, "gradients")
 
 
-def test_tree_backward_beyond_state_vector_reach():
+@pytest.mark.parametrize("slices", [1, 4], ids=["unsliced", "sliced"])
+def test_tree_backward_beyond_state_vector_reach(slices):
     """Gradients of a 32-qubit circuit in tensor-network mode: no state vector exists (34 GB), the reverse pass runs
-    on the contraction tree; checked against central finite differences of the same contraction."""
+    on the contraction tree (slice by slice for a sliced plan); checked against central finite differences of the
+    same contraction."""
     n = 32
     b = W._Builder("chain32", n)
     for q in range(n):
@@ -224,7 +229,9 @@ def test_tree_backward_beyond_state_vector_reach():
     b.expval(["PauliZ", [n - 1]])
     spec = b.spec
     circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
-    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, dtype=torch.complex128, hyper_opt={"max_repeats": 4})
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, dtype=torch.complex128,
+                             hyper_opt={"max_repeats": 4, "slicing_opts": {"target_num_slices": slices}})
+    assert cc._tn.infos[0].n_slices >= slices
     x = torch.rand(2, spec["n_params"], dtype=torch.float64, device="cuda")
     xx = x.clone().requires_grad_(True)
     y = cc.batched(xx)
