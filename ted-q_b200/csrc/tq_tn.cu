@@ -358,6 +358,7 @@ __device__ __forceinline__ const cx<R>* fused_operand(const InputRef* __restrict
 // both operands come from shared-memory tables built once per step (low FUSE_KTAB_LOG2 bits; higher bits by
 // scatter per outer iteration) — the inner loop is 2 LDS + 2 LDG + 4 FMA instead of two bit-scatter loops.
 constexpr int FUSE_KTAB_LOG2 = 10;
+constexpr int FUSE_TABLE_WORK = 12;  // CTA steps with at least 2^12 MACs build offset tables in shared memory
 template <typename R, bool KTAB>
 __device__ __forceinline__ void fused_exec(const FusedStep& f, const InputRef* __restrict__ inputs, cx<R>* shared,
                                            cx<R>* perset, int64_t set, int64_t slice, int t, int G, int log2G,
@@ -491,6 +492,13 @@ k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ leve
       const int ncta = max(0, min(cta_end, c1) - c0);  // cta steps come first inside a level
       for (int i = (int)crank; i < ncta; i += CLUSTER) {
         const FusedStep& f = sdesc[i];
+        if (f.n_k + f.n_m + f.n_n + f.n_b < FUSE_TABLE_WORK) {
+          // medium step: the whole CTA, offsets by bit scatter — no tables, hence no barriers: independent steps
+          // of a level stream through back to back
+          fused_exec<R, false>(f, inputs, shared, perset, set, slice, (int)threadIdx.x, THREADS, LOG2T, nullptr,
+                               nullptr, nullptr, nullptr);
+          continue;
+        }
         const int n_lo = min((int)f.n_k, FUSE_KTAB_LOG2);
         for (int k = threadIdx.x; k < (1 << n_lo); k += THREADS) {
           ktab_a[k] = scat((uint32_t)k, f.a_bits, n_lo);
