@@ -1,13 +1,9 @@
 set -x
-timeout 600 python -m pytest tests/test_tn_fused_gpu.py tests/test_tn_gpu.py -x -q 2>&1 | tail -3
-timeout 300 python scripts/c2tn_run.py
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 10 --csv --log-file gpurun_out/launches_c2tn.csv python scripts/c2tn_run.py > /dev/null 2>&1
+timeout 600 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -2
+TQ_BENCH_EXTRAS=c1,c3,c2tn timeout 600 python bench.py --steps 10 > gpurun_out/bench_v13.json 2> gpurun_out/bench_v13.err; tail -c 300 gpurun_out/bench_v13.err
 python - <<'PY'
-import csv
-rows=list(csv.reader(open('gpurun_out/launches_c2tn.csv')))
-hi=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
-hdr=rows[hi]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value'); gi=hdr.index('Grid Size') if 'Grid Size' in hdr else None
-for r in rows[hi+2:hi+12]:
-    print(r[ki][:50], r[vi], r[gi] if gi else '')
+import json
+d=json.load(open('gpurun_out/bench_v13.json'))
+print('c2', d['value'], d['ms_per_step'], d['roofline']['fwd_ms'], d['roofline']['bwd_ms'], d['cpu_baseline']['sample'][-40:])
+for k,v in d['other_configs'].items(): print(k, round(v['value'],2), round(v['ms_per_step'],3), v.get('roofline',{}).get('fwd_ms'), v.get('roofline',{}).get('bwd_ms'))
 PY
-timeout 300 python scripts/c5_simplified.py 64 1 2>&1 | grep -E "amp|profiled" | tail -2
