@@ -1,0 +1,35 @@
+"""Multi-GPU sanity (torchrun, NCCL): measurement-parallel tensor-network mode and slice-parallel amplitudes give
+the single-rank numbers.  Prints OK lines on rank 0."""
+import os, sys
+sys.path.insert(0, ".")
+import numpy as np, torch, torch.distributed as dist
+import tedq_b200 as qb
+from tedq_b200 import workloads as W
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank = dist.get_rank()
+# 1. measurements dealt to ranks (C3-shaped: HEA with one Z expval per qubit)
+spec = W.hea(8, 3)
+circ = W.build_circuit(spec, qb)
+x = torch.tensor(np.random.RandomState(0).rand(5, spec["n_params"]), dtype=torch.float32, device="cuda")
+ref = circ.compilecircuit(backend="pytorch_b200").batched(x)
+cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, hyper_opt={"max_repeats": 2, "measurement_parallel": True})
+got = cc.batched(x)
+err1 = float((got - ref).abs().max())
+# 2. slices dealt to ranks, one all-reduce (C5-shaped, small lattice)
+spec = W.lattice_rcs(4, 4, 6, seed=2, measure="state")
+circ = W.build_circuit(spec, qb)
+bits = [1, 0] * 8
+one = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                          hyper_opt={"max_repeats": 4, "slicing_opts": {"target_num_slices": 8}})
+par = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                          hyper_opt={"max_repeats": 4, "slicing_opts": {"target_num_slices": 8, "contract_parallel": True}})
+a1, a2 = complex(one.amplitude(bits).cpu()), complex(par.amplitude(bits).cpu())
+err2 = abs(a1 - a2) / abs(a1)
+if rank == 0:
+    print("measurement_parallel max err %.2e %s" % (err1, "OK" if err1 < 1e-5 else "FAIL"))
+    print("contract_parallel rel err %.2e %s" % (err2, "OK" if err2 < 1e-5 else "FAIL"))
+dist.destroy_process_group()
