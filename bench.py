@@ -298,6 +298,10 @@ def measure_workload(name, steps, warmup, device, dist_on, world, do_e2e=True, d
 
 
 C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "64")),
+            "reconf_sweeps": int(os.environ.get("TQ_C5_RECONF", "6")),   # subtree reconfiguration of the greedy tree
+            # objective of the reconfiguration: estimated step time = max(flops / 200 TFLOP/s, bytes / 2.5 TB/s) +
+            # 12 us per launched step (planner.step_time_model), instead of the bare flop count
+            "time_model": None if os.environ.get("TQ_C5_TIME_MODEL", "1") == "0" else (2.0e14, 2.5e12, 1.2e-5),
             "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64}}
 
 
@@ -326,8 +330,10 @@ def c5_cpu_slices(n_slices_timed, slice_ids=None):
     cap0 = np.array([1, 0], dtype=np.complex64)
     inputs = [list(t) for t in inputs] + [[ix] for ix in output]
     arrays = list(arrays) + [cap0] * 40
-    info = planner.find_path(inputs, [], repeats=C5_HYPER["max_repeats"], seed=0)
-    info = planner.slice_path(inputs, [], info, target_size_log2=27, target_num_slices=64)
+    info = planner.find_path(inputs, [], repeats=C5_HYPER["max_repeats"], seed=0, reconf_sweeps=C5_HYPER["reconf_sweeps"],
+                             time_model=C5_HYPER["time_model"])
+    info = planner.slice_path(inputs, [], info, target_size_log2=27, target_num_slices=64,
+                              reconf_sweeps=min(3, C5_HYPER["reconf_sweeps"]), time_model=C5_HYPER["time_model"])
     ids = list(slice_ids) if slice_ids is not None else list(range(n_slices_timed))
     tn_ref.contract_slice_torch(arrays, inputs, [], info.path, info.sliced, 0)   # warm-up (threads, allocator)
     amps = []
@@ -338,7 +344,7 @@ def c5_cpu_slices(n_slices_timed, slice_ids=None):
     return dt, amps, info.n_slices, 2.0 ** info.flops_log2
 
 
-def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
+def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=False):
     """BASELINE config 5: 40-qubit lattice random circuit (5x8, 12 cycles), single amplitude <0..0|U|0..0>, sliced
     contraction; slices are sharded over ranks and combined with one all-reduce (strong scaling)."""
     import tedq_b200 as qb
@@ -346,7 +352,10 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
 
     spec = W.lattice_rcs(5, 8, 12, seed=0)
     circ = W.build_circuit(spec, qb)
-    hyper = {"max_repeats": C5_HYPER["max_repeats"],
+    # greedy_plan: the plain 64-repeat greedy tree (no reconfiguration): 2.5x the flops in larger, squarer GEMMs —
+    # the plan on which the tensor-core kernels are closest to their roofline
+    hyper = {"max_repeats": C5_HYPER["max_repeats"], "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
+             "time_model": None if greedy_plan else C5_HYPER["time_model"],
              "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=dist_on)}
     cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
     bits = [0] * 40
@@ -434,12 +443,13 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False):
     if do_cpu:
         dt, amps, n_slices, fl_slice = c5_cpu_slices(int(os.environ.get("TQ_C5_CPU_SLICES", "4")))
         got = [complex(cc.amplitude(bits, slice_range=(i, i + 1)).cpu()) for i in range(len(amps))]
-        err = max(abs(g - a) / abs(a) for g, a in zip(got, amps))
+        scale = max(abs(a) for a in amps) or 1.0     # a slice can be exactly zero (a sliced wire next to a |0> cap)
+        err = max(abs(g - a) / scale for g, a in zip(got, amps))
         res["cpu_baseline"] = {
             "value": 1.0 / (dt * n_slices), "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{len(amps)} of {n_slices} slices contracted with torch.tensordot complex64 on the host "
                       f"({dt:.2f} s per slice, {fl_slice / dt / 1e9:.0f} GFLOP/s), extrapolated x{n_slices}; host has "
-                      f"{os.cpu_count()} logical cores; max relative |gpu-cpu| on those slice amplitudes = {err:.2e}"}
+                      f"{os.cpu_count()} logical cores; max |gpu-cpu| on those slice amplitudes relative to the largest = {err:.2e}"}
     return res
 
 
@@ -550,7 +560,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c4d20,c4tn,c5,c5s"),
+    ap.add_argument("--extras", default=os.environ.get("TQ_BENCH_EXTRAS", "c2tn,c1,c3,c4,c4d20,c4tn,c5,c5g,c5s"),
                     help="other BASELINE configs measured briefly and reported inside the same JSON line")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
@@ -603,6 +613,13 @@ def main():
                                 "steps_per_slice": r["steps_per_slice"], "amplitude": r["amplitude"]}
                 if "cpu_baseline" in r:
                     extras[name]["cpu_baseline"] = r["cpu_baseline"]
+                continue
+            if name == "c5g":
+                r = measure_c5(3, 1, device, False, 1, do_cpu=False, greedy_plan=True)
+                extras[name] = {"value": r["value"], "unit": "evals/s", "ms_per_step": r["ms_per_step"],
+                                "workload": r["desc"] + " (plain greedy tree, no subtree reconfiguration)",
+                                "roofline": r["roofline"], "dtype": "c64", "step_table": r["step_table"][:8],
+                                "per_slice_ms_profiled": r["per_slice_ms_profiled"], "amplitude": r["amplitude"]}
                 continue
             if name == "c5s":
                 extras[name] = measure_c5_simplified(20, 3, device)

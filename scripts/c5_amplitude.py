@@ -21,7 +21,7 @@ spec = W.lattice_rcs(rows_, cols_, cyc, seed=0)
 circ = W.build_circuit(spec, qb)
 t = time.time()
 cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
-                         hyper_opt={"max_repeats": reps, "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64},
+                         hyper_opt={"max_repeats": reps, "reconf_sweeps": int(sys.argv[3]) if len(sys.argv) > 3 else 0, "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64},
                                     "engine_opts": {capi.TN_OPT_TENSOR_CORE: use_tc}})
 print("compile %.2fs" % (time.time() - t))
 bits = [0] * 40

@@ -1645,13 +1645,13 @@ static int tc_setup_once() {
   static int done = 0;
   if (done) return TQ_OK;
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::SMEM_BUDGET + 1024));
+                                  tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::SMEM_BUDGET + 1024));
+                                  tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::SMEM_BUDGET + 1024));
+                                  tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::SMEM_BUDGET + 1024));
+                                  tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_pack<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   done = 1;
   return TQ_OK;
@@ -1731,7 +1731,7 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   }
   const int64_t total = (int64_t)T.tiles_a * T.tiles_b * nz * splits;
   const unsigned grid = (unsigned)std::min<int64_t>(total, p->num_sms);
-  const size_t smem = tc::SMEM_BUDGET + 1024;
+  const size_t smem = tc::GEMM_SMEM;
   switch (T.c_t) {
     case 16: tc::k_tc_gemm<16><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
     case 32: tc::k_tc_gemm<32><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;

@@ -26,6 +26,7 @@ namespace tq {
 namespace tc {
 
 constexpr int ROWS = 128;                 // accumulator rows per tile (TMEM lanes)
+constexpr int ACC_WARPS_MAX = 8;
 #ifndef TQ_TC_KB_LOG
 #define TQ_TC_KB_LOG 3
 #endif
@@ -40,7 +41,11 @@ constexpr int A_PLANE = ROWS * ROW_BYTES; // one plane (hi or lo) of an A tile
 constexpr int A_CHUNK = 2 * A_PLANE;      // hi + lo
 constexpr int ACC_WARPS = 8;              // accumulation / epilogue warps (two per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 64 + 32 * ACC_WARPS;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 accumulate
-constexpr int SMEM_BUDGET = 220 * 1024;
+constexpr int SMEM_BUDGET = 200 * 1024;    // operand stages
+constexpr int EPI_PITCH = 80;             // bytes per staged row piece (64 data + 16 pad: conflict-free quarter-warps)
+constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
+constexpr int EPI_BYTES = ACC_WARPS_MAX * EPI_WARP_BYTES;  // epilogue staging, after the operand stages
+constexpr int GEMM_SMEM = SMEM_BUDGET + EPI_BYTES + 1024;
 
 __host__ __device__ inline int b_plane_bytes(int c_t) { return 2 * c_t * ROW_BYTES; }  // Re rows + Im rows
 __host__ __device__ inline int b_chunk_bytes(int c_t) { return 2 * b_plane_bytes(c_t); }
@@ -295,6 +300,7 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(g_smem) + 1023u) & ~1023u;
+  uint8_t* epi_smem = g_smem + (smem0 - smem_u32(g_smem)) + SMEM_BUDGET;  // after the operand stages
   const int S = p.stages;
   constexpr uint32_t sbytes = (uint32_t)(A_CHUNK + 4 * C_T * ROW_BYTES);
   constexpr uint32_t b_plane = (uint32_t)(2 * C_T * ROW_BYTES);
@@ -441,9 +447,28 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
       float2* dst = p.c + split * p.c_split_stride + set * p.c_set_stride + bb * p.c_bb_stride + row * p.c_rs +
                     col0 * p.c_cs;
       if (p.c_cs == 1) {
+        // Row-major result: a lane owns a row, so direct stores would touch 32 rows with 16 bytes each per
+        // instruction.  Stage 64-byte row pieces in shared memory and let 4 lanes write one row's piece: every
+        // store instruction covers 8 rows x 64 contiguous bytes (full sectors).
+        uint8_t* stg = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+        float2* tile0 = p.c + split * p.c_split_stride + set * p.c_set_stride + bb * p.c_bb_stride +
+                        (ta * ROWS + q * 32) * p.c_rs + col0;
 #pragma unroll
-        for (int j = 0; j < HALF; j += 2)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(acc_re[j], acc_im[j], acc_re[j + 1], acc_im[j + 1]);
+        for (int j0 = 0; j0 < HALF; j0 += 8) {
+          float4* mine = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            mine[c4] = make_float4(acc_re[j0 + 2 * c4], acc_im[j0 + 2 * c4], acc_re[j0 + 2 * c4 + 1],
+                                   acc_im[j0 + 2 * c4 + 1]);
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int row_l = rr * 8 + (lane >> 2), c4 = lane & 3;
+            const float4 v = *reinterpret_cast<const float4*>(stg + row_l * EPI_PITCH + c4 * 16);
+            *reinterpret_cast<float4*>(tile0 + (int64_t)row_l * p.c_rs + j0 + 2 * c4) = v;
+          }
+          __syncwarp();
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < HALF; ++j) dst[j * p.c_cs] = make_float2(acc_re[j], acc_im[j]);

@@ -159,8 +159,164 @@ def sequential_path(n_inputs: int):
     return path
 
 
+def step_time_model(n_a: int, n_b: int, n_out: int, n_union: int, model) -> float:
+    """Estimated seconds of one pairwise step on the engine: max(complex-GEMM time, HBM time) + launch overhead.
+    model = (algorithmic flop/s, bytes/s, seconds per step); ranks are log2 element counts (complex64)."""
+    f, bw, t0 = model
+    if n_union <= 14:        # small steps ride in a fused run: no launch of their own
+        return 1e-7
+    return max(8.0 * 2.0 ** n_union / f, 8.0 * (2.0 ** n_a + 2.0 ** n_b + 2.0 ** n_out) / bw) + t0
+
+
+def reconfigure(inputs, output, path, max_leaves: int = 8, sweeps: int = 3, sliced=(), time_model=None):
+    """Subtree reconfiguration: for every node of the contraction tree, cut out the subtree spanned by its
+    ``max_leaves`` largest descendants, find the cheapest order of contracting those leaves by dynamic programming
+    over subsets (cost = sum of 2^|indices of the pair|), and splice it in when it beats the current order.
+    Repeats for ``sweeps`` passes or until nothing improves.  ``sliced`` indices are treated as fixed (dropped), so
+    the same routine re-optimises the per-slice tree after slicing.  ``time_model`` (see step_time_model) replaces
+    the flop count by an estimate of the step's run time, which keeps the tree away from long chains of skinny,
+    bandwidth-bound steps that a pure flop count likes.  -> ssa path over the same inputs."""
+    import sys
+
+    n_in = len(inputs)
+    if n_in < 3:
+        return list(path)
+    sl = set(sliced)
+    children = {n_in + k: (a, b) for k, (a, b) in enumerate(path)}
+    root = n_in + len(path) - 1
+    count: Dict[int, int] = {}
+    for t in inputs:
+        for ix in t:
+            if ix not in sl:
+                count[ix] = count.get(ix, 0) + 1
+    for ix in output:
+        count[ix] = count.get(ix, 0) + 1
+    sys.setrecursionlimit(max(10000, 4 * n_in))
+
+    def compute_sets():
+        """index set of every node and, per node, how many leaves below it carry each index"""
+        sets, inside = {}, {}
+        stack = [(root, False)]
+        while stack:
+            v, done = stack.pop()
+            if v < n_in:
+                s = frozenset(ix for ix in inputs[v] if ix not in sl)
+                sets[v] = s
+                inside[v] = {ix: 1 for ix in s}
+            elif not done:
+                stack.append((v, True))
+                stack.append((children[v][0], False))
+                stack.append((children[v][1], False))
+            else:
+                a, b = children[v]
+                m = dict(inside[a])
+                for ix, c in inside[b].items():
+                    m[ix] = m.get(ix, 0) + c
+                inside[v] = m
+                sets[v] = frozenset(ix for ix, c in m.items() if c < count[ix])
+        return sets, inside
+
+    def pair_cost(sa, sb, so):
+        if time_model is None:
+            return 2.0 ** len(sa | sb)
+        return step_time_model(len(sa), len(sb), len(so), len(sa | sb), time_model)
+
+    next_id = max(children) + 1
+    for _ in range(max(1, sweeps)):
+        sets, inside = compute_sets()
+        improved = False
+        for v in sorted(children, key=lambda u: -len(sets[u])):
+            if v not in children:
+                continue
+            frontier, internal = [v], []
+            while len(frontier) < max_leaves:
+                cand = [u for u in frontier if u in children]
+                if not cand:
+                    break
+                u = max(cand, key=lambda w: len(sets[w]))
+                frontier.remove(u)
+                internal.append(u)
+                frontier += list(children[u])
+            L = len(frontier)
+            if L < 3:
+                continue
+            cur = sum(pair_cost(sets[children[u][0]], sets[children[u][1]], sets[u]) for u in internal)
+            full = (1 << L) - 1
+            insm = {1 << i: inside[frontier[i]] for i in range(L)}
+            sidx = {1 << i: sets[frontier[i]] for i in range(L)}
+            best = {1 << i: 0.0 for i in range(L)}
+            split = {}
+            for S in range(1, full + 1):
+                if S & (S - 1) == 0:
+                    continue
+                low = S & -S
+                m = dict(insm[S ^ low])
+                for ix, c in insm[low].items():
+                    m[ix] = m.get(ix, 0) + c
+                insm[S] = m
+                sidx[S] = frozenset(ix for ix, c in m.items() if c < count[ix])
+                b, bs = None, 0
+                sub = (S - 1) & S
+                while sub:
+                    if sub & low:   # canonical split: the lowest member stays in the first part
+                        o = S ^ sub
+                        c = best[sub] + best[o] + pair_cost(sidx[sub], sidx[o], sidx[S])
+                        if b is None or c < b:
+                            b, bs = c, sub
+                    sub = (sub - 1) & S
+                best[S], split[S] = b, bs
+            if best[full] >= cur * 0.999:
+                continue
+            improved = True
+            for u in internal:
+                del children[u]
+            stack = [(full, v)]      # rebuild the subtree under the same root id
+            while stack:
+                S, nid = stack.pop()
+                parts = []
+                for part in (split[S], S ^ split[S]):
+                    if part & (part - 1) == 0:
+                        parts.append(frontier[part.bit_length() - 1])
+                    else:
+                        parts.append(next_id)
+                        stack.append((part, next_id))
+                        next_id += 1
+                children[nid] = (parts[0], parts[1])
+            sets, inside = compute_sets()
+        if not improved:
+            break
+    new_path: List[Tuple[int, int]] = []
+    ids: Dict[int, int] = {}
+    stack = [(root, False)]
+    while stack:             # post-order: children before parents, ssa numbering
+        v, done = stack.pop()
+        if v < n_in:
+            ids[v] = v
+        elif not done:
+            stack.append((v, True))
+            stack.append((children[v][1], False))
+            stack.append((children[v][0], False))
+        else:
+            ids[v] = n_in + len(new_path)
+            new_path.append((ids[children[v][0]], ids[children[v][1]]))
+    return new_path
+
+
+def path_time(inputs, output, path, sliced, time_model) -> float:
+    """Estimated seconds of ONE slice of a path under ``time_model``."""
+    sl = set(sliced)
+    sets = [frozenset(ix for ix in t if ix not in sl) for t in inputs]
+    _, _, unions, results = path_cost(inputs, output, path, sliced)
+    total = 0.0
+    for (a, b), u, r in zip(path, unions, results):
+        total += step_time_model(len(sets[a]), len(sets[b]), len(r), len(u), time_model)
+        sets.append(r)
+    return total
+
+
 def find_path(inputs, output, repeats: int = 16, seed: int = 0, minimize: str = "flops",
-              alphas=(1.0, 0.5, 0.0), temperatures=(0.0, 0.3, 1.0)) -> PathInfo:
+              alphas=(1.0, 0.5, 0.0), temperatures=(0.0, 0.3, 1.0), reconf_sweeps: int = 0,
+              reconf_leaves: int = 8, time_model=None) -> PathInfo:
     """Best of ``repeats`` randomised greedy runs (first run is the deterministic alpha=1, T=0 greedy) and the
     time-ordered sequential path (deep circuits on few qubits: greedy merges wide, the sweep stays at width n)."""
     rng = random.Random(seed)
@@ -178,11 +334,15 @@ def find_path(inputs, output, repeats: int = 16, seed: int = 0, minimize: str = 
         if best is None or key < best[0]:
             best = (key, path, width, fl)
     _, path, width, fl = best
+    if reconf_sweeps > 0 and len(inputs) > 2:
+        path = reconfigure(inputs, output, path, max_leaves=reconf_leaves, sweeps=reconf_sweeps, time_model=time_model)
+        width, fl, _, _ = path_cost(inputs, output, path)
     return PathInfo(path, [], width, fl, len(path))
 
 
 def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] = None,
-               target_num_slices: int = 1, max_sliced: int = 24) -> PathInfo:
+               target_num_slices: int = 1, max_sliced: int = 24, reconf_sweeps: int = 0,
+               reconf_leaves: int = 8, time_model=None) -> PathInfo:
     """Greedy slicing: repeatedly fix the index that leaves the cheapest total work, until the largest
     intermediate of a slice has at most 2^target_size_log2 elements and there are >= target_num_slices slices."""
     sliced: List[int] = list(info.sliced)
@@ -215,5 +375,15 @@ def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] =
             if best is None or key < best[0]:
                 best = (key, ix)
         sliced.append(best[1])
-    width, fl, _, _ = path_cost(inputs, output, info.path, sliced)
-    return PathInfo(info.path, sliced, width, fl, len(info.path))
+    path = info.path
+    if reconf_sweeps > 0 and sliced and len(inputs) > 2:   # re-optimise the per-slice tree (sliced indices fixed)
+        cand = reconfigure(inputs, output, path, max_leaves=reconf_leaves, sweeps=reconf_sweeps, sliced=sliced,
+                           time_model=time_model)
+        w0, f0, _, _ = path_cost(inputs, output, path, sliced)
+        w1, f1, _, _ = path_cost(inputs, output, cand, sliced)
+        better = f1 < f0 if time_model is None else \
+            path_time(inputs, output, cand, sliced, time_model) < path_time(inputs, output, path, sliced, time_model)
+        if better and (target_size_log2 is None or w1 <= max(w0, target_size_log2)):
+            path = cand
+    width, fl, _, _ = path_cost(inputs, output, path, sliced)
+    return PathInfo(path, sliced, width, fl, len(path))

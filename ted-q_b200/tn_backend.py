@@ -54,13 +54,19 @@ class TNExecutor:
             else:
                 info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
                                          seed=int(self.ho.get("seed", 0)),
-                                         minimize=self.ho.get("minimize", "flops"))
+                                         minimize=self.ho.get("minimize", "flops"),
+                                         reconf_sweeps=int(self.ho.get("reconf_sweeps", 0)),
+                                         reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
+                                         time_model=self.ho.get("time_model"))
             tsize = so.get("target_size")
             tnum = int(so.get("target_num_slices", 1) or 1)
             if tsize or tnum > 1:
                 info = planner.slice_path(net.inputs, net.output, info,
                                           target_size_log2=int(np.log2(tsize)) if tsize else None,
-                                          target_num_slices=tnum)
+                                          target_num_slices=tnum,
+                                          reconf_sweeps=min(3, int(self.ho.get("reconf_sweeps", 0))),
+                                          reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
+                                          time_model=self.ho.get("time_model"))
             self.infos.append(info)
             self.plans.append(None)
         self._const = {}
@@ -329,13 +335,19 @@ class TNExecutor:
             net = amplitude_network(net0, [0] * self.n)
             so = self.ho.get("slicing_opts") or {}
             info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
-                                     seed=int(self.ho.get("seed", 0)), minimize=self.ho.get("minimize", "flops"))
+                                     seed=int(self.ho.get("seed", 0)), minimize=self.ho.get("minimize", "flops"),
+                                     reconf_sweeps=int(self.ho.get("reconf_sweeps", 0)),
+                                     reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
+                                     time_model=self.ho.get("time_model"))
             tsize = so.get("target_size")
             tnum = int(so.get("target_num_slices", 1) or 1)
             if tsize or tnum > 1:
                 info = planner.slice_path(net.inputs, net.output, info,
                                           target_size_log2=int(np.log2(tsize)) if tsize else None,
-                                          target_num_slices=tnum)
+                                          target_num_slices=tnum,
+                                          reconf_sweeps=min(3, int(self.ho.get("reconf_sweeps", 0))),
+                                          reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
+                                          time_model=self.ho.get("time_model"))
             self._amp = [net, info, None]
         return self._amp
 
