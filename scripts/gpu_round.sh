@@ -1,13 +1,10 @@
 set -x
-timeout 600 python -m pytest tests/test_tn_tc_gpu.py -x -q 2>&1 | tail -2
-timeout 100 python scripts/tc_gemm_single.py 15 8 7 32 3 | tail -1
-timeout 100 python scripts/tc_gemm_single.py 12 13 7 32 3 | tail -1
-timeout 100 python scripts/tc_gemm_single.py 11 10 13 32 3 | tail -1
-timeout 100 python scripts/tc_gemm_single.py 9 14 9 32 3 | tail -1
-timeout 600 python bench.py --workload c5 --steps 5 > gpurun_out/bench_c5_reconf.json 2> gpurun_out/bench_c5_reconf.err; tail -c 300 gpurun_out/bench_c5_reconf.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err; tail -c 300 gpurun_out/bench_final2.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_c5_reconf.json'))
-print(d['value'], d['ms_per_step'], d['per_slice_ms_profiled'])
-for r in d['step_table'][:8]: print(r.get('ms'), r.get('pack_ms'), r.get('M'), r.get('N'), r.get('K'), r.get('frac'))
+d=json.load(open('gpurun_out/bench_final2.json'))
+print('c2', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'cpu', d['cpu_baseline']['value'])
+for k,v in d['other_configs'].items(): print(k, round(v['value'],2), round(v['ms_per_step'],3), v.get('fwd_only_ms'), v.get('tree_backward_ms_per_step'), (v.get('roofline') or {}).get('dominant_steps_frac_of_complex_gemm_roofline'))
 PY

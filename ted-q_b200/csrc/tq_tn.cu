@@ -1848,19 +1848,22 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
       const int64_t nthr = (int64_t)1 << (ad.n_f + ad.n_b);
       const dim3 grid((unsigned)((nthr + 255) / 256), (unsigned)sets);
       TQ_REQUIRE(sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");
-      const int kc = ad.n_k <= 1 ? 0 : ad.n_k <= 2 ? 1 : 2, sc2 = ad.n_s <= 1 ? 0 : ad.n_s <= 2 ? 1 : 2;
+      const int kc = ad.n_k <= 1 ? 0 : ad.n_k - 1, sc2 = ad.n_s <= 1 ? 0 : ad.n_s - 1;  // classes 2, 4, 8, 16
 #define TQ_APPLY(KM, SM) k_tn_apply<R, KM, SM><<<grid, 256, 0, st>>>(sm, ssm, bg, sbg, c, sc, ad, nthr)
-      switch (kc * 3 + sc2) {
-        case 0: TQ_APPLY(2, 2); break;
-        case 1: TQ_APPLY(2, 4); break;
-        case 2: TQ_APPLY(2, 16); break;
-        case 3: TQ_APPLY(4, 2); break;
-        case 4: TQ_APPLY(4, 4); break;
-        case 5: TQ_APPLY(4, 16); break;
-        case 6: TQ_APPLY(16, 2); break;
-        case 7: TQ_APPLY(16, 4); break;
-        default: TQ_APPLY(16, 16); break;
+#define TQ_APPLY_ROW(KM)                 \
+  switch (sc2) {                         \
+    case 0: TQ_APPLY(KM, 2); break;      \
+    case 1: TQ_APPLY(KM, 4); break;      \
+    case 2: TQ_APPLY(KM, 8); break;      \
+    default: TQ_APPLY(KM, 16); break;    \
+  }
+      switch (kc) {
+        case 0: TQ_APPLY_ROW(2); break;
+        case 1: TQ_APPLY_ROW(4); break;
+        case 2: TQ_APPLY_ROW(8); break;
+        default: TQ_APPLY_ROW(16); break;
       }
+#undef TQ_APPLY_ROW
 #undef TQ_APPLY
     } else if (kernel == 3) {
       const int nblk = std::min(DOT_BLOCKS, 1 << (stp.n_k - DOT_LO));
