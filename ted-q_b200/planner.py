@@ -387,3 +387,37 @@ def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] =
             path = cand
     width, fl, _, _ = path_cost(inputs, output, path, sliced)
     return PathInfo(path, sliced, width, fl, len(path))
+
+
+def cached_plan(cache_dir, inputs, output, build, **key_args) -> PathInfo:
+    """On-disk plan cache ("plan cache keyed by the index-map hash"): ``build()`` -> PathInfo runs only
+    when no file for sha1(index maps, output, key_args) exists under ``cache_dir``; the stored plan is re-costed on
+    load, so a stale or foreign file cannot smuggle in a path that does not fit the network."""
+    import hashlib
+    import json
+    import os
+
+    if not cache_dir:
+        return build()
+    blob = json.dumps({"inputs": [list(map(int, t)) for t in inputs], "output": list(map(int, output)),
+                       "args": {k: (list(v) if isinstance(v, tuple) else v) for k, v in sorted(key_args.items())}},
+                      sort_keys=True).encode()
+    path = os.path.join(cache_dir, hashlib.sha1(blob).hexdigest() + ".json")
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                d = json.load(fh)
+            ssa = [tuple(p) for p in d["path"]]
+            sliced = [int(i) for i in d["sliced"]]
+            if len(ssa) == len(inputs) - 1:
+                width, fl, _, _ = path_cost(inputs, output, ssa, sliced)
+                return PathInfo(ssa, sliced, width, fl, len(ssa))
+        except (OSError, ValueError, KeyError, IndexError, TypeError):
+            pass
+    info = build()
+    os.makedirs(cache_dir, exist_ok=True)
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "w") as fh:
+        json.dump({"path": [list(p) for p in info.path], "sliced": list(info.sliced)}, fh)
+    os.replace(tmp, path)
+    return info

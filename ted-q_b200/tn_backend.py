@@ -52,24 +52,38 @@ class TNExecutor:
                 w, fl, _, _ = planner.path_cost(net.inputs, net.output, path)
                 info = planner.PathInfo(path, [], w, fl, len(path))
             else:
-                info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
-                                         seed=int(self.ho.get("seed", 0)),
-                                         minimize=self.ho.get("minimize", "flops"),
-                                         reconf_sweeps=int(self.ho.get("reconf_sweeps", 0)),
-                                         reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
-                                         time_model=self.ho.get("time_model"))
-            tsize = so.get("target_size")
-            tnum = int(so.get("target_num_slices", 1) or 1)
-            if tsize or tnum > 1:
-                info = planner.slice_path(net.inputs, net.output, info,
-                                          target_size_log2=int(np.log2(tsize)) if tsize else None,
-                                          target_num_slices=tnum,
-                                          reconf_sweeps=min(3, int(self.ho.get("reconf_sweeps", 0))),
-                                          reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
-                                          time_model=self.ho.get("time_model"))
+                info = planner.cached_plan(self.ho.get("plan_cache"), net.inputs, net.output,
+                                           lambda net=net: self._search(net), **self._plan_key())
             self.infos.append(info)
             self.plans.append(None)
         self._const = {}
+
+    def _plan_key(self):
+        so = self.ho.get("slicing_opts") or {}
+        return {"max_repeats": int(self.ho.get("max_repeats", 16)), "seed": int(self.ho.get("seed", 0)),
+                "minimize": self.ho.get("minimize", "flops"), "reconf_sweeps": int(self.ho.get("reconf_sweeps", 0)),
+                "reconf_leaves": int(self.ho.get("reconf_leaves", 8)), "time_model": self.ho.get("time_model"),
+                "target_size": so.get("target_size"), "target_num_slices": int(so.get("target_num_slices", 1) or 1)}
+
+    def _search(self, net) -> planner.PathInfo:
+        """Path search + slicing for one network (hyper_opt: max_repeats, seed, minimize, reconf_sweeps,
+        reconf_leaves, time_model, slicing_opts{target_size, target_num_slices})."""
+        so = self.ho.get("slicing_opts") or {}
+        info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
+                                 seed=int(self.ho.get("seed", 0)), minimize=self.ho.get("minimize", "flops"),
+                                 reconf_sweeps=int(self.ho.get("reconf_sweeps", 0)),
+                                 reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
+                                 time_model=self.ho.get("time_model"))
+        tsize = so.get("target_size")
+        tnum = int(so.get("target_num_slices", 1) or 1)
+        if tsize or tnum > 1:
+            info = planner.slice_path(net.inputs, net.output, info,
+                                      target_size_log2=int(np.log2(tsize)) if tsize else None,
+                                      target_num_slices=tnum,
+                                      reconf_sweeps=min(3, int(self.ho.get("reconf_sweeps", 0))),
+                                      reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
+                                      time_model=self.ho.get("time_model"))
+        return info
 
     # ------------------------------------------------------------------
     def _plan(self, i) -> capi.TnPlan:
@@ -333,21 +347,8 @@ class TNExecutor:
             else:
                 net0 = tn_index.index_maps(self.n, gq, [("state", None)])[0]
             net = amplitude_network(net0, [0] * self.n)
-            so = self.ho.get("slicing_opts") or {}
-            info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
-                                     seed=int(self.ho.get("seed", 0)), minimize=self.ho.get("minimize", "flops"),
-                                     reconf_sweeps=int(self.ho.get("reconf_sweeps", 0)),
-                                     reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
-                                     time_model=self.ho.get("time_model"))
-            tsize = so.get("target_size")
-            tnum = int(so.get("target_num_slices", 1) or 1)
-            if tsize or tnum > 1:
-                info = planner.slice_path(net.inputs, net.output, info,
-                                          target_size_log2=int(np.log2(tsize)) if tsize else None,
-                                          target_num_slices=tnum,
-                                          reconf_sweeps=min(3, int(self.ho.get("reconf_sweeps", 0))),
-                                          reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
-                                          time_model=self.ho.get("time_model"))
+            info = planner.cached_plan(self.ho.get("plan_cache"), net.inputs, net.output,
+                                       lambda: self._search(net), **self._plan_key())
             self._amp = [net, info, None]
         return self._amp
 

@@ -32,3 +32,25 @@ def test_reconfigured_path_is_valid_cheaper_and_equal(seed):
     total = sum(complex(tn_ref.contract_slice_torch(arrays, inputs, [], sliced.path, sliced.sliced, s, torch.complex128))
                 for s in range(sliced.n_slices))
     assert abs(total - a) < 1e-12
+
+
+def test_plan_cache_round_trip(tmp_path):
+    """hyper_opt["plan_cache"]: the second search of the same network reads the stored plan; a corrupt or foreign
+    file is ignored (the plan is re-costed against the network on load)."""
+    inputs = [[0, 1], [1, 2, 3], [2, 4], [3, 4, 5], [0, 5]]
+    calls = []
+
+    def build():
+        calls.append(1)
+        return planner.slice_path(inputs, [], planner.find_path(inputs, [], repeats=2), target_num_slices=2)
+
+    a = planner.cached_plan(str(tmp_path), inputs, [], build, max_repeats=2, target_num_slices=2)
+    b = planner.cached_plan(str(tmp_path), inputs, [], build, max_repeats=2, target_num_slices=2)
+    assert len(calls) == 1 and a.path == b.path and a.sliced == b.sliced and abs(a.flops_log2 - b.flops_log2) < 1e-12
+    planner.cached_plan(str(tmp_path), inputs, [], build, max_repeats=3, target_num_slices=2)   # other key: new search
+    assert len(calls) == 2
+    for f in tmp_path.iterdir():
+        f.write_text("{not json")
+    c = planner.cached_plan(str(tmp_path), inputs, [], build, max_repeats=2, target_num_slices=2)
+    assert len(calls) == 3 and c.path == a.path
+    assert planner.cached_plan(None, inputs, [], build).path == a.path and len(calls) == 4       # no cache dir: search
