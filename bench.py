@@ -486,7 +486,7 @@ def measure_c5_simplified(steps, warmup, device):
 def measure_tn_mode(name, steps, warmup, device):
     """BASELINE configs 2 and 4 in the mode they name: tensor-network contraction (tn_mode=True) through the public
     API — values from the contraction plan (one network per measurement, batched gate operands), gradient from the
-    adjoint sweeps (tn_backend._TNExecute)."""
+    adjoint sweeps (backend.B200Execute, B200Backend._vjp)."""
     import tedq_b200 as qb
     from tedq_b200 import workloads as W
 

@@ -2,7 +2,8 @@
 
 Import name is ``tedq_b200`` (the directory is ``ted-q_b200/``; ``tedq_b200/__init__.py`` at the repo
 root aliases it because a hyphen is not importable)."""
-from .backend import BACKEND_NAME, B200Backend, B200Execute, B200ParamShift  # noqa: F401
+from .backend import (BACKEND_NAME, QUDIO_BACKEND_NAME, B200Backend, B200Execute, B200Grad,  # noqa: F401
+                      B200ParamShift, B200QUDIOBackend)
 from .frontend import *  # noqa: F401,F403
 from .frontend import Circuit  # noqa: F401
 from .register import register_backend  # noqa: F401

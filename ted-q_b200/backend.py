@@ -49,17 +49,36 @@ def _is_functorch_wrapped(t) -> bool:
         return True
 
 
+def _fold_vmapped(info, in_dims, *tensors):
+    """vmap rule shared by every node: the ops are natively batched over dim 0, so the vmapped dimension is
+    folded into it ([V, B, ...] -> [V*B, ...]; an un-vmapped operand is repeated V times)."""
+    V = info.batch_size
+    out = []
+    for t, d in zip(tensors, in_dims):
+        t = t.unsqueeze(0).expand((V,) + tuple(t.shape)) if d is None else t.movedim(d, 0)
+        out.append(t.reshape((V * t.shape[1],) + tuple(t.shape[2:])))
+    return out, V
+
+
+def _unfold(t, V):
+    return t.reshape((V, t.shape[0] // V) + tuple(t.shape[1:]))
+
+
 class B200Execute(torch.autograd.Function):
-    """Adjoint-method autograd node.  ``apply(run_kwargs, flat)`` with ``flat`` = [B, P] real.
+    """Values of every measurement.  ``apply(run_kwargs, flat)`` with ``flat`` = [B, P] real.
 
     Calling convention follows TorchExecute (pytorch_backend.py:1191-1223): first argument is a dict
-    carrying the backend, ``backward`` returns ``(None, grads)``.
-    """
+    carrying the backend, ``backward`` returns ``(None, grads)``.  The gradient is the engine's reverse pass
+    (adjoint sweeps, or reverse mode through the contraction trees in tensor-network mode) on the state the
+    forward call kept.  When the gradient itself has to be differentiable (``create_graph=True``,
+    ``torch.func.hessian``/``jacrev``/``jacfwd``: Hessian_&_batch_executation notebook cells 24-30) ``backward``
+    returns the ``B200Grad`` node instead, whose own derivatives come from the parameter-shift identities of the
+    gate set (ops_abc.py:261-280, qubit.py:37-42) evaluated in batched launches."""
 
     @staticmethod
     def forward(run_kwargs, flat):
         backend = run_kwargs["backend"]
-        out, ws = backend._forward_device(flat, run_kwargs["need_grad"])
+        out, ws = backend._values(flat, run_kwargs["need_grad"])
         run_kwargs["_ws"] = ws
         return out
 
@@ -69,27 +88,123 @@ class B200Execute(torch.autograd.Function):
         ctx.backend = run_kwargs["backend"]
         ctx.ws = run_kwargs.pop("_ws", None)
         ctx.save_for_backward(flat)
+        ctx.save_for_forward(flat)
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         (flat,) = ctx.saved_tensors
-        if ctx.ws is None:
-            raise RuntimeError("backward through a circuit evaluated with requires_grad=False")
-        grad = ctx.backend._backward_device(flat, dy, ctx.ws)
-        ctx.ws = None
-        return None, grad
+        be = ctx.backend
+        plain = not (_is_functorch_wrapped(flat) or _is_functorch_wrapped(dy))
+        if plain and ctx.ws is not None and not (torch.is_grad_enabled() and (dy.requires_grad or flat.requires_grad)):
+            grad = be._vjp(flat, dy, ctx.ws)
+            ctx.ws = None
+            return None, grad
+        return None, B200Grad.apply({"backend": be}, flat, dy)
+
+    @staticmethod
+    def jvp(ctx, _, t_flat):
+        (flat,) = ctx.saved_tensors
+        jac = B200Jac.apply({"backend": ctx.backend}, flat)              # [B, n_meas, ..., P]
+        return torch.einsum("b...p,bp->b...", jac, t_flat.to(jac.dtype))
 
     @staticmethod
     def vmap(info, in_dims, run_kwargs, flat):
-        # the op is natively batched over dim 0: fold the vmapped dim into it
-        d = in_dims[1]
-        if d is None:
+        if in_dims[1] is None:
             return B200Execute.apply(run_kwargs, flat), None
-        flat = flat.movedim(d, 0)
-        lead = flat.shape[:2]
-        out = B200Execute.apply(dict(run_kwargs), flat.reshape(lead[0] * lead[1], flat.shape[2]))
-        return out.reshape(lead + out.shape[1:]), 0
+        (flat,), V = _fold_vmapped(info, in_dims[1:], flat)
+        return _unfold(B200Execute.apply(dict(run_kwargs), flat), V), 0
+
+
+class B200Grad(torch.autograd.Function):
+    """(flat [B, P], dy [B, n_meas, ...]) -> dy . J(flat)  [B, P], as a differentiable node: a forward pass and the
+    engine's reverse pass.  Its derivatives: d/dflat = the dy-weighted Hessian (``B200Hess``), d/ddy = J (``B200Jac``)."""
+
+    @staticmethod
+    def forward(run_kwargs, flat, dy):
+        return run_kwargs["backend"]._vjp_fresh(flat, dy)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        run_kwargs, flat, dy = inputs
+        ctx.backend = run_kwargs["backend"]
+        ctx.save_for_backward(flat, dy)
+        ctx.save_for_forward(flat, dy)
+
+    @staticmethod
+    def backward(ctx, u):
+        flat, dy = ctx.saved_tensors
+        rk = {"backend": ctx.backend}
+        g_flat = g_dy = None
+        if ctx.needs_input_grad[1]:
+            hess = B200Hess.apply(rk, flat, dy)                          # [B, P, P], symmetric
+            g_flat = torch.einsum("bjk,bj->bk", hess, u.to(hess.dtype))
+        if ctx.needs_input_grad[2]:
+            jac = B200Jac.apply(rk, flat)
+            g_dy = torch.einsum("b...p,bp->b...", jac, u.to(jac.dtype)).to(dy.dtype)
+        return None, g_flat, g_dy
+
+    @staticmethod
+    def jvp(ctx, _, t_flat, t_dy):
+        flat, dy = ctx.saved_tensors
+        rk = {"backend": ctx.backend}
+        out = 0
+        if t_flat is not None:
+            hess = B200Hess.apply(rk, flat, dy)
+            out = out + torch.einsum("bjk,bk->bj", hess, t_flat.to(hess.dtype))
+        if t_dy is not None:
+            out = out + B200Grad.apply(rk, flat, t_dy)
+        return out
+
+    @staticmethod
+    def vmap(info, in_dims, run_kwargs, flat, dy):
+        (flat, dy), V = _fold_vmapped(info, in_dims[1:], flat, dy)
+        return _unfold(B200Grad.apply(run_kwargs, flat, dy), V), 0
+
+
+class B200Hess(torch.autograd.Function):
+    """(flat, dy) -> H[b, j, k] = d(dy . J)_j / dflat_k from shifted gradient evaluations (one batched launch
+    sequence per chunk of shifts).  Third derivatives are not provided."""
+
+    @staticmethod
+    def forward(run_kwargs, flat, dy):
+        return run_kwargs["backend"]._shift_hessian(flat, dy)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("pytorch_b200: derivatives beyond second order are not implemented")
+
+    @staticmethod
+    def vmap(info, in_dims, run_kwargs, flat, dy):
+        (flat, dy), V = _fold_vmapped(info, in_dims[1:], flat, dy)
+        return _unfold(B200Hess.apply(run_kwargs, flat, dy), V), 0
+
+
+class B200Jac(torch.autograd.Function):
+    """flat -> J[b, m, ..., p] = d out[b, m, ...] / dflat_p from shifted forward evaluations in one batched launch
+    sequence (the rule of jacobian_param_shift, pytorch_backend.py:180-212)."""
+
+    @staticmethod
+    def forward(run_kwargs, flat):
+        return run_kwargs["backend"]._shift_jacobian(flat)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("pytorch_b200: derivatives beyond second order are not implemented")
+
+    @staticmethod
+    def vmap(info, in_dims, run_kwargs, flat):
+        if in_dims[1] is None:
+            return B200Jac.apply(run_kwargs, flat), None
+        (flat,), V = _fold_vmapped(info, in_dims[1:], flat)
+        return _unfold(B200Jac.apply(run_kwargs, flat), V), 0
 
 
 class B200ParamShift(torch.autograd.Function):
@@ -98,7 +213,7 @@ class B200ParamShift(torch.autograd.Function):
 
     @staticmethod
     def forward(run_kwargs, flat):
-        out, _ = run_kwargs["backend"]._forward_device(flat, False)
+        out, _ = run_kwargs["backend"]._values(flat, False)
         return out
 
     @staticmethod
@@ -214,30 +329,93 @@ class B200Backend:
             plan.backward(flat.data_ptr(), B, dy.data_ptr(), grad.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         return grad
 
+    # ---------------------------------------------------- mode-independent value / gradient primitives
+    def _values(self, flat, need_grad):
+        """[B, P] -> (stacked results [B, n_meas, ...], state kept for ``_vjp`` or None)."""
+        if self._tn is None:
+            return self._forward_device(flat, need_grad)
+        kept = [] if need_grad and self._tn.tree_backward_available() else None
+        out = self._tn._forward_values(flat, kept)
+        return out, (("tn", kept) if need_grad else None)
+
+    def _vjp(self, flat, dy, state):
+        """dy . J(flat) -> [B, P] from the state ``_values(flat, True)`` kept."""
+        if self._tn is None:
+            return self._backward_device(flat, dy, state)
+        kept = state[1]
+        if kept is not None:
+            return self._tn.tree_backward(flat.contiguous(), dy, kept)
+        if self._num_qubits > 26:
+            raise NotImplementedError("gradients of sliced networks beyond 26 qubits are not implemented")
+        _, ws = self._forward_device(flat, True)       # adjoint state-vector sweeps of the same engine
+        return self._backward_device(flat, dy, ws)
+
+    def _vjp_fresh(self, flat, dy):
+        flat = flat.detach()
+        _, state = self._values(flat, True)
+        return self._vjp(flat, dy.detach(), state)
+
+    def _shift_rows(self):
+        """[(parameter, coefficient, shift)] over every trainable slot (jacobian_param_shift, :180-212)."""
+        return [(j, c, s) for j, name in enumerate(self._param_gate_names()) for c, _a, s in _shift_recipe(name)]
+
+    _SHIFT_SETS_PER_LAUNCH = 4096
+
+    def _shifted_chunks(self, flat):
+        """Yields (rows, [B * T, P] shifted parameter sets) with B * T bounded per launch sequence."""
+        B, P = flat.shape
+        rows = self._shift_rows()
+        per = max(1, self._SHIFT_SETS_PER_LAUNCH // max(B, 1))
+        for lo in range(0, len(rows), per):
+            part = rows[lo:lo + per]
+            T = len(part)
+            shifted = flat.detach().unsqueeze(1).repeat(1, T, 1)          # [B, T, P]
+            idx = torch.tensor([j for j, _, _ in part], device=flat.device)
+            add = torch.tensor([s for _, _, s in part], dtype=flat.dtype, device=flat.device)
+            shifted[:, torch.arange(T, device=flat.device), idx] += add
+            yield part, shifted.reshape(B * T, P)
+
+    def _shift_jacobian(self, flat):
+        """J [B, n_meas, ..., P] from shifted forward evaluations."""
+        if self._res_complex:
+            raise NotImplementedError("forward-mode / second-order derivatives need real-valued measurements")
+        B, P = flat.shape
+        jac = None
+        for part, shifted in self._shifted_chunks(flat):
+            ev, _ = self._values(shifted, False)
+            ev = ev.reshape((B, len(part)) + tuple(ev.shape[1:]))
+            if jac is None:
+                jac = torch.zeros(tuple(ev.shape[2:]) + (B, P), dtype=ev.dtype, device=ev.device)
+            coef = torch.tensor([c for _, c, _ in part], dtype=ev.dtype, device=ev.device)
+            idx = torch.tensor([j for j, _, _ in part], device=ev.device)
+            jac.index_add_(-1, idx, ev.movedim(0, -1).movedim(0, -1) * coef)   # [..., B, T]
+        if jac is None:      # parameter-free circuit
+            ev, _ = self._values(flat.detach(), False)
+            return torch.zeros(tuple(ev.shape) + (0,), dtype=ev.dtype, device=ev.device)
+        return jac.movedim(-2, 0)
+
+    def _shift_hessian(self, flat, dy):
+        """H[b, j, k] = d(dy . J)_j / dflat_k from shifted gradient evaluations."""
+        B, P = flat.shape
+        hess = torch.zeros((B, P, P), dtype=self._rdtype, device=flat.device)
+        dy = dy.detach()
+        for part, shifted in self._shifted_chunks(flat):
+            T = len(part)
+            g = self._vjp_fresh(shifted, dy.repeat_interleave(T, dim=0)).reshape(B, T, P)
+            coef = torch.tensor([c for _, c, _ in part], dtype=g.dtype, device=g.device)
+            idx = torch.tensor([j for j, _, _ in part], device=g.device)
+            hess.index_add_(2, idx, (g * coef[None, :, None]).transpose(1, 2))
+        return hess
+
     def _param_shift_vjp(self, flat, dy):
         """vjp = dy @ J with J from shifted evaluations (pytorch_backend.py:180-212, :1211-1223)."""
         B, P = flat.shape
-        rows, coefs, cols = [], [], []
-        for j, name in enumerate(self._param_gate_names()):
-            for c, a, s in _shift_recipe(name):
-                rows.append((j, a, s))
-                coefs.append(c)
-                cols.append(j)
-        T = len(rows)
-        shifted = flat.unsqueeze(1).repeat(1, T, 1)  # [B, T, P]
-        for t, (j, a, s) in enumerate(rows):
-            shifted[:, t, :] *= a
-            shifted[:, t, j] += s
-        ev, _ = self._forward_device(shifted.reshape(B * T, P), False)  # [B*T, n_meas]
-        if ev.dim() != 2:
+        if P == 0:
+            return torch.zeros((B, 0), dtype=self._rdtype, device=flat.device)
+        jac = self._shift_jacobian(flat)
+        if jac.dim() != 3:
             raise ValueError("parameter shift needs scalar measurements (1-D output), as in the reference")
-        ev = ev.reshape(B, T, -1)
-        coef = torch.tensor(coefs, dtype=ev.dtype, device=ev.device)
-        idx = torch.tensor(cols, dtype=torch.long, device=ev.device)
-        contrib = torch.einsum("btm,bm,t->bt", ev, dy.to(ev.dtype).reshape(B, -1), coef)
-        grad = torch.zeros((B, P), dtype=ev.dtype, device=ev.device)
-        grad.index_add_(1, idx, contrib)
-        return grad
+        return torch.einsum("bmp,bm->bp", jac, dy.to(jac.dtype).reshape(B, -1))
 
     def _param_gate_names(self) -> List[str]:
         names = [None] * self._ir.n_params
@@ -325,11 +503,13 @@ class B200Backend:
         raise NotImplementedError
 
     def _run(self, flat, fn):
-        if self._tn is not None:
-            return self._tn.run(flat)
-        need_grad = torch.is_grad_enabled() and bool(self._requires_grad) and (
-            flat.requires_grad or _is_functorch_wrapped(flat))
-        return fn.apply({"backend": self, "need_grad": need_grad}, flat)
+        wrapped = _is_functorch_wrapped(flat)
+        track = torch.is_grad_enabled() and bool(self._requires_grad) and (flat.requires_grad or wrapped)
+        if not track and not wrapped:
+            with torch.no_grad():
+                return self._values(flat, False)[0]
+        # under torch.func transforms the reverse pass re-runs the forward (B200Grad): keep no state
+        return fn.apply({"backend": self, "need_grad": track and not wrapped}, flat)
 
     def batched(self, *params, in_dims=None):
         """Evaluate a batch of parameter sets at once -> [B, n_meas, ...].
@@ -476,3 +656,54 @@ class B200Backend:
             scale = torch.sqrt(torch.sum(torch.abs(part) ** 2))             # rescale_state, tools/helpers.py:43-51
             res["".join(str(b) for b in outcome)] = [s / scale for s in part]
         return res
+
+
+QUDIO_BACKEND_NAME = "pytorch_QUDIO_b200"
+
+
+class B200QUDIOBackend(B200Backend):
+    """Drop-in for ``QUDIOBackend`` (tedq/backends/qudio_backend.py:46-120): ``set_dataset(d)`` once, then
+    ``__call__(*params)`` evaluates the circuit on every data row with the shared ``params``; row i binds
+    ``(d[i], *params)`` positionally, as ``TorchModel.forward`` does (:149-150).  The reference feeds one row per
+    visible GPU through ``torch.nn.DataParallel`` and concatenates the per-row results along dim 0 (:86-102);
+    here all rows of this rank go through the device in ONE batched launch sequence and the result has the same
+    layout: ``[n_rows * n_meas, ...]``.  Under ``torch.distributed`` the rows are sharded over ranks
+    (dist.sharded_batched): every rank gets the full result, gradients flow through this rank's rows only and
+    shared-parameter gradients are combined by the caller with one all-reduce (dist.allreduce_sum_)."""
+
+    def __init__(self, backend, circuit, **kwargs):
+        super().__init__(backend, circuit, **kwargs)
+        self._dataset = None
+        self._data_dev = None
+
+    def set_dataset(self, dataset):
+        if not isinstance(dataset, torch.Tensor):
+            dataset = torch.as_tensor(np.asarray(dataset))
+        if dataset.dim() < 2:
+            dataset = dataset.reshape(-1, 1)
+        self._dataset = dataset
+        self._data_dev = None
+
+    def dataset(self):
+        return self._dataset
+
+    def __call__(self, *params):
+        if self._dataset is None:
+            raise ValueError("set_dataset() must be called before the circuit is evaluated")
+        self.check_parameters_torch_device(params)
+        dev = self._device if params else torch.device("cuda", torch.cuda.current_device())
+        self._require_cuda(dev)
+        if self._data_dev is None or self._data_dev.device != dev:
+            src = self._dataset
+            if not src.is_cuda and torch.cuda.is_available():
+                src = src.pin_memory()
+            self._data_dev = src.to(dev, non_blocking=True)
+        from . import dist as tqd
+
+        in_dims = (0,) + (None,) * len(params)
+        if tqd.world()[1] > 1:
+            local = tqd.sharded_batched(self, self._data_dev, *params, in_dims=in_dims, gather=False)
+            out = tqd.gather_rows(local, self._data_dev.shape[0], dev, keep_local_graph=True)
+        else:
+            out = self.batched(self._data_dev, *params, in_dims=in_dims)
+        return out.reshape((out.shape[0] * out.shape[1],) + tuple(out.shape[2:]))

@@ -42,18 +42,28 @@ def sharded_batched(backend, *params, in_dims=None, gather=True):
     out = backend.batched(*local, in_dims=in_dims) if hi > lo else None
     if not gather or ws == 1:
         return out
+    return gather_rows(out, B, params[0].device)
+
+
+def gather_rows(out, B: int, dev, keep_local_graph: bool = False):
+    """All-gather the per-rank row blocks of ``shard_range`` into [B, ...] on every rank (values only).  With
+    ``keep_local_graph`` this rank's rows stay attached to its autograd graph."""
+    rank, ws = world()
+    lo, hi = shard_range(B, rank, ws)
     per = (B + ws - 1) // ws
     shape = None if out is None else tuple(out.shape[1:])
     meta = [None] * ws
     dist.all_gather_object(meta, (shape, None if out is None else out.dtype))
     shape, dtype = next(m for m in meta if m[0] is not None)
-    dev = params[0].device
     buf = torch.zeros((per,) + shape, dtype=dtype, device=dev)
     if out is not None:
         buf[: hi - lo] = out.detach()
     parts = [torch.empty_like(buf) for _ in range(ws)]
     dist.all_gather(parts, buf)
-    return torch.cat(parts, 0)[:B]
+    full = torch.cat(parts, 0)[:B]
+    if keep_local_graph and out is not None and out.requires_grad:
+        full = torch.cat([full[:lo], out, full[hi:]], 0)
+    return full
 
 
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:

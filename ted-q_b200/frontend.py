@@ -260,10 +260,12 @@ class Circuit:
 
     def compilecircuit(self, backend=None, **kwargs):
         """String dispatch as circuit.py:268-285; this front end only knows the B200 backend."""
-        from .backend import BACKEND_NAME, B200Backend
+        from .backend import BACKEND_NAME, QUDIO_BACKEND_NAME, B200Backend, B200QUDIOBackend
 
         if backend == BACKEND_NAME:
             return B200Backend(backend, self, **kwargs)
+        if backend == QUDIO_BACKEND_NAME:
+            return B200QUDIOBackend(backend, self, **kwargs)
         raise ValueError(f"{backend}: unknown backend input")
 
 

@@ -5,7 +5,7 @@ read-only here, so the one extra branch a maintainer would add (see INTEGRATION.
 import time by wrapping the method.  Every other backend string falls through to the original."""
 from __future__ import annotations
 
-from .backend import BACKEND_NAME, B200Backend
+from .backend import BACKEND_NAME, QUDIO_BACKEND_NAME, B200Backend, B200QUDIOBackend
 
 
 def register_backend(tedq_module=None):
@@ -21,6 +21,8 @@ def register_backend(tedq_module=None):
     def compilecircuit(self, backend=None, **kwargs):
         if backend == BACKEND_NAME:
             return B200Backend(backend, self, **kwargs)
+        if backend == QUDIO_BACKEND_NAME:      # the "pytorch_QUDIO" branch's twin (circuit.py:276-277)
+            return B200QUDIOBackend(backend, self, **kwargs)
         return original(self, backend=backend, **kwargs)
 
     compilecircuit._tedq_b200 = True

@@ -452,12 +452,10 @@ class TNExecutor:
         return rows
 
     def run(self, flat: torch.Tensor) -> torch.Tensor:
-        be = self.backend
-        need_grad = torch.is_grad_enabled() and bool(be._requires_grad) and flat.requires_grad
-        if need_grad:
-            return _TNExecute.apply({"backend": be, "executor": self}, flat)
-        with torch.no_grad():
-            return self._forward_values(flat)
+        """Values (and, through ``backend.B200Execute``, gradients: reverse mode through the same contraction trees
+        where ``tree_backward_available()``, otherwise the adjoint state-vector sweeps of the same engine)."""
+        from .backend import B200Execute
+        return self.backend._run(flat, B200Execute)
 
     def _forward_values(self, flat, keep=None):
         be = self.backend
@@ -483,32 +481,6 @@ class TNExecutor:
                                    dtype=be._cdtype if ms0.is_complex else be._rdtype)
             return tqd.combine_measurements({i: r for i, r in enumerate(res) if r is not None}, len(res), like)
         return torch.stack(res, 1)
-
-
-class _TNExecute(torch.autograd.Function):
-    """Values from the contraction.  Gradient: reverse mode through the same contraction trees (unsliced plans:
-    tq_tn_backward + tq_tn_param_grads, any number of qubits), otherwise the adjoint state-vector sweeps of the
-    same engine (<= 26 qubits)."""
-
-    @staticmethod
-    def forward(ctx, run_kwargs, flat):
-        ctx.backend = run_kwargs["backend"]
-        ctx.executor = run_kwargs["executor"]
-        ctx.save_for_backward(flat)
-        ctx.kept = [] if ctx.executor.tree_backward_available() else None
-        return ctx.executor._forward_values(flat, ctx.kept)
-
-    @staticmethod
-    @torch.autograd.function.once_differentiable
-    def backward(ctx, dy):
-        (flat,) = ctx.saved_tensors
-        be = ctx.backend
-        if ctx.kept is not None:
-            return None, ctx.executor.tree_backward(flat.contiguous(), dy, ctx.kept)
-        if be._num_qubits > 26:
-            raise NotImplementedError("gradients of sliced networks beyond 26 qubits are not implemented")
-        _, ws = be._forward_device(flat, True)
-        return None, be._backward_device(flat, dy, ws)
 
 
 def amplitude_network(net: tn_index.Network, bits):

@@ -41,3 +41,25 @@ def assert_close(a, b, tol, what=""):
     bound = tol * np.maximum(1.0, np.abs(b))
     worst = float(np.max(err - bound)) if err.size else 0.0
     assert worst <= 0, f"{what}: max |a-b| = {float(err.max()):.3e} exceeds {tol:g}*max(1,|b|)"
+
+
+def all_kinds_spec():
+    """Every parametrised gate kind of the reference on an entangled 4-qubit state (controls live)."""
+    b = W._Builder("hess4", 4)
+    for q in range(4):
+        b.g("RY", [q], b.p())
+    b.g("CNOT", [0, 1])
+    b.g("CRX", [1, 2], b.p())
+    b.g("Rot", [3], b.p(), b.p(), b.p())
+    b.g("CRY", [3, 0], b.p())
+    b.g("ControlledPhaseShift", [2, 3], b.p())
+    b.g("Hadamard", [2])
+    b.g("CRZ", [0, 2], b.p())
+    b.g("PhaseShift", [1], b.p())
+    b.g("RZ", [0], b.p())
+    b.g("CNOT", [2, 3])
+    for q in range(4):
+        b.g("RX", [q], b.p())
+    for q in range(3):
+        b.expval(("PauliZ", [q]))
+    return b.spec

@@ -51,7 +51,23 @@ def _worker(rank, world_size, port, ret):
         mine = tqd.my_measurements(n_meas)
         truth = torch.arange(3 * n_meas * 2, dtype=torch.float64).reshape(3, n_meas, 2)
         combined = tqd.combine_measurements({i: truth[:, i] for i in mine}, n_meas, truth[:, 0])
-        ret[rank] = (complex(t[0]), full, gathered, info.n_slices, mine, bool(torch.equal(combined, truth)))
+        # data rows sharded over ranks with shared weights (the QUDIO front): every rank sees all values, the
+        # autograd graph covers this rank's rows only; one all-reduce completes the shared-weight gradient
+        class RowEngine:
+            @staticmethod
+            def batched(X, w, in_dims=None):
+                return (X * w).sum(1, keepdim=True)
+
+        X = torch.arange(15, dtype=torch.float64).reshape(5, 3)
+        w = torch.tensor([0.5, -1.0, 2.0], dtype=torch.float64, requires_grad=True)
+        local = tqd.sharded_batched(RowEngine, X, w, in_dims=(0, None), gather=False)
+        rows_all = tqd.gather_rows(local, 5, X.device, keep_local_graph=True)
+        rows_all.sum().backward()
+        g = tqd.allreduce_sum_(w.grad.clone())
+        rows_ok = bool(torch.equal(rows_all.detach(), (X * w.detach()).sum(1, keepdim=True))) and \
+            bool(torch.allclose(g, X.sum(0)))
+        ret[rank] = (complex(t[0]), full, gathered, info.n_slices, mine,
+                     bool(torch.equal(combined, truth)) and rows_ok)
     finally:
         dist.destroy_process_group()
 

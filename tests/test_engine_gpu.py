@@ -6,7 +6,7 @@ import torch
 
 import tedq_b200 as qb
 from conftest import case_id, load_golden
-from helpers import TOL, assert_close, build, cdtype, golden_out, rdtype
+from helpers import TOL, all_kinds_spec, assert_close, build, cdtype, golden_out, rdtype
 from tedq_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
@@ -201,3 +201,97 @@ def test_states_after_measurement_match_reference():
     plain(pa[0].cuda())
     with pytest.raises(ValueError):
         plain.states_after_measurement
+
+
+# ---------------------------------------------------------------- second order, torch.func, QUDIO front
+@pytest.mark.parametrize("mode", ["sv", "tn"])
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+def test_hessian_matches_oracle(mode, dt):
+    """Double backward through the engine (gradient node differentiated by the gate set's shift identities)
+    against torch's own double backward through the oracle, every parametrised gate kind in the circuit."""
+    from oracle import sv_ref
+
+    spec = all_kinds_spec()
+    circ = build(spec, dt)
+    kw = {"tn_mode": True} if mode == "tn" else {}
+    cc = circ.compilecircuit(backend="pytorch_b200", dtype=cdtype(dt), **kw)
+    P = spec["n_params"]
+    rng = np.random.RandomState(5)
+    x0 = torch.tensor(rng.uniform(-3, 3, P), dtype=rdtype(dt))
+    w = torch.tensor([0.7, -1.3, 0.4], dtype=rdtype(dt))
+    H = torch.autograd.functional.hessian(lambda x: (cc(x) * w.cuda()).sum(), x0.cuda())
+    Href = torch.autograd.functional.hessian(
+        lambda x: (sv_ref.run_sv(circ, x, torch.complex128) * w.double()).sum(), x0.double())
+    assert_close(H.cpu().numpy(), Href.numpy(), 10 * TOL[dt], "hessian")
+    assert_close(H.cpu().numpy(), H.cpu().numpy().T, 10 * TOL[dt], "symmetry")
+
+
+@pytest.mark.parametrize("kw", [{}, {"tn_mode": True}, {"use_jdopttn": "B200OptTN"}], ids=["sv", "tn", "jdopttn"])
+def test_notebook_hessian_and_batch(kw):
+    """Hessian_&_batch_executation notebook cells 5-30: cost(params, weight), vmap(cost), hessian(cost),
+    vmap(hessian(cost)) on RX(p0) RY(p1) <Z> = cos(p0) cos(p1)."""
+    def circuitDef(params):
+        qb.RX(params[0], qubits=[0])
+        qb.RY(params[1], qubits=[0])
+        return qb.expval(qb.PauliZ(qubits=[0]))
+
+    kw = dict(kw)
+    if kw.get("use_jdopttn") == "B200OptTN":
+        kw["use_jdopttn"] = qb.B200OptTN
+    circuit = qb.Circuit(circuitDef, 1, parameter_shapes=[(2,)])
+    cc = circuit.compilecircuit(backend="pytorch_b200", **kw)
+
+    def cost(params, weight):
+        return weight[0] * cc(params) + weight[1] + weight[2]
+
+    torch.manual_seed(3)
+    P = torch.rand(5, 2, device="cuda")
+    Wt = torch.rand(5, 3, device="cuda")
+    exact = lambda p, w: w[0] * (torch.cos(p[0]) * torch.cos(p[1])).reshape(1) + w[1] + w[2]
+    assert_close(torch.func.vmap(cost)(P, Wt).cpu(), torch.func.vmap(exact)(P, Wt).cpu(), 1e-5, "vmap(cost)")
+    h = torch.func.hessian(cost)(P[0], Wt[0])
+    assert h.shape == (1, 2, 2)
+    assert_close(h.cpu(), torch.func.hessian(exact)(P[0], Wt[0]).cpu(), 2e-5, "hessian")
+    hb = torch.func.vmap(torch.func.hessian(cost))(P, Wt)
+    assert_close(hb.cpu(), torch.func.vmap(torch.func.hessian(exact))(P, Wt).cpu(), 2e-5, "vmap(hessian)")
+    jb = torch.func.vmap(torch.func.jacrev(cost, argnums=(0, 1)))(P, Wt)
+    je = torch.func.vmap(torch.func.jacrev(exact, argnums=(0, 1)))(P, Wt)
+    for a, b in zip(jb, je):
+        assert_close(a.cpu(), b.cpu(), 2e-5, "vmap(jacrev)")
+    jf = torch.func.jacfwd(cost)(P[1], Wt[1])
+    assert_close(jf.cpu(), torch.func.jacfwd(exact)(P[1], Wt[1]).cpu(), 2e-5, "jacfwd")
+
+
+def test_retain_graph_and_repeated_backward():
+    spec = W.qnn4()
+    cc = W.build_circuit(spec, qb).compilecircuit(backend="pytorch_b200")
+    x = torch.rand(4, device="cuda")
+    w = torch.rand(2, 4, 2, device="cuda", requires_grad=True)
+    y = cc(x, w).sum()
+    (g1,) = torch.autograd.grad(y, w, retain_graph=True)
+    (g2,) = torch.autograd.grad(y, w)
+    assert torch.allclose(g1, g2, atol=1e-6)
+
+
+def test_qudio_front_matches_row_loop():
+    """qudio_backend.py:86-111: set_dataset(d) then cc(params) == cat over rows of cc_plain(d[i], params)."""
+    spec = W.qnn4()
+    circ = W.build_circuit(spec, qb)
+    cq = circ.compilecircuit(backend="pytorch_QUDIO_b200")
+    cp = circ.compilecircuit(backend="pytorch_b200")
+    torch.manual_seed(0)
+    d = torch.rand(6, 4)                                   # host dataset, like the example script
+    w = torch.rand(2, 4, 2, device="cuda", requires_grad=True)
+    with pytest.raises(ValueError):
+        cq(w)
+    cq.set_dataset(d)
+    assert cq.dataset() is d
+    y = cq(w)
+    rows = torch.cat([cp(d[i].cuda(), w) for i in range(6)], 0)
+    assert y.shape == rows.shape == (24,)
+    assert torch.allclose(y, rows, atol=1e-6)
+    ct = torch.rand(24, device="cuda")
+    (g,) = torch.autograd.grad((y * ct).sum(), w)
+    (gr,) = torch.autograd.grad((rows * ct).sum(), w)
+    assert torch.allclose(g, gr, atol=1e-5)
+    assert str(cq.device).startswith("cuda")
