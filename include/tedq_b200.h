@@ -235,9 +235,13 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
  *     level, one CTA per parameter set, tiny steps one per warp; 0 launches every step on its own.
  *   TQ_TN_OPT_TC_SPLITK (default 1): a tensor-core step whose output tiles cover at most half of the SMs is cut
  *     along K (>= 128 complex k per part) so that every SM has work; the parts write partial sums that are added
- *     in a fixed order (deterministic). */
+ *     in a fixed order (deterministic).
+ *   TQ_TN_OPT_TC_GATHER (default 0, experimental): 1 = the row operand of a tensor-core step whose tiles are read
+ *     once or twice (<= 2 column tiles) is gathered, split and swizzled into shared memory by the GEMM kernel itself,
+ *     straight from the tensor (no operand image in HBM for it).  Bit-identical results; measured slower than the
+ *     image path on B200 so far ("Experiments that did not pay"). */
 enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2,
-                    TQ_TN_OPT_FUSE_SMALL = 3, TQ_TN_OPT_TC_SPLITK = 4 };
+                    TQ_TN_OPT_FUSE_SMALL = 3, TQ_TN_OPT_TC_SPLITK = 4, TQ_TN_OPT_TC_GATHER = 5 };
 int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
 /* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,
  * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096),

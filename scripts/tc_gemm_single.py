@@ -19,6 +19,8 @@ a_idx, b_idx, o_idx = M + K, K + N, M + N
 plan = capi.TnPlan([a_idx, b_idx], o_idx, [(0, 1)], [], [False, False], capi.TQ_C128 if c128 else capi.TQ_C64)
 plan.set_option(capi.TN_OPT_TC_MIN_LOG2, 0)
 plan.set_option(capi.TN_OPT_TC_CHUNK, chunk)
+import os
+plan.set_option(capi.TN_OPT_TC_GATHER, int(os.environ.get("TQ_GATHER", "0")))
 assert plan.step_kernel(0) == (1 if c128 else 2)
 g = torch.Generator(device="cuda").manual_seed(0)
 rd = torch.float64 if c128 else torch.float32

@@ -776,6 +776,9 @@ struct TcStep {
   int64_t img_a_z = 0, img_b_z = 0;  // image bytes per z (= parameter set x kept-shared index value)
   // a slice-invariant operand of a per-slice step is packed ONCE per call into a pinned image
   bool pin_a = false, pin_b = false;
+  // the row operand is streamed (every tile read once or twice): when its image is not pinned the GEMM kernel
+  // gathers it itself (k_tc_gemm<C_T, true>), no image is written
+  bool gather_a = false;
   tc::PackParams pa, pb;
 };
 
@@ -847,6 +850,7 @@ struct tq_tn_plan {
   int tc_min_log2 = 20;    // TQ_TN_OPT_TC_MIN_LOG2: a step runs on tensor cores when k+m+n+b >= this
   int tc_chunk = 32;       // TQ_TN_OPT_TC_CHUNK: complex k accumulated in TMEM between round-to-nearest drains
   int tc_splitk = 1;       // TQ_TN_OPT_TC_SPLITK
+  int tc_gather = 0;       // TQ_TN_OPT_TC_GATHER
   int num_sms = 148;
 };
 
@@ -945,6 +949,7 @@ static int setup_steps(tq_tn_plan* p, int first) {
     T.tiles_a = 1 << (n_row - 7);
     T.tiles_b = 1 << (n_col - col_t_log2);
     T.stages = tc::num_stages(T.c_t);
+    T.gather_a = st.n_k >= tc::KB_LOG && T.tiles_b <= 2;
     T.img_a_z = (int64_t)T.tiles_a * T.kblocks * tc::A_CHUNK;
     T.img_b_z = (int64_t)T.tiles_b * T.kblocks * tc::b_chunk_bytes(T.c_t);
     const int8_t* lhs_k = st.lhs_bits;
@@ -1541,6 +1546,9 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
     case TQ_TN_OPT_TC_SPLITK:
       p->tc_splitk = value != 0;
       return TQ_OK;
+    case TQ_TN_OPT_TC_GATHER:
+      p->tc_gather = value != 0;
+      return TQ_OK;
     case TQ_TN_OPT_FUSE_SMALL:
       p->fuse_enabled = value != 0;
       return build_schedule(p);
@@ -1644,14 +1652,14 @@ namespace tq {
 static int tc_setup_once() {
   static int done = 0;
   if (done) return TQ_OK;
-  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::GEMM_SMEM));
-  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::GEMM_SMEM));
-  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::GEMM_SMEM));
-  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
+  TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_pack<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   done = 1;
   return TQ_OK;
@@ -1669,6 +1677,8 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   const TcStep& T = p->tc[s];
   const int64_t nz = sets << stp.n_b;
   TQ_REQUIRE(nz < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step %d has %lld batched GEMMs", s, (long long)nz);
+  const bool gather_a = gemm && pack_a && T.gather_a && p->tc_gather;
+  if (gather_a) pack_a = false;
   if (pack_a || pack_b) {
     tc::PackPair pp;
     memset(&pp, 0, sizeof(pp));
@@ -1732,11 +1742,23 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   const int64_t total = (int64_t)T.tiles_a * T.tiles_b * nz * splits;
   const unsigned grid = (unsigned)std::min<int64_t>(total, p->num_sms);
   const size_t smem = tc::GEMM_SMEM;
-  switch (T.c_t) {
-    case 16: tc::k_tc_gemm<16><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
-    case 32: tc::k_tc_gemm<32><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
-    case 64: tc::k_tc_gemm<64><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
-    default: tc::k_tc_gemm<128><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+  if (gather_a) {
+    g.ga = T.pa;
+    g.ga.src = reinterpret_cast<const float2*>(T.swap ? b : a);
+    g.ga.src_set_stride = T.swap ? sb : sa;
+    switch (T.c_t) {
+      case 16: tc::k_tc_gemm<16, true><<<grid, tc::GEMM_THREADS_GA, smem, st>>>(g); break;
+      case 32: tc::k_tc_gemm<32, true><<<grid, tc::GEMM_THREADS_GA, smem, st>>>(g); break;
+      case 64: tc::k_tc_gemm<64, true><<<grid, tc::GEMM_THREADS_GA, smem, st>>>(g); break;
+      default: tc::k_tc_gemm<128, true><<<grid, tc::GEMM_THREADS_GA, smem, st>>>(g); break;
+    }
+  } else {
+    switch (T.c_t) {
+      case 16: tc::k_tc_gemm<16, false><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+      case 32: tc::k_tc_gemm<32, false><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+      case 64: tc::k_tc_gemm<64, false><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+      default: tc::k_tc_gemm<128, false><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
+    }
   }
   if (splits > 1) {
     const int64_t n4 = c_elems / 2;

@@ -41,6 +41,14 @@ constexpr int A_PLANE = ROWS * ROW_BYTES; // one plane (hi or lo) of an A tile
 constexpr int A_CHUNK = 2 * A_PLANE;      // hi + lo
 constexpr int ACC_WARPS = 8;              // accumulation / epilogue warps (two per TMEM lane quadrant)
 constexpr int GEMM_THREADS = 64 + 32 * ACC_WARPS;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 accumulate
+// gather-A variant: 4 warpgroups.  WG0 = B bulk-copy producer (warp 0), MMA issuer (warp 1), A loaders (warps 2-3);
+// WG1-2 = the 8 accumulation warps; WG3 = 4 converter warps.  Registers are re-balanced with setmaxnreg.
+constexpr int GA_ACC0 = 4;                // first accumulation warp
+constexpr int GA_CONV0 = 12;              // first converter warp
+constexpr int CONV_WARPS = 4;
+constexpr int CONV_ITERS = ROWS * KB_CPLX / (32 * CONV_WARPS);  // complex entries of a k-block per converter thread
+constexpr int LOAD_ITERS = ROWS * KB_CPLX / 64;                 // ... per loader thread (2 loader warps)
+constexpr int GEMM_THREADS_GA = 512;
 constexpr int SMEM_BUDGET = 200 * 1024;    // operand stages
 constexpr int EPI_PITCH = 80;             // bytes per staged row piece (64 data + 16 pad: conflict-free quarter-warps)
 constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
@@ -284,6 +292,9 @@ struct GemmParams {
   int32_t splits, kb_per_split;
   int64_t c_split_stride;
   int64_t c_bb_stride;       // complex entries between kept-shared index values (2^(n_m + n_n))
+  // gather-A variant (k_tc_gemm<C_T, true>): the A operand is read ONCE from its tensor (bit-permuted gather),
+  // split and written to the swizzled stage by two extra warps; there is no A image.  ga = pack tables of A.
+  PackParams ga;
 };
 
 // Accumulation is two-level.  tcgen05 adds into its fp32 accumulator with round-toward-zero, a bias of about
@@ -291,12 +302,19 @@ struct GemmParams {
 // are accumulated in TMEM; the 8 accumulation warps then drain that partial sum and add it to fp32 registers with
 // round-to-nearest while the MMA issuer fills the other TMEM buffer (Ootomo & Yokota's error-compensated scheme,
 // moved from mma.sync registers to TMEM).
-template <int C_T>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+//
+// GA = true: the "streamed" operand (the one whose tiles are read once: tiles_b <= 2) never takes the detour
+// through an HBM image (write 2x its bytes, read them back).  Warps 10..11 gather a k-block of A straight from the
+// tensor (bit-permuted 8-byte loads, ascending addresses across the warp), split it into hi / lo and store both
+// planes at their swizzled places in the stage; a generic->async proxy fence and one arrive per warp on the
+// stage's full barrier (which also counts the B image's bulk-copy bytes) hand it to the MMA issuer.  The loads of
+// the next k-block are in flight while the current one waits for its stage.
+template <int C_T, bool GA>
+__global__ void __launch_bounds__(GA ? GEMM_THREADS_GA : GEMM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ GemmParams p) {
   constexpr int HALF = C_T / 2;  // complex columns owned by one accumulation warp
   extern __shared__ __align__(1024) uint8_t g_smem[];
-  __shared__ __align__(8) uint64_t bars[4 + 4 + 2 + 2];
+  __shared__ __align__(8) uint64_t bars[4 + 4 + 2 + 2 + 4];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(g_smem) + 1023u) & ~1023u;
@@ -310,12 +328,14 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
   auto empty_bar = [&](int s) { return bar0 + 8u * (4 + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (10 + s); };
+  auto raw_full_bar = [&](int s) { return bar0 + 8u * (12 + s); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), GA ? 1 + CONV_WARPS : 1);  // GA: the B bulk copy's expect_tx arrive + the converter warps
       mbar_init(empty_bar(s), 1);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(raw_full_bar(s), 64);  // one cp.async-tracking arrive per loader lane
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), ACC_WARPS);
@@ -334,8 +354,8 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
 
   const int64_t tiles_per_z = (int64_t)p.tiles_a * p.tiles_b;
   const int64_t total = tiles_per_z * p.n_z * p.splits;  // work item = (tile, K range), K range fastest
-
-  if (warp == 0) {
+  constexpr int ACC0 = GA ? GA_ACC0 : 2;
+  auto role_producer = [&]() {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -349,9 +369,9 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         const uint8_t* gb = p.img_b + z * p.img_b_z + tb * (int64_t)p.kblocks * b_chunk;
         for (int kb = kbeg; kb < kbeg + p.kb_per_split; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), sbytes);
+          mbar_expect_tx(full_bar(stage), GA ? b_chunk : sbytes);
           const uint32_t sa = smem0 + (uint32_t)stage * sbytes;
-          bulk_g2s(sa, ga + (int64_t)kb * A_CHUNK, A_CHUNK, full_bar(stage));
+          if (!GA) bulk_g2s(sa, ga + (int64_t)kb * A_CHUNK, A_CHUNK, full_bar(stage));
           bulk_g2s(sa + A_CHUNK, gb + (int64_t)kb * b_chunk, b_chunk, full_bar(stage));
           if (++stage == S) {
             stage = 0;
@@ -360,7 +380,8 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  };
+  auto role_issuer = [&]() {
     if (lane == 0) {
       constexpr uint32_t idesc =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * C_T >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
@@ -399,9 +420,128 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         }
       }
     }
-  } else {
+  };
+  auto role_gather = [&]() {
+    // Gather-A roles.  Warps 2..3 (loaders) request a k-block of A as 8-byte cp.async copies that land at their
+    // swizzled places in the hi plane of a free stage (no registers held; up to `stages` k-blocks in flight per SM);
+    // a cp.async-tracking arrive on the stage's raw barrier fires when they have landed.  Warps 12..15 (converters)
+    // then split the k-block in place (hi rounded back to where it was, lo to the other plane), fence generic ->
+    // async proxy and arrive on the stage's full barrier.  Loading and converting are separate warps because
+    // that proxy fence waits for the executing thread's outstanding copies: a thread that both prefetches and
+    // fences has nothing in flight across the fence.
+    const PackParams& P = p.ga;
+    const int64_t my_items = (int64_t)blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_blocks = my_items * p.kb_per_split;
+    const bool loader = warp < 4;
+    // loaders: element e = tl + 64 i (tl = 0..63); converters: e = tc + 128 i (tc = 0..127)
+    const int tl = loader ? (int)threadIdx.x - 64 : (int)threadIdx.x - 32 * GA_CONV0;
+    const int tbits = loader ? 6 : 7;
+    uint32_t so_t = 0, d_t = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < tbits && ((tl >> j) & 1)) {
+        so_t |= 1u << P.local_src[j];
+        d_t |= (uint32_t)P.local_dst[j];
+      }
+    auto dst_of = [&](uint32_t d) {
+      const uint32_t r = d >> 4, kk = d & 15u;
+      return r * ROW_BYTES + ((((kk >> 1) ^ swz(r)) << 4) | ((kk & 1u) << 3));
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    // one polling lane per warp: 192 threads spinning on try_wait would compete with the MMA issuer's own waits
+    auto warp_wait = [&](uint32_t bar, uint32_t parity) {
+      if (p.debug & 16) {
+        mbar_wait(bar, parity);
+      } else {
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+      }
+    };
+    if (loader) {
+      uint32_t so_i[LOAD_ITERS], d_i[LOAD_ITERS];
+#pragma unroll
+      for (int i = 0; i < LOAD_ITERS; ++i) {
+        uint32_t so = so_t, d = d_t;
+#pragma unroll
+        for (int j = 6; j < 7 + KB_LOG; ++j)
+          if ((i >> (j - 6)) & 1) {
+            so |= 1u << P.local_src[j];
+            d |= (uint32_t)P.local_dst[j];
+          }
+        so_i[i] = so;
+        d_i[i] = dst_of(d);
+      }
+      const uint32_t bb_mask = (1u << P.n_b) - 1u;
+      int64_t wi = blockIdx.x;
+      int kbi = (int)(wi % p.splits) * p.kb_per_split, kend = kbi + p.kb_per_split;
+      for (int64_t n = 0; n < n_blocks; ++n) {
+        const int64_t t = wi / p.splits;
+        const int64_t z = t / tiles_per_z;
+        const int64_t r = t - z * tiles_per_z;
+        const uint32_t ta = (uint32_t)(r % p.tiles_a);
+        const uint32_t bb = (uint32_t)z & bb_mask;
+        int64_t base = (z >> P.n_b) * P.src_set_stride;
+        for (int j = 0; j < P.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << P.b_bits[j];
+        for (int j = 7; j < P.n_row; ++j) base |= (int64_t)((ta >> (j - 7)) & 1u) << P.row_bits[j];
+        for (int j = KB_LOG; j < P.n_k; ++j) base |= (int64_t)(((uint32_t)kbi >> (j - KB_LOG)) & 1u) << P.k_bits[j];
+        const float2* src = P.src + base;
+        warp_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t dst = smem0 + (uint32_t)stage * sbytes;
+        if (!(p.debug & 8)) {
+#pragma unroll
+          for (int i = 0; i < LOAD_ITERS; ++i)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + d_i[i]), "l"(src + so_i[i]) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(raw_full_bar(stage)) : "memory");
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        if (++kbi == kend) {
+          wi += gridDim.x;
+          kbi = (int)(wi % p.splits) * p.kb_per_split;
+          kend = kbi + p.kb_per_split;
+        }
+      }
+    } else {
+      uint32_t d_i[CONV_ITERS];
+#pragma unroll
+      for (int i = 0; i < CONV_ITERS; ++i) {
+        uint32_t d = d_t;
+#pragma unroll
+        for (int j = 7; j < 7 + KB_LOG; ++j)
+          if ((i >> (j - 7)) & 1) d |= (uint32_t)P.local_dst[j];
+        d_i[i] = dst_of(d);
+      }
+      for (int64_t n = 0; n < n_blocks; ++n) {
+        warp_wait(raw_full_bar(stage), phase);
+        uint8_t* buf = g_smem + (smem0 - smem_u32(g_smem)) + (size_t)stage * sbytes;
+        if (!(p.debug & 4)) {
+          float2 v[CONV_ITERS];
+#pragma unroll
+          for (int i = 0; i < CONV_ITERS; ++i) v[i] = *reinterpret_cast<const float2*>(buf + d_i[i]);
+#pragma unroll
+          for (int i = 0; i < CONV_ITERS; ++i) {
+            const float hr = to_tf32(v[i].x), hi = to_tf32(v[i].y);
+            const float lr = to_tf32(v[i].x - hr), li = to_tf32(v[i].y - hi);
+            *reinterpret_cast<float2*>(buf + d_i[i]) = make_float2(hr, hi);
+            *reinterpret_cast<float2*>(buf + A_PLANE + d_i[i]) = make_float2(lr, li);
+          }
+        }
+        if (!(p.debug & 2)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  };
+  auto role_acc = [&]() {
     const int q = warp & 3;           // TMEM lane quadrant this warp may read
-    const int h = (warp - 2) >> 2;    // which half of the complex columns it accumulates
+    const int h = (warp - ACC0) >> 2;  // which half of the complex columns it accumulates
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t bb_mask = (1u << p.n_b_log2) - 1u;
@@ -450,7 +590,7 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         // Row-major result: a lane owns a row, so direct stores would touch 32 rows with 16 bytes each per
         // instruction.  Stage 64-byte row pieces in shared memory and let 4 lanes write one row's piece: every
         // store instruction covers 8 rows x 64 contiguous bytes (full sectors).
-        uint8_t* stg = epi_smem + (warp - 2) * EPI_WARP_BYTES;
+        uint8_t* stg = epi_smem + (warp - ACC0) * EPI_WARP_BYTES;
         float2* tile0 = p.c + split * p.c_split_stride + set * p.c_set_stride + bb * p.c_bb_stride +
                         (ta * ROWS + q * 32) * p.c_rs + col0;
 #pragma unroll
@@ -474,6 +614,29 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         for (int j = 0; j < HALF; ++j) dst[j * p.c_cs] = make_float2(acc_re[j], acc_im[j]);
       }
     }
+  
+  };
+  if constexpr (GA) {
+    // 512 threads start with 128 registers each; setmaxnreg moves registers from the light warpgroups to the two
+    // accumulation warpgroups (88 * 128 + 72 * 128 + 176 * 256 = 65536).  One setmaxnreg per warpgroup, at the top
+    // of that warpgroup's branch, so that the register allocator sees the limit of the code that follows it.
+    const int wg = warp >> 2;
+    if (wg == 0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+      if (warp == 0) role_producer();
+      else if (warp == 1) role_issuer();
+      else role_gather();
+    } else if (wg == 3) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      role_gather();
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+      role_acc();
+    }
+  } else {
+    if (warp == 0) role_producer();
+    else if (warp == 1) role_issuer();
+    else role_acc();
   }
   tc_fence_before();
   __syncthreads();

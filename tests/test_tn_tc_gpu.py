@@ -14,7 +14,8 @@ from tedq_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
-def _contract(inputs, output, arrays, batched, tensor_core, B=1, min_log2=0, chunk=None, c128=False, splitk=True):
+def _contract(inputs, output, arrays, batched, tensor_core, B=1, min_log2=0, chunk=None, c128=False, splitk=True,
+              gather=False):
     plan = capi.TnPlan(inputs, output, [(0, 1)], [], batched, capi.TQ_C128 if c128 else capi.TQ_C64)
     plan.set_option(capi.TN_OPT_TENSOR_CORE, 1 if tensor_core else 0)
     plan.set_option(capi.TN_OPT_TC_MIN_LOG2, min_log2)
@@ -22,6 +23,7 @@ def _contract(inputs, output, arrays, batched, tensor_core, B=1, min_log2=0, chu
         plan.set_option(capi.TN_OPT_TC_CHUNK, chunk)
     if not splitk:
         plan.set_option(capi.TN_OPT_TC_SPLITK, 0)
+    plan.set_option(capi.TN_OPT_TC_GATHER, 1 if gather else 0)
     kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
     dev = "cuda"
     cd = torch.complex128 if c128 else torch.complex64
@@ -67,17 +69,22 @@ SHAPES = [  # (n_m, n_n, n_k, n_b)
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "m%d_n%d_k%d_b%d" % s)
 @pytest.mark.parametrize("shuffle", [False, True], ids=["canonical", "permuted"])
-def test_tc_step_matches_einsum(shape, shuffle):
+@pytest.mark.parametrize("gather", [True, False], ids=["gatherA", "images"])
+def test_tc_step_matches_einsum(shape, shuffle, gather):
+    """gatherA: the row operand is gathered by the GEMM kernel itself where it is streamed (<= 2 column tiles);
+    images: both operands go through packed HBM images."""
     n_m, n_n, n_k, n_b = shape
     rng = np.random.RandomState(hash(shape) % 10000 + int(shuffle))
     a_idx, b_idx, o_idx = _case(rng, n_m, n_n, n_k, n_b, shuffle)
     A = _rand(rng, (2,) * len(a_idx))
     B = _rand(rng, (2,) * len(b_idx))
     ref = _einsum(a_idx, b_idx, o_idx, A, B).reshape(-1)
-    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], True, gather=gather)
     assert kinds == [2], kinds                      # the tensor-core kernel really ran
     scale = np.abs(ref).max()
     assert np.abs(got.reshape(-1) - ref).max() <= 1e-5 * scale, np.abs(got.reshape(-1) - ref).max() / scale
+    if gather:
+        return
     fma, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [False, False], False)
     assert 2 not in kinds
     assert np.abs(fma.reshape(-1) - ref).max() <= 1e-5 * scale
@@ -102,7 +109,8 @@ def test_tc_error_is_fp32_class():
 
 @pytest.mark.parametrize("which", ["a", "b", "both"])
 @pytest.mark.parametrize("shape", [(8, 5, 6, 1), (7, 6, 11, 0)], ids=["plain", "splitk"])
-def test_tc_step_batched_parameter_sets(which, shape):
+@pytest.mark.parametrize("gather", [False, True], ids=["images", "gatherA"])
+def test_tc_step_batched_parameter_sets(which, shape, gather):
     rng = np.random.RandomState(11)
     n_sets = 3
     a_idx, b_idx, o_idx = _case(rng, *shape)
@@ -110,7 +118,7 @@ def test_tc_step_batched_parameter_sets(which, shape):
     A = _rand(rng, ((n_sets,) if ba else ()) + (2,) * len(a_idx))
     B = _rand(rng, ((n_sets,) if bb else ()) + (2,) * len(b_idx))
     ref = _einsum(a_idx, b_idx, o_idx, A, B, ba, bb).reshape(n_sets, -1)
-    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [ba, bb], True, B=n_sets)
+    got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [ba, bb], True, B=n_sets, gather=gather)
     assert kinds == [2]
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
 
