@@ -381,7 +381,9 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=
     if dist_on:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     total_ms = float(t.item())
-    flops = plan.flops * plan.n_slices
+    info = cc._tn._amplitude_plan()[1]
+    group = len(cc._tn.slice_members(0))          # slices that share one launch sequence (hyper_opt["slice_batch"])
+    flops = 2.0 ** info.flops_log2 * info.n_slices
     peak, kind = tf32_peak()
     hbm_peak, _ = load_peaks()
     ach = flops * steps / (total_ms * 1e-3) / 1e12
@@ -398,12 +400,13 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=
         if r["kernel"] == 4:   # a fused run of small steps is timed as one launch (on its first member)
             table.append({"kernel": "k_tn_fused (run of small steps)", "ms": round(r["ms"], 4)})
             continue
-        fl = 8.0 * 2.0 ** (r["k"] + r["m"] + r["n"] + r["b"])
-        byts = 8.0 * (2.0 ** (r["k"] + r["m"] + r["b"]) + 2.0 ** (r["k"] + r["n"] + r["b"]) + 2.0 ** (r["m"] + r["n"] + r["b"]))
+        sets = r["sets"] if r.get("per_set") else 1   # a grouped step runs `sets` slices' GEMMs in one launch
+        fl = sets * 8.0 * 2.0 ** (r["k"] + r["m"] + r["n"] + r["b"])
+        byts = sets * 8.0 * (2.0 ** (r["k"] + r["m"] + r["b"]) + 2.0 ** (r["k"] + r["n"] + r["b"]) + 2.0 ** (r["m"] + r["n"] + r["b"]))
         t_fl = 3.0 * fl / (peak * 1e12)          # 4M x 3-term split-TF32: 24 TF32 flops per 8 algorithmic
         t_by = byts / (hbm_peak * 1e9)
         roof_ms = max(t_fl, t_by) * 1e3
-        table.append({"M": 2 ** r["m"], "N": 2 ** r["n"], "K": 2 ** r["k"], "batch": 2 ** r["b"],
+        table.append({"M": 2 ** r["m"], "N": 2 ** r["n"], "K": 2 ** r["k"], "batch": 2 ** r["b"] * sets,
                       "kernel": ["k_tn_step", "k_tn_gemm", "k_tc_pack+k_tc_gemm", "k_tn_dot", "k_tn_fused", "k_tn_apply"][r["kernel"]],
                       "ms": round(r["ms"], 4), "pack_ms": round(r["pack_ms"], 4),
                       "algorithmic_tflops": round(fl / (r["ms"] * 1e-3) / 1e12, 2),
@@ -415,8 +418,9 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=
             tc_gemm_ms += r["ms"] - r["pack_ms"]
     res = {
         "value": steps / (total_ms * 1e-3), "unit": "evals/s", "ms_per_step": total_ms / steps, "dtype": "c64",
-        "desc": f"c5: 40-qubit 5x8 lattice random circuit, 12 cycles, amplitude <0|U|0>, {plan.n_slices} slices, "
-                f"width {plan.width}, {plan.n_steps} pairwise steps, {flops:.3e} flop per amplitude",
+        "desc": f"c5: 40-qubit 5x8 lattice random circuit, 12 cycles, amplitude <0|U|0>, {info.n_slices} slices"
+                + (f" in groups of {group} (one launch sequence per group)" if group > 1 else "") +
+                f", width {plan.width}, {plan.n_steps} pairwise steps, {flops:.3e} flop per amplitude",
         "amplitude": [float(amp.real), float(amp.imag)],
         "roofline": {
             "bound": "tensor", "kernel": "k_tc_gemm", "unit": "TFLOP/s", "peak": peak, "peak_kind": kind,
@@ -433,7 +437,7 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=
                     "roofline is peak/3: dominant_steps_frac_of_complex_gemm_roofline = executed TF32 flops / time "
                     "(operand packing included) / peak for the tensor-bound steps.",
         },
-        "per_slice_ms_profiled": slice_ms, "steps_per_slice": len(per_slice), "steps_once_per_call": len(rows) - len(per_slice),
+        "per_slice_ms_profiled": slice_ms / group, "slices_per_launch_sequence": group, "steps_per_slice": len(per_slice), "steps_once_per_call": len(rows) - len(per_slice),
         "step_table": table,
         "clocks": sampler.summary(),
         "gpu_launches": int(sum((3 if r["kernel"] == 2 else 2 if r["kernel"] == 3 else 1 if r["kernel"] < 4 else
@@ -441,10 +445,14 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=
         "scaling": "strong",
     }
     if do_cpu:
-        dt, amps, n_slices, fl_slice = c5_cpu_slices(int(os.environ.get("TQ_C5_CPU_SLICES", "4")))
-        got = [complex(cc.amplitude(bits, slice_range=(i, i + 1)).cpu()) for i in range(len(amps))]
+        n_cpu = int(os.environ.get("TQ_C5_CPU_SLICES", "4"))
+        groups = max(1, (n_cpu + group - 1) // group)
+        members = [cc._tn.slice_members(i) for i in range(groups)]
+        dt, amps, n_slices, fl_slice = c5_cpu_slices(0, slice_ids=[sid for m in members for sid in m])
+        got = [complex(cc.amplitude(bits, slice_range=(i, i + 1)).cpu()) for i in range(groups)]
+        want = [sum(amps[i * group:(i + 1) * group]) for i in range(groups)]
         scale = max(abs(a) for a in amps) or 1.0     # a slice can be exactly zero (a sliced wire next to a |0> cap)
-        err = max(abs(g - a) / scale for g, a in zip(got, amps))
+        err = max(abs(g - a) / scale for g, a in zip(got, want))
         res["cpu_baseline"] = {
             "value": 1.0 / (dt * n_slices), "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{len(amps)} of {n_slices} slices contracted with torch.tensordot complex64 on the host "

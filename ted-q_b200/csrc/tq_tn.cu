@@ -940,6 +940,7 @@ static int setup_steps(tq_tn_plan* p, int first) {
       const bool a_var = T.swap ? rhs_var : lhs_var, b_var = T.swap ? lhs_var : rhs_var;
       T.pin_a = p->dep_slice[s] && !a_var;
       T.pin_b = p->dep_slice[s] && !b_var;
+      if (getenv("TQ_TN_NO_PIN")) T.pin_a = T.pin_b = false;  // experiments: repack invariant operands every slice
     }
     T.shape_ok = n_row >= 7 && n_col >= 4 && n_row + n_col + st.n_b <= 31;
     if (!T.shape_ok) continue;

@@ -197,9 +197,12 @@ k_tc_pack(const __grid_constant__ PackPair pp) {
   const uint32_t bb = z & ((1u << p.n_b) - 1u);
   const uint32_t set = z >> p.n_b;
   // base source offset of this (set, bb, tile)
-  int64_t base = (int64_t)set * p.src_set_stride;
+  // bit offsets inside the tensor are OR-ed together; the set offset is ADDED (a per-set arena stride is not a
+  // multiple of the tensor's size in general)
+  int64_t base = 0;
   for (int j = 0; j < p.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << p.b_bits[j];
   for (int j = p.rows_t_log2; j < p.n_row; ++j) base |= (int64_t)((tile >> (j - p.rows_t_log2)) & 1u) << p.row_bits[j];
+  base += (int64_t)set * p.src_set_stride;
   if (p.n_k < KB_LOG) {  // K padded to one k-block: the missing columns are zero (nch == 1)
     for (int i = tid; i < chunk / 16; i += THREADS) reinterpret_cast<float4*>(pk_smem)[i] = make_float4(0, 0, 0, 0);
     __syncthreads();
@@ -481,11 +484,11 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         const int64_t r = t - z * tiles_per_z;
         const uint32_t ta = (uint32_t)(r % p.tiles_a);
         const uint32_t bb = (uint32_t)z & bb_mask;
-        int64_t base = (z >> P.n_b) * P.src_set_stride;
+        int64_t base = 0;
         for (int j = 0; j < P.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << P.b_bits[j];
         for (int j = 7; j < P.n_row; ++j) base |= (int64_t)((ta >> (j - 7)) & 1u) << P.row_bits[j];
         for (int j = KB_LOG; j < P.n_k; ++j) base |= (int64_t)(((uint32_t)kbi >> (j - KB_LOG)) & 1u) << P.k_bits[j];
-        const float2* src = P.src + base;
+        const float2* src = P.src + base + (z >> P.n_b) * P.src_set_stride;
         warp_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t dst = smem0 + (uint32_t)stage * sbytes;
         if (!(p.debug & 8)) {

@@ -360,10 +360,19 @@ class TNExecutor:
         if amp[2] is None:
             batched = [kind == OPD_GATE and self.gate_batched[ref] for kind, ref in net.operands]
             dt = capi.TQ_C64 if be._cdtype == torch.complex64 else capi.TQ_C128
-            amp[2] = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
+            grp = self._slice_group(net, info, batched)
+            self._amp_group = grp
+            if grp is None:
+                amp[2] = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
+            else:   # the grouped indices leave the network: their values become the plan's batch ("set") dimension
+                gset = set(grp["indices"])
+                inputs2 = [[ix for ix in t if ix not in gset] for t in net.inputs]
+                batched2 = [bool(grp["axes"].get(t)) for t in range(len(net.inputs))]
+                amp[2] = capi.TnPlan(inputs2, net.output, info.path, grp["rest"], batched2, dt)
             for opt, val in (self.ho.get("engine_opts") or {}).items():
                 amp[2].set_option(int(opt), int(val))
         plan = amp[2]
+        grp = getattr(self, "_amp_group", None)
         plan_sv = be.plan()
         L = capi.lib()
         B = flat.shape[0]
@@ -408,18 +417,81 @@ class TNExecutor:
             ptrs[closing] = np.where(bit_arr == 1, cap1.data_ptr(), cap0.data_ptr())
         strides = tab["stride"]
         any_b = bool((strides != 0).any())
+        keep = [gm, am, red_buf]
+        if grp is not None:
+            # slice group: every combination of the grouped indices is one "set" of the plan.  The few operands that
+            # carry a grouped index are re-laid out as [G sets][tensor without those indices] (tiny gate tensors).
+            assert B == 1 and not any_b
+            G = 1 << len(grp["indices"])
+            ptrs = ptrs.copy()
+            strides = strides.copy()
+            for t, axes in grp["axes"].items():
+                rank = len(net.inputs[t])
+                kind = int(tab["base"][t])
+                if tab["capq"][t] >= 0 or kind == 0:
+                    src = cap1 if ptrs[t] == cap1.data_ptr() else cap0
+                    full = src.reshape(-1)[: 1 << rank]
+                else:
+                    buf = gm if kind == 1 else red_buf
+                    off = int(tab["off"][t])
+                    full = buf.reshape(-1)[off: off + (1 << rank)]
+                full = full.reshape((2,) * rank)
+                rows = []
+                for sset in range(G):
+                    sel = [slice(None)] * rank
+                    for ax, gi in axes:        # gi: position of that index in the group (bit of the set id)
+                        sel[ax] = (sset >> gi) & 1
+                    rows.append(full[tuple(sel)].reshape(-1))
+                stacked = torch.stack(rows).contiguous()
+                keep.append(stacked)
+                ptrs[t] = stacked.data_ptr()
+                strides[t] = stacked.shape[1]
+            B = G
+            any_b = True
         out = torch.zeros((B if any_b else 1, 1), dtype=cd, device=dev)
         ws_bytes = plan.workspace_bytes(B)
         ws = getattr(self, "_amp_ws", None)
         if ws is None or ws.numel() < ws_bytes or ws.device != dev:
             ws = self._amp_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        return plan, ptrs, strides, out, ws, ws_bytes, any_b, (gm, am, red_buf)
+        return plan, ptrs, strides, out, ws, ws_bytes, any_b, tuple(keep)
+
+    def _slice_group(self, net, info, batched):
+        """hyper_opt["slice_batch"] = g: 2^g slices go through the device together as the batch dimension of ONE
+        launch sequence (default 3 when no gate is batched over parameter sets, fewer when ranks would go idle; 0 = one
+        slice at a time).  A slice
+        of a 40-qubit amplitude is ~20 launches of 20-90 us with one tile per SM: grouping slices gives every launch
+        several tiles per SM (prologue / epilogue overlap inside the persistent kernels) and divides the launch count.
+        -> None or {"indices": grouped sliced indices, "rest": the others, "axes": {tensor: [(axis, group bit)]}}."""
+        g = int(self.ho.get("slice_batch", 3))
+        if self.contract_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()     # keep at least one group per rank
+            while g > 0 and (info.n_slices >> g) < world:
+                g -= 1
+        if g <= 0 or any(batched) or not info.sliced or self.ho.get("tn_backward") == "tree":
+            return None
+        chosen, axes = [], {}
+        for ix in reversed(list(info.sliced)):
+            if len(chosen) == g:
+                break
+            holders = [t for t, idxs in enumerate(net.inputs) if ix in idxs]
+            # keep every operand at rank >= 1 after the grouped indices are taken out
+            if any(len(net.inputs[t]) - len(axes.get(t, [])) - 1 < 1 for t in holders):
+                continue
+            for t in holders:
+                axes.setdefault(t, []).append((net.inputs[t].index(ix), len(chosen)))
+            chosen.append(ix)
+        if not chosen:
+            return None
+        rest = [ix for ix in info.sliced if ix not in chosen]
+        return {"indices": chosen, "rest": rest, "axes": axes}
 
     def amplitude(self, flat: torch.Tensor, bits, slice_range=None):
         """<bits| U(params) |0...0> for every parameter set -> complex [B].  Slices are sharded over ranks
         (contract_parallel) and combined with one all-reduce."""
         plan, ptrs, strides, out, ws, ws_bytes, any_b, _keep = self._amplitude_operands(flat, bits)
         B = flat.shape[0]
+        grouped = getattr(self, "_amp_group", None) is not None
+        Bp = out.shape[0] if grouped else B      # sets of the plan: slice-group members, else parameter sets
         dev = flat.device
         stream = torch.cuda.current_stream(dev).cuda_stream
         if slice_range is None:
@@ -428,12 +500,34 @@ class TNExecutor:
             (s0, s1), dist_on = slice_range, False
         with torch.cuda.device(dev):
             if s1 > s0:
-                plan.contract(ptrs, strides, B, s0, s1, out.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+                plan.contract(ptrs, strides, Bp, s0, s1, out.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+        if grouped:
+            out = out.sum(0, keepdim=True)       # the grouped indices are summed like every sliced index
+            any_b = False
         if dist_on:
             if plan.n_slices == 1 and torch.distributed.get_rank() != 0:
                 out.zero_()
             torch.distributed.all_reduce(torch.view_as_real(out))
         return out.reshape(-1).expand(B) if not any_b else out.reshape(-1)
+
+    def slice_members(self, plan_slice: int):
+        """Slice ids of the path's own slicing (bit j <-> info.sliced[j]) that plan slice ``plan_slice`` covers: one
+        without slice groups, 2^g with them."""
+        info = self._amplitude_plan()[1]
+        grp = getattr(self, "_amp_group", None)
+        sliced = list(info.sliced)
+        if grp is None:
+            return [int(plan_slice)]
+        base = 0
+        for r, ix in enumerate(grp["rest"]):
+            base |= ((plan_slice >> r) & 1) << sliced.index(ix)
+        out = []
+        for m in range(1 << len(grp["indices"])):
+            sid = base
+            for gi, ix in enumerate(grp["indices"]):
+                sid |= ((m >> gi) & 1) << sliced.index(ix)
+            out.append(sid)
+        return out
 
     def amplitude_profile(self, flat: torch.Tensor, bits, slice_id=0):
         """Per-step timing of ONE slice of the amplitude contraction (tq_tn_profile): list of dicts with the step's
@@ -442,13 +536,15 @@ class TNExecutor:
         plan, ptrs, strides, out, ws, ws_bytes, _, _keep = self._amplitude_operands(flat, bits)
         dev = flat.device
         stream = torch.cuda.current_stream(dev).cuda_stream
+        Bp = out.shape[0] if getattr(self, "_amp_group", None) is not None else flat.shape[0]
         with torch.cuda.device(dev):
-            ms = plan.profile(ptrs, strides, flat.shape[0], slice_id, out.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+            ms = plan.profile(ptrs, strides, Bp, slice_id, out.data_ptr(), ws.data_ptr(), ws_bytes, stream)
         rows = []
         for s in range(plan.n_steps):
             st = plan.step(s)
             rows.append({"step": s, "k": st[2], "m": st[3], "n": st[4], "b": st[5], "kernel": plan.step_kernel(s),
-                         "per_slice": bool(plan.step_flags(s) & 1), "ms": float(ms[s, 0]), "pack_ms": float(ms[s, 1])})
+                         "per_slice": bool(plan.step_flags(s) & 1), "per_set": bool(plan.step_flags(s) & 2),
+                         "sets": Bp, "ms": float(ms[s, 0]), "pack_ms": float(ms[s, 1])})
         return rows
 
     def run(self, flat: torch.Tensor) -> torch.Tensor:

@@ -85,3 +85,59 @@ def test_oracle_tn_equals_oracle_sv(spec):
             order = np.argsort(np.argsort(spec["meas"][i][1]))
             ref = np.transpose(ref, order)
         assert np.allclose(t, ref, atol=1e-12)
+
+
+def test_slice_groups_partition_and_sum():
+    """Host logic of hyper_opt["slice_batch"]: the grouped sliced indices leave the network and become the plan's
+    batch dimension.  The groups partition the path's slices, no operand drops to rank 0, and contracting the
+    re-laid-out operands set by set (oracle) reproduces the sum of the member slices."""
+    import numpy as np
+    import torch
+    import tedq_b200 as qb
+    from oracle import tn_ref
+    from tedq_b200 import planner, tn_index
+    from tedq_b200 import workloads as W
+    from tedq_b200.tn_backend import TNExecutor, amplitude_network
+
+    spec = W.lattice_rcs(3, 3, 5, seed=4, measure="state")
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
+    net = amplitude_network(tn_index.networks_of_circuit(circ)[0], [0] * 9)
+    info = planner.slice_path(net.inputs, net.output, planner.find_path(net.inputs, net.output, repeats=2),
+                              target_num_slices=16)
+    arrays = [np.asarray(a) for a in tn_ref.operands(circ, torch.zeros(0, dtype=torch.float64))[0]] + \
+        [np.array([1.0, 0.0])] * 9
+    ex = object.__new__(TNExecutor)
+    ex.ho = {"slice_batch": 2}
+    ex.contract_parallel = False
+    ex._amp = [net, info, None]
+    grp = ex._slice_group(net, info, [False] * len(net.inputs))
+    assert grp is not None and len(grp["indices"]) == 2
+    assert sorted(grp["indices"] + grp["rest"]) == sorted(info.sliced)
+    ex._amp_group = grp
+    n_plan = 1 << len(grp["rest"])
+    seen = sorted(s for i in range(n_plan) for s in ex.slice_members(i))
+    assert seen == list(range(info.n_slices))
+    gset = set(grp["indices"])
+    inputs2 = [[ix for ix in t if ix not in gset] for t in net.inputs]
+    assert all(len(t) >= 1 for t in inputs2)
+
+    def one_slice(arrs, inputs, sliced, sid):
+        sl_a, sl_i = [], []
+        for a, ix in zip(arrs, inputs):
+            sel = tuple(((sid >> sliced.index(i)) & 1) if i in sliced else slice(None) for i in ix)
+            sl_a.append(a[sel])
+            sl_i.append([i for i in ix if i not in sliced])
+        return complex(tn_ref.contract_path(sl_a, sl_i, [], info.path))
+
+    for i in (0, n_plan - 1):
+        want = sum(one_slice(arrays, net.inputs, list(info.sliced), s) for s in ex.slice_members(i))
+        got = 0.0
+        for sset in range(4):      # the re-layout of TNExecutor._amplitude_operands, in numpy
+            arrs = []
+            for t, a in enumerate(arrays):
+                sel = [slice(None)] * a.ndim
+                for ax, gi in grp["axes"].get(t, []):
+                    sel[ax] = (sset >> gi) & 1
+                arrs.append(a[tuple(sel)])
+            got += one_slice(arrs, inputs2, list(grp["rest"]), i)
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want))

@@ -7,6 +7,7 @@ import tedq_b200 as qb
 from conftest import load_golden
 from helpers import TOL, assert_close, build, cdtype, golden_out, rdtype
 from oracle import sv_ref, tn_ref
+from tedq_b200 import capi
 from tedq_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
@@ -262,3 +263,37 @@ def test_tn_mode_without_parameters(simplify):
     got = cc().cpu().numpy()
     assert got.shape == (1, 2, 2, 2, 2)
     assert_close(got[0], ref.reshape(2, 2, 2, 2), 1e-6, "state")
+
+
+def test_slice_groups_match_single_slices():
+    """hyper_opt["slice_batch"] = g: 2^g slices share one launch sequence as the plan's batch dimension.  Same
+    amplitude for every g (tensor-core steps included), and plan slice i of the grouped backend is the sum of the
+    ungrouped slices slice_members(i) names."""
+    spec = W.lattice_rcs(4, 5, 10, seed=2, measure="state")
+    circ = W.build_circuit(spec, qb)
+    ref = sv_ref.run_sv(circ, torch.zeros(0), torch.complex64, return_state=True).numpy().reshape(-1)
+    bits = [0, 1] * 10
+    want = ref[int("".join(str(b) for b in bits), 2)]
+    ccs = {}
+    for g in (0, 1, 2, 3):
+        ho = {"max_repeats": 8, "slice_batch": g, "engine_opts": {capi.TN_OPT_TC_MIN_LOG2: 12},
+              "slicing_opts": {"target_num_slices": 16}}
+        cc = ccs[g] = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=ho)
+        amp = complex(cc.amplitude(bits).cpu())
+        assert abs(amp - want) <= 1e-5 * max(1.0, abs(want)), (g, amp, want)
+        plan = cc._tn._amplitude_plan()[2]
+        n_orig = cc._tn._amplitude_plan()[1].n_slices
+        assert plan.n_slices * len(cc._tn.slice_members(0)) == n_orig
+        if g:
+            assert len(cc._tn.slice_members(0)) == 1 << g
+            assert any(plan.step_kernel(s) == 2 for s in range(plan.n_steps))
+    n_orig = ccs[0]._tn._amplitude_plan()[1].n_slices
+    single = [complex(ccs[0].amplitude(bits, slice_range=(s, s + 1)).cpu()) for s in range(n_orig)]
+    scale = max(abs(a) for a in single)
+    seen = []
+    for i in range(ccs[2]._tn._amplitude_plan()[2].n_slices):
+        members = ccs[2]._tn.slice_members(i)
+        seen += members
+        got = complex(ccs[2].amplitude(bits, slice_range=(i, i + 1)).cpu())
+        assert abs(got - sum(single[m] for m in members)) <= 2e-6 * scale
+    assert sorted(seen) == list(range(n_orig))

@@ -108,7 +108,9 @@ def test_tc_error_is_fp32_class():
 
 
 @pytest.mark.parametrize("which", ["a", "b", "both"])
-@pytest.mark.parametrize("shape", [(8, 5, 6, 1), (7, 6, 11, 0)], ids=["plain", "splitk"])
+@pytest.mark.parametrize("shape", [(8, 5, 6, 1), (7, 6, 11, 0), (4, 7, 2, 0), (4, 7, 1, 0), (7, 7, 4, 0), (6, 7, 4, 0),
+                                   (8, 6, 6, 0), (8, 8, 6, 0), (7, 5, 6, 0), (8, 7, 5, 0)],
+                         ids=lambda s: "m%d_n%d_k%d_b%d" % s)
 @pytest.mark.parametrize("gather", [False, True], ids=["images", "gatherA"])
 def test_tc_step_batched_parameter_sets(which, shape, gather):
     rng = np.random.RandomState(11)
