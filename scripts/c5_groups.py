@@ -1,5 +1,6 @@
 """Config 5 (40-qubit amplitude, the bench's plan) timed for several slice-group sizes (hyper_opt["slice_batch"]).
 Usage: python scripts/c5_groups.py [g ...]"""
+import os
 import sys
 import time
 
@@ -8,7 +9,7 @@ import torch
 
 import bench
 import tedq_b200 as qb
-from tedq_b200 import workloads as W
+from tedq_b200 import capi, workloads as W
 
 gs = [int(v) for v in sys.argv[1:]] or [0, 1, 2, 3]
 spec = W.lattice_rcs(5, 8, 12, seed=0)
@@ -17,7 +18,8 @@ bits = [0] * 40
 for g in gs:
     hyper = {"max_repeats": bench.C5_HYPER["max_repeats"], "reconf_sweeps": bench.C5_HYPER["reconf_sweeps"],
              "time_model": bench.C5_HYPER["time_model"], "slicing_opts": dict(bench.C5_HYPER["slicing_opts"]),
-             "plan_cache": "/tmp/tq_plans", "slice_batch": g}
+             "plan_cache": "/tmp/tq_plans", "slice_batch": g,
+             "engine_opts": {capi.TN_OPT_TC_GATHER: int(os.environ.get("TQ_GATHER", "0"))}}
     t = time.time()
     cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
     amp = cc.amplitude(bits)
