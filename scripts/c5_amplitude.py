@@ -29,14 +29,16 @@ flat = torch.zeros((1, 0), device="cuda")
 amp = cc.amplitude(bits)
 torch.cuda.synchronize()
 net, info, plan = cc._tn._amplitude_plan()[:3]
-print(info, "flops/slice %.3e" % plan.flops, "slices", plan.n_slices, "width", plan.width, "steps", plan.n_steps)
+total_flops = 2.0 ** info.flops_log2 * info.n_slices
+print(info, "flops/slice %.3e" % 2.0 ** info.flops_log2, "slices", info.n_slices, "in", plan.n_slices,
+      "launch sequences, width", plan.width, "steps", plan.n_steps)
 for _ in range(2):
     torch.cuda.synchronize()
     t = time.time()
     amp = cc.amplitude(bits)
     torch.cuda.synchronize()
     dt = time.time() - t
-    print("amp", complex(amp.cpu()), "time %.4f s" % dt, "algorithmic TFLOP/s %.2f" % (plan.flops * plan.n_slices / dt / 1e12))
+    print("amp", complex(amp.cpu()), "time %.4f s" % dt, "algorithmic TFLOP/s %.2f" % (total_flops / dt / 1e12))
 a = cc.amplitude(bits, slice_range=(0, plan.n_slices // 2)) + cc.amplitude(bits, slice_range=(plan.n_slices // 2, plan.n_slices))
 print("halves", complex(a.cpu()))
 rows = cc._tn.amplitude_profile(torch.zeros((1, 0), device="cuda"), bits, 0)

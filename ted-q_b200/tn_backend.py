@@ -421,7 +421,7 @@ class TNExecutor:
         if grp is not None:
             # slice group: every combination of the grouped indices is one "set" of the plan.  The few operands that
             # carry a grouped index are re-laid out as [G sets][tensor without those indices] (tiny gate tensors).
-            assert B == 1 and not any_b
+            assert not any_b      # groups are only planned when no operand is batched over parameter sets
             G = 1 << len(grp["indices"])
             ptrs = ptrs.copy()
             strides = strides.copy()
