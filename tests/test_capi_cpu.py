@@ -65,3 +65,32 @@ def test_no_cpu_fallback_without_cuda():
     cc = qb.Circuit(circuit_def, 1, torch.tensor([0.1])).compilecircuit(backend="pytorch_b200")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cc(torch.tensor([0.1]))
+
+
+def test_qudio_front_host_contract_without_cuda():
+    """qudio_backend.py:86-111 twin: dataset bookkeeping and error behaviour of ``pytorch_QUDIO_b200`` that need no
+    device — no dataset -> ValueError; CPU parameters -> the same loud no-fallback error as the plain backend."""
+    import torch
+
+    import tedq_b200 as qb
+
+    def circuit_def(x, w):
+        qb.RX(x[0], qubits=[0])
+        qb.RY(w[0], qubits=[0])
+        return qb.expval(qb.PauliZ(qubits=[0]))
+
+    circ = qb.Circuit(circuit_def, 1, torch.tensor([0.1]), torch.tensor([0.2]))
+    cq = circ.compilecircuit(backend="pytorch_QUDIO_b200")
+    assert isinstance(cq, qb.B200QUDIOBackend) and cq.backend == "pytorch_QUDIO_b200"
+    with pytest.raises(ValueError, match="set_dataset"):
+        cq(torch.tensor([0.2]))
+    cq.set_dataset([0.1, 0.2, 0.3])                 # 1-D data: one value per row
+    assert tuple(cq.dataset().shape) == (3, 1)
+    d = torch.rand(5, 1)
+    cq.set_dataset(d)
+    assert cq.dataset() is d
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            cq(torch.tensor([0.2]))
+    with pytest.raises(ValueError, match="unknown backend input"):
+        circ.compilecircuit(backend="pytorch_QUDIO")
