@@ -297,6 +297,10 @@ def measure_workload(name, steps, warmup, device, dist_on, world, do_e2e=True, d
     return res
 
 
+# Pre-searched plans of the BASELINE networks (the planner's on-disk cache, hyper_opt["plan_cache"]): searched once
+# by scripts/make_bench_plans.py with exactly the options below and committed, so that a bench run spends its
+# time on the device, not in the 12 s path search.  A missing or foreign file only means the search runs again.
+PLAN_CACHE = os.path.join(ROOT, "ted-q_b200", "plans")
 C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "64")),
             "reconf_sweeps": int(os.environ.get("TQ_C5_RECONF", "6")),   # subtree reconfiguration of the greedy tree
             # objective of the reconfiguration: estimated step time = max(flops / 200 TFLOP/s, bytes / 2.5 TB/s) +
@@ -330,10 +334,17 @@ def c5_cpu_slices(n_slices_timed, slice_ids=None):
     cap0 = np.array([1, 0], dtype=np.complex64)
     inputs = [list(t) for t in inputs] + [[ix] for ix in output]
     arrays = list(arrays) + [cap0] * 40
-    info = planner.find_path(inputs, [], repeats=C5_HYPER["max_repeats"], seed=0, reconf_sweeps=C5_HYPER["reconf_sweeps"],
-                             time_model=C5_HYPER["time_model"])
-    info = planner.slice_path(inputs, [], info, target_size_log2=27, target_num_slices=64,
-                              reconf_sweeps=min(3, C5_HYPER["reconf_sweeps"]), time_model=C5_HYPER["time_model"])
+
+    def search():
+        first = planner.find_path(inputs, [], repeats=C5_HYPER["max_repeats"], seed=0,
+                                  reconf_sweeps=C5_HYPER["reconf_sweeps"], time_model=C5_HYPER["time_model"])
+        return planner.slice_path(inputs, [], first, target_size_log2=27, target_num_slices=64,
+                                  reconf_sweeps=min(3, C5_HYPER["reconf_sweeps"]), time_model=C5_HYPER["time_model"])
+
+    # same key as TNExecutor._plan_key(): the engine's amplitude plan and this one share a cache file
+    info = planner.cached_plan(PLAN_CACHE, inputs, [], search, max_repeats=C5_HYPER["max_repeats"], seed=0,
+                               minimize="flops", reconf_sweeps=C5_HYPER["reconf_sweeps"], reconf_leaves=8,
+                               time_model=C5_HYPER["time_model"], target_size=2 ** 27, target_num_slices=64)
     ids = list(slice_ids) if slice_ids is not None else list(range(n_slices_timed))
     tn_ref.contract_slice_torch(arrays, inputs, [], info.path, info.sliced, 0)   # warm-up (threads, allocator)
     amps = []
@@ -356,7 +367,7 @@ def measure_c5(steps, warmup, device, dist_on, world, do_cpu=False, greedy_plan=
     # the plan on which the tensor-core kernels are closest to their roofline
     hyper = {"max_repeats": C5_HYPER["max_repeats"], "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
              "time_model": None if greedy_plan else C5_HYPER["time_model"],
-             "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=dist_on)}
+             "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=dist_on), "plan_cache": PLAN_CACHE}
     cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
     bits = [0] * 40
     for _ in range(max(1, warmup)):
@@ -469,7 +480,7 @@ def measure_c5_simplified(steps, warmup, device):
 
     spec = W.lattice_rcs(5, 8, 12, seed=0)
     cc = W.build_circuit(spec, qb).compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=True,
-                                                  hyper_opt={"max_repeats": 64})
+                                                  hyper_opt={"max_repeats": 64, "plan_cache": PLAN_CACHE})
     bits = [0] * 40
     for _ in range(max(1, warmup)):
         amp = cc.amplitude(bits)

@@ -54,3 +54,18 @@ def test_plan_cache_round_trip(tmp_path):
     c = planner.cached_plan(str(tmp_path), inputs, [], build, max_repeats=2, target_num_slices=2)
     assert len(calls) == 3 and c.path == a.path
     assert planner.cached_plan(None, inputs, [], build).path == a.path and len(calls) == 4       # no cache dir: search
+
+
+def test_committed_bench_plans_are_hit(monkeypatch):
+    """ted-q_b200/plans/ holds the pre-searched plans of BASELINE config 5 (scripts/make_bench_plans.py): with
+    bench.py's options the planner's cache must answer without searching, and the stored plan must be the one the
+    bench documents (64 slices, width 23, 2.7e12 flop per amplitude)."""
+    import bench
+
+    def no_search(*a, **k):
+        raise AssertionError("plan cache miss: re-run scripts/make_bench_plans.py")
+
+    monkeypatch.setattr(planner, "find_path", no_search)
+    dt, amps, n_slices, flops_per_slice = bench.c5_cpu_slices(0, slice_ids=[])
+    assert n_slices == 64 and amps == []
+    assert 2.5e12 < flops_per_slice * n_slices < 2.8e12
