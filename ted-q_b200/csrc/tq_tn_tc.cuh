@@ -18,7 +18,9 @@
 // swizzle into "operand images" — every (row tile, k block) is one contiguous chunk in HBM that is exactly the
 // shared-memory image the MMA wants, so the GEMM kernel's producer is two bulk-async (TMA engine) copies per
 // stage, no tensor maps.  GEMM kernel: persistent, warp-specialised (bulk-copy producer / single-thread MMA
-// issuer / 4 epilogue warps), 2-4 smem stages, double-buffered TMEM accumulator (2 x 256 columns).
+// issuer / 8 accumulation warps that drain TMEM into fp32 registers and write C), 2-4 smem stages,
+// double-buffered TMEM accumulator (2 x 256 columns).  An opt-in variant (k_tc_gemm<C_T, true>) gathers and splits
+// the row operand itself instead of reading its image (see the comment above the kernel).
 #pragma once
 #include "tq_common.h"
 
@@ -289,7 +291,9 @@ struct GemmParams {
   int64_t c_rs, c_cs;        // complex-entry stride of an accumulator row / column inside C
   int32_t tiles_a, tiles_b, kblocks, n_z, n_b_log2, stages;
   int32_t chunk;             // k-blocks accumulated inside the tensor core before a drain (see below)
-  int32_t debug;             // experiments only: bit 0 = drains skip their TMEM loads (wrong results)
+  // experiments only (TQ_TC_DEBUG; bits 0-3 give wrong results): bit 0 = drains skip their TMEM loads; gather-A
+  // variant: bit 1 = no generic->async proxy fence, bit 2 = no conversion, bit 3 = no loads, bit 4 = every lane polls
+  int32_t debug;
   // split-K: a step with few output tiles and a long K is cut into `splits` K ranges per tile so that every SM
   // has work; split s writes its partial sums to c + s * c_split_stride, k_tc_splitk_sum adds them in order
   int32_t splits, kb_per_split;

@@ -463,6 +463,10 @@ class TNExecutor:
         several tiles per SM (prologue / epilogue overlap inside the persistent kernels) and divides the launch count.
         -> None or {"indices": grouped sliced indices, "rest": the others, "axes": {tensor: [(axis, group bit)]}}."""
         g = int(self.ho.get("slice_batch", 3))
+        # memory: the per-set arena is a few times the largest intermediate (2^width entries); keep a group's
+        # largest tensors at <= 2^28 entries together (2 GiB complex64) unless the caller asked for a size
+        if "slice_batch" not in self.ho:
+            g = min(g, max(0, 28 - int(info.width)))
         if self.contract_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()     # keep at least one group per rank
             while g > 0 and (info.n_slices >> g) < world:

@@ -114,6 +114,14 @@ def test_slice_groups_partition_and_sum():
     assert grp is not None and len(grp["indices"]) == 2
     assert sorted(grp["indices"] + grp["rest"]) == sorted(info.sliced)
     ex._amp_group = grp
+    # default size: 2^3 slices, fewer when the network is wide (memory) — never for parameter-batched operands
+    ex.ho = {}
+    assert len(ex._slice_group(net, info, [False] * len(net.inputs))["indices"]) == 3
+    wide = lambda w: planner.PathInfo(info.path, info.sliced, w, info.flops_log2, info.n_steps)
+    assert len(ex._slice_group(net, wide(27), [False] * len(net.inputs))["indices"]) == 1
+    assert ex._slice_group(net, wide(30), [False] * len(net.inputs)) is None
+    assert ex._slice_group(net, info, [True] + [False] * (len(net.inputs) - 1)) is None
+    ex.ho = {"slice_batch": 2}
     n_plan = 1 << len(grp["rest"])
     seen = sorted(s for i in range(n_plan) for s in ex.slice_members(i))
     assert seen == list(range(info.n_slices))
