@@ -197,6 +197,18 @@ typedef struct tq_tn_step {
   int32_t out_idx[TQ_TN_MAX_RANK];
 } tq_tn_step;
 
+/* Planner, host only: the dynamic programme of the subtree reconfiguration (ted-q_b200/planner.py: reconfigure; the
+ * search the reference delegates to cotengra / jdtensorpath, compiled_circuit.py:340-393).  A subtree has n_leaves
+ * (2..12) leaf tensors over n_idx distinct indices: leaf_open[l][x] != 0 when index x is an open leg of leaf l,
+ * inside[l][x] = how many input tensors below leaf l carry x, count[x] = how many tensors of the whole network (plus
+ * the output) carry x.  Finds for every subset S of the leaves the cheapest way to contract it pairwise
+ * (cost of a pair = 2^|union of open legs|, or with time_model = {flop/s, bytes/s, s per step} the estimated step
+ * time of planner.step_time_model); *best_full = cost of the whole subtree, split[S] = the first part of S's best
+ * split (the part that contains S's lowest leaf), for every S with at least two leaves.  Bit-identical to the
+ * Python mirror planner._subtree_dp_py.  Returns 0 or a negative tq_status. */
+int32_t tq_tn_subtree_order(int32_t n_leaves, int32_t n_idx, const int32_t* leaf_open, const int32_t* inside,
+                            const int32_t* count, const double* time_model, double* best_full, int32_t* split);
+
 /* Lower an ssa path over n_in input tensors into steps (host only).  sliced[] index ids become per-slice base
  * offsets of the inputs that carry them: slice_tensor[i], slice_ord[i], slice_bit[i] (count returned in
  * *n_slice_entries, capacity slice_cap).  final_perm[j] = bit of the last tensor that becomes output bit j

@@ -80,6 +80,9 @@ def lib() -> C.CDLL:
                                  i32, i32, C.POINTER(C.c_double), C.POINTER(PlanOpts), C.POINTER(vp)]
     L.tq_plan_destroy.argtypes = [vp]
     L.tq_plan_destroy.restype = None
+    L.tq_tn_subtree_order.restype = i32
+    L.tq_tn_subtree_order.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(i32)]
     for name in ("tq_plan_num_qubits", "tq_plan_num_params"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = i32

@@ -168,14 +168,92 @@ def step_time_model(n_a: int, n_b: int, n_out: int, n_union: int, model) -> floa
     return max(8.0 * 2.0 ** n_union / f, 8.0 * (2.0 ** n_a + 2.0 ** n_b + 2.0 ** n_out) / bw) + t0
 
 
-def reconfigure(inputs, output, path, max_leaves: int = 8, sweeps: int = 3, sliced=(), time_model=None):
+def _subtree_dp_py(leaf_sets, leaf_inside, count, time_model):
+    """Cheapest pairwise contraction order of a subtree's leaves by dynamic programming over subsets.
+    leaf_sets[i]: open indices of leaf i; leaf_inside[i]: {index: number of input tensors below leaf i that carry
+    it}; count: {index: number of tensors of the network (+ output) that carry it}.  -> (cost of the whole
+    subtree, split) with split[S] = the part of subset S (bit mask over leaves) that is contracted first and
+    contains S's lowest leaf.  Python mirror of tq_tn_subtree_order (csrc/tq_planner.cu)."""
+    L = len(leaf_sets)
+    full = (1 << L) - 1
+
+    def pair_cost(sa, sb, so):
+        if time_model is None:
+            return 2.0 ** len(sa | sb)
+        return step_time_model(len(sa), len(sb), len(so), len(sa | sb), time_model)
+
+    insm = {1 << i: leaf_inside[i] for i in range(L)}
+    sidx = {1 << i: leaf_sets[i] for i in range(L)}
+    best = {1 << i: 0.0 for i in range(L)}
+    split = {}
+    for S in range(1, full + 1):
+        if S & (S - 1) == 0:
+            continue
+        low = S & -S
+        m = dict(insm[S ^ low])
+        for ix, c in insm[low].items():
+            m[ix] = m.get(ix, 0) + c
+        insm[S] = m
+        sidx[S] = frozenset(ix for ix, c in m.items() if c < count[ix])
+        b, bs = None, 0
+        sub = (S - 1) & S
+        while sub:
+            if sub & low:   # canonical split: the lowest member stays in the first part
+                o = S ^ sub
+                c = best[sub] + best[o] + pair_cost(sidx[sub], sidx[o], sidx[S])
+                if b is None or c < b:
+                    b, bs = c, sub
+            sub = (sub - 1) & S
+        best[S], split[S] = b, bs
+    return best[full], split
+
+
+def _subtree_dp_native(leaf_sets, leaf_inside, count, time_model):
+    """The same through the C ABI (tq_tn_subtree_order): dense arrays over the indices the leaves touch."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import capi
+
+    L = len(leaf_sets)
+    idx = {}
+    for m in leaf_inside:
+        for ix in m:
+            idx.setdefault(ix, len(idx))
+    n_idx = len(idx)
+    open_a = np.zeros((L, max(1, n_idx)), dtype=np.int32)
+    inside_a = np.zeros((L, max(1, n_idx)), dtype=np.int32)
+    for i in range(L):
+        for ix, c in leaf_inside[i].items():
+            inside_a[i, idx[ix]] = c
+        for ix in leaf_sets[i]:
+            open_a[i, idx[ix]] = 1
+    count_a = np.zeros(max(1, n_idx), dtype=np.int32)
+    for ix, x in idx.items():
+        count_a[x] = count[ix]
+    split = np.zeros(1 << L, dtype=np.int32)
+    best = C.c_double(0.0)
+    model = None
+    if time_model is not None:
+        model = (C.c_double * 3)(*[float(v) for v in time_model])
+    i32p = C.POINTER(C.c_int32)
+    capi.check(capi.lib().tq_tn_subtree_order(L, n_idx, open_a.ctypes.data_as(i32p), inside_a.ctypes.data_as(i32p),
+                                              count_a.ctypes.data_as(i32p), model, C.byref(best),
+                                              split.ctypes.data_as(i32p)), "tq_tn_subtree_order")
+    return best.value, split
+
+
+def reconfigure(inputs, output, path, max_leaves: int = 8, sweeps: int = 3, sliced=(), time_model=None,
+                native: bool = True):
     """Subtree reconfiguration: for every node of the contraction tree, cut out the subtree spanned by its
     ``max_leaves`` largest descendants, find the cheapest order of contracting those leaves by dynamic programming
     over subsets (cost = sum of 2^|indices of the pair|), and splice it in when it beats the current order.
     Repeats for ``sweeps`` passes or until nothing improves.  ``sliced`` indices are treated as fixed (dropped), so
     the same routine re-optimises the per-slice tree after slicing.  ``time_model`` (see step_time_model) replaces
     the flop count by an estimate of the step's run time, which keeps the tree away from long chains of skinny,
-    bandwidth-bound steps that a pure flop count likes.  -> ssa path over the same inputs."""
+    bandwidth-bound steps that a pure flop count likes.  ``native``: the dynamic programme runs in the compiled
+    library (tq_tn_subtree_order); False = its Python mirror, bit-identical.  -> ssa path over the same inputs."""
     import sys
 
     n_in = len(inputs)
@@ -242,30 +320,9 @@ def reconfigure(inputs, output, path, max_leaves: int = 8, sweeps: int = 3, slic
                 continue
             cur = sum(pair_cost(sets[children[u][0]], sets[children[u][1]], sets[u]) for u in internal)
             full = (1 << L) - 1
-            insm = {1 << i: inside[frontier[i]] for i in range(L)}
-            sidx = {1 << i: sets[frontier[i]] for i in range(L)}
-            best = {1 << i: 0.0 for i in range(L)}
-            split = {}
-            for S in range(1, full + 1):
-                if S & (S - 1) == 0:
-                    continue
-                low = S & -S
-                m = dict(insm[S ^ low])
-                for ix, c in insm[low].items():
-                    m[ix] = m.get(ix, 0) + c
-                insm[S] = m
-                sidx[S] = frozenset(ix for ix, c in m.items() if c < count[ix])
-                b, bs = None, 0
-                sub = (S - 1) & S
-                while sub:
-                    if sub & low:   # canonical split: the lowest member stays in the first part
-                        o = S ^ sub
-                        c = best[sub] + best[o] + pair_cost(sidx[sub], sidx[o], sidx[S])
-                        if b is None or c < b:
-                            b, bs = c, sub
-                    sub = (sub - 1) & S
-                best[S], split[S] = b, bs
-            if best[full] >= cur * 0.999:
+            dp = _subtree_dp_native if native and L <= 12 else _subtree_dp_py
+            best_full, split = dp([sets[u] for u in frontier], [inside[u] for u in frontier], count, time_model)
+            if best_full >= cur * 0.999:
                 continue
             improved = True
             for u in internal:
@@ -274,7 +331,8 @@ def reconfigure(inputs, output, path, max_leaves: int = 8, sweeps: int = 3, slic
             while stack:
                 S, nid = stack.pop()
                 parts = []
-                for part in (split[S], S ^ split[S]):
+                first = int(split[S])
+                for part in (first, S ^ first):
                     if part & (part - 1) == 0:
                         parts.append(frontier[part.bit_length() - 1])
                     else:

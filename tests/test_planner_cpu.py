@@ -69,3 +69,43 @@ def test_committed_bench_plans_are_hit(monkeypatch):
     dt, amps, n_slices, flops_per_slice = bench.c5_cpu_slices(0, slice_ids=[])
     assert n_slices == 64 and amps == []
     assert 2.5e12 < flops_per_slice * n_slices < 2.8e12
+
+
+def test_native_subtree_dp_is_bit_identical_to_python_mirror():
+    """tq_tn_subtree_order (C ABI, csrc/tq_planner.cu) against planner._subtree_dp_py on random subtrees: same cost
+    bits and the same split for every subset, with and without the step-time model."""
+    import random
+
+    rng = random.Random(7)
+    for trial in range(40):
+        L = rng.randint(2, 8)
+        n_idx = rng.randint(1, 70)
+        count = {ix: rng.randint(1, 4) for ix in range(n_idx)}
+        leaf_inside, leaf_sets = [], []
+        for _ in range(L):
+            m = {ix: rng.randint(1, count[ix]) for ix in rng.sample(range(n_idx), rng.randint(1, min(n_idx, 24)))}
+            leaf_inside.append(m)
+            leaf_sets.append(frozenset(ix for ix, c in m.items() if c < count[ix] or rng.random() < 0.1))
+        for ix in range(n_idx):      # a leaf set may not hold more carriers than the network has
+            tot = sum(m.get(ix, 0) for m in leaf_inside)
+            count[ix] = max(count[ix], tot)
+        for model in (None, (2.0e14, 2.5e12, 1.2e-5)):
+            b_py, s_py = planner._subtree_dp_py(leaf_sets, leaf_inside, count, model)
+            b_c, s_c = planner._subtree_dp_native(leaf_sets, leaf_inside, count, model)
+            assert b_py == b_c, (trial, b_py, b_c)
+            assert all(int(s_c[S]) == s_py[S] for S in s_py), trial
+
+
+def test_native_reconfigure_reproduces_python_path_and_committed_plan():
+    """Whole reconfiguration: native and mirror give the same ssa path; and the search with bench.py's options still
+    reproduces the committed 40-qubit plan (ted-q_b200/plans/), i.e. the compiled planner did not move the plan the
+    GPU numbers were measured on."""
+    spec = W.lattice_rcs(3, 4, 6, seed=1, measure="state")
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
+    inputs, output = tn_ref.index_maps(circ)[0]
+    inputs = [list(t) for t in inputs] + [[ix] for ix in output]
+    start = planner.find_path(inputs, [], repeats=2, seed=0).path
+    for model in (None, (2.0e14, 2.5e12, 1.2e-5)):
+        a = planner.reconfigure(inputs, [], start, sweeps=2, time_model=model, native=True)
+        b = planner.reconfigure(inputs, [], start, sweeps=2, time_model=model, native=False)
+        assert a == b
