@@ -94,3 +94,36 @@ def test_qudio_front_host_contract_without_cuda():
             cq(torch.tensor([0.2]))
     with pytest.raises(ValueError, match="unknown backend input"):
         circ.compilecircuit(backend="pytorch_QUDIO")
+
+
+def test_product_sources_never_touch_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under the package (Python or CUDA) may import, open or name it,
+    nor read /root/reference at run time; bench.py may use it only in its CPU legs and __graft_entry__ only in
+    smoke()."""
+    import ast
+    import os
+
+    from conftest import ROOT
+
+    pkg = os.path.join(ROOT, "ted-q_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+            assert "/root/reference" not in text, f
+            if f.endswith(".py"):
+                tree = ast.parse(text)
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        names = [node.module or ""]
+                    assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (f, names)
+    # bench.py: oracle imports live inside functions of the CPU legs only (never at module level)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read())
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names)
