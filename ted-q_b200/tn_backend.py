@@ -35,7 +35,10 @@ class TNExecutor:
         # tn_simplify=True (the reference's default; its own simplifier does not work, tensor_network.py:94):
         # diagonal / controlled gates enter with shared wire indices and reduced tensors (tn_simplify.py)
         self.simplify = bool(getattr(backend, "_tn_simplify", False))
-        self.networks = (tn_simplify if self.simplify else tn_index).networks_of_circuit(circuit)
+        # hyper_opt["light_cone"] (opt-in): expval / marginal networks keep only the gates inside the measurement's
+        # causal cone (tn_index.light_cone); the gates outside cancel against their own adjoints
+        self.networks = (tn_simplify if self.simplify else tn_index).networks_of_circuit(
+            circuit, prune_light_cone=bool(self.ho.get("light_cone", False)))
         self.gate_structs = tn_simplify.gate_structures(circuit) if self.simplify else [None] * len(circuit.operators)
         self.gate_batched = [any(i >= 0 for i in g.param_idx) for g in backend._ir.gates]
         self.infos: List[planner.PathInfo] = []

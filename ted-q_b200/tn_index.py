@@ -63,10 +63,36 @@ def _thread(wire_id: List[int], cur: int, qubits: Sequence[int]):
     return idx, cur + k
 
 
-def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measurements) -> List[Network]:
+def light_cone(gate_qubits: Sequence[Sequence[int]], qubits: Sequence[int]) -> List[int]:
+    """Gates (ids, ascending) inside the causal cone of ``qubits`` at the end of the circuit: walking the gate list
+    backwards, a gate belongs to the cone when it touches a qubit the cone has reached.  Every other gate meets its
+    own adjoint in <0|U^dagger O U|0> (or under the partial trace of a marginal) and cancels: U^dagger U = 1."""
+    active = set(int(q) for q in qubits)
+    cone = []
+    for gi in range(len(gate_qubits) - 1, -1, -1):
+        qs = set(int(q) for q in gate_qubits[gi])
+        if active & qs:
+            cone.append(gi)
+            active |= qs
+    return cone[::-1]
+
+
+def cone_of_measurement(gate_qubits, kind, payload):
+    """Gate ids a measurement's network needs under light-cone pruning, or None (no pruning: state(), probs())."""
+    if kind == "expval":
+        return light_cone(gate_qubits, [q for qs in payload for q in qs])
+    if kind == "probs" and payload is not None:
+        return light_cone(gate_qubits, payload)
+    return None
+
+
+def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measurements,
+               prune_light_cone: bool = False) -> List[Network]:
     """``measurements``: sequence of (kind, payload) with kind in {"expval", "probs", "state"};
     payload = list of observable qubit-lists (expval: one entry per observable of a list observable,
-    or a single multi-qubit entry), kept-qubit list or None (probs), None (state)."""
+    or a single multi-qubit entry), kept-qubit list or None (probs), None (state).
+    ``prune_light_cone`` (not in the reference, whose networks always hold every gate twice): expval / marginal
+    networks keep only the gates inside the measurement's causal cone; operand refs stay the circuit's gate ids."""
     n = num_qubits
     wire0 = list(range(n))
     cur0 = n - 1
@@ -83,6 +109,16 @@ def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measuremen
         cur = cur0
         inputs = [list(t) for t in base_inputs]
         ops = list(base_ops)
+        gates = list(range(len(gate_qubits)))
+        cone = cone_of_measurement(gate_qubits, kind, payload) if prune_light_cone else None
+        if cone is not None and len(cone) < len(gates):
+            gates = cone
+            wire, cur = list(range(n)), n - 1
+            inputs, ops = [[q] for q in range(n)], [(OPD_CAP, q) for q in range(n)]
+            for gi in gates:
+                idx, cur = _thread(wire, cur, list(gate_qubits[gi]))
+                inputs.append(idx)
+                ops.append((OPD_GATE, gi))
         output: List[int] = []
         if kind == "state":
             output = [wire[q] for q in range(n)]
@@ -98,7 +134,7 @@ def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measuremen
                 output = [wire[q] for q in payload]
         else:
             raise ValueError(kind)
-        for gi in range(len(gate_qubits) - 1, -1, -1):
+        for gi in reversed(gates):
             qs = list(gate_qubits[gi])
             if len(qs) > 3:
                 raise ValueError("Error!! unknown operator with len of applied qubits larger than 3!")
@@ -112,7 +148,7 @@ def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measuremen
     return nets
 
 
-def networks_of_circuit(circuit) -> List[Network]:
+def networks_of_circuit(circuit, prune_light_cone: bool = False) -> List[Network]:
     meas = []
     for ms in circuit.measurements:
         rt = getattr(ms.return_type, "value", ms.return_type)
@@ -125,4 +161,4 @@ def networks_of_circuit(circuit) -> List[Network]:
             meas.append(("state", None))
         else:
             raise NotImplementedError(rt)
-    return index_maps(circuit.num_qubits, [list(op.qubits) for op in circuit.operators], meas)
+    return index_maps(circuit.num_qubits, [list(op.qubits) for op in circuit.operators], meas, prune_light_cone)

@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .tn_index import OPD_ADJ, OPD_CAP, OPD_GATE, OPD_OBS, Network
+from .tn_index import OPD_ADJ, OPD_CAP, OPD_GATE, OPD_OBS, Network, cone_of_measurement
 
 DIAG1 = {"I", "PauliZ", "S", "T", "RZ", "PhaseShift"}
 DIAG2 = {"CZ", "ControlledPhaseShift", "CRZ"}
@@ -78,7 +78,8 @@ def _thread(wire: List[int], cur: int, qubits: Sequence[int], st):
     return idx, cur + n_t
 
 
-def index_maps(num_qubits: int, gate_qubits, gate_structs, measurements, obs_structs=None) -> List[Network]:
+def index_maps(num_qubits: int, gate_qubits, gate_structs, measurements, obs_structs=None,
+               prune_light_cone: bool = False) -> List[Network]:
     """Same contract as tn_index.index_maps plus ``gate_structs[g]`` (``structure`` result or None) and, per
     expval measurement, ``obs_structs[m][j]``.  Network.reductions[t] = entry offsets of operand t or None."""
     n = num_qubits
@@ -96,6 +97,18 @@ def index_maps(num_qubits: int, gate_qubits, gate_structs, measurements, obs_str
     for mi, (kind, payload) in enumerate(measurements):
         wire, cur = list(wire0), cur0
         inputs, ops, red = [list(t) for t in base_inputs], list(base_ops), list(base_red)
+        gates = list(range(len(gate_qubits)))
+        cone = cone_of_measurement(gate_qubits, kind, payload) if prune_light_cone else None
+        if cone is not None and len(cone) < len(gates):      # tn_index.light_cone: the other gates cancel
+            gates = cone
+            wire, cur = list(range(n)), n - 1
+            inputs, ops = [[q] for q in range(n)], [(OPD_CAP, q) for q in range(n)]
+            red = [None] * n
+            for gi in gates:
+                idx, cur = _thread(wire, cur, list(gate_qubits[gi]), gate_structs[gi])
+                inputs.append(idx)
+                ops.append((OPD_GATE, gi))
+                red.append(gate_structs[gi][2] if gate_structs[gi] else None)
         output: List[int] = []
         if kind == "state":
             net = Network(inputs, [wire[q] for q in range(n)], ops)
@@ -114,7 +127,7 @@ def index_maps(num_qubits: int, gate_qubits, gate_structs, measurements, obs_str
                 output = [wire[q] for q in payload]
         else:
             raise ValueError(kind)
-        for gi in range(len(gate_qubits) - 1, -1, -1):
+        for gi in reversed(gates):
             qs = list(gate_qubits[gi])
             if len(qs) > 3:
                 raise ValueError("Error!! unknown operator with len of applied qubits larger than 3!")
@@ -136,7 +149,7 @@ def gate_structures(circuit):
     return [verified_structure(op.name, len(op.qubits), getattr(op, "matrix", None)) for op in circuit.operators]
 
 
-def networks_of_circuit(circuit) -> List[Network]:
+def networks_of_circuit(circuit, prune_light_cone: bool = False) -> List[Network]:
     meas, obs_structs = [], []
     for ms in circuit.measurements:
         rt = getattr(ms.return_type, "value", ms.return_type)
@@ -153,4 +166,4 @@ def networks_of_circuit(circuit) -> List[Network]:
         else:
             raise NotImplementedError(rt)
     return index_maps(circuit.num_qubits, [list(op.qubits) for op in circuit.operators], gate_structures(circuit),
-                      meas, obs_structs)
+                      meas, obs_structs, prune_light_cone)

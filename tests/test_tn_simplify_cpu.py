@@ -78,3 +78,61 @@ def test_simplification_cuts_the_cost_of_the_lattice_circuit():
     fd = planner.find_path(cap(dense), [], repeats=4).flops_log2
     fs = planner.find_path(cap(simp), [], repeats=4).flops_log2
     assert fs < fd - 2, (fs, fd)
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("simplify", [False, True], ids=["dense", "structured"])
+def test_light_cone_pruned_networks_equal_the_full_ones(seed, simplify):
+    """hyper_opt["light_cone"]: networks of expval / marginal measurements without the gates outside the causal
+    cone contract (oracle, numpy) to the same numbers as the reference-exact networks; state() and probs() are
+    left whole; the cone really removes gates when the observable sits on few qubits of a shallow circuit."""
+    from tedq_b200 import tn_index
+
+    meas = [["expval", [["PauliZ", [1]]]], ["probs", [0, 3]], ["state"], ["expval", [["PauliX", [2]], ["PauliZ", [4]]]],
+            ["probs", None]]
+    spec = W.random_circuit(6, 14, seed=seed, meas=meas)
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
+    flat = torch.rand(spec["n_params"], dtype=torch.float64)
+    mod = tn_simplify if simplify else tn_index
+    full = mod.networks_of_circuit(circ)
+    pruned = mod.networks_of_circuit(circ, prune_light_cone=True)
+    ref = tn_ref.run_tn(circ, flat, torch.complex128)
+    arrays_all = tn_ref.operands(circ, flat, torch.complex128)
+    fewer = 0
+    for m, (net_f, net_p, arrs, r) in enumerate(zip(full, pruned, arrays_all, ref)):
+        if meas[m][0] == "state" or (meas[m][0] == "probs" and meas[m][1] is None):
+            assert net_p.inputs == net_f.inputs and net_p.operands == net_f.operands
+            continue
+        lookup = {}
+        red_f = getattr(net_f, "reductions", None) or [None] * len(net_f.operands)
+        for key, a, red in zip(net_f.operands, arrs, red_f):
+            a = np.asarray(a)
+            if red is not None:
+                a = a.reshape(-1)[list(red)].reshape((2,) * int(np.log2(len(red))))
+            lookup[key] = a
+        ops = [lookup[key] for key in net_p.operands]
+        assert [len(t) for t in net_p.inputs] == [o.ndim for o in ops]
+        assert len(net_p.inputs) <= len(net_f.inputs)
+        fewer += len(net_f.inputs) - len(net_p.inputs)
+        gates_f = sorted(ref_ for kind, ref_ in net_f.operands if kind == tn_index.OPD_GATE)
+        gates_p = sorted(ref_ for kind, ref_ in net_p.operands if kind == tn_index.OPD_GATE)
+        adj_p = sorted(ref_ for kind, ref_ in net_p.operands if kind == tn_index.OPD_ADJ)
+        assert gates_p == adj_p and set(gates_p) <= set(gates_f)
+        info = planner.find_path(net_p.inputs, net_p.output, repeats=2, seed=seed)
+        got = np.asarray(tn_ref.contract_path(ops, net_p.inputs, net_p.output, info.path))
+        want = np.asarray(r)
+        got = got if np.iscomplexobj(want) else np.real(got)
+        assert np.abs(got - want).max() < 1e-12, (m, np.abs(got - want).max())
+    assert fewer > 0
+
+
+def test_light_cone_of_a_brick_circuit():
+    from tedq_b200 import tn_index
+
+    gq = [[0, 1], [2, 3], [4, 5], [1, 2], [3, 4], [0], [5]]
+    # gate 4 = [3, 4] acts after [4, 5] and nothing later links it to qubit 5: it cancels against its adjoint
+    assert tn_index.light_cone(gq, [5]) == [2, 6]
+    assert tn_index.light_cone(gq, [0]) == [0, 5]
+    assert tn_index.light_cone(gq, [0, 5]) == [0, 2, 5, 6]
+    assert tn_index.light_cone(gq, [3]) == [1, 2, 4]
+    assert tn_index.light_cone(gq, []) == []
