@@ -77,8 +77,8 @@ def test_native_subtree_dp_is_bit_identical_to_python_mirror():
     import random
 
     rng = random.Random(7)
-    for trial in range(40):
-        L = rng.randint(2, 8)
+    for trial in range(44):
+        L = rng.randint(2, 8) if trial < 40 else rng.randint(9, 11)   # a few large subtrees (the C limit is 12)
         n_idx = rng.randint(1, 70)
         count = {ix: rng.randint(1, 4) for ix in range(n_idx)}
         leaf_inside, leaf_sets = [], []
