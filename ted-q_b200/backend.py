@@ -285,7 +285,7 @@ class B200Backend:
         self._shapes_ok = len(shapes) == 1 and len(kinds) == 1
         self._res_shape = next(iter(shapes)) if self._shapes_ok else None
         self._res_complex = next(iter(kinds)) if self._shapes_ok else False
-        self._plan: Optional[capi.Plan] = None
+        self._plans = {}          # CUDA device index -> capi.Plan (a plan's tables live on ONE device)
         self._device = None
         self._last_flat = None
         self._tn = None
@@ -297,15 +297,21 @@ class B200Backend:
                 self._calculation_mode = self._hyper_opt["slicing_opts"].get("contract_parallel", False)
 
     # ------------------------------------------------------------------ plan
-    def plan(self) -> capi.Plan:
-        if self._plan is None:
+    def plan(self, device=None) -> capi.Plan:
+        """The engine plan of ``device`` (default: the current CUDA device).  Plans are created and cached per
+        device, inside that device's context: their descriptor tables are device memory (the reference's backend
+        accepts any device on every call, pytorch_backend.py:85-119)."""
+        idx = capi.device_index(device)
+        plan = self._plans.get(idx)
+        if plan is None:
             dt = capi.TQ_C64 if self._cdtype == torch.complex64 else capi.TQ_C128
-            self._plan = capi.Plan(self._ir, dt, self._plan_opts)
-        return self._plan
+            with capi.on_device(idx):
+                plan = self._plans[idx] = capi.Plan(self._ir, dt, self._plan_opts)
+        return plan
 
     # ------------------------------------------------------------ device side
     def _forward_device(self, flat: torch.Tensor, need_grad: bool):
-        plan = self.plan()
+        plan = self.plan(flat.device)
         B = flat.shape[0]
         flat = flat.contiguous()
         out = torch.empty((B, plan.out_reals), dtype=self._rdtype, device=flat.device)
@@ -317,7 +323,7 @@ class B200Backend:
         return self._shape_result(out), (ws if need_grad else None)
 
     def _backward_device(self, flat, dy, ws):
-        plan = self.plan()
+        plan = self.plan(flat.device)
         B = flat.shape[0]
         flat = flat.contiguous()
         if self._res_complex:
@@ -632,12 +638,15 @@ class B200Backend:
         flat = getattr(self, "_last_flat", None)
         if target is None or flat is None:
             raise ValueError("no states after measurement found! please measure probs with qubits.")
-        if getattr(self, "_state_plan", None) is None:
+        state_plans = self.__dict__.setdefault("_state_plans", {})
+        didx = capi.device_index(flat.device)
+        if didx not in state_plans:
             n = self._ir.num_qubits
             ir_state = dataclasses.replace(self._ir, meas=[MeasRec(MEAS_STATE, 0, (), shape=(2,) * n, is_complex=True)])
             dt = capi.TQ_C64 if self._cdtype == torch.complex64 else capi.TQ_C128
-            self._state_plan = capi.Plan(ir_state, dt, self._plan_opts)
-        plan = self._state_plan
+            with capi.on_device(didx):
+                state_plans[didx] = capi.Plan(ir_state, dt, self._plan_opts)
+        plan = state_plans[didx]
         flat = flat[:1].detach().contiguous()
         out = torch.empty((1, plan.out_reals), dtype=self._rdtype, device=flat.device)
         ws_bytes = plan.workspace_bytes(1, False)

@@ -68,9 +68,9 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build_library()
+    # build_library() is a digest check when the library is up to date; edited sources are rebuilt, never run stale.
+    # Without nvcc (a deployment box) an existing library whose stamp matches the sources is loaded as is.
+    path = _build.build_library()
     L = C.CDLL(path)
     vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
     L.tq_abi_version.restype = i32
@@ -166,6 +166,26 @@ def lib() -> C.CDLL:
         raise EngineError("libtedq_b200.so ABI version mismatch: rebuild with `python -m tedq_b200.build --force`")
     _lib = L
     return L
+
+
+def device_index(device=None) -> int:
+    """CUDA device index of ``device`` (a torch.device, an int, None = the current device); -1 without CUDA."""
+    import torch
+
+    if device is not None and not isinstance(device, int):
+        device = torch.device(device).index
+    if device is None:
+        return torch.cuda.current_device() if torch.cuda.is_available() else -1
+    return int(device)
+
+
+def on_device(index: int):
+    """Context manager: CUDA device ``index`` current (no-op for -1 = no CUDA)."""
+    import contextlib
+
+    import torch
+
+    return torch.cuda.device(index) if index >= 0 else contextlib.nullcontext()
 
 
 def check(rc: int, what: str):

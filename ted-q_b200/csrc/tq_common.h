@@ -31,6 +31,23 @@ void set_error(const char* fmt, ...);
     }                                \
   } while (0)
 
+// ---- device ownership: a plan's tables live on the device that was current when it was created ---------------
+inline int current_device() {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess) {
+    (void)cudaGetLastError();
+    d = -1;
+  }
+  return d;
+}
+#define TQ_REQUIRE_DEVICE(plan, what)                                                                          \
+  do {                                                                                                         \
+    const int _cur = ::tq::current_device();                                                                   \
+    TQ_REQUIRE((plan)->device < 0 || _cur == (plan)->device, TQ_E_INVALID,                                     \
+               "%s: the plan was created on CUDA device %d but device %d is current (create one plan per "    \
+               "device, inside that device's context)", what, (plan)->device, _cur);                          \
+  } while (0)
+
 // ---- complex value type -----------------------------------------------------
 template <typename R>
 struct __align__(2 * sizeof(R)) cx {

@@ -71,6 +71,7 @@ using namespace tq;
 
 struct tq_plan {
   int n = 0, n_params = 0, dtype = TQ_C64, n_gates = 0;
+  int device = -1;  // CUDA device that owns the plan's tables
   std::vector<HostGate> gates;
   std::vector<HostBlock> blocks;  // alive blocks only, execution order
   std::vector<MatBlock> mblocks;
@@ -463,6 +464,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   p->dtype = dtype;
   p->n_gates = n_gates;
   p->sv_ok = sv_ok;
+  p->device = tq::current_device();
   const int n = n_qubits;
   const zc* zpool = reinterpret_cast<const zc*>(pool);
   const bool c64 = dtype == TQ_C64;
@@ -953,6 +955,7 @@ int tq_tn_param_grads(const tq_plan* p, const void* params, int64_t batch, const
   TQ_REQUIRE(p && arena && off_g && off_a && grad_params && batch > 0, TQ_E_INVALID,
              "tq_tn_param_grads: null argument");
   TQ_REQUIRE(params || p->n_params == 0, TQ_E_INVALID, "tq_tn_param_grads: params is null");
+  TQ_REQUIRE_DEVICE(p, "tq_tn_param_grads");
   const int ng = (int)p->gate_t.size();
   if (ng == 0 || p->n_params == 0) return TQ_OK;
   const int64_t total = batch * ng;
@@ -1187,6 +1190,7 @@ int tq_forward(const tq_plan* p, const void* params, int64_t batch, void* out, v
   TQ_REQUIRE(p && out && workspace && batch > 0, TQ_E_INVALID, "tq_forward: null argument or empty batch");
   TQ_REQUIRE(params || p->n_params == 0, TQ_E_INVALID, "tq_forward: params is null");
   TQ_REQUIRE(p->sv_ok, TQ_E_UNSUPPORTED, "tq_forward: %d qubits exceed the state-vector limit of 30; use the tensor-network entry points", p->n);
+  TQ_REQUIRE_DEVICE(p, "tq_forward");
   if (p->dtype == TQ_C64)
     return forward_impl<float>(p, params, batch, out, workspace, ws_bytes, with_backward, (cudaStream_t)stream);
   return forward_impl<double>(p, params, batch, out, workspace, ws_bytes, with_backward, (cudaStream_t)stream);
@@ -1198,6 +1202,7 @@ int tq_backward(const tq_plan* p, const void* params, int64_t batch, const void*
              "tq_backward: null argument or empty batch");
   TQ_REQUIRE(p->n_params > 0, TQ_E_INVALID, "tq_backward: circuit has no parameters");
   TQ_REQUIRE(p->sv_ok, TQ_E_UNSUPPORTED, "tq_backward: %d qubits exceed the state-vector limit of 30", p->n);
+  TQ_REQUIRE_DEVICE(p, "tq_backward");
   if (p->dtype == TQ_C64)
     return backward_impl<float>(p, params, batch, grad_out, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
   return backward_impl<double>(p, params, batch, grad_out, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
@@ -1214,6 +1219,7 @@ int tq_execute_host(tq_plan* p, const void* params, int64_t batch, void* out, co
   TQ_REQUIRE(p && out && batch > 0, TQ_E_INVALID, "tq_execute_host: null argument or empty batch");
   TQ_REQUIRE((grad_out == nullptr) == (grad_params == nullptr), TQ_E_INVALID,
              "tq_execute_host: grad_out and grad_params go together");
+  TQ_REQUIRE_DEVICE(p, "tq_execute_host");
   const int with_b = grad_out != nullptr;
   const size_t rs = rsize(p->dtype);
   const size_t pb = align_up((size_t)batch * p->n_params * rs);
@@ -1266,6 +1272,7 @@ int tq_tn_operands(const tq_plan* p, const void* params, int64_t batch, void* ga
                    void* stream) {
   TQ_REQUIRE(p && gate_mats && adj_mats && batch > 0, TQ_E_INVALID, "tq_tn_operands: null argument");
   TQ_REQUIRE(params || p->n_params == 0, TQ_E_INVALID, "tq_tn_operands: params is null");
+  TQ_REQUIRE_DEVICE(p, "tq_tn_operands");
   const int ng = (int)p->gate_t.size();
   if (ng == 0) return TQ_OK;
   const int64_t total = batch * ng;

@@ -811,6 +811,7 @@ using namespace tq;
 
 struct tq_tn_plan {
   int dtype = TQ_C64, n_in = 0, n_out = 0, n_sliced = 0;
+  int device = -1;  // CUDA device that owns the plan's tables
   std::vector<tq_tn_step> steps;
   std::vector<int> slice_tensor, slice_ord, slice_bit, final_perm;
   std::vector<int> in_rank;
@@ -1358,6 +1359,7 @@ int tq_tn_plan_create(const int32_t* tensor_off, const int32_t* tensor_idx, int3
   p->n_in = n_in;
   p->n_out = n_out;
   p->n_sliced = n_sliced;
+  p->device = tq::current_device();
   LowerResult R;
   int rc = lower_impl(tensor_off, tensor_idx, n_in, out_idx, n_out, ssa_path, n_steps, sliced, n_sliced, R);
   if (rc) return rc;
@@ -1650,8 +1652,10 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* p, int64_t batch) {
 
 namespace tq {
 
-static int tc_setup_once() {
-  static int done = 0;
+static int tc_setup_once() {  // once per device: the opt-in shared-memory size is a per-device function attribute
+  static bool done_dev[64] = {};
+  const int dev = current_device();
+  bool& done = done_dev[dev >= 0 && dev < 64 ? dev : 0];
   if (done) return TQ_OK;
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
@@ -1662,7 +1666,7 @@ static int tc_setup_once() {
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_gemm<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GEMM_SMEM));
   TQ_CUDA_OK(cudaFuncSetAttribute(tc::k_tc_pack<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  done = 1;
+  done = true;
   return TQ_OK;
 }
 
@@ -2019,6 +2023,7 @@ static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const
                            size_t workspace_bytes, void* stream, float* step_ms, bool backward = false) {
   TQ_REQUIRE(p && inputs && out && workspace && batch > 0, TQ_E_INVALID, "tq_tn_contract: null argument");
   TQ_REQUIRE(!p->steps.empty(), TQ_E_INVALID, "tq_tn_contract: empty plan");
+  TQ_REQUIRE_DEVICE(p, "tq_tn_contract");
   const int64_t ns = (int64_t)1 << p->n_sliced;
   TQ_REQUIRE(slice_begin >= 0 && slice_begin <= slice_end && slice_end <= ns, TQ_E_INVALID,
              "tq_tn_contract: slice range [%lld, %lld) outside [0, %lld)", (long long)slice_begin,

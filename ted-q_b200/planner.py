@@ -447,10 +447,35 @@ def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] =
     return PathInfo(path, sliced, width, fl, len(path))
 
 
+PLANNER_VERSION = 1   # bump when the search changes: stored plans of another version are searched again
+
+
+def valid_plan(inputs, output, ssa, sliced) -> bool:
+    """A stored path fits the network: n-1 steps, every tensor id consumed exactly once and only after it was
+    produced, sliced indices are indices of the network and none of them is an open output."""
+    n = len(inputs)
+    if len(ssa) != n - 1:
+        return False
+    used = set()
+    for s, pair in enumerate(ssa):
+        if len(pair) != 2 or pair[0] == pair[1]:
+            return False
+        for t in pair:
+            if not isinstance(t, int) or t < 0 or t >= n + s or t in used:
+                return False
+            used.add(t)
+    if len(used) != 2 * (n - 1) or (n + len(ssa) - 1) in used:
+        return False
+    all_idx = {int(i) for t in inputs for i in t}
+    out = {int(i) for i in output}
+    return len(set(sliced)) == len(sliced) and all(i in all_idx and i not in out for i in sliced)
+
+
 def cached_plan(cache_dir, inputs, output, build, **key_args) -> PathInfo:
     """On-disk plan cache ("plan cache keyed by the index-map hash"): ``build()`` -> PathInfo runs only
-    when no file for sha1(index maps, output, key_args) exists under ``cache_dir``; the stored plan is re-costed on
-    load, so a stale or foreign file cannot smuggle in a path that does not fit the network."""
+    when no valid file for sha1(index maps, output, key_args) exists under ``cache_dir``.  A stored plan is
+    validated (``valid_plan``) and re-costed on load; a stale, foreign or other-version file is searched again
+    and overwritten."""
     import hashlib
     import json
     import os
@@ -465,9 +490,9 @@ def cached_plan(cache_dir, inputs, output, build, **key_args) -> PathInfo:
         try:
             with open(path) as fh:
                 d = json.load(fh)
-            ssa = [tuple(p) for p in d["path"]]
+            ssa = [tuple(int(x) for x in p) for p in d["path"]]
             sliced = [int(i) for i in d["sliced"]]
-            if len(ssa) == len(inputs) - 1:
+            if int(d.get("version", 1)) == PLANNER_VERSION and valid_plan(inputs, output, ssa, sliced):
                 width, fl, _, _ = path_cost(inputs, output, ssa, sliced)
                 return PathInfo(ssa, sliced, width, fl, len(ssa))
         except (OSError, ValueError, KeyError, IndexError, TypeError):
@@ -476,6 +501,6 @@ def cached_plan(cache_dir, inputs, output, build, **key_args) -> PathInfo:
     os.makedirs(cache_dir, exist_ok=True)
     tmp = path + ".tmp%d" % os.getpid()
     with open(tmp, "w") as fh:
-        json.dump({"path": [list(p) for p in info.path], "sliced": list(info.sliced)}, fh)
+        json.dump({"version": PLANNER_VERSION, "path": [list(p) for p in info.path], "sliced": list(info.sliced)}, fh)
     os.replace(tmp, path)
     return info

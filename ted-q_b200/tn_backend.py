@@ -58,7 +58,7 @@ class TNExecutor:
                 info = planner.cached_plan(self.ho.get("plan_cache"), net.inputs, net.output,
                                            lambda net=net: self._search(net), **self._plan_key())
             self.infos.append(info)
-            self.plans.append(None)
+        self.plans = {}           # (network, CUDA device index) -> capi.TnPlan: a plan's tables live on one device
         self._const = {}
 
     def _plan_key(self):
@@ -89,13 +89,22 @@ class TNExecutor:
         return info
 
     # ------------------------------------------------------------------
-    def _plan(self, i) -> capi.TnPlan:
-        if self.plans[i] is None:
+    def _engine_opts(self, plan):
+        """hyper_opt["engine_opts"] = {TQ_TN_OPT_*: value}, applied to every plan this executor builds."""
+        for opt, val in (self.ho.get("engine_opts") or {}).items():
+            plan.set_option(int(opt), int(val))
+        return plan
+
+    def _plan(self, i, device=None) -> capi.TnPlan:
+        key = (i, capi.device_index(device))
+        if key not in self.plans:
             net, info = self.networks[i], self.infos[i]
             batched = [kind in (OPD_GATE, OPD_ADJ) and self.gate_batched[ref] for kind, ref in net.operands]
             dt = capi.TQ_C64 if self.backend._cdtype == torch.complex64 else capi.TQ_C128
-            self.plans[i] = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
-        return self.plans[i]
+            with capi.on_device(key[1]):
+                self.plans[key] = self._engine_opts(
+                    capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt))
+        return self.plans[key]
 
     def _constants(self, device):
         key = str(device)
@@ -202,19 +211,19 @@ class TNExecutor:
                              "measurement_parallel)")
         return ok and (mode == "tree" or self.n > 26)
 
-    def _plan_bwd(self, i) -> capi.TnPlan:
+    def _plan_bwd(self, i, device=None) -> capi.TnPlan:
         """Plan of network i with the reverse pass appended (forward-only calls keep the leaner plan)."""
         cache = self.__dict__.setdefault("_plans_bwd", {})
-        if i not in cache:
+        key = (i, capi.device_index(device))
+        if key not in cache:
             net, info = self.networks[i], self.infos[i]
             batched = [kind in (OPD_GATE, OPD_ADJ) and self.gate_batched[ref] for kind, ref in net.operands]
             dt = capi.TQ_C64 if self.backend._cdtype == torch.complex64 else capi.TQ_C128
-            plan = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
-            for opt, val in (self.ho.get("engine_opts") or {}).items():
-                plan.set_option(int(opt), int(val))
-            plan.enable_backward(batched)
-            cache[i] = plan
-        return cache[i]
+            with capi.on_device(key[1]):
+                plan = self._engine_opts(capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt))
+                plan.enable_backward(batched)
+            cache[key] = plan
+        return cache[key]
 
     def _grad_tables(self, i, device, slice_id=0):
         """Per network and slice, once: device int32 [n_gates, 16] tables (ket half, bra half) of the per-set-arena
@@ -223,7 +232,7 @@ class TNExecutor:
         cache = self.__dict__.setdefault("_grad_tabs", {})
         key = (i, str(device), int(slice_id))
         if key not in cache:
-            net, plan = self.networks[i], self._plan_bwd(i)
+            net, plan = self.networks[i], self._plan_bwd(i, device)
             sliced = list(self.infos[i].sliced)
             ng = len(self.backend._ir.gates)
             og = np.full((ng, 16), -1, dtype=np.int32)
@@ -254,10 +263,10 @@ class TNExecutor:
         """-> list of complex tensors [B or 1, 2^n_out] (one per measurement).  ``keep`` (a list): use the plans with
         a reverse pass and append (network id, plan, ptrs, strides, workspace, keep-alive) for tree_backward."""
         be = self.backend
-        plan_sv = be.plan()
+        dev = flat.device
+        plan_sv = be.plan(dev)
         L = capi.lib()
         B = flat.shape[0]
-        dev = flat.device
         cd = be._cdtype
         total = int(L.tq_tn_gate_offset(plan_sv.handle, len(be._ir.gates)))
         gm = torch.empty((B, max(1, total)), dtype=cd, device=dev)
@@ -284,7 +293,7 @@ class TNExecutor:
             tab = self._operand_tables(i, net, plan_sv, total)
             use_bwd = keep is not None and bool(tab["any_batched"])   # a constant network has no gradient
             # a sliced plan re-runs its forward slice by slice inside tree_backward: plain forward here
-            plan = self._plan_bwd(i) if use_bwd and not self.infos[i].sliced else self._plan(i)
+            plan = self._plan_bwd(i, dev) if use_bwd and not self.infos[i].sliced else self._plan(i, dev)
             bases = np.array([cap0.data_ptr(), gm.data_ptr(), am.data_ptr(),
                               red_buf.data_ptr() if red_buf is not None else 0] + [o.data_ptr() for o in obs[i]],
                              dtype=np.int64)
@@ -303,7 +312,7 @@ class TNExecutor:
                     out.zero_()
                 torch.distributed.all_reduce(torch.view_as_real(out))
             if use_bwd:
-                keep.append((i, self._plan_bwd(i), ptrs, strides, None if self.infos[i].sliced else ws,
+                keep.append((i, self._plan_bwd(i, dev), ptrs, strides, None if self.infos[i].sliced else ws,
                              (gm, am, red_buf)))
             if not any_b and B > 1:
                 out = out.expand(B, -1)
@@ -319,7 +328,7 @@ class TNExecutor:
         L = capi.lib()
         stream = torch.cuda.current_stream(dev).cuda_stream
         grad = torch.zeros((B, be._ir.n_params), dtype=be._rdtype, device=dev)
-        plan_sv = be.plan()
+        plan_sv = be.plan(dev)
         for i, plan, ptrs, strides, ws, _alive in kept:
             gi = dy[:, i].reshape(B, -1)
             gout = (gi if gi.is_complex() else gi.to(be._rdtype) + 0j).to(be._cdtype).contiguous()
@@ -360,26 +369,28 @@ class TNExecutor:
         be = self.backend
         amp = self._amplitude_plan()
         net, info = amp[0], amp[1]
-        if amp[2] is None:
+        dev = flat.device
+        plans = self.__dict__.setdefault("_amp_plans", {})      # CUDA device index -> plan
+        didx = capi.device_index(dev)
+        if didx not in plans:
             batched = [kind == OPD_GATE and self.gate_batched[ref] for kind, ref in net.operands]
             dt = capi.TQ_C64 if be._cdtype == torch.complex64 else capi.TQ_C128
             grp = self._slice_group(net, info, batched)
             self._amp_group = grp
-            if grp is None:
-                amp[2] = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
-            else:   # the grouped indices leave the network: their values become the plan's batch ("set") dimension
-                gset = set(grp["indices"])
-                inputs2 = [[ix for ix in t if ix not in gset] for t in net.inputs]
-                batched2 = [bool(grp["axes"].get(t)) for t in range(len(net.inputs))]
-                amp[2] = capi.TnPlan(inputs2, net.output, info.path, grp["rest"], batched2, dt)
-            for opt, val in (self.ho.get("engine_opts") or {}).items():
-                amp[2].set_option(int(opt), int(val))
-        plan = amp[2]
+            with capi.on_device(didx):
+                if grp is None:
+                    plan = capi.TnPlan(net.inputs, net.output, info.path, info.sliced, batched, dt)
+                else:   # the grouped indices leave the network: their values become the plan's batch ("set") dimension
+                    gset = set(grp["indices"])
+                    inputs2 = [[ix for ix in t if ix not in gset] for t in net.inputs]
+                    batched2 = [bool(grp["axes"].get(t)) for t in range(len(net.inputs))]
+                    plan = capi.TnPlan(inputs2, net.output, info.path, grp["rest"], batched2, dt)
+                plans[didx] = self._engine_opts(plan)
+        plan = amp[2] = plans[didx]       # amp[2]: the plan of the device used last (introspection)
         grp = getattr(self, "_amp_group", None)
-        plan_sv = be.plan()
+        plan_sv = be.plan(dev)
         L = capi.lib()
         B = flat.shape[0]
-        dev = flat.device
         cd = be._cdtype
         total = int(L.tq_tn_gate_offset(plan_sv.handle, len(be._ir.gates)))
         gm = torch.empty((B, max(1, total)), dtype=cd, device=dev)

@@ -53,19 +53,24 @@ class B200OptTN:
         self.info = info
         self._plans: Dict[int, capi.TnPlan] = {}
 
-    def _plan(self, dtype) -> capi.TnPlan:
-        key = capi.TQ_C64 if dtype == torch.complex64 else capi.TQ_C128
+    def _plan(self, dtype, device=None) -> capi.TnPlan:
+        """Plans are cached per (dtype, CUDA device): their tables are device memory."""
+        dt = capi.TQ_C64 if dtype == torch.complex64 else capi.TQ_C128
+        key = (dt, capi.device_index(device))
         if key not in self._plans:
-            self._plans[key] = capi.TnPlan(self.inputs, self.output, self.info.path, self.info.sliced,
-                                           [False] * len(self.inputs), key)
+            with capi.on_device(key[1]):
+                self._plans[key] = capi.TnPlan(self.inputs, self.output, self.info.path, self.info.sliced,
+                                               [False] * len(self.inputs), dt)
         return self._plans[key]
 
-    def _plan_bwd(self, dtype, needs) -> capi.TnPlan:
-        key = (capi.TQ_C64 if dtype == torch.complex64 else capi.TQ_C128, tuple(bool(b) for b in needs))
+    def _plan_bwd(self, dtype, needs, device=None) -> capi.TnPlan:
+        dt = capi.TQ_C64 if dtype == torch.complex64 else capi.TQ_C128
+        key = (dt, capi.device_index(device), tuple(bool(b) for b in needs))
         if key not in self._plans:
-            plan = capi.TnPlan(self.inputs, self.output, self.info.path, self.info.sliced, [False] * len(self.inputs),
-                               key[0])
-            plan.enable_backward(key[1])
+            with capi.on_device(key[1]):
+                plan = capi.TnPlan(self.inputs, self.output, self.info.path, self.info.sliced,
+                                   [False] * len(self.inputs), dt)
+                plan.enable_backward(key[2])
             self._plans[key] = plan
         return self._plans[key]
 
@@ -93,7 +98,7 @@ class B200OptTN:
         for a, ix in zip(keep, self.inputs):
             if a.numel() != 1 << len(ix):
                 raise ValueError(f"operand with {a.numel()} entries for {len(ix)} indices of size 2")
-        plan = self._plan(dtype)
+        plan = self._plan(dtype, dev)
         out = torch.zeros((1, 1 << len(self.output)), dtype=dtype, device=dev)
         ws_bytes = plan.workspace_bytes(1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -114,7 +119,7 @@ class _TreeContract(torch.autograd.Function):
         if dev.type != "cuda":
             raise RuntimeError("B200OptTN.contract needs CUDA tensors: the engine has no CPU fallback")
         needs = [bool(a.requires_grad) for a in arrays]
-        plan = tree._plan_bwd(dtype, needs)
+        plan = tree._plan_bwd(dtype, needs, dev)
         keep = [a.detach().to(dtype).contiguous() for a in arrays]
         out = torch.zeros((1, 1 << len(tree.output)), dtype=dtype, device=dev)
         ws_bytes = plan.workspace_bytes(1)

@@ -295,3 +295,19 @@ def test_qudio_front_matches_row_loop():
     (gr,) = torch.autograd.grad((rows * ct).sum(), w)
     assert torch.allclose(g, gr, atol=1e-5)
     assert str(cq.device).startswith("cuda")
+
+
+def _c4d20_case():
+    case = load_golden("c4d20_case.json")
+    spec = W.mbl_2d(*case["spec"]["args"])
+    assert len(spec["gates"]) == case["spec"]["n_gates"] and spec["n_params"] == case["spec"]["n_params"]
+    return dict(case, spec=spec)
+
+
+def test_c4_depth20_matches_reference_fixture():
+    """BASELINE config 4 at "depth 20" (10 Hd + 10 H0 Trotter sweeps of the 4x4 MBL-2D circuit: 17 819 gates,
+    complex128): values and gradients against the unmodified reference (tests/golden/generate_golden_c4d20.py)."""
+    case = _c4d20_case()
+    out, grad = run_engine(case)
+    assert_close(out, golden_out(case), TOL["c128"], "c4d20 out")
+    assert_close(grad, np.asarray(case["grad"]), TOL["c128"], "c4d20 grad")

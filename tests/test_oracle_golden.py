@@ -70,3 +70,16 @@ def test_frontend_gate_matrices_match_reference():
         op = getattr(qb, name)(*rec["params"], qubits=list(range(nq)), do_queue=False)
         ref = np.asarray(rec["re"]) + 1j * np.asarray(rec["im"])
         assert np.allclose(np.asarray(op.matrix, dtype=complex), ref, rtol=0, atol=1e-15), name
+
+
+def test_oracle_matches_c4_depth20_fixture():
+    """The oracle at BASELINE config 4 "depth 20" (17 819 gates, 16 qubits, complex128) against the reference's own
+    output for the same parameters (forward only: keeps the CPU suite short; gradients are pinned on the GPU side)."""
+    from tedq_b200 import workloads as W
+
+    case = load_golden("c4d20_case.json")
+    spec = W.mbl_2d(*case["spec"]["args"])
+    circ = build(spec, "c128", case["flat"][0])
+    with torch.no_grad():
+        out = sv_ref.run_sv(circ, torch.tensor(case["flat"][0], dtype=torch.float64), torch.complex128)
+    assert_close(out.numpy()[None], np.asarray(case["out"]), 1e-12, "c4d20 out")

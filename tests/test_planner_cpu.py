@@ -109,3 +109,40 @@ def test_native_reconfigure_reproduces_python_path_and_committed_plan():
         a = planner.reconfigure(inputs, [], start, sweeps=2, time_model=model, native=True)
         b = planner.reconfigure(inputs, [], start, sweeps=2, time_model=model, native=False)
         assert a == b
+
+
+def test_cached_plan_rejects_malformed_files(tmp_path):
+    """A stored plan that does not fit the network (reused / dead ssa ids, a sliced open index, another planner
+    version) is searched again and overwritten, not handed to the lowering."""
+    import json
+    import os
+
+    inputs = [[0, 1], [1, 2], [2, 3], [3, 0, 4]]
+    output = [4]
+    calls = []
+
+    def build():
+        calls.append(1)
+        return planner.find_path(inputs, output, repeats=2, seed=0)
+
+    good = planner.cached_plan(str(tmp_path), inputs, output, build, k=1)
+    (fname,) = os.listdir(tmp_path)
+    path = os.path.join(tmp_path, fname)
+    assert planner.valid_plan(inputs, output, good.path, good.sliced)
+    bad_files = [
+        {"path": [[0, 1], [0, 2], [4, 3]], "sliced": []},            # tensor 0 consumed twice
+        {"path": [[0, 1], [2, 6], [4, 3]], "sliced": []},            # id 6 used before it exists
+        {"path": [[0, 1], [2, 3]], "sliced": []},                    # too short
+        {"path": [list(p) for p in good.path], "sliced": [4]},       # an open output index cannot be sliced
+        {"path": [list(p) for p in good.path], "sliced": [9]},       # not an index of the network
+        {"version": planner.PLANNER_VERSION + 1, "path": [list(p) for p in good.path], "sliced": []},
+    ]
+    for i, bad in enumerate(bad_files):
+        with open(path, "w") as fh:
+            json.dump(bad, fh)
+        n = len(calls)
+        info = planner.cached_plan(str(tmp_path), inputs, output, build, k=1)
+        assert len(calls) == n + 1, i                 # searched again
+        assert info.path == good.path
+        with open(path) as fh:
+            assert json.load(fh)["path"] == [list(p) for p in good.path]   # overwritten with a valid plan

@@ -78,7 +78,7 @@ def test_fused_runs_match_einsum(seed, c128):
     fused, kinds_f = _run(inputs, output, info.path, sliced, arrays, batched, B, c128, True)
     plain, kinds_p = _run(inputs, output, info.path, sliced, arrays, batched, B, c128, False)
     assert 4 in kinds_f and 4 not in kinds_p
-    tol = (1e-11 if c128 else 1e-5) * max(1.0, np.abs(ref).max())
+    tol = (1e-11 if c128 else 1e-5) * np.abs(ref).max()
     assert np.abs(fused - ref).max() <= tol, np.abs(fused - ref).max()
     assert np.abs(plain - ref).max() <= tol, np.abs(plain - ref).max()
 
