@@ -131,6 +131,9 @@ int64_t tq_plan_out_reals(const tq_plan* plan);
 /* algorithmic HBM bytes one forward / backward evaluation moves (sweeps x read+write of psi [and lambda]) */
 int64_t tq_plan_hbm_bytes(const tq_plan* plan, int32_t backward);
 int64_t tq_plan_launches(const tq_plan* plan, int32_t backward);
+/* algorithmic real flops of one forward / backward evaluation on the fused-block schedule (complex MAC = 8 flops);
+ * the sweeps of a shared-memory-resident state are bound by the FP32 / FP64 pipe, not by HBM */
+double tq_plan_flops(const tq_plan* plan, int32_t backward);
 
 /* ---- execution (replaces PyTorchBackend.execute state-vector branch,
  *      pytorch_backend.py:358-391 + get_measurement_results :393-498;
@@ -251,14 +254,22 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
  *   TQ_TN_OPT_TC_GATHER (default 0, experimental): 1 = the row operand of a tensor-core step whose tiles are read
  *     once or twice (<= 2 column tiles) is gathered, split and swizzled into shared memory by the GEMM kernel itself,
  *     straight from the tensor (no operand image in HBM for it).  Bit-identical results; measured slower than the
- *     image path on B200 so far ("Experiments that did not pay"). */
+ *     image path on B200 so far ("Experiments that did not pay").
+ *   TQ_TN_OPT_TC_FUSE_PACK (default 1): a tensor-core step whose result is read by exactly one step, itself a
+ *     tensor-core step, writes that step's operand image (hi / lo TF32 planes, permuted, swizzled) straight from its
+ *     epilogue: the intermediate is never stored in its plain layout, the consumer runs no pack pass.  0 = every
+ *     tensor-core step packs its operands from plain tensors (bit-identical results; parity tests compare both). */
 enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2,
-                    TQ_TN_OPT_FUSE_SMALL = 3, TQ_TN_OPT_TC_SPLITK = 4, TQ_TN_OPT_TC_GATHER = 5 };
+                    TQ_TN_OPT_FUSE_SMALL = 3, TQ_TN_OPT_TC_SPLITK = 4, TQ_TN_OPT_TC_GATHER = 5,
+                    TQ_TN_OPT_TC_FUSE_PACK = 6 };
 int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
 /* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,
  * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096),
  * 4 = member of a fused run of small steps, 5 = apply kernel (one gate-sized operand, one large operand) */
 int32_t tq_tn_plan_step_kernel(const tq_tn_plan* plan, int32_t s);
+/* fused pack: the step whose operand image step s writes from its own epilogue, -1 when s stores a plain tensor
+ * (a split-K launch of s still falls back to plain + pack at run time) */
+int32_t tq_tn_plan_step_fuse_to(const tq_tn_plan* plan, int32_t s);
 /* bit 0: step s repeats for every slice (it depends on a sliced index); bit 1: it carries the parameter-set
  * batch dimension.  Steps with neither bit run once per call, outside the slice loop. */
 int32_t tq_tn_plan_step_flags(const tq_tn_plan* plan, int32_t s);
@@ -305,6 +316,11 @@ int tq_tn_param_grads(const tq_plan* plan, const void* params, int64_t batch, co
 int tq_tn_profile(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides, int64_t batch,
                   int64_t slice, void* out, void* workspace, size_t workspace_bytes, void* cuda_stream,
                   float* step_ms);
+
+/* Kernel launches enqueued by tq_tn_contract / tq_tn_backward / tq_tn_profile since the library was loaded
+ * (monotonic; a caller diffs it around a region: bench.py's gpu_launches).  The state-vector side reports its
+ * launches per call through tq_plan_launches. */
+int64_t tq_tn_launch_count(void);
 
 /* Operand tensors of a circuit's network on the device (replaces _parse_circuit_cotengra + the arrays
  * assembly, compiled_circuit.py:442-467, pytorch_backend.py:311-336, :524-546): for every gate of `plan`

@@ -564,6 +564,22 @@ class B200Backend:
             amp = self._tn.amplitude(flat.contiguous(), bits, slice_range)
         return amp if batched else amp[0]
 
+    def amplitudes(self, bits_batch, *params, batched=False, slice_range=None):
+        """Batch of amplitudes <b_a| U(params) |0...0>, ``bits_batch`` an [A, n] array / tensor of 0/1 (host or
+        device) -> complex [A] (``batched=True``: [A, B]).  One pass over the gate operands, one contraction per
+        bitstring, and under ``contract_parallel`` ONE all-reduce of the whole batch's partial sums."""
+        if self._tn is None:
+            raise ValueError("amplitudes() needs tensor-network mode: compile with tn_mode=True (or use_jdopttn=...)")
+        self.check_parameters_torch_device(params)
+        if params:
+            self._require_cuda(self._device)
+        if batched:
+            flat = torch.cat([p.reshape(p.shape[0], -1).to(self._rdtype) for p in params], dim=1)
+        else:
+            flat = self._flatten(params)
+        with torch.no_grad():
+            return self._tn.amplitudes(flat.contiguous(), bits_batch, slice_range)
+
     def execute_host(self, params: np.ndarray, grad_out: Optional[np.ndarray] = None):
         """HOST numpy [B, P] -> (out [B, n_meas, ...], grad [B, P] or None); copies are inside the call."""
         out, grad = self.plan().execute_host(params, grad_out)

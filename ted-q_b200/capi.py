@@ -41,6 +41,7 @@ class PlanOpts(C.Structure):
 TN_MAX_RANK = 32
 TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK, TN_OPT_FUSE_SMALL, TN_OPT_TC_SPLITK = 0, 1, 2, 3, 4
 TN_OPT_TC_GATHER = 5
+TN_OPT_TC_FUSE_PACK = 6
 
 
 class TnStep(C.Structure):
@@ -98,6 +99,8 @@ def lib() -> C.CDLL:
     L.tq_plan_out_reals.restype = i64
     L.tq_plan_hbm_bytes.argtypes = [vp, i32]
     L.tq_plan_hbm_bytes.restype = i64
+    L.tq_plan_flops.argtypes = [vp, i32]
+    L.tq_plan_flops.restype = C.c_double
     L.tq_plan_launches.argtypes = [vp, i32]
     L.tq_plan_launches.restype = i64
     L.tq_workspace_bytes.argtypes = [vp, i64, i32]
@@ -154,10 +157,14 @@ def lib() -> C.CDLL:
     L.tq_tn_plan_set_option.restype = i32
     L.tq_tn_plan_step_kernel.argtypes = [vp, i32]
     L.tq_tn_plan_step_kernel.restype = i32
+    L.tq_tn_plan_step_fuse_to.argtypes = [vp, i32]
+    L.tq_tn_plan_step_fuse_to.restype = i32
     L.tq_tn_plan_step_flags.argtypes = [vp, i32]
     L.tq_tn_plan_step_flags.restype = i32
     L.tq_tn_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, vp, sz, vp, C.POINTER(C.c_float)]
     L.tq_tn_profile.restype = i32
+    L.tq_tn_launch_count.argtypes = []
+    L.tq_tn_launch_count.restype = i64
     L.tq_tn_gate_offset.argtypes = [vp, i32]
     L.tq_tn_gate_offset.restype = i64
     L.tq_tn_operands.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -286,6 +293,9 @@ class Plan:
 
     def hbm_bytes(self, backward=False) -> int:
         return int(lib().tq_plan_hbm_bytes(self.handle, int(backward)))
+
+    def flops(self, backward=False) -> float:
+        return float(lib().tq_plan_flops(self.handle, int(backward)))
 
     def launches(self, backward=False) -> int:
         return int(lib().tq_plan_launches(self.handle, int(backward)))
@@ -451,6 +461,10 @@ class TnPlan:
     def step_kernel(self, s):
         """0: per-element kernel, 1: tiled fp32 FMA GEMM, 2: tcgen05 split-TF32 GEMM."""
         return int(lib().tq_tn_plan_step_kernel(self.handle, s))
+
+    def step_fuse_to(self, s):
+        """Step whose operand image step s writes from its epilogue (fused pack), -1: plain result."""
+        return int(lib().tq_tn_plan_step_fuse_to(self.handle, s))
 
     def step_flags(self, s):
         """bit 0: repeats per slice, bit 1: batched over parameter sets."""

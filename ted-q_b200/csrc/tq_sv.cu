@@ -944,6 +944,22 @@ int64_t tq_plan_hbm_bytes(const tq_plan* p, int32_t backward) {
   return io + pay + sv * (2 + 4 * (int64_t)p->bwd.size());
 }
 
+/* Algorithmic real flops of one evaluation on the fused-block schedule (complex MAC = 8 flops, complex multiply = 6):
+ * forward: a dense block on t target qubits costs 8 * 2^t per amplitude it touches (2^(n - controls) of them), a
+ * diagonal block 6; backward (adjoint method): psi <- G^dagger psi, lambda <- G^dagger lambda and the accumulation of
+ * W = psi (x) conj(lambda) cost one such product each, i.e. 3x the forward count.  Measurement passes not counted. */
+double tq_plan_flops(const tq_plan* p, int32_t backward) {
+  if (!p) return -1.0;
+  double fl = 0.0;
+  for (const HostBlock& b : p->blocks) {
+    if (!b.alive) continue;
+    const double amps = ldexp(1.0, p->n - (int)b.controls.size());
+    const double per = b.cls == OP_DIAG ? 6.0 : 8.0 * ldexp(1.0, (int)b.targets.size());
+    fl += amps * per;
+  }
+  return backward ? 3.0 * fl : fl;
+}
+
 int64_t tq_plan_launches(const tq_plan* p, int32_t backward) {
   if (!p) return -1;
   if (!backward) return 1 + (p->fwd_full ? 1 : (int64_t)p->fwd.size() + 1);

@@ -7,6 +7,7 @@
 // permutation folded into the address computation of the contraction kernel itself (no transposed
 // copy of either operand is ever materialised).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -780,6 +781,17 @@ struct TcStep {
   // gathers it itself (k_tc_gemm<C_T, true>), no image is written
   bool gather_a = false;
   tc::PackParams pa, pb;
+  // fused pack: this step's epilogue writes operand image `fuse_is_b ? B : A` of step fuse_to (its only consumer);
+  // src_a / src_b: the step that writes this step's A / B image that way (-1: packed from the plain tensor)
+  int fuse_to = -1, src_a = -1, src_b = -1;
+  bool fuse_is_b = false;
+  // index orders of this step's GEMM: position t of the accumulator rows / columns / contracted extent is default
+  // position ord_*[t] (default = the lowering's order).  A step that stores a plain result keeps its row / column
+  // order (the result layout is [b | m | n]); a fused-pack producer's rows and columns are ordered so that its
+  // epilogue's stores fall into whole 64-byte row pieces of the consumer's image.
+  std::vector<int> ord_row, ord_col, ord_k;
+  int64_t out_entries = 0;  // size of the image in complex entries per parameter set
+  tc::ImgOut out;
 };
 
 static void tc_pack_tables(tc::PackParams& P, const int8_t* row_bits, int n_row, const int8_t* k_bits, int n_k,
@@ -808,6 +820,9 @@ static void tc_pack_tables(tc::PackParams& P, const int8_t* row_bits, int n_row,
 }  // namespace tq
 
 using namespace tq;
+
+struct tq_tn_plan;
+static void tc_build_tables(tq_tn_plan* p, int s);
 
 struct tq_tn_plan {
   int dtype = TQ_C64, n_in = 0, n_out = 0, n_sliced = 0;
@@ -852,8 +867,41 @@ struct tq_tn_plan {
   int tc_chunk = 32;       // TQ_TN_OPT_TC_CHUNK: complex k accumulated in TMEM between round-to-nearest drains
   int tc_splitk = 1;       // TQ_TN_OPT_TC_SPLITK
   int tc_gather = 0;       // TQ_TN_OPT_TC_GATHER
+  int tc_fuse_pack = 1;    // TQ_TN_OPT_TC_FUSE_PACK
   int num_sms = 148;
 };
+
+// Default (lowering-order) physical bit lists of a step's two GEMM operands: A provides the accumulator rows.
+struct TcSides {
+  const int8_t *a_free, *a_k, *a_b, *b_free, *b_k, *b_b;
+  int n_row, n_col;
+};
+static TcSides tc_sides(const tq_tn_step& st, bool swap) {
+  const int8_t* lhs_k = st.lhs_bits;
+  const int8_t* lhs_m = st.lhs_bits + st.n_k;
+  const int8_t* lhs_b = st.lhs_bits + st.n_k + st.n_m;
+  const int8_t* rhs_k = st.rhs_bits;
+  const int8_t* rhs_n = st.rhs_bits + st.n_k;
+  const int8_t* rhs_b = st.rhs_bits + st.n_k + st.n_n;
+  if (!swap) return TcSides{lhs_m, lhs_k, lhs_b, rhs_n, rhs_k, rhs_b, st.n_m, st.n_n};
+  return TcSides{rhs_n, rhs_k, rhs_b, lhs_m, lhs_k, lhs_b, st.n_n, st.n_m};
+}
+
+// pack tables of both operand images of step s for its current row / column / k orders
+static void tc_build_tables(tq_tn_plan* p, int s) {
+  const tq_tn_step& st = p->steps[s];
+  TcStep& T = p->tc[s];
+  const TcSides S = tc_sides(st, T.swap);
+  int8_t rowb[TQ_TN_MAX_RANK], colb[TQ_TN_MAX_RANK], ka[TQ_TN_MAX_RANK], kb[TQ_TN_MAX_RANK];
+  for (int i = 0; i < S.n_row; ++i) rowb[i] = S.a_free[T.ord_row[i]];
+  for (int i = 0; i < S.n_col; ++i) colb[i] = S.b_free[T.ord_col[i]];
+  for (int i = 0; i < st.n_k; ++i) {
+    ka[i] = S.a_k[T.ord_k[i]];
+    kb[i] = S.b_k[T.ord_k[i]];
+  }
+  tc_pack_tables(T.pa, rowb, S.n_row, ka, st.n_k, S.a_b, st.n_b, false, 7);
+  tc_pack_tables(T.pb, colb, S.n_col, kb, st.n_k, S.b_b, st.n_b, true, std::min(S.n_col, 7));
+}
 
 // Per-step derived data for steps [first, end): dependency flags, ranks, layouts, K tables, tensor-core lowering.
 static int setup_steps(tq_tn_plan* p, int first) {
@@ -954,19 +1002,13 @@ static int setup_steps(tq_tn_plan* p, int first) {
     T.gather_a = st.n_k >= tc::KB_LOG && T.tiles_b <= 2;
     T.img_a_z = (int64_t)T.tiles_a * T.kblocks * tc::A_CHUNK;
     T.img_b_z = (int64_t)T.tiles_b * T.kblocks * tc::b_chunk_bytes(T.c_t);
-    const int8_t* lhs_k = st.lhs_bits;
-    const int8_t* lhs_m = st.lhs_bits + st.n_k;
-    const int8_t* lhs_b = st.lhs_bits + st.n_k + st.n_m;
-    const int8_t* rhs_k = st.rhs_bits;
-    const int8_t* rhs_n = st.rhs_bits + st.n_k;
-    const int8_t* rhs_b = st.rhs_bits + st.n_k + st.n_n;
-    if (!T.swap) {
-      tc_pack_tables(T.pa, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, false, 7);
-      tc_pack_tables(T.pb, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, true, col_t_log2);
-    } else {
-      tc_pack_tables(T.pa, rhs_n, st.n_n, rhs_k, st.n_k, rhs_b, st.n_b, false, 7);
-      tc_pack_tables(T.pb, lhs_m, st.n_m, lhs_k, st.n_k, lhs_b, st.n_b, true, col_t_log2);
-    }
+    T.ord_row.resize(n_row);
+    T.ord_col.resize(n_col);
+    T.ord_k.resize(st.n_k);
+    for (int i = 0; i < n_row; ++i) T.ord_row[i] = i;
+    for (int i = 0; i < n_col; ++i) T.ord_col[i] = i;
+    for (int i = 0; i < st.n_k; ++i) T.ord_k[i] = i;
+    tc_build_tables(p, s);
   }
   return TQ_OK;
 }
@@ -1019,6 +1061,135 @@ static int build_schedule(tq_tn_plan* p) {
         a.small_b[j] = sb[st.n_k + a.n_s + j];
         a.big_b[j] = bbits[st.n_k + a.n_f + j];
       }
+    }
+  }
+  // ---- fused pack: a tensor-core step whose result is read by exactly one step, itself a tensor-core step of the
+  // same phase with the same batch / slice dependence, writes that step's operand image from its epilogue.
+  // Steps are visited consumers first: a consumer d picks the three contracted indices that become the low k bits
+  // of its image (one 64-byte row piece = 8 consecutive k) among those its producer c holds as accumulator ROW bits
+  // (lanes of a warp: 8 lanes x 8 bytes fill a piece) or, failing that, as COLUMN bits (consecutive registers of one
+  // thread: 16-byte stores), and fixes c's row / column order accordingly; c's own k order is chosen when c is
+  // visited as a consumer.
+  {
+    static_assert(tc::KB_LOG == 3, "the image address maps below assume 64-byte rows");
+    std::vector<int> n_cons(n_in + n_steps, 0);
+    for (int s = 0; s < n_steps; ++s) {
+      n_cons[p->steps[s].lhs] += 1;
+      if (s != p->seed_step) n_cons[p->steps[s].rhs] += 1;
+    }
+    for (int s = 0; s < n_steps; ++s) {
+      TcStep& T = p->tc[s];
+      T.fuse_to = T.src_a = T.src_b = -1;
+      T.out_entries = 0;
+      for (size_t i = 0; i < T.ord_row.size(); ++i) T.ord_row[i] = (int)i;
+      for (size_t i = 0; i < T.ord_col.size(); ++i) T.ord_col[i] = (int)i;
+      for (size_t i = 0; i < T.ord_k.size(); ++i) T.ord_k[i] = (int)i;
+    }
+    auto front = [](std::vector<int>& ord, const std::vector<int>& first) {  // `first`, then the rest in old order
+      std::vector<int> out(first);
+      for (int v : ord)
+        if (std::find(first.begin(), first.end(), v) == first.end()) out.push_back(v);
+      ord.swap(out);
+    };
+    for (int d = n_steps - 1; d >= 0 && p->tc_fuse_pack; --d) {
+      if (p->kind[d] != 2 || !p->tc[d].shape_ok) continue;
+      const tq_tn_step& sd = p->steps[d];
+      TcStep& Td = p->tc[d];
+      if (sd.n_k < tc::KB_LOG) continue;  // a padded k-block has zero columns only the pack kernel writes
+      bool k_fixed = false;
+      for (int pass = 0; pass < 2 && !k_fixed; ++pass) {  // the row operand (A image) first
+        const int side = (pass == 0) == !Td.swap ? 0 : 1;  // 0: lhs, 1: rhs
+        const bool is_b = pass == 1;
+        const int t = side == 0 ? sd.lhs : sd.rhs;
+        if (t < n_in || n_cons[t] != 1) continue;
+        const int c = t - n_in;
+        if (p->kind[c] != 2 || !p->tc[c].shape_ok || p->phase[c] != p->phase[d] ||
+            p->dep_batch[c] != p->dep_batch[d] || p->dep_slice[c] != p->dep_slice[d] || p->tc[c].fuse_to >= 0)
+          continue;
+        if (is_b ? Td.pin_b : Td.pin_a) continue;
+        const int64_t img_z = is_b ? Td.img_b_z : Td.img_a_z;
+        if ((img_z << sd.n_b) >= ((int64_t)1 << 32)) continue;
+        const tq_tn_step& sc = p->steps[c];
+        TcStep& Tc = p->tc[c];
+        if (sc.n_b > 8) continue;
+        // role of every bit of the tensor inside the producer's GEMM: default row / column position
+        int prow[TQ_TN_MAX_RANK], pcol[TQ_TN_MAX_RANK];
+        for (int b = 0; b < TQ_TN_MAX_RANK; ++b) prow[b] = pcol[b] = -1;
+        for (int i = 0; i < sc.n_n; ++i) (Tc.swap ? prow : pcol)[i] = i;
+        for (int i = 0; i < sc.n_m; ++i) (Tc.swap ? pcol : prow)[sc.n_n + i] = i;
+        const int8_t* bits_t = side == 0 ? sd.lhs_bits : sd.rhs_bits;  // [k..., free..., b...] positions in the tensor
+        std::vector<int> kr, kc;  // contracted indices of d (default k positions) held as rows / columns by c
+        for (int j = 0; j < sd.n_k; ++j) {  // (an index the producer kept as a batch index is neither)
+          if (prow[bits_t[j]] >= 0) kr.push_back(j);
+          else if (pcol[bits_t[j]] >= 0) kc.push_back(j);
+        }
+        std::vector<int> kk;       // the three low k bits of d's images
+        std::vector<int> c_rows_first, c_cols_first;
+        if (kr.size() >= 3) {
+          kk = {kr[0], kr[1], kr[2]};
+          for (int j : kk) c_rows_first.push_back(prow[bits_t[j]]);
+        } else if (kr.size() == 2 && !kc.empty()) {
+          kk = {kc[0], kr[0], kr[1]};
+          c_cols_first.push_back(pcol[bits_t[kc[0]]]);
+          c_rows_first = {prow[bits_t[kr[0]]], prow[bits_t[kr[1]]]};
+        } else if (kc.size() >= 3) {
+          kk = {kc[0], kc[1], kc[2]};
+          for (int j : kk) c_cols_first.push_back(pcol[bits_t[j]]);
+        } else {
+          continue;
+        }
+        // after the k bits: the image's row order, so that neighbouring lanes / registers hit neighbouring rows
+        const std::vector<int>& d_rows = is_b ? Td.ord_col : Td.ord_row;
+        for (int pos : d_rows) {
+          const int bit = bits_t[sd.n_k + pos];
+          if (prow[bit] >= 0) c_rows_first.push_back(prow[bit]);
+          else if (pcol[bit] >= 0) c_cols_first.push_back(pcol[bit]);
+        }
+        front(Td.ord_k, kk);
+        front(Tc.ord_row, c_rows_first);
+        front(Tc.ord_col, c_cols_first);
+        Tc.fuse_to = d;
+        Tc.fuse_is_b = is_b;
+        Tc.out_entries = (img_z << sd.n_b) / 8;
+        (is_b ? Td.src_b : Td.src_a) = c;
+        k_fixed = true;
+      }
+    }
+    for (int s = 0; s < n_steps; ++s)
+      if (p->dtype == TQ_C64 && s != p->seed_step && p->tc[s].shape_ok) tc_build_tables(p, s);
+    // byte-offset maps of every fused producer (the consumers' tables are final now)
+    for (int c = 0; c < n_steps; ++c) {
+      TcStep& Tc = p->tc[c];
+      if (Tc.fuse_to < 0) continue;
+      const int d = Tc.fuse_to;
+      const tq_tn_step& sd = p->steps[d];
+      const tq_tn_step& sc = p->steps[c];
+      const TcStep& Td = p->tc[d];
+      const bool is_b = Tc.fuse_is_b;
+      const tc::PackParams& P = is_b ? Td.pb : Td.pa;
+      const int64_t img_z = is_b ? Td.img_b_z : Td.img_a_z;
+      const uint32_t chunk = is_b ? (uint32_t)tc::b_chunk_bytes(Td.c_t) : (uint32_t)tc::A_CHUNK;
+      const uint32_t tile_stride = (uint32_t)Td.kblocks * chunk;
+      uint32_t contrib[TQ_TN_MAX_RANK];
+      for (int j = 0; j < TQ_TN_MAX_RANK; ++j) contrib[j] = 0;
+      for (int j = 0; j < P.n_k; ++j)
+        contrib[P.k_bits[j]] = j == 0 ? 8u : j == 1 ? 16u : j == 2 ? 32u : (1u << (j - 3)) * chunk;
+      for (int j = 0; j < P.n_row; ++j)
+        contrib[P.row_bits[j]] = j < P.rows_t_log2 ? (((1u << j) * 64u) ^ (j == 1 ? 16u : j == 2 ? 32u : 0u))
+                                                   : (1u << (j - P.rows_t_log2)) * tile_stride;
+      for (int j = 0; j < P.n_b; ++j) contrib[P.b_bits[j]] = (1u << j) * (uint32_t)img_z;
+      const int n_row_c = Tc.swap ? sc.n_n : sc.n_m, n_col_c = Tc.swap ? sc.n_m : sc.n_n;
+      tc::ImgOut& O = Tc.out;
+      memset(&O, 0, sizeof(O));
+      // accumulator row bit i = default row position ord_row[i] = result bit (n bits first, then m bits)
+      for (int i = 0; i < n_row_c; ++i) O.rmap[i] = contrib[Tc.swap ? Tc.ord_row[i] : sc.n_n + Tc.ord_row[i]];
+      for (int i = 0; i < n_col_c; ++i) O.cmap[i] = contrib[Tc.swap ? sc.n_n + Tc.ord_col[i] : Tc.ord_col[i]];
+      for (int i = 0; i < sc.n_b; ++i) O.bmap[i] = contrib[sc.n_m + sc.n_n + i];
+      O.plane = is_b ? (uint32_t)tc::b_plane_bytes(Td.c_t) : (uint32_t)tc::A_PLANE;
+      O.im_off = is_b ? (uint32_t)(Td.c_t * tc::ROW_BYTES) : 0u;
+      O.n_row = n_row_c;
+      O.n_col = n_col_c;
+      O.n_b = sc.n_b;
     }
   }
   // ---- execution order
@@ -1128,6 +1299,7 @@ static int build_schedule(tq_tn_plan* p) {
       for (int s : members) {
         if ((int)p->arena_const[s] != arena) continue;
         int64_t size = ((int64_t)1 << p->t_rank[n_in + s]);
+        size = std::max(size, p->tc[s].out_entries);  // a fused-pack result lives as its consumer's operand image
         size = (size + 15) & ~(int64_t)15;
         int best = -1;
         for (size_t j = 0; j < freel.size(); ++j)
@@ -1552,6 +1724,9 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
     case TQ_TN_OPT_TC_GATHER:
       p->tc_gather = value != 0;
       return TQ_OK;
+    case TQ_TN_OPT_TC_FUSE_PACK:
+      p->tc_fuse_pack = value != 0;
+      return build_schedule(p);
     case TQ_TN_OPT_FUSE_SMALL:
       p->fuse_enabled = value != 0;
       return build_schedule(p);
@@ -1569,6 +1744,12 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
 int32_t tq_tn_plan_step_kernel(const tq_tn_plan* p, int32_t s) {
   if (!p || s < 0 || s >= (int)p->steps.size()) return TQ_E_INVALID;
   return p->kind[s];
+}
+
+/* step whose operand image step s writes from its epilogue (fused pack), -1: s stores its result plain */
+int32_t tq_tn_plan_step_fuse_to(const tq_tn_plan* p, int32_t s) {
+  if (!p || s < 0 || s >= (int)p->steps.size() || !p->tc_fuse_pack || p->kind[s] != 2) return -1;
+  return p->tc[s].fuse_to;
 }
 
 int32_t tq_tn_plan_num_steps(const tq_tn_plan* p) { return p ? (int32_t)p->steps.size() : -1; }
@@ -1652,6 +1833,9 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* p, int64_t batch) {
 
 namespace tq {
 
+// kernel launches enqueued by the tensor-network entry points since the library was loaded (bench.py's gpu_launches)
+static std::atomic<int64_t> g_tn_launches{0};
+
 static int tc_setup_once() {  // once per device: the opt-in shared-memory size is a per-device function attribute
   static bool done_dev[64] = {};
   const int dev = current_device();
@@ -1670,6 +1854,13 @@ static int tc_setup_once() {  // once per device: the opt-in shared-memory size 
   return TQ_OK;
 }
 
+// Does step s write its consumer's operand image instead of a plain tensor?  (From the GEMM epilogue, or — a split-K
+// launch — from the kernel that adds the partial sums.)
+static bool fused_out_active(const tq_tn_plan* p, int s, int64_t sets) {
+  (void)sets;
+  return s >= 0 && p->tc_fuse_pack && p->tc[s].fuse_to >= 0;
+}
+
 // Pack operands into images (mode bit 0), run one persistent tcgen05 GEMM over all (z, row tile, column tile)
 // (mode bit 1).  img_a / img_b: where each operand's image lives (scratch or pinned); skip_a / skip_b: that image
 // is pinned and already packed.
@@ -1682,6 +1873,19 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   const TcStep& T = p->tc[s];
   const int64_t nz = sets << stp.n_b;
   TQ_REQUIRE(nz < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step %d has %lld batched GEMMs", s, (long long)nz);
+  // operand images written by the producing step's epilogue (fused pack): nothing to pack, the image is the tensor
+  const bool premade_a = fused_out_active(p, T.src_a, sets), premade_b = fused_out_active(p, T.src_b, sets);
+  int64_t img_a_set = T.img_a_z << stp.n_b, img_b_set = T.img_b_z << stp.n_b;
+  if (premade_a) {
+    pack_a = false;
+    img_a = (uint8_t*)const_cast<cx<float>*>(T.swap ? b : a);
+    img_a_set = (T.swap ? sb : sa) * (int64_t)sizeof(cx<float>);
+  }
+  if (premade_b) {
+    pack_b = false;
+    img_b = (uint8_t*)const_cast<cx<float>*>(T.swap ? a : b);
+    img_b_set = (T.swap ? sa : sb) * (int64_t)sizeof(cx<float>);
+  }
   const bool gather_a = gemm && pack_a && T.gather_a && p->tc_gather;
   if (gather_a) pack_a = false;
   if (pack_a || pack_b) {
@@ -1709,6 +1913,7 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
       smem = std::max(smem, 2 * (size_t)tc::b_chunk_bytes(T.c_t));
     }
     tc::k_tc_pack<256><<<dim3((unsigned)(pp.blocks_a + pp.blocks_b), (unsigned)nz), 256, smem, st>>>(pp);
+    g_tn_launches += 1;
   }
   TQ_CUDA_OK(cudaGetLastError());
   if (ev_packed) TQ_CUDA_OK(cudaEventRecord(ev_packed, st));
@@ -1720,6 +1925,8 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   g.c = reinterpret_cast<float2*>(c);
   g.img_a_z = T.img_a_z;
   g.img_b_z = T.img_b_z;
+  g.img_a_set = img_a_set;
+  g.img_b_set = img_b_set;
   g.c_set_stride = sc;
   g.c_rs = T.swap ? 1 : ((int64_t)1 << stp.n_n);
   g.c_cs = T.swap ? ((int64_t)1 << stp.n_n) : 1;
@@ -1739,10 +1946,20 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   const int64_t c_elems = (int64_t)1 << (stp.n_m + stp.n_n + stp.n_b);
   g.splits = splits;
   g.kb_per_split = T.kblocks / splits;
+  const bool img_out = fused_out_active(p, s, sets);
+  tc::ImgOut out_img = T.out;
+  out_img.img = (uint8_t*)c;
+  out_img.set_stride = sc * (int64_t)sizeof(cx<float>);
+  if (img_out && splits == 1) g.out = out_img;  // the result goes straight into the consumer's operand image
   if (splits > 1) {  // partial sums: [split][set][C], summed in order afterwards
     g.c = reinterpret_cast<float2*>(partials);
     g.c_set_stride = c_elems;
     g.c_split_stride = sets * c_elems;
+    if (img_out) {  // accumulator order [bb][row][col]: the rows / columns of a fused producer are re-ordered
+      const int n_col = T.swap ? stp.n_m : stp.n_n;
+      g.c_rs = (int64_t)1 << n_col;
+      g.c_cs = 1;
+    }
   }
   const int64_t total = (int64_t)T.tiles_a * T.tiles_b * nz * splits;
   const unsigned grid = (unsigned)std::min<int64_t>(total, p->num_sms);
@@ -1765,7 +1982,11 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
       default: tc::k_tc_gemm<128, false><<<grid, tc::GEMM_THREADS, smem, st>>>(g); break;
     }
   }
-  if (splits > 1) {
+  g_tn_launches += splits > 1 ? 2 : 1;
+  if (splits > 1 && img_out) {
+    tc::k_tc_splitk_sum_img<<<dim3((unsigned)((c_elems + 255) / 256), (unsigned)sets), 256, 0, st>>>(
+        reinterpret_cast<const float2*>(partials), splits, sets * c_elems, c_elems, out_img, c_elems);
+  } else if (splits > 1) {
     const int64_t n4 = c_elems / 2;
     tc::k_tc_splitk_sum<<<dim3((unsigned)((n4 + 255) / 256), (unsigned)sets), 256, 0, st>>>(
         reinterpret_cast<const float4*>(partials), splits, sets * n4, n4, reinterpret_cast<float4*>(c), sc / 2, n4);
@@ -1915,6 +2136,7 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
       k_tn_step<R><<<dim3((unsigned)blocks, (unsigned)sets), 256, 0, st>>>(a, sa, b, sb, c, sc, d, n_out_elems);
     }
     TQ_CUDA_OK(cudaGetLastError());
+    if (kernel != 2) g_tn_launches += kernel == 3 ? 2 : 1;   // tensor-core steps are counted in run_step_tc
     if (timed) {
       if (kernel != 2) TQ_CUDA_OK(cudaEventRecord(ev[3 * s + 1], st));
       TQ_CUDA_OK(cudaEventRecord(ev[3 * s + 2], st));
@@ -1952,6 +2174,7 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
                                                             p->d_micro, table, shared, perset, p->arena_set, slice);
     }
     TQ_CUDA_OK(cudaGetLastError());
+    g_tn_launches += 1;
     if (timed) {
       TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 1], st));
       TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 2], st));
@@ -1988,6 +2211,7 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     k_tn_final<R><<<dim3((unsigned)((n_final + 255) / 256), (unsigned)sets), 256, 0, st>>>(last, sl, (cx<R>*)out,
                                                                                           n_final, f, n_final);
     TQ_CUDA_OK(cudaGetLastError());
+    g_tn_launches += 1;
     if (!last_dep_slice) break;  // nothing depends on the slice index: one pass is the whole sum
   }
   if (step_ms) {
@@ -2034,6 +2258,8 @@ static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const
   return contract_impl<double>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
                                workspace_bytes, (cudaStream_t)stream, step_ms, backward);
 }
+
+extern "C" int64_t tq_tn_launch_count(void) { return tq::g_tn_launches.load(); }
 
 extern "C" int tq_tn_gather(const void* gate_mats, const void* adj_mats, int64_t src_stride, const int32_t* idx,
                             int64_t n, void* dst, int64_t batch, int32_t dtype, void* stream) {

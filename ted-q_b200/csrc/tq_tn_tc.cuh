@@ -282,11 +282,61 @@ k_tc_pack(const __grid_constant__ PackPair pp) {
 // ---------------------------------------------------------------------------------------------------------
 // GEMM over operand images
 // ---------------------------------------------------------------------------------------------------------
+// Image output ("fused pack"): the epilogue writes the result straight into the operand image of the ONE step that
+// consumes it (split into hi / lo TF32 planes, permuted, swizzled), so that the consumer needs no pack pass: the
+// tensor is never stored in its plain layout and never re-read.  Every bit of the consumer's image address is a
+// GF(2)-linear function of the producer's (row, column, kept-shared) index bits — the swizzle is an XOR of address
+// bits 4-5 with row bits 1-2 — so the byte offset of element (row, col, bb) is the XOR of one table entry per set
+// index bit.
+struct ImgOut {
+  uint8_t* img;          // nullptr: plain output
+  int64_t set_stride;    // bytes between parameter sets
+  uint32_t rmap[26];     // byte-offset contribution of accumulator row bit i
+  uint32_t cmap[26];     // ... of accumulator column bit i
+  uint32_t bmap[8];      // ... of kept-shared index bit i
+  uint32_t plane;        // hi plane -> lo plane
+  uint32_t im_off;       // B image: Re rows -> Im rows (0: the consumer reads this tensor as its row operand A)
+  int32_t n_row, n_col, n_b;  // log2 rows / columns / kept-shared extent of THIS step
+};
+
+// hi / lo split of one complex result and its stores into an A image (one place) or a B image (Re row and Im row)
+__device__ __forceinline__ void img_store1(uint8_t* dst, uint32_t plane, uint32_t im_off, float re, float im) {
+  const float hr = to_tf32(re), hi = to_tf32(im);
+  const float lr = to_tf32(re - hr), li = to_tf32(im - hi);
+  if (im_off == 0) {
+    *reinterpret_cast<float2*>(dst) = make_float2(hr, hi);
+    *reinterpret_cast<float2*>(dst + plane) = make_float2(lr, li);
+  } else {
+    *reinterpret_cast<float2*>(dst) = make_float2(hr, -hi);
+    *reinterpret_cast<float2*>(dst + im_off) = make_float2(hi, hr);
+    *reinterpret_cast<float2*>(dst + plane) = make_float2(lr, -li);
+    *reinterpret_cast<float2*>(dst + plane + im_off) = make_float2(li, lr);
+  }
+}
+// two results that are neighbours along the image's k (16 contiguous bytes per plane)
+__device__ __forceinline__ void img_store2(uint8_t* dst, uint32_t plane, uint32_t im_off, float re0, float im0, float re1,
+                                           float im1) {
+  const float hr0 = to_tf32(re0), hi0 = to_tf32(im0), hr1 = to_tf32(re1), hi1 = to_tf32(im1);
+  const float lr0 = to_tf32(re0 - hr0), li0 = to_tf32(im0 - hi0), lr1 = to_tf32(re1 - hr1), li1 = to_tf32(im1 - hi1);
+  if (im_off == 0) {
+    *reinterpret_cast<float4*>(dst) = make_float4(hr0, hi0, hr1, hi1);
+    *reinterpret_cast<float4*>(dst + plane) = make_float4(lr0, li0, lr1, li1);
+  } else {
+    *reinterpret_cast<float4*>(dst) = make_float4(hr0, -hi0, hr1, -hi1);
+    *reinterpret_cast<float4*>(dst + im_off) = make_float4(hi0, hr0, hi1, hr1);
+    *reinterpret_cast<float4*>(dst + plane) = make_float4(lr0, -li0, lr1, -li1);
+    *reinterpret_cast<float4*>(dst + plane + im_off) = make_float4(li0, lr0, li1, lr1);
+  }
+}
+
 struct GemmParams {
   const uint8_t* img_a;
   const uint8_t* img_b;
   float2* c;
   int64_t img_a_z, img_b_z;  // bytes between z images
+  int64_t img_a_set, img_b_set;  // bytes between parameter sets (img_z << n_b for scratch / pinned images; the per-set
+                                 // arena stride when the producing step wrote the image)
+  ImgOut out;
   int64_t c_set_stride;      // complex entries between parameter sets of C
   int64_t c_rs, c_cs;        // complex-entry stride of an accumulator row / column inside C
   int32_t tiles_a, tiles_b, kblocks, n_z, n_b_log2, stages;
@@ -372,8 +422,9 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         const int64_t z = t / tiles_per_z;
         const int64_t r = t - z * tiles_per_z;
         const int64_t tb = r / p.tiles_a, ta = r - tb * p.tiles_a;
-        const uint8_t* ga = p.img_a + z * p.img_a_z + ta * (int64_t)p.kblocks * A_CHUNK;
-        const uint8_t* gb = p.img_b + z * p.img_b_z + tb * (int64_t)p.kblocks * b_chunk;
+        const int64_t zset = z >> p.n_b_log2, zbb = z & (((int64_t)1 << p.n_b_log2) - 1);
+        const uint8_t* ga = p.img_a + zset * p.img_a_set + zbb * p.img_a_z + ta * (int64_t)p.kblocks * A_CHUNK;
+        const uint8_t* gb = p.img_b + zset * p.img_b_set + zbb * p.img_b_z + tb * (int64_t)p.kblocks * b_chunk;
         for (int kb = kbeg; kb < kbeg + p.kb_per_split; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), GA ? b_chunk : sbytes);
@@ -593,7 +644,42 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
       const int64_t col0 = tb * C_T + h * HALF;
       float2* dst = p.c + split * p.c_split_stride + set * p.c_set_stride + bb * p.c_bb_stride + row * p.c_rs +
                     col0 * p.c_cs;
-      if (p.c_cs == 1) {
+      if (p.out.img != nullptr) {
+        // image output: hi / lo split and scatter into the consumer's operand image (see ImgOut)
+        constexpr int LOG2HALF = HALF == 64 ? 6 : HALF == 32 ? 5 : HALF == 16 ? 4 : 3;
+        const uint32_t urow = (uint32_t)row, ucol0 = (uint32_t)col0, ubb = (uint32_t)bb;
+        uint32_t off = 0;
+        for (int i = 0; i < p.out.n_row; ++i)
+          if ((urow >> i) & 1u) off ^= p.out.rmap[i];
+        for (int i = LOG2HALF; i < p.out.n_col; ++i)
+          if ((ucol0 >> i) & 1u) off ^= p.out.cmap[i];
+        for (int i = 0; i < p.n_b_log2; ++i)
+          if ((ubb >> i) & 1u) off ^= p.out.bmap[i];
+        uint32_t cm[LOG2HALF];
+#pragma unroll
+        for (int i = 0; i < LOG2HALF; ++i) cm[i] = p.out.cmap[i];
+        uint8_t* base = p.out.img + set * p.out.set_stride;
+        const uint32_t plane = p.out.plane, im_off = p.out.im_off;
+        if (cm[0] == 8u) {  // column bit 0 is the image's lowest k bit: neighbouring columns share a 16-byte word
+#pragma unroll
+          for (int j = 0; j < HALF; j += 2) {
+            uint32_t o = off;
+#pragma unroll
+            for (int i = 1; i < LOG2HALF; ++i)
+              if ((j >> i) & 1) o ^= cm[i];
+            img_store2(base + o, plane, im_off, acc_re[j], acc_im[j], acc_re[j + 1], acc_im[j + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < HALF; ++j) {
+            uint32_t o = off;
+#pragma unroll
+            for (int i = 0; i < LOG2HALF; ++i)
+              if ((j >> i) & 1) o ^= cm[i];
+            img_store1(base + o, plane, im_off, acc_re[j], acc_im[j]);
+          }
+        }
+      } else if (p.c_cs == 1) {
         // Row-major result: a lane owns a row, so direct stores would touch 32 rows with 16 bytes each per
         // instruction.  Stage 64-byte row pieces in shared memory and let 4 lanes write one row's piece: every
         // store instruction covers 8 rows x 64 contiguous bytes (full sectors).
@@ -667,6 +753,33 @@ __global__ void k_tc_splitk_sum(const float4* __restrict__ part, int splits, int
     acc.w += v.w;
   }
   c[blockIdx.y * c_set_stride4 + i] = acc;
+}
+
+// Split-K step whose result feeds a fused-pack consumer: adds the partial sums (stored [split][set][bb][row][col] in
+// accumulator order) in a fixed order and writes the consumer's operand image (see ImgOut).
+__global__ void k_tc_splitk_sum_img(const float2* __restrict__ part, int splits, int64_t split_stride,
+                                    int64_t part_set_stride, const __grid_constant__ ImgOut out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t set = blockIdx.y;
+  part += set * part_set_stride;
+  float2 acc = part[i];
+  for (int s = 1; s < splits; ++s) {
+    const float2 v = part[s * split_stride + i];
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  const uint32_t col = (uint32_t)i & ((1u << out.n_col) - 1u);
+  const uint32_t row = (uint32_t)(i >> out.n_col) & ((1u << out.n_row) - 1u);
+  const uint32_t bb = (uint32_t)(i >> (out.n_col + out.n_row));
+  uint32_t off = 0;
+  for (int b = 0; b < out.n_row; ++b)
+    if ((row >> b) & 1u) off ^= out.rmap[b];
+  for (int b = 0; b < out.n_col; ++b)
+    if ((col >> b) & 1u) off ^= out.cmap[b];
+  for (int b = 0; b < out.n_b; ++b)
+    if ((bb >> b) & 1u) off ^= out.bmap[b];
+  img_store1(out.img + set * out.set_stride + off, out.plane, out.im_off, acc.x, acc.y);
 }
 
 }  // namespace tc

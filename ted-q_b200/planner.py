@@ -27,6 +27,8 @@ class PathInfo:
         self.width = width          # log2 of the largest intermediate of ONE slice
         self.flops_log2 = flops_log2  # log2(8 * sum_steps 2^|a u b|) of ONE slice (complex MAC = 8 flops)
         self.n_steps = n_steps
+        self.search_s = None        # seconds the path search took (None: unknown, e.g. a plan given by the caller)
+        self.from_cache = False     # loaded from the on-disk plan cache
 
     @property
     def n_slices(self):
@@ -481,7 +483,12 @@ def cached_plan(cache_dir, inputs, output, build, **key_args) -> PathInfo:
     import os
 
     if not cache_dir:
-        return build()
+        import time
+
+        t0 = time.perf_counter()
+        info = build()
+        info.search_s = time.perf_counter() - t0
+        return info
     blob = json.dumps({"inputs": [list(map(int, t)) for t in inputs], "output": list(map(int, output)),
                        "args": {k: (list(v) if isinstance(v, tuple) else v) for k, v in sorted(key_args.items())}},
                       sort_keys=True).encode()
@@ -494,13 +501,21 @@ def cached_plan(cache_dir, inputs, output, build, **key_args) -> PathInfo:
             sliced = [int(i) for i in d["sliced"]]
             if int(d.get("version", 1)) == PLANNER_VERSION and valid_plan(inputs, output, ssa, sliced):
                 width, fl, _, _ = path_cost(inputs, output, ssa, sliced)
-                return PathInfo(ssa, sliced, width, fl, len(ssa))
+                info = PathInfo(ssa, sliced, width, fl, len(ssa))
+                info.search_s = d.get("search_s")
+                info.from_cache = True
+                return info
         except (OSError, ValueError, KeyError, IndexError, TypeError):
             pass
+    import time
+
+    t0 = time.perf_counter()
     info = build()
+    info.search_s = time.perf_counter() - t0
     os.makedirs(cache_dir, exist_ok=True)
     tmp = path + ".tmp%d" % os.getpid()
     with open(tmp, "w") as fh:
-        json.dump({"version": PLANNER_VERSION, "path": [list(p) for p in info.path], "sliced": list(info.sliced)}, fh)
+        json.dump({"version": PLANNER_VERSION, "search_s": round(info.search_s, 2),
+                   "path": [list(p) for p in info.path], "sliced": list(info.sliced)}, fh)
     os.replace(tmp, path)
     return info

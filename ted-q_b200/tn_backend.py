@@ -425,10 +425,7 @@ class TNExecutor:
         bases = np.array([cap0.data_ptr(), gm.data_ptr(), red_buf.data_ptr() if red_buf is not None else 0],
                          dtype=np.int64)
         ptrs = bases[tab["base"]] + tab["off"] * esz
-        closing = tab["capq"] >= 0
-        if closing.any():
-            bit_arr = np.asarray(bits, dtype=np.int64)[tab["capq"][closing]]
-            ptrs[closing] = np.where(bit_arr == 1, cap1.data_ptr(), cap0.data_ptr())
+        ptrs = self._patch_caps(ptrs, bits, dev)
         strides = tab["stride"]
         any_b = bool((strides != 0).any())
         keep = [gm, am, red_buf]
@@ -468,6 +465,18 @@ class TNExecutor:
         if ws is None or ws.numel() < ws_bytes or ws.device != dev:
             ws = self._amp_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         return plan, ptrs, strides, out, ws, ws_bytes, any_b, tuple(keep)
+
+    def _patch_caps(self, ptrs, bits, dev):
+        """Operand pointer table with the closing caps <bits| of the amplitude network (cap q points at [1, 0] or
+        [0, 1]); every other operand is independent of the bitstring."""
+        tab = self._amplitude_plan()[3]
+        cap0, cap1, _ = self._constants(dev)
+        closing = tab["capq"] >= 0
+        if closing.any():
+            ptrs = ptrs.copy()
+            bit_arr = np.asarray(bits, dtype=np.int64).reshape(-1)[tab["capq"][closing]]
+            ptrs[closing] = np.where(bit_arr == 1, cap1.data_ptr(), cap0.data_ptr())
+        return ptrs
 
     def _slice_group(self, net, info, batched):
         """hyper_opt["slice_batch"] = g: 2^g slices go through the device together as the batch dimension of ONE
@@ -527,6 +536,41 @@ class TNExecutor:
                 out.zero_()
             torch.distributed.all_reduce(torch.view_as_real(out))
         return out.reshape(-1).expand(B) if not any_b else out.reshape(-1)
+
+    def amplitudes(self, flat: torch.Tensor, bits_batch, slice_range=None):
+        """<b_a| U(params) |0...0> for a batch of bitstrings b_a ([A, n] array of 0/1) -> complex [A] (or [A, B] when
+        the gates are batched over parameter sets).  The gate operands are built once, only the closing caps change
+        per bitstring.  Every rank contracts its slice range of every amplitude; the partial sums of the whole batch
+        are combined with ONE all-reduce (contract_parallel)."""
+        if torch.is_tensor(bits_batch):
+            bits_batch = bits_batch.detach().cpu().numpy()
+        bits_batch = np.asarray(bits_batch, dtype=np.int64).reshape(-1, self.n)
+        A = bits_batch.shape[0]
+        plan, ptrs, strides, out0, ws, ws_bytes, any_b, _keep = self._amplitude_operands(flat, bits_batch[0])
+        B = flat.shape[0]
+        grouped = getattr(self, "_amp_group", None) is not None
+        Bp = out0.shape[0] if grouped else B
+        dev = flat.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if slice_range is None:
+            s0, s1, dist_on = self._slice_range(plan.n_slices)
+        else:
+            (s0, s1), dist_on = slice_range, False
+        out = torch.zeros((A,) + tuple(out0.shape), dtype=out0.dtype, device=dev)
+        with torch.cuda.device(dev):
+            for a in range(A):
+                if s1 > s0:
+                    plan.contract(self._patch_caps(ptrs, bits_batch[a], dev), strides, Bp, s0, s1, out[a].data_ptr(),
+                                  ws.data_ptr(), ws_bytes, stream)
+        if grouped:
+            out = out.sum(1, keepdim=True)       # the grouped indices are summed like every sliced index
+            any_b = False
+        if dist_on:
+            if plan.n_slices == 1 and torch.distributed.get_rank() != 0:
+                out.zero_()
+            torch.distributed.all_reduce(torch.view_as_real(out))
+        out = out.reshape(A, -1)
+        return out if any_b else out[:, 0]
 
     def slice_members(self, plan_slice: int):
         """Slice ids of the path's own slicing (bit j <-> info.sliced[j]) that plan slice ``plan_slice`` covers: one

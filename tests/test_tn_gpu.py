@@ -344,7 +344,7 @@ def test_c5_slices_match_host_tensordot():
     cc.amplitude(bits, slice_range=(0, 1))
     n_groups = int(os.environ.get("TQ_TEST_C5_GROUPS", "1"))
     members = [cc._tn.slice_members(i) for i in range(n_groups)]
-    _, amps, n_slices, _ = c5_cpu_slices(0, slice_ids=[sid for m in members for sid in m])
+    _, amps, n_slices, _ = c5_cpu_slices(0, slice_ids=[sid for m in members for sid in m], dtype=torch.complex128)
     assert n_slices == 64
     group = len(members[0])
     scale = max(abs(a) for a in amps)

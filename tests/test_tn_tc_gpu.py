@@ -195,3 +195,74 @@ def test_apply_kernel_batched_sets():
     got, kinds = _contract([a_idx, b_idx], o_idx, [A, B], [True, True], False, B=n_sets, min_log2=20)
     assert kinds == [5]
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def _contract_net(inputs, output, path, arrays, batched, B=1, opts=()):
+    plan = capi.TnPlan(inputs, output, path, [], batched, capi.TQ_C64)
+    plan.set_option(capi.TN_OPT_TC_MIN_LOG2, 0)
+    plan.set_option(capi.TN_OPT_FUSE_SMALL, 0)
+    for k, v in opts:
+        plan.set_option(k, v)
+    cd = torch.complex64
+    ts = [torch.tensor(a, dtype=cd, device="cuda").contiguous() for a in arrays]
+    ptrs = [t.data_ptr() for t in ts]
+    strides = [int(np.prod(a.shape[1:])) if b else 0 for a, b in zip(arrays, batched)]
+    out = torch.zeros((B if any(batched) else 1, 1 << len(output)), dtype=cd, device="cuda")
+    ws_bytes = plan.workspace_bytes(B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    plan.contract(ptrs, strides, B, 0, 1, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                  torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
+    fused = [plan.step_fuse_to(s) for s in range(plan.n_steps)]
+    return out.cpu().numpy(), kinds, fused
+
+
+# (free of T0, K0, free of T1, K1 taken from T0's free, K1 taken from T1's free, free of T2, kept-shared, batch B)
+CHAINS = [
+    (9, 4, 5, 3, 0, 5, 0, 1),     # consumer contracts indices that were rows of the producer
+    (9, 4, 6, 0, 3, 5, 0, 1),     # ... that were columns of the producer
+    (10, 5, 6, 2, 3, 6, 0, 1),    # both
+    (4, 5, 9, 0, 4, 7, 0, 1),     # the producer's rows come from its rhs (swap)
+    (8, 3, 4, 4, 0, 9, 0, 1),     # the fused tensor becomes the COLUMN operand (B image) of the consumer
+    (9, 4, 5, 3, 0, 5, 1, 1),     # a kept-shared index runs through both steps
+    (9, 6, 5, 2, 2, 4, 0, 3),     # batched parameter sets
+    (7, 11, 4, 3, 0, 5, 0, 1),    # producer with few tiles and a long K: split-K, falls back to plain + pack
+]
+
+
+@pytest.mark.parametrize("shape", CHAINS, ids=lambda s: "m%d_k%d_n%d_kr%d_kc%d_f%d_b%d_B%d" % s)
+@pytest.mark.parametrize("shuffle", [False, True], ids=["canonical", "permuted"])
+def test_fused_pack_chain_matches_einsum_and_unfused(shape, shuffle):
+    """Fused pack (TQ_TN_OPT_TC_FUSE_PACK): the first tensor-core step writes the second step's operand image from
+    its epilogue.  Same numbers as the pack-kernel path (to fp32 rounding), both within 1e-5 of a complex128 einsum."""
+    f0, k0, f1, kr, kc, f2, nb, B = shape
+    rng = np.random.RandomState(sum(shape) * 7 + int(shuffle))
+    ids = iter(range(64))
+    M0 = [next(ids) for _ in range(f0)]
+    K0 = [next(ids) for _ in range(k0)]
+    N0 = [next(ids) for _ in range(f1)]
+    F2 = [next(ids) for _ in range(f2)]
+    Bt = [next(ids) for _ in range(nb)]
+    K1 = M0[:kr] + N0[:kc]
+    t0, t1, t2 = M0 + K0 + Bt, K0 + N0 + Bt, K1 + F2 + Bt
+    out = [i for i in M0 + N0 if i not in K1] + F2 + Bt
+    if shuffle:
+        for l in (t0, t1, t2, out):
+            rng.shuffle(l)
+    batched = [B > 1, False, False]
+    arrays = [_rand(rng, ((B,) if b else ()) + (2,) * len(t)) / 2 for t, b in zip((t0, t1, t2), batched)]
+    sub = lambda idx, b: ([51] if b else []) + list(idx)
+    ref = np.einsum(arrays[0].astype(np.complex128), sub(t0, batched[0]), arrays[1].astype(np.complex128), sub(t1, False),
+                    arrays[2].astype(np.complex128), sub(t2, False), sub(out, B > 1)).reshape(B, -1)
+    path = [(0, 1), (3, 2)]
+    on, kinds, fused = _contract_net([t0, t1, t2], out, path, arrays, batched, B)
+    off, kinds_off, fused_off = _contract_net([t0, t1, t2], out, path, arrays, batched, B,
+                                              opts=[(capi.TN_OPT_TC_FUSE_PACK, 0)])
+    assert kinds == [2, 2] and kinds_off == [2, 2], kinds
+    assert fused == [1, -1] and fused_off == [-1, -1], (fused, fused_off)
+    assert np.abs(off - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert np.abs(on - ref).max() <= 1e-5 * np.abs(ref).max()
+    # same hi / lo split of the same fp32 values; only the order in which k is accumulated may differ (the consumer
+    # moves the three k bits its producer can store contiguously to the front): fp32 rounding noise
+    assert np.abs(on - off).max() <= 2e-6 * np.abs(ref).max(), np.abs(on - off).max()
