@@ -74,7 +74,7 @@ def load_peaks():
 C3_TOTAL_SETS = int(os.environ.get("TQ_C3_SETS", "1024"))
 
 
-def workload(name, world=1):
+def workload(name, world=1, rank=None):
     """-> (spec, inputs [B, P] float np array of THIS rank's share, complex dtype string, description, scaling)"""
     from tedq_b200 import workloads as W
 
@@ -90,7 +90,7 @@ def workload(name, world=1):
     if name == "c3":
         spec = W.hea(20, 10)
         full = rng.uniform(0, 1, size=(C3_TOTAL_SETS, spec["n_params"])).astype(np.float32)
-        rank = int(os.environ.get("RANK", "0"))
+        rank = (int(os.environ.get("RANK", "0")) if world > 1 else 0) if rank is None else rank
         per = (C3_TOTAL_SETS + world - 1) // world
         return spec, full[rank * per:(rank + 1) * per], "c64", \
             (f"c3: 20-qubit HEA depth 10 (630 gates, 440 params), 20 Z expvals, {C3_TOTAL_SETS} parameter sets in "
@@ -250,8 +250,8 @@ def cpu_baseline_entry(cpu, B, note=""):
 def check_against_cpu(what, cpu, out_gpu, grad_gpu, cdt):
     """max |gpu - cpu| over the sampled sets, against tol * max(1, |ref|) (values) and 4x that (gradients)."""
     tol = 1e-5 if cdt == "c64" else 1e-11
-    n = cpu["n"]
-    ref = cpu["out"].reshape(n, -1)
+    n = min(cpu["n"], out_gpu.shape[0])
+    ref = cpu["out"][:n].reshape(n, -1)
     got = out_gpu[:n].reshape(n, -1).cpu()
     if ref.is_complex():
         ref, got = torch.view_as_real(ref.contiguous()), torch.view_as_real(got.contiguous().to(ref.dtype))
@@ -259,7 +259,7 @@ def check_against_cpu(what, cpu, out_gpu, grad_gpu, cdt):
     assert_parity(f"{what} outputs", err_o, tol)
     err_g = None
     if grad_gpu is not None:
-        rg = cpu["grad"].double()
+        rg = cpu["grad"][:n].double()
         err_g = float(((grad_gpu[:n].cpu().double() - rg).abs() / rg.abs().clamp(min=1.0)).max())
         assert_parity(f"{what} gradients", err_g, 4 * tol)
     return {"sets": n, "max_err_out": err_o, "max_err_grad": err_g, "tolerance": tol, "asserted": True}
@@ -858,7 +858,10 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: ONE JSON line
-        torch.distributed.init_process_group("nccl", device_id=device)
+        import datetime
+        # a rank that dies inside a collective must take the job down in minutes, not after NCCL's default 10
+        torch.distributed.init_process_group("nccl", device_id=device,
+                                             timeout=datetime.timedelta(seconds=int(os.environ.get("TQ_NCCL_TIMEOUT", "300"))))
     dist = Dist(device)
     do_cpu = rank == 0 and world == 1 and os.environ.get("TQ_BENCH_CPU", "1") == "1"
     budget = float(os.environ.get("TQ_CPU_BASELINE_SECONDS", "8"))

@@ -284,6 +284,19 @@ int tq_tn_contract(const tq_tn_plan* plan, const void* const* inputs, const int6
                    int64_t slice_begin, int64_t slice_end, void* out, void* workspace, size_t workspace_bytes,
                    void* cuda_stream);
 
+/* Two-stage form of tq_tn_contract, for callers that contract the same network many times (a batch of amplitudes):
+ * tq_tn_contract_prepare runs the once-per-call part (the steps that depend on no sliced index, the pinned operand
+ * images) into `workspace`; tq_tn_contract_slices then runs only the slice loop on that workspace with the same
+ * inputs.  With two workspaces and two streams the (latency-bound) preparation of the next contraction overlaps the
+ * (throughput-bound) slices of the current one; the caller orders the two calls with events.  slice_begin of
+ * _prepare: the first slice the following _slices call will run (it selects the sliced entries of pinned images). */
+int tq_tn_contract_prepare(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides,
+                           int64_t batch, int64_t slice_begin, void* workspace, size_t workspace_bytes,
+                           void* cuda_stream);
+int tq_tn_contract_slices(const tq_tn_plan* plan, const void* const* inputs, const int64_t* input_strides,
+                          int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
+                          size_t workspace_bytes, void* cuda_stream);
+
 /* ---- reverse mode through the contraction tree (the reference differentiates through tree.contract with torch's
  *      tape, pytorch_backend.py:276/:339 under back_prop) ------------------------------------------------------
  * tq_tn_plan_enable_backward appends, for every forward step C = A x B on the way to an input that needs a

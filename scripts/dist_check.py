@@ -29,7 +29,28 @@ par = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=Fals
                           hyper_opt={"max_repeats": 4, "slicing_opts": {"target_num_slices": 8, "contract_parallel": True}})
 a1, a2 = complex(one.amplitude(bits).cpu()), complex(par.amplitude(bits).cpu())
 err2 = abs(a1 - a2) / abs(a1)
+# 3. slice-sharded reverse pass: forward + reverse pass of this rank's slices, one all-reduce of the gradients
+spec = W.mbl_1d(8)
+circ = W.build_circuit(spec, qb)
+x = torch.tensor(W.c2_inputs(3, 8, 1), device="cuda")
+res = []
+for par_on in (False, True):
+    cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                             hyper_opt={"max_repeats": 2, "tn_backward": "tree",
+                                        "slicing_opts": {"target_num_slices": 8, "contract_parallel": par_on}})
+    assert cc._tn.infos[0].n_slices >= 8
+    xx = x.clone().requires_grad_(True)
+    y = cc.batched(xx)
+    (y * torch.tensor([0.3, -0.8], device="cuda")).sum().backward()
+    res.append((y.detach(), xx.grad.clone()))
+err3 = max(float((res[0][0] - res[1][0]).abs().max()), float((res[0][1] - res[1][1]).abs().max()))
+# 4. a batch of amplitudes: slices sharded, ONE all-reduce for the whole batch
+bits_batch = np.random.RandomState(3).randint(0, 2, size=(5, 16))
+b1, b2 = one.amplitudes(bits_batch).cpu(), par.amplitudes(bits_batch).cpu()
+err4 = float((b1 - b2).abs().max() / b1.abs().max())
 if rank == 0:
+    print("sharded reverse pass max err %.2e %s" % (err3, "OK" if err3 < 1e-5 else "FAIL"))
+    print("amplitudes batch rel err %.2e %s" % (err4, "OK" if err4 < 1e-5 else "FAIL"))
     print("measurement_parallel max err %.2e %s" % (err1, "OK" if err1 < 1e-5 else "FAIL"))
     print("contract_parallel rel err %.2e %s" % (err2, "OK" if err2 < 1e-5 else "FAIL"))
 dist.destroy_process_group()

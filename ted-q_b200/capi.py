@@ -141,6 +141,10 @@ def lib() -> C.CDLL:
     L.tq_tn_workspace_bytes.restype = sz
     L.tq_tn_contract.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
     L.tq_tn_contract.restype = i32
+    L.tq_tn_contract_prepare.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, sz, vp]
+    L.tq_tn_contract_prepare.restype = i32
+    L.tq_tn_contract_slices.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
+    L.tq_tn_contract_slices.restype = i32
     L.tq_tn_plan_enable_backward.argtypes = [vp, pi32]
     L.tq_tn_plan_enable_backward.restype = i32
     L.tq_tn_backward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, vp, sz, vp]
@@ -490,6 +494,19 @@ class TnPlan:
         arr = np.asarray(ms, dtype=np.float32)
         self.last_pinned_pack_ms = float(arr[2 * self.n_steps])
         return arr[:2 * self.n_steps].reshape(self.n_steps, 2)
+
+    def contract_prepare(self, input_ptrs, input_strides, batch, slice_begin, ws_ptr, ws_bytes, stream):
+        """Once-per-call part of a contraction (slice-invariant steps, pinned operand images) into the workspace."""
+        ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
+        check(lib().tq_tn_contract_prepare(self.handle, ptrs, strides, batch, slice_begin, ws_ptr, ws_bytes, stream),
+              "tq_tn_contract_prepare")
+
+    def contract_slices(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes,
+                        stream):
+        """Slice loop of a contraction on a workspace ``contract_prepare`` filled with the same inputs."""
+        ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
+        check(lib().tq_tn_contract_slices(self.handle, ptrs, strides, batch, slice_begin, slice_end, out_ptr, ws_ptr,
+                                          ws_bytes, stream), "tq_tn_contract_slices")
 
     def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
         ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)

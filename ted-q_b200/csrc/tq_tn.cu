@@ -2000,7 +2000,9 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
 template <typename R>
 static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const int64_t* strides, int64_t B,
                          int64_t s_begin, int64_t s_end, void* out, void* workspace, size_t ws_bytes,
-                         cudaStream_t st, float* step_ms, bool backward) {
+                         cudaStream_t st, float* step_ms, bool backward, int stage = 0) {
+  // stage 0: the whole call; 1: only the once-per-call part (slice-invariant steps, pinned operand images);
+  // 2: only the slice loop, on a workspace that stage 1 prepared with the same inputs
   TQ_REQUIRE(ws_bytes >= tq_tn_workspace_bytes(p, B), TQ_E_WORKSPACE, "tq_tn_contract: workspace too small");
   const int n_in = p->n_in;
   const int n_steps = (int)p->steps.size();
@@ -2188,12 +2190,15 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     return TQ_OK;
   }
   // once-per-call items, then the slice loop
-  for (const SchedItem& it : p->items[0])
-    if ((rc = run_item(it, 0))) return rc;
-  if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps], st));
-  for (int s = 0; s < n_steps; ++s)
-    if (p->dep_slice[s] && (rc = run_step(s, s_begin, true))) return rc;
-  if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps + 1], st));
+  if (stage != 2) {
+    for (const SchedItem& it : p->items[0])
+      if ((rc = run_item(it, 0))) return rc;
+    if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps], st));
+    for (int s = 0; s < n_steps; ++s)
+      if (p->dep_slice[s] && (rc = run_step(s, s_begin, true))) return rc;
+    if (step_ms) TQ_CUDA_OK(cudaEventRecord(ev[3 * n_steps + 1], st));
+  }
+  if (stage == 1) return TQ_OK;
   FinalDev f;
   memset(&f, 0, sizeof(f));
   f.rank = p->n_out;
@@ -2244,8 +2249,9 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
 
 static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
                            int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
-                           size_t workspace_bytes, void* stream, float* step_ms, bool backward = false) {
-  TQ_REQUIRE(p && inputs && out && workspace && batch > 0, TQ_E_INVALID, "tq_tn_contract: null argument");
+                           size_t workspace_bytes, void* stream, float* step_ms, bool backward = false, int stage = 0) {
+  TQ_REQUIRE(p && inputs && (out || stage == 1) && workspace && batch > 0, TQ_E_INVALID,
+             "tq_tn_contract: null argument");
   TQ_REQUIRE(!p->steps.empty(), TQ_E_INVALID, "tq_tn_contract: empty plan");
   TQ_REQUIRE_DEVICE(p, "tq_tn_contract");
   const int64_t ns = (int64_t)1 << p->n_sliced;
@@ -2254,9 +2260,9 @@ static int tn_contract_any(const tq_tn_plan* p, const void* const* inputs, const
              (long long)slice_end, (long long)ns);
   if (p->dtype == TQ_C64)
     return contract_impl<float>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
-                                workspace_bytes, (cudaStream_t)stream, step_ms, backward);
+                                workspace_bytes, (cudaStream_t)stream, step_ms, backward, stage);
   return contract_impl<double>(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace,
-                               workspace_bytes, (cudaStream_t)stream, step_ms, backward);
+                               workspace_bytes, (cudaStream_t)stream, step_ms, backward, stage);
 }
 
 extern "C" int64_t tq_tn_launch_count(void) { return tq::g_tn_launches.load(); }
@@ -2282,6 +2288,20 @@ extern "C" int tq_tn_contract(const tq_tn_plan* p, const void* const* inputs, co
                               size_t workspace_bytes, void* stream) {
   return tn_contract_any(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace, workspace_bytes,
                          stream, nullptr);
+}
+
+extern "C" int tq_tn_contract_prepare(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
+                                      int64_t batch, int64_t slice_begin, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  return tn_contract_any(p, inputs, input_strides, batch, slice_begin, slice_begin, nullptr, workspace,
+                         workspace_bytes, stream, nullptr, false, 1);
+}
+
+extern "C" int tq_tn_contract_slices(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,
+                                     int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  return tn_contract_any(p, inputs, input_strides, batch, slice_begin, slice_end, out, workspace, workspace_bytes,
+                         stream, nullptr, false, 2);
 }
 
 extern "C" int tq_tn_backward(const tq_tn_plan* p, const void* const* inputs, const int64_t* input_strides,

@@ -35,10 +35,11 @@ class TNExecutor:
         # tn_simplify=True (the reference's default; its own simplifier does not work, tensor_network.py:94):
         # diagonal / controlled gates enter with shared wire indices and reduced tensors (tn_simplify.py)
         self.simplify = bool(getattr(backend, "_tn_simplify", False))
-        # hyper_opt["light_cone"] (opt-in): expval / marginal networks keep only the gates inside the measurement's
-        # causal cone (tn_index.light_cone); the gates outside cancel against their own adjoints
+        # hyper_opt["light_cone"] (default on): expval / marginal networks keep only the gates inside the
+        # measurement's causal cone (tn_index.light_cone); the gates outside cancel against their own adjoints.
+        # False = the reference's networks, every gate twice (tensor_network.py:1027-1072)
         self.networks = (tn_simplify if self.simplify else tn_index).networks_of_circuit(
-            circuit, prune_light_cone=bool(self.ho.get("light_cone", False)))
+            circuit, prune_light_cone=bool(self.ho.get("light_cone", True)))
         self.gate_structs = tn_simplify.gate_structures(circuit) if self.simplify else [None] * len(circuit.operators)
         self.gate_batched = [any(i >= 0 for i in g.param_idx) for g in backend._ir.gates]
         self.infos: List[planner.PathInfo] = []
@@ -199,16 +200,18 @@ class TNExecutor:
         return cache[i]
 
     def tree_backward_available(self) -> bool:
-        """Reverse mode through the contraction tree needs unsliced plans on one rank.  hyper_opt["tn_backward"] =
-        "tree" | "adjoint" forces one of the two gradient paths; default: the adjoint state-vector sweeps while a
-        state vector fits comfortably (<= 26 qubits: they are the cheaper gradient there), the tree beyond."""
+        """Reverse mode through the contraction tree.  hyper_opt["tn_backward"] = "tree" | "adjoint" forces one of the
+        two gradient paths; default: the adjoint state-vector sweeps while a state vector fits comfortably (<= 26
+        qubits: they are the cheaper gradient there), the tree beyond.  With ``contract_parallel`` the slices of the
+        reverse pass are sharded over the ranks like those of the forward pass (every rank runs forward + reverse
+        pass of its slice range, ONE all-reduce of the [B, P] gradients; the reference's RPC runner does backward
+        across its slice workers the same way, examples/qubit_rpc.py:81-83)."""
         mode = self.ho.get("tn_backward")
         if mode == "adjoint":
             return False
-        ok = not self.contract_parallel and not self.measurement_parallel and any(self.gate_batched)
+        ok = not self.measurement_parallel and any(self.gate_batched)
         if mode == "tree" and not ok:
-            raise ValueError("tn_backward='tree' needs trainable parameters and a single rank (no contract_parallel / "
-                             "measurement_parallel)")
+            raise ValueError("tn_backward='tree' needs trainable parameters and no measurement_parallel")
         return ok and (mode == "tree" or self.n > 26)
 
     def _plan_bwd(self, i, device=None) -> capi.TnPlan:
@@ -329,6 +332,7 @@ class TNExecutor:
         stream = torch.cuda.current_stream(dev).cuda_stream
         grad = torch.zeros((B, be._ir.n_params), dtype=be._rdtype, device=dev)
         plan_sv = be.plan(dev)
+        sharded = False
         for i, plan, ptrs, strides, ws, _alive in kept:
             gi = dy[:, i].reshape(B, -1)
             gout = (gi if gi.is_complex() else gi.to(be._rdtype) + 0j).to(be._cdtype).contiguous()
@@ -339,14 +343,20 @@ class TNExecutor:
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 scratch = torch.zeros((B, 1 << plan.n_out), dtype=be._cdtype, device=dev)
             base = (ws.data_ptr() + 255) // 256 * 256 + perset_off
+            s0, s1, dist_on = self._slice_range(plan.n_slices)
+            sharded = sharded or dist_on
+            if dist_on and plan.n_slices == 1:      # an unsliced network: rank 0's reverse pass is the whole gradient
+                s0, s1 = (0, 1) if torch.distributed.get_rank() == 0 else (0, 0)
             with torch.cuda.device(dev):
-                for sl in range(plan.n_slices):
+                for sl in range(s0, s1):
                     if scratch is not None:
                         plan.contract(ptrs, strides, B, sl, sl + 1, scratch.data_ptr(), ws.data_ptr(), ws.numel(), stream)
                     og, oa = self._grad_tables(i, dev, sl)
                     plan.backward(ptrs, strides, B, gout.data_ptr(), ws.data_ptr(), ws.numel(), stream, sl)
                     capi.check(L.tq_tn_param_grads(plan_sv.handle, flat.data_ptr(), B, base, set_stride, og.data_ptr(),
                                                    oa.data_ptr(), grad.data_ptr(), stream), "tq_tn_param_grads")
+        if sharded:     # the contraction is a sum over slices: so are its parameter gradients
+            torch.distributed.all_reduce(grad)
         return grad
 
     # ------------------------------------------------------------------ amplitudes (C5)
@@ -557,11 +567,44 @@ class TNExecutor:
         else:
             (s0, s1), dist_on = slice_range, False
         out = torch.zeros((A,) + tuple(out0.shape), dtype=out0.dtype, device=dev)
+        overlap = A > 1 and s1 > s0 and bool(self.ho.get("overlap_prepare", True))
         with torch.cuda.device(dev):
-            for a in range(A):
-                if s1 > s0:
-                    plan.contract(self._patch_caps(ptrs, bits_batch[a], dev), strides, Bp, s0, s1, out[a].data_ptr(),
-                                  ws.data_ptr(), ws_bytes, stream)
+            if not overlap:
+                for a in range(A):
+                    if s1 > s0:
+                        plan.contract(self._patch_caps(ptrs, bits_batch[a], dev), strides, Bp, s0, s1,
+                                      out[a].data_ptr(), ws.data_ptr(), ws_bytes, stream)
+            else:
+                # Two workspaces, two streams: the once-per-call part of amplitude a + 1 (hundreds of tiny,
+                # latency-bound steps and the pinned operand images) runs on a side stream while the slices of
+                # amplitude a (throughput-bound GEMMs) run on the caller's stream.
+                ws2 = getattr(self, "_amp_ws2", None)
+                if ws2 is None or ws2.numel() < ws_bytes or ws2.device != dev:
+                    ws2 = self._amp_ws2 = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                side = getattr(self, "_amp_side_stream", None)
+                if side is None or side.device != dev:
+                    side = self._amp_side_stream = torch.cuda.Stream(device=dev)
+                wss = (ws, ws2)
+                main = torch.cuda.current_stream(dev)
+                ptr_tabs = [self._patch_caps(ptrs, bits_batch[a], dev) for a in range(A)]
+                ev_prep = [torch.cuda.Event() for _ in range(A)]
+                ev_done = [torch.cuda.Event() for _ in range(A)]
+                side.wait_stream(main)            # gate operands / zeroed output are ready
+                plan.contract_prepare(ptr_tabs[0], strides, Bp, s0, wss[0].data_ptr(), ws_bytes, side.cuda_stream)
+                ev_prep[0].record(side)
+                for a in range(A):
+                    main.wait_event(ev_prep[a])
+                    plan.contract_slices(ptr_tabs[a], strides, Bp, s0, s1, out[a].data_ptr(), wss[a & 1].data_ptr(),
+                                         ws_bytes, stream)
+                    ev_done[a].record(main)
+                    if a + 1 < A:
+                        if a >= 1:
+                            side.wait_event(ev_done[a - 1])     # workspace (a + 1) & 1 is free again
+                        plan.contract_prepare(ptr_tabs[a + 1], strides, Bp, s0, wss[(a + 1) & 1].data_ptr(), ws_bytes,
+                                              side.cuda_stream)
+                        ev_prep[a + 1].record(side)
+                ws2.record_stream(side)
+                ws.record_stream(side)
         if grouped:
             out = out.sum(1, keepdim=True)       # the grouped indices are summed like every sliced index
             any_b = False

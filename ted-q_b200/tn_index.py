@@ -86,6 +86,17 @@ def cone_of_measurement(gate_qubits, kind, payload):
     return None
 
 
+def cone_qubits(gate_qubits, cone, kind, payload) -> List[int]:
+    """Qubits a pruned network keeps (ascending): those the cone's gates touch plus the measured ones.  Every other
+    wire is an opening |0> cap contracted with its own closing cap, <0|0> = 1: both caps are dropped."""
+    qs = {int(q) for gi in cone for q in gate_qubits[gi]}
+    if kind == "expval":
+        qs |= {int(q) for ob in payload for q in ob}
+    elif payload is not None:
+        qs |= {int(q) for q in payload}
+    return sorted(qs)
+
+
 def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measurements,
                prune_light_cone: bool = False) -> List[Network]:
     """``measurements``: sequence of (kind, payload) with kind in {"expval", "probs", "state"};
@@ -111,10 +122,12 @@ def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measuremen
         ops = list(base_ops)
         gates = list(range(len(gate_qubits)))
         cone = cone_of_measurement(gate_qubits, kind, payload) if prune_light_cone else None
+        kept_q = list(range(n))
         if cone is not None and len(cone) < len(gates):
             gates = cone
+            kept_q = cone_qubits(gate_qubits, cone, kind, payload)
             wire, cur = list(range(n)), n - 1
-            inputs, ops = [[q] for q in range(n)], [(OPD_CAP, q) for q in range(n)]
+            inputs, ops = [[q] for q in kept_q], [(OPD_CAP, q) for q in kept_q]
             for gi in gates:
                 idx, cur = _thread(wire, cur, list(gate_qubits[gi]))
                 inputs.append(idx)
@@ -141,7 +154,7 @@ def index_maps(num_qubits: int, gate_qubits: Sequence[Sequence[int]], measuremen
             idx, cur = _thread(wire, cur, qs)
             inputs.append(idx)
             ops.append((OPD_ADJ, gi))
-        for q in range(n):
+        for q in kept_q:
             inputs.append([wire[q]])
             ops.append((OPD_CAP, q))
         nets.append(Network(inputs, output, ops))

