@@ -239,6 +239,73 @@ class B200ParamShift(torch.autograd.Function):
         return out.reshape(lead + out.shape[1:]), 0
 
 
+class _ObsShim:
+    """A fixed Hermitian observable derived from the user's (O^2 of ``var``, an eigenprojector of ``sample``)."""
+
+    is_observable = True
+    name = "Hermitian"
+
+    def __init__(self, qubits, matrix):
+        self.qubits = [int(q) for q in qubits]
+        self.matrix = np.asarray(matrix, dtype=np.complex128)
+        self.num_qubits = len(self.qubits)
+        self.parameters, self.trainable_params = [], []
+
+
+class _MeasShim:
+    def __init__(self, obs):
+        from .frontend import Expectation
+
+        self.return_type, self.obs, self.qubits, self.after_state = Expectation, obs, None, False
+
+
+class _CircuitShim:
+    """The user's circuit with its ``var`` / ``sample`` measurements expanded into plain expectation values."""
+
+    def __init__(self, circuit, measurements):
+        self.num_qubits, self.operators, self.init_state = circuit.num_qubits, circuit.operators, circuit.init_state
+        self.measurements = measurements
+
+
+def _obs_matrix(obs):
+    """(qubits, dense matrix) of an observable or a product of single-qubit observables."""
+    if isinstance(obs, list):
+        from .ir import _kron_obs
+
+        return _kron_obs(obs, None)
+    k = len(obs.qubits)
+    return tuple(int(q) for q in obs.qubits), np.asarray(obs.matrix, dtype=np.complex128).reshape(2 ** k, 2 ** k)
+
+
+def _expand_measurements(circuit):
+    """-> (inner measurement list, recipe) or (None, None) when the circuit has no ``var`` / ``sample``.
+    recipe[j] = ("copy", i) | ("var", i_O, i_O2) | ("sample", [i_projectors], eigenvalues, shots)."""
+    kinds = [getattr(ms.return_type, "value", ms.return_type) for ms in circuit.measurements]
+    if not any(k in ("var", "sample") for k in kinds):
+        return None, None
+    inner, recipe = [], []
+    for ms, kind in zip(circuit.measurements, kinds):
+        if kind == "var":
+            qs, mat = _obs_matrix(ms.obs)
+            inner += [_MeasShim(_ObsShim(qs, mat)), _MeasShim(_ObsShim(qs, mat @ mat))]
+            recipe.append(("var", len(inner) - 2, len(inner) - 1))
+        elif kind == "sample":
+            qs, mat = _obs_matrix(ms.obs)
+            if len(qs) > 4:
+                raise ValueError("sample: observables on more than 4 qubits are not supported")
+            if not np.allclose(mat, mat.conj().T, atol=1e-10):
+                raise ValueError("sample: the observable's matrix is not Hermitian")
+            lam, vec = np.linalg.eigh(mat)
+            first = len(inner)
+            for i in range(len(lam)):
+                inner.append(_MeasShim(_ObsShim(qs, np.outer(vec[:, i], vec[:, i].conj()))))
+            recipe.append(("sample", list(range(first, len(inner))), lam, int(getattr(ms, "num_shots", 1))))
+        else:
+            inner.append(ms)
+            recipe.append(("copy", len(inner) - 1))
+    return inner, recipe
+
+
 class B200Backend:
     """Drop-in for ``PyTorchBackend`` on B200 (constructor: pytorch_backend.py:67-82, compiled_circuit.py:48-69)."""
 
@@ -256,6 +323,12 @@ class B200Backend:
         self._tn_simplify = tn_simplify
         self._hyper_opt = hyper_opt if isinstance(hyper_opt, dict) else {}
         self._backend = backend
+        # var / sample (declared but NotImplemented in the reference, measurement.py:158-171) are served by plain
+        # expectation values of derived observables (<O>, <O^2>; eigenprojectors) and combined after the engine ran
+        self._user_measurements = circuit.measurements
+        inner, self._recipe = _expand_measurements(circuit)
+        if inner is not None:
+            circuit = _CircuitShim(circuit, inner)
         self._circuit = circuit
         self._num_qubits = circuit.num_qubits
         self._operators = list(circuit.operators)
@@ -513,9 +586,30 @@ class B200Backend:
         track = torch.is_grad_enabled() and bool(self._requires_grad) and (flat.requires_grad or wrapped)
         if not track and not wrapped:
             with torch.no_grad():
-                return self._values(flat, False)[0]
+                return self._combine(self._values(flat, False)[0])
         # under torch.func transforms the reverse pass re-runs the forward (B200Grad): keep no state
-        return fn.apply({"backend": self, "need_grad": track and not wrapped}, flat)
+        return self._combine(fn.apply({"backend": self, "need_grad": track and not wrapped}, flat))
+
+    def _combine(self, inner: torch.Tensor) -> torch.Tensor:
+        """Engine results [B, n_inner] -> the user's measurements [B, n_meas, ...] (identity without var / sample):
+        var = <O^2> - <O>^2 (differentiable); sample = eigenvalues drawn from the exact outcome distribution."""
+        if self._recipe is None:
+            return inner
+        cols = []
+        for item in self._recipe:
+            if item[0] == "copy":
+                cols.append(inner[:, item[1]])
+            elif item[0] == "var":
+                cols.append(inner[:, item[2]] - inner[:, item[1]] ** 2)
+            else:
+                _, idx, lam, shots = item
+                p = inner[:, idx].detach().clamp(min=0).to(torch.float64)
+                draws = torch.multinomial(p / p.sum(1, keepdim=True), shots, replacement=True)
+                cols.append(torch.as_tensor(lam, dtype=inner.dtype, device=inner.device)[draws])
+        shapes = {tuple(c.shape[1:]) for c in cols}
+        if len(shapes) != 1:
+            raise ValueError("You can not have multiple measurements with different shapes!!")
+        return torch.stack(cols, 1)
 
     def batched(self, *params, in_dims=None):
         """Evaluate a batch of parameter sets at once -> [B, n_meas, ...].
@@ -582,6 +676,9 @@ class B200Backend:
 
     def execute_host(self, params: np.ndarray, grad_out: Optional[np.ndarray] = None):
         """HOST numpy [B, P] -> (out [B, n_meas, ...], grad [B, P] or None); copies are inside the call."""
+        if self._recipe is not None:
+            raise NotImplementedError("execute_host serves expval / probs / state measurements; call the backend "
+                                      "with CUDA tensors for var / sample")
         out, grad = self.plan().execute_host(params, grad_out)
         B = out.shape[0]
         nm = len(self._ir.meas)
@@ -636,7 +733,7 @@ class B200Backend:
     interface = property(lambda self: self._interface)
     diff_method = property(lambda self: self._diff_method)
     backend = property(lambda self: self._backend)
-    measurements = property(lambda self: self._measurements)
+    measurements = property(lambda self: self._user_measurements)
     calculation_mode = property(lambda self: self._calculation_mode)
     device = property(lambda self: self._device)
 

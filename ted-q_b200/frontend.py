@@ -36,8 +36,8 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 __all__ = [
-    "Circuit", "expval", "probs", "state", "InitStateVector", "MeasurementReturnTypes",
-    "Expectation", "Probability", "State", "GATE_NAMES", "HardwareEfficient",
+    "Circuit", "expval", "probs", "state", "var", "sample", "InitStateVector", "MeasurementReturnTypes",
+    "Expectation", "Probability", "State", "Variance", "Sample", "GATE_NAMES", "HardwareEfficient", "Unitary",
 ]
 
 
@@ -54,6 +54,8 @@ class MeasurementReturnTypes(enum.Enum):
 Expectation = MeasurementReturnTypes.Expectation
 Probability = MeasurementReturnTypes.Probability
 State = MeasurementReturnTypes.State
+Variance = MeasurementReturnTypes.Variance
+Sample = MeasurementReturnTypes.Sample
 
 _ids = itertools.count()
 _trace_stack: List[list] = []
@@ -144,8 +146,8 @@ class Operator:
     is_observable = False
 
     def __init__(self, name, params, qubits, do_queue=True, trainable_params=None, is_preparation=False,
-                 matrix=None):
-        nq, npar, fn, obs = _GATES[name] if name in _GATES else (len(qubits), 0, None, False)
+                 matrix=None, is_observable=None):
+        nq, npar, fn, obs = _GATES[name] if name in _GATES else (len(qubits), 0, None, bool(is_observable))
         if len(params) != npar:
             raise ValueError(f"{name}: # of parameters is not matched! expected {npar}parameters, but got {len(params)}.")
         if name in _GATES and len(qubits) != nq:
@@ -184,6 +186,15 @@ for _n in _GATES:
     __all__.append(_n)
 
 
+def Unitary(matrix, qubits, do_queue=True, **kwargs):
+    """User-defined gate / observable from its matrix (qubit.py:1696-1730; the reference's own constructor stops at
+    an undefined name, :1719).  ``matrix``: (2^k, 2^k) or [2]*2k, first qubit = most significant bit.  As a gate
+    k <= 3, as an observable (``expval`` / ``var`` / ``sample``) k <= 4 and the matrix must be Hermitian."""
+    k = len(qubits)
+    m = np.asarray(matrix, dtype=complex).reshape(2 ** k, 2 ** k)
+    return Operator("Unitary", (), qubits, do_queue=do_queue, matrix=m, is_observable=True)
+
+
 def InitStateVector(matrix, do_queue=True):
     """User-defined initial state (prepared_state.py: IintStateVector)."""
     return Operator("InitStateVector", (), [], do_queue=do_queue, is_preparation=True, matrix=np.asarray(matrix))
@@ -217,6 +228,28 @@ def expval(observable, do_queue=True):
         if not getattr(ob, "is_observable", False):
             raise ValueError(f"{getattr(ob, 'name', ob)} is not a subclass of ObservableBase: cannot be used with expval")
     return QuantumMeasurement(Expectation, obs=observable, do_queue=do_queue)
+
+
+def _check_observables(observable, what):
+    for ob in observable if isinstance(observable, list) else [observable]:
+        if not getattr(ob, "is_observable", False):
+            raise ValueError(f"{getattr(ob, 'name', ob)} is not a subclass of ObservableBase: cannot be used with {what}")
+
+
+def var(observable, do_queue=True):
+    """Variance <O^2> - <O>^2 of an observable (or a product of single-qubit observables given as a list).  The
+    reference declares it and raises NotImplementedError (measurement.py:158-163)."""
+    _check_observables(observable, "var")
+    return QuantumMeasurement(Variance, obs=observable, do_queue=do_queue)
+
+
+def sample(observable, num_shots, do_queue=True):
+    """``num_shots`` eigenvalue samples of an observable on at most 4 qubits, drawn on the device from the exact
+    outcome distribution (reference: declared, NotImplementedError, measurement.py:166-171).  Not differentiable."""
+    _check_observables(observable, "sample")
+    ms = QuantumMeasurement(Sample, obs=observable, do_queue=do_queue)
+    ms.num_shots = int(num_shots)
+    return ms
 
 
 def probs(qubits=None, do_queue=True, after_state=False):

@@ -311,3 +311,87 @@ def test_c4_depth20_matches_reference_fixture():
     out, grad = run_engine(case)
     assert_close(out, golden_out(case), TOL["c128"], "c4d20 out")
     assert_close(grad, np.asarray(case["grad"]), TOL["c128"], "c4d20 grad")
+
+
+def _state_and_ops(circuit_def, n, params):
+    """Oracle state of a traced circuit (torch, differentiable) for observables the oracle itself does not know."""
+    from oracle import sv_ref
+
+    circ = qb.Circuit(circuit_def, n, *params)
+    flat = torch.cat([p.reshape(-1) for p in params]).detach().cpu().double().requires_grad_(True)
+    psi = sv_ref.run_sv(circ, flat, torch.complex128, return_state=True).reshape(-1)
+    return circ, flat, psi
+
+
+def test_var_sample_and_user_unitary():
+    """f4: ``var`` and ``sample`` (declared, NotImplemented in the reference: measurement.py:158-171) and the
+    user-defined ``Unitary`` gate / Hermitian observable (qubit.py:1696-1730, broken at :1719).  var = <O^2> - <O>^2
+    with gradients, against the oracle's state; samples are eigenvalues whose mean converges to <O>."""
+    rng = np.random.RandomState(5)
+    h = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    herm = (h + h.conj().T) / 2                     # 2-qubit Hermitian observable
+    ang = 0.37
+    u1 = np.array([[np.cos(ang / 2), -1j * np.sin(ang / 2)], [-1j * np.sin(ang / 2), np.cos(ang / 2)]])   # = RX(0.37)
+
+    def body(a, b, c):
+        qb.RY(a, qubits=[0]); qb.RX(b, qubits=[1]); qb.CNOT(qubits=[0, 1]); qb.CRZ(c, qubits=[1, 2])
+        qb.Unitary(u1, qubits=[2]); qb.Hadamard(qubits=[0])
+
+    def with_var(a, b, c):
+        body(a, b, c)
+        return [qb.var(qb.PauliZ(qubits=[0])), qb.var(qb.Unitary(herm, qubits=[1, 2])),
+                qb.expval(qb.PauliX(qubits=[1])), qb.var([qb.PauliZ(qubits=[0]), qb.PauliX(qubits=[2])])]
+
+    params = [torch.tensor([v], dtype=torch.float64, device="cuda", requires_grad=True) for v in (0.54, -0.8, 1.3)]
+    for kw in ({}, {"tn_mode": True, "tn_simplify": False, "hyper_opt": {"max_repeats": 2, "tn_backward": "tree"}}):
+        for p in params:
+            p.grad = None
+        cc = qb.Circuit(with_var, 3, *params).compilecircuit(backend="pytorch_b200", dtype=torch.complex128, **kw)
+        out = cc(*params)
+        assert out.shape == (4,) and len(cc.measurements) == 4
+        w = torch.tensor([0.3, -1.1, 0.7, 0.5], dtype=torch.float64, device="cuda")
+        (out * w).sum().backward()
+        # oracle: the same circuit with RX(0.37) in place of the user unitary, observables applied in numpy / torch
+        def ref_def(a, b, c):
+            qb.RY(a, qubits=[0]); qb.RX(b, qubits=[1]); qb.CNOT(qubits=[0, 1]); qb.CRZ(c, qubits=[1, 2])
+            qb.RX(torch.tensor(ang), qubits=[2], trainable_params=[]); qb.Hadamard(qubits=[0])
+            return qb.state()
+        _, flat, psi = _state_and_ops(ref_def, 3, [p.detach().cpu() for p in params])
+        Z, X, I2 = np.diag([1.0, -1.0]), np.array([[0, 1.0], [1.0, 0]]), np.eye(2)
+        ops = [np.kron(np.kron(Z, I2), I2), np.kron(I2, herm), np.kron(np.kron(I2, X), I2), np.kron(np.kron(Z, I2), X)]
+        vals = []
+        for j, O in enumerate(ops):
+            Ot = torch.tensor(O, dtype=torch.complex128)
+            e1 = torch.real(torch.vdot(psi, Ot @ psi))
+            e2 = torch.real(torch.vdot(psi, Ot @ (Ot @ psi)))
+            vals.append(e1 if j == 2 else e2 - e1 ** 2)
+        ref = torch.stack(vals)
+        (ref * w.cpu()).sum().backward()
+        assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), 1e-11, "var")
+        got_g = np.array([float(p.grad) for p in params])
+        assert_close(got_g, flat.grad.numpy(), 1e-10, "var grad")
+
+    def with_sample(a, b, c):
+        body(a, b, c)
+        return [qb.sample(qb.PauliZ(qubits=[1]), 20000), qb.sample(qb.Unitary(herm, qubits=[0, 2]), 20000)]
+
+    def with_expval(a, b, c):
+        body(a, b, c)
+        return [qb.expval(qb.PauliZ(qubits=[1])), qb.expval(qb.Unitary(herm, qubits=[0, 2]))]
+
+    torch.manual_seed(0)
+    p32 = [p.detach().float() for p in params]
+    smp = qb.Circuit(with_sample, 3, *p32).compilecircuit(backend="pytorch_b200")(*p32)
+    exp = qb.Circuit(with_expval, 3, *p32).compilecircuit(backend="pytorch_b200")(*p32).cpu().numpy()
+    assert smp.shape == (2, 20000) and not smp.requires_grad
+    lam = np.linalg.eigvalsh(herm)
+    s = smp.cpu().numpy()
+    assert set(np.unique(s[0])) <= {-1.0, 1.0}
+    assert all(np.abs(lam - v).min() < 1e-5 for v in np.unique(s[1]))
+    for j, spread in ((0, 1.0), (1, float(lam.max() - lam.min()))):
+        assert abs(s[j].mean() - exp[j]) < 5 * spread / np.sqrt(20000), (j, s[j].mean(), exp[j])
+    with pytest.raises(ValueError):      # measurements of different shapes cannot be stacked (pytorch_backend.py:385-389)
+        def mixed(a, b, c):
+            body(a, b, c)
+            return [qb.sample(qb.PauliZ(qubits=[1]), 10), qb.expval(qb.PauliZ(qubits=[0]))]
+        qb.Circuit(mixed, 3, *p32).compilecircuit(backend="pytorch_b200")(*p32)
