@@ -5,7 +5,7 @@
 
 Headline (default) = BASELINE.json configs[4], the north-star workload and the only one with a collective on its data
 path: single amplitudes <b|U|0> of a 40-qubit random circuit (5x8 lattice, 12 cycles) by SLICED tensor-network
-contraction.  A *step* is one pass of the hot path over one batch of synthetic input: AMPS (16) random bitstrings b;
+contraction.  A *step* is one pass of the hot path over one batch of synthetic input: AMPS (24) random bitstrings b;
 an *evaluation* is one amplitude.  STRONG scaling: the 64 slices of every amplitude are sharded over the ranks
 (contiguous ranges of slice groups), the partial sums of the whole batch are combined with ONE NCCL all-reduce per
 step, inside the timed region.  `value` = amplitudes/s, device-timed (CUDA events on the launching stream, max
@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-AMPS = int(os.environ.get("TQ_C5_AMPS", "16"))     # bitstrings per step of the headline
+AMPS = int(os.environ.get("TQ_C5_AMPS", "24"))     # bitstrings per step of the headline
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -764,16 +764,17 @@ def measure_c5(steps, warmup, device, dist, do_cpu=False, greedy_plan=False, n_a
             tc_gemm_ms += r["ms"] - r["pack_ms"]
     flops_amp = 2.0 ** info.flops_log2 * info.n_slices
     ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
-    traffic = None
+    traffic = traffic_detail = None      # dram__bytes_read + write of the longest GEMM launch, from one ncu --set full
     try:
         with open(os.path.join(ROOT, "profiles", "r02_c5_traffic.json")) as fh:
-            traffic = json.load(fh)
+            traffic_detail = json.load(fh)
+        traffic = traffic_detail["dram_bytes_per_launch"]
     except Exception:
         pass
     res["roofline"] = {
         "bound": "tensor", "kernel": "k_tc_gemm (+ k_tc_pack) on the tensor-bound steps of a slice group",
         "unit": "TFLOP/s", "achieved": ach, "peak": peak_cgemm, "frac": ach / peak_cgemm if tc_ms else None,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_detail": traffic_detail,
         "peak_kind": f"complex-GEMM tensor-core roofline = TF32 peak / 3; TF32 peak {pk['tf32']:.1f} TFLOP/s "
                      f"{pk['tc_kind']}; sustained {pk['tf32_sustained']:.1f}",
         "frac_of_sustained_peak": ach / (pk["tf32_sustained"] / 3.0) if tc_ms else None,

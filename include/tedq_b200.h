@@ -270,6 +270,10 @@ int32_t tq_tn_plan_step_kernel(const tq_tn_plan* plan, int32_t s);
 /* fused pack: the step whose operand image step s writes from its own epilogue, -1 when s stores a plain tensor
  * (a split-K launch of s still falls back to plain + pack at run time) */
 int32_t tq_tn_plan_step_fuse_to(const tq_tn_plan* plan, int32_t s);
+/* how the epilogue of a fused-pack producer reaches whole 64-byte image rows (0: not fused): 1 = the consumer's three
+ * low k bits are accumulator ROW bits of the producer (8 lanes x 8 bytes), 2 = the lowest k bit is a column bit and the
+ * next two are row bits (4 lanes x 16 bytes), 3 = all three are column bits (one thread, 16-byte stores) */
+int32_t tq_tn_plan_step_fuse_mode(const tq_tn_plan* plan, int32_t s);
 /* bit 0: step s repeats for every slice (it depends on a sliced index); bit 1: it carries the parameter-set
  * batch dimension.  Steps with neither bit run once per call, outside the slice loop. */
 int32_t tq_tn_plan_step_flags(const tq_tn_plan* plan, int32_t s);

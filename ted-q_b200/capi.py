@@ -163,6 +163,8 @@ def lib() -> C.CDLL:
     L.tq_tn_plan_step_kernel.restype = i32
     L.tq_tn_plan_step_fuse_to.argtypes = [vp, i32]
     L.tq_tn_plan_step_fuse_to.restype = i32
+    L.tq_tn_plan_step_fuse_mode.argtypes = [vp, i32]
+    L.tq_tn_plan_step_fuse_mode.restype = i32
     L.tq_tn_plan_step_flags.argtypes = [vp, i32]
     L.tq_tn_plan_step_flags.restype = i32
     L.tq_tn_profile.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, vp, sz, vp, C.POINTER(C.c_float)]
@@ -469,6 +471,9 @@ class TnPlan:
     def step_fuse_to(self, s):
         """Step whose operand image step s writes from its epilogue (fused pack), -1: plain result."""
         return int(lib().tq_tn_plan_step_fuse_to(self.handle, s))
+
+    def step_fuse_mode(self, s):
+        return int(lib().tq_tn_plan_step_fuse_mode(self.handle, s))
 
     def step_flags(self, s):
         """bit 0: repeats per slice, bit 1: batched over parameter sets."""

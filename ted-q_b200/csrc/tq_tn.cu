@@ -784,6 +784,8 @@ struct TcStep {
   // fused pack: this step's epilogue writes operand image `fuse_is_b ? B : A` of step fuse_to (its only consumer);
   // src_a / src_b: the step that writes this step's A / B image that way (-1: packed from the plain tensor)
   int fuse_to = -1, src_a = -1, src_b = -1;
+  int fuse_mode = 0;  // 1: the image's low k bits are accumulator ROW bits (8-byte stores, 8 lanes per 64-byte piece),
+                      // 2: lowest k bit a column bit, the next two row bits (16-byte stores), 3: all three column bits
   bool fuse_is_b = false;
   // index orders of this step's GEMM: position t of the accumulator rows / columns / contracted extent is default
   // position ord_*[t] (default = the lowering's order).  A step that stores a plain result keeps its row / column
@@ -1125,6 +1127,7 @@ static int build_schedule(tq_tn_plan* p) {
         }
         std::vector<int> kk;       // the three low k bits of d's images
         std::vector<int> c_rows_first, c_cols_first;
+        int mode = kr.size() >= 3 ? 1 : (kr.size() == 2 && !kc.empty()) ? 2 : 3;
         if (kr.size() >= 3) {
           kk = {kr[0], kr[1], kr[2]};
           for (int j : kk) c_rows_first.push_back(prow[bits_t[j]]);
@@ -1149,6 +1152,7 @@ static int build_schedule(tq_tn_plan* p) {
         front(Tc.ord_row, c_rows_first);
         front(Tc.ord_col, c_cols_first);
         Tc.fuse_to = d;
+        Tc.fuse_mode = mode;
         Tc.fuse_is_b = is_b;
         Tc.out_entries = (img_z << sd.n_b) / 8;
         (is_b ? Td.src_b : Td.src_a) = c;
@@ -1750,6 +1754,13 @@ int32_t tq_tn_plan_step_kernel(const tq_tn_plan* p, int32_t s) {
 int32_t tq_tn_plan_step_fuse_to(const tq_tn_plan* p, int32_t s) {
   if (!p || s < 0 || s >= (int)p->steps.size() || !p->tc_fuse_pack || p->kind[s] != 2) return -1;
   return p->tc[s].fuse_to;
+}
+
+/* store mode of a fused-pack producer (0: none): 1 = the consumer's low k bits are accumulator row bits, 2 = lowest k
+ * bit a column bit + two row bits, 3 = three column bits */
+int32_t tq_tn_plan_step_fuse_mode(const tq_tn_plan* p, int32_t s) {
+  if (tq_tn_plan_step_fuse_to(p, s) < 0) return 0;
+  return p->tc[s].fuse_mode;
 }
 
 int32_t tq_tn_plan_num_steps(const tq_tn_plan* p) { return p ? (int32_t)p->steps.size() : -1; }
