@@ -258,14 +258,19 @@ size_t tq_tn_workspace_bytes(const tq_tn_plan* plan, int64_t batch);
  *   TQ_TN_OPT_TC_FUSE_PACK (default 1): a tensor-core step whose result is read by exactly one step, itself a
  *     tensor-core step, writes that step's operand image (hi / lo TF32 planes, permuted, swizzled) straight from its
  *     epilogue: the intermediate is never stored in its plain layout, the consumer runs no pack pass.  0 = every
- *     tensor-core step packs its operands from plain tensors (bit-identical results; parity tests compare both). */
+ *     tensor-core step packs its operands from plain tensors (bit-identical results; parity tests compare both).
+ *   TQ_TN_OPT_CHAIN (default 1): runs of consecutive gate-like apply steps on the same large tensor (each contracts
+ *     k <= 4 of its indices with a small operand and puts k new ones in their place: every step of a
+ *     state-vector-like plan) execute as ONE launch of k_tn_chain — a shared-memory tile per CTA, the tensors between
+ *     the steps are never materialised.  0 = one k_tn_apply launch per step. */
 enum tq_tn_option { TQ_TN_OPT_TENSOR_CORE = 0, TQ_TN_OPT_TC_MIN_LOG2 = 1, TQ_TN_OPT_TC_CHUNK = 2,
                     TQ_TN_OPT_FUSE_SMALL = 3, TQ_TN_OPT_TC_SPLITK = 4, TQ_TN_OPT_TC_GATHER = 5,
-                    TQ_TN_OPT_TC_FUSE_PACK = 6 };
+                    TQ_TN_OPT_TC_FUSE_PACK = 6, TQ_TN_OPT_CHAIN = 7 };
 int tq_tn_plan_set_option(tq_tn_plan* plan, int32_t option, int32_t value);
 /* kernel that runs step s: 0 = one thread per output element, 1 = tiled fp32 FMA GEMM,
  * 2 = tcgen05 split-TF32 GEMM over packed operand images, 3 = split-K reduction (<= 64 outputs, K >= 4096),
- * 4 = member of a fused run of small steps, 5 = apply kernel (one gate-sized operand, one large operand) */
+ * 4 = member of a fused run of small steps, 5 = apply kernel (one gate-sized operand, one large operand),
+ * 6 = gradient seed, 7 = member of an apply-chain run (k_tn_chain) */
 int32_t tq_tn_plan_step_kernel(const tq_tn_plan* plan, int32_t s);
 /* fused pack: the step whose operand image step s writes from its own epilogue, -1 when s stores a plain tensor
  * (a split-K launch of s still falls back to plain + pack at run time) */

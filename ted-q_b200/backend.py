@@ -593,7 +593,7 @@ class B200Backend:
     def _combine(self, inner: torch.Tensor) -> torch.Tensor:
         """Engine results [B, n_inner] -> the user's measurements [B, n_meas, ...] (identity without var / sample):
         var = <O^2> - <O>^2 (differentiable); sample = eigenvalues drawn from the exact outcome distribution."""
-        if self._recipe is None:
+        if getattr(self, "_recipe", None) is None:
             return inner
         cols = []
         for item in self._recipe:
@@ -676,7 +676,7 @@ class B200Backend:
 
     def execute_host(self, params: np.ndarray, grad_out: Optional[np.ndarray] = None):
         """HOST numpy [B, P] -> (out [B, n_meas, ...], grad [B, P] or None); copies are inside the call."""
-        if self._recipe is not None:
+        if getattr(self, "_recipe", None) is not None:
             raise NotImplementedError("execute_host serves expval / probs / state measurements; call the backend "
                                       "with CUDA tensors for var / sample")
         out, grad = self.plan().execute_host(params, grad_out)

@@ -42,6 +42,7 @@ TN_MAX_RANK = 32
 TN_OPT_TENSOR_CORE, TN_OPT_TC_MIN_LOG2, TN_OPT_TC_CHUNK, TN_OPT_FUSE_SMALL, TN_OPT_TC_SPLITK = 0, 1, 2, 3, 4
 TN_OPT_TC_GATHER = 5
 TN_OPT_TC_FUSE_PACK = 6
+TN_OPT_CHAIN = 7
 
 
 class TnStep(C.Structure):

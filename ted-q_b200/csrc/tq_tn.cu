@@ -529,6 +529,114 @@ k_tn_fused(const FusedStep* __restrict__ steps, const int32_t* __restrict__ leve
   }
 }
 
+// ---------------------------------------------------------------------------
+// Apply-chain sweep: a RUN of consecutive gate-like apply steps on the same large tensor (every step contracts k <= 4
+// indices of it with a small operand and puts k new ones in their place — the shape of every step of a
+// state-vector-like plan) in ONE launch.  A CTA owns a tile of 2^L elements of one parameter set: the L "local"
+// indices are those the run's steps touch (plus the lowest bits of the layout, for coalescing); the other indices
+// of the tensor pass through untouched and only number the tiles.  The tile is read once from the first step's
+// operand, every step is applied in shared memory (a new index takes the bit position of the one it replaces: no
+// data movement), and the tile is written once in the LAST step's result layout.  The tensors between the steps of
+// the run are never materialised: 2 passes over the tensor per run instead of 2 per step.
+// ---------------------------------------------------------------------------
+constexpr int CHAIN_MAX_K = 4, CHAIN_MAX_B = 2, CHAIN_MAX_LOCAL = 13, CHAIN_GATE_ENTRIES = 4096;
+struct alignas(16) ChainStep {
+  int64_t off;                 // element offset of the small operand inside its space
+  int32_t in;                  // >= 0: input tensor id, -1: shared arena, -2: per-set arena
+  int32_t g_begin;             // first entry of its staged gate G[bv][s][k] in shared memory
+  int8_t n_k, n_b, pad0, pad1;
+  int8_t tpos[CHAIN_MAX_K];    // tile bit of contracted index j = tile bit of the new index j (ascending in j? no: any)
+  int8_t tsort[CHAIN_MAX_K];   // tpos sorted ascending (zero-bit insertion order)
+  int8_t bpos[CHAIN_MAX_B];    // kept-shared index j: tile bit (>= 0) or -1 - (tile-number bit) when it is not local
+  int8_t gk[CHAIN_MAX_K], gs[CHAIN_MAX_K], gb[CHAIN_MAX_B];  // bit of k_j / new_j / b_j inside the small operand
+  int8_t sl_ord[4], sl_bit[4]; // sliced bits of an input operand (-1: none)
+};
+struct ChainHdr {
+  int32_t L, n_glob, n_steps, gate_entries;
+  int8_t in_loc[CHAIN_MAX_LOCAL], out_loc[CHAIN_MAX_LOCAL];  // physical bit of tile bit j in the first operand / last result
+  int8_t in_glob[TQ_TN_MAX_RANK], out_glob[TQ_TN_MAX_RANK];  // physical bit of tile-number bit j
+};
+
+template <typename R, int K>
+__device__ __forceinline__ void chain_apply(cx<R>* tile, const cx<R>* G, const ChainStep& c, int L, uint32_t tile_id) {
+  constexpr int D = 1 << K;
+  const uint32_t groups = 1u << (L - K);
+  uint32_t toff[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int t = 0; t < K; ++t) o |= ((j >> t) & 1u) << c.tpos[t];
+    toff[j] = o;
+  }
+  for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
+    uint32_t base = g;
+#pragma unroll
+    for (int t = 0; t < K; ++t) base = insert_zero_bit(base, c.tsort[t]);
+    uint32_t bv = 0;
+    for (int j = 0; j < c.n_b; ++j) {
+      const int bp = c.bpos[j];
+      bv |= (bp >= 0 ? (base >> bp) & 1u : (tile_id >> (-1 - bp)) & 1u) << j;
+    }
+    const cx<R>* Gb = G + ((size_t)bv << (2 * K));
+    cx<R> v[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) v[j] = tile[base | toff[j]];
+#pragma unroll
+    for (int sv = 0; sv < D; ++sv) {
+      cx<R> acc = cmul(Gb[sv * D], v[0]);
+#pragma unroll
+      for (int j = 1; j < D; ++j) acc = cfma(Gb[sv * D + j], v[j], acc);
+      tile[base | toff[sv]] = acc;
+    }
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_tn_chain(const __grid_constant__ ChainHdr h, const ChainStep* __restrict__ steps, const InputRef* __restrict__ inputs,
+           cx<R>* shared, cx<R>* perset_base, int64_t set_stride, int64_t slice, const cx<R>* __restrict__ src,
+           int64_t src_stride, cx<R>* __restrict__ dst, int64_t dst_stride) {
+  extern __shared__ __align__(16) unsigned char chain_smem[];
+  cx<R>* tile = reinterpret_cast<cx<R>*>(chain_smem);
+  cx<R>* gates = tile + ((size_t)1 << h.L);
+  const int64_t set = blockIdx.y;
+  const uint32_t tile_id = blockIdx.x;
+  cx<R>* perset = perset_base + set * set_stride;
+  const uint32_t n_tile = 1u << h.L;
+  uint32_t in_base = 0, out_base = 0;
+  for (int j = 0; j < h.n_glob; ++j) {
+    in_base |= ((tile_id >> j) & 1u) << h.in_glob[j];
+    out_base |= ((tile_id >> j) & 1u) << h.out_glob[j];
+  }
+  const cx<R>* sp = src + set * src_stride + in_base;
+  for (uint32_t l = threadIdx.x; l < n_tile; l += blockDim.x) tile[l] = sp[scat(l, h.in_loc, h.L)];
+  // stage every gate of the run: G[bv][new][old], entry e of step i at gates[g_begin + e]
+  for (int i = 0; i < h.n_steps; ++i) {
+    const ChainStep& c = steps[i];
+    const cx<R>* g = fused_operand<R>(inputs, shared, perset, set, slice, c.in, c.off, c.sl_ord, c.sl_bit);
+    const int n = 1 << (2 * c.n_k + c.n_b);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const uint32_t kk = e & ((1u << c.n_k) - 1u), sv = (e >> c.n_k) & ((1u << c.n_k) - 1u), bv = e >> (2 * c.n_k);
+      gates[c.g_begin + e] = g[scat(kk, c.gk, c.n_k) | scat(sv, c.gs, c.n_k) | scat(bv, c.gb, c.n_b)];
+    }
+  }
+  __syncthreads();
+  for (int i = 0; i < h.n_steps; ++i) {
+    const ChainStep c = steps[i];
+    const cx<R>* G = gates + c.g_begin;
+    switch (c.n_k) {
+      case 1: chain_apply<R, 1>(tile, G, c, h.L, tile_id); break;
+      case 2: chain_apply<R, 2>(tile, G, c, h.L, tile_id); break;
+      case 3: chain_apply<R, 3>(tile, G, c, h.L, tile_id); break;
+      default: chain_apply<R, 4>(tile, G, c, h.L, tile_id); break;
+    }
+    __syncthreads();
+  }
+  cx<R>* dp = dst + set * dst_stride + out_base;
+  for (uint32_t l = threadIdx.x; l < n_tile; l += blockDim.x) dp[scat(l, h.out_loc, h.L)] = tile[l];
+}
+
 // Tiled complex GEMM with the permutation folded into the gathers: a CTA owns a 64 x 64 tile of
 // C[m, n] for one kept-shared index value and one parameter set; A and B tiles are gathered through
 // per-CTA offset tables into shared memory (K tile = 16), each thread accumulates a 4 x 4 block.
@@ -767,6 +875,15 @@ struct SchedItem {
                                        // fs_begin), then n_levels cta-step counts
   bool batched = false;
   std::vector<int> members;            // steps of the run, in execution order
+  int chain = -1;                      // >= 0: an apply-chain run (k_tn_chain) = chains[chain]; members = its steps
+};
+
+struct ChainRun {
+  ChainHdr hdr;
+  int step_begin = 0;   // first entry of its ChainStep table inside d_chain_steps
+  int big_in = -1;      // tensor id of the first step's large operand
+  int last = -1;        // last step of the run (its result is what the launch writes)
+  int rank = 0;         // rank of the large tensor
 };
 
 // Tensor-core lowering of one step: which operand provides accumulator rows, image geometry, pack tables.
@@ -870,6 +987,9 @@ struct tq_tn_plan {
   int tc_splitk = 1;       // TQ_TN_OPT_TC_SPLITK
   int tc_gather = 0;       // TQ_TN_OPT_TC_GATHER
   int tc_fuse_pack = 1;    // TQ_TN_OPT_TC_FUSE_PACK
+  int chain_enabled = 1;   // TQ_TN_OPT_CHAIN
+  std::vector<ChainRun> chains;
+  ChainStep* d_chain_steps = nullptr;
   int num_sms = 148;
 };
 
@@ -1202,6 +1322,164 @@ static int build_schedule(tq_tn_plan* p) {
   std::vector<FusedStep> fsteps;
   std::vector<int32_t> levels;
   std::vector<uint32_t> microtab;
+  // ---- apply-chain runs (k_tn_chain): consecutive gate-like apply steps on the same large tensor
+  p->chains.clear();
+  std::vector<ChainStep> chain_steps;
+  std::vector<int> chain_small;  // small operand (tensor id) of every chain step: arena offsets are filled in later
+  std::vector<int> consumer_of(n_in + n_steps, -1), n_consumers(n_in + n_steps, 0);
+  for (int s = 0; s < n_steps; ++s) {
+    for (int t : {p->steps[s].lhs, p->steps[s].rhs}) {
+      consumer_of[t] = s;
+      n_consumers[t] += 1;
+    }
+  }
+  auto gate_like = [&](int s) {
+    if (p->kind[s] != 5 || s == p->seed_step) return false;
+    const ApplyDev& a = p->apply[s];
+    return a.n_k >= 1 && a.n_k <= CHAIN_MAX_K && a.n_s == a.n_k && a.n_b <= CHAIN_MAX_B;
+  };
+  auto big_of = [&](int s) { return p->apply_small_rhs[s] ? p->steps[s].lhs : p->steps[s].rhs; };
+  auto small_of = [&](int s) { return p->apply_small_rhs[s] ? p->steps[s].rhs : p->steps[s].lhs; };
+  auto build_chain = [&](int s0, SchedItem& it) -> bool {
+    if (!gate_like(s0)) return false;
+    const int big0 = big_of(s0);
+    const std::vector<int>& lay0 = p->layout[big0];
+    const int r = (int)lay0.size();
+    for (int x : lay0)
+      if (x < 0) return false;  // an input with sliced bits: leave it to the apply kernel
+    // candidate run: follow the single consumer while it is a gate-like apply on the result
+    std::vector<int> cand{s0};
+    for (int cur = s0; (int)cand.size() < 2048;) {
+      const int t = n_in + cur;
+      if (n_consumers[t] != 1) break;
+      const int c = consumer_of[t];
+      if (c < 0 || !gate_like(c) || big_of(c) != t || p->phase[c] != p->phase[s0] ||
+          p->dep_batch[c] != p->dep_batch[s0] || p->dep_slice[c] != p->dep_slice[s0])
+        break;
+      const int sm = small_of(c);
+      if (!done[sm] || (sm < n_in && in_slice_bits[sm] > 4)) break;
+      cand.push_back(c);
+      cur = c;
+    }
+    {
+      const int sm0 = small_of(s0);
+      if (sm0 < n_in && in_slice_bits[sm0] > 4) return false;
+    }
+    if (cand.size() < 2) return false;
+    const int Lmax = p->dtype == TQ_C64 ? CHAIN_MAX_LOCAL : CHAIN_MAX_LOCAL - 1;
+    const int L = std::min(Lmax, r);
+    const int gate_cap = (32 * 1024) / (p->dtype == TQ_C64 ? 8 : 16);
+    // local set: the indices the run contracts (as long as they fit), then the lowest bits of the layout
+    std::set<int> original(lay0.begin(), lay0.end()), local;
+    for (int b = 0; b < std::min(3, r) && (int)local.size() < L; ++b) local.insert(lay0[b]);
+    int n_take = 0, gate_total = 0;
+    {
+      int big = big0;
+      std::set<int> created;
+      for (int s : cand) {
+        const tq_tn_step& st = p->steps[s];
+        const ApplyDev& a = p->apply[s];
+        const int8_t* bb = p->apply_small_rhs[s] ? st.lhs_bits : st.rhs_bits;
+        std::vector<int> need;
+        for (int j = 0; j < a.n_k; ++j) {
+          const int x = p->layout[big][bb[j]];
+          if (original.count(x) && !created.count(x) && !local.count(x) &&
+              std::find(need.begin(), need.end(), x) == need.end())
+            need.push_back(x);
+        }
+        const int entries = 1 << (2 * a.n_k + a.n_b);
+        if ((int)(local.size() + need.size()) > L || gate_total + entries > gate_cap) break;
+        for (int x : need) local.insert(x);
+        const int8_t* sb = p->apply_small_rhs[s] ? st.rhs_bits : st.lhs_bits;
+        const int sm = small_of(s);
+        for (int j = 0; j < a.n_k; ++j) created.insert(p->layout[sm][sb[a.n_k + j]]);
+        gate_total += entries;
+        big = n_in + s;
+        ++n_take;
+      }
+    }
+    if (n_take < 2) return false;
+    for (int b = 0; b < r && (int)local.size() < L; ++b) local.insert(lay0[b]);
+    ChainRun run;
+    memset(&run.hdr, 0, sizeof(run.hdr));
+    run.hdr.L = L;
+    run.hdr.n_glob = r - L;
+    run.hdr.n_steps = n_take;
+    run.hdr.gate_entries = gate_total;
+    run.step_begin = (int)chain_steps.size();
+    run.big_in = big0;
+    run.rank = r;
+    std::map<int, int> pos, glob;        // index id -> tile bit / tile-number bit
+    std::vector<int> at(L, -1);          // tile bit -> index id it holds now
+    for (int b = 0, jl = 0, jg = 0; b < r; ++b) {
+      const int x = lay0[b];
+      if (local.count(x)) {
+        pos[x] = jl;
+        at[jl] = x;
+        run.hdr.in_loc[jl++] = (int8_t)b;
+      } else {
+        glob[x] = jg;
+        run.hdr.in_glob[jg++] = (int8_t)b;
+      }
+    }
+    int big = big0, g_begin = 0;
+    for (int i = 0; i < n_take; ++i) {
+      const int s = cand[i];
+      const tq_tn_step& st = p->steps[s];
+      const ApplyDev& a = p->apply[s];
+      const bool srhs = p->apply_small_rhs[s] != 0;
+      const int8_t* bb = srhs ? st.lhs_bits : st.rhs_bits;   // large operand: [k..., free..., b...]
+      const int8_t* sb = srhs ? st.rhs_bits : st.lhs_bits;   // small operand: [k..., new..., b...]
+      const int sm = small_of(s);
+      ChainStep c;
+      memset(&c, 0, sizeof(c));
+      c.n_k = (int8_t)a.n_k;
+      c.n_b = (int8_t)a.n_b;
+      c.g_begin = g_begin;
+      g_begin += 1 << (2 * a.n_k + a.n_b);
+      c.in = sm < n_in ? sm : (p->arena_const[sm - n_in] ? -1 : -2);
+      c.off = -1;  // arena offsets are filled in once the layout is known (below: small_tensor)
+      for (int j = 0; j < a.n_k; ++j) {
+        const int x = p->layout[big][bb[j]];
+        const int tp = pos.at(x);
+        c.tpos[j] = (int8_t)tp;
+        c.gk[j] = sb[j];
+        c.gs[j] = sb[a.n_k + j];
+        const int nx = p->layout[sm][sb[a.n_k + j]];
+        pos.erase(x);
+        pos[nx] = tp;
+        at[tp] = nx;
+      }
+      for (int j = 0; j < a.n_k; ++j) c.tsort[j] = c.tpos[j];
+      std::sort(c.tsort, c.tsort + a.n_k);
+      const int n_f = a.n_f;
+      for (int j = 0; j < a.n_b; ++j) {
+        const int x = p->layout[big][bb[a.n_k + n_f + j]];
+        c.bpos[j] = pos.count(x) ? (int8_t)pos[x] : (int8_t)(-1 - glob.at(x));
+        c.gb[j] = sb[2 * a.n_k + j];
+      }
+      for (int j = 0; j < 4; ++j) c.sl_ord[j] = c.sl_bit[j] = -1;
+      int ns = 0;
+      for (size_t e = 0; e < p->slice_tensor.size(); ++e)
+        if (p->slice_tensor[e] == sm && ns < 4) {
+          c.sl_ord[ns] = (int8_t)p->slice_ord[e];
+          c.sl_bit[ns++] = (int8_t)p->slice_bit[e];
+        }
+      chain_steps.push_back(c);
+      chain_small.push_back(sm);
+      it.members.push_back(s);
+      big = n_in + s;
+    }
+    run.last = cand[n_take - 1];
+    const std::vector<int>& layf = p->layout[n_in + run.last];
+    std::map<int, int> fpos;
+    for (size_t b = 0; b < layf.size(); ++b) fpos[layf[b]] = (int)b;
+    for (int j = 0; j < L; ++j) run.hdr.out_loc[j] = (int8_t)fpos.at(at[j]);
+    for (auto& kv : glob) run.hdr.out_glob[kv.second] = (int8_t)fpos.at(kv.first);
+    it.chain = (int)p->chains.size();
+    p->chains.push_back(run);
+    return true;
+  };
   for (int phase = 0; phase < 3; ++phase) {
     p->items[phase].clear();
     std::vector<int> remaining;
@@ -1257,12 +1535,21 @@ static int build_schedule(tq_tn_plan* p) {
       std::vector<int> rest;
       for (int s : remaining) {
         const tq_tn_step& st = p->steps[s];
+        if (done[n_in + s]) continue;  // taken by an apply-chain run earlier in this pass
         if (p->kind[s] != 4 && done[st.lhs] && done[st.rhs]) {
           SchedItem it;
           it.step = s;
           it.batched = p->dep_batch[s] != 0;
+          if (p->kind[s] == 5 && p->chain_enabled && build_chain(s, it)) {
+            for (int m : it.members) {
+              done[n_in + m] = 1;
+              p->kind[m] = 7;
+            }
+            it.step = -1;
+          } else {
+            done[n_in + s] = 1;
+          }
           p->items[phase].push_back(it);
-          done[n_in + s] = 1;
           progressed = true;
         } else {
           rest.push_back(s);
@@ -1302,6 +1589,7 @@ static int build_schedule(tq_tn_plan* p) {
       if (it.step >= 0) members.push_back(it.step);
       for (int s : members) {
         if ((int)p->arena_const[s] != arena) continue;
+        if (it.chain >= 0 && s != p->chains[it.chain].last) continue;  // never materialised: lives in shared memory
         int64_t size = ((int64_t)1 << p->t_rank[n_in + s]);
         size = std::max(size, p->tc[s].out_entries);  // a fused-pack result lives as its consumer's operand image
         size = (size + 15) & ~(int64_t)15;
@@ -1347,6 +1635,7 @@ static int build_schedule(tq_tn_plan* p) {
   // ---- device tables of the fused runs
   for (int phase = 0; phase < 3; ++phase)
     for (const SchedItem& it : p->items[phase]) {
+      if (it.chain >= 0) continue;  // an apply-chain run has its own step table
       for (size_t i = 0; i < it.members.size(); ++i) {
         const int s = it.members[i];
         const tq_tn_step& st = p->steps[s];
@@ -1410,6 +1699,17 @@ static int build_schedule(tq_tn_plan* p) {
         }
       }
     }
+  for (size_t i = 0; i < chain_steps.size(); ++i) {
+    const int sm = chain_small[i];
+    chain_steps[i].off = sm < n_in ? 0 : p->arena_off[sm - n_in];
+  }
+  cudaFree(p->d_chain_steps);
+  p->d_chain_steps = nullptr;
+  if (!chain_steps.empty()) {
+    TQ_CUDA_OK(cudaMalloc((void**)&p->d_chain_steps, chain_steps.size() * sizeof(ChainStep)));
+    TQ_CUDA_OK(cudaMemcpy(p->d_chain_steps, chain_steps.data(), chain_steps.size() * sizeof(ChainStep),
+                          cudaMemcpyHostToDevice));
+  }
   cudaFree(p->d_fsteps);
   cudaFree(p->d_levels);
   cudaFree(p->d_micro);
@@ -1518,6 +1818,7 @@ void tq_tn_plan_destroy(tq_tn_plan* p) {
   cudaFree(p->d_fsteps);
   cudaFree(p->d_levels);
   cudaFree(p->d_micro);
+  cudaFree(p->d_chain_steps);
   delete p;
 }
 
@@ -1730,6 +2031,9 @@ int tq_tn_plan_set_option(tq_tn_plan* p, int32_t option, int32_t value) {
       return TQ_OK;
     case TQ_TN_OPT_TC_FUSE_PACK:
       p->tc_fuse_pack = value != 0;
+      return build_schedule(p);
+    case TQ_TN_OPT_CHAIN:
+      p->chain_enabled = value != 0;
       return build_schedule(p);
     case TQ_TN_OPT_FUSE_SMALL:
       p->fuse_enabled = value != 0;
@@ -2020,7 +2324,7 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
   InputRef* table = (InputRef*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   cx<R>* shared = (cx<R>*)((uint8_t*)table + tn_table_bytes(p));
   cx<R>* perset = shared + p->arena_shared;
-  if (p->d_fsteps) {
+  if (p->d_fsteps || p->d_chain_steps) {
     std::vector<InputRef> host(n_in);
     for (int t = 0; t < n_in; ++t) {
       host[t].ptr = inputs[t];
@@ -2162,6 +2466,26 @@ static int contract_impl(const tq_tn_plan* p, const void* const* inputs, const i
     const bool timed = step_ms && (slice == s_begin || !p->dep_slice[first]);
     if (timed) TQ_CUDA_OK(cudaEventRecord(ev[3 * first], st));
     const int64_t sets = it.batched ? B : 1;
+    if (it.chain >= 0) {
+      const ChainRun& run = p->chains[it.chain];
+      const cx<R>*src, *dst0;
+      int64_t ss, sd;
+      tensor_ptr(run.big_in, slice, src, ss);
+      tensor_ptr(n_in + run.last, slice, dst0, sd);
+      const size_t smem = (((size_t)1 << run.hdr.L) + (size_t)run.hdr.gate_entries) * sizeof(cx<R>);
+      TQ_REQUIRE(sets < 65536, TQ_E_UNSUPPORTED, "tq_tn_contract: step too large");
+      TQ_CUDA_OK(cudaFuncSetAttribute(k_tn_chain<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_tn_chain<R><<<dim3(1u << run.hdr.n_glob, (unsigned)sets), 256, smem, st>>>(
+          run.hdr, p->d_chain_steps + run.step_begin, (const InputRef*)table, shared, perset, p->arena_set, slice, src,
+          ss, const_cast<cx<R>*>(dst0), sd);
+      TQ_CUDA_OK(cudaGetLastError());
+      g_tn_launches += 1;
+      if (timed) {
+        TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 1], st));
+        TQ_CUDA_OK(cudaEventRecord(ev[3 * first + 2], st));
+      }
+      return TQ_OK;
+    }
     // one CTA per parameter set (2 CTAs per SM); a run shared by all sets gets a cluster of FUSE_CLUSTER CTAs
     if (sets == 1) {
       cudaLaunchConfig_t cfg;

@@ -161,6 +161,92 @@ def sequential_path(n_inputs: int):
     return path
 
 
+def sequential_blocked_path(inputs, output, max_block_rank: int = 4):
+    """Time-ordered sweep with GATE BLOCKING: like ``sequential_path`` the operands are taken in their (time) order,
+    but a small operand is first merged with the pending small tensors it is wired to while the merged tensor keeps
+    rank <= ``max_block_rank`` (4 = a two-qubit block [out, out, in, in]); only full blocks are contracted with the
+    growing state tensor.  Pending blocks sit on disjoint wires, so they commute and can be flushed in any order.
+    The state tensor then sees one gate-like apply step per BLOCK instead of one per gate — what the state-vector
+    engine's gate fusion does expressed as a contraction path; the engine runs the applies as
+    shared-memory chain sweeps (k_tn_chain)."""
+    n = len(inputs)
+    count: Dict[int, int] = {}
+    for t in inputs:
+        for ix in t:
+            count[ix] = count.get(ix, 0) + 1
+    for ix in output:
+        count[ix] = count.get(ix, 0) + 1
+    sets: Dict[int, frozenset] = {t: frozenset(inputs[t]) for t in range(n)}
+    path: List[Tuple[int, int]] = []
+    nxt = [n]
+
+    def result_of(a, b):
+        union = sets[a] | sets[b]
+        return frozenset(ix for ix in union if count[ix] - (ix in sets[a]) - (ix in sets[b]) > 0)
+
+    def contract(a, b):
+        res = result_of(a, b)
+        for ix in sets[a] | sets[b]:
+            c = count[ix] - (ix in sets[a]) - (ix in sets[b])
+            count[ix] = c + 1 if c > 0 else 0
+        path.append((a, b))
+        new = nxt[0]
+        nxt[0] += 1
+        sets[new] = res
+        del sets[a], sets[b]
+        return new
+
+    owner: Dict[int, int] = {}      # open index -> pending block that carries it
+    pending: List[int] = []         # pending blocks (tensor ids), oldest first
+    state = [None]
+
+    def claim(t):
+        for ix in sets[t]:
+            owner[ix] = t
+
+    def release(t):
+        for ix in sets[t]:
+            if owner.get(ix) == t:
+                del owner[ix]
+
+    def flush(blk):
+        release(blk)
+        pending.remove(blk)
+        state[0] = blk if state[0] is None else contract(state[0], blk)
+
+    for t in range(n):
+        touching = []
+        for ix in inputs[t]:
+            b = owner.get(ix)
+            if b is not None and b not in touching:
+                touching.append(b)
+        # merged index set if t joins every pending block it is wired to
+        merged = set(sets[t])
+        for b in touching:
+            merged |= sets[b]
+        group = touching + [t]
+        inner = {ix for ix in merged if count[ix] - sum(ix in sets[g] for g in group) <= 0}
+        if touching and len(merged - inner) <= max_block_rank:
+            cur = touching[0]
+            release(cur)
+            pending.remove(cur)
+            for b in touching[1:]:
+                release(b)
+                pending.remove(b)
+                cur = contract(cur, b)
+            cur = contract(cur, t)
+            pending.append(cur)
+            claim(cur)
+        else:
+            for b in touching:
+                flush(b)
+            pending.append(t)
+            claim(t)
+    for b in list(pending):
+        flush(b)
+    return path
+
+
 def step_time_model(n_a: int, n_b: int, n_out: int, n_union: int, model) -> float:
     """Estimated seconds of one pairwise step on the engine: max(complex-GEMM time, HBM time) + launch overhead.
     model = (algorithmic flop/s, bytes/s, seconds per step); ranks are log2 element counts (complex64)."""
@@ -382,9 +468,11 @@ def find_path(inputs, output, repeats: int = 16, seed: int = 0, minimize: str = 
     rng = random.Random(seed)
     best = None
     if len(inputs) > 1:
-        path = sequential_path(len(inputs))
-        width, fl, _, _ = path_cost(inputs, output, path)
-        best = ((fl, width) if minimize == "flops" else (width, fl), path, width, fl)
+        for path in (sequential_path(len(inputs)), sequential_blocked_path(inputs, output)):
+            width, fl, _, _ = path_cost(inputs, output, path)
+            key = (fl, width) if minimize == "flops" else (width, fl)
+            if best is None or key < best[0]:
+                best = (key, path, width, fl)
     for r in range(max(1, repeats)):
         alpha = alphas[0] if r == 0 else rng.choice(alphas)
         temp = temperatures[0] if r == 0 else rng.choice(temperatures[1:])
@@ -449,7 +537,7 @@ def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] =
     return PathInfo(path, sliced, width, fl, len(path))
 
 
-PLANNER_VERSION = 1   # bump when the search changes: stored plans of another version are searched again
+PLANNER_VERSION = 2   # bump when the search changes: stored plans of another version are searched again
 
 
 def valid_plan(inputs, output, ssa, sliced) -> bool:

@@ -445,3 +445,39 @@ def test_amplitude_batch_matches_single_calls(slice_batch):
         assert np.abs(got - single).max() <= 1e-6 * np.abs(ref).max()
         again = cc.amplitudes(bits).cpu().numpy()                        # numpy in, workspaces reused
         assert np.array_equal(again, got)
+
+
+@pytest.mark.parametrize("name,dt", [("mbl2d", "c128"), ("mbl1d", "c64"), ("hea", "c64"), ("rand", "c128")])
+def test_apply_chain_runs_match_single_applies(name, dt):
+    """TQ_TN_OPT_CHAIN: runs of gate-like apply steps on the same large tensor execute as one shared-memory sweep
+    (k_tn_chain).  Same values as one k_tn_apply launch per step and as the state-vector engine; the plans of these
+    circuits are state-vector shaped, so most of their steps must land in chain runs."""
+    if name == "mbl2d":
+        spec = W.mbl_2d(4, 1)
+    elif name == "mbl1d":
+        spec = W.mbl_1d(14)
+    elif name == "hea":
+        spec = W.hea(15, 3)
+    else:
+        spec = W.random_circuit(13, 80, seed=9, meas=[["probs", [12, 3]], ["probs", [0, 7]]])
+    rd = rdtype(dt)
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=rd))
+    x = torch.tensor(np.random.RandomState(2).rand(3, spec["n_params"]), dtype=rd, device="cuda")
+    ref = circ.compilecircuit(backend="pytorch_b200", dtype=cdtype(dt)).batched(x).cpu().numpy()
+    outs = {}
+    for chain in (1, 0):
+        cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, dtype=cdtype(dt),
+                                 hyper_opt={"max_repeats": 4, "light_cone": False,
+                                            "engine_opts": {capi.TN_OPT_CHAIN: chain}})
+        outs[chain] = cc.batched(x).cpu().numpy()
+        plan = cc._tn._plan(0, torch.device("cuda", torch.cuda.current_device()))
+        kinds = [plan.step_kernel(s) for s in range(plan.n_steps)]
+        if chain and name in ("mbl2d", "hea"):     # wide plans: the applies on the large tensor run as chain sweeps
+            assert kinds.count(7) > 4 * kinds.count(5), (kinds.count(7), kinds.count(5), len(kinds))
+        if not chain:
+            assert 7 not in kinds
+    if spec["meas"][0][0] == "probs" and name == "rand":   # TN branch keeps the listed qubit order, SV sorts ascending
+        ref = np.stack([np.transpose(ref[:, 0], (0, 2, 1)), ref[:, 1]], 1)
+    assert_close(outs[0], ref, TOL[dt], "apply steps")
+    assert_close(outs[1], ref, TOL[dt], "chain runs")
+    assert_close(outs[1], outs[0], TOL[dt] * 0.1, "chain vs apply")
