@@ -306,6 +306,24 @@ int tq_tn_contract_slices(const tq_tn_plan* plan, const void* const* inputs, con
                           int64_t batch, int64_t slice_begin, int64_t slice_end, void* out, void* workspace,
                           size_t workspace_bytes, void* cuda_stream);
 
+/* ---- multi-GPU (reference analogue: jdtensorpath's RPC slice workers, examples/qubit_rpc.py:110-126,
+ *      tedq/distributed_worker/rpc_workers.py:55-59) ----------------------------------------------------------
+ * One process per GPU.  The host creates the NCCL communicator (ncclCommInitRank, or the one its framework owns) and
+ * hands it over as an opaque pointer; the library resolves ncclAllReduce from the NCCL already loaded in the process
+ * (dlopen of libnccl.so.2: no link-time dependency).  tq_tn_contract_sharded contracts THIS rank's contiguous range
+ * of slices (tq_dist_slice_range: ceil(n / world) per rank) into `out` (zeroed by the caller) and combines the
+ * partial sums of all ranks with ONE ncclAllReduce(sum) enqueued on the same stream; every rank ends up with the
+ * full result.  An unsliced plan is contracted by rank 0 only (the others contribute zeros). */
+typedef struct tq_dist tq_dist;
+int tq_dist_create(void* nccl_comm /* ncclComm_t */, int32_t rank, int32_t world, tq_dist** out);
+void tq_dist_destroy(tq_dist* dist);
+int tq_dist_slice_range(int64_t n_slices, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
+/* in-place sum over ranks of `count` reals (dtype: TQ_C64 -> float, TQ_C128 -> double) on the stream */
+int tq_dist_allreduce(const tq_dist* dist, void* buf, int64_t count, int32_t dtype, void* cuda_stream);
+int tq_tn_contract_sharded(const tq_tn_plan* plan, const tq_dist* dist, const void* const* inputs,
+                           const int64_t* input_strides, int64_t batch, void* out, void* workspace,
+                           size_t workspace_bytes, void* cuda_stream);
+
 /* ---- reverse mode through the contraction tree (the reference differentiates through tree.contract with torch's
  *      tape, pytorch_backend.py:276/:339 under back_prop) ------------------------------------------------------
  * tq_tn_plan_enable_backward appends, for every forward step C = A x B on the way to an input that needs a

@@ -1,0 +1,36 @@
+"""C3 (20-qubit HEA) forward / backward sweep times for plan-option variants (threads per CTA, tile sizes)."""
+import sys
+sys.path.insert(0, ".")
+import numpy as np, torch
+import tedq_b200 as qb
+from tedq_b200 import workloads as W
+
+spec = W.hea(20, 10)
+circ = W.build_circuit(spec, qb)
+B = 64
+x = torch.tensor(np.random.RandomState(0).rand(B, spec["n_params"]), dtype=torch.float32, device="cuda")
+variants = [{}, {"threads": 128}, {"threads": 64}, {"max_local_qubits_bwd": 13}, {"max_local_qubits_bwd": 13, "threads": 128},
+            {"max_local_qubits_bwd": 11, "threads": 128}, {"max_local_qubits_fwd": 14, "threads": 256}, {"max_local_qubits_fwd": 12, "threads": 128}]
+for opts in variants:
+    cc = circ.compilecircuit(backend="pytorch_b200", plan_opts=opts or None)
+    plan = cc.plan(x.device)
+    out = torch.empty((B, plan.out_reals), device="cuda")
+    dy = torch.ones_like(out)
+    grad = torch.empty((B, plan.n_params), device="cuda")
+    wsb = plan.workspace_bytes(B, True)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    def step():
+        plan.forward(x.data_ptr(), B, out.data_ptr(), ws.data_ptr(), wsb, True, st)
+        e1.record()
+        plan.backward(x.data_ptr(), B, dy.data_ptr(), grad.data_ptr(), ws.data_ptr(), wsb, st)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    f = b = 0.0
+    for _ in range(3):
+        e0.record(); step(); e2.record(); torch.cuda.synchronize()
+        f += e0.elapsed_time(e1) / 3; b += e1.elapsed_time(e2) / 3
+    print(opts, "sweeps", plan.num_sweeps(False), plan.num_sweeps(True), "fwd %.2f ms bwd %.2f ms -> %.0f evals/s" % (f, b, B / ((f + b) * 1e-3)),
+          "gradsum %.6f" % float(grad.sum()))

@@ -48,7 +48,33 @@ err3 = max(float((res[0][0] - res[1][0]).abs().max()), float((res[0][1] - res[1]
 bits_batch = np.random.RandomState(3).randint(0, 2, size=(5, 16))
 b1, b2 = one.amplitudes(bits_batch).cpu(), par.amplitudes(bits_batch).cpu()
 err4 = float((b1 - b2).abs().max() / b1.abs().max())
+# 5. the C ABI's own multi-GPU entry (tq_dist_create / tq_tn_contract_sharded): a raw ncclComm_t made with ctypes on
+#    the NCCL library torch loaded, handed to the library as an opaque pointer
+import ctypes
+import nvidia.nccl
+from tedq_b200 import capi
+nccl = ctypes.CDLL(os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2"))
+class UniqueId(ctypes.Structure):
+    _fields_ = [("internal", ctypes.c_char * 128)]
+uid = UniqueId()
 if rank == 0:
+    assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+buf = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).cuda()
+dist.broadcast(buf, 0)
+uid = UniqueId.from_buffer_copy(bytes(buf.cpu().numpy().tobytes()))
+comm = ctypes.c_void_p()
+nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+assert nccl.ncclCommInitRank(ctypes.byref(comm), dist.get_world_size(), uid, rank) == 0
+tqd = capi.Dist(comm.value, rank, dist.get_world_size())
+flat0 = torch.zeros((1, 0), device="cuda")
+plan, ptrs, strides, out, ws, ws_bytes, _, _keep = one._tn._amplitude_operands(flat0, bits)
+out.zero_()
+plan.contract_sharded(tqd.handle, ptrs, strides, out.shape[0], out.data_ptr(), ws.data_ptr(), ws_bytes,
+                      torch.cuda.current_stream().cuda_stream)
+a5 = complex(out.sum().cpu())
+err5 = abs(a5 - a1) / abs(a1)
+if rank == 0:
+    print("C-ABI contract_sharded rel err %.2e %s" % (err5, "OK" if err5 < 1e-5 else "FAIL"))
     print("sharded reverse pass max err %.2e %s" % (err3, "OK" if err3 < 1e-5 else "FAIL"))
     print("amplitudes batch rel err %.2e %s" % (err4, "OK" if err4 < 1e-5 else "FAIL"))
     print("measurement_parallel max err %.2e %s" % (err1, "OK" if err1 < 1e-5 else "FAIL"))

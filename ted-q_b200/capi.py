@@ -146,6 +146,16 @@ def lib() -> C.CDLL:
     L.tq_tn_contract_prepare.restype = i32
     L.tq_tn_contract_slices.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, i64, vp, vp, sz, vp]
     L.tq_tn_contract_slices.restype = i32
+    L.tq_dist_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.tq_dist_create.restype = i32
+    L.tq_dist_destroy.argtypes = [vp]
+    L.tq_dist_destroy.restype = None
+    L.tq_dist_slice_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.tq_dist_slice_range.restype = i32
+    L.tq_dist_allreduce.argtypes = [vp, vp, i64, i32, vp]
+    L.tq_dist_allreduce.restype = i32
+    L.tq_tn_contract_sharded.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i64), i64, vp, vp, sz, vp]
+    L.tq_tn_contract_sharded.restype = i32
     L.tq_tn_plan_enable_backward.argtypes = [vp, pi32]
     L.tq_tn_plan_enable_backward.restype = i32
     L.tq_tn_backward.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), i64, i64, vp, vp, sz, vp]
@@ -180,6 +190,31 @@ def lib() -> C.CDLL:
         raise EngineError("libtedq_b200.so ABI version mismatch: rebuild with `python -m tedq_b200.build --force`")
     _lib = L
     return L
+
+
+def slice_range(n_slices: int, rank: int, world: int):
+    """[begin, end) of the slices rank ``rank`` of ``world`` contracts (tq_dist_slice_range; host only)."""
+    b, e = C.c_int64(), C.c_int64()
+    check(lib().tq_dist_slice_range(n_slices, rank, world, C.byref(b), C.byref(e)), "tq_dist_slice_range")
+    return int(b.value), int(e.value)
+
+
+class Dist:
+    """Owns a tq_dist*: the library's handle on an NCCL communicator the host created (``comm``: ncclComm_t as int)."""
+
+    def __init__(self, comm: int, rank: int, world: int):
+        h = C.c_void_p()
+        check(lib().tq_dist_create(C.c_void_p(comm), rank, world, C.byref(h)), "tq_dist_create")
+        self.handle, self.rank, self.world = h, rank, world
+
+    def allreduce(self, ptr, count, dtype, stream):
+        check(lib().tq_dist_allreduce(self.handle, ptr, count, dtype, stream), "tq_dist_allreduce")
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and _lib is not None:
+            _lib.tq_dist_destroy(h)
+            self.handle = None
 
 
 def device_index(device=None) -> int:
@@ -513,6 +548,12 @@ class TnPlan:
         ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
         check(lib().tq_tn_contract_slices(self.handle, ptrs, strides, batch, slice_begin, slice_end, out_ptr, ws_ptr,
                                           ws_bytes, stream), "tq_tn_contract_slices")
+
+    def contract_sharded(self, dist_handle, input_ptrs, input_strides, batch, out_ptr, ws_ptr, ws_bytes, stream):
+        """This rank's slice range + one ncclAllReduce inside the library (tq_tn_contract_sharded)."""
+        ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)
+        check(lib().tq_tn_contract_sharded(self.handle, dist_handle, ptrs, strides, batch, out_ptr, ws_ptr, ws_bytes,
+                                           stream), "tq_tn_contract_sharded")
 
     def contract(self, input_ptrs, input_strides, batch, slice_begin, slice_end, out_ptr, ws_ptr, ws_bytes, stream):
         ptrs, strides, _keep = self._ptr_arrays(input_ptrs, input_strides)

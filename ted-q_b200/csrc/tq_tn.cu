@@ -6,6 +6,8 @@
 // All extents are 2: a tensor of rank r is addressed by r bits; "permute into GEMM" is a bit
 // permutation folded into the address computation of the contraction kernel itself (no transposed
 // copy of either operand is ever materialised).
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -2247,6 +2249,7 @@ static int run_step_tc(const tq_tn_plan* p, int s, const cx<float>* a, int64_t s
   g.c_cs = T.swap ? ((int64_t)1 << stp.n_n) : 1;
   g.tiles_a = T.tiles_a;
   g.tiles_b = T.tiles_b;
+  g.tb_fast = T.img_a_z >= T.img_b_z ? 1 : 0;  // keep the larger image's tile shared through L2
   g.kblocks = T.kblocks;
   g.chunk = std::max(1, p->tc_chunk / tc::KB_CPLX);  // in k-blocks
   {
@@ -2654,4 +2657,79 @@ extern "C" int tq_tn_profile(const tq_tn_plan* p, const void* const* inputs, con
   TQ_REQUIRE(step_ms, TQ_E_INVALID, "tq_tn_profile: step_ms is null");
   return tn_contract_any(p, inputs, input_strides, batch, slice, slice + 1, out, workspace, workspace_bytes, stream,
                          step_ms);
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU: slice ranges + one NCCL all-reduce, for hosts that do not go through torch.distributed
+// ---------------------------------------------------------------------------
+struct tq_dist {
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*error_string)(int) = nullptr;
+};
+
+extern "C" int tq_dist_create(void* nccl_comm, int32_t rank, int32_t world, tq_dist** out) {
+  TQ_REQUIRE(out, TQ_E_INVALID, "tq_dist_create: out is null");
+  *out = nullptr;
+  TQ_REQUIRE(world >= 1 && rank >= 0 && rank < world, TQ_E_INVALID, "tq_dist_create: bad rank %d / world %d", rank, world);
+  TQ_REQUIRE(nccl_comm || world == 1, TQ_E_INVALID, "tq_dist_create: a communicator is needed for world > 1");
+  std::unique_ptr<tq_dist> d(new tq_dist());
+  d->comm = nccl_comm;
+  d->rank = rank;
+  d->world = world;
+  if (world > 1) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the NCCL the host already uses
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    TQ_REQUIRE(h, TQ_E_UNSUPPORTED, "tq_dist_create: libnccl.so.2 not found (%s)", dlerror());
+    d->all_reduce = reinterpret_cast<decltype(d->all_reduce)>(dlsym(h, "ncclAllReduce"));
+    d->error_string = reinterpret_cast<decltype(d->error_string)>(dlsym(h, "ncclGetErrorString"));
+    TQ_REQUIRE(d->all_reduce, TQ_E_UNSUPPORTED, "tq_dist_create: ncclAllReduce not found in libnccl");
+  }
+  *out = d.release();
+  return TQ_OK;
+}
+
+extern "C" void tq_dist_destroy(tq_dist* d) { delete d; }
+
+extern "C" int tq_dist_slice_range(int64_t n_slices, int32_t rank, int32_t world, int64_t* begin, int64_t* end) {
+  TQ_REQUIRE(begin && end && n_slices >= 0 && world >= 1 && rank >= 0 && rank < world, TQ_E_INVALID,
+             "tq_dist_slice_range: bad arguments");
+  const int64_t per = (n_slices + world - 1) / world;
+  *begin = std::min<int64_t>(n_slices, (int64_t)rank * per);
+  *end = std::min<int64_t>(n_slices, (int64_t)(rank + 1) * per);
+  return TQ_OK;
+}
+
+extern "C" int tq_dist_allreduce(const tq_dist* d, void* buf, int64_t count, int32_t dtype, void* stream) {
+  TQ_REQUIRE(d && buf && count >= 0, TQ_E_INVALID, "tq_dist_allreduce: bad arguments");
+  if (d->world == 1 || count == 0) return TQ_OK;
+  const int nccl_dtype = dtype == TQ_C64 ? 7 : 8;  // ncclFloat32 = 7, ncclFloat64 = 8; ncclSum = 0
+  const int rc = d->all_reduce(buf, buf, (size_t)count, nccl_dtype, 0, d->comm, (cudaStream_t)stream);
+  TQ_REQUIRE(rc == 0, TQ_E_CUDA, "ncclAllReduce failed: %s", d->error_string ? d->error_string(rc) : "?");
+  return TQ_OK;
+}
+
+extern "C" int tq_tn_contract_sharded(const tq_tn_plan* p, const tq_dist* d, const void* const* inputs,
+                                      const int64_t* input_strides, int64_t batch, void* out, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  TQ_REQUIRE(p && d && out, TQ_E_INVALID, "tq_tn_contract_sharded: null argument");
+  const int64_t ns = (int64_t)1 << p->n_sliced;
+  int64_t b = 0, e = ns;
+  if (ns > 1) {
+    int rc = tq_dist_slice_range(ns, d->rank, d->world, &b, &e);
+    if (rc) return rc;
+  } else if (d->rank != 0) {
+    e = 0;  // an unsliced plan: rank 0's contraction is the whole result
+  }
+  if (e > b) {
+    int rc = tq_tn_contract(p, inputs, input_strides, batch, b, e, out, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  bool any_batched = false;
+  for (int t = 0; t < p->n_in; ++t) any_batched |= p->in_batched[t] != 0;
+  const int64_t reals = 2 * (any_batched ? batch : 1) * ((int64_t)1 << p->n_out);
+  return tq_dist_allreduce(d, out, reals, p->dtype, stream);
 }

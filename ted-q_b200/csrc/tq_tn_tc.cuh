@@ -340,6 +340,11 @@ struct GemmParams {
   int64_t c_set_stride;      // complex entries between parameter sets of C
   int64_t c_rs, c_cs;        // complex-entry stride of an accumulator row / column inside C
   int32_t tiles_a, tiles_b, kblocks, n_z, n_b_log2, stages;
+  // order of the tiles of one z over the persistent CTAs: consecutive work items run on different SMs at the same
+  // time, so the tile index that varies fastest shares ITS PARTNER's tile through L2.  tb_fast = 1: column tile
+  // fastest (the row operand's tile is fetched from HBM once, by two SMs at once) — chosen when the A image is the
+  // larger one; 0: row tile fastest.
+  int32_t tb_fast;
   int32_t chunk;             // k-blocks accumulated inside the tensor core before a drain (see below)
   // experiments only (TQ_TC_DEBUG; bits 0-3 give wrong results): bit 0 = drains skip their TMEM loads; gather-A
   // variant: bit 1 = no generic->async proxy fence, bit 2 = no conversion, bit 3 = no loads, bit 4 = every lane polls
@@ -421,7 +426,8 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         const int kbeg = (int)(w - t * p.splits) * p.kb_per_split;
         const int64_t z = t / tiles_per_z;
         const int64_t r = t - z * tiles_per_z;
-        const int64_t tb = r / p.tiles_a, ta = r - tb * p.tiles_a;
+        const int64_t tb = p.tb_fast ? r % p.tiles_b : r / p.tiles_a;
+        const int64_t ta = p.tb_fast ? r / p.tiles_b : r - tb * p.tiles_a;
         const int64_t zset = z >> p.n_b_log2, zbb = z & (((int64_t)1 << p.n_b_log2) - 1);
         const uint8_t* ga = p.img_a + zset * p.img_a_set + zbb * p.img_a_z + ta * (int64_t)p.kblocks * A_CHUNK;
         const uint8_t* gb = p.img_b + zset * p.img_b_set + zbb * p.img_b_z + tb * (int64_t)p.kblocks * b_chunk;
@@ -537,7 +543,7 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
         const int64_t t = wi / p.splits;
         const int64_t z = t / tiles_per_z;
         const int64_t r = t - z * tiles_per_z;
-        const uint32_t ta = (uint32_t)(r % p.tiles_a);
+        const uint32_t ta = (uint32_t)(p.tb_fast ? r / p.tiles_b : r % p.tiles_a);
         const uint32_t bb = (uint32_t)z & bb_mask;
         int64_t base = 0;
         for (int j = 0; j < P.n_b; ++j) base |= (int64_t)((bb >> j) & 1u) << P.b_bits[j];
@@ -638,7 +644,8 @@ k_tc_gemm(const __grid_constant__ GemmParams p) {
       }
       const int64_t z = t / tiles_per_z;
       const int64_t r = t - z * tiles_per_z;
-      const int64_t tb = r / p.tiles_a, ta = r - tb * p.tiles_a;
+      const int64_t tb = p.tb_fast ? r % p.tiles_b : r / p.tiles_a;
+      const int64_t ta = p.tb_fast ? r / p.tiles_b : r - tb * p.tiles_a;
       const int64_t set = z >> p.n_b_log2, bb = z & bb_mask;
       const int64_t row = ta * ROWS + q * 32 + lane;
       const int64_t col0 = tb * C_T + h * HALF;

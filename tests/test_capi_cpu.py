@@ -127,3 +127,18 @@ def test_product_sources_never_touch_the_oracle_or_the_reference():
         if isinstance(node, (ast.Import, ast.ImportFrom)):
             names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
             assert not any(n == "oracle" or n.startswith("oracle.") for n in names)
+
+
+def test_dist_slice_range_matches_python_sharding():
+    """tq_dist_slice_range (the C ABI's multi-GPU entry) deals slices exactly like dist.shard_range does for the
+    torch.distributed path: contiguous blocks of ceil(n / world), every slice exactly once."""
+    from tedq_b200 import capi, dist
+
+    for n in (0, 1, 5, 8, 64, 65, 1000):
+        for world in (1, 2, 3, 4, 8):
+            got = [capi.slice_range(n, r, world) for r in range(world)]
+            assert got == [dist.shard_range(n, r, world) for r in range(world)]
+            covered = [s for b, e in got for s in range(b, e)]
+            assert covered == list(range(n))
+    d = capi.Dist(0, 0, 1)      # world 1 needs no communicator; all-reduce is a no-op
+    d.allreduce(0, 0, capi.TQ_C64, 0)
