@@ -2704,8 +2704,9 @@ extern "C" int tq_dist_slice_range(int64_t n_slices, int32_t rank, int32_t world
 }
 
 extern "C" int tq_dist_allreduce(const tq_dist* d, void* buf, int64_t count, int32_t dtype, void* stream) {
-  TQ_REQUIRE(d && buf && count >= 0, TQ_E_INVALID, "tq_dist_allreduce: bad arguments");
+  TQ_REQUIRE(d && count >= 0, TQ_E_INVALID, "tq_dist_allreduce: bad arguments");
   if (d->world == 1 || count == 0) return TQ_OK;
+  TQ_REQUIRE(buf, TQ_E_INVALID, "tq_dist_allreduce: buf is null");
   const int nccl_dtype = dtype == TQ_C64 ? 7 : 8;  // ncclFloat32 = 7, ncclFloat64 = 8; ncclSum = 0
   const int rc = d->all_reduce(buf, buf, (size_t)count, nccl_dtype, 0, d->comm, (cudaStream_t)stream);
   TQ_REQUIRE(rc == 0, TQ_E_CUDA, "ncclAllReduce failed: %s", d->error_string ? d->error_string(rc) : "?");
