@@ -507,6 +507,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   };
   p->threads_f = pick_threads(m_f);
   p->threads_b = pick_threads(m_b);
+  // tiled complex64 adjoint sweeps: 128 threads per CTA, 3 CTAs per SM — every thread runs twice the amplitude groups
+  // per op, which halves the per-op overhead (matrix loads, W reduction, barrier) per amplitude: 49.2 -> 45.7 ms on
+  // the 20-qubit HEA (scripts/c3_threads.py); the forward sweep is faster with 256
+  if (threads == 0 && c64 && !p->bwd_full) p->threads_b = 128;
   TQ_REQUIRE(p->threads_f % 32 == 0 && p->threads_f <= 256 && p->threads_b % 32 == 0 && p->threads_b <= 256,
              TQ_E_INVALID, "tq_plan_create: threads must be a multiple of 32, <= 256");
 

@@ -354,7 +354,7 @@ def test_var_sample_and_user_unitary():
         # oracle: the same circuit with RX(0.37) in place of the user unitary, observables applied in numpy / torch
         def ref_def(a, b, c):
             qb.RY(a, qubits=[0]); qb.RX(b, qubits=[1]); qb.CNOT(qubits=[0, 1]); qb.CRZ(c, qubits=[1, 2])
-            qb.RX(torch.tensor(ang), qubits=[2], trainable_params=[]); qb.Hadamard(qubits=[0])
+            qb.RX(torch.tensor(ang, dtype=torch.float64), qubits=[2], trainable_params=[]); qb.Hadamard(qubits=[0])
             return qb.state()
         _, flat, psi = _state_and_ops(ref_def, 3, [p.detach().cpu() for p in params])
         Z, X, I2 = np.diag([1.0, -1.0]), np.array([[0, 1.0], [1.0, 0]]), np.eye(2)
