@@ -634,7 +634,8 @@ def measure_tn_mode(name, steps, warmup, device, dist, do_cpu, cpu_budget=10.0, 
 # C5: sliced single-amplitude contraction (headline)
 # ----------------------------------------------------------------------------------------------------------
 def c5_hyper(greedy_plan, contract_parallel):
-    return {"max_repeats": C5_HYPER["max_repeats"], "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
+    extra = {"slice_batch": int(os.environ["TQ_C5_SLICE_BATCH"])} if "TQ_C5_SLICE_BATCH" in os.environ else {}
+    return {**extra, "max_repeats": C5_HYPER["max_repeats"], "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
             "time_model": None if greedy_plan else C5_HYPER["time_model"],
             "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=contract_parallel),
             "plan_cache": PLAN_CACHE}

@@ -490,12 +490,12 @@ class TNExecutor:
 
     def _slice_group(self, net, info, batched):
         """hyper_opt["slice_batch"] = g: 2^g slices go through the device together as the batch dimension of ONE
-        launch sequence (default 3 when no gate is batched over parameter sets, fewer when ranks would go idle; 0 = one
+        launch sequence (default 4 when no gate is batched over parameter sets, fewer when ranks would go idle; 0 = one
         slice at a time).  A slice
         of a 40-qubit amplitude is ~20 launches of 20-90 us with one tile per SM: grouping slices gives every launch
         several tiles per SM (prologue / epilogue overlap inside the persistent kernels) and divides the launch count.
         -> None or {"indices": grouped sliced indices, "rest": the others, "axes": {tensor: [(axis, group bit)]}}."""
-        g = int(self.ho.get("slice_batch", 3))
+        g = int(self.ho.get("slice_batch", 4))
         # memory: the per-set arena is a few times the largest intermediate (2^width entries); keep a group's
         # largest tensors at <= 2^28 entries together (2 GiB complex64) unless the caller asked for a size
         if "slice_batch" not in self.ho:
