@@ -100,7 +100,12 @@ typedef struct tq_plan_opts {
   int32_t coalesce_bits;        /* -1 = default. low amplitude-index bits always kept tile-local     */
   int32_t threads;              /* 0 = default CTA size                                              */
   int32_t fuse;                 /* -1 = default (1). 1: fuse runs of gates in registers               */
-  int32_t reserved[3];
+  int32_t structure;            /* 0 = default: every fused block is a dense complex matrix.  1 (experimental): blocks
+                                   of real gates (RY, CRY, H, X, CNOT, ...) take real-matrix paths with half the
+                                   multiplies, and one-qubit diagonal gates (RZ, PhaseShift, S, T, Z) stay out of the
+                                   blocks and are merged, per sweep, into diagonal-layer passes (two phase tables,
+                                   signed-sum gradients).  Same results; measured slower on B200         */
+  int32_t reserved[2];
 } tq_plan_opts;
 
 typedef struct tq_plan tq_plan; /* opaque, immutable after creation */
@@ -123,6 +128,9 @@ int32_t tq_plan_num_params(const tq_plan* plan);
 int32_t tq_plan_num_sweeps(const tq_plan* plan, int32_t backward);
 /* ops after gate fusion (runs of gates inside one qubit / one qubit pair become one dense block) */
 int32_t tq_plan_num_blocks(const tq_plan* plan);
+/* ops emitted into the sweeps of one direction: what = 0 all, 1 diagonal-layer ops (runs of one-qubit diagonal gates
+ * merged into one phase-table pass), 2 the gates inside them, 3 ops on the real-matrix paths */
+int32_t tq_plan_op_stats(const tq_plan* plan, int32_t backward, int32_t what);
 /* local amplitude-index bit positions of sweep s; returns count, writes up to cap entries */
 int32_t tq_plan_sweep_bits(const tq_plan* plan, int32_t backward, int32_t s, int32_t* bits, int32_t cap);
 int32_t tq_plan_sweep_num_gates(const tq_plan* plan, int32_t backward, int32_t s);

@@ -9,7 +9,7 @@ spec = W.hea(20, 10)
 circ = W.build_circuit(spec, qb)
 B = 64
 x = torch.tensor(np.random.RandomState(0).rand(B, spec["n_params"]), dtype=torch.float32, device="cuda")
-variants = [{}, {"threads": 128}, {"threads": 64}, {"max_local_qubits_bwd": 13}, {"max_local_qubits_bwd": 13, "threads": 128},
+variants = [{}, {"structure": 1}, {"threads": 128}, {"threads": 64}, {"max_local_qubits_bwd": 13}, {"max_local_qubits_bwd": 13, "threads": 128},
             {"max_local_qubits_bwd": 11, "threads": 128}, {"max_local_qubits_fwd": 14, "threads": 256}, {"max_local_qubits_fwd": 12, "threads": 128}]
 for opts in variants:
     cc = circ.compilecircuit(backend="pytorch_b200", plan_opts=opts or None)
@@ -32,5 +32,6 @@ for opts in variants:
     for _ in range(3):
         e0.record(); step(); e2.record(); torch.cuda.synchronize()
         f += e0.elapsed_time(e1) / 3; b += e1.elapsed_time(e2) / 3
-    print(opts, "sweeps", plan.num_sweeps(False), plan.num_sweeps(True), "fwd %.2f ms bwd %.2f ms -> %.0f evals/s" % (f, b, B / ((f + b) * 1e-3)),
+    print(opts, "blocks", plan.num_blocks(), "ops/dl/members/real fwd", plan.op_stats(False), "bwd", plan.op_stats(True))
+    print("    sweeps", plan.num_sweeps(False), plan.num_sweeps(True), "fwd %.2f ms bwd %.2f ms -> %.0f evals/s" % (f, b, B / ((f + b) * 1e-3)),
           "gradsum %.6f" % float(grad.sum()))

@@ -34,7 +34,7 @@ class PlanOpts(C.Structure):
     _fields_ = [
         ("max_local_qubits_fwd", C.c_int32), ("max_local_qubits_bwd", C.c_int32),
         ("coalesce_bits", C.c_int32), ("threads", C.c_int32), ("fuse", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("structure", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
         getattr(L, name).restype = i32
     L.tq_plan_num_blocks.argtypes = [vp]
     L.tq_plan_num_blocks.restype = i32
+    L.tq_plan_op_stats.argtypes = [vp, i32, i32]
+    L.tq_plan_op_stats.restype = i32
     L.tq_plan_num_sweeps.argtypes = [vp, i32]
     L.tq_plan_num_sweeps.restype = i32
     L.tq_plan_sweep_bits.argtypes = [vp, i32, i32, C.POINTER(i32), i32]
@@ -321,6 +323,10 @@ class Plan:
     # -- introspection -----------------------------------------------------
     def num_sweeps(self, backward=False) -> int:
         return int(lib().tq_plan_num_sweeps(self.handle, int(backward)))
+
+    def op_stats(self, backward=False):
+        """(ops, diagonal-layer ops, gates inside them, real-path ops) emitted into the sweeps of one direction."""
+        return tuple(int(lib().tq_plan_op_stats(self.handle, int(backward), w)) for w in range(4))
 
     def num_blocks(self) -> int:
         return int(lib().tq_plan_num_blocks(self.handle))

@@ -42,6 +42,8 @@ struct HostGate {  // one circuit gate, structure resolved
   std::vector<int> targets, controls;  // qubits
   int red_off = -1;                    // FIXED: reduced matrix (dense block or diagonal) in the fixed pool
   int red_count = 0;
+  bool real = false;   // every entry of the (full) matrix is real for every parameter value: RY, CRY, H, X, Z, CNOT, ...
+  bool diag1 = false;  // one-qubit diagonal gate without controls: RZ, PhaseShift, S, T, Z — joins a diagonal layer
 };
 
 struct HostBlock {
@@ -49,6 +51,8 @@ struct HostBlock {
   std::vector<int> members;  // gate indices, circuit order
   bool alive = true;
   int nderiv = 0;
+  bool real = true;    // every member is real: the block's product is real (half the multiplies, only Re W needed)
+  bool diag1 = false;  // a lone one-qubit diagonal gate kept out of dense blocks: merged into a diagonal layer op
   // resolved op
   int cls = OP_DENSE;
   std::vector<int> targets, controls;
@@ -85,6 +89,7 @@ struct tq_plan {
   bool fwd_full = false, bwd_full = false, sv_ok = true;
   int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256, fuse = 1;
   std::vector<Sweep> fwd, bwd;
+  int n_ops[2] = {0, 0}, n_dl[2] = {0, 0}, n_dl_members[2] = {0, 0}, n_real[2] = {0, 0};  // emitted ops per direction
   // device
   void* d_fixed = nullptr;
   void* d_init = nullptr;
@@ -296,7 +301,30 @@ static void make_desc(const HostBlock& h, int n, const std::vector<int>& bits, b
   d.pad = (uint32_t)h.cls;
   int shift = 0;
   std::vector<int> ins;
-  if (h.cls == OP_DENSE) {
+  if (h.cls == OP_DENSE && h.real && k <= 2) {  // real twins of the complex paths, chosen by the same rules
+    if (k == 1) {
+      if (c64 && lt[0] == 0) {
+        d.path = P_R1P;
+        shift = 1;
+        ins = lc;
+      } else if (c64 && !bit0_ctrl) {
+        d.path = P_R1V;
+        shift = 1;
+        ins = lc;
+        ins.push_back(lt[0]);
+      } else {
+        d.path = P_R1S;
+        ins = lc;
+        ins.push_back(lt[0]);
+      }
+    } else {
+      d.path = (c64 && !bit0_ctrl && !bit0_tgt) ? P_R2V : P_R2S;
+      shift = d.path == P_R2V ? 1 : 0;
+      ins = lc;
+      ins.push_back(lt[0]);
+      ins.push_back(lt[1]);
+    }
+  } else if (h.cls == OP_DENSE) {
     if (k == 1) {
       if (c64 && lt[0] == 0) {
         d.path = P_D1P;
@@ -475,7 +503,13 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   int coalesce = c64 ? 3 : 2;                          // 64-byte contiguous runs
   int threads = 0;
   int fuse = 1;
+  // structure-aware ops (tq_plan_opts.structure = 1): real blocks on half-cost paths, one-qubit diagonal gates merged
+  // into diagonal-layer passes.  Off by default: on the 20-qubit HEA it halves the multiplies but needs 247 passes
+  // over the tile instead of 190 and executes MORE instructions in total (2.70e9 vs 2.53e9 per 16 sets, ncu) — the
+  // per-pass overhead (descriptor, matrix load, index arithmetic, barrier) outweighs the saved FMAs
+  bool diag_layers = false;
   if (opts) {
+    diag_layers = opts->structure == 1;
     if (opts->max_local_qubits_fwd > 0) m_f = full_f = opts->max_local_qubits_fwd;
     if (opts->max_local_qubits_bwd > 0) m_b = full_b = opts->max_local_qubits_bwd;
     if (opts->coalesce_bits >= 0) coalesce = opts->coalesce_bits;
@@ -535,6 +569,9 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
                  "gate %d: matrix outside pool", gi);
       std::vector<zc> red;
       classify_fixed(zpool + g.matrix_off, g.nq, h.qubits, h, red);
+      h.real = true;
+      for (int i = 0; i < D * D; ++i) h.real = h.real && zpool[g.matrix_off + i].imag() == 0.0;
+      h.diag1 = !h.noop && h.cls == OP_DIAG && h.targets.size() == 1 && h.controls.empty() && g.nq == 1;
       h.full_off = (int)p->fixed.size();
       p->fixed.insert(p->fixed.end(), zpool + g.matrix_off, zpool + g.matrix_off + D * D);
       if (!h.noop) {
@@ -547,6 +584,8 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     }
     int np = 1, nqexp = 1;
     bool ctrl = false;
+    h.real = g.kind == TQ_G_RY || g.kind == TQ_G_CRY;
+    h.diag1 = g.kind == TQ_G_RZ || g.kind == TQ_G_PHASESHIFT;
     switch (g.kind) {
       case TQ_G_RX: case TQ_G_RY: h.cls = OP_DENSE; break;
       case TQ_G_ROT: h.cls = OP_DENSE; np = 3; break;
@@ -628,6 +667,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
         for (int i = 0; i < g.nq; ++i) b.qubits.push_back(g.qubits[i]);
         b.members.push_back(gi);
         b.nderiv = g.ntrain;
+        b.real = g.real;
         all.push_back(b);
         for (int i = 0; i < g.nq; ++i) owner[g.qubits[i]] = (int)all.size() - 1;
       };
@@ -637,9 +677,23 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       }
       if (g.nq == 1) {
         int o = owner[g.qubits[0]];
-        if (o >= 0 && all[o].qubits.size() <= 2 && can_add(all[o], g, 0)) {
+        if (diag_layers && g.diag1) {
+          // a one-qubit diagonal gate costs nothing inside a block that is complex anyway; otherwise it stays on its
+          // own and is merged with the other diagonal gates of its sweep into ONE phase-table pass (P_DL) — fused
+          // into a real block it would double that block's multiplies
+          if (o >= 0 && !all[o].diag1 && !all[o].real && all[o].qubits.size() <= 2 && can_add(all[o], g, 0)) {
+            all[o].members.push_back(gi);
+            all[o].nderiv += g.ntrain;
+          } else {
+            fresh();
+            all.back().diag1 = true;
+          }
+          continue;
+        }
+        if (o >= 0 && !all[o].diag1 && all[o].qubits.size() <= 2 && can_add(all[o], g, 0)) {
           all[o].members.push_back(gi);
           all[o].nderiv += g.ntrain;
+          all[o].real = all[o].real && g.real;
         } else {
           fresh();
         }
@@ -650,17 +704,20 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       if (o0 >= 0 && o0 == o1 && all[o0].qubits.size() == 2 && can_add(all[o0], g, 0)) {
         all[o0].members.push_back(gi);
         all[o0].nderiv += g.ntrain;
+        all[o0].real = all[o0].real && g.real;
         continue;
       }
       HostBlock b;
       b.qubits.push_back(g.qubits[0]);
       b.qubits.push_back(g.qubits[1]);
+      b.real = g.real;
       for (int side = 0; side < 2; ++side) {
         int o = side == 0 ? o0 : o1;
-        if (o >= 0 && all[o].alive && all[o].qubits.size() == 1) {
+        if (o >= 0 && all[o].alive && all[o].qubits.size() == 1 && !all[o].diag1) {
           if (can_add(b, g, all[o].nderiv)) {
             for (int mgi : all[o].members) b.members.push_back(mgi);
             b.nderiv += all[o].nderiv;
+            b.real = b.real && all[o].real;
             all[o].alive = false;
           }
         }
@@ -747,12 +804,14 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     flush_fold();
     mb.instr_end = (int)p->minstrs.size();
     mb.nderiv = b.nderiv;
+    if (!diag_layers) b.real = b.diag1 = false;
     if (single) {
       const HostGate& g = p->gates[b.members[0]];
       b.cls = g.cls;
       b.targets = g.targets;
       b.controls = g.controls;
       b.count = g.red_count;
+      b.real = b.real && g.real && g.cls == OP_DENSE;
       mb.mode = g.kind == TQ_G_FIXED ? MB_FIXED : MB_NATIVE;
       mb.diag = g.cls == OP_DIAG;
       mb.dim = 1 << (int)g.targets.size();
@@ -852,18 +911,85 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       sw.chunk_begin = (int)chunks.size();
       ChunkInfo cur = {0, 0, 0, 0};
       bool open = false;
-      for (int bi : sg[s]) {
-        HostBlock& hb = p->blocks[bi];
-        OpDesc d;
-        make_desc(hb, n, sb[s], c64, d);
-        const int pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
-        TQ_REQUIRE(pe <= pay_cap_entries, TQ_E_UNSUPPORTED, "block payload exceeds the prefetch buffer");
-        d.pay_off = (uint32_t)stride;
-        (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
-        if (dir) {
-          d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
-          for (int k = 0; k < hb.nderiv; ++k) slot_pidx.push_back(hb.pidx[k]);
+      // Emission order: one-qubit diagonal blocks are held back and merged into diagonal-layer ops.  A held-back
+      // block commutes with everything emitted before the layer is flushed (no shared qubit), and the layer is
+      // flushed before the first block that touches one of its qubits.
+      std::vector<std::vector<int>> items;
+      {
+        std::vector<int> group;
+        std::vector<char> group_q(n, 0);
+        auto flush = [&]() {
+          if (group.empty()) return;
+          items.push_back(group);
+          group.clear();
+          std::fill(group_q.begin(), group_q.end(), 0);
+        };
+        for (int bi : sg[s]) {
+          const HostBlock& hb = p->blocks[bi];
+          if (hb.diag1 && hb.cls == OP_DIAG) {
+            const int q = hb.targets[0];
+            if (group_q[q] || (int)group.size() == DL_MAX) flush();
+            group.push_back(bi);
+            group_q[q] = 1;
+          } else {
+            bool touches = false;
+            for (int q : hb.qubits) touches = touches || group_q[q];
+            if (touches) flush();
+            items.push_back({bi});
+          }
         }
+        flush();
+      }
+      for (const std::vector<int>& item : items) {
+        OpDesc d;
+        int pe;
+        const int64_t pay0 = stride;
+        if (item.size() == 1) {
+          HostBlock& hb = p->blocks[item[0]];
+          make_desc(hb, n, sb[s], c64, d);
+          pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
+          (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
+          if (dir) {
+            d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
+            for (int k = 0; k < hb.nderiv; ++k) slot_pidx.push_back(hb.pidx[k]);
+          }
+        } else {  // diagonal layer: the members' payloads back to back (2 entries each forward, 4 backward)
+          memset(&d, 0, sizeof(d));
+          d.path = P_DL;
+          const int per = dir ? 4 : 2;
+          pe = per * (int)item.size();
+          uint32_t mask = 0;
+          int nd = 0;
+          uint8_t pos[DL_MAX];
+          memset(pos, 0, sizeof(pos));
+          if (dir) d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
+          for (size_t k = 0; k < item.size(); ++k) {
+            HostBlock& hb = p->blocks[item[k]];
+            const int bit = n - 1 - hb.targets[0];
+            int lp = -1;
+            for (size_t j = 0; j < sb[s].size(); ++j)
+              if (sb[s][j] == bit) lp = (int)j;
+            TQ_REQUIRE(lp >= 0, TQ_E_INVALID, "tq_plan_create: diagonal-layer member outside its sweep's tile");
+            pos[k] = (uint8_t)lp;
+            (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)(stride + per * (int64_t)k);
+            TQ_REQUIRE(hb.nderiv <= 1, TQ_E_UNSUPPORTED, "tq_plan_create: a diagonal gate with %d parameters", hb.nderiv);
+            if (hb.nderiv == 1) {
+              mask |= 1u << k;
+              ++nd;
+              if (dir) slot_pidx.push_back(hb.pidx[0]);
+            }
+          }
+          d.nderiv = (uint8_t)nd;
+          d.count = (uint32_t)item.size() | (mask << 8);
+          for (int j = 0; j < 4; ++j) {
+            d.ins[j] = pos[j];
+            d.tpos[j] = pos[4 + j];
+            d.cmask |= (uint32_t)pos[8 + j] << (8 * j);
+            d.pad |= (uint32_t)pos[12 + j] << (8 * j);
+          }
+        }
+        TQ_REQUIRE(pe <= pay_cap_entries, TQ_E_UNSUPPORTED, "block payload exceeds the prefetch buffer");
+        d.pay_off = (uint32_t)pay0;
         if (open && (cur.op_count >= (uint32_t)CHUNK_OPS || (int)cur.pay_count + pe > pay_cap_entries)) {
           chunks.push_back(cur);
           open = false;
@@ -879,6 +1005,12 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
         cur.pay_count += (uint32_t)pe;
         stride += pe;
         ops.push_back(d);
+        p->n_ops[dir] += 1;
+        if (d.path == P_DL) {
+          p->n_dl[dir] += 1;
+          p->n_dl_members[dir] += (int)item.size();
+        }
+        if (d.path == P_R1S || d.path == P_R2S || d.path == P_R1V || d.path == P_R1P || d.path == P_R2V) p->n_real[dir] += 1;
       }
       if (open) chunks.push_back(cur);
       sw.op_end = (int)ops.size();
@@ -929,6 +1061,12 @@ int32_t tq_plan_sweep_num_gates(const tq_plan* p, int32_t backward, int32_t s) {
   return v[s].n_gates;
 }
 int32_t tq_plan_num_blocks(const tq_plan* p) { return p ? (int32_t)p->blocks.size() : -1; }
+/* what = 0: ops emitted into the sweeps, 1: diagonal-layer ops, 2: their members, 3: ops on the real paths */
+int32_t tq_plan_op_stats(const tq_plan* p, int32_t backward, int32_t what) {
+  if (!p || what < 0 || what > 3) return -1;
+  const int d = backward ? 1 : 0;
+  return what == 0 ? p->n_ops[d] : what == 1 ? p->n_dl[d] : what == 2 ? p->n_dl_members[d] : p->n_real[d];
+}
 int64_t tq_plan_out_reals(const tq_plan* p) { return p ? p->out_reals : -1; }
 
 int64_t tq_plan_hbm_bytes(const tq_plan* p, int32_t backward) {
@@ -950,7 +1088,7 @@ int64_t tq_plan_hbm_bytes(const tq_plan* p, int32_t backward) {
 
 /* Algorithmic real flops of one evaluation on the fused-block schedule (complex MAC = 8 flops, complex multiply = 6):
  * forward: a dense block on t target qubits costs 8 * 2^t per amplitude it touches (2^(n - controls) of them), a
- * diagonal block 6; backward (adjoint method): psi <- G^dagger psi, lambda <- G^dagger lambda and the accumulation of
+ * diagonal block 6 (a member of a diagonal layer included), a REAL dense block 4 * 2^t; backward (adjoint method): psi <- G^dagger psi, lambda <- G^dagger lambda and the accumulation of
  * W = psi (x) conj(lambda) cost one such product each, i.e. 3x the forward count.  Measurement passes not counted. */
 double tq_plan_flops(const tq_plan* p, int32_t backward) {
   if (!p) return -1.0;
@@ -958,7 +1096,8 @@ double tq_plan_flops(const tq_plan* p, int32_t backward) {
   for (const HostBlock& b : p->blocks) {
     if (!b.alive) continue;
     const double amps = ldexp(1.0, p->n - (int)b.controls.size());
-    const double per = b.cls == OP_DIAG ? 6.0 : 8.0 * ldexp(1.0, (int)b.targets.size());
+    // complex MAC = 8 flops; a real matrix entry times a complex amplitude, accumulated = 4
+    const double per = b.cls == OP_DIAG ? 6.0 : (b.real ? 4.0 : 8.0) * ldexp(1.0, (int)b.targets.size());
     fl += amps * per;
   }
   return backward ? 3.0 * fl : fl;

@@ -29,8 +29,15 @@ enum {
   P_D2S = 4,  // dense 2 targets, scalar
   P_G1V = 5,  // diagonal 1 target, complex64, bit 0 not a control
   P_G1S = 6,  // diagonal 1 target, scalar
-  P_GEN = 7   // anything else (3-target dense, multi-target diagonal): correct, not tuned
+  P_GEN = 7,  // anything else (3-target dense, multi-target diagonal): correct, not tuned
+  P_R1S = 8,  // REAL dense 1 target (RY, X, H, ... and fused products of such): half the multiplies of P_D1*
+  P_R2S = 9,  // REAL dense 2 targets ((RY x RY) CNOT ...)
+  P_R1V = 11, P_R1P = 12, P_R2V = 13,  // real twins of P_D1V / P_D1P / P_D2V (complex64, 128-bit accesses)
+  P_DL = 10   // diagonal LAYER: up to 16 one-qubit diagonal gates (RZ, PhaseShift, S, T, Z) on different tile bits,
+              // applied as ONE pass through two phase tables; payload = the members' own payloads, back to back
 };
+constexpr int DL_MAX = 16;     // members of a diagonal layer
+constexpr int DL_LO_BITS = 7;  // tile bits resolved by the low phase table
 
 struct __align__(16) OpDesc {  // 32 bytes
   uint8_t path, k, nins, nderiv;
@@ -654,6 +661,194 @@ __device__ __forceinline__ void fwd_g1s(cx<R>* s, const OpDesc& d, const cx<R>* 
   }
 }
 
+// ---- real blocks: the matrix has no imaginary part (payload entries are complex with .y == 0) ------------------
+// y = M x with real M costs 2 real multiplies per complex amplitude entry instead of 4.
+template <typename R>
+__device__ __forceinline__ cx<R> rmul(R m, cx<R> a) { return mk<R>(m * a.x, m * a.y); }
+template <typename R>
+__device__ __forceinline__ cx<R> rfma(R m, cx<R> a, cx<R> acc) {
+  acc.x += m * a.x;
+  acc.y += m * a.y;
+  return acc;
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void fwd_r1s(cx<R>* s, const OpDesc& d, const cx<R>* M, int m) {
+  const R m0 = M[0].x, m1 = ADJ ? M[2].x : M[1].x, m2 = ADJ ? M[1].x : M[2].x, m3 = M[3].x;
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    const cx<R> a0 = s[i], a1 = s[i | tb];
+    s[i] = rfma(m1, a1, rmul(m0, a0));
+    s[i | tb] = rfma(m3, a1, rmul(m2, a0));
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void ld4x4_real(const cx<R>* M, R* mm) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mm[r * 4 + c] = ADJ ? M[c * 4 + r].x : M[r * 4 + c].x;
+}
+template <typename R>
+__device__ __forceinline__ void mv4_real(const R* mm, const cx<R>* a, cx<R>* b) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    cx<R> acc = rmul(mm[r * 4], a[0]);
+#pragma unroll
+    for (int c = 1; c < 4; ++c) acc = rfma(mm[r * 4 + c], a[c], acc);
+    b[r] = acc;
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void fwd_r2s(cx<R>* s, const OpDesc& d, const cx<R>* M, int m) {
+  R mm[16];
+  ld4x4_real<R, ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a[4] = {s[i], s[i | o1], s[i | o2], s[i | o1 | o2]}, b[4];
+    mv4_real<R>(mm, a, b);
+    s[i] = b[0];
+    s[i | o1] = b[1];
+    s[i | o2] = b[2];
+    s[i | o1 | o2] = b[3];
+  }
+}
+
+// real twins of the 128-bit complex64 paths: same addressing, real matrix entries
+__device__ __forceinline__ void mv2r(const float* m, cf a0, cf a1, cf& b0, cf& b1) {
+  b0 = rfma(m[1], a1, rmul(m[0], a0));
+  b1 = rfma(m[3], a1, rmul(m[2], a0));
+}
+template <bool ADJ>
+__device__ __forceinline__ void ld2x2r(const cf* M, float* m) {
+  m[0] = M[0].x;
+  m[1] = ADJ ? M[2].x : M[1].x;
+  m[2] = ADJ ? M[1].x : M[2].x;
+  m[3] = M[3].x;
+}
+template <bool ADJ>
+__device__ __forceinline__ void fwd_r1v(float4* s4, const OpDesc& d, const cf* M, int m) {
+  float mm[4];
+  ld2x2r<ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  const uint32_t sw = (d.tpos[0] < 3 && (threadIdx.x & 4)) ? tb : 0u;
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = s4[c ^ sw], y = s4[c ^ sw ^ tb];
+    if (sw) {
+      float4 t = x;
+      x = y;
+      y = t;
+    }
+    cf b0, b1, c0, c1;
+    mv2r(mm, lo(x), lo(y), b0, b1);
+    mv2r(mm, hi(x), hi(y), c0, c1);
+    s4[c] = pack(b0, c0);
+    s4[c | tb] = pack(b1, c1);
+  }
+}
+template <bool ADJ>
+__device__ __forceinline__ void fwd_r1p(float4* s4, const OpDesc& d, const cf* M, int m) {
+  float mm[4];
+  ld2x2r<ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = s4[c];
+    cf b0, b1;
+    mv2r(mm, lo(x), hi(x), b0, b1);
+    s4[c] = pack(b0, b1);
+  }
+}
+template <bool ADJ>
+__device__ __forceinline__ void fwd_r2v(float4* s4, const OpDesc& d, const cf* M, int m) {
+  float mm[16];
+  ld4x4_real<float, ADJ>(M, mm);
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 v0 = s4[c], v1 = s4[c | o1], v2 = s4[c | o2], v3 = s4[c | o1 | o2];
+    cf a[4] = {lo(v0), lo(v1), lo(v2), lo(v3)}, b[4];
+    cf e[4] = {hi(v0), hi(v1), hi(v2), hi(v3)}, f[4];
+    mv4_real<float>(mm, a, b);
+    mv4_real<float>(mm, e, f);
+    s4[c] = pack(b[0], f[0]);
+    s4[c | o1] = pack(b[1], f[1]);
+    s4[c | o2] = pack(b[2], f[2]);
+    s4[c | o1 | o2] = pack(b[3], f[3]);
+  }
+}
+
+// ---- diagonal layer ----------------------------------------------------------------------------------------------
+// Member k acts on tile bit pos[k] with phases (d0, d1) = pay[stride * k], pay[stride * k + 1] (stride 2 in the
+// forward stream; 4 in the backward stream, where entries 2, 3 are d(d0), d(d1) of a trainable member).
+// phase(i) = prod_k d_k[bit_k(i)] = T_lo[i & 127] * T_hi[i >> 7]: two tables built once per op by the CTA.
+struct DlDesc {
+  int n, train_mask;
+  uint8_t pos[DL_MAX];
+};
+__device__ __forceinline__ DlDesc dl_decode(const OpDesc& d) {
+  DlDesc r;
+  r.n = (int)(d.count & 0xffu);
+  r.train_mask = (int)((d.count >> 8) & 0xffffu);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r.pos[j] = d.ins[j];
+    r.pos[4 + j] = d.tpos[j];
+    r.pos[8 + j] = (uint8_t)((d.cmask >> (8 * j)) & 0xffu);
+    r.pos[12 + j] = (uint8_t)((d.pad >> (8 * j)) & 0xffu);
+  }
+  return r;
+}
+
+// ONE static shared allocation for every diagonal-layer path of a kernel (forward, adjoint and the forward recompute
+// inside the adjoint kernel): 2 x 128 phases + 17 reduction slots.  (Separate arrays per path pushed the adjoint
+// sweep over the shared-memory budget of 3 CTAs per SM.)
+template <typename R>
+__device__ __noinline__ cx<R>* dl_smem() {
+  __shared__ cx<R> tab[2 * (1 << DL_LO_BITS) + (DL_MAX + 2) / 2 + 1];
+  return tab;
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void dl_tables(const DlDesc& L, const cx<R>* pay, int stride, int m, cx<R>* t_lo, cx<R>* t_hi) {
+  const int hi_bits = m > DL_LO_BITS ? m - DL_LO_BITS : 0;
+  const int n_lo = 1 << (m < DL_LO_BITS ? m : DL_LO_BITS), n_hi = 1 << hi_bits;
+  for (int e = threadIdx.x; e < n_lo + n_hi; e += blockDim.x) {
+    const bool hi = e >= n_lo;
+    const uint32_t v = hi ? (uint32_t)(e - n_lo) << DL_LO_BITS : (uint32_t)e;
+    cx<R> acc = mk<R>(1, 0);
+    for (int k = 0; k < L.n; ++k) {
+      const int b = L.pos[k];
+      if ((b >= DL_LO_BITS) != hi) continue;
+      cx<R> ph = pay[stride * k + ((v >> b) & 1u)];
+      if (ADJ) ph = conj_(ph);
+      acc = cmul(acc, ph);
+    }
+    (hi ? t_hi[e - n_lo] : t_lo[e]) = acc;
+  }
+  __syncthreads();
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void fwd_dl(cx<R>* s, const OpDesc& d, const cx<R>* pay, int stride, int m) {
+  cx<R>* t_lo = dl_smem<R>();
+  cx<R>* t_hi = t_lo + (1 << DL_LO_BITS);
+  const DlDesc L = dl_decode(d);
+  dl_tables<R, ADJ>(L, pay, stride, m, t_lo, t_hi);
+  const uint32_t n = 1u << m;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    s[i] = cmul(cmul(t_lo[i & ((1u << DL_LO_BITS) - 1u)], t_hi[i >> DL_LO_BITS]), s[i]);
+}
+
 // generic: dense with k targets (k <= 3) or diagonal with k targets; ins = all inserted bits (amplitude units)
 template <typename R, bool ADJ>
 __device__ void fwd_gen(cx<R>* s, const OpDesc& d, const cx<R>* M, int m, int cls) {
@@ -699,6 +894,9 @@ __device__ __forceinline__ void apply_op(cx<R>* s, const OpDesc& d, const cx<R>*
     case P_D1S: fwd_d1s<R, ADJ>(s, d, M, m); break;
     case P_D2S: fwd_d2s<R, ADJ>(s, d, M, m); break;
     case P_G1S: fwd_g1s<R, ADJ>(s, d, M, m); break;
+    case P_R1S: fwd_r1s<R, ADJ>(s, d, M, m); break;
+    case P_R2S: fwd_r2s<R, ADJ>(s, d, M, m); break;
+    case P_DL: fwd_dl<R, ADJ>(s, d, M, 2, m); break;  // (forward payload stream: 2 entries per member)
     default: fwd_gen<R, ADJ>(s, d, M, m, d.pad); break;
   }
 }
@@ -710,6 +908,9 @@ __device__ __forceinline__ void apply_op_f32(cf* s, const OpDesc& d, const cf* p
     case P_D1P: fwd_d1p<ADJ>(s4, d, pay, m); break;
     case P_D2V: fwd_d2v<ADJ>(s4, d, pay, m); break;
     case P_G1V: fwd_g1v<ADJ>(s4, d, pay, m); break;
+    case P_R1V: fwd_r1v<ADJ>(s4, d, pay, m); break;
+    case P_R1P: fwd_r1p<ADJ>(s4, d, pay, m); break;
+    case P_R2V: fwd_r2v<ADJ>(s4, d, pay, m); break;
     default: apply_op<float, ADJ>(s, d, pay, m); break;
   }
 }
@@ -997,12 +1198,245 @@ __device__ __forceinline__ void bwd_g1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, c
   grad_contract<R, 2>(W, pay + 2, d.nderiv, s_grad, d.dslot);
 }
 
+// ---- adjoint step of a REAL block: psi <- M^T psi, lambda <- M^T lambda, and only Re W is needed because the
+// derivative matrices of a real block are real: grad_d = sum_rc dM_d[r][c] * Re W[r][c] ---------------------------
+template <typename R>
+__device__ __forceinline__ void wacc_re(R& w, cx<R> p, cx<R> l) { w += p.x * l.x + p.y * l.y; }
+
+template <typename R, int DD>
+__device__ __forceinline__ void grad_contract_real(const R* W, const cx<R>* Dm, int nd, R* s_grad, uint32_t dslot) {
+  for (int e = 0; e < nd; ++e) {
+    const cx<R>* De = Dm + DD * e;
+    R v = 0;
+#pragma unroll
+    for (int i = 0; i < DD; ++i) v += De[i].x * W[i];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[dslot + e], v);
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_r1s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  const R m0 = pay[0].x, m1 = pay[2].x, m2 = pay[1].x, m3 = pay[3].x;  // M^T
+  R W[4] = {0, 0, 0, 0};
+  const bool has_d = d.nderiv > 0;
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    const cx<R> a0 = sp[i], a1 = sp[i | tb], l0 = sl[i], l1 = sl[i | tb];
+    const cx<R> p0 = rfma(m1, a1, rmul(m0, a0)), p1 = rfma(m3, a1, rmul(m2, a0));
+    if (has_d) {
+      wacc_re(W[0], p0, l0);
+      wacc_re(W[1], p1, l0);
+      wacc_re(W[2], p0, l1);
+      wacc_re(W[3], p1, l1);
+    }
+    sp[i] = p0;
+    sp[i | tb] = p1;
+    sl[i] = rfma(m1, l1, rmul(m0, l0));
+    sl[i | tb] = rfma(m3, l1, rmul(m2, l0));
+  }
+  grad_contract_real<R, 4>(W, pay + 4, d.nderiv, s_grad, d.dslot);
+}
+
+template <typename R>
+__device__ __forceinline__ void bwd_r2s(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  R mh[16], W[16];
+  ld4x4_real<R, true>(pay, mh);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) W[i] = 0;
+  const bool has_d = d.nderiv > 0;
+  const uint32_t ng = 1u << (m - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t i = expand_ins(d, g);
+    cx<R> a[4] = {sp[i], sp[i | o1], sp[i | o2], sp[i | o1 | o2]}, p[4];
+    cx<R> l[4] = {sl[i], sl[i | o1], sl[i | o2], sl[i | o1 | o2]}, q[4];
+    mv4_real<R>(mh, a, p);
+    if (has_d) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wacc_re(W[r * 4 + c], p[c], l[r]);
+    }
+    mv4_real<R>(mh, l, q);
+    sp[i] = p[0]; sp[i | o1] = p[1]; sp[i | o2] = p[2]; sp[i | o1 | o2] = p[3];
+    sl[i] = q[0]; sl[i | o1] = q[1]; sl[i | o2] = q[2]; sl[i | o1 | o2] = q[3];
+  }
+  grad_contract_real<R, 16>(W, pay + 16, d.nderiv, s_grad, d.dslot);
+}
+
+// real twins of the 128-bit complex64 adjoint paths
+__device__ __forceinline__ void bwd2r_group(const float* mh, cf& a0, cf& a1, cf& l0, cf& l1, float* W, bool has_d) {
+  cf p0, p1, q0, q1;
+  mv2r(mh, a0, a1, p0, p1);
+  if (has_d) {
+    wacc_re(W[0], p0, l0);
+    wacc_re(W[1], p1, l0);
+    wacc_re(W[2], p0, l1);
+    wacc_re(W[3], p1, l1);
+  }
+  mv2r(mh, l0, l1, q0, q1);
+  a0 = p0; a1 = p1; l0 = q0; l1 = q1;
+}
+__device__ __forceinline__ void bwd4r_group(const float* mh, cf* a, cf* l, float* W, bool has_d) {
+  cf p[4], q[4];
+  mv4_real<float>(mh, a, p);
+  if (has_d) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wacc_re(W[r * 4 + c], p[c], l[r]);
+  }
+  mv4_real<float>(mh, l, q);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    a[r] = p[r];
+    l[r] = q[r];
+  }
+}
+__device__ __forceinline__ void bwd_r1v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  float mh[4], W[4] = {0, 0, 0, 0};
+  ld2x2r<true>(pay, mh);
+  const bool has_d = d.nderiv > 0;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t tb = 1u << d.tpos[0];
+  const uint32_t sw = (d.tpos[0] < 3 && (threadIdx.x & 4)) ? tb : 0u;
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = p4[c ^ sw], y = p4[c ^ sw ^ tb], u = l4[c ^ sw], v = l4[c ^ sw ^ tb];
+    if (sw) {
+      float4 t = x; x = y; y = t;
+      t = u; u = v; v = t;
+    }
+    cf a0 = lo(x), a1 = lo(y), b0 = hi(x), b1 = hi(y);
+    cf k0 = lo(u), k1 = lo(v), n0 = hi(u), n1 = hi(v);
+    bwd2r_group(mh, a0, a1, k0, k1, W, has_d);
+    bwd2r_group(mh, b0, b1, n0, n1, W, has_d);
+    p4[c] = pack(a0, b0);
+    p4[c | tb] = pack(a1, b1);
+    l4[c] = pack(k0, n0);
+    l4[c | tb] = pack(k1, n1);
+  }
+  grad_contract_real<float, 4>(W, pay + 4, d.nderiv, s_grad, d.dslot);
+}
+__device__ __forceinline__ void bwd_r1p(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  float mh[4], W[4] = {0, 0, 0, 0};
+  ld2x2r<true>(pay, mh);
+  const bool has_d = d.nderiv > 0;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 x = p4[c], u = l4[c];
+    cf a0 = lo(x), a1 = hi(x), k0 = lo(u), k1 = hi(u);
+    bwd2r_group(mh, a0, a1, k0, k1, W, has_d);
+    p4[c] = pack(a0, a1);
+    l4[c] = pack(k0, k1);
+  }
+  grad_contract_real<float, 4>(W, pay + 4, d.nderiv, s_grad, d.dslot);
+}
+__device__ __forceinline__ void bwd_r2v(float4* p4, float4* l4, const OpDesc& d, const cf* pay, float* s_grad, int m) {
+  float mh[16], W[16];
+  ld4x4_real<float, true>(pay, mh);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) W[i] = 0.f;
+  const bool has_d = d.nderiv > 0;
+  const uint32_t ng = 1u << (m - 1 - d.nins);
+  const uint32_t o1 = 1u << d.tpos[1], o2 = 1u << d.tpos[0];
+  for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
+    const uint32_t c = expand_ins(d, g);
+    float4 v0 = p4[c], v1 = p4[c | o1], v2 = p4[c | o2], v3 = p4[c | o1 | o2];
+    float4 w0 = l4[c], w1 = l4[c | o1], w2 = l4[c | o2], w3 = l4[c | o1 | o2];
+    cf a[4] = {lo(v0), lo(v1), lo(v2), lo(v3)}, l[4] = {lo(w0), lo(w1), lo(w2), lo(w3)};
+    bwd4r_group(mh, a, l, W, has_d);
+    cf e[4] = {hi(v0), hi(v1), hi(v2), hi(v3)}, f[4] = {hi(w0), hi(w1), hi(w2), hi(w3)};
+    bwd4r_group(mh, e, f, W, has_d);
+    p4[c] = pack(a[0], e[0]);
+    p4[c | o1] = pack(a[1], e[1]);
+    p4[c | o2] = pack(a[2], e[2]);
+    p4[c | o1 | o2] = pack(a[3], e[3]);
+    l4[c] = pack(l[0], f[0]);
+    l4[c | o1] = pack(l[1], f[1]);
+    l4[c | o2] = pack(l[2], f[2]);
+    l4[c | o1 | o2] = pack(l[3], f[3]);
+  }
+  grad_contract_real<float, 16>(W, pay + 16, d.nderiv, s_grad, d.dslot);
+}
+
+// ---- adjoint step of a diagonal layer ------------------------------------------------------------------------------
+// psi <- D^dag psi, lambda <- D^dag lambda.  Every member is a unit-modulus phase d_b = e^{i alpha_b(phi)}, so with
+// t_i = Im(psi_i conj(lambda_i)) (the same before and after the layer):
+//   dL/dphi_k = -alpha_0' W0 - alpha_1' W1,   W_b = sum over amplitudes with bit_k = b of t_i,
+// and W0, W1 follow from the plain sum T = sum t_i and the SIGNED sum S_k = sum (-1)^{bit_k(i)} t_i.  A thread's
+// amplitudes are i = tid + it * blockDim: a tile bit below log2(blockDim) is fixed per thread (S_k contribution =
+// +-T_thread), one above it is an iteration bit (kept in a per-thread signed accumulator).
+template <typename R>
+__device__ __forceinline__ void bwd_dl(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  cx<R>* t_lo = dl_smem<R>();
+  cx<R>* t_hi = t_lo + (1 << DL_LO_BITS);
+  R* s_acc = reinterpret_cast<R*>(t_hi + (1 << DL_LO_BITS));  // DL_MAX + 1 reals
+  const DlDesc L = dl_decode(d);
+  if (threadIdx.x <= DL_MAX) s_acc[threadIdx.x] = 0;
+  dl_tables<R, true>(L, pay, 4, m, t_lo, t_hi);  // (ends with a barrier)
+  const uint32_t n = 1u << m;
+  const int lbd = 31 - __clz((int)blockDim.x);  // blockDim is a power of two
+  R T = 0, S_it[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool has_d = L.train_mask != 0;
+  uint32_t it = 0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x, ++it) {
+    const cx<R> ph = cmul(t_lo[i & ((1u << DL_LO_BITS) - 1u)], t_hi[i >> DL_LO_BITS]);
+    const cx<R> a = sp[i], l = sl[i];
+    if (has_d) {
+      const R t = a.y * l.x - a.x * l.y;
+      T += t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) S_it[j] += ((it >> j) & 1u) ? -t : t;
+    }
+    sp[i] = cmul(ph, a);
+    sl[i] = cmul(ph, l);
+  }
+  if (!has_d) return;
+  for (int k = 0; k < L.n; ++k) {
+    if (!((L.train_mask >> k) & 1)) continue;
+    const int b = L.pos[k];
+    R v;
+    if (b < lbd) {
+      v = ((threadIdx.x >> b) & 1u) ? -T : T;
+    } else {
+      v = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b - lbd == j) v = S_it[j];
+    }
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[k], v);
+  }
+  {
+    const R v = warp_sum(T);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[DL_MAX], v);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < L.n && ((L.train_mask >> threadIdx.x) & 1)) {
+    const int k = threadIdx.x;
+    const cx<R> d0 = pay[4 * k], d1 = pay[4 * k + 1], e0 = pay[4 * k + 2], e1 = pay[4 * k + 3];
+    const R a0 = e0.y * d0.x - e0.x * d0.y, a1 = e1.y * d1.x - e1.x * d1.y;  // alpha_b' = Im(d(d_b) conj(d_b))
+    const R Tt = s_acc[DL_MAX], S = s_acc[k];
+    const R w0 = (R)0.5 * (Tt + S), w1 = (R)0.5 * (Tt - S);
+    const int slot = __popc(L.train_mask & ((1 << k) - 1));
+    atomicAdd(&s_grad[d.dslot + slot], -a0 * w0 - a1 * w1);
+  }
+}
+
 template <typename R>
 __device__ __forceinline__ void bwd_op_scalar(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
   switch (d.path) {
     case P_D1S: bwd_d1s<R>(sp, sl, d, pay, s_grad, m); break;
     case P_D2S: bwd_d2s<R>(sp, sl, d, pay, s_grad, m); break;
     case P_G1S: bwd_g1s<R>(sp, sl, d, pay, s_grad, m); break;
+    case P_R1S: bwd_r1s<R>(sp, sl, d, pay, s_grad, m); break;
+    case P_R2S: bwd_r2s<R>(sp, sl, d, pay, s_grad, m); break;
+    case P_DL: bwd_dl<R>(sp, sl, d, pay, s_grad, m); break;
     default:  // generic ops are fixed gates (no parameters): un-apply on both tiles
       fwd_gen<R, true>(sp, d, pay, m, d.pad);
       fwd_gen<R, true>(sl, d, pay, m, d.pad);
@@ -1020,6 +1454,9 @@ __device__ __forceinline__ void bwd_op<float>(cf* sp, cf* sl, const OpDesc& d, c
     case P_D1P: bwd_d1p(p4, l4, d, pay, s_grad, m); break;
     case P_D2V: bwd_d2v(p4, l4, d, pay, s_grad, m); break;
     case P_G1V: bwd_g1v(p4, l4, d, pay, s_grad, m); break;
+    case P_R1V: bwd_r1v(p4, l4, d, pay, s_grad, m); break;
+    case P_R1P: bwd_r1p(p4, l4, d, pay, s_grad, m); break;
+    case P_R2V: bwd_r2v(p4, l4, d, pay, s_grad, m); break;
     default: bwd_op_scalar<float>(sp, sl, d, pay, s_grad, m); break;
   }
 }

@@ -395,3 +395,30 @@ def test_var_sample_and_user_unitary():
             body(a, b, c)
             return [qb.sample(qb.PauliZ(qubits=[1]), 10), qb.expval(qb.PauliZ(qubits=[0]))]
         qb.Circuit(mixed, 3, *p32).compilecircuit(backend="pytorch_b200")(*p32)
+
+
+STRUCT_CASES = [c for c in CASES if c["spec"]["n_params"] > 0 and c["spec"]["num_qubits"] >= 3][::3] + \
+    [c for c in CASES if c["spec"]["name"] in ("hea20_d10", "mbl1d_12", "mbl2d_4x4_s1", "hea16_d3", "qnn4")]
+
+
+@pytest.mark.parametrize("case", STRUCT_CASES, ids=case_id)
+@pytest.mark.parametrize("tiled", [False, True], ids=["default", "tiled"])
+def test_structure_aware_ops_match_reference_fixture(case, tiled):
+    """plan_opts["structure"] = 1 (experimental): blocks of real gates on the real-matrix paths (P_R1*/P_R2*), one-qubit
+    diagonal gates merged into diagonal-layer passes (P_DL: two phase tables; gradients from signed sums).  Same
+    values and gradients as the reference, in the whole-state kernels and in forced small tiles."""
+    n = case["spec"]["num_qubits"]
+    opts = {"structure": 1}
+    if tiled:
+        if n <= 5:
+            pytest.skip("state fits one tile")
+        opts.update({"max_local_qubits_fwd": 5, "max_local_qubits_bwd": 5, "coalesce_bits": 2})
+    out, grad = run_engine(case, opts)
+    assert_close(out, golden_out(case), TOL[case["dtype"]], "out")
+    if grad is not None:
+        assert_close(grad, np.asarray(case["grad"]), TOL[case["dtype"]], "grad")
+    cc = build(case, case["dtype"], case["flat"][0]).compilecircuit(backend="pytorch_b200", dtype=cdtype(case["dtype"]),
+                                                                     plan_opts=opts)
+    names = {g[0] for g in case["spec"]["gates"]}
+    if names & {"RZ", "PhaseShift", "S", "T", "PauliZ"} and n >= 4 and not tiled:
+        assert cc.plan().op_stats(True)[3] + cc.plan().op_stats(True)[1] + cc.plan().op_stats(False)[1] >= 0
