@@ -733,7 +733,7 @@ def measure_c5(steps, warmup, device, dist, do_cpu=False, greedy_plan=False, n_a
                   float((host_amp - amp.cpu()).abs().max() / amp.abs().max().cpu()), 1e-6)
 
     # ---- per-step table of one slice group (tq_tn_profile: CUDA events around every step) and the roofline
-    rows = cc._tn.amplitude_profile(torch.zeros((1, 0), device=device), bits[0].tolist(), 0)
+    rows, amps_per_seq, sets_per_seq, pin_ms = cc._tn.amplitudes_profile(torch.zeros((1, 0), device=device), bits, 0)
     per_slice = [r for r in rows if r["per_slice"]]
     slice_ms = sum(r["ms"] for r in per_slice)
     once_ms = sum(r["ms"] for r in rows if not r["per_slice"])
@@ -791,12 +791,13 @@ def measure_c5(steps, warmup, device, dist, do_cpu=False, greedy_plan=False, n_a
                 "flops of all pairwise steps x 64 slices by the timed region (launch gaps, HBM-bound steps, the "
                 "all-reduce included).",
     }
-    res["workload"] = (f"{C5_DESC}; slices in groups of {group} (one launch sequence per group), width {plan.width}, "
-                       f"{plan.n_steps} pairwise steps, {flops_amp:.3e} flop per amplitude"
+    res["workload"] = (f"{C5_DESC}; {sets_per_seq} slices per launch sequence ({group} slices of each of {amps_per_seq} "
+                       f"amplitudes), width {plan.width}, {plan.n_steps} pairwise steps, {flops_amp:.3e} flop per amplitude"
                        + (" (plain greedy tree, no subtree reconfiguration)" if greedy_plan else ""))
-    res["per_slice_ms_profiled"] = slice_ms / group
-    res["once_per_call_ms_profiled"] = once_ms + float(getattr(plan, "last_pinned_pack_ms", 0.0))
-    res["slices_per_launch_sequence"] = group
+    res["per_slice_ms_profiled"] = slice_ms / sets_per_seq
+    res["once_per_launch_sequence_ms_profiled"] = once_ms + pin_ms
+    res["slices_per_launch_sequence"] = sets_per_seq
+    res["amplitudes_per_launch_sequence"] = amps_per_seq
     res["steps_per_slice"] = len(per_slice)
     res["steps_once_per_call"] = len(rows) - len(per_slice)
     res["step_table"] = table
@@ -914,7 +915,7 @@ def main():
             "dtype": main_res["dtype"], "data": "synthetic",
             "config": config_of(wl, C5_DESC if wl == "c5" else main_res["workload"]),
             "engine": {k: main_res[k] for k in ("workload", "ms_per_amplitude", "slices_per_launch_sequence",
-                                                "per_slice_ms_profiled", "once_per_call_ms_profiled", "steps_per_slice",
+                                                "per_slice_ms_profiled", "once_per_launch_sequence_ms_profiled", "amplitudes_per_launch_sequence", "steps_per_slice",
                                                 "steps_once_per_call", "planner", "amplitude_0", "parity",
                                                 "sets_per_gpu", "e2e_python") if k in main_res},
             "parallelism": (f"slices sharded over {world} GPU(s), one all-reduce per step" if wl == "c5" else

@@ -439,6 +439,7 @@ class TNExecutor:
         strides = tab["stride"]
         any_b = bool((strides != 0).any())
         keep = [gm, am, red_buf]
+        self._amp_stacked = {}      # input id -> [G, entries] re-laid-out operand of the last call (slice groups)
         if grp is not None:
             # slice group: every combination of the grouped indices is one "set" of the plan.  The few operands that
             # carry a grouped index are re-laid out as [G sets][tensor without those indices] (tiny gate tensors).
@@ -464,6 +465,7 @@ class TNExecutor:
                         sel[ax] = (sset >> gi) & 1
                     rows.append(full[tuple(sel)].reshape(-1))
                 stacked = torch.stack(rows).contiguous()
+                self._amp_stacked[t] = stacked
                 keep.append(stacked)
                 ptrs[t] = stacked.data_ptr()
                 strides[t] = stacked.shape[1]
@@ -490,12 +492,12 @@ class TNExecutor:
 
     def _slice_group(self, net, info, batched):
         """hyper_opt["slice_batch"] = g: 2^g slices go through the device together as the batch dimension of ONE
-        launch sequence (default 4 when no gate is batched over parameter sets, fewer when ranks would go idle; 0 = one
+        launch sequence (default 5 when no gate is batched over parameter sets, fewer when ranks would go idle; 0 = one
         slice at a time).  A slice
         of a 40-qubit amplitude is ~20 launches of 20-90 us with one tile per SM: grouping slices gives every launch
         several tiles per SM (prologue / epilogue overlap inside the persistent kernels) and divides the launch count.
         -> None or {"indices": grouped sliced indices, "rest": the others, "axes": {tensor: [(axis, group bit)]}}."""
-        g = int(self.ho.get("slice_batch", 4))
+        g = int(self.ho.get("slice_batch", 5))
         # memory: the per-set arena is a few times the largest intermediate (2^width entries); keep a group's
         # largest tensors at <= 2^28 entries together (2 GiB complex64) unless the caller asked for a size
         if "slice_batch" not in self.ho:
@@ -547,37 +549,112 @@ class TNExecutor:
             torch.distributed.all_reduce(torch.view_as_real(out))
         return out.reshape(-1).expand(B) if not any_b else out.reshape(-1)
 
-    def amplitudes(self, flat: torch.Tensor, bits_batch, slice_range=None):
-        """<b_a| U(params) |0...0> for a batch of bitstrings b_a ([A, n] array of 0/1) -> complex [A] (or [A, B] when
-        the gates are batched over parameter sets).  The gate operands are built once, only the closing caps change
-        per bitstring.  Every rank contracts its slice range of every amplitude; the partial sums of the whole batch
-        are combined with ONE all-reduce (contract_parallel)."""
+    def _amp_batch(self, n_amps: int, group: int, width: int) -> int:
+        """Amplitudes that share one launch sequence (hyper_opt["amplitude_batch"]; default: as many as keep
+        amplitudes x slice-group members <= 2^(28 - width) sets, the memory rule of the slice groups)."""
+        if "amplitude_batch" in self.ho:
+            return max(1, min(n_amps, int(self.ho["amplitude_batch"])))
+        cap = 1 << max(0, 28 - int(width))
+        return max(1, min(n_amps, cap // max(1, group)))
+
+    def _multi_plan(self, dev, net, info, grp, closing):
+        """Plan of the amplitude network whose closing caps differ per set: sets = amplitudes x slice-group members."""
+        plans = self.__dict__.setdefault("_amp_plans_multi", {})
+        didx = capi.device_index(dev)
+        if didx not in plans:
+            dt = capi.TQ_C64 if self.backend._cdtype == torch.complex64 else capi.TQ_C128
+            if grp is None:
+                inputs2, rest = net.inputs, info.sliced
+                batched2 = [bool(c) for c in closing]
+            else:
+                gset = set(grp["indices"])
+                inputs2 = [[ix for ix in t if ix not in gset] for t in net.inputs]
+                rest = grp["rest"]
+                batched2 = [bool(grp["axes"].get(t)) or bool(closing[t]) for t in range(len(net.inputs))]
+            with capi.on_device(didx):
+                plans[didx] = self._engine_opts(capi.TnPlan(inputs2, net.output, info.path, rest, batched2, dt))
+        return plans[didx]
+
+    def _amplitude_items(self, flat: torch.Tensor, bits_batch):
+        """Launch sequences of a batch of amplitudes: -> (plan, [(pointers, strides, sets, output rows)], output
+        tensor, workspace, workspace bytes, A, multi, grouped, any_b, keep-alive list)."""
         if torch.is_tensor(bits_batch):
             bits_batch = bits_batch.detach().cpu().numpy()
         bits_batch = np.asarray(bits_batch, dtype=np.int64).reshape(-1, self.n)
         A = bits_batch.shape[0]
-        plan, ptrs, strides, out0, ws, ws_bytes, any_b, _keep = self._amplitude_operands(flat, bits_batch[0])
+        plan1, ptrs1, strides1, out0, ws, ws_bytes, any_b, keep1 = self._amplitude_operands(flat, bits_batch[0])
         B = flat.shape[0]
-        grouped = getattr(self, "_amp_group", None) is not None
-        Bp = out0.shape[0] if grouped else B
+        net, info = self._amplitude_plan()[0], self._amplitude_plan()[1]
+        grp = getattr(self, "_amp_group", None)
+        grouped = grp is not None
+        G = out0.shape[0] if grouped else 1
+        dev = flat.device
+        cd = self.backend._cdtype
+        params_batched = any_b and not grouped       # gates batched over parameter sets: one amplitude at a time
+        Ab = 1 if params_batched else self._amp_batch(A, G, info.width)
+        multi = Ab > 1
+        tab = self._amplitude_plan()[3]
+        closing = tab["capq"] >= 0
+        plan = self._multi_plan(dev, net, info, grp, closing) if multi else plan1
+        chunks = [(a0, min(A, a0 + Ab)) for a0 in range(0, A, Ab)]
+        keep = list(keep1)
+        if multi:
+            sets_max = Ab * G
+            ws_bytes = plan.workspace_bytes(sets_max)
+            ws = getattr(self, "_amp_ws_multi", None)
+            if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+                ws = self._amp_ws_multi = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            base_ptrs, base_strides = ptrs1.copy(), strides1.copy()
+            for t, stacked in self._amp_stacked.items():       # [G, entries] -> [Ab * G, entries], set = a * G + m
+                rep = stacked.repeat(Ab, 1).contiguous()
+                keep.append(rep)
+                base_ptrs[t], base_strides[t] = rep.data_ptr(), rep.shape[1]
+            cap_ids = np.nonzero(closing)[0]
+            cap_q = tab["capq"][cap_ids]
+            out = torch.zeros((A, G), dtype=cd, device=dev)
+            chunk_args = []
+            for a0, a1 in chunks:
+                nb = a1 - a0
+                bits_dev = torch.as_tensor(bits_batch[a0:a1][:, cap_q], device=dev)              # [nb, n_caps]
+                caps = torch.nn.functional.one_hot(bits_dev, 2).to(cd)                             # [nb, n_caps, 2]
+                caps = caps.permute(1, 0, 2).unsqueeze(2).expand(-1, -1, G, -1).reshape(len(cap_ids), nb * G, 2)
+                caps = caps.contiguous()
+                keep.append(caps)
+                p, st = base_ptrs.copy(), base_strides.copy()
+                p[cap_ids] = caps.data_ptr() + np.arange(len(cap_ids), dtype=np.int64) * (nb * G * 2 * caps.element_size())
+                st[cap_ids] = 2
+                chunk_args.append((p, st, nb * G, out[a0:a1]))
+        else:
+            out = torch.zeros((A,) + tuple(out0.shape), dtype=out0.dtype, device=dev)
+            Bp = out0.shape[0] if grouped else B
+            chunk_args = [(self._patch_caps(ptrs1, bits_batch[a], dev), strides1, Bp, out[a]) for a in range(A)]
+        return plan, chunk_args, out, ws, ws_bytes, A, multi, grouped, any_b, keep
+
+    def amplitudes(self, flat: torch.Tensor, bits_batch, slice_range=None):
+        """<b_a| U(params) |0...0> for a batch of bitstrings b_a ([A, n] array of 0/1) -> complex [A] (or [A, B] when
+        the gates are batched over parameter sets).  The gate operands are built once.  Several amplitudes share one
+        launch sequence: the closing caps <b_a| become per-set operands and the plan's batch dimension runs over
+        (amplitude, slice-group member) — every launch then has the tiles of up to 32 slices, whatever the rank's
+        share of one amplitude's slices is.  Every rank contracts its slice range of every amplitude; the partial sums
+        of the whole batch are combined with ONE all-reduce (contract_parallel)."""
+        plan, chunk_args, out, ws, ws_bytes, A, multi, grouped, any_b, keep = self._amplitude_items(flat, bits_batch)
         dev = flat.device
         stream = torch.cuda.current_stream(dev).cuda_stream
         if slice_range is None:
             s0, s1, dist_on = self._slice_range(plan.n_slices)
         else:
             (s0, s1), dist_on = slice_range, False
-        out = torch.zeros((A,) + tuple(out0.shape), dtype=out0.dtype, device=dev)
-        overlap = A > 1 and s1 > s0 and bool(self.ho.get("overlap_prepare", True))
+        n_items = len(chunk_args)
+        overlap = n_items > 1 and s1 > s0 and bool(self.ho.get("overlap_prepare", True))
         with torch.cuda.device(dev):
             if not overlap:
-                for a in range(A):
+                for p, st, sets, o in chunk_args:
                     if s1 > s0:
-                        plan.contract(self._patch_caps(ptrs, bits_batch[a], dev), strides, Bp, s0, s1,
-                                      out[a].data_ptr(), ws.data_ptr(), ws_bytes, stream)
+                        plan.contract(p, st, sets, s0, s1, o.data_ptr(), ws.data_ptr(), ws_bytes, stream)
             else:
-                # Two workspaces, two streams: the once-per-call part of amplitude a + 1 (hundreds of tiny,
-                # latency-bound steps and the pinned operand images) runs on a side stream while the slices of
-                # amplitude a (throughput-bound GEMMs) run on the caller's stream.
+                # Two workspaces, two streams: the once-per-call part of item i + 1 (hundreds of tiny, latency-bound
+                # steps and the pinned operand images) runs on a side stream while the slices of item i
+                # (throughput-bound GEMMs) run on the caller's stream.
                 ws2 = getattr(self, "_amp_ws2", None)
                 if ws2 is None or ws2.numel() < ws_bytes or ws2.device != dev:
                     ws2 = self._amp_ws2 = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -586,27 +663,28 @@ class TNExecutor:
                     side = self._amp_side_stream = torch.cuda.Stream(device=dev)
                 wss = (ws, ws2)
                 main = torch.cuda.current_stream(dev)
-                ptr_tabs = [self._patch_caps(ptrs, bits_batch[a], dev) for a in range(A)]
-                ev_prep = [torch.cuda.Event() for _ in range(A)]
-                ev_done = [torch.cuda.Event() for _ in range(A)]
-                side.wait_stream(main)            # gate operands / zeroed output are ready
-                plan.contract_prepare(ptr_tabs[0], strides, Bp, s0, wss[0].data_ptr(), ws_bytes, side.cuda_stream)
+                ev_prep = [torch.cuda.Event() for _ in range(n_items)]
+                ev_done = [torch.cuda.Event() for _ in range(n_items)]
+                side.wait_stream(main)            # gate operands / caps / zeroed output are ready
+                p, st, sets, _o = chunk_args[0]
+                plan.contract_prepare(p, st, sets, s0, wss[0].data_ptr(), ws_bytes, side.cuda_stream)
                 ev_prep[0].record(side)
-                for a in range(A):
-                    main.wait_event(ev_prep[a])
-                    plan.contract_slices(ptr_tabs[a], strides, Bp, s0, s1, out[a].data_ptr(), wss[a & 1].data_ptr(),
-                                         ws_bytes, stream)
-                    ev_done[a].record(main)
-                    if a + 1 < A:
-                        if a >= 1:
-                            side.wait_event(ev_done[a - 1])     # workspace (a + 1) & 1 is free again
-                        plan.contract_prepare(ptr_tabs[a + 1], strides, Bp, s0, wss[(a + 1) & 1].data_ptr(), ws_bytes,
+                for i, (p, st, sets, o) in enumerate(chunk_args):
+                    main.wait_event(ev_prep[i])
+                    plan.contract_slices(p, st, sets, s0, s1, o.data_ptr(), wss[i & 1].data_ptr(), ws_bytes, stream)
+                    ev_done[i].record(main)
+                    if i + 1 < n_items:
+                        if i >= 1:
+                            side.wait_event(ev_done[i - 1])     # workspace (i + 1) & 1 is free again
+                        pn, stn, setsn, _on = chunk_args[i + 1]
+                        plan.contract_prepare(pn, stn, setsn, s0, wss[(i + 1) & 1].data_ptr(), ws_bytes,
                                               side.cuda_stream)
-                        ev_prep[a + 1].record(side)
-                ws2.record_stream(side)
-                ws.record_stream(side)
-        if grouped:
+                        ev_prep[i + 1].record(side)
+        if multi:
             out = out.sum(1, keepdim=True)       # the grouped indices are summed like every sliced index
+            any_b = False
+        elif grouped:
+            out = out.sum(1, keepdim=True)
             any_b = False
         if dist_on:
             if plan.n_slices == 1 and torch.distributed.get_rank() != 0:
@@ -651,6 +729,25 @@ class TNExecutor:
                          "per_slice": bool(plan.step_flags(s) & 1), "per_set": bool(plan.step_flags(s) & 2),
                          "sets": Bp, "ms": float(ms[s, 0]), "pack_ms": float(ms[s, 1])})
         return rows
+
+    def amplitudes_profile(self, flat: torch.Tensor, bits_batch, slice_id=0):
+        """Per-step timing of ONE launch sequence of ``amplitudes(bits_batch)`` (its first chunk of amplitudes, plan
+        slice ``slice_id``): -> (rows as amplitude_profile, amplitudes in that launch sequence, sets)."""
+        plan, chunk_args, out, ws, ws_bytes, A, multi, grouped, _, _keep = self._amplitude_items(flat, bits_batch)
+        dev = flat.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p, st, sets, o = chunk_args[0]
+        scratch = torch.zeros_like(o)
+        with torch.cuda.device(dev):
+            ms = plan.profile(p, st, sets, slice_id, scratch.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+        rows = []
+        for s in range(plan.n_steps):
+            stp = plan.step(s)
+            rows.append({"step": s, "k": stp[2], "m": stp[3], "n": stp[4], "b": stp[5], "kernel": plan.step_kernel(s),
+                         "per_slice": bool(plan.step_flags(s) & 1), "per_set": bool(plan.step_flags(s) & 2),
+                         "sets": sets, "ms": float(ms[s, 0]), "pack_ms": float(ms[s, 1])})
+        G = o.shape[1] if (multi and o.dim() > 1) else (sets if grouped else 1)
+        return rows, max(1, sets // max(1, G)), sets, float(getattr(plan, "last_pinned_pack_ms", 0.0))
 
     def run(self, flat: torch.Tensor) -> torch.Tensor:
         """Values (and, through ``backend.B200Execute``, gradients: reverse mode through the same contraction trees

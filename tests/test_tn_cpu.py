@@ -114,7 +114,8 @@ def test_slice_groups_partition_and_sum():
     assert grp is not None and len(grp["indices"]) == 2
     assert sorted(grp["indices"] + grp["rest"]) == sorted(info.sliced)
     ex._amp_group = grp
-    # default size: 2^4 slices, fewer when the network is wide (memory) — never for parameter-batched operands
+    # default size: up to 2^5 slices (here all 16), fewer when the network is wide (memory) — never for
+    # parameter-batched operands
     ex.ho = {}
     assert len(ex._slice_group(net, info, [False] * len(net.inputs))["indices"]) == 4
     wide = lambda w: planner.PathInfo(info.path, info.sliced, w, info.flops_log2, info.n_steps)
