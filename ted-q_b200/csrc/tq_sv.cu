@@ -87,6 +87,7 @@ struct tq_plan {
   int64_t out_reals = 0;
   std::vector<zc> fixed;
   bool fwd_full = false, bwd_full = false, sv_ok = true;
+  bool structure = false;  // tq_plan_opts.structure: the sweeps run the kernel instantiations with the real / diagonal-layer paths
   int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256, fuse = 1;
   std::vector<Sweep> fwd, bwd;
   int n_ops[2] = {0, 0}, n_dl[2] = {0, 0}, n_dl_members[2] = {0, 0}, n_real[2] = {0, 0};  // emitted ops per direction
@@ -534,6 +535,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   p->m_b = m_b;
   p->coalesce = coalesce;
   p->fuse = fuse;
+  p->structure = diag_layers;
   auto pick_threads = [&](int m) {
     if (threads > 0) return threads;
     int t = 1 << std::max(5, m - 3);
@@ -1225,8 +1227,13 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
     a.tiles_log2 = 0;
     a.flags = SW_INIT | SW_MEASURE | (L.has_psi ? SW_STORE : 0);
     size_t smem = ((size_t)sizeof(cx<R>) << n) + RING_BYTES + sizeof(R) * p->n_slots;
-    if ((rc = prep_kernel(k_sweep_fwd<R>, smem))) return rc;
-    k_sweep_fwd<R><<<(unsigned)B, p->threads_f, smem, st>>>(a);
+    if (p->structure) {
+      if ((rc = prep_kernel(k_sweep_fwd<R, true>, smem))) return rc;
+      k_sweep_fwd<R, true><<<(unsigned)B, p->threads_f, smem, st>>>(a);
+    } else {
+      if ((rc = prep_kernel(k_sweep_fwd<R, false>, smem))) return rc;
+      k_sweep_fwd<R, false><<<(unsigned)B, p->threads_f, smem, st>>>(a);
+    }
     TQ_CUDA_OK(cudaGetLastError());
     return TQ_OK;
   }
@@ -1237,10 +1244,13 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
     a.tiles_log2 = n - sw.geom.m;
     a.flags = SW_STORE | (s == 0 ? SW_INIT : 0);
     size_t smem = ((size_t)sizeof(cx<R>) << sw.geom.m) + RING_BYTES;
-    if ((rc = prep_kernel(k_sweep_fwd<R>, smem))) return rc;
+    if ((rc = p->structure ? prep_kernel(k_sweep_fwd<R, true>, smem) : prep_kernel(k_sweep_fwd<R, false>, smem))) return rc;
     int64_t blocks = B << a.tiles_log2;
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_forward: batch too large for one launch");
-    k_sweep_fwd<R><<<(unsigned)blocks, p->threads_f, smem, st>>>(a);
+    if (p->structure)
+      k_sweep_fwd<R, true><<<(unsigned)blocks, p->threads_f, smem, st>>>(a);
+    else
+      k_sweep_fwd<R, false><<<(unsigned)blocks, p->threads_f, smem, st>>>(a);
     TQ_CUDA_OK(cudaGetLastError());
   }
   MeasArgs<R> ma;
@@ -1298,8 +1308,13 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
     a.flags = SW_FULL;
     a.tiles_log2 = 0;
     size_t smem = ((size_t)2 * sizeof(cx<R>) << n) + RING_BYTES + sizeof(R) * sb.n_dslots;
-    if ((rc = prep_kernel(k_sweep_bwd<R>, smem))) return rc;
-    k_sweep_bwd<R><<<(unsigned)B, p->threads_b, smem, st>>>(a);
+    if (p->structure) {
+      if ((rc = prep_kernel(k_sweep_bwd<R, true>, smem))) return rc;
+      k_sweep_bwd<R, true><<<(unsigned)B, p->threads_b, smem, st>>>(a);
+    } else {
+      if ((rc = prep_kernel(k_sweep_bwd<R, false>, smem))) return rc;
+      k_sweep_bwd<R, false><<<(unsigned)B, p->threads_b, smem, st>>>(a);
+    }
     TQ_CUDA_OK(cudaGetLastError());
     return TQ_OK;
   }
@@ -1326,10 +1341,13 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
     a.flags = SW_STORE;
     a.tiles_log2 = n - sb.geom.m;
     size_t smem = ((size_t)2 * sizeof(cx<R>) << sb.geom.m) + RING_BYTES + sizeof(R) * sb.n_dslots;
-    if ((rc = prep_kernel(k_sweep_bwd<R>, smem))) return rc;
+    if ((rc = p->structure ? prep_kernel(k_sweep_bwd<R, true>, smem) : prep_kernel(k_sweep_bwd<R, false>, smem))) return rc;
     int64_t blocks = B << a.tiles_log2;
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_backward: batch too large for one launch");
-    k_sweep_bwd<R><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
+    if (p->structure)
+      k_sweep_bwd<R, true><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
+    else
+      k_sweep_bwd<R, false><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
     TQ_CUDA_OK(cudaGetLastError());
   }
   return TQ_OK;

@@ -887,50 +887,51 @@ __device__ void fwd_gen(cx<R>* s, const OpDesc& d, const cx<R>* M, int m, int cl
   }
 }
 
-template <typename R, bool ADJ>
+// ST: the structure-aware paths (real blocks, diagonal layers; tq_plan_opts.structure) are compiled into separate
+// kernel instantiations, so that the default kernels keep the code (registers, spills) they had without them
+template <typename R, bool ADJ, bool ST>
 __device__ __forceinline__ void apply_op(cx<R>* s, const OpDesc& d, const cx<R>* pay, int m) {
   const cx<R>* M = pay;
+  if constexpr (ST) {
+    switch (d.path) {
+      case P_R1S: fwd_r1s<R, ADJ>(s, d, M, m); return;
+      case P_R2S: fwd_r2s<R, ADJ>(s, d, M, m); return;
+      case P_DL: fwd_dl<R, ADJ>(s, d, M, 2, m); return;  // (forward payload stream: 2 entries per member)
+      default: break;
+    }
+  }
   switch (d.path) {
     case P_D1S: fwd_d1s<R, ADJ>(s, d, M, m); break;
     case P_D2S: fwd_d2s<R, ADJ>(s, d, M, m); break;
     case P_G1S: fwd_g1s<R, ADJ>(s, d, M, m); break;
-    case P_R1S: fwd_r1s<R, ADJ>(s, d, M, m); break;
-    case P_R2S: fwd_r2s<R, ADJ>(s, d, M, m); break;
-    case P_DL: fwd_dl<R, ADJ>(s, d, M, 2, m); break;  // (forward payload stream: 2 entries per member)
     default: fwd_gen<R, ADJ>(s, d, M, m, d.pad); break;
   }
 }
-template <bool ADJ>
+template <bool ADJ, bool ST>
 __device__ __forceinline__ void apply_op_f32(cf* s, const OpDesc& d, const cf* pay, int m) {
   float4* s4 = reinterpret_cast<float4*>(s);
+  if constexpr (ST) {
+    switch (d.path) {
+      case P_R1V: fwd_r1v<ADJ>(s4, d, pay, m); return;
+      case P_R1P: fwd_r1p<ADJ>(s4, d, pay, m); return;
+      case P_R2V: fwd_r2v<ADJ>(s4, d, pay, m); return;
+      default: break;
+    }
+  }
   switch (d.path) {
     case P_D1V: fwd_d1v<ADJ>(s4, d, pay, m); break;
     case P_D1P: fwd_d1p<ADJ>(s4, d, pay, m); break;
     case P_D2V: fwd_d2v<ADJ>(s4, d, pay, m); break;
     case P_G1V: fwd_g1v<ADJ>(s4, d, pay, m); break;
-    case P_R1V: fwd_r1v<ADJ>(s4, d, pay, m); break;
-    case P_R1P: fwd_r1p<ADJ>(s4, d, pay, m); break;
-    case P_R2V: fwd_r2v<ADJ>(s4, d, pay, m); break;
-    default: apply_op<float, ADJ>(s, d, pay, m); break;
+    default: apply_op<float, ADJ, ST>(s, d, pay, m); break;
   }
 }
-template <typename R, bool ADJ>
-__device__ __forceinline__ void run_op(cx<R>* s, const OpDesc& d, const cx<R>* pay, int m);
-template <>
-__device__ __forceinline__ void run_op<float, false>(cf* s, const OpDesc& d, const cf* pay, int m) {
-  apply_op_f32<false>(s, d, pay, m);
-}
-template <>
-__device__ __forceinline__ void run_op<float, true>(cf* s, const OpDesc& d, const cf* pay, int m) {
-  apply_op_f32<true>(s, d, pay, m);
-}
-template <>
-__device__ __forceinline__ void run_op<double, false>(cx<double>* s, const OpDesc& d, const cx<double>* pay, int m) {
-  apply_op<double, false>(s, d, pay, m);
-}
-template <>
-__device__ __forceinline__ void run_op<double, true>(cx<double>* s, const OpDesc& d, const cx<double>* pay, int m) {
-  apply_op<double, true>(s, d, pay, m);
+template <typename R, bool ADJ, bool ST>
+__device__ __forceinline__ void run_op(cx<R>* s, const OpDesc& d, const cx<R>* pay, int m) {
+  if constexpr (sizeof(R) == 4)
+    apply_op_f32<ADJ, ST>(s, d, pay, m);
+  else
+    apply_op<R, ADJ, ST>(s, d, pay, m);
 }
 
 // ---- adjoint step: psi <- G^dag psi ; grad_d += Re <lambda | dG_d psi> ; lambda <- G^dag lambda -----------
@@ -1428,42 +1429,49 @@ __device__ __forceinline__ void bwd_dl(cx<R>* sp, cx<R>* sl, const OpDesc& d, co
   }
 }
 
-template <typename R>
+template <typename R, bool ST>
 __device__ __forceinline__ void bwd_op_scalar(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  if constexpr (ST) {
+    switch (d.path) {
+      case P_R1S: bwd_r1s<R>(sp, sl, d, pay, s_grad, m); return;
+      case P_R2S: bwd_r2s<R>(sp, sl, d, pay, s_grad, m); return;
+      case P_DL: bwd_dl<R>(sp, sl, d, pay, s_grad, m); return;
+      default: break;
+    }
+  }
   switch (d.path) {
     case P_D1S: bwd_d1s<R>(sp, sl, d, pay, s_grad, m); break;
     case P_D2S: bwd_d2s<R>(sp, sl, d, pay, s_grad, m); break;
     case P_G1S: bwd_g1s<R>(sp, sl, d, pay, s_grad, m); break;
-    case P_R1S: bwd_r1s<R>(sp, sl, d, pay, s_grad, m); break;
-    case P_R2S: bwd_r2s<R>(sp, sl, d, pay, s_grad, m); break;
-    case P_DL: bwd_dl<R>(sp, sl, d, pay, s_grad, m); break;
     default:  // generic ops are fixed gates (no parameters): un-apply on both tiles
       fwd_gen<R, true>(sp, d, pay, m, d.pad);
       fwd_gen<R, true>(sl, d, pay, m, d.pad);
       break;
   }
 }
-template <typename R>
-__device__ __forceinline__ void bwd_op(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m);
-template <>
-__device__ __forceinline__ void bwd_op<float>(cf* sp, cf* sl, const OpDesc& d, const cf* pay, float* s_grad, int m) {
-  float4* p4 = reinterpret_cast<float4*>(sp);
-  float4* l4 = reinterpret_cast<float4*>(sl);
-  switch (d.path) {
-    case P_D1V: bwd_d1v(p4, l4, d, pay, s_grad, m); break;
-    case P_D1P: bwd_d1p(p4, l4, d, pay, s_grad, m); break;
-    case P_D2V: bwd_d2v(p4, l4, d, pay, s_grad, m); break;
-    case P_G1V: bwd_g1v(p4, l4, d, pay, s_grad, m); break;
-    case P_R1V: bwd_r1v(p4, l4, d, pay, s_grad, m); break;
-    case P_R1P: bwd_r1p(p4, l4, d, pay, s_grad, m); break;
-    case P_R2V: bwd_r2v(p4, l4, d, pay, s_grad, m); break;
-    default: bwd_op_scalar<float>(sp, sl, d, pay, s_grad, m); break;
+template <typename R, bool ST>
+__device__ __forceinline__ void bwd_op(cx<R>* sp, cx<R>* sl, const OpDesc& d, const cx<R>* pay, R* s_grad, int m) {
+  if constexpr (sizeof(R) == 4) {
+    float4* p4 = reinterpret_cast<float4*>(sp);
+    float4* l4 = reinterpret_cast<float4*>(sl);
+    if constexpr (ST) {
+      switch (d.path) {
+        case P_R1V: bwd_r1v(p4, l4, d, pay, s_grad, m); return;
+        case P_R1P: bwd_r1p(p4, l4, d, pay, s_grad, m); return;
+        case P_R2V: bwd_r2v(p4, l4, d, pay, s_grad, m); return;
+        default: break;
+      }
+    }
+    switch (d.path) {
+      case P_D1V: bwd_d1v(p4, l4, d, pay, s_grad, m); break;
+      case P_D1P: bwd_d1p(p4, l4, d, pay, s_grad, m); break;
+      case P_D2V: bwd_d2v(p4, l4, d, pay, s_grad, m); break;
+      case P_G1V: bwd_g1v(p4, l4, d, pay, s_grad, m); break;
+      default: bwd_op_scalar<float, ST>(sp, sl, d, pay, s_grad, m); break;
+    }
+  } else {
+    bwd_op_scalar<R, ST>(sp, sl, d, pay, s_grad, m);
   }
-}
-template <>
-__device__ __forceinline__ void bwd_op<double>(cx<double>* sp, cx<double>* sl, const OpDesc& d, const cx<double>* pay,
-                                               double* s_grad, int m) {
-  bwd_op_scalar<double>(sp, sl, d, pay, s_grad, m);
 }
 
 // ---------------------------------------------------------------------------
@@ -1687,7 +1695,7 @@ struct FwdArgs {
 
 extern __shared__ __align__(16) unsigned char tq_smem[];
 
-template <typename R>
+template <typename R, bool ST>
 __device__ __forceinline__ void run_stream_fwd(cx<R>* sm, const Ring<R>& ring, const StreamRef& st, const cx<R>* pay_b,
                                                int m) {
   ring_start<R>(ring, st, pay_b);
@@ -1700,13 +1708,13 @@ __device__ __forceinline__ void run_stream_fwd(cx<R>* sm, const Ring<R>& ring, c
     const cx<R>* pp = ring.pay[c & 1];
     for (uint32_t o = 0; o < ci.op_count; ++o) {
       const OpDesc d = dd[o];
-      run_op<R, false>(sm, d, pp + (d.pay_off - ci.pay_begin), m);
+      run_op<R, false, ST>(sm, d, pp + (d.pay_off - ci.pay_begin), m);
       __syncthreads();
     }
   }
 }
 
-template <typename R>
+template <typename R, bool ST = false>
 // complex64: 80 registers -> 3 CTAs per SM (the shared-memory limit), +17 % on the 20-qubit sweeps; complex128
 // would spill at that cap and keeps 2
 __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) k_sweep_fwd(const __grid_constant__ FwdArgs<R> a) {
@@ -1731,7 +1739,7 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 3 : 2) k_sweep_fwd(const
   } else {
     for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = psi_b[tbase | dep_local(a.geom, l)];
   }
-  run_stream_fwd<R>(sm, ring, a.st, a.stream + b * a.stride, m);  // begins with a __syncthreads
+  run_stream_fwd<R, ST>(sm, ring, a.st, a.stream + b * a.stride, m);  // begins with a __syncthreads
 
   if (a.flags & SW_STORE) {
     for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) psi_b[tbase | dep_local(a.geom, l)] = sm[l];
@@ -1810,7 +1818,7 @@ struct BwdArgs {
   Geom geom;
 };
 
-template <typename R>
+template <typename R, bool ST = false>
 __global__ void __launch_bounds__(256, 2) k_sweep_bwd(const __grid_constant__ BwdArgs<R> a) {
   const int m = a.geom.m;
   const uint32_t tile_n = 1u << m;
@@ -1838,7 +1846,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_bwd(const __grid_constant__ Bw
         __syncthreads();
         if (threadIdx.x == 0) sp[0] = mk<R>(1, 0);
       }
-      run_stream_fwd<R>(sp, ring, a.st_f, a.stream_f + b * a.stride_f, m);
+      run_stream_fwd<R, ST>(sp, ring, a.st_f, a.stream_f + b * a.stride_f, m);
     }
     const R* dy_b = a.dy + b * a.out_reals;
     for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x)
@@ -1865,7 +1873,7 @@ __global__ void __launch_bounds__(256, 2) k_sweep_bwd(const __grid_constant__ Bw
     const cx<R>* pp = ring.pay[c & 1];
     for (uint32_t o = 0; o < ci.op_count; ++o) {
       const OpDesc d = dd[o];
-      bwd_op<R>(sp, sl, d, pp + (d.pay_off - ci.pay_begin), s_grad, m);
+      bwd_op<R, ST>(sp, sl, d, pp + (d.pay_off - ci.pay_begin), s_grad, m);
       __syncthreads();
     }
   }
