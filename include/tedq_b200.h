@@ -104,7 +104,12 @@ typedef struct tq_plan_opts {
                                    of real gates (RY, CRY, H, X, CNOT, ...) take real-matrix paths with half the
                                    multiplies, and one-qubit diagonal gates (RZ, PhaseShift, S, T, Z) stay out of the
                                    blocks and are merged, per sweep, into diagonal-layer passes (two phase tables,
-                                   signed-sum gradients).  Same results; measured slower on B200         */
+                                   signed-sum gradients).  Same results; measured slower on B200.
+                                   2: register-group sweeps (complex64, >= 9 qubits, every gate a (controlled)
+                                   one-target block or a diagonal): a thread keeps the 16 amplitudes of four tile bits
+                                   in registers across a run of blocks; one-qubit runs stay 2x2, controlled-X gates are
+                                   register swaps.  A circuit that does not qualify silently keeps the default sweeps
+                                   (tq_plan_op_stats(what = 4) tells which)                                          */
   int32_t reserved[2];
 } tq_plan_opts;
 
@@ -129,7 +134,8 @@ int32_t tq_plan_num_sweeps(const tq_plan* plan, int32_t backward);
 /* ops after gate fusion (runs of gates inside one qubit / one qubit pair become one dense block) */
 int32_t tq_plan_num_blocks(const tq_plan* plan);
 /* ops emitted into the sweeps of one direction: what = 0 all, 1 diagonal-layer ops (runs of one-qubit diagonal gates
- * merged into one phase-table pass), 2 the gates inside them, 3 ops on the real-matrix paths */
+ * merged into one phase-table pass), 2 the gates inside them, 3 ops on the real-matrix paths, 4 register groups
+ * (structure = 2; 0 when the plan kept the default sweeps) */
 int32_t tq_plan_op_stats(const tq_plan* plan, int32_t backward, int32_t what);
 /* local amplitude-index bit positions of sweep s; returns count, writes up to cap entries */
 int32_t tq_plan_sweep_bits(const tq_plan* plan, int32_t backward, int32_t s, int32_t* bits, int32_t cap);

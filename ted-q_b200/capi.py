@@ -328,6 +328,10 @@ class Plan:
         """(ops, diagonal-layer ops, gates inside them, real-path ops) emitted into the sweeps of one direction."""
         return tuple(int(lib().tq_plan_op_stats(self.handle, int(backward), w)) for w in range(4))
 
+    def num_register_groups(self, backward=False) -> int:
+        """Register groups emitted into the sweeps (plan_opts["structure"] = 2); 0 = the plan runs the default sweeps."""
+        return int(lib().tq_plan_op_stats(self.handle, int(backward), 4))
+
     def num_blocks(self) -> int:
         return int(lib().tq_plan_num_blocks(self.handle))
 

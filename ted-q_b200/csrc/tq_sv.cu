@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "tq_sv_kernels.cuh"
+#include "tq_sv_rg.cuh"
 
 namespace tq {
 
@@ -53,6 +54,7 @@ struct HostBlock {
   int nderiv = 0;
   bool real = true;    // every member is real: the block's product is real (half the multiplies, only Re W needed)
   bool diag1 = false;  // a lone one-qubit diagonal gate kept out of dense blocks: merged into a diagonal layer op
+  bool is_x = false;   // a lone fixed gate whose target block is exactly PauliX (CNOT, Toffoli, X): a permutation
   // resolved op
   int cls = OP_DENSE;
   std::vector<int> targets, controls;
@@ -88,6 +90,8 @@ struct tq_plan {
   std::vector<zc> fixed;
   bool fwd_full = false, bwd_full = false, sv_ok = true;
   bool structure = false;  // tq_plan_opts.structure: the sweeps run the kernel instantiations with the real / diagonal-layer paths
+  bool rg = false;         // tq_plan_opts.structure = 2 and the circuit qualifies: register-group sweeps (tq_sv_rg.cuh)
+  int n_rg[2] = {0, 0};    // register groups emitted per direction
   int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256, fuse = 1;
   std::vector<Sweep> fwd, bwd;
   int n_ops[2] = {0, 0}, n_dl[2] = {0, 0}, n_dl_members[2] = {0, 0}, n_real[2] = {0, 0};  // emitted ops per direction
@@ -508,9 +512,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   // into diagonal-layer passes.  Off by default: on the 20-qubit HEA it halves the multiplies but needs 247 passes
   // over the tile instead of 190 and executes MORE instructions in total (2.70e9 vs 2.53e9 per 16 sets, ncu) — the
   // per-pass overhead (descriptor, matrix load, index arithmetic, barrier) outweighs the saved FMAs
-  bool diag_layers = false;
+  bool diag_layers = false, want_rg = false;
   if (opts) {
     diag_layers = opts->structure == 1;
+    want_rg = opts->structure == 2;
     if (opts->max_local_qubits_fwd > 0) m_f = full_f = opts->max_local_qubits_fwd;
     if (opts->max_local_qubits_bwd > 0) m_b = full_b = opts->max_local_qubits_bwd;
     if (opts->coalesce_bits >= 0) coalesce = opts->coalesce_bits;
@@ -648,6 +653,21 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     return TQ_OK;
   }
 
+  // ---- register-group mode (structure = 2): complex64, tiles of >= 2^9 amplitudes, and every gate either a (controlled)
+  // one-target block or a diagonal — anything else (SWAP, a dense two-qubit Unitary) keeps the default sweeps
+  bool rg = want_rg && c64 && std::min(m_f, m_b) >= RG_MIN_TILE;
+  for (int gi = 0; gi < n_gates && rg; ++gi) {
+    const HostGate& g = p->gates[gi];
+    if (g.noop) continue;
+    if (g.cls == OP_DENSE && g.targets.size() != 1) rg = false;
+    if (g.cls == OP_DIAG && g.targets.size() > 1 && g.ntrain > 0) rg = false;
+  }
+  p->rg = rg;
+  if (rg) {
+    p->threads_f = std::min(256, 1 << (m_f - RG_BITS));
+    p->threads_b = std::min(256, 1 << (m_b - RG_BITS));
+  }
+
   // ---- fusion: runs of gates inside one qubit or one qubit pair become one dense block -------------
   const int pay_cap_entries = CHUNK_PAY_BYTES / (int)csize(dtype);
   std::vector<HostBlock> all;
@@ -675,6 +695,18 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       };
       if (!fuse || g.nq == 3) {
         fresh();
+        continue;
+      }
+      if (rg) {
+        // register groups: only runs of one-qubit gates on the SAME qubit are multiplied together (2x2); entanglers
+        // stay on their own (a CNOT is a register swap there, not a factor that turns its neighbours into a 4x4)
+        const int o = g.nq == 1 ? owner[g.qubits[0]] : -1;
+        if (o >= 0 && all[o].qubits.size() == 1 && can_add(all[o], g, 0)) {
+          all[o].members.push_back(gi);
+          all[o].nderiv += g.ntrain;
+        } else {
+          fresh();
+        }
         continue;
       }
       if (g.nq == 1) {
@@ -814,6 +846,10 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       b.controls = g.controls;
       b.count = g.red_count;
       b.real = b.real && g.real && g.cls == OP_DENSE;
+      if (g.kind == TQ_G_FIXED && g.cls == OP_DENSE && g.targets.size() == 1 && g.red_count == 4) {
+        const zc* X = p->fixed.data() + g.red_off;
+        b.is_x = X[0] == zc(0, 0) && X[1] == zc(1, 0) && X[2] == zc(1, 0) && X[3] == zc(0, 0);
+      }
       mb.mode = g.kind == TQ_G_FIXED ? MB_FIXED : MB_NATIVE;
       mb.diag = g.cls == OP_DIAG;
       mb.dim = 1 << (int)g.targets.size();
@@ -913,106 +949,206 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       sw.chunk_begin = (int)chunks.size();
       ChunkInfo cur = {0, 0, 0, 0};
       bool open = false;
-      // Emission order: one-qubit diagonal blocks are held back and merged into diagonal-layer ops.  A held-back
-      // block commutes with everything emitted before the layer is flushed (no shared qubit), and the layer is
-      // flushed before the first block that touches one of its qubits.
-      std::vector<std::vector<int>> items;
-      {
-        std::vector<int> group;
-        std::vector<char> group_q(n, 0);
-        auto flush = [&]() {
-          if (group.empty()) return;
-          items.push_back(group);
-          group.clear();
-          std::fill(group_q.begin(), group_q.end(), 0);
+      if (p->rg) {
+        // Register groups: walk the sweep's blocks in order; a block joins the open group when the group's tile bits plus
+        // its own stay within four and none of its bits belongs to a block that was passed over (it commutes with every
+        // passed-over block then); passed-over blocks start the next groups.
+        const std::vector<int>& tb = sb[s];
+        const int m_t = (int)tb.size();
+        auto local = [&](int q) {
+          const int b = n - 1 - q;
+          for (int j = 0; j < m_t; ++j)
+            if (tb[j] == b) return j;
+          return -1;
         };
-        for (int bi : sg[s]) {
-          const HostBlock& hb = p->blocks[bi];
-          if (hb.diag1 && hb.cls == OP_DIAG) {
-            const int q = hb.targets[0];
-            if (group_q[q] || (int)group.size() == DL_MAX) flush();
-            group.push_back(bi);
-            group_q[q] = 1;
-          } else {
-            bool touches = false;
-            for (int q : hb.qubits) touches = touches || group_q[q];
-            if (touches) flush();
-            items.push_back({bi});
-          }
-        }
-        flush();
-      }
-      for (const std::vector<int>& item : items) {
-        OpDesc d;
-        int pe;
-        const int64_t pay0 = stride;
-        if (item.size() == 1) {
-          HostBlock& hb = p->blocks[item[0]];
-          make_desc(hb, n, sb[s], c64, d);
-          pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
-          (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
-          if (dir) {
-            d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
-            for (int k = 0; k < hb.nderiv; ++k) slot_pidx.push_back(hb.pidx[k]);
-          }
-        } else {  // diagonal layer: the members' payloads back to back (2 entries each forward, 4 backward)
-          memset(&d, 0, sizeof(d));
-          d.path = P_DL;
-          const int per = dir ? 4 : 2;
-          pe = per * (int)item.size();
-          uint32_t mask = 0;
-          int nd = 0;
-          uint8_t pos[DL_MAX];
-          memset(pos, 0, sizeof(pos));
-          if (dir) d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
-          for (size_t k = 0; k < item.size(); ++k) {
-            HostBlock& hb = p->blocks[item[k]];
-            const int bit = n - 1 - hb.targets[0];
-            int lp = -1;
-            for (size_t j = 0; j < sb[s].size(); ++j)
-              if (sb[s][j] == bit) lp = (int)j;
-            TQ_REQUIRE(lp >= 0, TQ_E_INVALID, "tq_plan_create: diagonal-layer member outside its sweep's tile");
-            pos[k] = (uint8_t)lp;
-            (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)(stride + per * (int64_t)k);
-            TQ_REQUIRE(hb.nderiv <= 1, TQ_E_UNSUPPORTED, "tq_plan_create: a diagonal gate with %d parameters", hb.nderiv);
-            if (hb.nderiv == 1) {
-              mask |= 1u << k;
-              ++nd;
-              if (dir) slot_pidx.push_back(hb.pidx[0]);
+        std::vector<int> rest(sg[s]);
+        while (!rest.empty()) {
+          std::vector<int> group, keep;
+          std::vector<char> inb(m_t, 0), blocked(m_t, 0);
+          int nbits = 0, pay = 0;
+          for (int bi : rest) {
+            const HostBlock& hb = p->blocks[bi];
+            bool ok = (int)group.size() < RG_MAX_SUB;
+            int need = 0;
+            std::vector<int> lb;
+            for (int q : hb.targets) lb.push_back(local(q));
+            for (int q : hb.controls) lb.push_back(local(q));
+            for (int b : lb) {
+              TQ_REQUIRE(b >= 0, TQ_E_INVALID, "tq_plan_create: block outside its sweep's tile");
+              if (blocked[b]) ok = false;
+              if (!inb[b]) ++need;
+            }
+            const int pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
+            if (ok && nbits + need <= RG_BITS && pay + pe <= pay_cap_entries) {
+              for (int b : lb)
+                if (!inb[b]) {
+                  inb[b] = 1;
+                  ++nbits;
+                }
+              pay += pe;
+              group.push_back(bi);
+            } else {
+              for (int b : lb) blocked[b] = 1;
+              keep.push_back(bi);
             }
           }
-          d.nderiv = (uint8_t)nd;
-          d.count = (uint32_t)item.size() | (mask << 8);
-          for (int j = 0; j < 4; ++j) {
-            d.ins[j] = pos[j];
-            d.tpos[j] = pos[4 + j];
-            d.cmask |= (uint32_t)pos[8 + j] << (8 * j);
-            d.pad |= (uint32_t)pos[12 + j] << (8 * j);
+          rest.swap(keep);
+          int used[RG_BITS], nu = 0, reg[RG_BITS];
+          for (int b = 0; b < m_t; ++b)
+            if (inb[b]) used[nu++] = b;
+          rg_pick_bits(m_t, used, nu, reg);
+          auto reg_index = [&](int q) {
+            const int b = local(q);
+            for (int i = 0; i < RG_BITS; ++i)
+              if (reg[i] == b) return i;
+            return -1;
+          };
+          // the header and its sub-ops travel in one prefetch chunk
+          if (open && (cur.op_count + 1 + group.size() > (size_t)CHUNK_OPS || (int)cur.pay_count + pay > pay_cap_entries)) {
+            chunks.push_back(cur);
+            open = false;
           }
+          if (!open) {
+            cur.op_begin = (uint32_t)ops.size();
+            cur.op_count = 0;
+            cur.pay_begin = (uint32_t)stride;
+            cur.pay_count = 0;
+            open = true;
+          }
+          OpDesc h;
+          memset(&h, 0, sizeof(h));
+          h.path = P_RG;
+          h.k = RG_BITS;
+          h.nins = (uint8_t)group.size();
+          for (int i = 0; i < RG_BITS; ++i) h.tpos[i] = (uint8_t)reg[i];
+          ops.push_back(h);
+          cur.op_count += 1;
+          for (int bi : group) {
+            HostBlock& hb = p->blocks[bi];
+            int treg[4], creg[4], nt = 0, nc = 0;
+            for (int q : hb.targets) treg[nt++] = reg_index(q);
+            for (int q : hb.controls) creg[nc++] = reg_index(q);
+            TQ_REQUIRE(hb.cls == OP_DIAG || nt == 1, TQ_E_INVALID, "tq_plan_create: dense block with %d targets in a register group", nt);
+            OpDesc d;
+            rg_make_sub(hb.cls, nt, treg, nc, creg, hb.is_x, hb.count, hb.nderiv, d);
+            TQ_REQUIRE(d.path != RG_GEN || hb.nderiv == 0, TQ_E_UNSUPPORTED, "tq_plan_create: trainable multi-target diagonal");
+            const int pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
+            (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
+            d.pay_off = (uint32_t)stride;
+            if (dir) {
+              d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
+              for (int k = 0; k < hb.nderiv; ++k) slot_pidx.push_back(hb.pidx[k]);
+            }
+            ops.push_back(d);
+            cur.op_count += 1;
+            cur.pay_count += (uint32_t)pe;
+            stride += pe;
+          }
+          p->n_ops[dir] += (int)group.size();
+          p->n_rg[dir] += 1;
         }
-        TQ_REQUIRE(pe <= pay_cap_entries, TQ_E_UNSUPPORTED, "block payload exceeds the prefetch buffer");
-        d.pay_off = (uint32_t)pay0;
-        if (open && (cur.op_count >= (uint32_t)CHUNK_OPS || (int)cur.pay_count + pe > pay_cap_entries)) {
-          chunks.push_back(cur);
-          open = false;
+      } else {
+        // Emission order: one-qubit diagonal blocks are held back and merged into diagonal-layer ops.  A held-back
+        // block commutes with everything emitted before the layer is flushed (no shared qubit), and the layer is
+        // flushed before the first block that touches one of its qubits.
+        std::vector<std::vector<int>> items;
+        {
+          std::vector<int> group;
+          std::vector<char> group_q(n, 0);
+          auto flush = [&]() {
+            if (group.empty()) return;
+            items.push_back(group);
+            group.clear();
+            std::fill(group_q.begin(), group_q.end(), 0);
+          };
+          for (int bi : sg[s]) {
+            const HostBlock& hb = p->blocks[bi];
+            if (hb.diag1 && hb.cls == OP_DIAG) {
+              const int q = hb.targets[0];
+              if (group_q[q] || (int)group.size() == DL_MAX) flush();
+              group.push_back(bi);
+              group_q[q] = 1;
+            } else {
+              bool touches = false;
+              for (int q : hb.qubits) touches = touches || group_q[q];
+              if (touches) flush();
+              items.push_back({bi});
+            }
+          }
+          flush();
         }
-        if (!open) {
-          cur.op_begin = (uint32_t)ops.size();
-          cur.op_count = 0;
-          cur.pay_begin = (uint32_t)stride;
-          cur.pay_count = 0;
-          open = true;
+        for (const std::vector<int>& item : items) {
+          OpDesc d;
+          int pe;
+          const int64_t pay0 = stride;
+          if (item.size() == 1) {
+            HostBlock& hb = p->blocks[item[0]];
+            make_desc(hb, n, sb[s], c64, d);
+            pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
+            (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
+            if (dir) {
+              d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
+              for (int k = 0; k < hb.nderiv; ++k) slot_pidx.push_back(hb.pidx[k]);
+            }
+          } else {  // diagonal layer: the members' payloads back to back (2 entries each forward, 4 backward)
+            memset(&d, 0, sizeof(d));
+            d.path = P_DL;
+            const int per = dir ? 4 : 2;
+            pe = per * (int)item.size();
+            uint32_t mask = 0;
+            int nd = 0;
+            uint8_t pos[DL_MAX];
+            memset(pos, 0, sizeof(pos));
+            if (dir) d.dslot = (uint32_t)((int)slot_pidx.size() - sw.slot_begin);
+            for (size_t k = 0; k < item.size(); ++k) {
+              HostBlock& hb = p->blocks[item[k]];
+              const int bit = n - 1 - hb.targets[0];
+              int lp = -1;
+              for (size_t j = 0; j < sb[s].size(); ++j)
+                if (sb[s][j] == bit) lp = (int)j;
+              TQ_REQUIRE(lp >= 0, TQ_E_INVALID, "tq_plan_create: diagonal-layer member outside its sweep's tile");
+              pos[k] = (uint8_t)lp;
+              (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)(stride + per * (int64_t)k);
+              TQ_REQUIRE(hb.nderiv <= 1, TQ_E_UNSUPPORTED, "tq_plan_create: a diagonal gate with %d parameters", hb.nderiv);
+              if (hb.nderiv == 1) {
+                mask |= 1u << k;
+                ++nd;
+                if (dir) slot_pidx.push_back(hb.pidx[0]);
+              }
+            }
+            d.nderiv = (uint8_t)nd;
+            d.count = (uint32_t)item.size() | (mask << 8);
+            for (int j = 0; j < 4; ++j) {
+              d.ins[j] = pos[j];
+              d.tpos[j] = pos[4 + j];
+              d.cmask |= (uint32_t)pos[8 + j] << (8 * j);
+              d.pad |= (uint32_t)pos[12 + j] << (8 * j);
+            }
+          }
+          TQ_REQUIRE(pe <= pay_cap_entries, TQ_E_UNSUPPORTED, "block payload exceeds the prefetch buffer");
+          d.pay_off = (uint32_t)pay0;
+          if (open && (cur.op_count >= (uint32_t)CHUNK_OPS || (int)cur.pay_count + pe > pay_cap_entries)) {
+            chunks.push_back(cur);
+            open = false;
+          }
+          if (!open) {
+            cur.op_begin = (uint32_t)ops.size();
+            cur.op_count = 0;
+            cur.pay_begin = (uint32_t)stride;
+            cur.pay_count = 0;
+            open = true;
+          }
+          cur.op_count += 1;
+          cur.pay_count += (uint32_t)pe;
+          stride += pe;
+          ops.push_back(d);
+          p->n_ops[dir] += 1;
+          if (d.path == P_DL) {
+            p->n_dl[dir] += 1;
+            p->n_dl_members[dir] += (int)item.size();
+          }
+          if (d.path == P_R1S || d.path == P_R2S || d.path == P_R1V || d.path == P_R1P || d.path == P_R2V) p->n_real[dir] += 1;
         }
-        cur.op_count += 1;
-        cur.pay_count += (uint32_t)pe;
-        stride += pe;
-        ops.push_back(d);
-        p->n_ops[dir] += 1;
-        if (d.path == P_DL) {
-          p->n_dl[dir] += 1;
-          p->n_dl_members[dir] += (int)item.size();
-        }
-        if (d.path == P_R1S || d.path == P_R2S || d.path == P_R1V || d.path == P_R1P || d.path == P_R2V) p->n_real[dir] += 1;
       }
       if (open) chunks.push_back(cur);
       sw.op_end = (int)ops.size();
@@ -1063,10 +1199,12 @@ int32_t tq_plan_sweep_num_gates(const tq_plan* p, int32_t backward, int32_t s) {
   return v[s].n_gates;
 }
 int32_t tq_plan_num_blocks(const tq_plan* p) { return p ? (int32_t)p->blocks.size() : -1; }
-/* what = 0: ops emitted into the sweeps, 1: diagonal-layer ops, 2: their members, 3: ops on the real paths */
+/* what = 0: ops emitted into the sweeps, 1: diagonal-layer ops, 2: their members, 3: ops on the real paths,
+ * 4: register groups (structure = 2; 0 when the plan fell back to the default sweeps) */
 int32_t tq_plan_op_stats(const tq_plan* p, int32_t backward, int32_t what) {
-  if (!p || what < 0 || what > 3) return -1;
+  if (!p || what < 0 || what > 4) return -1;
   const int d = backward ? 1 : 0;
+  if (what == 4) return p->n_rg[d];
   return what == 0 ? p->n_ops[d] : what == 1 ? p->n_dl[d] : what == 2 ? p->n_dl_members[d] : p->n_real[d];
 }
 int64_t tq_plan_out_reals(const tq_plan* p) { return p ? p->out_reals : -1; }
@@ -1100,7 +1238,8 @@ double tq_plan_flops(const tq_plan* p, int32_t backward) {
     const double amps = ldexp(1.0, p->n - (int)b.controls.size());
     // complex MAC = 8 flops; a real matrix entry times a complex amplitude, accumulated = 4
     const double per = b.cls == OP_DIAG ? 6.0 : (b.real ? 4.0 : 8.0) * ldexp(1.0, (int)b.targets.size());
-    fl += amps * per;
+    if (p->rg && b.is_x) continue;                  // a register swap
+    fl += amps * (p->rg && b.cls == OP_DIAG && b.targets.size() == 1 ? 16.0 : per);  // diagonal applied as a 2x2 there
   }
   return backward ? 3.0 * fl : fl;
 }
@@ -1227,6 +1366,14 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
     a.tiles_log2 = 0;
     a.flags = SW_INIT | SW_MEASURE | (L.has_psi ? SW_STORE : 0);
     size_t smem = ((size_t)sizeof(cx<R>) << n) + RING_BYTES + sizeof(R) * p->n_slots;
+    if constexpr (sizeof(R) == 4) {
+      if (p->rg) {
+        if ((rc = prep_kernel(k_rg_fwd, smem))) return rc;
+        k_rg_fwd<<<(unsigned)B, p->threads_f, smem, st>>>(a);
+        TQ_CUDA_OK(cudaGetLastError());
+        return TQ_OK;
+      }
+    }
     if (p->structure) {
       if ((rc = prep_kernel(k_sweep_fwd<R, true>, smem))) return rc;
       k_sweep_fwd<R, true><<<(unsigned)B, p->threads_f, smem, st>>>(a);
@@ -1244,9 +1391,17 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
     a.tiles_log2 = n - sw.geom.m;
     a.flags = SW_STORE | (s == 0 ? SW_INIT : 0);
     size_t smem = ((size_t)sizeof(cx<R>) << sw.geom.m) + RING_BYTES;
-    if ((rc = p->structure ? prep_kernel(k_sweep_fwd<R, true>, smem) : prep_kernel(k_sweep_fwd<R, false>, smem))) return rc;
     int64_t blocks = B << a.tiles_log2;
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_forward: batch too large for one launch");
+    if constexpr (sizeof(R) == 4) {
+      if (p->rg) {
+        if ((rc = prep_kernel(k_rg_fwd, smem))) return rc;
+        k_rg_fwd<<<(unsigned)blocks, p->threads_f, smem, st>>>(a);
+        TQ_CUDA_OK(cudaGetLastError());
+        continue;
+      }
+    }
+    if ((rc = p->structure ? prep_kernel(k_sweep_fwd<R, true>, smem) : prep_kernel(k_sweep_fwd<R, false>, smem))) return rc;
     if (p->structure)
       k_sweep_fwd<R, true><<<(unsigned)blocks, p->threads_f, smem, st>>>(a);
     else
@@ -1308,6 +1463,15 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
     a.flags = SW_FULL;
     a.tiles_log2 = 0;
     size_t smem = ((size_t)2 * sizeof(cx<R>) << n) + RING_BYTES + sizeof(R) * sb.n_dslots;
+    if constexpr (sizeof(R) == 4) {
+      if (p->rg) {
+        TQ_REQUIRE(a.psi, TQ_E_INVALID, "tq_backward: the workspace holds no final state");
+        if ((rc = prep_kernel(k_rg_bwd, smem))) return rc;
+        k_rg_bwd<<<(unsigned)B, p->threads_b, smem, st>>>(a);
+        TQ_CUDA_OK(cudaGetLastError());
+        return TQ_OK;
+      }
+    }
     if (p->structure) {
       if ((rc = prep_kernel(k_sweep_bwd<R, true>, smem))) return rc;
       k_sweep_bwd<R, true><<<(unsigned)B, p->threads_b, smem, st>>>(a);
@@ -1341,9 +1505,17 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
     a.flags = SW_STORE;
     a.tiles_log2 = n - sb.geom.m;
     size_t smem = ((size_t)2 * sizeof(cx<R>) << sb.geom.m) + RING_BYTES + sizeof(R) * sb.n_dslots;
-    if ((rc = p->structure ? prep_kernel(k_sweep_bwd<R, true>, smem) : prep_kernel(k_sweep_bwd<R, false>, smem))) return rc;
     int64_t blocks = B << a.tiles_log2;
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_backward: batch too large for one launch");
+    if constexpr (sizeof(R) == 4) {
+      if (p->rg) {
+        if ((rc = prep_kernel(k_rg_bwd, smem))) return rc;
+        k_rg_bwd<<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
+        TQ_CUDA_OK(cudaGetLastError());
+        continue;
+      }
+    }
+    if ((rc = p->structure ? prep_kernel(k_sweep_bwd<R, true>, smem) : prep_kernel(k_sweep_bwd<R, false>, smem))) return rc;
     if (p->structure)
       k_sweep_bwd<R, true><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
     else

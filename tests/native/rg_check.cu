@@ -1,0 +1,261 @@
+// Host-side check of the register-group arithmetic and index maps (tq_sv_rg.cuh): the same inline functions the
+// kernels call, run on the CPU over a whole swizzled tile and compared with a gate-by-gate reference on the natural
+// tile.  Built and run by tests/test_rg_host_cpu.py (nvcc, host code only — no GPU needed).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <complex>
+#include <vector>
+
+#include "../../ted-q_b200/csrc/tq_sv_rg.cuh"
+
+using namespace tq;
+typedef std::complex<double> zc;
+typedef cx<float> cf32;
+
+static double urand() { return rand() / (double)RAND_MAX * 2.0 - 1.0; }
+
+struct Blk {
+  int cls;                      // OP_DENSE (1 target) or OP_DIAG (1..3 targets)
+  std::vector<int> targets;     // tile bits, MSB of the matrix index first
+  std::vector<int> controls;    // tile bits
+  bool is_x;
+  int nderiv;
+  std::vector<cf32> pay;        // matrix (4) / diagonal (2^k), then nderiv derivative matrices of the same size
+};
+
+static zc Z(cf32 v) { return zc(v.x, v.y); }
+
+// reference: apply block (or its conjugate transpose) to a natural-order tile
+static void ref_apply(std::vector<zc>& s, int m, const Blk& b, bool adj) {
+  const uint32_t n = 1u << m;
+  uint32_t cm = 0;
+  for (int c : b.controls) cm |= 1u << c;
+  if (b.cls == OP_DIAG) {
+    for (uint32_t i = 0; i < n; ++i) {
+      if ((i & cm) != cm) continue;
+      int idx = 0;
+      for (int t : b.targets) idx = (idx << 1) | ((i >> t) & 1);
+      zc v = Z(b.pay[idx]);
+      s[i] *= adj ? std::conj(v) : v;
+    }
+    return;
+  }
+  const uint32_t tb = 1u << b.targets[0];
+  zc M[4] = {Z(b.pay[0]), Z(b.pay[1]), Z(b.pay[2]), Z(b.pay[3])};
+  if (b.is_x) { M[0] = 0; M[1] = 1; M[2] = 1; M[3] = 0; }
+  if (adj) {
+    zc T[4] = {std::conj(M[0]), std::conj(M[2]), std::conj(M[1]), std::conj(M[3])};
+    for (int i = 0; i < 4; ++i) M[i] = T[i];
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    if ((i & tb) || (i & cm) != cm) continue;
+    zc a0 = s[i], a1 = s[i | tb];
+    s[i] = M[0] * a0 + M[1] * a1;
+    s[i | tb] = M[2] * a0 + M[3] * a1;
+  }
+}
+
+// reference gradient term of slot e: Re <lambda | dG_e | psi_prev> over the block's live amplitudes
+static double ref_grad(const std::vector<zc>& psi_prev, const std::vector<zc>& lam, int m, const Blk& b, int e) {
+  const uint32_t n = 1u << m;
+  uint32_t cm = 0;
+  for (int c : b.controls) cm |= 1u << c;
+  const uint32_t tb = 1u << b.targets[0];
+  double g = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if ((i & tb) || (i & cm) != cm) continue;
+    zc D[4];
+    if (b.cls == OP_DIAG) {
+      D[0] = Z(b.pay[2 + 2 * e]); D[1] = 0; D[2] = 0; D[3] = Z(b.pay[3 + 2 * e]);
+    } else {
+      for (int k = 0; k < 4; ++k) D[k] = Z(b.pay[4 + 4 * e + k]);
+    }
+    zc p0 = psi_prev[i], p1 = psi_prev[i | tb];
+    g += std::real(std::conj(lam[i]) * (D[0] * p0 + D[1] * p1) + std::conj(lam[i | tb]) * (D[2] * p0 + D[3] * p1));
+  }
+  return g;
+}
+
+static int fails = 0;
+#define CHECK(cond, ...)          \
+  do {                            \
+    if (!(cond)) {                \
+      printf("FAIL: " __VA_ARGS__); \
+      printf("\n");               \
+      ++fails;                    \
+    }                             \
+  } while (0)
+
+int main() {
+  srand(1234);
+  // 1. swizzle: bijection + involution inside aligned 16-word blocks
+  for (uint32_t i = 0; i < (1u << 14); ++i) {
+    const uint32_t p = rg_phys(i);
+    CHECK((p >> 4) == (i >> 4), "rg_phys leaves the 16-word block");
+    CHECK(rg_phys(p) == i, "rg_phys is not an involution at %u", i);
+  }
+  // 2. bank conflicts: contiguous register bits are conflict free for every tile size; padded picks are too
+  for (int m = RG_MIN_TILE; m <= 14; ++m) {
+    for (int b0 = 0; b0 + 4 <= m; ++b0) {
+      OpDesc h;
+      memset(&h, 0, sizeof(h));
+      for (int i = 0; i < 4; ++i) h.tpos[i] = (uint8_t)(b0 + i);
+      RgGeom G = rg_geom(h);
+      for (int j = 0; j < 16; ++j)
+        for (uint32_t w = 0; w < (1u << (m - 4)); w += 16) {  // a half-warp: 16 consecutive groups
+          int seen = 0;
+          for (uint32_t l = 0; l < 16; ++l) {
+            const uint32_t addr = rg_base(G, w + l) ^ G.off[j];
+            CHECK(addr < (1u << m), "address outside the tile");
+            seen |= 1 << (addr & 15);
+          }
+          CHECK(seen == 0xffff, "bank conflict m=%d b0=%d j=%d", m, b0, j);
+        }
+    }
+    for (int trial = 0; trial < 200; ++trial) {
+      int nu = 1 + rand() % 4, used[4];
+      for (int i = 0; i < nu;) {
+        int b = rand() % m;
+        bool dup = false;
+        for (int k = 0; k < i; ++k) dup = dup || used[k] == b;
+        if (!dup) used[i++] = b;
+      }
+      int reg[4];
+      rg_pick_bits(m, used, nu, reg);
+      for (int i = 0; i < 3; ++i) CHECK(reg[i] < reg[i + 1], "register bits not ascending");
+      for (int i = 0; i < nu; ++i) {
+        bool in = false;
+        for (int k = 0; k < 4; ++k) in = in || reg[k] == used[i];
+        CHECK(in, "used bit dropped");
+      }
+      CHECK(reg[3] < m, "register bit outside the tile");
+    }
+  }
+  // 3. forward + adjoint of random groups on random tiles
+  for (int trial = 0; trial < 300; ++trial) {
+    const int m = RG_MIN_TILE + rand() % 3;
+    const uint32_t n = 1u << m;
+    // register bits: random 4 of m
+    int reg[4];
+    {
+      int nu = 4, used[4];
+      for (int i = 0; i < nu;) {
+        int b = rand() % m;
+        bool dup = false;
+        for (int k = 0; k < i; ++k) dup = dup || used[k] == b;
+        if (!dup) used[i++] = b;
+      }
+      rg_pick_bits(m, used, 4, reg);
+    }
+    const int nsub = 1 + rand() % 8;
+    std::vector<Blk> blks;
+    std::vector<OpDesc> descs;
+    std::vector<cf32> payload;
+    OpDesc h;
+    memset(&h, 0, sizeof(h));
+    h.path = P_RG;
+    h.nins = (uint8_t)nsub;
+    for (int i = 0; i < 4; ++i) h.tpos[i] = (uint8_t)reg[i];
+    for (int sidx = 0; sidx < nsub; ++sidx) {
+      Blk b;
+      const int kind = rand() % 5;  // 0 dense, 1 diag-1, 2 controlled dense, 3 x (0..2 controls), 4 multi-target diag
+      int perm[4] = {0, 1, 2, 3};
+      for (int i = 3; i > 0; --i) {
+        int j = rand() % (i + 1);
+        int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+      }
+      b.is_x = false;
+      b.nderiv = 0;
+      int nt = 1, nc = 0;
+      b.cls = OP_DENSE;
+      if (kind == 1) b.cls = OP_DIAG;
+      if (kind == 2) nc = 1 + rand() % 2;
+      if (kind == 3) { b.is_x = true; nc = rand() % 3; }
+      if (kind == 4) { b.cls = OP_DIAG; nt = 2 + rand() % 2; nc = rand() % (5 - nt); }
+      if (kind <= 2) b.nderiv = rand() % 3;
+      if (kind == 1 && (rand() & 1)) nc = 1;
+      int treg[4], creg[4];
+      for (int i = 0; i < nt; ++i) { treg[i] = perm[i]; b.targets.push_back(reg[perm[i]]); }
+      for (int i = 0; i < nc; ++i) { creg[i] = perm[nt + i]; b.controls.push_back(reg[perm[nt + i]]); }
+      const int count = b.cls == OP_DIAG ? (1 << nt) : 4;
+      for (int i = 0; i < count * (1 + b.nderiv); ++i) b.pay.push_back(mk<float>((float)urand(), (float)urand()));
+      if (b.is_x) { b.pay[0] = mk<float>(0, 0); b.pay[1] = mk<float>(1, 0); b.pay[2] = mk<float>(1, 0); b.pay[3] = mk<float>(0, 0); }
+      OpDesc d;
+      rg_make_sub(b.cls, nt, treg, nc, creg, b.is_x, count, b.nderiv, d);
+      d.pay_off = (uint32_t)payload.size();
+      payload.insert(payload.end(), b.pay.begin(), b.pay.end());
+      if (payload.size() & 1) payload.push_back(mk<float>(0, 0));
+      blks.push_back(b);
+      descs.push_back(d);
+    }
+    // tiles
+    std::vector<zc> ref(n), lam_ref(n);
+    std::vector<cf32> sp(n), sl(n);
+    for (uint32_t i = 0; i < n; ++i) {
+      cf32 v = mk<float>((float)urand(), (float)urand()), w = mk<float>((float)urand(), (float)urand());
+      ref[i] = Z(v);
+      lam_ref[i] = Z(w);
+      sp[rg_phys(i)] = v;
+      sl[rg_phys(i)] = w;
+    }
+    const RgGeom G = rg_geom(h);
+    // forward on sp
+    for (uint32_t g = 0; g < (n >> 4); ++g) {
+      const uint32_t pb = rg_base(G, g);
+      cf32 a[16];
+      for (int j = 0; j < 16; ++j) a[j] = sp[pb ^ G.off[j]];
+      for (int i = 0; i < nsub; ++i) rg_fwd_sub(a, descs[i], payload.data() + descs[i].pay_off);
+      for (int j = 0; j < 16; ++j) sp[pb ^ G.off[j]] = a[j];
+    }
+    for (int i = 0; i < nsub; ++i) ref_apply(ref, m, blks[i], false);
+    double err = 0, nrm = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      err = fmax(err, std::abs(Z(sp[rg_phys(i)]) - ref[i]));
+      nrm = fmax(nrm, std::abs(ref[i]));
+    }
+    CHECK(err <= 2e-5 * nrm, "forward trial %d: err %g (max %g)", trial, err, nrm);
+    // adjoint: the same descriptors in reverse order on (sp, sl); reference un-applies block by block
+    std::vector<double> grad(64, 0.0), grad_ref(64, 0.0);
+    std::vector<int> slot0(nsub);
+    int ns = 0;
+    for (int i = 0; i < nsub; ++i) { slot0[i] = ns; ns += blks[i].nderiv; }
+    for (uint32_t g = 0; g < (n >> 4); ++g) {
+      const uint32_t pb = rg_base(G, g);
+      cf32 a[16], l[16];
+      for (int j = 0; j < 16; ++j) { a[j] = sp[pb ^ G.off[j]]; l[j] = sl[pb ^ G.off[j]]; }
+      for (int i = nsub - 1; i >= 0; --i) {
+        cf32 W[4];
+        const cf32* pay = payload.data() + descs[i].pay_off;
+        if (rg_bwd_sub(a, l, descs[i], pay, W))
+          for (int e = 0; e < descs[i].nderiv; ++e) grad[slot0[i] + e] += rg_grad_term(W, pay, descs[i].count, e);
+      }
+      for (int j = 0; j < 16; ++j) { sp[pb ^ G.off[j]] = a[j]; sl[pb ^ G.off[j]] = l[j]; }
+    }
+    for (int i = nsub - 1; i >= 0; --i) {
+      ref_apply(ref, m, blks[i], true);  // psi_prev
+      for (int e = 0; e < blks[i].nderiv; ++e) grad_ref[slot0[i] + e] = ref_grad(ref, lam_ref, m, blks[i], e);
+      ref_apply(lam_ref, m, blks[i], true);
+    }
+    double e1 = 0, e2 = 0, n1 = 0, n2 = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      e1 = fmax(e1, std::abs(Z(sp[rg_phys(i)]) - ref[i]));
+      e2 = fmax(e2, std::abs(Z(sl[rg_phys(i)]) - lam_ref[i]));
+      n1 = fmax(n1, std::abs(ref[i]));
+      n2 = fmax(n2, std::abs(lam_ref[i]));
+    }
+    CHECK(e1 <= 1e-4 * n1 && e2 <= 1e-4 * n2, "adjoint trial %d: err %g %g (max %g %g)", trial, e1, e2, n1, n2);
+    for (int sidx = 0; sidx < ns; ++sidx) {
+      double scale = fmax(1.0, fabs(grad_ref[sidx]));
+      CHECK(fabs(grad[sidx] - grad_ref[sidx]) <= 2e-3 * scale * sqrt((double)n) / 16.0 + 1e-3 * scale, "gradient trial %d slot %d: %g vs %g", trial, sidx, grad[sidx],
+            grad_ref[sidx]);
+    }
+  }
+  if (fails) {
+    printf("rg_check: %d failures\n", fails);
+    return 1;
+  }
+  printf("rg_check: ok\n");
+  return 0;
+}

@@ -1,0 +1,86 @@
+"""GPU parity of the register-group sweeps (plan_opts["structure"] = 2, csrc/tq_sv_rg.cuh): same values and gradients as
+the reference fixtures and the oracle, in the whole-state kernels and in forced HBM tiles; circuits that do not
+qualify fall back to the default sweeps."""
+import numpy as np
+import pytest
+import torch
+
+import tedq_b200 as qb
+from conftest import case_id, load_golden
+from helpers import TOL, assert_close, build, cdtype, golden_out, rdtype
+from oracle import sv_ref
+from tedq_b200 import workloads as W
+from test_engine_gpu import run_engine
+
+pytestmark = pytest.mark.gpu
+CASES = load_golden("sv_cases.json")
+RG_CASES = [c for c in CASES if c["dtype"] == "c64" and c["spec"]["num_qubits"] >= 9]
+TILES = {"whole": {}, "tiled": {"max_local_qubits_fwd": 9, "max_local_qubits_bwd": 9, "coalesce_bits": 3},
+         "tiled10": {"max_local_qubits_fwd": 11, "max_local_qubits_bwd": 10, "coalesce_bits": 2}}
+
+
+def qualifies(spec):
+    return not ({g[0] for g in spec["gates"]} & {"SWAP", "CSWAP"})
+
+
+@pytest.mark.parametrize("case", RG_CASES, ids=case_id)
+@pytest.mark.parametrize("tiles", list(TILES), ids=list(TILES))
+def test_register_group_sweeps_match_reference_fixture(case, tiles):
+    n = case["spec"]["num_qubits"]
+    opts = dict(TILES[tiles], structure=2)
+    if tiles != "whole" and n <= opts["max_local_qubits_fwd"]:
+        pytest.skip("state fits one tile")
+    out, grad = run_engine(case, opts)
+    assert_close(out, golden_out(case), TOL["c64"], "out")
+    if grad is not None:
+        assert_close(grad, np.asarray(case["grad"]), TOL["c64"], "grad")
+    cc = build(case, "c64", case["flat"][0]).compilecircuit(backend="pytorch_b200", dtype=torch.complex64, plan_opts=opts)
+    groups = cc.plan().num_register_groups(False), cc.plan().num_register_groups(True)
+    if qualifies(case["spec"]):
+        assert groups[0] > 0 and groups[1] > 0, "the plan did not take the register-group sweeps"
+    else:
+        assert groups == (0, 0)
+
+
+POOL = ["Hadamard", "PauliX", "PauliY", "PauliZ", "S", "T", "SX", "RX", "RY", "RZ", "Rot", "PhaseShift",
+        "CNOT", "CZ", "CY", "ControlledPhaseShift", "CRX", "CRY", "CRZ", "Toffoli"]
+MEAS = [
+    [["expval", [["PauliZ", [0]]]], ["expval", [["PauliX", [3]]]], ["expval", [["PauliZ", [1]], ["PauliZ", [7]]]]],
+    [["probs", [2, 5]]],
+    [["state"]],
+    [["probs", None]],
+]
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("tiles", ["whole", "tiled"])
+def test_register_group_sweeps_match_oracle_on_random_circuits(seed, tiles):
+    """Every gate kind a register group can hold (dense / diagonal one-target blocks with 0-2 controls, controlled-X
+    swaps, multi-target diagonals), every measurement kind, 3 parameter sets."""
+    n = 10 + seed % 3
+    spec = W.random_circuit(n, 70 + 10 * seed, 300 + seed, gate_pool=POOL, meas=MEAS[seed % len(MEAS)])
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float32))
+    opts = dict(TILES[tiles], structure=2)
+    cc = circ.compilecircuit(backend="pytorch_b200", dtype=torch.complex64, plan_opts=opts)
+    flat = torch.tensor(np.random.RandomState(seed).uniform(-np.pi, np.pi, (3, spec["n_params"])), dtype=torch.float32)
+    x = flat.cuda().requires_grad_(True)
+    y = cc.batched(x)
+    yr = torch.view_as_real(y) if y.is_complex() else y
+    ct = torch.tensor(np.random.RandomState(100 + seed).uniform(-1, 1, tuple(yr.shape[1:])), dtype=torch.float32)
+    (yr * ct.cuda()).sum().backward()
+    ref_y, ref_g = sv_ref.run_batch(circ, flat, torch.complex64, torch.view_as_complex(ct.contiguous()) if y.is_complex() else ct)
+    assert cc.plan().num_register_groups(False) > 0 and cc.plan().num_register_groups(True) > 0
+    assert_close(y.detach().cpu().numpy().reshape(3, -1), ref_y.numpy().reshape(3, -1), 1e-5, "out")
+    assert_close(x.grad.cpu().numpy(), ref_g.numpy(), 4e-5, "grad")
+
+
+def test_register_group_request_falls_back_when_the_circuit_does_not_qualify():
+    spec = W.random_circuit(10, 40, 5, gate_pool=["RX", "SWAP", "CNOT", "RY"])
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float32))
+    flat = torch.rand(2, spec["n_params"])
+    outs = []
+    for opts in (None, {"structure": 2}):
+        cc = circ.compilecircuit(backend="pytorch_b200", dtype=torch.complex64, plan_opts=opts)
+        outs.append(cc.batched(flat.cuda()).cpu().numpy())
+        assert cc.plan().num_register_groups(False) == 0
+    assert np.array_equal(outs[0], outs[1])
