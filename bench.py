@@ -446,7 +446,7 @@ def measure_sv(name, steps, warmup, device, dist, do_cpu, cpu_budget=10.0, with_
     ach_gbs = bytes_b / (bwd_ms * 1e-3) / 1e9
     ach_tf = fl_b / (bwd_ms * 1e-3) / 1e12
     res["roofline"] = {
-        "kernel": "k_sweep_bwd", "bound": bound,
+        "kernel": "k_rg_bwd" if plan.num_register_groups(True) else "k_sweep_bwd", "bound": bound,
         "achieved": ach_gbs if bound == "hbm" else ach_tf,
         "peak": pk["hbm_gbs"] if bound == "hbm" else pipe_peak,
         "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
@@ -460,6 +460,7 @@ def measure_sv(name, steps, warmup, device, dist, do_cpu, cpu_budget=10.0, with_
                 "achieved_tflops": fl_f / (fwd_avg * 1e-3) / 1e12},
         "bwd_ms": bwd_ms, "sweeps_bwd": plan.num_sweeps(True), "sweeps_fwd": plan.num_sweeps(False),
         "launch_ms": bwd_ms / max(1, plan.num_sweeps(True)),
+        "register_groups": {"fwd": plan.num_register_groups(False), "bwd": plan.num_register_groups(True)},
         "note": ("state resident in shared memory for the whole circuit: HBM sees parameters, outputs and gradients only"
                  if resident else "tiled sweeps: each sweep reads+writes psi (and lambda) once"),
     }

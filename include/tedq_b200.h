@@ -100,15 +100,20 @@ typedef struct tq_plan_opts {
   int32_t coalesce_bits;        /* -1 = default. low amplitude-index bits always kept tile-local     */
   int32_t threads;              /* 0 = default CTA size                                              */
   int32_t fuse;                 /* -1 = default (1). 1: fuse runs of gates in registers               */
-  int32_t structure;            /* 0 = default: every fused block is a dense complex matrix.  1 (experimental): blocks
-                                   of real gates (RY, CRY, H, X, CNOT, ...) take real-matrix paths with half the
-                                   multiplies, and one-qubit diagonal gates (RZ, PhaseShift, S, T, Z) stay out of the
-                                   blocks and are merged, per sweep, into diagonal-layer passes (two phase tables,
-                                   signed-sum gradients).  Same results; measured slower on B200.
-                                   2: register-group sweeps (complex64, >= 9 qubits, every gate a (controlled)
-                                   one-target block or a diagonal): a thread keeps the 16 amplitudes of four tile bits
-                                   in registers across a run of blocks; one-qubit runs stay 2x2, controlled-X gates are
-                                   register swaps.  A circuit that does not qualify silently keeps the default sweeps
+  int32_t structure;            /* 0 = default: automatic.  complex64 circuits of >= 9 qubits whose gates are all
+                                   (controlled) one-target blocks or diagonals take the register-group sweeps (2) when
+                                   those remove at least a third of the multiply-adds of the default fusion (layers of
+                                   one-qubit gates between sparse entanglers); everything else takes the default sweeps,
+                                   where every fused block is a dense complex matrix.
+                                   -1: the default sweeps whatever the circuit.
+                                   1 (experimental): blocks of real gates (RY, CRY, H, X, CNOT, ...) take real-matrix
+                                   paths with half the multiplies, and one-qubit diagonal gates (RZ, PhaseShift, S, T,
+                                   Z) stay out of the blocks and are merged, per sweep, into diagonal-layer passes (two
+                                   phase tables, signed-sum gradients).  Same results; measured slower on B200.
+                                   2: register-group sweeps whenever the circuit qualifies: a thread keeps the 16
+                                   amplitudes of four tile bits in registers across a run of blocks; one-qubit runs stay
+                                   2x2, X / CNOT blocks at the ends of a run are folded into the load / store addresses.
+                                   A circuit that does not qualify silently keeps the default sweeps
                                    (tq_plan_op_stats(what = 4) tells which)                                          */
   int32_t reserved[2];
 } tq_plan_opts;
@@ -225,6 +230,17 @@ typedef struct tq_tn_step {
  * Python mirror planner._subtree_dp_py.  Returns 0 or a negative tq_status. */
 int32_t tq_tn_subtree_order(int32_t n_leaves, int32_t n_idx, const int32_t* leaf_open, const int32_t* inside,
                             const int32_t* count, const double* time_model, double* best_full, int32_t* split);
+
+/* Planner, host only: one randomised greedy pass (ted-q_b200/planner.py: _greedy_once, whose path it reproduces bit for
+ * bit — same operations, same libm calls).  Inputs i = 0 .. n_inputs-1 carry the indices idx[idx_off[i] .. idx_off[i+1])
+ * (renumbered 0 .. n_idx-1), keep[x] != 0 marks the network's output indices.  Candidate pairs are scored
+ * log2-compressed |out| - alpha (|a| + |b|) minus temperature x Gumbel noise and contracted best first; init_pairs lists
+ * the pairs that share an index in the order the caller wants them scored (2 ids per pair), u[] supplies one uniform
+ * random number per scored pair when temperature > 0.  Writes the ssa path (2 (n_inputs - 1) ids; the k-th contraction
+ * creates id n_inputs + k) and the count of random numbers consumed.  TQ_E_WORKSPACE: u was too short. */
+int32_t tq_tn_greedy_path(int32_t n_inputs, int32_t n_idx, const int32_t* idx_off, const int32_t* idx, const int32_t* keep,
+                          int32_t n_init, const int32_t* init_pairs, const double* u, int64_t n_u, double alpha,
+                          double temperature, int32_t* path, int64_t* n_u_used);
 
 /* Lower an ssa path over n_in input tensors into steps (host only).  sliced[] index ids become per-slice base
  * offsets of the inputs that carry them: slice_tensor[i], slice_ord[i], slice_bit[i] (count returned in

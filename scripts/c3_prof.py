@@ -3,7 +3,7 @@ sys.path.insert(0, ".")
 import numpy as np, torch
 import tedq_b200 as qb
 from tedq_b200 import workloads as W
-structure = int(sys.argv[1]) if len(sys.argv) > 1 else 0    # tq_plan_opts.structure: 1 = real blocks + diagonal layers
+structure = int(sys.argv[1]) if len(sys.argv) > 1 else 0    # tq_plan_opts.structure: -1 default sweeps, 0 automatic, 1 real blocks + diagonal layers, 2 register groups
 spec = W.hea(20, 10)
 circ = W.build_circuit(spec, qb)
 B = 16

@@ -9,8 +9,9 @@ spec = W.hea(20, 10)
 circ = W.build_circuit(spec, qb)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 x = torch.tensor(np.random.RandomState(0).rand(B, spec["n_params"]), dtype=torch.float32, device="cuda")
-variants = [{}, {"structure": 2}, {"structure": 2, "max_local_qubits_bwd": 13}, {"structure": 2, "max_local_qubits_fwd": 14},
-            {"structure": 2, "max_local_qubits_fwd": 12, "max_local_qubits_bwd": 11}]
+variants = [{"structure": -1}, {}, {"structure": 2, "coalesce_bits": 2}, {"structure": 2, "coalesce_bits": 1}]
+if len(sys.argv) > 2:
+    variants = [eval(v) for v in sys.argv[2:]]
 ref = None
 for opts in variants:
     cc = circ.compilecircuit(backend="pytorch_b200", plan_opts=opts or None)

@@ -85,6 +85,10 @@ def lib() -> C.CDLL:
     L.tq_tn_subtree_order.restype = i32
     L.tq_tn_subtree_order.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(i32)]
+    L.tq_tn_greedy_path.restype = i32
+    L.tq_tn_greedy_path.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, C.POINTER(i32),
+                                    C.POINTER(C.c_double), i64, C.c_double, C.c_double, C.POINTER(i32),
+                                    C.POINTER(i64)]
     for name in ("tq_plan_num_qubits", "tq_plan_num_params"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = i32
@@ -237,6 +241,9 @@ def on_device(index: int):
     import torch
 
     return torch.cuda.device(index) if index >= 0 else contextlib.nullcontext()
+
+
+E_WORKSPACE = -4   # TQ_E_WORKSPACE
 
 
 def check(rc: int, what: str):

@@ -1,11 +1,16 @@
-// tq_planner.cu — host-only part of the contraction planner that is worth compiling: the dynamic programme of the
+// tq_planner.cu — host-only parts of the contraction planner that are worth compiling: the randomised greedy pass
+// (planner.py: _greedy_once; tq_tn_greedy_path below is its bit-identical mirror) and the dynamic programme of the
 // subtree reconfiguration (planner.py: reconfigure).  For a subtree with L <= 12 leaves it finds, over all subsets
 // of the leaves, the cheapest order of contracting them pairwise.  planner._subtree_dp_py is the Python mirror
 // (tests/test_planner_cpu.py checks bit-equality of costs and splits); the reference's counterpart is the external
 // cotengra / jdtensorpath search called at compiled_circuit.py:340-393.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <queue>
+#include <set>
+#include <tuple>
 #include <vector>
 
 #include "tq_common.h"
@@ -86,6 +91,155 @@ int32_t tq_tn_subtree_order(int32_t n_leaves, int32_t n_idx, const int32_t* leaf
     split[S] = bs;
   }
   *best_full = best[full];
+  return TQ_OK;
+}
+
+// One randomised greedy pass over an all-extent-2 network (planner._greedy_once, same operations in the same order
+// and the same libm calls, so the path is identical to the Python mirror's).
+//   idx_off[n_inputs + 1], idx[]: index lists of the inputs, indices renumbered 0 .. n_idx-1
+//   keep[n_idx]: 1 for the network's output indices
+//   init_pairs[2 * n_init]: the pairs of tensors that share an index, in the order the mirror pushes them
+//   u[n_u]: uniform random numbers in [0, 1), one per push when temperature > 0
+// Writes the ssa path (2 * (n_inputs - 1) ids) and the number of random numbers consumed.  TQ_E_WORKSPACE: u was too
+// short (call again with more).
+int32_t tq_tn_greedy_path(int32_t n_inputs, int32_t n_idx, const int32_t* idx_off, const int32_t* idx, const int32_t* keep,
+                          int32_t n_init, const int32_t* init_pairs, const double* u, int64_t n_u, double alpha,
+                          double temperature, int32_t* path, int64_t* n_u_used) {
+  TQ_REQUIRE(n_inputs >= 1 && n_idx >= 0 && idx_off && keep && path && n_u_used && (n_init == 0 || init_pairs), TQ_E_INVALID,
+             "tq_tn_greedy_path: invalid argument");
+  const int words = (std::max(n_idx, 1) + 63) / 64;
+  const int max_ids = 2 * n_inputs;
+  std::vector<uint64_t> bits((size_t)max_ids * words, 0);
+  std::vector<int> size(max_ids, 0);
+  std::vector<char> alive(max_ids, 0);
+  std::vector<std::set<int>> where((size_t)std::max(n_idx, 1));
+  auto at = [&](int t) { return bits.data() + (size_t)t * words; };
+  for (int i = 0; i < n_inputs; ++i) {
+    alive[i] = 1;
+    for (int k = idx_off[i]; k < idx_off[i + 1]; ++k) {
+      const int x = idx[k];
+      TQ_REQUIRE(x >= 0 && x < n_idx, TQ_E_INVALID, "tq_tn_greedy_path: index out of range");
+      if (!((at(i)[x >> 6] >> (x & 63)) & 1ull)) {
+        at(i)[x >> 6] |= 1ull << (x & 63);
+        ++size[i];
+      }
+      where[x].insert(i);
+    }
+  }
+  // the indices of a x b that survive: output indices and indices some third tensor still holds
+  std::vector<uint64_t> tmp(words);
+  auto result_of = [&](int a, int b) {
+    int cnt = 0;
+    for (int w = 0; w < words; ++w) {
+      uint64_t un = at(a)[w] | at(b)[w], out = 0;
+      while (un) {
+        const int bit = __builtin_ctzll(un);
+        un &= un - 1;
+        const int x = w * 64 + bit;
+        bool stays = keep[x] != 0;
+        if (!stays)
+          for (int t : where[x])
+            if (t != a && t != b) {
+              stays = true;
+              break;
+            }
+        if (stays) {
+          out |= 1ull << bit;
+          ++cnt;
+        }
+      }
+      tmp[w] = out;
+    }
+    return cnt;
+  };
+  typedef std::tuple<double, int, int> Item;
+  std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+  int64_t used = 0;
+  bool starved = false;
+  auto push = [&](int a, int b) {
+    const int so = result_of(a, b);
+    const double cost = std::ldexp(1.0, so) - alpha * (std::ldexp(1.0, size[a]) + std::ldexp(1.0, size[b]));
+    double score = std::copysign(std::log2(std::fabs(cost) + 1.0), cost);
+    if (temperature > 0) {
+      if (used >= n_u) {
+        starved = true;
+        return;
+      }
+      const double r = u[used++];
+      score -= temperature * (-std::log(-std::log(r + 1e-300) + 1e-300));
+    }
+    heap.push(Item(score, a, b));
+  };
+  for (int k = 0; k < n_init && !starved; ++k) push(init_pairs[2 * k], init_pairs[2 * k + 1]);
+  int next_id = n_inputs, n_path = 0;
+  while (!heap.empty() && !starved) {
+    const Item top = heap.top();
+    heap.pop();
+    const int a = std::get<1>(top), b = std::get<2>(top);
+    if (!alive[a] || !alive[b]) continue;
+    const int so = result_of(a, b);
+    const int c = next_id++;
+    std::memcpy(at(c), tmp.data(), sizeof(uint64_t) * words);
+    size[c] = so;
+    for (int side = 0; side < 2; ++side) {
+      const int t = side ? b : a;
+      for (int w = 0; w < words; ++w) {
+        uint64_t v = at(t)[w];
+        while (v) {
+          const int bit = __builtin_ctzll(v);
+          v &= v - 1;
+          where[w * 64 + bit].erase(t);
+        }
+      }
+      alive[t] = 0;
+    }
+    alive[c] = 1;
+    path[2 * n_path] = a;
+    path[2 * n_path + 1] = b;
+    ++n_path;
+    std::set<int> nbrs;
+    for (int w = 0; w < words; ++w) {
+      uint64_t v = at(c)[w];
+      while (v) {
+        const int bit = __builtin_ctzll(v);
+        v &= v - 1;
+        std::set<int>& h = where[w * 64 + bit];
+        nbrs.insert(h.begin(), h.end());
+        h.insert(c);
+      }
+    }
+    for (int t : nbrs) {
+      push(t, c);
+      if (starved) break;
+    }
+  }
+  if (starved) {
+    ::tq::set_error("tq_tn_greedy_path: %lld random numbers were not enough", (long long)n_u);
+    return TQ_E_WORKSPACE;
+  }
+  // disconnected leftovers: outer products, smallest first
+  std::vector<int> rest;
+  for (int t = 0; t < next_id; ++t)
+    if (alive[t]) rest.push_back(t);
+  auto by_size = [&](int x, int y) { return size[x] != size[y] ? size[x] < size[y] : x < y; };
+  std::sort(rest.begin(), rest.end(), by_size);
+  while (rest.size() > 1) {
+    const int a = rest[0], b = rest[1], c = next_id++;
+    int cnt = 0;
+    for (int w = 0; w < words; ++w) {
+      at(c)[w] = at(a)[w] | at(b)[w];
+      cnt += __builtin_popcountll(at(c)[w]);
+    }
+    size[c] = cnt;
+    path[2 * n_path] = a;
+    path[2 * n_path + 1] = b;
+    ++n_path;
+    rest.erase(rest.begin(), rest.begin() + 2);
+    rest.push_back(c);
+    std::sort(rest.begin(), rest.end(), by_size);
+  }
+  TQ_REQUIRE(n_path == n_inputs - 1, TQ_E_INVALID, "tq_tn_greedy_path: %d steps for %d inputs", n_path, n_inputs);
+  *n_u_used = used;
   return TQ_OK;
 }
 

@@ -92,6 +92,7 @@ struct tq_plan {
   bool structure = false;  // tq_plan_opts.structure: the sweeps run the kernel instantiations with the real / diagonal-layer paths
   bool rg = false;         // tq_plan_opts.structure = 2 and the circuit qualifies: register-group sweeps (tq_sv_rg.cuh)
   int n_rg[2] = {0, 0};    // register groups emitted per direction
+  int n_rg_folded[2] = {0, 0};  // X / CNOT blocks folded into group load / store addresses
   int m_f = 0, m_b = 0, coalesce = 0, threads_f = 256, threads_b = 256, fuse = 1;
   std::vector<Sweep> fwd, bwd;
   int n_ops[2] = {0, 0}, n_dl[2] = {0, 0}, n_dl_members[2] = {0, 0}, n_real[2] = {0, 0};  // emitted ops per direction
@@ -512,10 +513,15 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   // into diagonal-layer passes.  Off by default: on the 20-qubit HEA it halves the multiplies but needs 247 passes
   // over the tile instead of 190 and executes MORE instructions in total (2.70e9 vs 2.53e9 per 16 sets, ncu) — the
   // per-pass overhead (descriptor, matrix load, index arithmetic, barrier) outweighs the saved FMAs
-  bool diag_layers = false, want_rg = false;
+  bool diag_layers = false, want_rg = false, auto_rg = true;
   if (opts) {
     diag_layers = opts->structure == 1;
     want_rg = opts->structure == 2;
+    auto_rg = opts->structure == 0 && opts->threads == 0;  // -1: the default sweeps whatever the circuit
+    if (opts->structure < -1 || opts->structure > 2) {
+      set_error("tq_plan_create: structure = %d (expected -1 .. 2)", opts->structure);
+      return TQ_E_INVALID;
+    }
     if (opts->max_local_qubits_fwd > 0) m_f = full_f = opts->max_local_qubits_fwd;
     if (opts->max_local_qubits_bwd > 0) m_b = full_b = opts->max_local_qubits_bwd;
     if (opts->coalesce_bits >= 0) coalesce = opts->coalesce_bits;
@@ -655,23 +661,19 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
 
   // ---- register-group mode (structure = 2): complex64, tiles of >= 2^9 amplitudes, and every gate either a (controlled)
   // one-target block or a diagonal — anything else (SWAP, a dense two-qubit Unitary) keeps the default sweeps
-  bool rg = want_rg && c64 && std::min(m_f, m_b) >= RG_MIN_TILE;
+  bool rg = (want_rg || auto_rg) && c64 && std::min(m_f, m_b) >= RG_MIN_TILE;
   for (int gi = 0; gi < n_gates && rg; ++gi) {
     const HostGate& g = p->gates[gi];
     if (g.noop) continue;
     if (g.cls == OP_DENSE && g.targets.size() != 1) rg = false;
     if (g.cls == OP_DIAG && g.targets.size() > 1 && g.ntrain > 0) rg = false;
   }
-  p->rg = rg;
-  if (rg) {
-    p->threads_f = std::min(256, 1 << (m_f - RG_BITS));
-    p->threads_b = std::min(256, 1 << (m_b - RG_BITS));
-  }
 
   // ---- fusion: runs of gates inside one qubit or one qubit pair become one dense block -------------
   const int pay_cap_entries = CHUNK_PAY_BYTES / (int)csize(dtype);
   std::vector<HostBlock> all;
-  {
+  auto fuse_gates = [&](bool rg, std::vector<HostBlock>& all) {
+    all.clear();
     std::vector<int> owner(n, -1);
     auto can_add = [&](const HostBlock& b, const HostGate& g, int extra_deriv) {
       if (!fuse) return false;
@@ -761,7 +763,45 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       all.push_back(b);
       owner[g.qubits[0]] = owner[g.qubits[1]] = (int)all.size() - 1;
     }
+  };
+  // multiply-adds per evaluation of a fusion result (a fused block is a dense matrix on its qubits; a lone gate keeps
+  // its own structure; X / CNOT cost nothing in a register group)
+  auto fused_macs = [&](const std::vector<HostBlock>& blocks, bool rg_mode) {
+    double macs = 0.0;
+    for (const HostBlock& b : blocks) {
+      if (!b.alive) continue;
+      if (b.members.size() > 1) {
+        macs += ldexp(1.0, n + (int)b.qubits.size());
+        continue;
+      }
+      const HostGate& g = p->gates[b.members[0]];
+      const bool x = g.kind == TQ_G_FIXED && g.cls == OP_DENSE && g.targets.size() == 1 && g.red_count == 4 &&
+                     p->fixed[g.red_off] == zc(0, 0) && p->fixed[g.red_off + 1] == zc(1, 0) &&
+                     p->fixed[g.red_off + 2] == zc(1, 0) && p->fixed[g.red_off + 3] == zc(0, 0);
+      if (x) continue;  // a permutation: data movement only, in either mode
+      double per = ldexp(1.0, (int)g.targets.size());          // dense: 2^t multiply-adds per amplitude it touches
+      if (g.cls == OP_DIAG) per = rg_mode && g.targets.size() == 1 ? 2.0 : 1.0;  // (a register group runs it as a 2x2)
+      macs += ldexp(1.0, n - (int)g.controls.size()) * per;
+    }
+    return macs;
+  };
+  if (rg && auto_rg && !want_rg) {
+    // automatic choice: register groups only where keeping the one-qubit runs 2x2 removes at least a third of the
+    // arithmetic of the default fusion (layers of one-qubit gates between sparse entanglers: QNN / HEA circuits);
+    // circuits whose pair blocks fold many gates (the many-body-localisation Trotter steps) keep the default sweeps
+    std::vector<HostBlock> a0, a1;
+    fuse_gates(false, a0);
+    fuse_gates(true, a1);
+    rg = fused_macs(a1, true) <= 0.67 * fused_macs(a0, false);
   }
+  p->rg = rg;
+  if (rg) {
+    coalesce = std::max(coalesce, 1);  // the tile <-> state copies move pairs of amplitudes
+    p->coalesce = coalesce;
+    p->threads_f = std::min(256, 1 << (m_f - RG_BITS));
+    p->threads_b = std::min(256, 1 << (m_b - RG_BITS));
+  }
+  fuse_gates(rg, all);
   // resolve blocks -> ops + materialisation program
   for (HostBlock& b : all) {
     if (!b.alive) continue;
@@ -936,6 +976,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     std::vector<std::vector<int>> sg, sb;
     schedule(n, dir ? m_b : m_f, coalesce, p->blocks, dir ? order_b : order_f, sg, sb);
     std::vector<Sweep>& sweeps = dir ? p->bwd : p->fwd;
+    std::vector<int> folded;  // register-group mode: X / CNOT blocks folded into load / store addresses
     std::vector<OpDesc>& ops = dir ? ops_b : ops_f;
     std::vector<ChunkInfo>& chunks = dir ? chunks_b : chunks_f;
     int64_t& stride = dir ? p->stride_b : p->stride_f;
@@ -961,38 +1002,26 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
             if (tb[j] == b) return j;
           return -1;
         };
+        // the sweep's blocks as the grouper sees them (rg_next_group, tq_sv_rg.cuh)
+        std::vector<RgItem> items(p->blocks.size());
+        for (int bi : sg[s]) {
+          const HostBlock& hb = p->blocks[bi];
+          RgItem& it = items[bi];
+          it.nbits = 0;
+          for (int q : hb.targets) it.bits[it.nbits++] = local(q);
+          for (int q : hb.controls) it.bits[it.nbits++] = local(q);
+          for (int k = 0; k < it.nbits; ++k)
+            TQ_REQUIRE(it.bits[k] >= 0, TQ_E_INVALID, "tq_plan_create: block outside its sweep's tile");
+          it.foldable = hb.is_x && hb.nderiv == 0 && hb.controls.size() <= 1;
+          it.pay = block_pay_entries(hb.count, hb.nderiv, dir != 0);
+        }
         std::vector<int> rest(sg[s]);
         while (!rest.empty()) {
-          std::vector<int> group, keep;
-          std::vector<char> inb(m_t, 0), blocked(m_t, 0);
-          int nbits = 0, pay = 0;
-          for (int bi : rest) {
-            const HostBlock& hb = p->blocks[bi];
-            bool ok = (int)group.size() < RG_MAX_SUB;
-            int need = 0;
-            std::vector<int> lb;
-            for (int q : hb.targets) lb.push_back(local(q));
-            for (int q : hb.controls) lb.push_back(local(q));
-            for (int b : lb) {
-              TQ_REQUIRE(b >= 0, TQ_E_INVALID, "tq_plan_create: block outside its sweep's tile");
-              if (blocked[b]) ok = false;
-              if (!inb[b]) ++need;
-            }
-            const int pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
-            if (ok && nbits + need <= RG_BITS && pay + pe <= pay_cap_entries) {
-              for (int b : lb)
-                if (!inb[b]) {
-                  inb[b] = 1;
-                  ++nbits;
-                }
-              pay += pe;
-              group.push_back(bi);
-            } else {
-              for (int b : lb) blocked[b] = 1;
-              keep.push_back(bi);
-            }
-          }
-          rest.swap(keep);
+          std::vector<int> pre, mid, post;
+          std::vector<char> inb;
+          rg_next_group(items, rest, m_t, pay_cap_entries, pre, mid, post, inb);
+          int pay = 0;
+          for (int bi : mid) pay += items[bi].pay;
           int used[RG_BITS], nu = 0, reg[RG_BITS];
           for (int b = 0; b < m_t; ++b)
             if (inb[b]) used[nu++] = b;
@@ -1003,8 +1032,17 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
               if (reg[i] == b) return i;
             return -1;
           };
+          auto fold = [&](const std::vector<int>& xs, bool forward_order) {
+            std::vector<int> tg, ct;
+            for (int bi : xs) {
+              const HostBlock& hb = p->blocks[bi];
+              tg.push_back(reg_index(hb.targets[0]));
+              ct.push_back(hb.controls.empty() ? -1 : reg_index(hb.controls[0]));
+            }
+            return rg_affine_map(tg.data(), ct.data(), (int)xs.size(), forward_order);
+          };
           // the header and its sub-ops travel in one prefetch chunk
-          if (open && (cur.op_count + 1 + group.size() > (size_t)CHUNK_OPS || (int)cur.pay_count + pay > pay_cap_entries)) {
+          if (open && (cur.op_count + 1 + mid.size() > (size_t)CHUNK_OPS || (int)cur.pay_count + pay > pay_cap_entries)) {
             chunks.push_back(cur);
             open = false;
           }
@@ -1016,14 +1054,17 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
             open = true;
           }
           OpDesc h;
-          memset(&h, 0, sizeof(h));
-          h.path = P_RG;
-          h.k = RG_BITS;
-          h.nins = (uint8_t)group.size();
-          for (int i = 0; i < RG_BITS; ++i) h.tpos[i] = (uint8_t)reg[i];
+          rg_pack_header(reg, (int)mid.size(), fold(pre, false), fold(post, true), h);
           ops.push_back(h);
           cur.op_count += 1;
-          for (int bi : group) {
+          // folded blocks still own a (never read) slot in the payload streams, placed behind the last sweep's
+          // payload: k_materialize writes every block
+          for (const std::vector<int>* xs : {&pre, &post})
+            for (int bi : *xs) {
+              folded.push_back(bi);
+              p->n_rg_folded[dir] += 1;
+            }
+          for (int bi : mid) {
             HostBlock& hb = p->blocks[bi];
             int treg[4], creg[4], nt = 0, nc = 0;
             for (int q : hb.targets) treg[nt++] = reg_index(q);
@@ -1044,6 +1085,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
             cur.pay_count += (uint32_t)pe;
             stride += pe;
           }
+          const std::vector<int>& group = mid;
           p->n_ops[dir] += (int)group.size();
           p->n_rg[dir] += 1;
         }
@@ -1157,6 +1199,11 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
       sw.n_chunks = (int)chunks.size() - sw.chunk_begin;
       sweeps.push_back(sw);
     }
+    for (int bi : folded) {
+      HostBlock& hb = p->blocks[bi];
+      (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;
+      stride += block_pay_entries(hb.count, hb.nderiv, dir != 0);
+    }
     stride = (stride + 31) & ~(int64_t)31;  // keep every set's stream 256-byte aligned
   }
   TQ_REQUIRE(p->stride_f < ((int64_t)1 << 31) && p->stride_b < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "circuit too long");
@@ -1200,11 +1247,13 @@ int32_t tq_plan_sweep_num_gates(const tq_plan* p, int32_t backward, int32_t s) {
 }
 int32_t tq_plan_num_blocks(const tq_plan* p) { return p ? (int32_t)p->blocks.size() : -1; }
 /* what = 0: ops emitted into the sweeps, 1: diagonal-layer ops, 2: their members, 3: ops on the real paths,
- * 4: register groups (structure = 2; 0 when the plan fell back to the default sweeps) */
+ * 4: register groups (structure = 2; 0 when the plan fell back to the default sweeps), 5: X / CNOT blocks folded into
+ * the groups' load / store addresses */
 int32_t tq_plan_op_stats(const tq_plan* p, int32_t backward, int32_t what) {
-  if (!p || what < 0 || what > 4) return -1;
+  if (!p || what < 0 || what > 5) return -1;
   const int d = backward ? 1 : 0;
   if (what == 4) return p->n_rg[d];
+  if (what == 5) return p->n_rg_folded[d];
   return what == 0 ? p->n_ops[d] : what == 1 ? p->n_dl[d] : what == 2 ? p->n_dl_members[d] : p->n_real[d];
 }
 int64_t tq_plan_out_reals(const tq_plan* p) { return p ? p->out_reals : -1; }

@@ -7,11 +7,15 @@
 // them in registers, and applies a whole run of blocks that live inside those four bits before it writes them back:
 //   * one shared-memory round trip per GROUP instead of per block,
 //   * one-qubit runs stay 2x2 (8 FMAs per amplitude instead of 16 for the 4x4 product they would be fused into),
-//   * CNOT / Toffoli-style controlled-X blocks are register swaps (no arithmetic),
+//   * CNOT / X blocks at the start or the end of a group cost nothing: a network of them is an affine map over GF(2)
+//     on the 4-bit register pattern, folded into the addresses the group loads from / stores to; controlled-X blocks
+//     in the middle of a group (and Toffoli) are register swaps,
 //   * the adjoint pass accumulates the 2x2 W of every block in registers: one warp reduction per block and thread.
 // The tile is stored XOR-swizzled (rg_phys) so that the 16 lanes of a half-warp always hit 16 different 8-byte bank
 // pairs whichever four bits are register bits.  Replaces pytorch_backend.py:365-379 + autograd like the default sweeps.
 #pragma once
+#include <vector>
+
 #include "tq_sv_kernels.cuh"
 
 namespace tq {
@@ -21,9 +25,13 @@ enum { RG_D1 = 0, RG_X1 = 1, RG_GEN = 2 };        // sub-op kinds (OpDesc.path o
 constexpr int RG_BITS = 4;                         // register bits of a group
 constexpr int RG_MAX_SUB = CHUNK_OPS - 1;          // header + sub-ops travel in one prefetch chunk
 constexpr int RG_MIN_TILE = 9;                     // 2^(m-4) >= 32 items: every lane of a warp owns a group
+constexpr uint32_t RG_MAP_ID = 0x8421u;            // identity relabelling
 
 // Header:  path = P_RG, nins = number of sub-ops, tpos[0..3] = register bits (tile-local amplitude-bit positions,
-//          ascending).
+//          ascending), and the swizzled word offsets of the LOAD and STORE relabellings, five 16-bit values each
+//          (RgAddr: offset of register pattern j = c ^ XOR_{b in j} b_b), packed by rg_pack_header.  A relabelling
+//          is an affine map over GF(2) on the register pattern j (bits 4b..4b+3 = image of the unit pattern e_b,
+//          bits 16..19 = constant): register j is loaded from the tile pattern load(j), stored to store(j).
 // Sub-op:  path = kind, k = register-bit INDEX (0..3) of the target (RG_D1, RG_X1), cmask = 16-bit "live" mask (bit j
 //          set when register pattern j satisfies the block's controls), nderiv / dslot / pay_off / count as in the
 //          default ops (count = 2: the payload is a diagonal, applied as a 2x2 with zero off-diagonals).
@@ -34,29 +42,76 @@ __host__ __device__ __forceinline__ uint32_t rg_phys(uint32_t i) {
   return i ^ ((i >> 4) & 15u) ^ ((i >> 8) & 15u) ^ ((i >> 12) & 15u);
 }
 
-struct RgGeom {
-  int r0, r1, r2, r3;
-  uint32_t off[16];  // swizzled word offset of register pattern j (XOR-linear: phys(base | off) = phys(base) ^ off[j])
+// the two 16-byte halves of an OpDesc, decoded
+struct RgSub {
+  uint32_t kind, k, nsub, nderiv, count, live, tlo, thi, pay_off, dslot;
 };
-
-__host__ __device__ __forceinline__ RgGeom rg_geom(const OpDesc& h) {
-  RgGeom G;
-  G.r0 = h.tpos[0];
-  G.r1 = h.tpos[1];
-  G.r2 = h.tpos[2];
-  G.r3 = h.tpos[3];
-  const uint32_t o1 = rg_phys(1u << G.r0), o2 = rg_phys(1u << G.r1), o4 = rg_phys(1u << G.r2), o8 = rg_phys(1u << G.r3);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) G.off[j] = ((j & 1) ? o1 : 0u) ^ ((j & 2) ? o2 : 0u) ^ ((j & 4) ? o4 : 0u) ^ ((j & 8) ? o8 : 0u);
-  return G;
+__host__ __device__ __forceinline__ RgSub rg_decode(uint4 w0, uint4 w1) {
+  RgSub d;
+  d.kind = w0.x & 255u;            // path
+  d.k = (w0.x >> 8) & 255u;        // k
+  d.nsub = (w0.x >> 16) & 255u;    // nins
+  d.nderiv = w0.x >> 24;           // nderiv
+  d.tlo = w0.y;                    // ins[0..3]
+  d.thi = w0.z;                    // tpos[0..3]
+  d.live = w0.w;                   // cmask
+  d.pay_off = w1.x;
+  d.dslot = w1.y;
+  d.count = w1.z;
+  return d;
 }
 
-__host__ __device__ __forceinline__ uint32_t rg_base(const RgGeom& G, uint32_t g) {
-  uint32_t b = insert_zero_bit(g, G.r0);
-  b = insert_zero_bit(b, G.r1);
-  b = insert_zero_bit(b, G.r2);
-  b = insert_zero_bit(b, G.r3);
+// word offsets (swizzled) of the 16 register patterns under an affine relabelling: off(j) = c ^ XOR_{b in j} b_b
+struct RgAddr {
+  uint32_t b1, b2, b4, b8, c;
+};
+__host__ __device__ __forceinline__ uint32_t rg_img(const uint32_t* o, uint32_t nib) {
+  return ((nib & 1u) ? o[0] : 0u) ^ ((nib & 2u) ? o[1] : 0u) ^ ((nib & 4u) ? o[2] : 0u) ^ ((nib & 8u) ? o[3] : 0u);
+}
+__host__ __device__ __forceinline__ RgAddr rg_addr(const uint32_t* o, uint32_t map) {
+  RgAddr A;
+  A.b1 = rg_img(o, map & 15u);
+  A.b2 = rg_img(o, (map >> 4) & 15u);
+  A.b4 = rg_img(o, (map >> 8) & 15u);
+  A.b8 = rg_img(o, (map >> 12) & 15u);
+  A.c = rg_img(o, (map >> 16) & 15u);
+  return A;
+}
+#define RG_OFF(A, j) ((A).c ^ (((j) & 1) ? (A).b1 : 0u) ^ (((j) & 2) ? (A).b2 : 0u) ^ (((j) & 4) ? (A).b4 : 0u) ^ (((j) & 8) ? (A).b8 : 0u))
+
+// header words: w0 = (x: path | k | nins | nderiv, y: ins, z: tpos, w: cmask), w1 = (x: pay_off, y: dslot, z: count)
+__host__ __device__ __forceinline__ RgAddr rg_header_load(const uint4 w0, const uint4 w1) {
+  RgAddr A;
+  A.b1 = w0.y & 0xffffu;
+  A.b2 = w0.y >> 16;
+  A.b4 = w0.w & 0xffffu;
+  A.b8 = w0.w >> 16;
+  A.c = w1.x & 0xffffu;
+  return A;
+}
+__host__ __device__ __forceinline__ RgAddr rg_header_store(const uint4 w1) {
+  RgAddr A;
+  A.b1 = w1.y & 0xffffu;
+  A.b2 = w1.y >> 16;
+  A.b4 = w1.z & 0xffffu;
+  A.b8 = w1.z >> 16;
+  A.c = w1.x >> 16;
+  return A;
+}
+
+// swizzled word index of the group's pattern-0 amplitude for item g (the m-4 non-register bits of the tile index)
+__host__ __device__ __forceinline__ uint32_t rg_base(uint32_t regbits /* tpos[0..3] packed */, uint32_t g) {
+  uint32_t b = insert_zero_bit(g, (int)(regbits & 255u));
+  b = insert_zero_bit(b, (int)((regbits >> 8) & 255u));
+  b = insert_zero_bit(b, (int)((regbits >> 16) & 255u));
+  b = insert_zero_bit(b, (int)(regbits >> 24));
   return rg_phys(b);
+}
+__host__ __device__ __forceinline__ void rg_bit_offsets(uint32_t regbits, uint32_t* o) {
+  o[0] = rg_phys(1u << (regbits & 255u));
+  o[1] = rg_phys(1u << ((regbits >> 8) & 255u));
+  o[2] = rg_phys(1u << ((regbits >> 16) & 255u));
+  o[3] = rg_phys(1u << (regbits >> 24));
 }
 
 // ---- arithmetic on the 16 register amplitudes (host-callable: tests/native/rg_check.cu runs the same code) ---------
@@ -93,14 +148,6 @@ __host__ __device__ __forceinline__ void rg_x1(cx<float> (&a)[16], uint32_t live
     }
 }
 
-// the sixteen 4-bit diagonal indices of an RG_GEN sub-op: patterns 0..7 in ins[0..3], 8..15 in tpos[0..3]
-__host__ __device__ __forceinline__ uint32_t rg_tab_lo(const OpDesc& d) {
-  return (uint32_t)d.ins[0] | ((uint32_t)d.ins[1] << 8) | ((uint32_t)d.ins[2] << 16) | ((uint32_t)d.ins[3] << 24);
-}
-__host__ __device__ __forceinline__ uint32_t rg_tab_hi(const OpDesc& d) {
-  return (uint32_t)d.tpos[0] | ((uint32_t)d.tpos[1] << 8) | ((uint32_t)d.tpos[2] << 16) | ((uint32_t)d.tpos[3] << 24);
-}
-
 template <bool ADJ>
 __host__ __device__ __forceinline__ void rg_gen(cx<float> (&a)[16], uint32_t tlo, uint32_t thi, uint32_t live,
                                                 const cx<float>* pay) {
@@ -114,46 +161,36 @@ __host__ __device__ __forceinline__ void rg_gen(cx<float> (&a)[16], uint32_t tlo
     }
 }
 
-// the 2x2 of a sub-op: dense payload (4 entries) or diagonal payload (2 entries); ADJ: conjugate transpose
+// the 2x2 of a sub-op from its first four payload entries p[0..3] (count = 2: p[0], p[1] are a diagonal); ADJ:
+// conjugate transpose
 template <bool ADJ>
-__host__ __device__ __forceinline__ void rg_ld2x2(const cx<float>* pay, uint32_t count, cx<float>* m) {
+__host__ __device__ __forceinline__ void rg_ld2x2(const cx<float>* p, uint32_t count, cx<float>* m) {
   const cx<float> z = mk<float>(0.f, 0.f);
   if (count == 2) {
-    m[0] = ADJ ? conj_(pay[0]) : pay[0];
+    m[0] = ADJ ? conj_(p[0]) : p[0];
     m[1] = z;
     m[2] = z;
-    m[3] = ADJ ? conj_(pay[1]) : pay[1];
+    m[3] = ADJ ? conj_(p[1]) : p[1];
   } else if (ADJ) {
-    m[0] = conj_(pay[0]); m[1] = conj_(pay[2]); m[2] = conj_(pay[1]); m[3] = conj_(pay[3]);
+    m[0] = conj_(p[0]); m[1] = conj_(p[2]); m[2] = conj_(p[1]); m[3] = conj_(p[3]);
   } else {
-    m[0] = pay[0]; m[1] = pay[1]; m[2] = pay[2]; m[3] = pay[3];
+    m[0] = p[0]; m[1] = p[1]; m[2] = p[2]; m[3] = p[3];
   }
 }
 
-__host__ __device__ __forceinline__ void rg_fwd_sub(cx<float> (&a)[16], const OpDesc& d, const cx<float>* pay) {
-  const uint32_t live = d.cmask;
-  switch (d.path) {
-    case RG_D1: {
-      cx<float> m[4];
-      rg_ld2x2<false>(pay, d.count, m);
-      switch (d.k) {
-        case 0: rg_d1<0>(a, m, live); break;
-        case 1: rg_d1<1>(a, m, live); break;
-        case 2: rg_d1<2>(a, m, live); break;
-        default: rg_d1<3>(a, m, live); break;
-      }
-    } break;
-    case RG_X1:
-      switch (d.k) {
-        case 0: rg_x1<0>(a, live); break;
-        case 1: rg_x1<1>(a, live); break;
-        case 2: rg_x1<2>(a, live); break;
-        default: rg_x1<3>(a, live); break;
-      }
-      break;
-    default: {
-      rg_gen<false>(a, rg_tab_lo(d), rg_tab_hi(d), live, pay);
-    } break;
+// forward sub-op; m = the 2x2 (RG_D1), pay = the payload (RG_GEN only)
+__host__ __device__ __forceinline__ void rg_fwd_sub(cx<float> (&a)[16], const RgSub& d, const cx<float>* m,
+                                                    const cx<float>* pay) {
+  switch (d.kind * 4u + (d.kind == RG_GEN ? 0u : d.k)) {
+    case RG_D1 * 4 + 0: rg_d1<0>(a, m, d.live); break;
+    case RG_D1 * 4 + 1: rg_d1<1>(a, m, d.live); break;
+    case RG_D1 * 4 + 2: rg_d1<2>(a, m, d.live); break;
+    case RG_D1 * 4 + 3: rg_d1<3>(a, m, d.live); break;
+    case RG_X1 * 4 + 0: rg_x1<0>(a, d.live); break;
+    case RG_X1 * 4 + 1: rg_x1<1>(a, d.live); break;
+    case RG_X1 * 4 + 2: rg_x1<2>(a, d.live); break;
+    case RG_X1 * 4 + 3: rg_x1<3>(a, d.live); break;
+    default: rg_gen<false>(a, d.tlo, d.thi, d.live, pay); break;
   }
 }
 
@@ -186,51 +223,35 @@ __host__ __device__ __forceinline__ void rg_bwd_d1(cx<float> (&a)[16], cx<float>
     if (!(j & tb) && ((live >> j) & 1u)) rg_bwd2(mh, a[j], a[j | tb], l[j], l[j | tb], W, has_d);
 }
 
-// what one thread adds to gradient slot e of a 2x2 sub-op: Re sum_rc dG_e[r][c] W[r][c]
-__host__ __device__ __forceinline__ float rg_grad_term(const cx<float>* W, const cx<float>* pay, uint32_t count, int e) {
-  if (count == 2) {
-    const cx<float>* De = pay + 2 + 2 * e;
-    return De[0].x * W[0].x - De[0].y * W[0].y + De[1].x * W[3].x - De[1].y * W[3].y;
-  }
-  const cx<float>* De = pay + 4 + 4 * e;
+// what one thread adds to a gradient slot of a 2x2 sub-op: Re sum_rc dG[r][c] W[r][c]; De = the slot's derivative
+// entries (4 dense, 2 diagonal)
+__host__ __device__ __forceinline__ float rg_grad_term(const cx<float>* W, const cx<float>* De, uint32_t count) {
+  if (count == 2) return De[0].x * W[0].x - De[0].y * W[0].y + De[1].x * W[3].x - De[1].y * W[3].y;
   float v = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) v += De[i].x * W[i].x - De[i].y * W[i].y;
   return v;
 }
 
-// returns true when W holds gradient contributions the caller has to reduce (RG_D1 with trainable slots)
-__host__ __device__ __forceinline__ bool rg_bwd_sub(cx<float> (&a)[16], cx<float> (&l)[16], const OpDesc& d,
-                                                    const cx<float>* pay, cx<float>* W) {
-  const uint32_t live = d.cmask;
-  switch (d.path) {
-    case RG_D1: {
-      cx<float> mh[4];
-      rg_ld2x2<true>(pay, d.count, mh);
-      const bool has_d = d.nderiv > 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) W[i] = mk<float>(0.f, 0.f);
-      switch (d.k) {
-        case 0: rg_bwd_d1<0>(a, l, mh, live, has_d, W); break;
-        case 1: rg_bwd_d1<1>(a, l, mh, live, has_d, W); break;
-        case 2: rg_bwd_d1<2>(a, l, mh, live, has_d, W); break;
-        default: rg_bwd_d1<3>(a, l, mh, live, has_d, W); break;
-      }
-      return has_d;
-    }
-    case RG_X1:  // a permutation is its own adjoint
-      switch (d.k) {
-        case 0: rg_x1<0>(a, live); rg_x1<0>(l, live); break;
-        case 1: rg_x1<1>(a, live); rg_x1<1>(l, live); break;
-        case 2: rg_x1<2>(a, live); rg_x1<2>(l, live); break;
-        default: rg_x1<3>(a, live); rg_x1<3>(l, live); break;
-      }
+// adjoint sub-op; mh = conjugate transpose of the 2x2 (RG_D1).  Returns true when W holds gradient contributions the
+// caller has to reduce (RG_D1 with trainable slots)
+__host__ __device__ __forceinline__ bool rg_bwd_sub(cx<float> (&a)[16], cx<float> (&l)[16], const RgSub& d,
+                                                    const cx<float>* mh, const cx<float>* pay, cx<float>* W) {
+  const bool has_d = d.nderiv > 0;
+  switch (d.kind * 4u + (d.kind == RG_GEN ? 0u : d.k)) {
+    case RG_D1 * 4 + 0: rg_bwd_d1<0>(a, l, mh, d.live, has_d, W); return has_d;
+    case RG_D1 * 4 + 1: rg_bwd_d1<1>(a, l, mh, d.live, has_d, W); return has_d;
+    case RG_D1 * 4 + 2: rg_bwd_d1<2>(a, l, mh, d.live, has_d, W); return has_d;
+    case RG_D1 * 4 + 3: rg_bwd_d1<3>(a, l, mh, d.live, has_d, W); return has_d;
+    // a permutation is its own adjoint
+    case RG_X1 * 4 + 0: rg_x1<0>(a, d.live); rg_x1<0>(l, d.live); return false;
+    case RG_X1 * 4 + 1: rg_x1<1>(a, d.live); rg_x1<1>(l, d.live); return false;
+    case RG_X1 * 4 + 2: rg_x1<2>(a, d.live); rg_x1<2>(l, d.live); return false;
+    case RG_X1 * 4 + 3: rg_x1<3>(a, d.live); rg_x1<3>(l, d.live); return false;
+    default:
+      rg_gen<true>(a, d.tlo, d.thi, d.live, pay);
+      rg_gen<true>(l, d.tlo, d.thi, d.live, pay);
       return false;
-    default: {
-      rg_gen<true>(a, rg_tab_lo(d), rg_tab_hi(d), live, pay);
-      rg_gen<true>(l, rg_tab_lo(d), rg_tab_hi(d), live, pay);
-      return false;
-    }
   }
 }
 
@@ -323,56 +344,201 @@ inline void rg_pick_bits(int m, const int* used, int n_used, int* reg) {
   for (int i = 0; i < 4; ++i) reg[i] = best[i];
 }
 
+// Affine relabelling of the register pattern by a network of X / CNOT blocks (targets and controls as register-bit
+// indices, ctl < 0: plain X), written as the 20-bit map of the header.  forward_order = true: the image of pattern j
+// after the blocks ran in the given order (STORE map: register j goes to tile pattern net(j)); false: the pre-image
+// (LOAD map: register j comes from the tile pattern that the network sends to j).
+inline uint32_t rg_affine_map(const int* tgt, const int* ctl, int n_ops, bool forward_order) {
+  uint32_t T[16];
+  for (uint32_t j = 0; j < 16; ++j) {
+    uint32_t x = j;
+    // every block is an involution, so the pre-image applies them last to first
+    for (int s = 0; s < n_ops; ++s) {
+      const int i = forward_order ? s : n_ops - 1 - s;
+      if (ctl[i] < 0 || ((x >> ctl[i]) & 1u)) x ^= 1u << tgt[i];
+    }
+    T[j] = x;
+  }
+  uint32_t map = T[0] << 16;
+  for (int b = 0; b < 4; ++b) map |= (T[1u << b] ^ T[0]) << (4 * b);
+  return map;
+}
+
+// the header of a group: register bits, number of sub-ops, load / store relabelling as swizzled word offsets
+inline void rg_pack_header(const int* reg, int n_sub, uint32_t load_map, uint32_t store_map, OpDesc& h) {
+  memset(&h, 0, sizeof(h));
+  h.path = P_RG;
+  h.k = RG_BITS;
+  h.nins = (uint8_t)n_sub;
+  uint32_t regbits = 0, o[4];
+  for (int i = 0; i < RG_BITS; ++i) {
+    h.tpos[i] = (uint8_t)reg[i];
+    regbits |= (uint32_t)reg[i] << (8 * i);
+  }
+  rg_bit_offsets(regbits, o);
+  const RgAddr L = rg_addr(o, load_map), S = rg_addr(o, store_map);
+  const uint32_t ins = L.b1 | (L.b2 << 16);
+  memcpy(h.ins, &ins, 4);
+  h.cmask = L.b4 | (L.b8 << 16);
+  h.pay_off = L.c | (S.c << 16);
+  h.dslot = S.b1 | (S.b2 << 16);
+  h.count = S.b4 | (S.b8 << 16);
+}
+
+// ---- group formation (host) -----------------------------------------------------------------------------------------
+// One block of a sweep as the grouper sees it: its tile bits, whether it is an X / CNOT (foldable into the load / store
+// addresses), its payload entries.
+struct RgItem {
+  int bits[4];
+  int nbits;
+  bool foldable;
+  int pay;
+};
+// Takes the next group out of `rest` (indices into items, execution order).  pre: foldable blocks before the first
+// other block; post: foldable blocks after the last one; mid: everything else, in order.  A block joins the open group
+// when the group's tile bits plus its own stay within four and none of its bits belongs to a block that was passed over
+// (it commutes with every passed-over block then); a block that is not foldable also must not share a bit with an
+// accepted post block (it runs before them).  A foldable block in the pre phase has to touch a bit the group already
+// has: otherwise unrelated CNOTs fill the four bits before the blocks they belong with arrive.
+inline void rg_next_group(const std::vector<RgItem>& items, std::vector<int>& rest, int m_t, int pay_cap,
+                          std::vector<int>& pre, std::vector<int>& mid, std::vector<int>& post, std::vector<char>& inb) {
+  pre.clear();
+  mid.clear();
+  post.clear();
+  inb.assign(m_t, 0);
+  std::vector<char> blocked(m_t, 0), postb(m_t, 0);
+  std::vector<int> keep;
+  int nbits = 0, pay = 0;
+  for (int bi : rest) {
+    const RgItem& it = items[bi];
+    bool ok = (int)mid.size() < RG_MAX_SUB;
+    int need = 0;
+    for (int k = 0; k < it.nbits; ++k) {
+      const int b = it.bits[k];
+      if (blocked[b]) ok = false;
+      if (!it.foldable && postb[b]) ok = false;
+      if (!inb[b]) ++need;
+    }
+    if (it.foldable && mid.empty() && nbits > 0 && need == it.nbits) ok = false;  // pre phase: connected growth only
+    const int pe = it.foldable ? 0 : it.pay;
+    if (ok && nbits + need <= RG_BITS && pay + pe <= pay_cap) {
+      for (int k = 0; k < it.nbits; ++k)
+        if (!inb[it.bits[k]]) {
+          inb[it.bits[k]] = 1;
+          ++nbits;
+        }
+      pay += pe;
+      if (!it.foldable) {
+        mid.push_back(bi);
+      } else if (mid.empty()) {
+        pre.push_back(bi);
+      } else {
+        post.push_back(bi);
+        for (int k = 0; k < it.nbits; ++k) postb[it.bits[k]] = 1;
+      }
+    } else {
+      for (int k = 0; k < it.nbits; ++k) blocked[it.bits[k]] = 1;
+      keep.push_back(bi);
+    }
+  }
+  rest.swap(keep);
+}
+
 #ifdef __CUDACC__
+// ---- explicit shared-memory accesses (32-bit shared addresses: no generic-address loads on the dispatch path) --------
+__device__ __forceinline__ uint32_t rg_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 rg_lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void rg_lds_c2(uint32_t a, cf& u, cf& v) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(u.x), "=f"(u.y), "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+}
+
 // ---- one group on a shared-memory tile ------------------------------------------------------------------------------
-__device__ __forceinline__ void rg_run_fwd(cf* s, const OpDesc& h, const OpDesc* sub, const cf* pp, uint32_t pay_begin,
+// hdr: shared address of the header (its sub-op descriptors follow it); pay: shared address of the chunk's payload
+// buffer, pay_gen the same as a pointer (RG_GEN indexes it), pay_begin the chunk's first entry.  The store map is read
+// (volatile) after the sub-op loop so that the 16 store addresses are not kept alive across it.
+__device__ __forceinline__ void rg_run_fwd(cf* s, uint32_t hdr, uint32_t pay, const cf* pay_gen, uint32_t pay_begin,
                                            int m) {
-  const RgGeom G = rg_geom(h);
-  const int nsub = h.nins;
+  const uint4 h0 = rg_lds_u4(hdr);
+  const uint32_t sub = hdr + 32u;
+  const uint32_t nsub = (h0.x >> 16) & 255u;
   const uint32_t ng = 1u << (m - RG_BITS);
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
-    const uint32_t pb = rg_base(G, g);
+    const uint32_t pb = rg_base(h0.z, g);
     cf a[16];
+    {
+      const RgAddr L = rg_header_load(h0, rg_lds_u4(hdr + 16u));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = s[pb ^ G.off[j]];
-    for (int i = 0; i < nsub; ++i) {
-      const OpDesc& d = sub[i];
-      rg_fwd_sub(a, d, pp + (d.pay_off - pay_begin));
+      for (int j = 0; j < 16; ++j) a[j] = s[pb ^ RG_OFF(L, j)];
     }
+    for (uint32_t i = 0; i < nsub; ++i) {
+      const RgSub d = rg_decode(rg_lds_u4(sub + 32u * i), rg_lds_u4(sub + 32u * i + 16u));
+      const uint32_t pa = pay + 8u * (d.pay_off - pay_begin);
+      cf p[4], mm[4];
+      rg_lds_c2(pa, p[0], p[1]);
+      if (d.count != 2) rg_lds_c2(pa + 16u, p[2], p[3]);
+      rg_ld2x2<false>(p, d.count, mm);
+      rg_fwd_sub(a, d, mm, pay_gen + (d.pay_off - pay_begin));
+    }
+    {
+      const RgAddr S = rg_header_store(rg_lds_u4(hdr + 16u));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) s[pb ^ G.off[j]] = a[j];
+      for (int j = 0; j < 16; ++j) s[pb ^ RG_OFF(S, j)] = a[j];
+    }
   }
 }
 
 // ng is a multiple of blockDim (host: threads = min(256, 2^(m-4)) >= 32), so every lane takes part in the reductions
-__device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, const OpDesc& h, const OpDesc* sub, const cf* pp,
+__device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_t pay, const cf* pay_gen,
                                            uint32_t pay_begin, float* s_grad, int m) {
-  const RgGeom G = rg_geom(h);
-  const int nsub = h.nins;
+  const uint4 h0 = rg_lds_u4(hdr);
+  const uint32_t sub = hdr + 32u;
+  const uint32_t nsub = (h0.x >> 16) & 255u;
   const uint32_t ng = 1u << (m - RG_BITS);
   for (uint32_t g = threadIdx.x; g < ng; g += blockDim.x) {
-    const uint32_t pb = rg_base(G, g);
+    const uint32_t pb = rg_base(h0.z, g);
     cf a[16], l[16];
+    {
+      const RgAddr L = rg_header_load(h0, rg_lds_u4(hdr + 16u));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      a[j] = sp[pb ^ G.off[j]];
-      l[j] = sl[pb ^ G.off[j]];
+      for (int j = 0; j < 16; ++j) {
+        a[j] = sp[pb ^ RG_OFF(L, j)];
+        l[j] = sl[pb ^ RG_OFF(L, j)];
+      }
     }
-    for (int i = 0; i < nsub; ++i) {
-      const OpDesc& d = sub[i];
-      const cf* pay = pp + (d.pay_off - pay_begin);
-      cf W[4];
-      if (rg_bwd_sub(a, l, d, pay, W)) {
-        for (int e = 0; e < d.nderiv; ++e) {
-          const float v = warp_sum(rg_grad_term(W, pay, d.count, e));
+    for (uint32_t i = 0; i < nsub; ++i) {
+      const RgSub d = rg_decode(rg_lds_u4(sub + 32u * i), rg_lds_u4(sub + 32u * i + 16u));
+      const uint32_t pa = pay + 8u * (d.pay_off - pay_begin);
+      cf p[4], mh[4], W[4];
+      rg_lds_c2(pa, p[0], p[1]);
+      if (d.count != 2) rg_lds_c2(pa + 16u, p[2], p[3]);
+      rg_ld2x2<true>(p, d.count, mh);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) W[e] = mk<float>(0.f, 0.f);
+      if (rg_bwd_sub(a, l, d, mh, pay_gen + (d.pay_off - pay_begin), W)) {
+        for (uint32_t e = 0; e < d.nderiv; ++e) {
+          cf De[4];
+          if (d.count == 2) {
+            rg_lds_c2(pa + 16u + 16u * e, De[0], De[1]);
+          } else {
+            rg_lds_c2(pa + 32u + 32u * e, De[0], De[1]);
+            rg_lds_c2(pa + 48u + 32u * e, De[2], De[3]);
+          }
+          const float v = warp_sum(rg_grad_term(W, De, d.count));
           if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[d.dslot + e], v);
         }
       }
     }
+    {
+      const RgAddr S = rg_header_store(rg_lds_u4(hdr + 16u));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      sp[pb ^ G.off[j]] = a[j];
-      sl[pb ^ G.off[j]] = l[j];
+      for (int j = 0; j < 16; ++j) {
+        sp[pb ^ RG_OFF(S, j)] = a[j];
+        sl[pb ^ RG_OFF(S, j)] = l[j];
+      }
     }
   }
 }
@@ -391,6 +557,32 @@ __device__ __forceinline__ void rg_swizzle_tile(cf* s, uint32_t tile_n) {
   __syncthreads();
 }
 
+// ---- tile <-> state vector: pairs of amplitudes (tile bit 0 is state bit 0: the host keeps >= 1 coalesce bit), the
+// scatter of the tile index split into a per-thread part and a per-iteration table (blockDim is a power of two, so
+// the two parts have disjoint bits and dep_local is an OR of the parts) -------------------------------------------------
+constexpr int RG_IO_TAB = 64;
+__device__ __forceinline__ void rg_io_table(const Geom& g, uint32_t tile_n, uint32_t* tab) {
+  const uint32_t iters = tile_n / (2u * blockDim.x);
+  for (uint32_t i = threadIdx.x; i < iters; i += blockDim.x) tab[i] = dep_local(g, 2u * i * blockDim.x);
+}
+template <bool STORE>
+__device__ __forceinline__ void rg_tile_io(cf* sm, cf* hbm, const uint32_t* tab, uint32_t base, uint32_t tile_n) {
+  const uint32_t iters = tile_n / (2u * blockDim.x);
+  for (uint32_t it = 0; it < iters; ++it) {
+    const uint32_t q2 = 2u * (it * blockDim.x + threadIdx.x);
+    const uint32_t p = rg_phys(q2);  // q2 + 1 sits at p ^ 1
+    float4* sp = reinterpret_cast<float4*>(sm + (p & ~1u));
+    float4* gp = reinterpret_cast<float4*>(hbm + (base | tab[it]));
+    if (STORE) {
+      const float4 v = *sp;
+      *gp = (p & 1u) ? make_float4(v.z, v.w, v.x, v.y) : v;
+    } else {
+      const float4 v = *gp;
+      *sp = (p & 1u) ? make_float4(v.z, v.w, v.x, v.y) : v;
+    }
+  }
+}
+
 template <bool BWD>
 __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& ring, const StreamRef& st, const cf* pay_b,
                                           float* s_grad, int m) {
@@ -400,15 +592,16 @@ __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& rin
     __syncthreads();  // chunk c landed; everyone is done with the buffer chunk c+1 will overwrite
     if (c + 1 < st.n_chunks) ring_issue<float>(ring, st, pay_b, c + 1);
     const ChunkInfo ci = chunk_info<float>(ring, st, c);
-    const OpDesc* dd = ring.desc[c & 1];
-    const cf* pp = ring.pay[c & 1];
+    const cf* pp = (c & 1) ? ring.pay[1] : ring.pay[0];
+    const uint32_t dd = rg_saddr((c & 1) ? ring.desc[1] : ring.desc[0]);
+    const uint32_t pa = rg_saddr(pp);
     for (uint32_t o = 0; o < ci.op_count;) {
-      const OpDesc& h = dd[o];
+      const uint32_t hdr = dd + 32u * o;
       if (BWD)
-        rg_run_bwd(sp, sl, h, dd + o + 1, pp, ci.pay_begin, s_grad, m);
+        rg_run_bwd(sp, sl, hdr, pa, pp, ci.pay_begin, s_grad, m);
       else
-        rg_run_fwd(sp, h, dd + o + 1, pp, ci.pay_begin, m);
-      o += 1u + h.nins;
+        rg_run_fwd(sp, hdr, pa, pp, ci.pay_begin, m);
+      o += 1u + ((rg_lds_u4(hdr).x >> 16) & 255u);
       __syncthreads();
     }
   }
@@ -416,32 +609,33 @@ __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& rin
 
 // ---- kernels (same arguments, flags and shared-memory layout as k_sweep_fwd / k_sweep_bwd) --------------------------
 __global__ void __launch_bounds__(256, 3) k_rg_fwd(const __grid_constant__ FwdArgs<float> a) {
+  __shared__ uint32_t io_tab[RG_IO_TAB];
   const int m = a.geom.m;
   const uint32_t tile_n = 1u << m;
   cf* sm = reinterpret_cast<cf*>(tq_smem);
   Ring<float> ring = ring_carve<float>(tq_smem + sizeof(cf) * tile_n);
   const int64_t b = (int64_t)(blockIdx.x >> a.tiles_log2);
   const uint32_t tile = blockIdx.x & ((1u << a.tiles_log2) - 1u);
-  const uint32_t tbase = dep_tile(a.geom, tile);
+  const uint32_t tbase = dep_tile(a.geom, tile) | dep_local(a.geom, 2u * threadIdx.x);
   const size_t sv = (size_t)1 << a.geom.n;
   cf* psi_b = a.psi ? a.psi + (size_t)b * sv : nullptr;
+  rg_io_table(a.geom, tile_n, io_tab);
+  __syncthreads();
 
   if (a.flags & SW_INIT) {
     if (a.init_state) {
-      for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[rg_phys(l)] = a.init_state[tbase | dep_local(a.geom, l)];
+      rg_tile_io<false>(sm, const_cast<cf*>(a.init_state), io_tab, tbase, tile_n);
     } else {
       for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[l] = mk<float>(0.f, 0.f);
       __syncthreads();
-      if (threadIdx.x == 0 && tbase == 0) sm[0] = mk<float>(1.f, 0.f);  // rg_phys(0) = 0
+      if (threadIdx.x == 0 && dep_tile(a.geom, tile) == 0) sm[0] = mk<float>(1.f, 0.f);  // rg_phys(0) = 0
     }
   } else {
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sm[rg_phys(l)] = psi_b[tbase | dep_local(a.geom, l)];
+    rg_tile_io<false>(sm, psi_b, io_tab, tbase, tile_n);
   }
   rg_stream<false>(sm, nullptr, ring, a.st, a.stream + b * a.stride, nullptr, m);  // begins and ends with a barrier
 
-  if (a.flags & SW_STORE) {
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) psi_b[tbase | dep_local(a.geom, l)] = sm[rg_phys(l)];
-  }
+  if (a.flags & SW_STORE) rg_tile_io<true>(sm, psi_b, io_tab, tbase, tile_n);
   if (a.flags & SW_MEASURE) {
     __syncthreads();
     rg_swizzle_tile(sm, tile_n);  // back to natural order for the measurement code
@@ -453,6 +647,7 @@ __global__ void __launch_bounds__(256, 3) k_rg_fwd(const __grid_constant__ FwdAr
 }
 
 __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdArgs<float> a) {
+  __shared__ uint32_t io_tab[RG_IO_TAB];
   const int m = a.geom.m;
   const uint32_t tile_n = 1u << m;
   cf* sp = reinterpret_cast<cf*>(tq_smem);
@@ -461,9 +656,10 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
   float* s_grad = reinterpret_cast<float*>(tq_smem + 2 * sizeof(cf) * tile_n + RING_BYTES);
   const int64_t b = (int64_t)(blockIdx.x >> a.tiles_log2);
   const uint32_t tile = blockIdx.x & ((1u << a.tiles_log2) - 1u);
-  const uint32_t tbase = dep_tile(a.geom, tile);
+  const uint32_t tbase = dep_tile(a.geom, tile) | dep_local(a.geom, 2u * threadIdx.x);
   const size_t sv = (size_t)1 << a.geom.n;
   cf* psi_b = a.psi + (size_t)b * sv;  // the forward pass (with_backward) left the final state here
+  cf* lam_b = a.lam ? a.lam + (size_t)b * sv : nullptr;
 
   for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) s_grad[s] = 0;
 
@@ -477,24 +673,16 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
     rg_swizzle_tile(sp, tile_n);
     rg_swizzle_tile(sl, tile_n);
   } else {
-    const cf* lam_b = a.lam + (size_t)b * sv;
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) {
-      const uint32_t gi = tbase | dep_local(a.geom, l);
-      const uint32_t p = rg_phys(l);
-      sp[p] = psi_b[gi];
-      sl[p] = lam_b[gi];
-    }
+    rg_io_table(a.geom, tile_n, io_tab);
+    __syncthreads();
+    rg_tile_io<false>(sp, psi_b, io_tab, tbase, tile_n);
+    rg_tile_io<false>(sl, lam_b, io_tab, tbase, tile_n);
   }
   rg_stream<true>(sp, sl, ring, a.st_b, a.stream_b + b * a.stride_b, s_grad, m);  // begins and ends with a barrier
 
   if (!(a.flags & SW_FULL) && (a.flags & SW_STORE)) {
-    cf* lam_b = a.lam + (size_t)b * sv;
-    for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) {
-      const uint32_t gi = tbase | dep_local(a.geom, l);
-      const uint32_t p = rg_phys(l);
-      psi_b[gi] = sp[p];
-      lam_b[gi] = sl[p];
-    }
+    rg_tile_io<true>(sp, psi_b, io_tab, tbase, tile_n);
+    rg_tile_io<true>(sl, lam_b, io_tab, tbase, tile_n);
   }
   float* grad_b = a.grad + b * a.n_params;
   for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) {

@@ -110,6 +110,66 @@ def _greedy_once(inputs: Sequence[Sequence[int]], output: Sequence[int], rng: ra
     return path
 
 
+def _greedy_once_native(inputs: Sequence[Sequence[int]], output: Sequence[int], rng: random.Random, alpha: float,
+                        temperature: float):
+    """``_greedy_once`` through the compiled library (tq_tn_greedy_path, csrc/tq_planner.cu): the same path and the
+    same state of ``rng`` afterwards (tests/test_planner_cpu.py).  The pairs are scored in the order the mirror
+    scores them, which is decided here (dict / frozenset iteration order); the heap loop — the part that costs
+    seconds on a 40-qubit network — runs compiled."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import capi
+
+    n = len(inputs)
+    sets = {i: frozenset(t) for i, t in enumerate(inputs)}
+    where: Dict[int, set] = {}
+    for i, s in sets.items():
+        for ix in s:
+            where.setdefault(ix, set()).add(i)
+    dense = {ix: k for k, ix in enumerate(where)}
+    for ix in output:
+        dense.setdefault(ix, len(dense))
+    init = []
+    for ix, ts in where.items():
+        ts = sorted(ts)
+        for x in range(len(ts)):
+            for y in range(x + 1, len(ts)):
+                init.append((ts[x], ts[y]))
+    off = np.zeros(n + 1, dtype=np.int32)
+    flat = []
+    for i in range(n):
+        flat.extend(dense[ix] for ix in sets[i])
+        off[i + 1] = len(flat)
+    idx = np.asarray(flat if flat else [0], dtype=np.int32)
+    keep = np.zeros(max(1, len(dense)), dtype=np.int32)
+    for ix in output:
+        keep[dense[ix]] = 1
+    pairs = np.asarray(init if init else [(0, 0)], dtype=np.int32).reshape(-1)
+    path = np.zeros(2 * max(1, n - 1), dtype=np.int32)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    n_u = 4 * len(init) + 64 * n if temperature > 0 else 0
+    state = rng.getstate()
+    while True:
+        rng.setstate(state)
+        u = np.asarray([rng.random() for _ in range(n_u)] if n_u else [0.0], dtype=np.float64)
+        used = C.c_int64(0)
+        rc = capi.lib().tq_tn_greedy_path(n, len(dense), off.ctypes.data_as(i32p), idx.ctypes.data_as(i32p),
+                                          keep.ctypes.data_as(i32p), len(init), pairs.ctypes.data_as(i32p),
+                                          u.ctypes.data_as(f64p), n_u, float(alpha), float(temperature),
+                                          path.ctypes.data_as(i32p), C.byref(used))
+        if rc == capi.E_WORKSPACE and n_u:
+            n_u *= 2
+            continue
+        capi.check(rc, "tq_tn_greedy_path")
+        break
+    rng.setstate(state)      # leave rng where the mirror would: exactly the numbers the pass consumed are gone
+    for _ in range(used.value):
+        rng.random()
+    return [(int(path[2 * k]), int(path[2 * k + 1])) for k in range(n - 1)]
+
+
 def path_cost(inputs, output, path, sliced=()):
     """(width, log2 flops of one slice, list of per-step union masks, list of result masks)."""
     sl = set(sliced)
@@ -462,9 +522,10 @@ def path_time(inputs, output, path, sliced, time_model) -> float:
 
 def find_path(inputs, output, repeats: int = 16, seed: int = 0, minimize: str = "flops",
               alphas=(1.0, 0.5, 0.0), temperatures=(0.0, 0.3, 1.0), reconf_sweeps: int = 0,
-              reconf_leaves: int = 8, time_model=None) -> PathInfo:
+              reconf_leaves: int = 8, time_model=None, native_greedy: bool = True) -> PathInfo:
     """Best of ``repeats`` randomised greedy runs (first run is the deterministic alpha=1, T=0 greedy) and the
-    time-ordered sequential path (deep circuits on few qubits: greedy merges wide, the sweep stays at width n)."""
+    time-ordered sequential path (deep circuits on few qubits: greedy merges wide, the sweep stays at width n).
+    ``native_greedy``: the greedy passes run in the compiled library (same paths, same random stream)."""
     rng = random.Random(seed)
     best = None
     if len(inputs) > 1:
@@ -476,7 +537,7 @@ def find_path(inputs, output, repeats: int = 16, seed: int = 0, minimize: str = 
     for r in range(max(1, repeats)):
         alpha = alphas[0] if r == 0 else rng.choice(alphas)
         temp = temperatures[0] if r == 0 else rng.choice(temperatures[1:])
-        path = _greedy_once(inputs, output, rng, alpha, temp)
+        path = (_greedy_once_native if native_greedy else _greedy_once)(inputs, output, rng, alpha, temp)
         width, fl, _, _ = path_cost(inputs, output, path)
         key = (fl, width) if minimize == "flops" else (width, fl)
         if best is None or key < best[0]:

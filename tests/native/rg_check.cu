@@ -78,6 +78,12 @@ static double ref_grad(const std::vector<zc>& psi_prev, const std::vector<zc>& l
   return g;
 }
 
+static RgSub decode(const OpDesc& d) {
+  uint4 w[2];
+  memcpy(w, &d, 32);
+  return rg_decode(w[0], w[1]);
+}
+
 static int fails = 0;
 #define CHECK(cond, ...)          \
   do {                            \
@@ -99,15 +105,15 @@ int main() {
   // 2. bank conflicts: contiguous register bits are conflict free for every tile size; padded picks are too
   for (int m = RG_MIN_TILE; m <= 14; ++m) {
     for (int b0 = 0; b0 + 4 <= m; ++b0) {
-      OpDesc h;
-      memset(&h, 0, sizeof(h));
-      for (int i = 0; i < 4; ++i) h.tpos[i] = (uint8_t)(b0 + i);
-      RgGeom G = rg_geom(h);
+      uint32_t regbits = 0, o[4];
+      for (int i = 0; i < 4; ++i) regbits |= (uint32_t)(b0 + i) << (8 * i);
+      rg_bit_offsets(regbits, o);
+      const RgAddr G = rg_addr(o, RG_MAP_ID);
       for (int j = 0; j < 16; ++j)
         for (uint32_t w = 0; w < (1u << (m - 4)); w += 16) {  // a half-warp: 16 consecutive groups
           int seen = 0;
           for (uint32_t l = 0; l < 16; ++l) {
-            const uint32_t addr = rg_base(G, w + l) ^ G.off[j];
+            const uint32_t addr = rg_base(regbits, w + l) ^ RG_OFF(G, j);
             CHECK(addr < (1u << m), "address outside the tile");
             seen |= 1 << (addr & 15);
           }
@@ -200,16 +206,47 @@ int main() {
       sp[rg_phys(i)] = v;
       sl[rg_phys(i)] = w;
     }
-    const RgGeom G = rg_geom(h);
+    // X / CNOT networks folded into the load (pre) and store (post) addresses
+    std::vector<Blk> pre, post;
+    int pre_t[8], pre_c[8], post_t[8], post_c[8];
+    const int npre = rand() % 5, npost = rand() % 5;
+    for (int side = 0; side < 2; ++side)
+      for (int i = 0; i < (side ? npost : npre); ++i) {
+        const int t = rand() % 4;
+        int c = rand() % 5 - 1;  // -1: plain X
+        if (c == t) c = -1;
+        (side ? post_t : pre_t)[i] = t;
+        (side ? post_c : pre_c)[i] = c;
+        Blk b;
+        b.cls = OP_DENSE;
+        b.is_x = true;
+        b.nderiv = 0;
+        b.targets.push_back(reg[t]);
+        if (c >= 0) b.controls.push_back(reg[c]);
+        b.pay.assign(4, mk<float>(0, 0));
+        (side ? post : pre).push_back(b);
+      }
+    uint32_t regbits = 0, o[4];
+    for (int i = 0; i < 4; ++i) regbits |= (uint32_t)reg[i] << (8 * i);
+    rg_bit_offsets(regbits, o);
+    const RgAddr LF = rg_addr(o, rg_affine_map(pre_t, pre_c, npre, false)), SF = rg_addr(o, rg_affine_map(post_t, post_c, npost, true));
+    std::vector<RgSub> subs;
+    for (int i = 0; i < nsub; ++i) subs.push_back(decode(descs[i]));
     // forward on sp
     for (uint32_t g = 0; g < (n >> 4); ++g) {
-      const uint32_t pb = rg_base(G, g);
+      const uint32_t pb = rg_base(regbits, g);
       cf32 a[16];
-      for (int j = 0; j < 16; ++j) a[j] = sp[pb ^ G.off[j]];
-      for (int i = 0; i < nsub; ++i) rg_fwd_sub(a, descs[i], payload.data() + descs[i].pay_off);
-      for (int j = 0; j < 16; ++j) sp[pb ^ G.off[j]] = a[j];
+      for (int j = 0; j < 16; ++j) a[j] = sp[pb ^ RG_OFF(LF, j)];
+      for (int i = 0; i < nsub; ++i) {
+        cf32 mm[4];
+        rg_ld2x2<false>(payload.data() + subs[i].pay_off, subs[i].count, mm);
+        rg_fwd_sub(a, subs[i], mm, payload.data() + subs[i].pay_off);
+      }
+      for (int j = 0; j < 16; ++j) sp[pb ^ RG_OFF(SF, j)] = a[j];
     }
+    for (const Blk& b : pre) ref_apply(ref, m, b, false);
     for (int i = 0; i < nsub; ++i) ref_apply(ref, m, blks[i], false);
+    for (const Blk& b : post) ref_apply(ref, m, b, false);
     double err = 0, nrm = 0;
     for (uint32_t i = 0; i < n; ++i) {
       err = fmax(err, std::abs(Z(sp[rg_phys(i)]) - ref[i]));
@@ -221,23 +258,32 @@ int main() {
     std::vector<int> slot0(nsub);
     int ns = 0;
     for (int i = 0; i < nsub; ++i) { slot0[i] = ns; ns += blks[i].nderiv; }
+    // the adjoint group: the blocks in reverse order; its pre network is the forward post network reversed
+    int bpre_t[8], bpre_c[8], bpost_t[8], bpost_c[8];
+    for (int i = 0; i < npost; ++i) { bpre_t[i] = post_t[npost - 1 - i]; bpre_c[i] = post_c[npost - 1 - i]; }
+    for (int i = 0; i < npre; ++i) { bpost_t[i] = pre_t[npre - 1 - i]; bpost_c[i] = pre_c[npre - 1 - i]; }
+    const RgAddr LB = rg_addr(o, rg_affine_map(bpre_t, bpre_c, npost, false)), SB = rg_addr(o, rg_affine_map(bpost_t, bpost_c, npre, true));
     for (uint32_t g = 0; g < (n >> 4); ++g) {
-      const uint32_t pb = rg_base(G, g);
+      const uint32_t pb = rg_base(regbits, g);
       cf32 a[16], l[16];
-      for (int j = 0; j < 16; ++j) { a[j] = sp[pb ^ G.off[j]]; l[j] = sl[pb ^ G.off[j]]; }
+      for (int j = 0; j < 16; ++j) { a[j] = sp[pb ^ RG_OFF(LB, j)]; l[j] = sl[pb ^ RG_OFF(LB, j)]; }
       for (int i = nsub - 1; i >= 0; --i) {
-        cf32 W[4];
-        const cf32* pay = payload.data() + descs[i].pay_off;
-        if (rg_bwd_sub(a, l, descs[i], pay, W))
-          for (int e = 0; e < descs[i].nderiv; ++e) grad[slot0[i] + e] += rg_grad_term(W, pay, descs[i].count, e);
+        cf32 W[4] = {mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0)}, mh[4];
+        const cf32* pay = payload.data() + subs[i].pay_off;
+        rg_ld2x2<true>(pay, subs[i].count, mh);
+        if (rg_bwd_sub(a, l, subs[i], mh, pay, W))
+          for (uint32_t e = 0; e < subs[i].nderiv; ++e)
+            grad[slot0[i] + e] += rg_grad_term(W, pay + (subs[i].count == 2 ? 2 + 2 * e : 4 + 4 * e), subs[i].count);
       }
-      for (int j = 0; j < 16; ++j) { sp[pb ^ G.off[j]] = a[j]; sl[pb ^ G.off[j]] = l[j]; }
+      for (int j = 0; j < 16; ++j) { sp[pb ^ RG_OFF(SB, j)] = a[j]; sl[pb ^ RG_OFF(SB, j)] = l[j]; }
     }
+    for (int i = npost - 1; i >= 0; --i) { ref_apply(ref, m, post[i], true); ref_apply(lam_ref, m, post[i], true); }
     for (int i = nsub - 1; i >= 0; --i) {
       ref_apply(ref, m, blks[i], true);  // psi_prev
       for (int e = 0; e < blks[i].nderiv; ++e) grad_ref[slot0[i] + e] = ref_grad(ref, lam_ref, m, blks[i], e);
       ref_apply(lam_ref, m, blks[i], true);
     }
+    for (int i = npre - 1; i >= 0; --i) { ref_apply(ref, m, pre[i], true); ref_apply(lam_ref, m, pre[i], true); }
     double e1 = 0, e2 = 0, n1 = 0, n2 = 0;
     for (uint32_t i = 0; i < n; ++i) {
       e1 = fmax(e1, std::abs(Z(sp[rg_phys(i)]) - ref[i]));
@@ -251,6 +297,60 @@ int main() {
       CHECK(fabs(grad[sidx] - grad_ref[sidx]) <= 2e-3 * scale * sqrt((double)n) / 16.0 + 1e-3 * scale, "gradient trial %d slot %d: %g vs %g", trial, sidx, grad[sidx],
             grad_ref[sidx]);
     }
+  }
+  // 4. grouping of a hardware-efficient ansatz inside one tile: every block lands in exactly one group, blocks that
+  //    share a bit keep their order, and the groups hold close to four one-qubit blocks each
+  for (int m = 9; m <= 14; ++m) {
+    std::vector<RgItem> items;
+    auto add = [&](int b0, int b1, bool fold) {
+      RgItem it;
+      it.nbits = b1 < 0 ? 1 : 2;
+      it.bits[0] = b0;
+      it.bits[1] = b1;
+      it.foldable = fold;
+      it.pay = fold ? 4 : 12;
+      items.push_back(it);
+    };
+    const int depth = 10;
+    for (int d = 0; d < depth; ++d) {
+      for (int q = 0; q < m; ++q) add(m - 1 - q, -1, false);
+      for (int first = 2; first >= 1; --first)
+        for (int w = first; w < m; w += 2) add(m - 1 - (w - 1), m - 1 - w, true);
+    }
+    for (int q = 0; q < m; ++q) add(m - 1 - q, -1, false);
+    std::vector<int> rest(items.size()), stamp(items.size(), -1);
+    for (size_t i = 0; i < items.size(); ++i) rest[i] = (int)i;
+    int groups = 0, d1 = 0, empty_groups = 0, clock = 0;
+    while (!rest.empty()) {
+      std::vector<int> pre, mid, post;
+      std::vector<char> inb;
+      const size_t before = rest.size();
+      rg_next_group(items, rest, m, 256, pre, mid, post, inb);
+      CHECK(pre.size() + mid.size() + post.size() + rest.size() == before, "grouping lost a block");
+      CHECK(pre.size() + mid.size() + post.size() > 0, "grouping made no progress");
+      if (pre.size() + mid.size() + post.size() == 0) break;
+      int nb = 0;
+      for (int b = 0; b < m; ++b) nb += inb[b];
+      CHECK(nb <= 4, "group spans %d bits", nb);
+      for (const std::vector<int>* part : {&pre, &mid, &post})
+        for (int bi : *part) {
+          stamp[bi] = clock++;
+          for (int k = 0; k < items[bi].nbits; ++k) CHECK(inb[items[bi].bits[k]], "block bit outside the group");
+        }
+      ++groups;
+      d1 += (int)mid.size();
+      empty_groups += mid.empty();
+    }
+    for (size_t i = 0; i < items.size(); ++i)
+      for (size_t j = i + 1; j < items.size(); ++j) {
+        bool share = false;
+        for (int a = 0; a < items[i].nbits; ++a)
+          for (int b = 0; b < items[j].nbits; ++b) share = share || items[i].bits[a] == items[j].bits[b];
+        if (share) CHECK(stamp[i] < stamp[j], "blocks %zu and %zu share a bit and were reordered", i, j);
+      }
+    printf("hea m=%d depth=%d: %d groups (%d without a one-qubit block), %.2f one-qubit blocks per group\n", m, depth, groups,
+           empty_groups, d1 / (double)groups);
+    CHECK(d1 / (double)groups >= 2.5, "groups too small");
   }
   if (fails) {
     printf("rg_check: %d failures\n", fails);

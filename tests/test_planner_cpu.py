@@ -146,3 +146,30 @@ def test_cached_plan_rejects_malformed_files(tmp_path):
         assert info.path == good.path
         with open(path) as fh:
             assert json.load(fh)["path"] == [list(p) for p in good.path]   # overwritten with a valid plan
+
+
+@pytest.mark.parametrize("alpha,temp", [(1.0, 0.0), (0.5, 0.3), (0.0, 1.0), (1.0, 1.0)])
+def test_native_greedy_pass_is_bit_identical_to_its_python_mirror(alpha, temp):
+    """tq_tn_greedy_path (csrc/tq_planner.cu) against planner._greedy_once: the same ssa path and the same state of
+    the random stream afterwards, on closed and open networks, with disconnected parts, and through find_path."""
+    import random
+
+    nets = []
+    for seed, (rows, cols, cycles) in enumerate([(3, 4, 6), (4, 5, 8), (2, 3, 4)]):
+        spec = W.lattice_rcs(rows, cols, cycles, seed=seed, measure="state")
+        circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
+        inputs, output = tn_ref.index_maps(circ)[0]
+        nets.append(([list(t) for t in inputs], list(output)))                                   # open: a state network
+        nets.append(([list(t) for t in inputs] + [[ix] for ix in output], []))                   # closed: an amplitude
+    nets.append(([[0, 1], [1, 2], [7, 8], [8, 9, 7], [20]], [0, 2]))                             # disconnected parts
+    nets.append(([[5]], [5]))                                                                    # one tensor
+    for inputs, output in nets:
+        r1, r2 = random.Random(11), random.Random(11)
+        a = planner._greedy_once(inputs, output, r1, alpha, temp)
+        b = planner._greedy_once_native(inputs, output, r2, alpha, temp)
+        assert a == b
+        assert r1.getstate() == r2.getstate()
+    inputs, output = nets[3]
+    p1 = planner.find_path(inputs, output, repeats=6, seed=3, native_greedy=False)
+    p2 = planner.find_path(inputs, output, repeats=6, seed=3, native_greedy=True)
+    assert p1.path == p2.path and p1.flops_log2 == p2.flops_log2
