@@ -102,9 +102,9 @@ typedef struct tq_plan_opts {
   int32_t fuse;                 /* -1 = default (1). 1: fuse runs of gates in registers               */
   int32_t structure;            /* 0 = default: automatic.  complex64 circuits of >= 9 qubits whose gates are all
                                    (controlled) one-target blocks or diagonals take the register-group sweeps (2) when
-                                   those remove at least a third of the multiply-adds of the default fusion (layers of
-                                   one-qubit gates between sparse entanglers); everything else takes the default sweeps,
-                                   where every fused block is a dense complex matrix.
+                                   those need no more multiply-adds than the default fusion (layers of one-qubit gates
+                                   between sparse entanglers); everything else takes the default sweeps, where every
+                                   fused block is a dense complex matrix.
                                    -1: the default sweeps whatever the circuit.
                                    1 (experimental): blocks of real gates (RY, CRY, H, X, CNOT, ...) take real-matrix
                                    paths with half the multiplies, and one-qubit diagonal gates (RZ, PhaseShift, S, T,

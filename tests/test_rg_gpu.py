@@ -88,8 +88,8 @@ def test_register_group_request_falls_back_when_the_circuit_does_not_qualify():
 
 @pytest.mark.parametrize("case", RG_CASES, ids=case_id)
 def test_automatic_choice_and_forced_default_sweeps(case):
-    """plan_opts["structure"]: 0 (default) picks the register groups for the hardware-efficient ansatz circuits (they
-    halve the arithmetic there) and the default sweeps for the many-body-localisation circuits (their pair blocks fold
+    """plan_opts["structure"]: 0 (default) picks the register groups for the hardware-efficient ansatz circuits (the same
+    arithmetic in half the passes over the tile) and the default sweeps for the many-body-localisation circuits (their pair blocks fold
     ~18 gates each); -1 forces the default sweeps, which still match the fixtures on every case."""
     name = case["spec"]["name"]
     cc = build(case, "c64", case["flat"][0]).compilecircuit(backend="pytorch_b200", dtype=torch.complex64)
