@@ -55,6 +55,8 @@ struct HostBlock {
   bool real = true;    // every member is real: the block's product is real (half the multiplies, only Re W needed)
   bool diag1 = false;  // a lone one-qubit diagonal gate kept out of dense blocks: merged into a diagonal layer op
   bool is_x = false;   // a lone fixed gate whose target block is exactly PauliX (CNOT, Toffoli, X): a permutation
+  uint32_t gen = 0;    // register groups: generator codes (first | last << 4) when every trainable slot belongs to a
+                       // Pauli rotation that is the block's first or last member (tq_sv_rg.cuh: rg_bwd_d1_gen)
   // resolved op
   int cls = OP_DENSE;
   std::vector<int> targets, controls;
@@ -883,6 +885,34 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     flush_fold();
     mb.instr_end = (int)p->minstrs.size();
     mb.nderiv = b.nderiv;
+    if (p->rg && b.nderiv > 0) {
+      auto code = [](const HostGate& g) -> uint32_t {
+        switch (g.kind) {
+          case TQ_G_RX: case TQ_G_CRX: return RG_PX;
+          case TQ_G_RY: case TQ_G_CRY: return RG_PY;
+          case TQ_G_RZ: case TQ_G_CRZ: return RG_PZ;
+          case TQ_G_PHASESHIFT: case TQ_G_CPHASE: return RG_PP;
+          default: return 0u;
+        }
+      };
+      const int first = b.members.front(), last = b.members.back();
+      bool ok = true;
+      uint32_t gf = 0, gl = 0;
+      for (int gi : b.members) {
+        const HostGate& g = p->gates[gi];
+        if (g.ntrain == 0) continue;
+        const uint32_t c = (g.ntrain == 1 && g.nparams == 1) ? code(g) : 0u;
+        if (!c)
+          ok = false;
+        else if (gi == last)
+          gl = c;
+        else if (gi == first)
+          gf = c;
+        else
+          ok = false;
+      }
+      b.gen = ok ? (gf | (gl << 4)) : 0u;
+    }
     if (!diag_layers) b.real = b.diag1 = false;
     if (single) {
       const HostGate& g = p->gates[b.members[0]];
@@ -1076,7 +1106,7 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
             for (int q : hb.controls) creg[nc++] = reg_index(q);
             TQ_REQUIRE(hb.cls == OP_DIAG || nt == 1, TQ_E_INVALID, "tq_plan_create: dense block with %d targets in a register group", nt);
             OpDesc d;
-            rg_make_sub(hb.cls, nt, treg, nc, creg, hb.is_x, hb.count, hb.nderiv, d);
+            rg_make_sub(hb.cls, nt, treg, nc, creg, hb.is_x, hb.count, hb.nderiv, d, hb.gen);
             TQ_REQUIRE(d.path != RG_GEN || hb.nderiv == 0, TQ_E_UNSUPPORTED, "tq_plan_create: trainable multi-target diagonal");
             const int pe = block_pay_entries(hb.count, hb.nderiv, dir != 0);
             (dir ? p->mblocks[hb.mat_block].off_b : p->mblocks[hb.mat_block].off_f) = (int32_t)stride;

@@ -26,6 +26,7 @@ constexpr int RG_BITS = 4;                         // register bits of a group
 constexpr int RG_MAX_SUB = CHUNK_OPS - 1;          // header + sub-ops travel in one prefetch chunk
 constexpr int RG_MIN_TILE = 9;                     // 2^(m-4) >= 32 items: every lane of a warp owns a group
 constexpr uint32_t RG_MAP_ID = 0x8421u;            // identity relabelling
+enum { RG_PX = 1, RG_PY = 2, RG_PZ = 3, RG_PP = 4 };  // generator of a trainable member: RX, RY, RZ, PhaseShift (and controlled)
 
 // Header:  path = P_RG, nins = number of sub-ops, tpos[0..3] = register bits (tile-local amplitude-bit positions,
 //          ascending), and the swizzled word offsets of the LOAD and STORE relabellings, five 16-bit values each
@@ -35,6 +36,8 @@ constexpr uint32_t RG_MAP_ID = 0x8421u;            // identity relabelling
 // Sub-op:  path = kind, k = register-bit INDEX (0..3) of the target (RG_D1, RG_X1), cmask = 16-bit "live" mask (bit j
 //          set when register pattern j satisfies the block's controls), nderiv / dslot / pay_off / count as in the
 //          default ops (count = 2: the payload is a diagonal, applied as a 2x2 with zero off-diagonals).
+//          pad = generator codes: (first) | (last) << 4 when every trainable slot of the block belongs to a Pauli
+//          rotation that is the block's first or last member (RG_PX .. RG_PP); 0: gradients through W.
 //          RG_GEN (multi-target diagonal, no trainable slot): ins[0..3] | tpos[0..3] hold sixteen 4-bit diagonal
 //          indices, one per register pattern.
 
@@ -44,7 +47,7 @@ __host__ __device__ __forceinline__ uint32_t rg_phys(uint32_t i) {
 
 // the two 16-byte halves of an OpDesc, decoded
 struct RgSub {
-  uint32_t kind, k, nsub, nderiv, count, live, tlo, thi, pay_off, dslot;
+  uint32_t kind, k, nsub, nderiv, count, live, tlo, thi, pay_off, dslot, gen;
 };
 __host__ __device__ __forceinline__ RgSub rg_decode(uint4 w0, uint4 w1) {
   RgSub d;
@@ -58,6 +61,7 @@ __host__ __device__ __forceinline__ RgSub rg_decode(uint4 w0, uint4 w1) {
   d.pay_off = w1.x;
   d.dslot = w1.y;
   d.count = w1.z;
+  d.gen = w1.w;                    // pad: generator codes of the block's trainable slots (RG_GEN_*), 0 = use W
   return d;
 }
 
@@ -223,6 +227,54 @@ __host__ __device__ __forceinline__ void rg_bwd_d1(cx<float> (&a)[16], cx<float>
     if (!(j & tb) && ((live >> j) & 1u)) rg_bwd2(mh, a[j], a[j | tb], l[j], l[j | tb], W, has_d);
 }
 
+// Gradient of a Pauli-rotation slot without W.  A block U whose LAST member is L = exp(-i theta P / 2) has
+// dU/dtheta = (-i/2 P) U, so dL/dtheta = Re <lambda | (-i/2 P) | psi> with both vectors at the block's OUTPUT (before
+// the un-apply); one whose FIRST member is such a rotation has dU/dtheta = U (-i/2 P): the same expression at the
+// block's INPUT (after the un-apply of psi and lambda).  PhaseShift: generator i |1><1|.  Four multiply-adds per pair
+// and slot instead of the sixteen of W (the factor 1/2 is applied once, by the caller).
+template <int P>
+__host__ __device__ __forceinline__ float rg_gen_term(cx<float> l0, cx<float> l1, cx<float> a0, cx<float> a1) {
+  if (P == RG_PX) return (l0.x * a1.y - l0.y * a1.x) + (l1.x * a0.y - l1.y * a0.x);   // Im(conj(l0) a1 + conj(l1) a0)
+  if (P == RG_PY) return (l1.x * a0.x + l1.y * a0.y) - (l0.x * a1.x + l0.y * a1.y);   // Re(conj(l1) a0 - conj(l0) a1)
+  if (P == RG_PZ) return (l0.x * a0.y - l0.y * a0.x) - (l1.x * a1.y - l1.y * a1.x);   // Im(conj(l0) a0 - conj(l1) a1)
+  return -2.f * (l1.x * a1.y - l1.y * a1.x);                                         // 2 Re(conj(l1) i a1)
+}
+template <int T, int P>
+__host__ __device__ __forceinline__ float rg_gen_sum(const cx<float> (&a)[16], const cx<float> (&l)[16], uint32_t live) {
+  constexpr int tb = 1 << T;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (!(j & tb) && ((live >> j) & 1u)) s += rg_gen_term<P>(l[j], l[j | tb], a[j], a[j | tb]);
+  return 0.5f * s;
+}
+template <int T>
+__host__ __device__ __forceinline__ float rg_gen_sum_dyn(const cx<float> (&a)[16], const cx<float> (&l)[16], uint32_t live,
+                                                         uint32_t P) {
+  switch (P) {
+    case RG_PX: return rg_gen_sum<T, RG_PX>(a, l, live);
+    case RG_PY: return rg_gen_sum<T, RG_PY>(a, l, live);
+    case RG_PZ: return rg_gen_sum<T, RG_PZ>(a, l, live);
+    default: return rg_gen_sum<T, RG_PP>(a, l, live);
+  }
+}
+// adjoint step with generator gradients: W[0].x / W[0].y receive the sums of the block's slots in slot order
+template <int T>
+__host__ __device__ __forceinline__ void rg_bwd_d1_gen(cx<float> (&a)[16], cx<float> (&l)[16], const cx<float>* mh,
+                                                       uint32_t live, uint32_t gen, cx<float>* W) {
+  const uint32_t gf = gen & 15u, gl = gen >> 4;
+  float s_last = 0.f, s_first = 0.f;
+  if (gl) s_last = rg_gen_sum_dyn<T>(a, l, live, gl);
+  rg_bwd_d1<T>(a, l, mh, live, false, W);
+  if (gf) s_first = rg_gen_sum_dyn<T>(a, l, live, gf);
+  if (gf) {
+    W[0].x = s_first;
+    W[0].y = s_last;
+  } else {
+    W[0].x = s_last;
+  }
+}
+
 // what one thread adds to a gradient slot of a 2x2 sub-op: Re sum_rc dG[r][c] W[r][c]; De = the slot's derivative
 // entries (4 dense, 2 diagonal)
 __host__ __device__ __forceinline__ float rg_grad_term(const cx<float>* W, const cx<float>* De, uint32_t count) {
@@ -238,6 +290,15 @@ __host__ __device__ __forceinline__ float rg_grad_term(const cx<float>* W, const
 __host__ __device__ __forceinline__ bool rg_bwd_sub(cx<float> (&a)[16], cx<float> (&l)[16], const RgSub& d,
                                                     const cx<float>* mh, const cx<float>* pay, cx<float>* W) {
   const bool has_d = d.nderiv > 0;
+  if (d.kind == RG_D1 && d.gen) {
+    switch (d.k) {
+      case 0: rg_bwd_d1_gen<0>(a, l, mh, d.live, d.gen, W); break;
+      case 1: rg_bwd_d1_gen<1>(a, l, mh, d.live, d.gen, W); break;
+      case 2: rg_bwd_d1_gen<2>(a, l, mh, d.live, d.gen, W); break;
+      default: rg_bwd_d1_gen<3>(a, l, mh, d.live, d.gen, W); break;
+    }
+    return true;
+  }
   switch (d.kind * 4u + (d.kind == RG_GEN ? 0u : d.k)) {
     case RG_D1 * 4 + 0: rg_bwd_d1<0>(a, l, mh, d.live, has_d, W); return has_d;
     case RG_D1 * 4 + 1: rg_bwd_d1<1>(a, l, mh, d.live, has_d, W); return has_d;
@@ -258,8 +319,9 @@ __host__ __device__ __forceinline__ bool rg_bwd_sub(cx<float> (&a)[16], cx<float
 // ---- descriptors (host) ------------------------------------------------------------------------------------------------
 // treg / creg: register-bit INDEX (0..3) of every target (most significant bit of the matrix index first) / control
 inline void rg_make_sub(int cls, int ntargets, const int* treg, int nctrl, const int* creg, bool is_x, int count,
-                        int nderiv, OpDesc& d) {
+                        int nderiv, OpDesc& d, uint32_t gen = 0) {
   memset(&d, 0, sizeof(d));
+  d.pad = ntargets == 1 && nderiv > 0 ? gen : 0u;
   uint32_t cm = 0;
   for (int c = 0; c < nctrl; ++c) cm |= 1u << creg[c];
   uint32_t live = 0;
@@ -519,6 +581,12 @@ __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_
 #pragma unroll
       for (int e = 0; e < 4; ++e) W[e] = mk<float>(0.f, 0.f);
       if (rg_bwd_sub(a, l, d, mh, pay_gen + (d.pay_off - pay_begin), W)) {
+        if (d.gen) {  // generator sums, in slot order
+          for (uint32_t e = 0; e < d.nderiv; ++e) {
+            const float v = warp_sum(e == 0 ? W[0].x : W[0].y);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[d.dslot + e], v);
+          }
+        } else
         for (uint32_t e = 0; e < d.nderiv; ++e) {
           cf De[4];
           if (d.count == 2) {

@@ -298,6 +298,102 @@ int main() {
             grad_ref[sidx]);
     }
   }
+  // 3b. generator gradients: blocks U = L * M * F with Pauli rotations as first / last member against the derivative
+  //     matrices of the same block
+  {
+    auto rot = [](int P, double t, zc* M) {  // exp(-i t P / 2); P = 4: diag(1, e^{it})
+      const double c = cos(t / 2), sn = sin(t / 2);
+      const zc I(0, 1);
+      if (P == RG_PX) { M[0] = c; M[1] = -I * sn; M[2] = -I * sn; M[3] = c; }
+      if (P == RG_PY) { M[0] = c; M[1] = -sn; M[2] = sn; M[3] = c; }
+      if (P == RG_PZ) { M[0] = std::exp(-I * (t / 2)); M[1] = 0; M[2] = 0; M[3] = std::exp(I * (t / 2)); }
+      if (P == RG_PP) { M[0] = 1; M[1] = 0; M[2] = 0; M[3] = std::exp(I * t); }
+    };
+    auto gen = [](int P, zc* G) {  // dR/dt = G R
+      const zc I(0, 1);
+      for (int i = 0; i < 4; ++i) G[i] = 0;
+      if (P == RG_PX) { G[1] = -I * 0.5; G[2] = -I * 0.5; }
+      if (P == RG_PY) { G[1] = -0.5; G[2] = 0.5; }
+      if (P == RG_PZ) { G[0] = -I * 0.5; G[3] = I * 0.5; }
+      if (P == RG_PP) { G[3] = I; }
+    };
+    auto mul = [](const zc* A, const zc* B, zc* C) {
+      zc T[4] = {A[0] * B[0] + A[1] * B[2], A[0] * B[1] + A[1] * B[3], A[2] * B[0] + A[3] * B[2], A[2] * B[1] + A[3] * B[3]};
+      for (int i = 0; i < 4; ++i) C[i] = T[i];
+    };
+    for (int trial = 0; trial < 200; ++trial) {
+      const int m = RG_MIN_TILE;
+      const uint32_t n = 1u << m;
+      int reg[4] = {1, 4, 6, 7};
+      const int pf = rand() % 5, pl = rand() % 5;          // 0: that end is not trainable
+      if (!pf && !pl) continue;
+      const bool single = pf == 0 && (rand() & 1);         // one gate: first == last
+      zc F[4], L[4], Mid[4], U[4], dF[4], dL[4], G[4], T[4];
+      const double tf = urand() * 3, tl = urand() * 3;
+      rot(pf ? pf : RG_PX, tf, F);
+      rot(pl ? pl : RG_PY, tl, L);
+      {  // a unitary middle part (the identity U U^dagger = 1 is what makes the output-side formula exact)
+        zc A[4], B[4], C[4];
+        rot(RG_PX, urand() * 3, A); rot(RG_PZ, urand() * 3, B); rot(RG_PY, urand() * 3, C);
+        mul(B, A, Mid); mul(C, Mid, Mid);
+        if (single) for (int i = 0; i < 4; ++i) Mid[i] = zc(i == 0 || i == 3, 0);
+      }
+      if (single) for (int i = 0; i < 4; ++i) F[i] = zc(i == 0 || i == 3, 0);
+      mul(Mid, F, T);
+      mul(L, T, U);
+      Blk b;
+      b.cls = OP_DENSE;
+      b.is_x = false;
+      const int t = rand() % 4;
+      b.targets.push_back(reg[t]);
+      int nc = rand() % 2, creg[1] = {(t + 1) % 4}, treg[1] = {t};
+      if (nc) b.controls.push_back(reg[creg[0]]);
+      b.nderiv = (pf && !single ? 1 : 0) + (pl ? 1 : 0);
+      for (int i = 0; i < 4; ++i) b.pay.push_back(mk<float>((float)U[i].real(), (float)U[i].imag()));
+      if (pf && !single) {  // dU = L Mid (G F)
+        gen(pf, G); mul(G, F, dF); mul(Mid, dF, T); mul(L, T, T);
+        for (int i = 0; i < 4; ++i) b.pay.push_back(mk<float>((float)T[i].real(), (float)T[i].imag()));
+      }
+      if (pl) {
+        gen(pl, G); mul(G, U, dL);
+        for (int i = 0; i < 4; ++i) b.pay.push_back(mk<float>((float)dL[i].real(), (float)dL[i].imag()));
+      }
+      const uint32_t code = (uint32_t)((pf && !single ? pf : 0) | ((pl ? pl : 0) << 4));
+      if (!b.nderiv) continue;
+      OpDesc d;
+      rg_make_sub(b.cls, 1, treg, nc, creg, false, 4, b.nderiv, d, code);
+      const RgSub sub = decode(d);
+      std::vector<zc> psi(n), lam(n);
+      std::vector<cf32> sp(n), sl(n);
+      for (uint32_t i = 0; i < n; ++i) {
+        cf32 v = mk<float>((float)urand(), (float)urand()), w = mk<float>((float)urand(), (float)urand());
+        psi[i] = Z(v); lam[i] = Z(w);
+        sp[rg_phys(i)] = v; sl[rg_phys(i)] = w;
+      }
+      uint32_t regbits = 0, o[4];
+      for (int i = 0; i < 4; ++i) regbits |= (uint32_t)reg[i] << (8 * i);
+      rg_bit_offsets(regbits, o);
+      const RgAddr A = rg_addr(o, RG_MAP_ID);
+      double g[2] = {0, 0};
+      for (uint32_t gi = 0; gi < (n >> 4); ++gi) {
+        const uint32_t pb = rg_base(regbits, gi);
+        cf32 a[16], l[16], W[4] = {mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0), mk<float>(0, 0)}, mh[4];
+        for (int j = 0; j < 16; ++j) { a[j] = sp[pb ^ RG_OFF(A, j)]; l[j] = sl[pb ^ RG_OFF(A, j)]; }
+        rg_ld2x2<true>(b.pay.data(), 4, mh);
+        CHECK(rg_bwd_sub(a, l, sub, mh, b.pay.data(), W), "generator sub-op reports no gradient");
+        g[0] += W[0].x;
+        g[1] += W[0].y;
+      }
+      // reference: Re <lambda | dU_e | psi_prev>, psi_prev = U^dagger psi, with the block's own derivative matrices
+      std::vector<zc> prev = psi;
+      ref_apply(prev, m, b, true);
+      for (int e = 0; e < b.nderiv; ++e) {
+        const double r = ref_grad(prev, lam, m, b, e);
+        CHECK(fabs(g[e] - r) <= 2e-3 * fmax(1.0, fabs(r)), "generator gradient trial %d slot %d: %g vs %g (pf %d pl %d single %d)", trial,
+              e, g[e], r, pf, pl, (int)single);
+      }
+    }
+  }
   // 4. grouping of a hardware-efficient ansatz inside one tile: every block lands in exactly one group, blocks that
   //    share a bit keep their order, and the groups hold close to four one-qubit blocks each
   for (int m = 9; m <= 14; ++m) {
