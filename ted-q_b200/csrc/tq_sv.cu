@@ -799,10 +799,9 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
   }
   p->rg = rg;
   if (rg) {
-    // the tile <-> state copies move pairs of amplitudes (>= 1 bit); the default is 2 bits (32-byte sectors): a
-    // register-group sweep is bound by instruction issue, not by HBM, and two more free tile bits make the sweeps
-    // deeper (20-qubit HEA: 9 + 12 sweeps instead of 13 + 14, 1241 -> 1267 evaluations/s)
-    if (!opts || opts->coalesce_bits < 0) coalesce = std::min(coalesce, 2);
+    // the tile <-> state copies move pairs of amplitudes: at least one coalesce bit.  (Fewer coalesce bits make the
+    // sweeps deeper — 20-qubit HEA: 9 + 12 sweeps with 2 bits, 7 + 11 with 1, against 13 + 14 with the default 3 — but
+    // the register-group sweeps are bound by instruction issue, not by HBM: 1369 / 1333 / 1405 evaluations/s.)
     coalesce = std::max(coalesce, 1);
     p->coalesce = coalesce;
     p->threads_f = std::min(256, 1 << (m_f - RG_BITS));
@@ -1510,6 +1509,21 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
   return TQ_OK;
 }
 
+// Register-group adjoint sweep: shared memory for the gradient cells (tq_sv_rg.cuh: rg_grad_cell).  The fewest butterfly
+// rounds whose cells still fit beside two resident CTAs per SM (one when the tiles alone exceed half an SM).
+static int rg_grad_layout(size_t used, int n_dslots, int threads, size_t* smem) {
+  const size_t sm_bytes = 227 * 1024, two = sm_bytes / 2 - 1024, one = sm_bytes - 2048;
+  const size_t limit = used + 32 * (size_t)n_dslots <= two ? two : one;
+  for (int r = 0; r <= 5; ++r) {
+    const size_t need = used + sizeof(float) * (size_t)n_dslots * (size_t)(threads >> r);
+    if (need <= limit || r == 5) {
+      *smem = need;
+      return r;
+    }
+  }
+  return 5;
+}
+
 template <typename R>
 static int backward_impl(const tq_plan* p, const void* params, int64_t B, const void* grad_out, void* grad_params,
                          void* workspace, size_t ws_bytes, cudaStream_t st) {
@@ -1550,6 +1564,8 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
     if constexpr (sizeof(R) == 4) {
       if (p->rg) {
         TQ_REQUIRE(a.psi, TQ_E_INVALID, "tq_backward: the workspace holds no final state");
+        a.grad_rounds = rg_grad_layout(((size_t)2 * sizeof(cx<R>) << n) + RING_BYTES, sb.n_dslots, p->threads_b, &smem);
+        TQ_REQUIRE(smem <= 227 * 1024 - 1024, TQ_E_UNSUPPORTED, "tq_backward: %d gradient slots exceed shared memory", sb.n_dslots);
         if ((rc = prep_kernel(k_rg_bwd, smem))) return rc;
         k_rg_bwd<<<(unsigned)B, p->threads_b, smem, st>>>(a);
         TQ_CUDA_OK(cudaGetLastError());
@@ -1593,6 +1609,8 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
     TQ_REQUIRE(blocks < ((int64_t)1 << 31), TQ_E_UNSUPPORTED, "tq_backward: batch too large for one launch");
     if constexpr (sizeof(R) == 4) {
       if (p->rg) {
+        a.grad_rounds = rg_grad_layout(((size_t)2 * sizeof(cx<R>) << sb.geom.m) + RING_BYTES, sb.n_dslots, p->threads_b, &smem);
+        TQ_REQUIRE(smem <= 227 * 1024 - 1024, TQ_E_UNSUPPORTED, "tq_backward: %d gradient slots exceed shared memory", sb.n_dslots);
         if ((rc = prep_kernel(k_rg_bwd, smem))) return rc;
         k_rg_bwd<<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
         TQ_CUDA_OK(cudaGetLastError());

@@ -1815,6 +1815,7 @@ struct BwdArgs {
   int32_t n_meas, n_params, n_dslots;
   int32_t flags;
   int32_t tiles_log2;
+  int32_t grad_rounds;  // register-group sweeps: butterfly steps before a gradient term goes to its shared-memory cell
   Geom geom;
 };
 

@@ -553,9 +553,17 @@ __device__ __forceinline__ void rg_run_fwd(cf* s, uint32_t hdr, uint32_t pay, co
   }
 }
 
-// ng is a multiple of blockDim (host: threads = min(256, 2^(m-4)) >= 32), so every lane takes part in the reductions
+// Gradient contributions go to per-thread-group CELLS in shared memory, cells[slot][threadIdx >> rounds], after `rounds`
+// butterfly steps inside the group (rounds = 0: every thread owns a cell: no shuffle, no atomic — a cell has one
+// writer); the kernel adds the cells of a slot up once, at its end.  (One warp reduction + shared-memory atomic per
+// slot and block was a fifth of the adjoint sweep: five dependent shuffles, and float atomics on shared memory are
+// compare-and-swap loops.)  ng is a multiple of blockDim (host: threads = min(256, 2^(m-4)) >= 32).
+__device__ __forceinline__ void rg_grad_cell(float* cells, uint32_t slot, float v, int rounds) {
+  for (int r = 0; r < rounds; ++r) v += __shfl_xor_sync(0xffffffffu, v, 1 << r);
+  if ((threadIdx.x & ((1u << rounds) - 1u)) == 0) cells[slot * (blockDim.x >> rounds) + (threadIdx.x >> rounds)] += v;
+}
 __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_t pay, const cf* pay_gen,
-                                           uint32_t pay_begin, float* s_grad, int m) {
+                                           uint32_t pay_begin, float* s_grad, int rounds, int m) {
   const uint4 h0 = rg_lds_u4(hdr);
   const uint32_t sub = hdr + 32u;
   const uint32_t nsub = (h0.x >> 16) & 255u;
@@ -582,10 +590,7 @@ __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_
       for (int e = 0; e < 4; ++e) W[e] = mk<float>(0.f, 0.f);
       if (rg_bwd_sub(a, l, d, mh, pay_gen + (d.pay_off - pay_begin), W)) {
         if (d.gen) {  // generator sums, in slot order
-          for (uint32_t e = 0; e < d.nderiv; ++e) {
-            const float v = warp_sum(e == 0 ? W[0].x : W[0].y);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[d.dslot + e], v);
-          }
+          for (uint32_t e = 0; e < d.nderiv; ++e) rg_grad_cell(s_grad, d.dslot + e, e == 0 ? W[0].x : W[0].y, rounds);
         } else
         for (uint32_t e = 0; e < d.nderiv; ++e) {
           cf De[4];
@@ -595,8 +600,7 @@ __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_
             rg_lds_c2(pa + 32u + 32u * e, De[0], De[1]);
             rg_lds_c2(pa + 48u + 32u * e, De[2], De[3]);
           }
-          const float v = warp_sum(rg_grad_term(W, De, d.count));
-          if ((threadIdx.x & 31) == 0) atomicAdd(&s_grad[d.dslot + e], v);
+          rg_grad_cell(s_grad, d.dslot + e, rg_grad_term(W, De, d.count), rounds);
         }
       }
     }
@@ -633,27 +637,34 @@ __device__ __forceinline__ void rg_io_table(const Geom& g, uint32_t tile_n, uint
   const uint32_t iters = tile_n / (2u * blockDim.x);
   for (uint32_t i = threadIdx.x; i < iters; i += blockDim.x) tab[i] = dep_local(g, 2u * i * blockDim.x);
 }
+__device__ __forceinline__ void rg_cp_async8(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+}
+// STORE = false: asynchronous copies (LDGSTS, 8 bytes each: the two amplitudes of a pair may land swapped), every copy
+// of the tile in flight at once; they are complete after the next cp_async_wait_all + barrier (rg_stream begins with
+// one)
 template <bool STORE>
 __device__ __forceinline__ void rg_tile_io(cf* sm, cf* hbm, const uint32_t* tab, uint32_t base, uint32_t tile_n) {
   const uint32_t iters = tile_n / (2u * blockDim.x);
   for (uint32_t it = 0; it < iters; ++it) {
     const uint32_t q2 = 2u * (it * blockDim.x + threadIdx.x);
     const uint32_t p = rg_phys(q2);  // q2 + 1 sits at p ^ 1
-    float4* sp = reinterpret_cast<float4*>(sm + (p & ~1u));
-    float4* gp = reinterpret_cast<float4*>(hbm + (base | tab[it]));
+    cf* gp = hbm + (base | tab[it]);
     if (STORE) {
-      const float4 v = *sp;
-      *gp = (p & 1u) ? make_float4(v.z, v.w, v.x, v.y) : v;
+      const float4 v = *reinterpret_cast<const float4*>(sm + (p & ~1u));
+      *reinterpret_cast<float4*>(gp) = (p & 1u) ? make_float4(v.z, v.w, v.x, v.y) : v;
     } else {
-      const float4 v = *gp;
-      *sp = (p & 1u) ? make_float4(v.z, v.w, v.x, v.y) : v;
+      rg_cp_async8(sm + p, gp);
+      rg_cp_async8(sm + (p ^ 1u), gp + 1);
     }
   }
+  if (!STORE) cp_async_commit();
 }
 
 template <bool BWD>
 __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& ring, const StreamRef& st, const cf* pay_b,
-                                          float* s_grad, int m) {
+                                          float* s_grad, int rounds, int m) {
   ring_start<float>(ring, st, pay_b);
   for (int c = 0; c < st.n_chunks; ++c) {
     cp_async_wait_all();
@@ -666,7 +677,7 @@ __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& rin
     for (uint32_t o = 0; o < ci.op_count;) {
       const uint32_t hdr = dd + 32u * o;
       if (BWD)
-        rg_run_bwd(sp, sl, hdr, pa, pp, ci.pay_begin, s_grad, m);
+        rg_run_bwd(sp, sl, hdr, pa, pp, ci.pay_begin, s_grad, rounds, m);
       else
         rg_run_fwd(sp, hdr, pa, pp, ci.pay_begin, m);
       o += 1u + ((rg_lds_u4(hdr).x >> 16) & 255u);
@@ -701,7 +712,9 @@ __global__ void __launch_bounds__(256, 3) k_rg_fwd(const __grid_constant__ FwdAr
   } else {
     rg_tile_io<false>(sm, psi_b, io_tab, tbase, tile_n);
   }
-  rg_stream<false>(sm, nullptr, ring, a.st, a.stream + b * a.stride, nullptr, m);  // begins and ends with a barrier
+  rg_stream<false>(sm, nullptr, ring, a.st, a.stream + b * a.stride, nullptr, 0, m);  // begins and ends with a barrier
+  cp_async_wait_all();  // (a sweep without ops: the tile copies still have to land)
+  __syncthreads();
 
   if (a.flags & SW_STORE) rg_tile_io<true>(sm, psi_b, io_tab, tbase, tile_n);
   if (a.flags & SW_MEASURE) {
@@ -729,7 +742,9 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
   cf* psi_b = a.psi + (size_t)b * sv;  // the forward pass (with_backward) left the final state here
   cf* lam_b = a.lam ? a.lam + (size_t)b * sv : nullptr;
 
-  for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) s_grad[s] = 0;
+  const int rounds = a.grad_rounds;
+  const uint32_t ncell = blockDim.x >> rounds;
+  for (uint32_t s = threadIdx.x; s < (uint32_t)a.n_dslots * ncell; s += blockDim.x) s_grad[s] = 0;
 
   if (a.flags & SW_FULL) {
     for (uint32_t l = threadIdx.x; l < tile_n; l += blockDim.x) sp[l] = psi_b[l];
@@ -746,18 +761,26 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
     rg_tile_io<false>(sp, psi_b, io_tab, tbase, tile_n);
     rg_tile_io<false>(sl, lam_b, io_tab, tbase, tile_n);
   }
-  rg_stream<true>(sp, sl, ring, a.st_b, a.stream_b + b * a.stride_b, s_grad, m);  // begins and ends with a barrier
+  rg_stream<true>(sp, sl, ring, a.st_b, a.stream_b + b * a.stride_b, s_grad, rounds, m);  // begins and ends with a barrier
+  cp_async_wait_all();
+  __syncthreads();
 
   if (!(a.flags & SW_FULL) && (a.flags & SW_STORE)) {
     rg_tile_io<true>(sp, psi_b, io_tab, tbase, tile_n);
     rg_tile_io<true>(sl, lam_b, io_tab, tbase, tile_n);
   }
+  // one warp per slot adds its cells up
   float* grad_b = a.grad + b * a.n_params;
-  for (int s = threadIdx.x; s < a.n_dslots; s += blockDim.x) {
-    if (a.flags & SW_FULL)
-      grad_b[a.slot_pidx[s]] = s_grad[s];
-    else
-      atomicAdd(&grad_b[a.slot_pidx[s]], s_grad[s]);
+  for (int s = threadIdx.x >> 5; s < a.n_dslots; s += blockDim.x >> 5) {
+    float v = 0.f;
+    for (uint32_t c = threadIdx.x & 31u; c < ncell; c += 32u) v += s_grad[(uint32_t)s * ncell + c];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31u) == 0) {
+      if (a.flags & SW_FULL)
+        grad_b[a.slot_pidx[s]] = v;
+      else
+        atomicAdd(&grad_b[a.slot_pidx[s]], v);
+    }
   }
 }
 #endif  // __CUDACC__
