@@ -269,11 +269,15 @@ def check_against_cpu(what, cpu, out_gpu, grad_gpu, cdt):
 # by scripts/make_bench_plans.py with exactly the options below and committed, so that a bench run spends its
 # time on the device, not in the path search.  A missing or foreign file only means the search runs again.
 PLAN_CACHE = os.path.join(ROOT, "ted-q_b200", "plans")
-C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "64")),
-            "reconf_sweeps": int(os.environ.get("TQ_C5_RECONF", "6")),   # subtree reconfiguration of the greedy tree
-            # objective of the reconfiguration: estimated step time = max(flops / 200 TFLOP/s, bytes / 2.5 TB/s) +
-            # 12 us per launched step (planner.step_time_model), instead of the bare flop count
-            "time_model": None if os.environ.get("TQ_C5_TIME_MODEL", "1") == "0" else (2.0e14, 2.5e12, 1.2e-5),
+C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "128")),
+            "max_repeats_greedy": 64,                                    # the plain greedy plan reported beside it (c5g)
+            "reconf_sweeps": int(os.environ.get("TQ_C5_RECONF", "10")),  # subtree reconfiguration of the greedy tree
+            "reconf_leaves": int(os.environ.get("TQ_C5_LEAVES", "9")),
+            # objective of the reconfiguration: estimated step time on this engine (planner.step_time_model with the
+            # calibrated five-value model: tensor-core steps max(flops / 200 TFLOP/s, bytes / 2.5 TB/s), steps the
+            # dispatch rule keeps off the tensor cores at the FP32 GEMM / per-element rates, 1.5 us per launched step
+            # = a 32-slice launch sequence's share of a launch) instead of the bare flop count
+            "time_model": None if os.environ.get("TQ_C5_TIME_MODEL", "1") == "0" else (2.0e14, 2.5e12, 1.5e-6, 2.5e13, 1.5e12),
             "slicing_opts": {"target_size": 2 ** 27, "target_num_slices": 64}}
 
 
@@ -295,17 +299,19 @@ def c5_cpu_slices(n_slices_timed, slice_ids=None, bits=None, greedy_plan=False, 
     arrays = list(arrays) + [caps[b] for b in bits]
 
     reconf = 0 if greedy_plan else C5_HYPER["reconf_sweeps"]
+    leaves = 8 if greedy_plan else C5_HYPER["reconf_leaves"]
     tmodel = None if greedy_plan else C5_HYPER["time_model"]
+    repeats = C5_HYPER["max_repeats_greedy"] if greedy_plan else C5_HYPER["max_repeats"]
 
     def search():
-        first = planner.find_path(inputs, [], repeats=C5_HYPER["max_repeats"], seed=0, reconf_sweeps=reconf,
+        first = planner.find_path(inputs, [], repeats=repeats, seed=0, reconf_sweeps=reconf, reconf_leaves=leaves,
                                   time_model=tmodel)
         return planner.slice_path(inputs, [], first, target_size_log2=27, target_num_slices=64,
-                                  reconf_sweeps=min(3, reconf), time_model=tmodel)
+                                  reconf_sweeps=min(3, reconf), reconf_leaves=leaves, time_model=tmodel)
 
     # same key as TNExecutor._plan_key(): the engine's amplitude plan and this one share a cache file
-    info = planner.cached_plan(PLAN_CACHE, inputs, [], search, max_repeats=C5_HYPER["max_repeats"], seed=0,
-                               minimize="flops", reconf_sweeps=reconf, reconf_leaves=8, time_model=tmodel,
+    info = planner.cached_plan(PLAN_CACHE, inputs, [], search, max_repeats=repeats, seed=0,
+                               minimize="flops", reconf_sweeps=reconf, reconf_leaves=leaves, time_model=tmodel,
                                target_size=2 ** 27, target_num_slices=64)
     ids = list(slice_ids) if slice_ids is not None else list(range(n_slices_timed))
     tn_ref.contract_slice_torch(arrays, inputs, [], info.path, info.sliced, 0, dtype)   # warm-up (threads, allocator)
@@ -636,7 +642,9 @@ def measure_tn_mode(name, steps, warmup, device, dist, do_cpu, cpu_budget=10.0, 
 # ----------------------------------------------------------------------------------------------------------
 def c5_hyper(greedy_plan, contract_parallel):
     extra = {"slice_batch": int(os.environ["TQ_C5_SLICE_BATCH"])} if "TQ_C5_SLICE_BATCH" in os.environ else {}
-    return {**extra, "max_repeats": C5_HYPER["max_repeats"], "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
+    return {**extra, "max_repeats": C5_HYPER["max_repeats_greedy"] if greedy_plan else C5_HYPER["max_repeats"],
+            "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
+            "reconf_leaves": 8 if greedy_plan else C5_HYPER["reconf_leaves"],
             "time_model": None if greedy_plan else C5_HYPER["time_model"],
             "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=contract_parallel),
             "plan_cache": PLAN_CACHE}

@@ -224,8 +224,8 @@ typedef struct tq_tn_step {
  * (2..12) leaf tensors over n_idx distinct indices: leaf_open[l][x] != 0 when index x is an open leg of leaf l,
  * inside[l][x] = how many input tensors below leaf l carry x, count[x] = how many tensors of the whole network (plus
  * the output) carry x.  Finds for every subset S of the leaves the cheapest way to contract it pairwise
- * (cost of a pair = 2^|union of open legs|, or with time_model = {flop/s, bytes/s, s per step} the estimated step
- * time of planner.step_time_model); *best_full = cost of the whole subtree, split[S] = the first part of S's best
+ * (cost of a pair = 2^|union of open legs|, or with time_model = {tensor-core flop/s, bytes/s, s per step, FP32-GEMM
+ * flop/s or 0, per-element-kernel flop/s: FIVE values} the estimated step time of planner.step_time_model); *best_full = cost of the whole subtree, split[S] = the first part of S's best
  * split (the part that contains S's lowest leaf), for every S with at least two leaves.  Bit-identical to the
  * Python mirror planner._subtree_dp_py.  Returns 0 or a negative tq_status. */
 int32_t tq_tn_subtree_order(int32_t n_leaves, int32_t n_idx, const int32_t* leaf_open, const int32_t* inside,

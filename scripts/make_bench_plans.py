@@ -12,9 +12,7 @@ from tedq_b200 import workloads as W
 spec = W.lattice_rcs(5, 8, 12, seed=0)
 circ = W.build_circuit(spec, qb)
 for greedy in (False, True):
-    hyper = {"max_repeats": bench.C5_HYPER["max_repeats"], "reconf_sweeps": 0 if greedy else bench.C5_HYPER["reconf_sweeps"],
-             "time_model": None if greedy else bench.C5_HYPER["time_model"],
-             "slicing_opts": dict(bench.C5_HYPER["slicing_opts"], contract_parallel=False), "plan_cache": bench.PLAN_CACHE}
+    hyper = bench.c5_hyper(greedy, False)
     t = time.time()
     cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
     info = cc._tn._amplitude_plan()[1]

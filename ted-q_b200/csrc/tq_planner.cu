@@ -34,11 +34,25 @@ struct Bits {
   }
 };
 
-// planner.step_time_model, same operations in the same order (doubles)
+// planner.step_time_model, same operations in the same order (doubles); model = {tensor-core flop/s, bytes/s, seconds
+// per step, FP32-GEMM flop/s or 0, per-element-kernel flop/s}: FIVE values
 inline double pair_cost(int n_a, int n_b, int n_out, int n_union, const double* model) {
   if (!model) return std::ldexp(1.0, n_union);
   if (n_union <= 14) return 1e-7;
-  const double t_fl = 8.0 * std::ldexp(1.0, n_union) / model[0];
+  double f = model[0];
+  if (model[3] > 0) {
+    const int k = n_union - n_out, b = n_a + n_b - n_union - k, m = n_a - k - b, n = n_b - k - b;
+    const int hi = m > n ? m : n, lo = m < n ? m : n;
+    if (n_union >= 20 && hi >= 7 && lo >= 4) {
+    } else if (n_out <= 6 && k >= 12) {
+    } else if (m >= 6 && n >= 6 && k >= 4) {
+      f = model[3];
+    } else if (lo <= 4 && k <= 4 && n_out >= 10 && b <= 8) {
+    } else {
+      f = model[4];
+    }
+  }
+  const double t_fl = 8.0 * std::ldexp(1.0, n_union) / f;
   const double t_by = 8.0 * (std::ldexp(1.0, n_a) + std::ldexp(1.0, n_b) + std::ldexp(1.0, n_out)) / model[1];
   return (t_fl >= t_by ? t_fl : t_by) + model[2];
 }

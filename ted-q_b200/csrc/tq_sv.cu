@@ -1321,10 +1321,17 @@ double tq_plan_flops(const tq_plan* p, int32_t backward) {
     const double amps = ldexp(1.0, p->n - (int)b.controls.size());
     // complex MAC = 8 flops; a real matrix entry times a complex amplitude, accumulated = 4
     const double per = b.cls == OP_DIAG ? 6.0 : (b.real ? 4.0 : 8.0) * ldexp(1.0, (int)b.targets.size());
-    if (p->rg && b.is_x) continue;                  // a register swap
-    fl += amps * (p->rg && b.cls == OP_DIAG && b.targets.size() == 1 ? 16.0 : per);  // diagonal applied as a 2x2 there
+    if (p->rg && b.is_x) continue;                  // a register swap / an address relabelling
+    const double fwd = amps * (p->rg && b.cls == OP_DIAG && b.targets.size() == 1 ? 16.0 : per);  // diagonal applied as a 2x2 there
+    // adjoint: psi <- G^dagger psi and lambda <- G^dagger lambda cost one forward product each; the gradient terms one
+    // more (W = psi (x) conj(lambda)), or, in a register group whose slots have generator gradients, 4 multiply-adds
+    // per amplitude pair and slot (a quarter of a 2x2 product each)
+    double factor = 3.0;
+    if (p->rg && b.gen) factor = 2.0 + 0.25 * b.nderiv;
+    if (p->rg && b.nderiv == 0) factor = 2.0;
+    fl += backward ? factor * fwd : fwd;
   }
-  return backward ? 3.0 * fl : fl;
+  return fl;
 }
 
 int64_t tq_plan_launches(const tq_plan* p, int32_t backward) {

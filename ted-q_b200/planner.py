@@ -307,12 +307,42 @@ def sequential_blocked_path(inputs, output, max_block_rank: int = 4):
     return path
 
 
+# Calibrated on per-step profiles of three config-5 plans on a B200 (scripts/c5_plan_profile.py,
+# profiles/r02_plan_profile_*.json; scripts/plan_model_rank.py prints model against measurement).  Tensor-core steps
+# follow max(flops / 200 TFLOP/s, operand bytes / 2.5 TB/s) to within 20 % (the byte rate already contains the 2x / 4x
+# operand images).  What the 3-value model got wrong is every step the engine's dispatch rule (csrc/tq_tn.cu:
+# build_schedule) keeps OFF the tensor cores: it charged them the tensor-core rate.  The tiled FP32 GEMM runs at
+# ~25 TFLOP/s, and a step that fits no kernel class — neither >= 128 x 16 free extents, nor >= 64 x 64, nor <= 64
+# outputs, nor a gate-sized operand — falls to one thread per output element at ~1.7 TFLOP/s: one such step (K = 2^15,
+# 64 x 32 outputs, 10.0 of 12.5 ms per 32 slices) is why the 9.7e11-flop plan of the large search measured 26 ms against
+# the 13 ms the old model promised.
+CALIBRATED_TIME_MODEL = (2.0e14, 2.5e12, 1.2e-5, 2.5e13, 1.5e12)
+
+
 def step_time_model(n_a: int, n_b: int, n_out: int, n_union: int, model) -> float:
-    """Estimated seconds of one pairwise step on the engine: max(complex-GEMM time, HBM time) + launch overhead.
-    model = (algorithmic flop/s, bytes/s, seconds per step); ranks are log2 element counts (complex64)."""
-    f, bw, t0 = model
+    """Estimated seconds of one pairwise step on the engine: max(compute time, HBM time) + launch overhead.
+    model = (tensor-core algorithmic flop/s, bytes/s, seconds per step[, FP32-GEMM flop/s, per-element-kernel flop/s]);
+    ranks are log2 element counts (complex64).  With five values the step is classified the way the engine dispatches
+    it ("Dispatch"): tensor cores (>= 128 x 16 free extents, k + m + n + b >= 20), split-K reduction
+    (<= 64 outputs, K >= 4096) and gate-sized applies are rate / bandwidth bound as before; >= 64 x 64 x 16 steps run the
+    FP32 GEMM; everything else one thread per output element."""
+    f, bw, t0 = model[0], model[1], model[2]
     if n_union <= 14:        # small steps ride in a fused run: no launch of their own
         return 1e-7
+    if len(model) > 4 and model[3] > 0:
+        k = n_union - n_out
+        b = n_a + n_b - n_union - k
+        m, n = n_a - k - b, n_b - k - b
+        if n_union >= 20 and max(m, n) >= 7 and min(m, n) >= 4:
+            pass                                           # tensor cores
+        elif n_out <= 6 and k >= 12:
+            pass                                           # split-K reduction: bandwidth bound
+        elif m >= 6 and n >= 6 and k >= 4:
+            f = model[3]                                   # tiled FP32 GEMM
+        elif (min(m, n) <= 4 and k <= 4) and n_out >= 10 and b <= 8:
+            pass                                           # gate-sized operand applied to a large one: bandwidth bound
+        else:
+            f = model[4]                                   # one thread per output element
     return max(8.0 * 2.0 ** n_union / f, 8.0 * (2.0 ** n_a + 2.0 ** n_b + 2.0 ** n_out) / bw) + t0
 
 
@@ -384,7 +414,7 @@ def _subtree_dp_native(leaf_sets, leaf_inside, count, time_model):
     best = C.c_double(0.0)
     model = None
     if time_model is not None:
-        model = (C.c_double * 3)(*[float(v) for v in time_model])
+        model = (C.c_double * 5)(*([float(v) for v in time_model] + [0.0, 0.0])[:5])
     i32p = C.POINTER(C.c_int32)
     capi.check(capi.lib().tq_tn_subtree_order(L, n_idx, open_a.ctypes.data_as(i32p), inside_a.ctypes.data_as(i32p),
                                               count_a.ctypes.data_as(i32p), model, C.byref(best),
