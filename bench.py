@@ -273,6 +273,8 @@ C5_HYPER = {"max_repeats": int(os.environ.get("TQ_C5_REPEATS", "128")),
             "max_repeats_greedy": 64,                                    # the plain greedy plan reported beside it (c5g)
             "reconf_sweeps": int(os.environ.get("TQ_C5_RECONF", "10")),  # subtree reconfiguration of the greedy tree
             "reconf_leaves": int(os.environ.get("TQ_C5_LEAVES", "9")),
+            # independent searches (seeds 0 .. restarts-1); the calibrated model below picks the plan to run
+            "restarts": int(os.environ.get("TQ_C5_RESTARTS", "8")),
             # objective of the reconfiguration: estimated step time on this engine (planner.step_time_model with the
             # calibrated five-value model: tensor-core steps max(flops / 200 TFLOP/s, bytes / 2.5 TB/s), steps the
             # dispatch rule keeps off the tensor cores at the FP32 GEMM / per-element rates, 1.5 us per launched step
@@ -303,16 +305,12 @@ def c5_cpu_slices(n_slices_timed, slice_ids=None, bits=None, greedy_plan=False, 
     tmodel = None if greedy_plan else C5_HYPER["time_model"]
     repeats = C5_HYPER["max_repeats_greedy"] if greedy_plan else C5_HYPER["max_repeats"]
 
-    def search():
-        first = planner.find_path(inputs, [], repeats=repeats, seed=0, reconf_sweeps=reconf, reconf_leaves=leaves,
-                                  time_model=tmodel)
-        return planner.slice_path(inputs, [], first, target_size_log2=27, target_num_slices=64,
-                                  reconf_sweeps=min(3, reconf), reconf_leaves=leaves, time_model=tmodel)
-
-    # same key as TNExecutor._plan_key(): the engine's amplitude plan and this one share a cache file
-    info = planner.cached_plan(PLAN_CACHE, inputs, [], search, max_repeats=repeats, seed=0,
-                               minimize="flops", reconf_sweeps=reconf, reconf_leaves=leaves, time_model=tmodel,
-                               target_size=2 ** 27, target_num_slices=64)
+    # same key and search as TNExecutor._plan_key() / _search(): the engine's amplitude plan and this one share a cache file
+    key = dict(max_repeats=repeats, seed=0, minimize="flops", reconf_sweeps=reconf, reconf_leaves=leaves, time_model=tmodel,
+               target_size=2 ** 27, target_num_slices=64)
+    if not greedy_plan and C5_HYPER["restarts"] > 1:
+        key["restarts"] = C5_HYPER["restarts"]
+    info = planner.cached_plan(PLAN_CACHE, inputs, [], lambda: planner.search_plan(inputs, [], **key), **key)
     ids = list(slice_ids) if slice_ids is not None else list(range(n_slices_timed))
     tn_ref.contract_slice_torch(arrays, inputs, [], info.path, info.sliced, 0, dtype)   # warm-up (threads, allocator)
     amps = []
@@ -645,6 +643,7 @@ def c5_hyper(greedy_plan, contract_parallel):
     return {**extra, "max_repeats": C5_HYPER["max_repeats_greedy"] if greedy_plan else C5_HYPER["max_repeats"],
             "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
             "reconf_leaves": 8 if greedy_plan else C5_HYPER["reconf_leaves"],
+            "restarts": 1 if greedy_plan else C5_HYPER["restarts"],
             "time_model": None if greedy_plan else C5_HYPER["time_model"],
             "slicing_opts": dict(C5_HYPER["slicing_opts"], contract_parallel=contract_parallel),
             "plan_cache": PLAN_CACHE}

@@ -1,6 +1,7 @@
-"""Config 5 with alternative planner options (one GPU): python scripts/c5_try_plan.py REPEATS SWEEPS LEAVES T0 [G]
+"""Config 5 with alternative planner options (one GPU): python scripts/c5_try_plan.py REPEATS SWEEPS LEAVES T0 [G [SEED]]
 T0 = the time model's seconds per launched step.  With --plan-only the plans are searched and cached, no GPU; with
 --calibrated the five-value model of planner.CALIBRATED_TIME_MODEL (engine dispatch classes) at that T0."""
+import os
 import sys
 import time
 
@@ -14,12 +15,14 @@ from tedq_b200 import workloads as W
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 reps, sweeps, leaves, t0 = int(args[0]), int(args[1]), int(args[2]), float(args[3])
 g = int(args[4]) if len(args) > 4 else 3
+seed = int(args[5]) if len(args) > 5 else 0
 spec = W.lattice_rcs(5, 8, 12, seed=0)
 circ = W.build_circuit(spec, qb)
 from tedq_b200 import planner
 tmodel = (2.0e14, 2.5e12, t0) + (tuple(planner.CALIBRATED_TIME_MODEL[3:]) if "--calibrated" in sys.argv else ())
 hyper = {"max_repeats": reps, "reconf_sweeps": sweeps, "reconf_leaves": leaves, "time_model": tmodel,
-         "slicing_opts": dict(bench.C5_HYPER["slicing_opts"]), "plan_cache": bench.PLAN_CACHE, "slice_batch": g}
+         "slicing_opts": dict(bench.C5_HYPER["slicing_opts"]), "plan_cache": os.environ.get("TQ_PLAN_DIR", bench.PLAN_CACHE),
+         "slice_batch": g, "seed": seed}
 t = time.time()
 cc = circ.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper)
 info = cc._tn._amplitude_plan()[1]

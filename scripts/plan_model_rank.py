@@ -14,24 +14,30 @@ spec = W.lattice_rcs(5, 8, 12, seed=0)
 circ = W.build_circuit(spec, qb)
 net = tn_index.index_maps(circ.num_qubits, [list(op.qubits) for op in circ.operators], [("state", None)])[0]
 inputs = [list(t) for t in net.inputs] + [[ix] for ix in net.output]
-tm = bench.C5_HYPER["time_model"]
+import os
+CACHE = os.path.join(bench.ROOT, "profiles", "r02_plans")   # the plans that were measured (copies of the planner's cache files)
 variants = {
-    "c5 (bench plan: 64 repeats, 6 sweeps, time objective)": dict(max_repeats=64, reconf_sweeps=6, reconf_leaves=8, time_model=tm),
+    "old (first round-2 bench plan: 64 repeats, 6 sweeps, 3-value model)": dict(max_repeats=64, reconf_sweeps=6, reconf_leaves=8,
+                                                                                time_model=(2.0e14, 2.5e12, 1.2e-5)),
     "c5g (plain greedy, 64 repeats)": dict(max_repeats=64, reconf_sweeps=0, reconf_leaves=8, time_model=None),
-    "large search (128 repeats, 10 sweeps, 9 leaves, t0 = 1.5 us)": dict(max_repeats=128, reconf_sweeps=10, reconf_leaves=9,
-                                                                        time_model=(2.0e14, 2.5e12, 1.5e-6)),
+    "large search under the 3-value model (128 repeats, 10 sweeps, 9 leaves)": dict(max_repeats=128, reconf_sweeps=10, reconf_leaves=9,
+                                                                                   time_model=(2.0e14, 2.5e12, 1.5e-6)),
+    "c5 (bench plan: the same search under the calibrated model)": dict(max_repeats=128, reconf_sweeps=10, reconf_leaves=9,
+                                                                       time_model=(2.0e14, 2.5e12, 1.5e-6, 2.5e13, 1.5e12)),
+    "small search under the calibrated model (64 repeats, 6 sweeps, 8 leaves)": dict(max_repeats=64, reconf_sweeps=6, reconf_leaves=8,
+                                                                                    time_model=(2.0e14, 2.5e12, 1.5e-6, 2.5e13, 1.5e12)),
 }
-measured = {"c5": 17.8, "c5g": 41.0, "large": 62.9}   # ms per amplitude on one B200 (profiles/r02_bench_final_n1.json)
+# ms per amplitude on one B200, 32 slices per launch sequence (profiles/r02_plan_profile_*.json)
+measured = {"old": 18.6, "c5g": 41.3, "large": 26.9, "c5": 9.8, "small": 14.3}
 for name, kw in variants.items():
     def search():
         raise SystemExit("plan not in the cache: run scripts/make_bench_plans.py / scripts/c5_try_plan.py ... --plan-only first")
-    info = planner.cached_plan(bench.PLAN_CACHE, inputs, [], search, seed=0, minimize="flops", target_size=2 ** 27,
+    info = planner.cached_plan(CACHE, inputs, [], search, seed=0, minimize="flops", target_size=2 ** 27,
                                target_num_slices=64, **kw)
     row = []
-    for label, model in (("old", (2.0e14, 2.5e12, 1.2e-5)), ("old, t0 = 1.5 us", (2.0e14, 2.5e12, 1.5e-6)),
-                         ("calibrated", planner.CALIBRATED_TIME_MODEL)):
+    for label, model in (("3-value", (2.0e14, 2.5e12, 1.5e-6)), ("calibrated", (2.0e14, 2.5e12, 1.5e-6, 2.5e13, 1.5e12))):
         t = planner.path_time(inputs, [], info.path, info.sliced, model) * info.n_slices
         row.append("%s %.1f ms" % (label, t * 1e3))
     key = name.split(" ")[0]
-    print("%-62s flops/amplitude %.2e  width %d | model: %s | measured %.1f ms" % (
+    print("%-80s flops/amplitude %.2e  width %d | model: %s | measured %.1f ms" % (
         name, 2.0 ** info.flops_log2 * info.n_slices, info.width, ", ".join(row), measured[key]))

@@ -628,6 +628,31 @@ def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] =
     return PathInfo(path, sliced, width, fl, len(path))
 
 
+def search_plan(inputs, output, max_repeats: int = 16, seed: int = 0, minimize: str = "flops", reconf_sweeps: int = 0,
+                reconf_leaves: int = 8, time_model=None, target_size=None, target_num_slices: int = 1,
+                restarts: int = 1) -> PathInfo:
+    """The whole search the executors and the bench share: ``find_path`` + ``slice_path``, ``restarts`` times with
+    seeds seed, seed + 1, ...; the plan with the smallest estimated run time (``path_time`` x slices under
+    ``time_model``; flops without a model) is kept.  The restarts are independent searches: what ranks them is the
+    calibrated step-time model, which is the point of having one ("Planner")."""
+    best = None
+    for r in range(max(1, int(restarts))):
+        info = find_path(inputs, output, repeats=int(max_repeats), seed=int(seed) + r, minimize=minimize,
+                         reconf_sweeps=int(reconf_sweeps), reconf_leaves=int(reconf_leaves), time_model=time_model)
+        tnum = int(target_num_slices or 1)
+        if target_size or tnum > 1:
+            info = slice_path(inputs, output, info, target_size_log2=int(math.log2(target_size)) if target_size else None,
+                              target_num_slices=tnum, reconf_sweeps=min(3, int(reconf_sweeps)),
+                              reconf_leaves=int(reconf_leaves), time_model=time_model)
+        if time_model is not None:
+            score = path_time(inputs, output, info.path, info.sliced, time_model) * info.n_slices
+        else:
+            score = info.flops_log2 + len(info.sliced)
+        if best is None or score < best[0]:
+            best = (score, info)
+    return best[1]
+
+
 PLANNER_VERSION = 2   # bump when the search changes: stored plans of another version are searched again
 
 

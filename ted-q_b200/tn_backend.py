@@ -64,30 +64,18 @@ class TNExecutor:
 
     def _plan_key(self):
         so = self.ho.get("slicing_opts") or {}
-        return {"max_repeats": int(self.ho.get("max_repeats", 16)), "seed": int(self.ho.get("seed", 0)),
-                "minimize": self.ho.get("minimize", "flops"), "reconf_sweeps": int(self.ho.get("reconf_sweeps", 0)),
-                "reconf_leaves": int(self.ho.get("reconf_leaves", 8)), "time_model": self.ho.get("time_model"),
-                "target_size": so.get("target_size"), "target_num_slices": int(so.get("target_num_slices", 1) or 1)}
+        key = {"max_repeats": int(self.ho.get("max_repeats", 16)), "seed": int(self.ho.get("seed", 0)),
+               "minimize": self.ho.get("minimize", "flops"), "reconf_sweeps": int(self.ho.get("reconf_sweeps", 0)),
+               "reconf_leaves": int(self.ho.get("reconf_leaves", 8)), "time_model": self.ho.get("time_model"),
+               "target_size": so.get("target_size"), "target_num_slices": int(so.get("target_num_slices", 1) or 1)}
+        if int(self.ho.get("restarts", 1)) > 1:
+            key["restarts"] = int(self.ho["restarts"])
+        return key
 
     def _search(self, net) -> planner.PathInfo:
         """Path search + slicing for one network (hyper_opt: max_repeats, seed, minimize, reconf_sweeps,
-        reconf_leaves, time_model, slicing_opts{target_size, target_num_slices})."""
-        so = self.ho.get("slicing_opts") or {}
-        info = planner.find_path(net.inputs, net.output, repeats=int(self.ho.get("max_repeats", 16)),
-                                 seed=int(self.ho.get("seed", 0)), minimize=self.ho.get("minimize", "flops"),
-                                 reconf_sweeps=int(self.ho.get("reconf_sweeps", 0)),
-                                 reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
-                                 time_model=self.ho.get("time_model"))
-        tsize = so.get("target_size")
-        tnum = int(so.get("target_num_slices", 1) or 1)
-        if tsize or tnum > 1:
-            info = planner.slice_path(net.inputs, net.output, info,
-                                      target_size_log2=int(np.log2(tsize)) if tsize else None,
-                                      target_num_slices=tnum,
-                                      reconf_sweeps=min(3, int(self.ho.get("reconf_sweeps", 0))),
-                                      reconf_leaves=int(self.ho.get("reconf_leaves", 8)),
-                                      time_model=self.ho.get("time_model"))
-        return info
+        reconf_leaves, time_model, restarts, slicing_opts{target_size, target_num_slices})."""
+        return planner.search_plan(net.inputs, net.output, **self._plan_key())
 
     # ------------------------------------------------------------------
     def _engine_opts(self, plan):

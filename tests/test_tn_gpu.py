@@ -381,7 +381,7 @@ def test_c5_slices_match_host_tensordot():
 
     spec = W.lattice_rcs(5, 8, 12, seed=0)
     hyper = {"max_repeats": C5_HYPER["max_repeats"], "reconf_sweeps": C5_HYPER["reconf_sweeps"],
-             "reconf_leaves": C5_HYPER["reconf_leaves"], "time_model": C5_HYPER["time_model"],
+             "reconf_leaves": C5_HYPER["reconf_leaves"], "restarts": C5_HYPER["restarts"], "time_model": C5_HYPER["time_model"],
              "slicing_opts": dict(C5_HYPER["slicing_opts"]), "plan_cache": PLAN_CACHE}
     cc = W.build_circuit(spec, qb).compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False,
                                                   hyper_opt=hyper)
