@@ -5,7 +5,7 @@
 
 Headline (default) = BASELINE.json configs[4], the north-star workload and the only one with a collective on its data
 path: single amplitudes <b|U|0> of a 40-qubit random circuit (5x8 lattice, 12 cycles) by SLICED tensor-network
-contraction.  A *step* is one pass of the hot path over one batch of synthetic input: AMPS (24) random bitstrings b;
+contraction.  A *step* is one pass of the hot path over one batch of synthetic input: AMPS (96) random bitstrings b;
 an *evaluation* is one amplitude.  STRONG scaling: the 64 slices of every amplitude are sharded over the ranks
 (contiguous ranges of slice groups), the partial sums of the whole batch are combined with ONE NCCL all-reduce per
 step, inside the timed region.  `value` = amplitudes/s, device-timed (CUDA events on the launching stream, max
@@ -38,7 +38,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-AMPS = int(os.environ.get("TQ_C5_AMPS", "24"))     # bitstrings per step of the headline
+# bitstrings per step of the headline: a multiple of the 16 amplitudes one launch sequence holds on 8 ranks, and enough
+# that 20 steps stay above a second of device time at N = 8 (96 amplitudes: 0.54 s per step on one B200, 78 ms on eight)
+AMPS = int(os.environ.get("TQ_C5_AMPS", "96"))
 
 
 # ----------------------------------------------------------------------------------------------------------
