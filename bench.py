@@ -118,8 +118,9 @@ def config_of(name, desc):
     """The `config` dict, identical in both arms (the driver compares them)."""
     if name == "c5":
         return {"workload": desc, "amplitudes_per_step": AMPS, "slices": 64, "scaling": "strong",
-                "l2": "GPU arm: per-slice intermediates (2^23..2^27 complex64) exceed L2 between steps, no flush "
-                      "needed; CPU arm: n/a"}
+                "l2": "GPU arm: the intermediates of a launch sequence (128 slice x amplitude sets of up to 2^21 "
+                      "complex64 each, 2 GB per step of the plan) exceed the 126 MB L2 between steps, no flush needed; "
+                      "CPU arm: n/a"}
     return {"workload": desc, "l2": "GPU arm: L2 flushed between timed iterations (256 MiB write); CPU arm: n/a"}
 
 
