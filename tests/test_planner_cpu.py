@@ -176,3 +176,46 @@ def test_native_greedy_pass_is_bit_identical_to_its_python_mirror(alpha, temp):
     p1 = planner.find_path(inputs, output, repeats=6, seed=3, native_greedy=False)
     p2 = planner.find_path(inputs, output, repeats=6, seed=3, native_greedy=True)
     assert p1.path == p2.path and p1.flops_log2 == p2.flops_log2
+
+
+def test_search_plan_restarts_keep_the_model_best_search():
+    """planner.search_plan: R restarts = R independent searches (seeds s .. s+R-1); the plan with the smallest modelled
+    time is kept, and the executor's cache key carries the restart count only when it is used."""
+    from tedq_b200 import tn_backend
+
+    spec = W.lattice_rcs(3, 4, 6, seed=2, measure="state")
+    circ = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
+    inputs, output = tn_ref.index_maps(circ)[0]
+    inputs = [list(t) for t in inputs] + [[ix] for ix in output]
+    model = (2.0e10, 2.5e8, 1.2e-7, 2.5e9, 1.5e8)      # (rates scaled down so that a 12-qubit network has real trade-offs)
+    kw = dict(max_repeats=4, reconf_sweeps=2, reconf_leaves=6, time_model=model, target_num_slices=4)
+    singles = [planner.search_plan(inputs, [], seed=s, **kw) for s in range(3)]
+    times = [planner.path_time(inputs, [], p.path, p.sliced, model) * p.n_slices for p in singles]
+    best = planner.search_plan(inputs, [], seed=0, restarts=3, **kw)
+    assert best.path == singles[times.index(min(times))].path
+    lowering.lower(inputs, [], best.path, best.sliced)
+    ex = tn_backend.TNExecutor.__new__(tn_backend.TNExecutor)
+    ex.ho = {"max_repeats": 4}
+    assert "restarts" not in ex._plan_key()
+    ex.ho = {"max_repeats": 4, "restarts": 8}
+    assert ex._plan_key()["restarts"] == 8
+
+
+def test_calibrated_step_time_model_follows_the_dispatch_classes():
+    """planner.step_time_model with five values charges a step by the kernel class the engine would dispatch it to
+    (csrc/tq_tn.cu: build_schedule)."""
+    tc, bw, t0, fma, elem = planner.CALIBRATED_TIME_MODEL
+    m5 = planner.CALIBRATED_TIME_MODEL
+    flops = lambda nu: 8.0 * 2.0 ** nu
+    # tensor cores: 128 x 16 free extents, k + m + n >= 20 (k 9, m 7, n 4)
+    assert planner.step_time_model(16, 13, 11, 20, m5) == max(flops(20) / tc, 8.0 * (2 ** 16 + 2 ** 13 + 2 ** 11) / bw) + t0
+    # the step of the mis-ranked plan: K = 2^15, 64 x 32 outputs -> one thread per output element
+    assert planner.step_time_model(21, 20, 11, 26, m5) == flops(26) / elem + t0
+    # 64 x 64 x 16 -> the FP32 GEMM
+    assert planner.step_time_model(10, 10, 12, 16, m5) == flops(16) / fma + t0
+    # <= 64 outputs with K >= 4096 -> split-K reduction, bandwidth bound
+    assert planner.step_time_model(18, 17, 5, 20, m5) == max(flops(20) / tc, 8.0 * (2 ** 18 + 2 ** 17 + 2 ** 5) / bw) + t0
+    # small steps ride in a fused run
+    assert planner.step_time_model(8, 8, 10, 13, m5) == 1e-7
+    # three values: every launched step at the tensor-core rate (the pre-calibration model)
+    assert planner.step_time_model(21, 20, 11, 26, m5[:3]) == max(flops(26) / tc, 8.0 * (2 ** 21 + 2 ** 20 + 2 ** 11) / bw) + t0
