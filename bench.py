@@ -643,6 +643,8 @@ def measure_tn_mode(name, steps, warmup, device, dist, do_cpu, cpu_budget=10.0, 
 # ----------------------------------------------------------------------------------------------------------
 def c5_hyper(greedy_plan, contract_parallel):
     extra = {"slice_batch": int(os.environ["TQ_C5_SLICE_BATCH"])} if "TQ_C5_SLICE_BATCH" in os.environ else {}
+    if "TQ_C5_AMP_BATCH" in os.environ:      # amplitudes per launch sequence (default: fill 2^(28 - width) sets)
+        extra["amplitude_batch"] = int(os.environ["TQ_C5_AMP_BATCH"])
     return {**extra, "max_repeats": C5_HYPER["max_repeats_greedy"] if greedy_plan else C5_HYPER["max_repeats"],
             "reconf_sweeps": 0 if greedy_plan else C5_HYPER["reconf_sweeps"],
             "reconf_leaves": 8 if greedy_plan else C5_HYPER["reconf_leaves"],

@@ -7,6 +7,7 @@
 // Amplitude index bit b (0 = fastest) <-> qubit n-1-b  (pytorch_backend.py:513-522).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <complex>
@@ -1521,14 +1522,17 @@ static int forward_impl(const tq_plan* p, const void* params, int64_t B, void* o
 static int rg_grad_layout(size_t used, int n_dslots, int threads, size_t* smem) {
   const size_t sm_bytes = 227 * 1024, two = sm_bytes / 2 - 1024, one = sm_bytes - 2048;
   const size_t limit = used + 32 * (size_t)n_dslots <= two ? two : one;
-  for (int r = 0; r <= 5; ++r) {
+  static const bool force_direct = getenv("TQ_RG_GRAD_DIRECT") != nullptr;  // tests: exercise the no-cells path
+  for (int r = 0; r <= 5 && !force_direct; ++r) {
     const size_t need = used + sizeof(float) * (size_t)n_dslots * (size_t)(threads >> r);
-    if (need <= limit || r == 5) {
+    if (need <= limit) {
       *smem = need;
       return r;
     }
   }
-  return 5;
+  // thousands of trainable slots in one sweep: no cells, every warp adds its sums to the gradient in global memory
+  *smem = used;
+  return RG_GRAD_DIRECT;
 }
 
 template <typename R>
@@ -1573,8 +1577,13 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
         TQ_REQUIRE(a.psi, TQ_E_INVALID, "tq_backward: the workspace holds no final state");
         a.grad_rounds = rg_grad_layout(((size_t)2 * sizeof(cx<R>) << n) + RING_BYTES, sb.n_dslots, p->threads_b, &smem);
         TQ_REQUIRE(smem <= 227 * 1024 - 1024, TQ_E_UNSUPPORTED, "tq_backward: %d gradient slots exceed shared memory", sb.n_dslots);
-        if ((rc = prep_kernel(k_rg_bwd, smem))) return rc;
-        k_rg_bwd<<<(unsigned)B, p->threads_b, smem, st>>>(a);
+        if (a.grad_rounds == RG_GRAD_DIRECT) {
+          if ((rc = prep_kernel(k_rg_bwd<true>, smem))) return rc;
+          k_rg_bwd<true><<<(unsigned)B, p->threads_b, smem, st>>>(a);
+        } else {
+          if ((rc = prep_kernel(k_rg_bwd<false>, smem))) return rc;
+          k_rg_bwd<false><<<(unsigned)B, p->threads_b, smem, st>>>(a);
+        }
         TQ_CUDA_OK(cudaGetLastError());
         return TQ_OK;
       }
@@ -1618,8 +1627,13 @@ static int backward_impl(const tq_plan* p, const void* params, int64_t B, const 
       if (p->rg) {
         a.grad_rounds = rg_grad_layout(((size_t)2 * sizeof(cx<R>) << sb.geom.m) + RING_BYTES, sb.n_dslots, p->threads_b, &smem);
         TQ_REQUIRE(smem <= 227 * 1024 - 1024, TQ_E_UNSUPPORTED, "tq_backward: %d gradient slots exceed shared memory", sb.n_dslots);
-        if ((rc = prep_kernel(k_rg_bwd, smem))) return rc;
-        k_rg_bwd<<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
+        if (a.grad_rounds == RG_GRAD_DIRECT) {
+          if ((rc = prep_kernel(k_rg_bwd<true>, smem))) return rc;
+          k_rg_bwd<true><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
+        } else {
+          if ((rc = prep_kernel(k_rg_bwd<false>, smem))) return rc;
+          k_rg_bwd<false><<<(unsigned)blocks, p->threads_b, smem, st>>>(a);
+        }
         TQ_CUDA_OK(cudaGetLastError());
         continue;
       }

@@ -370,7 +370,6 @@ inline void rg_pick_bits(int m, const int* used, int n_used, int* reg) {
   }
   const int need = 4 - n_used;
   int best[4], cand[4];
-  bool have = false;
   // enumerate pad choices (at most C(13, 3) = 286), keep the first conflict-free one, else the lowest free bits
   int idx[3] = {0, 1, 2};
   auto fill = [&](int* out) {
@@ -393,7 +392,6 @@ inline void rg_pick_bits(int m, const int* used, int n_used, int* reg) {
     fill(cand);
     if (conflict_free(cand)) {
       for (int i = 0; i < 4; ++i) best[i] = cand[i];
-      have = true;
       break;
     }
     int k = need - 1;
@@ -402,7 +400,6 @@ inline void rg_pick_bits(int m, const int* used, int n_used, int* reg) {
     ++idx[k];
     for (int i = k + 1; i < need; ++i) idx[i] = idx[i - 1] + 1;
   }
-  (void)have;
   for (int i = 0; i < 4; ++i) reg[i] = best[i];
 }
 
@@ -558,12 +555,29 @@ __device__ __forceinline__ void rg_run_fwd(cf* s, uint32_t hdr, uint32_t pay, co
 // writer); the kernel adds the cells of a slot up once, at its end.  (One warp reduction + shared-memory atomic per
 // slot and block was a fifth of the adjoint sweep: five dependent shuffles, and float atomics on shared memory are
 // compare-and-swap loops.)  ng is a multiple of blockDim (host: threads = min(256, 2^(m-4)) >= 32).
-__device__ __forceinline__ void rg_grad_cell(float* cells, uint32_t slot, float v, int rounds) {
-  for (int r = 0; r < rounds; ++r) v += __shfl_xor_sync(0xffffffffu, v, 1 << r);
-  if ((threadIdx.x & ((1u << rounds) - 1u)) == 0) cells[slot * (blockDim.x >> rounds) + (threadIdx.x >> rounds)] += v;
+constexpr int RG_GRAD_DIRECT = 31;  // rounds value: no cells (they would not fit): warp sum + atomic on the gradient itself
+struct RgGrad {
+  float* cells;             // shared memory: n_dslots x (blockDim >> rounds)
+  float* direct;            // RG_GRAD_DIRECT: this set's gradient row in global memory
+  const int32_t* slot_pidx;
+  int rounds;
+};
+// DIRECT is a template parameter: the no-cells path lives in its own kernel instantiation so that the common kernel keeps
+// its code (the run-time branch cost 5 % of the adjoint sweep)
+template <bool DIRECT>
+__device__ __forceinline__ void rg_grad_cell(const RgGrad& G, uint32_t slot, float v) {
+  if constexpr (DIRECT) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31u) == 0) atomicAdd(&G.direct[G.slot_pidx[slot]], v);
+  } else {
+    for (int r = 0; r < G.rounds; ++r) v += __shfl_xor_sync(0xffffffffu, v, 1 << r);
+    if ((threadIdx.x & ((1u << G.rounds) - 1u)) == 0)
+      G.cells[slot * (blockDim.x >> G.rounds) + (threadIdx.x >> G.rounds)] += v;
+  }
 }
+template <bool DIRECT>
 __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_t pay, const cf* pay_gen,
-                                           uint32_t pay_begin, float* s_grad, int rounds, int m) {
+                                           uint32_t pay_begin, const RgGrad& grad, int m) {
   const uint4 h0 = rg_lds_u4(hdr);
   const uint32_t sub = hdr + 32u;
   const uint32_t nsub = (h0.x >> 16) & 255u;
@@ -590,7 +604,7 @@ __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_
       for (int e = 0; e < 4; ++e) W[e] = mk<float>(0.f, 0.f);
       if (rg_bwd_sub(a, l, d, mh, pay_gen + (d.pay_off - pay_begin), W)) {
         if (d.gen) {  // generator sums, in slot order
-          for (uint32_t e = 0; e < d.nderiv; ++e) rg_grad_cell(s_grad, d.dslot + e, e == 0 ? W[0].x : W[0].y, rounds);
+          for (uint32_t e = 0; e < d.nderiv; ++e) rg_grad_cell<DIRECT>(grad, d.dslot + e, e == 0 ? W[0].x : W[0].y);
         } else
         for (uint32_t e = 0; e < d.nderiv; ++e) {
           cf De[4];
@@ -600,7 +614,7 @@ __device__ __forceinline__ void rg_run_bwd(cf* sp, cf* sl, uint32_t hdr, uint32_
             rg_lds_c2(pa + 32u + 32u * e, De[0], De[1]);
             rg_lds_c2(pa + 48u + 32u * e, De[2], De[3]);
           }
-          rg_grad_cell(s_grad, d.dslot + e, rg_grad_term(W, De, d.count), rounds);
+          rg_grad_cell<DIRECT>(grad, d.dslot + e, rg_grad_term(W, De, d.count));
         }
       }
     }
@@ -662,9 +676,9 @@ __device__ __forceinline__ void rg_tile_io(cf* sm, cf* hbm, const uint32_t* tab,
   if (!STORE) cp_async_commit();
 }
 
-template <bool BWD>
+template <bool BWD, bool DIRECT>
 __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& ring, const StreamRef& st, const cf* pay_b,
-                                          float* s_grad, int rounds, int m) {
+                                          const RgGrad& grad, int m) {
   ring_start<float>(ring, st, pay_b);
   for (int c = 0; c < st.n_chunks; ++c) {
     cp_async_wait_all();
@@ -677,7 +691,7 @@ __device__ __forceinline__ void rg_stream(cf* sp, cf* sl, const Ring<float>& rin
     for (uint32_t o = 0; o < ci.op_count;) {
       const uint32_t hdr = dd + 32u * o;
       if (BWD)
-        rg_run_bwd(sp, sl, hdr, pa, pp, ci.pay_begin, s_grad, rounds, m);
+        rg_run_bwd<DIRECT>(sp, sl, hdr, pa, pp, ci.pay_begin, grad, m);
       else
         rg_run_fwd(sp, hdr, pa, pp, ci.pay_begin, m);
       o += 1u + ((rg_lds_u4(hdr).x >> 16) & 255u);
@@ -712,7 +726,8 @@ __global__ void __launch_bounds__(256, 3) k_rg_fwd(const __grid_constant__ FwdAr
   } else {
     rg_tile_io<false>(sm, psi_b, io_tab, tbase, tile_n);
   }
-  rg_stream<false>(sm, nullptr, ring, a.st, a.stream + b * a.stride, nullptr, 0, m);  // begins and ends with a barrier
+  const RgGrad no_grad = {nullptr, nullptr, nullptr, 0};
+  rg_stream<false, false>(sm, nullptr, ring, a.st, a.stream + b * a.stride, no_grad, m);  // begins and ends with a barrier
   cp_async_wait_all();  // (a sweep without ops: the tile copies still have to land)
   __syncthreads();
 
@@ -727,6 +742,7 @@ __global__ void __launch_bounds__(256, 3) k_rg_fwd(const __grid_constant__ FwdAr
   }
 }
 
+template <bool DIRECT>
 __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdArgs<float> a) {
   __shared__ uint32_t io_tab[RG_IO_TAB];
   const int m = a.geom.m;
@@ -743,7 +759,9 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
   cf* lam_b = a.lam ? a.lam + (size_t)b * sv : nullptr;
 
   const int rounds = a.grad_rounds;
-  const uint32_t ncell = blockDim.x >> rounds;
+  const uint32_t ncell = DIRECT ? 0u : blockDim.x >> (DIRECT ? 0 : rounds);
+  float* grad_b = a.grad + b * a.n_params;
+  const RgGrad grad = {s_grad, grad_b, a.slot_pidx, rounds};
   for (uint32_t s = threadIdx.x; s < (uint32_t)a.n_dslots * ncell; s += blockDim.x) s_grad[s] = 0;
 
   if (a.flags & SW_FULL) {
@@ -761,7 +779,7 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
     rg_tile_io<false>(sp, psi_b, io_tab, tbase, tile_n);
     rg_tile_io<false>(sl, lam_b, io_tab, tbase, tile_n);
   }
-  rg_stream<true>(sp, sl, ring, a.st_b, a.stream_b + b * a.stride_b, s_grad, rounds, m);  // begins and ends with a barrier
+  rg_stream<true, DIRECT>(sp, sl, ring, a.st_b, a.stream_b + b * a.stride_b, grad, m);  // begins and ends with a barrier
   cp_async_wait_all();
   __syncthreads();
 
@@ -769,17 +787,18 @@ __global__ void __launch_bounds__(256, 2) k_rg_bwd(const __grid_constant__ BwdAr
     rg_tile_io<true>(sp, psi_b, io_tab, tbase, tile_n);
     rg_tile_io<true>(sl, lam_b, io_tab, tbase, tile_n);
   }
-  // one warp per slot adds its cells up
-  float* grad_b = a.grad + b * a.n_params;
-  for (int s = threadIdx.x >> 5; s < a.n_dslots; s += blockDim.x >> 5) {
-    float v = 0.f;
-    for (uint32_t c = threadIdx.x & 31u; c < ncell; c += 32u) v += s_grad[(uint32_t)s * ncell + c];
-    v = warp_sum(v);
-    if ((threadIdx.x & 31u) == 0) {
-      if (a.flags & SW_FULL)
-        grad_b[a.slot_pidx[s]] = v;
-      else
-        atomicAdd(&grad_b[a.slot_pidx[s]], v);
+  // one warp per slot adds its cells up (tq_backward zeroed the gradient, so the whole-state mode may add as well)
+  if constexpr (!DIRECT) {
+    for (int s = threadIdx.x >> 5; s < a.n_dslots; s += blockDim.x >> 5) {
+      float v = 0.f;
+      for (uint32_t c = threadIdx.x & 31u; c < ncell; c += 32u) v += s_grad[(uint32_t)s * ncell + c];
+      v = warp_sum(v);
+      if ((threadIdx.x & 31u) == 0) {
+        if (a.flags & SW_FULL)
+          grad_b[a.slot_pidx[s]] = v;
+        else
+          atomicAdd(&grad_b[a.slot_pidx[s]], v);
+      }
     }
   }
 }

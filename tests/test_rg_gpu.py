@@ -105,3 +105,38 @@ def test_automatic_choice_and_forced_default_sweeps(case):
     cc = build(case, "c64", case["flat"][0]).compilecircuit(backend="pytorch_b200", dtype=torch.complex64,
                                                              plan_opts={"structure": -1})
     assert cc.plan().num_register_groups(False) == 0 and cc.plan().num_register_groups(True) == 0
+
+
+def test_gradients_without_shared_memory_cells_match(tmp_path):
+    """A sweep with thousands of trainable slots has no room for the gradient cells: the adjoint kernel then adds every
+    warp's sums to the gradient in global memory.  TQ_RG_GRAD_DIRECT forces that path (read once per process, hence the
+    subprocess); same gradients as the default sweeps, whole-state and tiled."""
+    import os
+    import subprocess
+    import sys
+
+    code = """
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import tedq_b200 as qb
+from tedq_b200 import workloads as W
+for n, opts in ((12, {}), (16, {})):
+    spec = W.hea(n, 3)
+    circ = W.build_circuit(spec, qb)
+    flat = torch.tensor(np.random.RandomState(1).uniform(-3, 3, (2, spec["n_params"])), dtype=torch.float32)
+    grads = []
+    for structure in (-1, 2):
+        cc = circ.compilecircuit(backend="pytorch_b200", plan_opts=dict(opts, structure=structure))
+        x = flat.cuda().requires_grad_(True)
+        y = cc.batched(x)
+        (y * torch.arange(1, y.shape[1] + 1, device="cuda")).sum().backward()
+        grads.append(x.grad.cpu().numpy())
+        if structure == 2:
+            assert cc.plan().num_register_groups(True) > 0
+    err = float(np.abs(grads[0] - grads[1]).max())
+    assert err < 2e-5, (n, err)
+print("direct ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TQ_RG_GRAD_DIRECT="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "direct ok" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
