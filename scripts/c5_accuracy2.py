@@ -10,7 +10,7 @@ from tedq_b200 import capi, workloads as W
 spec = W.lattice_rcs(5, 8, 12, seed=0)
 hyper = bench.c5_hyper(False, False)
 if len(sys.argv) > 1:
-    hyper["seed"] = int(sys.argv[1]); hyper["plan_cache"] = "scratch_plans"
+    hyper["seed"] = int(sys.argv[1]); hyper["restarts"] = 1; hyper["plan_cache"] = sys.argv[2] if len(sys.argv) > 2 else bench.PLAN_CACHE
 circ64 = W.build_circuit(spec, qb, tensor_fn=lambda v: torch.tensor(float(v), dtype=torch.float64))
 cc = circ64.compilecircuit(backend="pytorch_b200", tn_mode=True, tn_simplify=False, hyper_opt=hyper, dtype=torch.complex128)
 allbits = bench.c5_bitstrings(4)
