@@ -16,7 +16,9 @@ from __future__ import annotations
 
 import heapq
 import math
+import os
 import random
+import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
 
@@ -628,29 +630,88 @@ def slice_path(inputs, output, info: PathInfo, target_size_log2: Optional[int] =
     return PathInfo(path, sliced, width, fl, len(path))
 
 
+def _search_once(args):
+    """One search (find_path + slice_path) for one seed -> (score, PathInfo fields); module-level so that worker
+    processes can run it."""
+    (inputs, output, max_repeats, seed, minimize, reconf_sweeps, reconf_leaves, time_model, target_size,
+     target_num_slices) = args
+    t0 = time.time()
+    info = find_path(inputs, output, repeats=int(max_repeats), seed=int(seed), minimize=minimize,
+                     reconf_sweeps=int(reconf_sweeps), reconf_leaves=int(reconf_leaves), time_model=time_model)
+    tnum = int(target_num_slices or 1)
+    if target_size or tnum > 1:
+        info = slice_path(inputs, output, info, target_size_log2=int(math.log2(target_size)) if target_size else None,
+                          target_num_slices=tnum, reconf_sweeps=min(3, int(reconf_sweeps)),
+                          reconf_leaves=int(reconf_leaves), time_model=time_model)
+    if time_model is not None:
+        score = path_time(inputs, output, info.path, info.sliced, time_model) * info.n_slices
+    else:
+        score = info.flops_log2 + len(info.sliced)
+    return score, [list(p) for p in info.path], list(info.sliced), info.width, info.flops_log2, time.time() - t0
+
+
+def _search_in_subprocesses(jobs, workers: int):
+    """Each job in its own interpreter (``python -c "... planner._worker_main()"``, job and result as JSON on stdin /
+    stdout), ``workers`` at a time.  Plain subprocesses rather than multiprocessing: nothing of the caller's main module
+    is imported or re-run in the children, and they never see a GPU."""
+    import json
+    import subprocess
+    import sys
+    from concurrent.futures import ThreadPoolExecutor
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    code = "from tedq_b200 import planner; planner._worker_main()"
+
+    def run(job):
+        res = subprocess.run([sys.executable, "-c", code], input=json.dumps(job), capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError(res.stderr[-2000:])
+        return tuple(json.loads(res.stdout.strip().splitlines()[-1]))
+
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(run, jobs))
+
+
+def _worker_main():
+    import json
+    import sys
+
+    job = json.loads(sys.stdin.read())
+    job[7] = None if job[7] is None else tuple(job[7])       # time_model
+    print(json.dumps(list(_search_once(tuple(job)))))
+
+
 def search_plan(inputs, output, max_repeats: int = 16, seed: int = 0, minimize: str = "flops", reconf_sweeps: int = 0,
                 reconf_leaves: int = 8, time_model=None, target_size=None, target_num_slices: int = 1,
-                restarts: int = 1) -> PathInfo:
+                restarts: int = 1, workers: Optional[int] = None) -> PathInfo:
     """The whole search the executors and the bench share: ``find_path`` + ``slice_path``, ``restarts`` times with
     seeds seed, seed + 1, ...; the plan with the smallest estimated run time (``path_time`` x slices under
-    ``time_model``; flops without a model) is kept.  The restarts are independent searches: what ranks them is the
-    calibrated step-time model, which is the point of having one ("Planner")."""
-    best = None
-    for r in range(max(1, int(restarts))):
-        info = find_path(inputs, output, repeats=int(max_repeats), seed=int(seed) + r, minimize=minimize,
-                         reconf_sweeps=int(reconf_sweeps), reconf_leaves=int(reconf_leaves), time_model=time_model)
-        tnum = int(target_num_slices or 1)
-        if target_size or tnum > 1:
-            info = slice_path(inputs, output, info, target_size_log2=int(math.log2(target_size)) if target_size else None,
-                              target_num_slices=tnum, reconf_sweeps=min(3, int(reconf_sweeps)),
-                              reconf_leaves=int(reconf_leaves), time_model=time_model)
-        if time_model is not None:
-            score = path_time(inputs, output, info.path, info.sliced, time_model) * info.n_slices
-        else:
-            score = info.flops_log2 + len(info.sliced)
-        if best is None or score < best[0]:
-            best = (score, info)
-    return best[1]
+    ``time_model``; flops without a model) is kept, ties to the lower seed.  The restarts are independent searches:
+    what ranks them is the calibrated step-time model, which is the point of having one ("Planner").
+    They run in ``workers`` child interpreters (default: one per core, at most one per restart; 0 / 1 = in this
+    process) — the result does not depend on it."""
+    restarts = max(1, int(restarts))
+    inputs = [[int(i) for i in t] for t in inputs]
+    output = [int(i) for i in output]
+    jobs = [(inputs, output, max_repeats, int(seed) + r, minimize, reconf_sweeps, reconf_leaves,
+             None if time_model is None else tuple(time_model), target_size, target_num_slices) for r in range(restarts)]
+    if workers is None:
+        workers = min(restarts, os.cpu_count() or 1)
+    results = None
+    if restarts > 1 and workers > 1:
+        try:
+            results = _search_in_subprocesses(jobs, workers)
+        except Exception:            # no child processes in this environment: search in-process
+            results = None
+    if results is None:
+        results = [_search_once(j) for j in jobs]
+    best = min(range(restarts), key=lambda r: (results[r][0], r))
+    _, path, sliced, width, fl, _ = results[best]
+    info = PathInfo([tuple(p) for p in path], sliced, width, fl, len(path))
+    return info
 
 
 PLANNER_VERSION = 2   # bump when the search changes: stored plans of another version are searched again
