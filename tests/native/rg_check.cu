@@ -448,6 +448,52 @@ int main() {
            empty_groups, d1 / (double)groups);
     CHECK(d1 / (double)groups >= 2.5, "groups too small");
   }
+  // 5. grouping of random block lists (1-3 bits per block, X / CNOT-like blocks mixed in): the same invariants
+  for (int trial = 0; trial < 300; ++trial) {
+    const int m = RG_MIN_TILE + rand() % 6;
+    const int nblk = 20 + rand() % 200;
+    std::vector<RgItem> items(nblk);
+    for (RgItem& it : items) {
+      it.nbits = 1 + rand() % 3;
+      for (int k = 0; k < it.nbits;) {
+        const int b = rand() % m;
+        bool dup = false;
+        for (int j = 0; j < k; ++j) dup = dup || it.bits[j] == b;
+        if (!dup) it.bits[k++] = b;
+      }
+      it.foldable = it.nbits <= 2 && rand() % 3 == 0;
+      it.pay = 4 + 4 * (rand() % 4);
+    }
+    std::vector<int> rest(nblk), stamp(nblk, -1);
+    for (int i = 0; i < nblk; ++i) rest[i] = i;
+    int clock = 0;
+    while (!rest.empty()) {
+      std::vector<int> pre, mid, post;
+      std::vector<char> inb;
+      const size_t before = rest.size();
+      rg_next_group(items, rest, m, 64, pre, mid, post, inb);
+      if (pre.size() + mid.size() + post.size() + rest.size() != before || pre.size() + mid.size() + post.size() == 0) {
+        CHECK(false, "random grouping trial %d lost a block or made no progress", trial);
+        break;
+      }
+      int nb = 0, pay = 0;
+      for (int b = 0; b < m; ++b) nb += inb[b];
+      CHECK(nb <= 4 && (int)mid.size() <= RG_MAX_SUB, "random grouping: group spans %d bits, %zu sub-ops", nb, mid.size());
+      for (int bi : mid) pay += items[bi].pay;
+      CHECK(pay <= 64, "random grouping: payload %d over the cap", pay);
+      for (int bi : pre) CHECK(items[bi].foldable, "non-foldable block in the pre phase");
+      for (int bi : post) CHECK(items[bi].foldable, "non-foldable block in the post phase");
+      for (const std::vector<int>* part : {&pre, &mid, &post})
+        for (int bi : *part) stamp[bi] = clock++;
+    }
+    for (int i = 0; i < nblk; ++i)
+      for (int j = i + 1; j < nblk; ++j) {
+        bool share = false;
+        for (int a = 0; a < items[i].nbits; ++a)
+          for (int b = 0; b < items[j].nbits; ++b) share = share || items[i].bits[a] == items[j].bits[b];
+        if (share) CHECK(stamp[i] >= 0 && stamp[i] < stamp[j], "random grouping trial %d: blocks %d and %d share a bit and were reordered", trial, i, j);
+      }
+  }
   if (fails) {
     printf("rg_check: %d failures\n", fails);
     return 1;
