@@ -100,7 +100,7 @@ typedef struct tq_plan_opts {
   int32_t coalesce_bits;        /* -1 = default. low amplitude-index bits always kept tile-local     */
   int32_t threads;              /* 0 = default CTA size                                              */
   int32_t fuse;                 /* -1 = default (1). 1: fuse runs of gates in registers               */
-  int32_t structure;            /* 0 = default: automatic.  complex64 circuits of >= 9 qubits whose gates are all
+  int32_t structure;            /* 0 = default: automatic.  complex64 circuits of >= 12 qubits whose gates are all
                                    (controlled) one-target blocks or diagonals take the register-group sweeps (2) when
                                    those need no more multiply-adds than the default fusion (layers of one-qubit gates
                                    between sparse entanglers); everything else takes the default sweeps, where every

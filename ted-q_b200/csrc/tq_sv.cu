@@ -797,6 +797,18 @@ int tq_plan_create(const tq_gate_desc* gates, int32_t n_gates, const tq_meas_des
     fuse_gates(false, a0);
     fuse_gates(true, a1);
     rg = fused_macs(a1, true) <= 1.1 * fused_macs(a0, false);
+    // measured on B200 (scripts/rg_small.py, HEA depth 10): the groups win from 12 qubits on (+32 % at 12, +24 % at 14,
+    // +26 % at 16, +34 % at 20) and lose at 10 (64 threads per CTA: the whole-state kernels run out of warps)
+    if (n < 12) rg = false;
+  }
+  if (rg && p->bwd_full && n > 12 && !(opts && opts->max_local_qubits_bwd > 0)) {
+    // 13 qubits: a whole-state adjoint tile pair is 128 KiB = one CTA of 8 warps per SM; two tiled sweeps of 2^12 keep
+    // two CTAs resident
+    p->bwd_full = false;
+    m_b = 12;
+    p->m_b = m_b;
+    coalesce = std::min(coalesce, m_b - TQ_MAX_GATE_QUBITS);
+    p->coalesce = coalesce;
   }
   p->rg = rg;
   if (rg) {
